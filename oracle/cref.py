@@ -1,0 +1,179 @@
+"""ctypes front-end for oracle/halo2_oracle.c (TEST INFRASTRUCTURE ONLY -- see pasta.py).
+
+Everything is canonical little-endian bytes held in numpy uint8 arrays:
+scalars (n, 32), affine points (n, 64) with identity = 64 zero bytes.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libhalo2_oracle.so")
+_lib: Optional[ctypes.CDLL] = None
+
+FIELD_ID = {"fp": 0, "fq": 1}
+CURVE_ID = {"pallas": 0, "vesta": 1}
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "halo2_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+        for name in ("orc_best_multiexp", "orc_naive_msm", "orc_best_fft", "orc_ifft", "orc_coeff_to_extended",
+                     "orc_extended_to_coeff", "orc_field_op", "orc_scalar_mul", "orc_point_add",
+                     "orc_jac_to_affine", "orc_on_curve", "orc_gen_scalars", "orc_gen_points"):
+            getattr(_lib, name).restype = ctypes.c_int
+    return _lib
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _fe(x) -> np.ndarray:
+    if isinstance(x, (int,)):
+        return np.frombuffer(int(x).to_bytes(32, "little"), dtype=np.uint8).copy()
+    a = np.ascontiguousarray(x, dtype=np.uint8)
+    assert a.size == 32
+    return a
+
+
+def default_threads() -> int:
+    return os.cpu_count() or 1
+
+
+def best_multiexp(curve: str, scalars: np.ndarray, bases: np.ndarray, threads: Optional[int] = None) -> np.ndarray:
+    n = scalars.shape[0]
+    if bases.shape[0] != n:  # arithmetic.rs:144 assert_eq!
+        raise AssertionError("best_multiexp: coeffs.len() != bases.len()")
+    out = np.zeros(64, dtype=np.uint8)
+    lib().orc_best_multiexp(CURVE_ID[curve], _p(np.ascontiguousarray(scalars)), _p(np.ascontiguousarray(bases)),
+                            ctypes.c_size_t(n), threads or default_threads(), _p(out))
+    return out
+
+
+def naive_msm(curve: str, scalars: np.ndarray, bases: np.ndarray) -> np.ndarray:
+    out = np.zeros(64, dtype=np.uint8)
+    lib().orc_naive_msm(CURVE_ID[curve], _p(np.ascontiguousarray(scalars)), _p(np.ascontiguousarray(bases)),
+                        ctypes.c_size_t(scalars.shape[0]), _p(out))
+    return out
+
+
+def best_fft(field: str, a: np.ndarray, omega, log_n: int, threads: Optional[int] = None) -> np.ndarray:
+    if a.shape[0] != 1 << log_n:  # arithmetic.rs:205
+        raise AssertionError("best_fft: a.len() != 1 << log_n")
+    a = np.ascontiguousarray(a).copy()
+    lib().orc_best_fft(FIELD_ID[field], _p(a), _p(_fe(omega)), ctypes.c_uint32(log_n), threads or default_threads())
+    return a
+
+
+def ifft(field: str, a: np.ndarray, omega_inv, log_n: int, divisor, threads: Optional[int] = None) -> np.ndarray:
+    assert a.shape[0] == 1 << log_n
+    a = np.ascontiguousarray(a).copy()
+    lib().orc_ifft(FIELD_ID[field], _p(a), _p(_fe(omega_inv)), ctypes.c_uint32(log_n), _p(_fe(divisor)),
+                   threads or default_threads())
+    return a
+
+
+def coeff_to_extended(field: str, a: np.ndarray, k: int, ext_k: int, zeta, ext_omega,
+                      threads: Optional[int] = None) -> np.ndarray:
+    assert a.shape[0] == 1 << k
+    out = np.zeros((1 << ext_k, 32), dtype=np.uint8)
+    lib().orc_coeff_to_extended(FIELD_ID[field], _p(np.ascontiguousarray(a)), ctypes.c_uint32(k),
+                                ctypes.c_uint32(ext_k), _p(_fe(zeta)), _p(_fe(ext_omega)), _p(out),
+                                threads or default_threads())
+    return out
+
+
+def extended_to_coeff(field: str, a: np.ndarray, ext_k: int, ext_omega_inv, ext_divisor, zeta, out_len: int,
+                      threads: Optional[int] = None) -> np.ndarray:
+    assert a.shape[0] == 1 << ext_k
+    out = np.zeros((out_len, 32), dtype=np.uint8)
+    lib().orc_extended_to_coeff(FIELD_ID[field], _p(np.ascontiguousarray(a)), ctypes.c_uint32(ext_k),
+                                _p(_fe(ext_omega_inv)), _p(_fe(ext_divisor)), _p(_fe(zeta)),
+                                ctypes.c_size_t(out_len), _p(out), threads or default_threads())
+    return out
+
+
+def field_op(field: str, op: str, a, b=None) -> int:
+    ops = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "pow5": 4, "neg": 5}
+    out = np.zeros(32, dtype=np.uint8)
+    lib().orc_field_op(FIELD_ID[field], ops[op], _p(_fe(a)), _p(_fe(b)) if b is not None else None, _p(out))
+    return int.from_bytes(out.tobytes(), "little")
+
+
+def scalar_mul(curve: str, scalar, base: np.ndarray) -> np.ndarray:
+    out = np.zeros(64, dtype=np.uint8)
+    lib().orc_scalar_mul(CURVE_ID[curve], _p(_fe(scalar)), _p(np.ascontiguousarray(base)), _p(out))
+    return out
+
+
+def point_add(curve: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    out = np.zeros(64, dtype=np.uint8)
+    lib().orc_point_add(CURVE_ID[curve], _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out))
+    return out
+
+
+def jac_to_affine(curve: str, xyz: np.ndarray) -> np.ndarray:
+    out = np.zeros(64, dtype=np.uint8)
+    lib().orc_jac_to_affine(CURVE_ID[curve], _p(np.ascontiguousarray(xyz, dtype=np.uint8).reshape(-1)), _p(out))
+    return out
+
+
+def on_curve(curve: str, xy: np.ndarray) -> bool:
+    return bool(lib().orc_on_curve(CURVE_ID[curve], _p(np.ascontiguousarray(xy))))
+
+
+def gen_scalars(field: str, seed: int, n: int) -> np.ndarray:
+    out = np.zeros((n, 32), dtype=np.uint8)
+    lib().orc_gen_scalars(FIELD_ID[field], ctypes.c_uint64(seed), ctypes.c_size_t(n), _p(out))
+    return out
+
+
+def gen_points(curve: str, seed: int, n: int) -> np.ndarray:
+    out = np.zeros((n, 64), dtype=np.uint8)
+    lib().orc_gen_points(CURVE_ID[curve], ctypes.c_uint64(seed), ctypes.c_size_t(n), _p(out))
+    return out
+
+
+# conversions between python ints / pasta.py affine tuples and byte arrays ---------------
+def ints_to_bytes(xs) -> np.ndarray:
+    return np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in xs), dtype=np.uint8).reshape(-1, 32).copy()
+
+
+def bytes_to_ints(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+    return [int.from_bytes(row.tobytes(), "little") for row in a]
+
+
+def affines_to_bytes(pts) -> np.ndarray:
+    out = np.zeros((len(pts), 64), dtype=np.uint8)
+    for i, pt in enumerate(pts):
+        if pt is not None:
+            out[i, :32] = np.frombuffer(int(pt[0]).to_bytes(32, "little"), dtype=np.uint8)
+            out[i, 32:] = np.frombuffer(int(pt[1]).to_bytes(32, "little"), dtype=np.uint8)
+    return out
+
+
+def bytes_to_affine(a: np.ndarray):
+    b = np.ascontiguousarray(a, dtype=np.uint8).reshape(64).tobytes()
+    x = int.from_bytes(b[:32], "little")
+    y = int.from_bytes(b[32:], "little")
+    return None if (x == 0 and y == 0) else (x, y)

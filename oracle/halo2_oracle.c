@@ -1,0 +1,607 @@
+/*
+ * CPU oracle, C restatement (TEST INFRASTRUCTURE + the timed "reference algorithm" CPU
+ * baseline).  NOT part of the product: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.
+ *
+ * Restates, for the Pasta fields/curves (file:line relative to
+ * /root/reference/halo2_proofs/src):
+ *   best_multiexp      arithmetic.rs:143-180 with Bucket/Buckets :29-112 -- same window size
+ *                      c (:146-152), 256/c+1 windows (:154), unsigned digits from the canonical
+ *                      LE repr (get_at :95-111), None->Affine->Projective buckets (:37-46),
+ *                      summation by parts (:86-92), one task per window when n > threads
+ *                      (:157-167) else serial Horner (:168-179).
+ *   best_fft           arithmetic.rs:192-255 + recursive_butterfly_arithmetic :258-295:
+ *                      serial bit reversal (:207-212), serial twiddle scan (:215-221),
+ *                      iterative stages when log_n <= log2(threads) else join-recursion.
+ *   parallelize        arithmetic.rs:345-362 (chunk = n/threads; if chunk < threads one chunk).
+ *   ifft / distribute_powers_zeta / coeff_to_extended / extended_to_coeff
+ *                      poly/domain.rs:375-383, :357-373, :241-255, :303-325.
+ *
+ * The limb arithmetic itself lives in the un-vendored crate pasta_curves 0.5.1
+ * (Cargo.lock:1303-1306); it is restated from the definition (4x64 Montgomery, R = 2^256).
+ * The reference is Rust-only and cannot be compiled in this image, so there is no
+ * oracle/_ref; bench.py reports this library as cpu_baseline.kind = "port".
+ *
+ * PARITY PINNING: see oracle/pasta.py header.  best_multiexp/best_fft on synthetic inputs:
+ * "parity unpinned" (no reference vector exists); this file and pasta.py are two independent
+ * restatements that must agree (tests/test_oracle_*.py), and the field layer is pinned by the
+ * halo2_poseidon known-answer vectors.
+ *
+ * ABI: every element is canonical 32-byte little-endian; affine point = x||y (64 B),
+ * identity = 64 zero bytes.  field: 0 = Fp, 1 = Fq.  curve: 0 = Pallas (coords Fp, scalars
+ * Fq), 1 = Vesta (coords Fq, scalars Fp).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fe;           /* Montgomery form */
+typedef struct { fe x, y; int inf; } aff;       /* affine, inf=1 identity */
+typedef struct { fe x, y, z; } jac;             /* Jacobian, z==0 identity */
+
+typedef struct {
+    uint64_t m[4];   /* modulus */
+    uint64_t inv;    /* -m^-1 mod 2^64 */
+    fe r;            /* R mod m (Montgomery one) */
+    fe r2;           /* R^2 mod m */
+} field_t;
+
+static field_t FLD[2];
+static int g_init = 0;
+
+static const uint64_t MOD_P[4] = {0x992d30ed00000001ULL, 0x224698fc094cf91bULL, 0x0ULL, 0x4000000000000000ULL};
+static const uint64_t MOD_Q[4] = {0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0x0ULL, 0x4000000000000000ULL};
+
+/* ---------------------------------------------------------------- limb helpers */
+static inline int ge4(const uint64_t *a, const uint64_t *b) {
+    for (int i = 3; i >= 0; i--) { if (a[i] > b[i]) return 1; if (a[i] < b[i]) return 0; }
+    return 1;
+}
+static inline uint64_t sub4(uint64_t *r, const uint64_t *a, const uint64_t *b) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a[i] - b[i] - borrow;
+        r[i] = (uint64_t)d; borrow = (uint64_t)(d >> 64) & 1;
+    }
+    return borrow;
+}
+static inline uint64_t add4(uint64_t *r, const uint64_t *a, const uint64_t *b) {
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 s = (u128)a[i] + b[i] + carry;
+        r[i] = (uint64_t)s; carry = (uint64_t)(s >> 64);
+    }
+    return carry;
+}
+
+static inline void fe_add(const field_t *F, fe *r, const fe *a, const fe *b) {
+    uint64_t t[4]; add4(t, a->l, b->l);            /* < 2m < 2^256: no carry */
+    if (ge4(t, F->m)) sub4(t, t, F->m);
+    memcpy(r->l, t, 32);
+}
+static inline void fe_sub(const field_t *F, fe *r, const fe *a, const fe *b) {
+    uint64_t t[4];
+    if (sub4(t, a->l, b->l)) add4(t, t, F->m);
+    memcpy(r->l, t, 32);
+}
+static inline void fe_neg(const field_t *F, fe *r, const fe *a) {
+    fe z = {{0, 0, 0, 0}}; fe_sub(F, r, &z, a);
+}
+static inline int fe_is_zero(const fe *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static inline int fe_eq(const fe *a, const fe *b) { return memcmp(a->l, b->l, 32) == 0; }
+
+/* CIOS Montgomery multiplication, 4 x 64-bit limbs */
+static inline void fe_mul(const field_t *F, fe *r, const fe *a, const fe *b) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 4; j++) {
+            u128 s = (u128)a->l[j] * b->l[i] + t[j] + c;
+            t[j] = (uint64_t)s; c = (uint64_t)(s >> 64);
+        }
+        u128 s = (u128)t[4] + c; t[4] = (uint64_t)s; t[5] = (uint64_t)(s >> 64);
+        uint64_t q = t[0] * F->inv;
+        s = (u128)q * F->m[0] + t[0]; c = (uint64_t)(s >> 64);
+        for (int j = 1; j < 4; j++) {
+            s = (u128)q * F->m[j] + t[j] + c;
+            t[j - 1] = (uint64_t)s; c = (uint64_t)(s >> 64);
+        }
+        s = (u128)t[4] + c; t[3] = (uint64_t)s; t[4] = t[5] + (uint64_t)(s >> 64);
+    }
+    if (t[4] || ge4(t, F->m)) sub4(t, t, F->m);
+    memcpy(r->l, t, 32);
+}
+static inline void fe_sqr(const field_t *F, fe *r, const fe *a) { fe_mul(F, r, a, a); }
+
+static void fe_from_bytes(const field_t *F, fe *r, const uint8_t *b) {
+    fe t; memcpy(t.l, b, 32);                      /* little-endian host assumed */
+    fe_mul(F, r, &t, &F->r2);
+}
+static void fe_to_bytes(const field_t *F, uint8_t *b, const fe *a) {
+    fe one = {{1, 0, 0, 0}}, t; fe_mul(F, &t, a, &one);
+    memcpy(b, t.l, 32);
+}
+static void fe_pow(const field_t *F, fe *r, const fe *a, const uint64_t e[4]) {
+    fe acc = F->r, base = *a;
+    for (int i = 0; i < 256; i++) {
+        if ((e[i >> 6] >> (i & 63)) & 1) fe_mul(F, &acc, &acc, &base);
+        fe_sqr(F, &base, &base);
+    }
+    *r = acc;
+}
+static void fe_inv(const field_t *F, fe *r, const fe *a) {
+    uint64_t e[4] = {F->m[0] - 2, F->m[1], F->m[2], F->m[3]};
+    fe_pow(F, r, a, e);
+}
+
+static void field_setup(field_t *F, const uint64_t m[4]) {
+    memcpy(F->m, m, 32);
+    uint64_t x = 1;                                /* Newton: x = m^-1 mod 2^64 */
+    for (int i = 0; i < 6; i++) x *= 2 - m[0] * x;
+    F->inv = (uint64_t)0 - x;
+    /* R mod m by 256 modular doublings of 1, R^2 by 512 */
+    uint64_t t[4] = {1, 0, 0, 0};
+    for (int i = 0; i < 512; i++) {
+        uint64_t c = add4(t, t, t);
+        if (c || ge4(t, m)) sub4(t, t, m);
+        if (i == 255) memcpy(F->r.l, t, 32);
+    }
+    memcpy(F->r2.l, t, 32);
+}
+static void ensure_init(void) {
+    if (g_init) return;
+    field_setup(&FLD[0], MOD_P);
+    field_setup(&FLD[1], MOD_Q);
+    g_init = 1;
+}
+static inline const field_t *base_field(int curve) { return &FLD[curve]; }       /* pallas->fp */
+static inline const field_t *scalar_field(int curve) { return &FLD[1 - curve]; } /* pallas->fq */
+
+/* ---------------------------------------------------------------- curve: y^2 = x^3 + 5 */
+static inline void jac_identity(const field_t *F, jac *r) {
+    memset(r, 0, sizeof *r); r->y = F->r;
+}
+static inline int jac_is_id(const jac *a) { return fe_is_zero(&a->z); }
+
+static void jac_double(const field_t *F, jac *r, const jac *p) {
+    if (jac_is_id(p)) { *r = *p; return; }
+    fe A, B, C, D, E, Ff, t, X3, Y3, Z3;
+    fe_sqr(F, &A, &p->x); fe_sqr(F, &B, &p->y); fe_sqr(F, &C, &B);
+    fe_add(F, &t, &p->x, &B); fe_sqr(F, &t, &t); fe_sub(F, &t, &t, &A); fe_sub(F, &t, &t, &C);
+    fe_add(F, &D, &t, &t);
+    fe_add(F, &E, &A, &A); fe_add(F, &E, &E, &A);
+    fe_sqr(F, &Ff, &E);
+    fe_sub(F, &X3, &Ff, &D); fe_sub(F, &X3, &X3, &D);
+    fe_sub(F, &t, &D, &X3); fe_mul(F, &Y3, &E, &t);
+    fe_add(F, &C, &C, &C); fe_add(F, &C, &C, &C); fe_add(F, &C, &C, &C);
+    fe_sub(F, &Y3, &Y3, &C);
+    fe_mul(F, &Z3, &p->y, &p->z); fe_add(F, &Z3, &Z3, &Z3);
+    r->x = X3; r->y = Y3; r->z = Z3;
+}
+
+static void jac_add(const field_t *F, jac *r, const jac *a, const jac *b) {
+    if (jac_is_id(a)) { *r = *b; return; }
+    if (jac_is_id(b)) { *r = *a; return; }
+    fe z1z1, z2z2, u1, u2, s1, s2, h, rr, hh, hhh, v, t, X3, Y3, Z3;
+    fe_sqr(F, &z1z1, &a->z); fe_sqr(F, &z2z2, &b->z);
+    fe_mul(F, &u1, &a->x, &z2z2); fe_mul(F, &u2, &b->x, &z1z1);
+    fe_mul(F, &s1, &a->y, &b->z); fe_mul(F, &s1, &s1, &z2z2);
+    fe_mul(F, &s2, &b->y, &a->z); fe_mul(F, &s2, &s2, &z1z1);
+    if (fe_eq(&u1, &u2)) {
+        if (fe_eq(&s1, &s2)) { jac_double(F, r, a); return; }
+        jac_identity(F, r); return;
+    }
+    fe_sub(F, &h, &u2, &u1); fe_sub(F, &rr, &s2, &s1);
+    fe_sqr(F, &hh, &h); fe_mul(F, &hhh, &h, &hh); fe_mul(F, &v, &u1, &hh);
+    fe_sqr(F, &X3, &rr); fe_sub(F, &X3, &X3, &hhh); fe_sub(F, &X3, &X3, &v); fe_sub(F, &X3, &X3, &v);
+    fe_sub(F, &t, &v, &X3); fe_mul(F, &Y3, &rr, &t); fe_mul(F, &t, &s1, &hhh); fe_sub(F, &Y3, &Y3, &t);
+    fe_mul(F, &Z3, &a->z, &b->z); fe_mul(F, &Z3, &Z3, &h);
+    r->x = X3; r->y = Y3; r->z = Z3;
+}
+
+static void jac_add_mixed(const field_t *F, jac *r, const jac *a, const aff *b) {
+    if (b->inf) { *r = *a; return; }
+    if (jac_is_id(a)) { r->x = b->x; r->y = b->y; r->z = F->r; return; }
+    fe z1z1, u2, s2, h, rr, hh, hhh, v, t, X3, Y3, Z3;
+    fe_sqr(F, &z1z1, &a->z);
+    fe_mul(F, &u2, &b->x, &z1z1);
+    fe_mul(F, &s2, &b->y, &a->z); fe_mul(F, &s2, &s2, &z1z1);
+    if (fe_eq(&a->x, &u2)) {
+        if (fe_eq(&a->y, &s2)) { jac_double(F, r, a); return; }
+        jac_identity(F, r); return;
+    }
+    fe_sub(F, &h, &u2, &a->x); fe_sub(F, &rr, &s2, &a->y);
+    fe_sqr(F, &hh, &h); fe_mul(F, &hhh, &h, &hh); fe_mul(F, &v, &a->x, &hh);
+    fe_sqr(F, &X3, &rr); fe_sub(F, &X3, &X3, &hhh); fe_sub(F, &X3, &X3, &v); fe_sub(F, &X3, &X3, &v);
+    fe_sub(F, &t, &v, &X3); fe_mul(F, &Y3, &rr, &t); fe_mul(F, &t, &a->y, &hhh); fe_sub(F, &Y3, &Y3, &t);
+    fe_mul(F, &Z3, &a->z, &h);
+    r->x = X3; r->y = Y3; r->z = Z3;
+}
+
+static void jac_to_aff(const field_t *F, aff *r, const jac *a) {
+    if (jac_is_id(a)) { memset(r, 0, sizeof *r); r->inf = 1; return; }
+    fe zi, zi2;
+    fe_inv(F, &zi, &a->z); fe_sqr(F, &zi2, &zi);
+    fe_mul(F, &r->x, &a->x, &zi2); fe_mul(F, &zi2, &zi2, &zi); fe_mul(F, &r->y, &a->y, &zi2);
+    r->inf = 0;
+}
+static void aff_from_bytes(const field_t *F, aff *r, const uint8_t *b) {
+    int allz = 1;
+    for (int i = 0; i < 64; i++) if (b[i]) { allz = 0; break; }
+    if (allz) { memset(r, 0, sizeof *r); r->inf = 1; return; }
+    fe_from_bytes(F, &r->x, b); fe_from_bytes(F, &r->y, b + 32); r->inf = 0;
+}
+static void aff_to_bytes(const field_t *F, uint8_t *b, const aff *a) {
+    if (a->inf) { memset(b, 0, 64); return; }
+    fe_to_bytes(F, b, &a->x); fe_to_bytes(F, b + 32, &a->y);
+}
+static void scalar_mul_bytes(const field_t *F, jac *r, const uint8_t k[32], const aff *base) {
+    jac acc; jac_identity(F, &acc);
+    for (int i = 255; i >= 0; i--) {
+        jac_double(F, &acc, &acc);
+        if ((k[i >> 3] >> (i & 7)) & 1) jac_add_mixed(F, &acc, &acc, base);
+    }
+    *r = acc;
+}
+
+/* ---------------------------------------------------------------- best_multiexp */
+/* Bucket enum, arithmetic.rs:29-58 */
+typedef struct { int tag; aff a; jac p; } bucket_t;   /* 0 None, 1 Affine, 2 Projective */
+
+static inline void bucket_add_assign(const field_t *F, bucket_t *b, const aff *other) {
+    if (b->tag == 0) { b->a = *other; b->tag = 1; }
+    else if (b->tag == 1) {                      /* a + *other -> projective (arithmetic.rs:41) */
+        jac t;
+        if (b->a.inf) jac_identity(F, &t); else { t.x = b->a.x; t.y = b->a.y; t.z = F->r; }
+        jac_add_mixed(F, &b->p, &t, other); b->tag = 2;
+    } else jac_add_mixed(F, &b->p, &b->p, other);
+}
+static inline void bucket_add(const field_t *F, const bucket_t *b, jac *other) {
+    if (b->tag == 1) jac_add_mixed(F, other, other, &b->a);
+    else if (b->tag == 2) jac_add(F, other, other, &b->p);
+}
+/* get_at, arithmetic.rs:95-111 */
+static inline size_t get_at(size_t segment, size_t c, const uint8_t *bytes) {
+    size_t skip_bits = segment * c, skip_bytes = skip_bits / 8;
+    if (skip_bytes >= 32) return 0;
+    uint8_t v[8] = {0};
+    for (size_t i = 0; i < 8 && skip_bytes + i < 32; i++) v[i] = bytes[skip_bytes + i];
+    uint64_t tmp; memcpy(&tmp, v, 8);
+    tmp >>= skip_bits - skip_bytes * 8;
+    return (size_t)(tmp % ((uint64_t)1 << c));
+}
+/* Buckets::sum, arithmetic.rs:74-93 */
+static void buckets_sum(const field_t *F, size_t c, const uint8_t *reprs, const aff *bases, size_t n,
+                        size_t win, bucket_t *buckets, jac *out) {
+    size_t nb = ((size_t)1 << c) - 1;
+    for (size_t i = 0; i < nb; i++) buckets[i].tag = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t seg = get_at(win, c, reprs + 32 * i);
+        if (seg) bucket_add_assign(F, &buckets[seg - 1], &bases[i]);
+    }
+    jac acc, sum; jac_identity(F, &acc); jac_identity(F, &sum);
+    for (size_t i = nb; i-- > 0;) {
+        bucket_add(F, &buckets[i], &sum);
+        jac_add(F, &acc, &acc, &sum);
+    }
+    *out = acc;
+}
+
+typedef struct {
+    const field_t *F; size_t c, n, windows; const uint8_t *reprs; const aff *bases;
+    jac *results; volatile long next; pthread_mutex_t mu;
+} msm_job;
+
+static void *msm_worker(void *arg) {
+    msm_job *J = (msm_job *)arg;
+    bucket_t *buckets = (bucket_t *)malloc(sizeof(bucket_t) * (((size_t)1 << J->c) - 1));
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        long w = J->next; if (w >= 0) J->next = w - 1;    /* .rev(): top window first */
+        pthread_mutex_unlock(&J->mu);
+        if (w < 0) break;
+        jac acc;
+        buckets_sum(J->F, J->c, J->reprs, J->bases, J->n, (size_t)w, buckets, &acc);
+        for (size_t d = 0; d < J->c * (size_t)w; d++) jac_double(J->F, &acc, &acc);   /* :163 */
+        J->results[w] = acc;
+    }
+    free(buckets);
+    return NULL;
+}
+
+static size_t window_bits(size_t n) {               /* arithmetic.rs:146-152 */
+    if (n < 4) return 1;
+    if (n < 32) return 3;
+    return (size_t)ceil(log((double)(uint32_t)n));
+}
+
+/* scalars: n x 32 B canonical; bases: n x 64 B canonical affine; out: 64 B affine.
+ * threads plays the role of rayon's current_num_threads(). */
+int orc_best_multiexp(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, int threads,
+                      uint8_t *out_xy) {
+    ensure_init();
+    if (threads < 1) threads = 1;
+    const field_t *F = base_field(curve);
+    aff *pts = (aff *)malloc(sizeof(aff) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) aff_from_bytes(F, &pts[i], bases + 64 * i);
+    size_t c = window_bits(n), windows = 256 / c + 1;
+    jac total; jac_identity(F, &total);
+    if (n > (size_t)threads) {
+        msm_job J; J.F = F; J.c = c; J.n = n; J.windows = windows; J.reprs = scalars; J.bases = pts;
+        J.results = (jac *)malloc(sizeof(jac) * windows); J.next = (long)windows - 1;
+        pthread_mutex_init(&J.mu, NULL);
+        int nt = threads < (int)windows ? threads : (int)windows;
+        pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nt);
+        for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, msm_worker, &J);
+        msm_worker(&J);
+        for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+        for (size_t w = 0; w < windows; w++) jac_add(F, &total, &total, &J.results[w]);   /* :166 */
+        free(th); free(J.results); pthread_mutex_destroy(&J.mu);
+    } else {
+        bucket_t *buckets = (bucket_t *)malloc(sizeof(bucket_t) * (((size_t)1 << c) - 1));
+        for (size_t w = windows; w-- > 0;) {          /* :168-179 */
+            for (size_t d = 0; d < c; d++) jac_double(F, &total, &total);
+            jac acc; buckets_sum(F, c, scalars, pts, n, w, buckets, &acc);
+            jac_add(F, &total, &total, &acc);
+        }
+        free(buckets);
+    }
+    aff r; jac_to_aff(F, &r, &total); aff_to_bytes(F, out_xy, &r);
+    free(pts);
+    return 0;
+}
+
+/* naive sum_i k_i * P_i, the other side of test_multiexp (arithmetic.rs:440-458) */
+int orc_naive_msm(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint8_t *out_xy) {
+    ensure_init();
+    const field_t *F = base_field(curve);
+    jac total; jac_identity(F, &total);
+    for (size_t i = 0; i < n; i++) {
+        aff b; aff_from_bytes(F, &b, bases + 64 * i);
+        jac t; scalar_mul_bytes(F, &t, scalars + 32 * i, &b);
+        jac_add(F, &total, &total, &t);
+    }
+    aff r; jac_to_aff(F, &r, &total); aff_to_bytes(F, out_xy, &r);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- best_fft */
+static int log2_floor(unsigned v) { int r = -1; while (v) { v >>= 1; r++; } return r; }  /* :364-374 */
+
+typedef struct { const field_t *F; fe *a; size_t n, tc; const fe *tw; int depth; } fft_task;
+
+static void butterflies(const field_t *F, fe *left, fe *right, size_t half, size_t tc, const fe *tw) {
+    fe t = right[0];
+    right[0] = left[0];
+    fe_add(F, &left[0], &left[0], &t); fe_sub(F, &right[0], &right[0], &t);
+    for (size_t i = 1; i < half; i++) {
+        fe_mul(F, &t, &right[i], &tw[i * tc]);
+        right[i] = left[i];
+        fe_add(F, &left[i], &left[i], &t); fe_sub(F, &right[i], &right[i], &t);
+    }
+}
+static void *fft_rec(void *arg) {                     /* arithmetic.rs:258-295 */
+    fft_task *T = (fft_task *)arg;
+    if (T->n == 2) {
+        fe t = T->a[1]; T->a[1] = T->a[0];
+        fe_add(T->F, &T->a[0], &T->a[0], &t); fe_sub(T->F, &T->a[1], &T->a[1], &t);
+        return NULL;
+    }
+    size_t h = T->n / 2;
+    fft_task L = {T->F, T->a, h, T->tc * 2, T->tw, T->depth - 1};
+    fft_task R = {T->F, T->a + h, h, T->tc * 2, T->tw, T->depth - 1};
+    if (T->depth > 0) {                               /* multicore::join */
+        pthread_t th; pthread_create(&th, NULL, fft_rec, &L);
+        fft_rec(&R); pthread_join(th, NULL);
+    } else { fft_rec(&L); fft_rec(&R); }
+    butterflies(T->F, T->a, T->a + h, h, T->tc, T->tw);
+    return NULL;
+}
+static size_t bitrev(size_t n, unsigned l) { size_t r = 0; for (unsigned i = 0; i < l; i++) { r = (r << 1) | (n & 1); n >>= 1; } return r; }
+
+static void fft_mont(const field_t *F, fe *a, const fe *omega, uint32_t log_n, int threads) {
+    size_t n = (size_t)1 << log_n;
+    int log_threads = log2_floor((unsigned)threads);
+    for (size_t k = 0; k < n; k++) {
+        size_t rk = bitrev(k, log_n);
+        if (k < rk) { fe t = a[k]; a[k] = a[rk]; a[rk] = t; }
+    }
+    size_t nt = n / 2 ? n / 2 : 1;
+    fe *tw = (fe *)malloc(sizeof(fe) * nt);
+    fe w = F->r;
+    for (size_t i = 0; i < n / 2; i++) { tw[i] = w; fe_mul(F, &w, &w, omega); }
+    if ((int)log_n <= log_threads) {
+        size_t chunk = 2, tc = n / 2;
+        for (uint32_t s = 0; s < log_n; s++) {
+            for (size_t base = 0; base < n; base += chunk)
+                butterflies(F, a + base, a + base + chunk / 2, chunk / 2, tc, tw);
+            chunk *= 2; tc /= 2;
+        }
+    } else {
+        fft_task T = {F, a, n, 1, tw, log_threads};
+        fft_rec(&T);
+    }
+    free(tw);
+}
+
+/* parallelize, arithmetic.rs:345-362, applied to "a[i] *= f(i)" closures */
+typedef struct { const field_t *F; fe *a; size_t start, len; const fe *consts; int mode; } par_task;
+static void *par_worker(void *arg) {
+    par_task *T = (par_task *)arg;
+    for (size_t i = 0; i < T->len; i++) {
+        size_t idx = T->start + i;
+        if (T->mode == 0) fe_mul(T->F, &T->a[idx], &T->a[idx], &T->consts[0]);        /* divisor */
+        else { size_t r = idx % 3; if (r) fe_mul(T->F, &T->a[idx], &T->a[idx], &T->consts[r - 1]); }
+    }
+    return NULL;
+}
+static void parallelize_mul(const field_t *F, fe *a, size_t n, const fe *consts, int mode, int threads) {
+    size_t chunk = n / (size_t)threads;
+    if (chunk < (size_t)threads) chunk = n;
+    size_t nchunks = chunk ? (n + chunk - 1) / chunk : 0;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (nchunks ? nchunks : 1));
+    par_task *ts = (par_task *)malloc(sizeof(par_task) * (nchunks ? nchunks : 1));
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t start = c * chunk, len = (start + chunk <= n) ? chunk : n - start;
+        ts[c] = (par_task){F, a, start, len, consts, mode};
+        if (c + 1 < nchunks) pthread_create(&th[c], NULL, par_worker, &ts[c]); else par_worker(&ts[c]);
+    }
+    for (size_t c = 0; c + 1 < nchunks; c++) pthread_join(th[c], NULL);
+    free(th); free(ts);
+}
+
+static fe *load_vec(const field_t *F, const uint8_t *in, size_t n, size_t alloc_n) {
+    fe *a = (fe *)calloc(alloc_n ? alloc_n : 1, sizeof(fe));
+    for (size_t i = 0; i < n; i++) fe_from_bytes(F, &a[i], in + 32 * i);
+    return a;
+}
+static void store_vec(const field_t *F, uint8_t *out, const fe *a, size_t n) {
+    for (size_t i = 0; i < n; i++) fe_to_bytes(F, out + 32 * i, &a[i]);
+}
+
+/* best_fft(a, omega, log_n), in place on canonical bytes */
+int orc_best_fft(int field, uint8_t *a, const uint8_t *omega, uint32_t log_n, int threads) {
+    ensure_init(); if (threads < 1) threads = 1;
+    const field_t *F = &FLD[field]; size_t n = (size_t)1 << log_n;
+    fe *v = load_vec(F, a, n, n); fe w; fe_from_bytes(F, &w, omega);
+    fft_mont(F, v, &w, log_n, threads);
+    store_vec(F, a, v, n); free(v);
+    return 0;
+}
+/* EvaluationDomain::ifft, domain.rs:375-383 (== lagrange_to_coeff with omega_inv, 2^-k) */
+int orc_ifft(int field, uint8_t *a, const uint8_t *omega_inv, uint32_t log_n, const uint8_t *divisor, int threads) {
+    ensure_init(); if (threads < 1) threads = 1;
+    const field_t *F = &FLD[field]; size_t n = (size_t)1 << log_n;
+    fe *v = load_vec(F, a, n, n); fe w, d; fe_from_bytes(F, &w, omega_inv); fe_from_bytes(F, &d, divisor);
+    fft_mont(F, v, &w, log_n, threads);
+    parallelize_mul(F, v, n, &d, 0, threads);
+    store_vec(F, a, v, n); free(v);
+    return 0;
+}
+/* coeff_to_extended, domain.rs:241-255: in = 2^k elements, out = 2^ext_k elements */
+int orc_coeff_to_extended(int field, const uint8_t *in, uint32_t k, uint32_t ext_k, const uint8_t *zeta,
+                          const uint8_t *ext_omega, uint8_t *out, int threads) {
+    ensure_init(); if (threads < 1) threads = 1;
+    const field_t *F = &FLD[field]; size_t n = (size_t)1 << k, en = (size_t)1 << ext_k;
+    fe *v = load_vec(F, in, n, en); fe w, cp[2];
+    fe_from_bytes(F, &w, ext_omega); fe_from_bytes(F, &cp[0], zeta); fe_sqr(F, &cp[1], &cp[0]);
+    parallelize_mul(F, v, n, cp, 1, threads);          /* distribute_powers_zeta(into_coset) */
+    fft_mont(F, v, &w, ext_k, threads);
+    store_vec(F, out, v, en); free(v);
+    return 0;
+}
+/* extended_to_coeff, domain.rs:303-325: in = 2^ext_k, out = out_len (= n*(j-1)) elements */
+int orc_extended_to_coeff(int field, const uint8_t *in, uint32_t ext_k, const uint8_t *ext_omega_inv,
+                          const uint8_t *ext_divisor, const uint8_t *zeta, size_t out_len, uint8_t *out,
+                          int threads) {
+    ensure_init(); if (threads < 1) threads = 1;
+    const field_t *F = &FLD[field]; size_t en = (size_t)1 << ext_k;
+    fe *v = load_vec(F, in, en, en); fe w, d, z, cp[2];
+    fe_from_bytes(F, &w, ext_omega_inv); fe_from_bytes(F, &d, ext_divisor); fe_from_bytes(F, &z, zeta);
+    fe_sqr(F, &cp[0], &z); cp[1] = z;                   /* [g_coset_inv, g_coset], domain.rs:361 */
+    fft_mont(F, v, &w, ext_k, threads);
+    parallelize_mul(F, v, en, &d, 0, threads);
+    parallelize_mul(F, v, en, cp, 1, threads);
+    store_vec(F, out, v, out_len < en ? out_len : en); free(v);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- field / curve primitives for KATs */
+/* op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 a^5, 5 neg(a) */
+int orc_field_op(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    ensure_init();
+    const field_t *F = &FLD[field]; fe x, y, r;
+    fe_from_bytes(F, &x, a); if (b) fe_from_bytes(F, &y, b); else y = F->r;
+    switch (op) {
+    case 0: fe_add(F, &r, &x, &y); break;
+    case 1: fe_sub(F, &r, &x, &y); break;
+    case 2: fe_mul(F, &r, &x, &y); break;
+    case 3: fe_inv(F, &r, &x); break;
+    case 4: fe_sqr(F, &r, &x); fe_sqr(F, &r, &r); fe_mul(F, &r, &r, &x); break;
+    case 5: fe_neg(F, &r, &x); break;
+    default: return -1;
+    }
+    fe_to_bytes(F, out, &r);
+    return 0;
+}
+int orc_scalar_mul(int curve, const uint8_t *scalar, const uint8_t *base_xy, uint8_t *out_xy) {
+    ensure_init(); const field_t *F = base_field(curve);
+    aff b, r; aff_from_bytes(F, &b, base_xy);
+    jac t; scalar_mul_bytes(F, &t, scalar, &b);
+    jac_to_aff(F, &r, &t); aff_to_bytes(F, out_xy, &r);
+    return 0;
+}
+int orc_point_add(int curve, const uint8_t *a_xy, const uint8_t *b_xy, uint8_t *out_xy) {
+    ensure_init(); const field_t *F = base_field(curve);
+    aff a, b, r; aff_from_bytes(F, &a, a_xy); aff_from_bytes(F, &b, b_xy);
+    jac t; if (a.inf) jac_identity(F, &t); else { t.x = a.x; t.y = a.y; t.z = F->r; }
+    jac_add_mixed(F, &t, &t, &b);
+    jac_to_aff(F, &r, &t); aff_to_bytes(F, out_xy, &r);
+    return 0;
+}
+/* Jacobian (x,y,z canonical bytes, 96 B) -> affine 64 B */
+int orc_jac_to_affine(int curve, const uint8_t *xyz, uint8_t *out_xy) {
+    ensure_init(); const field_t *F = base_field(curve);
+    jac t; fe_from_bytes(F, &t.x, xyz); fe_from_bytes(F, &t.y, xyz + 32); fe_from_bytes(F, &t.z, xyz + 64);
+    aff r; jac_to_aff(F, &r, &t); aff_to_bytes(F, out_xy, &r);
+    return 0;
+}
+int orc_on_curve(int curve, const uint8_t *xy) {
+    ensure_init(); const field_t *F = base_field(curve);
+    aff a; aff_from_bytes(F, &a, xy); if (a.inf) return 1;
+    fe l, r, five, t; fe_sqr(F, &l, &a.y); fe_sqr(F, &r, &a.x); fe_mul(F, &r, &r, &a.x);
+    uint8_t fb[32] = {5}; fe_from_bytes(F, &five, fb); fe_add(F, &r, &r, &five);
+    (void)t; return fe_eq(&l, &r);
+}
+
+/* ---------------------------------------------------------------- seeded inputs (same PRNG as pasta.py) */
+typedef struct { uint64_t s[4]; } xo_t;
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static void xo_seed(xo_t *x, uint64_t seed) {
+    for (int i = 0; i < 4; i++) {
+        seed += 0x9E3779B97F4A7C15ULL; uint64_t z = seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        x->s[i] = z ^ (z >> 31);
+    }
+}
+static uint64_t xo_next(xo_t *x) {
+    uint64_t *s = x->s, result = rotl64(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+    return result;
+}
+static void xo_field(xo_t *x, const field_t *F, uint8_t out[32]) {
+    uint64_t v[4];
+    do { for (int i = 0; i < 4; i++) v[i] = xo_next(x); v[3] &= 0x7fffffffffffffffULL; } while (ge4(v, F->m));
+    memcpy(out, v, 32);
+}
+int orc_gen_scalars(int field, uint64_t seed, size_t n, uint8_t *out) {
+    ensure_init(); xo_t x; xo_seed(&x, seed);
+    for (size_t i = 0; i < n; i++) xo_field(&x, &FLD[field], out + 32 * i);
+    return 0;
+}
+/* P_0 = [s]G, P_{i+1} = P_i + [t]G, G = (-1, 2); batch-normalised */
+int orc_gen_points(int curve, uint64_t seed, size_t n, uint8_t *out) {
+    ensure_init(); const field_t *F = base_field(curve), *S = scalar_field(curve);
+    xo_t x; xo_seed(&x, seed);
+    uint8_t sb[32], tb[32]; xo_field(&x, S, sb); xo_field(&x, S, tb);
+    aff g; fe one = F->r, two; fe_neg(F, &g.x, &one); fe_add(F, &two, &one, &one); g.y = two; g.inf = 0;
+    jac cur, step; scalar_mul_bytes(F, &cur, sb, &g); scalar_mul_bytes(F, &step, tb, &g);
+    jac *pts = (jac *)malloc(sizeof(jac) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) { pts[i] = cur; jac_add(F, &cur, &cur, &step); }
+    /* Montgomery-trick batch normalisation */
+    fe *pre = (fe *)malloc(sizeof(fe) * (n ? n : 1)); fe acc = F->r;
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; if (!jac_is_id(&pts[i])) fe_mul(F, &acc, &acc, &pts[i].z); }
+    fe_inv(F, &acc, &acc);
+    for (size_t i = n; i-- > 0;) {
+        if (jac_is_id(&pts[i])) { memset(out + 64 * i, 0, 64); continue; }
+        fe zi, zi2; fe_mul(F, &zi, &acc, &pre[i]); fe_mul(F, &acc, &acc, &pts[i].z);
+        fe_sqr(F, &zi2, &zi); aff r; r.inf = 0;
+        fe_mul(F, &r.x, &pts[i].x, &zi2); fe_mul(F, &zi2, &zi2, &zi); fe_mul(F, &r.y, &pts[i].y, &zi2);
+        aff_to_bytes(F, out + 64 * i, &r);
+    }
+    free(pts); free(pre);
+    return 0;
+}

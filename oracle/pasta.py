@@ -1,0 +1,660 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) -- exact big-integer restatement of the
+halo2 MSM + FFT hot path over the Pasta fields/curves.
+
+*** This file is the checker, never the product. Only tests/, __graft_entry__.smoke()
+*** and bench.py's cpu_baseline / --impl reference leg may import it.
+
+What it restates (all file:line relative to /root/reference/halo2_proofs/src):
+  * best_multiexp            arithmetic.rs:143-180  (+ Bucket/Buckets :29-112)
+  * small_multiexp           arithmetic.rs:116-136
+  * best_fft                 arithmetic.rs:192-255  (+ recursive_butterfly_arithmetic :258-295)
+  * parallelize              arithmetic.rs:345-362  (chunking only; serial here)
+  * Params::commit{,_lagrange}  poly/commitment.rs:119-150
+  * Params::new's EC-FFT      poly/commitment.rs:77-94   (generators are synthetic, see below)
+  * EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff,
+    distribute_powers_zeta, ifft}   poly/domain.rs:40-146, 227-255, 303-325, 357-383
+
+Third-party arithmetic that is NOT in the reference tree: crate `pasta_curves 0.5.1`
+(Cargo.lock:1303-1306), `ff 0.13.0`, `group 0.13.0`.  Its published algorithm is restated
+here from the mathematical definition: Fp/Fq are prime fields with the two moduli pinned at
+halo2_proofs/tests/plonk_api.rs:591-592; Pallas/Vesta are y^2 = x^3 + 5 over Fp/Fq
+(book/src/background/curves.md); identity is encoded as affine (0, 0)
+(book/src/background/curves.md:226-230).
+
+PARITY PINNING STATUS
+  pinned:   moduli, ROOT_OF_UNITY (via the k=5 / k=11 omegas in the reference goldens),
+            field mul/add/x^5 (halo2_poseidon test vectors), golden commitments lie on Vesta
+            -- see tests/golden/ and tests/test_oracle_golden.py.
+  UNPINNED: best_multiexp / best_fft on synthetic inputs -- the reference holds no
+            input->output vector for either and cannot be built here (no Rust toolchain,
+            pasta_curves not vendored).  "parity unpinned" for those; soundness rests on the
+            uniqueness of canonical encodings (any correct MSM/NTT yields the same bytes) and
+            on two independent restatements (this file and oracle/halo2_oracle.c) agreeing.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+# --------------------------------------------------------------------------------------
+# Fields.  tests/plonk_api.rs:591-592
+# --------------------------------------------------------------------------------------
+P_MOD = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001  # Fp: Pallas base, Vesta scalar
+Q_MOD = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001  # Fq: Vesta base, Pallas scalar
+S_2ADICITY = 32  # book/src/background/fields.md:198-204
+MULT_GEN = 5  # multiplicative generator used by pasta_curves for both fields
+
+FIELDS = {"fp": P_MOD, "fq": Q_MOD}
+
+
+def field_modulus(field: str) -> int:
+    return FIELDS[field]
+
+
+def root_of_unity(field: str) -> int:
+    """ROOT_OF_UNITY = 5^T, T = (m-1) >> 32 (order exactly 2^32).  Pinned against the
+    reference's k=5 and k=11 omegas in tests/test_oracle_golden.py."""
+    m = FIELDS[field]
+    return pow(MULT_GEN, (m - 1) >> S_2ADICITY, m)
+
+
+def omega_for_k(field: str, k: int) -> int:
+    """domain.rs:58-78: omega = ROOT_OF_UNITY^(2^(S-k))."""
+    m = FIELDS[field]
+    w = root_of_unity(field)
+    for _ in range(k, S_2ADICITY):
+        w = w * w % m
+    return w
+
+
+def zeta_candidates(field: str) -> Tuple[int, int]:
+    """The two primitive cube roots of unity.  Which one pasta_curves calls ZETA is not
+    pinned by any in-tree golden; the engine therefore takes zeta as an argument
+    (domain.rs:85 reads F::ZETA)."""
+    m = FIELDS[field]
+    z = pow(MULT_GEN, (m - 1) // 3, m)
+    return z, z * z % m
+
+
+def inv(a: int, m: int) -> int:
+    return pow(a, m - 2, m)
+
+
+# --------------------------------------------------------------------------------------
+# Curves: y^2 = x^3 + 5.  Pallas over Fp (scalars Fq), Vesta over Fq (scalars Fp).
+# Affine point = (x, y) ints, identity = None.  Jacobian = (X, Y, Z), identity Z == 0.
+# --------------------------------------------------------------------------------------
+CURVE_B = 5
+
+
+@dataclass(frozen=True)
+class Curve:
+    name: str
+    base: str  # coordinate field
+    scalar: str  # scalar field
+
+    @property
+    def p(self) -> int:
+        return FIELDS[self.base]
+
+    @property
+    def r(self) -> int:
+        return FIELDS[self.scalar]
+
+
+PALLAS = Curve("pallas", "fp", "fq")
+VESTA = Curve("vesta", "fq", "fp")
+CURVES = {"pallas": PALLAS, "vesta": VESTA}
+
+Affine = Optional[Tuple[int, int]]
+Jac = Tuple[int, int, int]
+
+JAC_ID: Jac = (0, 1, 0)
+
+
+def on_curve(c: Curve, pt: Affine) -> bool:
+    if pt is None:
+        return True
+    x, y = pt
+    return (y * y - x * x * x - CURVE_B) % c.p == 0
+
+
+def generator(c: Curve) -> Affine:
+    """(-1, 2): on both curves; the concrete point the reference's msm test uses
+    (poly/commitment/msm.rs:181)."""
+    return (c.p - 1, 2)
+
+
+def to_jac(pt: Affine) -> Jac:
+    if pt is None:
+        return JAC_ID
+    return (pt[0], pt[1], 1)
+
+
+def to_affine(c: Curve, pt: Jac) -> Affine:
+    X, Y, Z = pt
+    if Z % c.p == 0:
+        return None
+    zi = inv(Z, c.p)
+    zi2 = zi * zi % c.p
+    return (X * zi2 % c.p, Y * zi2 * zi % c.p)
+
+
+def jac_double(c: Curve, pt: Jac) -> Jac:
+    p = c.p
+    X, Y, Z = pt
+    if Z == 0 or Y == 0:
+        return JAC_ID
+    A = X * X % p
+    B = Y * Y % p
+    C = B * B % p
+    D = 2 * ((X + B) * (X + B) - A - C) % p
+    E = 3 * A % p
+    F = E * E % p
+    X3 = (F - 2 * D) % p
+    Y3 = (E * (D - X3) - 8 * C) % p
+    Z3 = 2 * Y * Z % p
+    return (X3, Y3, Z3)
+
+
+def jac_add(c: Curve, a: Jac, b: Jac) -> Jac:
+    p = c.p
+    X1, Y1, Z1 = a
+    X2, Y2, Z2 = b
+    if Z1 == 0:
+        return b
+    if Z2 == 0:
+        return a
+    Z1Z1 = Z1 * Z1 % p
+    Z2Z2 = Z2 * Z2 % p
+    U1 = X1 * Z2Z2 % p
+    U2 = X2 * Z1Z1 % p
+    S1 = Y1 * Z2 * Z2Z2 % p
+    S2 = Y2 * Z1 * Z1Z1 % p
+    if U1 == U2:
+        if S1 == S2:
+            return jac_double(c, a)
+        return JAC_ID
+    H = (U2 - U1) % p
+    R = (S2 - S1) % p
+    HH = H * H % p
+    HHH = H * HH % p
+    V = U1 * HH % p
+    X3 = (R * R - HHH - 2 * V) % p
+    Y3 = (R * (V - X3) - S1 * HHH) % p
+    Z3 = Z1 * Z2 * H % p
+    return (X3, Y3, Z3)
+
+
+def jac_neg(c: Curve, a: Jac) -> Jac:
+    return (a[0], (-a[1]) % c.p, a[2])
+
+
+def jac_eq(c: Curve, a: Jac, b: Jac) -> bool:
+    return to_affine(c, a) == to_affine(c, b)
+
+
+def scalar_mul(c: Curve, k: int, pt: Affine) -> Jac:
+    """Plain left-to-right double-and-add -- the 'naive' side of the reference's
+    test_multiexp (arithmetic.rs:440-458)."""
+    k %= c.r
+    acc = JAC_ID
+    base = to_jac(pt)
+    for bit in bin(k)[2:] if k else "":
+        acc = jac_double(c, acc)
+        if bit == "1":
+            acc = jac_add(c, acc, base)
+    return acc
+
+
+def naive_msm(c: Curve, coeffs: Sequence[int], bases: Sequence[Affine]) -> Jac:
+    assert len(coeffs) == len(bases)
+    acc = JAC_ID
+    for k, b in zip(coeffs, bases):
+        acc = jac_add(c, acc, scalar_mul(c, k, b))
+    return acc
+
+
+def batch_normalize(c: Curve, pts: Sequence[Jac]) -> List[Affine]:
+    """Montgomery-trick batch inversion (group::Curve::batch_normalize)."""
+    p = c.p
+    prefix = []
+    acc = 1
+    for X, Y, Z in pts:
+        prefix.append(acc)
+        if Z % p:
+            acc = acc * Z % p
+    acc = inv(acc, p)
+    out: List[Affine] = [None] * len(pts)
+    for i in range(len(pts) - 1, -1, -1):
+        X, Y, Z = pts[i]
+        if Z % p == 0:
+            continue
+        zi = acc * prefix[i] % p
+        acc = acc * Z % p
+        zi2 = zi * zi % p
+        out[i] = (X * zi2 % p, Y * zi2 * zi % p)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# best_multiexp -- arithmetic.rs:143-180
+# --------------------------------------------------------------------------------------
+def multiexp_window_bits(n: int) -> int:
+    """arithmetic.rs:146-152."""
+    if n < 4:
+        return 1
+    if n < 32:
+        return 3
+    return int(math.ceil(math.log(float(n))))
+
+
+def get_at(segment: int, c_bits: int, repr32: bytes) -> int:
+    """arithmetic.rs:95-111: c bits at bit offset segment*c of the 32-byte LE repr."""
+    skip_bits = segment * c_bits
+    skip_bytes = skip_bits // 8
+    if skip_bytes >= 32:
+        return 0
+    v = repr32[skip_bytes : skip_bytes + 8].ljust(8, b"\0")
+    tmp = int.from_bytes(v, "little")
+    tmp >>= skip_bits - skip_bytes * 8
+    return tmp % (1 << c_bits)
+
+
+def _bucket_sum(c: Curve, c_bits: int, reprs: Sequence[bytes], bases: Sequence[Affine], i: int) -> Jac:
+    """Buckets::sum, arithmetic.rs:74-93 (None/Affine/Projective promotion collapses to
+    Jacobian adds: same group element)."""
+    buckets: List[Jac] = [JAC_ID] * ((1 << c_bits) - 1)
+    for rep, base in zip(reprs, bases):
+        seg = get_at(i, c_bits, rep)
+        if seg != 0:
+            buckets[seg - 1] = jac_add(c, buckets[seg - 1], to_jac(base))
+    acc = JAC_ID
+    run = JAC_ID
+    for b in reversed(buckets):
+        run = jac_add(c, b, run)
+        acc = jac_add(c, acc, run)
+    return acc
+
+
+def best_multiexp(c: Curve, coeffs: Sequence[int], bases: Sequence[Affine], num_threads: int = 8) -> Jac:
+    """arithmetic.rs:143-180, both branches.  Panics (AssertionError) on length mismatch
+    like the reference's assert_eq! at :144."""
+    assert len(coeffs) == len(bases)
+    n = len(bases)
+    c_bits = multiexp_window_bits(n)
+    windows = 256 // c_bits + 1
+    reprs = [int(k % c.r).to_bytes(32, "little") for k in coeffs]
+    if n > num_threads:
+        total = JAC_ID
+        for i in reversed(range(windows)):
+            acc = _bucket_sum(c, c_bits, reprs, bases, i)
+            for _ in range(c_bits * i):
+                acc = jac_double(c, acc)
+            total = jac_add(c, total, acc)
+        return total
+    total = JAC_ID
+    for i in reversed(range(windows)):
+        for _ in range(c_bits):
+            total = jac_double(c, total)
+        total = jac_add(c, total, _bucket_sum(c, c_bits, reprs, bases, i))
+    return total
+
+
+def small_multiexp(c: Curve, coeffs: Sequence[int], bases: Sequence[Affine]) -> Jac:
+    """arithmetic.rs:116-136."""
+    reprs = [int(k % c.r).to_bytes(32, "little") for k in coeffs]
+    acc = JAC_ID
+    for byte_idx in reversed(range(32)):
+        for bit_idx in reversed(range(8)):
+            acc = jac_double(c, acc)
+            for rep, base in zip(reprs, bases):
+                if (rep[byte_idx] >> bit_idx) & 1:
+                    acc = jac_add(c, acc, to_jac(base))
+    return acc
+
+
+# --------------------------------------------------------------------------------------
+# best_fft -- arithmetic.rs:192-295.  The butterfly NETWORK, valid for any omega
+# (benches/fft.rs:17 passes a random omega), not "the DFT".
+# --------------------------------------------------------------------------------------
+def bitreverse(n: int, l: int) -> int:
+    r = 0
+    for _ in range(l):
+        r = (r << 1) | (n & 1)
+        n >>= 1
+    return r
+
+
+def best_fft(field: str, a: List[int], omega: int, log_n: int) -> None:
+    """In place.  Iterative form, arithmetic.rs:207-251."""
+    m = FIELDS[field]
+    n = len(a)
+    assert n == 1 << log_n  # arithmetic.rs:205
+    for k in range(n):
+        rk = bitreverse(k, log_n)
+        if k < rk:
+            a[k], a[rk] = a[rk], a[k]
+    twiddles = [1] * (n // 2)
+    for i in range(1, n // 2):
+        twiddles[i] = twiddles[i - 1] * omega % m
+    chunk = 2
+    twiddle_chunk = n // 2
+    for _ in range(log_n):
+        half = chunk // 2
+        for base in range(0, n, chunk):
+            t = a[base + half]
+            a[base + half] = (a[base] - t) % m
+            a[base] = (a[base] + t) % m
+            for i in range(1, half):
+                t = a[base + half + i] * twiddles[i * twiddle_chunk] % m
+                u = a[base + i]
+                a[base + i] = (u + t) % m
+                a[base + half + i] = (u - t) % m
+        chunk *= 2
+        twiddle_chunk //= 2
+
+
+def best_fft_recursive(field: str, a: List[int], omega: int, log_n: int) -> None:
+    """Recursive form, arithmetic.rs:253,258-295 (same network)."""
+    m = FIELDS[field]
+    n = len(a)
+    assert n == 1 << log_n
+    for k in range(n):
+        rk = bitreverse(k, log_n)
+        if k < rk:
+            a[k], a[rk] = a[rk], a[k]
+    twiddles = [1] * max(1, n // 2)
+    for i in range(1, n // 2):
+        twiddles[i] = twiddles[i - 1] * omega % m
+
+    def rec(lo: int, nn: int, tc: int) -> None:
+        if nn == 2:
+            t = a[lo + 1]
+            a[lo + 1] = (a[lo] - t) % m
+            a[lo] = (a[lo] + t) % m
+            return
+        h = nn // 2
+        rec(lo, h, tc * 2)
+        rec(lo + h, h, tc * 2)
+        t = a[lo + h]
+        a[lo + h] = (a[lo] - t) % m
+        a[lo] = (a[lo] + t) % m
+        for i in range(1, h):
+            t = a[lo + h + i] * twiddles[i * tc] % m
+            u = a[lo + i]
+            a[lo + i] = (u + t) % m
+            a[lo + h + i] = (u - t) % m
+
+    if n >= 2:
+        rec(0, n, 1)
+
+
+def ec_fft(c: Curve, a: List[Jac], omega: int, log_n: int) -> None:
+    """best_fft with G = curve point (arithmetic.rs:17-27), as used by Params::new
+    (poly/commitment.rs:81-82).  '*' is scalar multiplication."""
+    n = len(a)
+    assert n == 1 << log_n
+    r = c.r
+    for k in range(n):
+        rk = bitreverse(k, log_n)
+        if k < rk:
+            a[k], a[rk] = a[rk], a[k]
+    twiddles = [1] * max(1, n // 2)
+    for i in range(1, n // 2):
+        twiddles[i] = twiddles[i - 1] * omega % r
+    chunk = 2
+    tc = n // 2
+    for _ in range(log_n):
+        half = chunk // 2
+        for base in range(0, n, chunk):
+            for i in range(half):
+                t = a[base + half + i]
+                if i:
+                    aff = to_affine(c, t)
+                    t = scalar_mul(c, twiddles[i * tc], aff)
+                u = a[base + i]
+                a[base + i] = jac_add(c, u, t)
+                a[base + half + i] = jac_add(c, u, jac_neg(c, t))
+        chunk *= 2
+        tc //= 2
+
+
+# --------------------------------------------------------------------------------------
+# parallelize chunking -- arithmetic.rs:345-362 (documented; the oracle runs serially)
+# --------------------------------------------------------------------------------------
+def parallelize_chunks(n: int, threads: int) -> List[Tuple[int, int]]:
+    chunk = n // threads
+    if chunk < threads:
+        chunk = n
+    out = []
+    start = 0
+    while start < n:
+        out.append((start, min(chunk, n - start)))
+        start += chunk
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# EvaluationDomain -- poly/domain.rs:40-146 and the three transforms
+# --------------------------------------------------------------------------------------
+class EvaluationDomain:
+    def __init__(self, field: str, j: int, k: int, zeta: Optional[int] = None):
+        m = FIELDS[field]
+        self.field = field
+        self.m = m
+        self.k = k
+        self.n = 1 << k
+        self.quotient_poly_degree = j - 1
+        ext_k = k
+        while (1 << ext_k) < self.n * self.quotient_poly_degree:
+            ext_k += 1
+        assert ext_k <= S_2ADICITY  # domain.rs:56
+        self.extended_k = ext_k
+        ew = root_of_unity(field)
+        for _ in range(ext_k, S_2ADICITY):
+            ew = ew * ew % m
+        self.extended_omega = ew
+        w = ew
+        for _ in range(k, ext_k):
+            w = w * w % m
+        self.omega = w
+        self.omega_inv = inv(w, m)
+        self.extended_omega_inv = inv(ew, m)
+        self.g_coset = zeta_candidates(field)[0] if zeta is None else zeta
+        self.g_coset_inv = self.g_coset * self.g_coset % m
+        self.ifft_divisor = inv((1 << k) % m, m)
+        self.extended_ifft_divisor = inv((1 << ext_k) % m, m)
+        # t(X) = X^n - 1 over the coset (domain.rs:88-107), inverted (:121-128)
+        orig = pow(self.g_coset, self.n, m)
+        step = pow(ew, self.n, m)
+        cur = orig
+        t = []
+        while True:
+            t.append(cur)
+            cur = cur * step % m
+            if cur == orig:
+                break
+        assert len(t) == 1 << (ext_k - k)
+        self.t_evaluations = [inv((x - 1) % m, m) for x in t]
+
+    def extended_len(self) -> int:
+        return 1 << self.extended_k
+
+    def distribute_powers_zeta(self, a: List[int], into_coset: bool) -> None:
+        """domain.rs:357-373."""
+        cp = [self.g_coset, self.g_coset_inv] if into_coset else [self.g_coset_inv, self.g_coset]
+        for idx in range(len(a)):
+            i = idx % 3
+            if i:
+                a[idx] = a[idx] * cp[i - 1] % self.m
+
+    def ifft(self, a: List[int], omega_inv: int, log_n: int, divisor: int) -> None:
+        """domain.rs:375-383."""
+        best_fft(self.field, a, omega_inv, log_n)
+        for i in range(len(a)):
+            a[i] = a[i] * divisor % self.m
+
+    def lagrange_to_coeff(self, a: Sequence[int]) -> List[int]:
+        """domain.rs:227-237."""
+        assert len(a) == 1 << self.k
+        a = list(a)
+        self.ifft(a, self.omega_inv, self.k, self.ifft_divisor)
+        return a
+
+    def coeff_to_extended(self, a: Sequence[int]) -> List[int]:
+        """domain.rs:241-255."""
+        assert len(a) == 1 << self.k
+        a = list(a)
+        self.distribute_powers_zeta(a, True)
+        a += [0] * (self.extended_len() - len(a))
+        best_fft(self.field, a, self.extended_omega, self.extended_k)
+        return a
+
+    def extended_to_coeff(self, a: Sequence[int]) -> List[int]:
+        """domain.rs:303-325."""
+        assert len(a) == self.extended_len()
+        a = list(a)
+        self.ifft(a, self.extended_omega_inv, self.extended_k, self.extended_ifft_divisor)
+        self.distribute_powers_zeta(a, False)
+        return a[: self.n * self.quotient_poly_degree]
+
+    def divide_by_vanishing_poly(self, a: Sequence[int]) -> List[int]:
+        """domain.rs:329-348."""
+        assert len(a) == self.extended_len()
+        t = self.t_evaluations
+        return [x * t[i % len(t)] % self.m for i, x in enumerate(a)]
+
+
+def eval_polynomial(field: str, poly: Sequence[int], point: int) -> int:
+    """arithmetic.rs:298-303."""
+    m = FIELDS[field]
+    acc = 0
+    for coeff in reversed(poly):
+        acc = (acc * point + coeff) % m
+    return acc
+
+
+# --------------------------------------------------------------------------------------
+# Params -- poly/commitment.rs:26-150.  Generators are SYNTHETIC ([s_i]*(-1,2) from the
+# seeded PRNG) because hash_to_curve lives in un-vendored pasta_curves; everything
+# downstream (EC-FFT for g_lagrange, commit, commit_lagrange) follows the reference.
+# --------------------------------------------------------------------------------------
+class Params:
+    def __init__(self, curve: Curve, k: int, seed: int = 0x48414C4F32):
+        assert k < 32  # commitment.rs:41
+        self.curve = curve
+        self.k = k
+        self.n = 1 << k
+        rng = Xoshiro256(seed)
+        g0 = generator(curve)
+        g_proj = [scalar_mul(curve, rng.field_element(curve.r), g0) for _ in range(self.n)]
+        self.g = batch_normalize(curve, g_proj)
+        # commitment.rs:77-94: alpha_inv = ROOT_OF_UNITY_INV^(2^(S-k)); EC-FFT; * 2^-k
+        r = curve.r
+        alpha_inv = inv(root_of_unity(curve.scalar), r)
+        for _ in range(k, S_2ADICITY):
+            alpha_inv = alpha_inv * alpha_inv % r
+        gl = list(g_proj)
+        ec_fft(curve, gl, alpha_inv, k)
+        minv = pow(inv(2, r), k, r)
+        gl = [scalar_mul(curve, minv, to_affine(curve, pt)) for pt in gl]
+        self.g_lagrange = batch_normalize(curve, gl)
+        self.w = to_affine(curve, scalar_mul(curve, rng.field_element(r), g0))
+        self.u = to_affine(curve, scalar_mul(curve, rng.field_element(r), g0))
+
+    def commit(self, poly: Sequence[int], blind: int) -> Jac:
+        """commitment.rs:119-130."""
+        return best_multiexp(self.curve, list(poly) + [blind], list(self.g) + [self.w])
+
+    def commit_lagrange(self, poly: Sequence[int], blind: int) -> Jac:
+        """commitment.rs:135-150."""
+        return best_multiexp(self.curve, list(poly) + [blind], list(self.g_lagrange) + [self.w])
+
+
+# --------------------------------------------------------------------------------------
+# Seeded PRNG shared by the oracle, the tests and bench.py (splitmix64 -> xoshiro256**),
+# SURVEY.md section 8(d).  Seed convention: 0x48414C4F32 ("HALO2") + config index.
+# --------------------------------------------------------------------------------------
+MASK64 = (1 << 64) - 1
+
+
+class Xoshiro256:
+    def __init__(self, seed: int):
+        s = seed & MASK64
+        st = []
+        for _ in range(4):
+            s = (s + 0x9E3779B97F4A7C15) & MASK64
+            z = s
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK64
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK64
+            st.append(z ^ (z >> 31))
+        self.s = st
+
+    @staticmethod
+    def _rotl(x: int, k: int) -> int:
+        return ((x << k) | (x >> (64 - k))) & MASK64
+
+    def next_u64(self) -> int:
+        s = self.s
+        result = (self._rotl((s[1] * 5) & MASK64, 7) * 9) & MASK64
+        t = (s[1] << 17) & MASK64
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = self._rotl(s[3], 45)
+        return result
+
+    def field_element(self, modulus: int) -> int:
+        """Uniform canonical element: 255-bit rejection sampling (limb 0 drawn first)."""
+        while True:
+            limbs = [self.next_u64() for _ in range(4)]
+            v = limbs[0] | (limbs[1] << 64) | (limbs[2] << 128) | ((limbs[3] & ((1 << 63) - 1)) << 192)
+            if v < modulus:
+                return v
+
+
+def gen_scalars(field: str, seed: int, n: int) -> List[int]:
+    rng = Xoshiro256(seed)
+    m = FIELDS[field]
+    return [rng.field_element(m) for _ in range(n)]
+
+
+def gen_points(c: Curve, seed: int, n: int) -> List[Affine]:
+    """P_0 = [s]G, P_{i+1} = P_i + [t]G with s, t from the PRNG: n distinct
+    pseudo-random points for the price of n additions."""
+    rng = Xoshiro256(seed)
+    g0 = generator(c)
+    cur = scalar_mul(c, rng.field_element(c.r), g0)
+    step = scalar_mul(c, rng.field_element(c.r), g0)
+    pts = []
+    for _ in range(n):
+        pts.append(cur)
+        cur = jac_add(c, cur, step)
+    return batch_normalize(c, pts)
+
+
+# byte helpers (canonical 32-byte LE, identity = 64 zero bytes) -------------------------
+def fe_to_bytes(x: int) -> bytes:
+    return int(x).to_bytes(32, "little")
+
+
+def fe_from_bytes(b: bytes) -> int:
+    return int.from_bytes(b, "little")
+
+
+def affine_to_bytes(pt: Affine) -> bytes:
+    if pt is None:
+        return b"\0" * 64
+    return fe_to_bytes(pt[0]) + fe_to_bytes(pt[1])
+
+
+def affine_from_bytes(b: bytes) -> Affine:
+    x = fe_from_bytes(b[:32])
+    y = fe_from_bytes(b[32:64])
+    if x == 0 and y == 0:
+        return None
+    return (x, y)
