@@ -1,0 +1,79 @@
+"""Pins the oracle against every known-answer datum the reference's tests hold for the path
+(SURVEY.md section 8(c)).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import cref, pasta
+from tests.poseidon_kat import permute
+
+
+def test_moduli_and_omegas(goldens):
+    vk5 = goldens["vk_plonk_api_k5"]
+    vk11 = goldens["vk_lookup_range_check_k11"]
+    # EqAffine = Vesta: base field Fq, scalar field Fp (tests/plonk_api.rs:591-592)
+    for vk in (vk5, vk11):
+        assert int(vk["base_modulus"], 16) == pasta.Q_MOD
+        assert int(vk["scalar_modulus"], 16) == pasta.P_MOD
+    # domain.rs:58-78 with ROOT_OF_UNITY = 5^T reproduces the pinned omegas
+    assert pasta.omega_for_k("fp", 5) == int(vk5["omega"], 16)
+    assert pasta.omega_for_k("fp", 11) == int(vk11["omega"], 16)
+    d = pasta.EvaluationDomain("fp", 4, 5)  # plonk_api circuit: extended_k = 7
+    assert d.omega == int(vk5["omega"], 16)
+    for f in ("fp", "fq"):
+        m = pasta.FIELDS[f]
+        w = pasta.root_of_unity(f)
+        assert pow(w, 1 << 32, m) == 1 and pow(w, 1 << 31, m) == m - 1
+        for z in pasta.zeta_candidates(f):
+            assert z != 1 and pow(z, 3, m) == 1
+
+
+def test_golden_commitments_on_vesta(goldens):
+    """commit_lagrange outputs pinned by the reference lie on y^2 = x^3 + 5 over Fq."""
+    n = 0
+    for key in ("vk_plonk_api_k5", "vk_lookup_range_check_k11"):
+        vk = goldens[key]
+        for x, y in vk["fixed_commitments"] + vk["permutation_commitments"]:
+            pt = (int(x, 16), int(y, 16))
+            assert pasta.on_curve(pasta.VESTA, pt)
+            assert not pasta.on_curve(pasta.PALLAS, pt)
+            assert cref.on_curve("vesta", cref.affines_to_bytes([pt])[0])
+            n += 1
+    assert n >= 19
+    # the all-zero column's commitment (= params.w, blind 1) recurs at k=5 and k=11
+    assert goldens["vk_plonk_api_k5"]["fixed_commitments"][0] in goldens["vk_lookup_range_check_k11"]["fixed_commitments"]
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_poseidon_permutation_kat_python(goldens, field):
+    m = pasta.FIELDS[field]
+    g = goldens["poseidon"][field]
+    rc = [int(x, 16) for x in g["round_constants"]]
+    mds = [int(x, 16) for x in g["mds"]]
+    assert len(g["permute"]) == 11
+    for tv in g["permute"]:
+        out = permute([int(x, 16) for x in tv["initial_state"]], rc, mds,
+                      lambda a, b: (a + b) % m, lambda a, b: a * b % m, lambda a: pow(a, 5, m))
+        assert out == [int(x, 16) for x in tv["final_state"]]
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_poseidon_permutation_kat_c(goldens, field):
+    g = goldens["poseidon"][field]
+    rc = [int(x, 16) for x in g["round_constants"]]
+    mds = [int(x, 16) for x in g["mds"]]
+    for tv in g["permute"][:4]:
+        out = permute([int(x, 16) for x in tv["initial_state"]], rc, mds,
+                      lambda a, b: cref.field_op(field, "add", a, b),
+                      lambda a, b: cref.field_op(field, "mul", a, b),
+                      lambda a: cref.field_op(field, "pow5", a))
+        assert out == [int(x, 16) for x in tv["final_state"]]
+
+
+def test_generator_order():
+    """(-1, 2) (poly/commitment/msm.rs:181) has prime order r on both curves."""
+    for c in (pasta.PALLAS, pasta.VESTA):
+        g = pasta.generator(c)
+        assert pasta.on_curve(c, g)
+        assert pasta.to_affine(c, pasta.scalar_mul(c, c.r - 1, g)) == (g[0], c.p - g[1])
+        gb = cref.affines_to_bytes([g])[0]
+        assert cref.bytes_to_affine(cref.scalar_mul(c.name, c.r - 1, gb)) == (g[0], c.p - g[1])
