@@ -1,0 +1,157 @@
+// Device curve library for Pallas / Vesta, y^2 = x^3 + 5 (K1 in SURVEY.md section 2.1).
+//
+// Replaces the pasta_curves Ep/Eq group law that the reference's buckets use
+// (halo2_proofs/src/arithmetic.rs:37-57 Bucket::add_assign/add, :86-91 running sums,
+// :163 window doubling, :166 window sum).  The template parameter is the COORDINATE field
+// (FpParams for Pallas, FqParams for Vesta).
+//
+// Accumulators use extended Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2):
+// mixed add 8M+2S, full add 12M+2S, double 6M+3S, no inversion anywhere on the hot path.
+// Identity: affine (0,0) (book/src/background/curves.md:226-230); XYZZ with ZZ == 0.
+// Every add handles P+P, P+(-P), identity operands (cf. the reference's msm_arithmetic test,
+// poly/commitment/msm.rs:179-219).
+#pragma once
+#include "field.cuh"
+
+namespace h2 {
+
+struct affine { fe x, y; };              // 64 B, Montgomery coordinates; (0,0) = identity
+struct xyzz { fe x, y, zz, zzz; };       // 128 B
+struct jacobian { fe x, y, z; };         // 96 B, the layout of pasta's Ep/Eq (x, y, z)
+
+H2_HD bool affine_is_identity(const affine &p) {
+    uint32_t t = 0;
+    for (int i = 0; i < 8; i++) t |= p.x.v[i] | p.y.v[i];
+    return t == 0;
+}
+H2_HD xyzz xyzz_identity() {
+    xyzz r; r.x = fe_zero(); r.y = fe_zero(); r.zz = fe_zero(); r.zzz = fe_zero();
+    return r;
+}
+H2_HD bool xyzz_is_identity(const xyzz &p) { return fe_is_zero(p.zz); }
+
+template <class P> H2_HD xyzz xyzz_from_affine(const affine &p) {
+    xyzz r;
+    if (affine_is_identity(p)) return xyzz_identity();
+    r.x = p.x; r.y = p.y; r.zz = fe_one<P>(); r.zzz = fe_one<P>();
+    return r;
+}
+template <class P> H2_HD void xyzz_neg(xyzz &p) { p.y = fe_neg<P>(p.y); }
+template <class P> H2_HD affine affine_neg(const affine &p) {
+    affine r; r.x = p.x; r.y = fe_neg<P>(p.y);   // -(0,0) = (0,0): fe_neg(0) = 0
+    return r;
+}
+
+// 2 * (affine p) -> XYZZ   (mdbl-2008-s-1, a = 0)
+template <class P> H2_HD xyzz xyzz_double_affine(const affine &p) {
+    xyzz r;
+    fe u = fe_dbl<P>(p.y);
+    fe v = fe_sqr<P>(u);
+    fe w = fe_mul<P>(u, v);
+    fe s = fe_mul<P>(p.x, v);
+    fe m = fe_sqr<P>(p.x);
+    m = fe_add<P>(fe_dbl<P>(m), m);
+    r.x = fe_sub<P>(fe_sub<P>(fe_sqr<P>(m), s), s);
+    r.y = fe_sub<P>(fe_mul<P>(m, fe_sub<P>(s, r.x)), fe_mul<P>(w, p.y));
+    r.zz = v; r.zzz = w;
+    return r;
+}
+
+// acc = 2 * acc   (dbl-2008-s-1, a = 0)
+template <class P> H2_HD void xyzz_double(xyzz &a) {
+    if (xyzz_is_identity(a)) return;
+    fe u = fe_dbl<P>(a.y);
+    fe v = fe_sqr<P>(u);
+    fe w = fe_mul<P>(u, v);
+    fe s = fe_mul<P>(a.x, v);
+    fe m = fe_sqr<P>(a.x);
+    m = fe_add<P>(fe_dbl<P>(m), m);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sqr<P>(m), s), s);
+    fe y3 = fe_sub<P>(fe_mul<P>(m, fe_sub<P>(s, x3)), fe_mul<P>(w, a.y));
+    a.x = x3; a.y = y3;
+    a.zz = fe_mul<P>(v, a.zz);
+    a.zzz = fe_mul<P>(w, a.zzz);
+}
+
+// acc += affine p   (madd-2008-s); the hot operation of the bucket accumulation
+template <class P> H2_HD void xyzz_add_mixed(xyzz &a, const affine &p) {
+    if (affine_is_identity(p)) return;
+    if (xyzz_is_identity(a)) { a = xyzz_from_affine<P>(p); return; }
+    fe u2 = fe_mul<P>(p.x, a.zz);
+    fe s2 = fe_mul<P>(p.y, a.zzz);
+    fe pp = fe_sub<P>(u2, a.x);
+    fe r = fe_sub<P>(s2, a.y);
+    if (fe_is_zero(pp)) {
+        if (fe_is_zero(r)) a = xyzz_double_affine<P>(p);   // same point
+        else a = xyzz_identity();                          // opposite points
+        return;
+    }
+    fe pp2 = fe_sqr<P>(pp);
+    fe ppp = fe_mul<P>(pp, pp2);
+    fe q = fe_mul<P>(a.x, pp2);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(r), ppp), q), q);
+    fe y3 = fe_sub<P>(fe_mul<P>(r, fe_sub<P>(q, x3)), fe_mul<P>(a.y, ppp));
+    a.x = x3; a.y = y3;
+    a.zz = fe_mul<P>(a.zz, pp2);
+    a.zzz = fe_mul<P>(a.zzz, ppp);
+}
+
+// acc += b   (add-2008-s)
+template <class P> H2_HD void xyzz_add(xyzz &a, const xyzz &b) {
+    if (xyzz_is_identity(b)) return;
+    if (xyzz_is_identity(a)) { a = b; return; }
+    fe u1 = fe_mul<P>(a.x, b.zz);
+    fe u2 = fe_mul<P>(b.x, a.zz);
+    fe s1 = fe_mul<P>(a.y, b.zzz);
+    fe s2 = fe_mul<P>(b.y, a.zzz);
+    fe pp = fe_sub<P>(u2, u1);
+    fe r = fe_sub<P>(s2, s1);
+    if (fe_is_zero(pp)) {
+        if (fe_is_zero(r)) xyzz_double<P>(a);
+        else a = xyzz_identity();
+        return;
+    }
+    fe pp2 = fe_sqr<P>(pp);
+    fe ppp = fe_mul<P>(pp, pp2);
+    fe q = fe_mul<P>(u1, pp2);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(r), ppp), q), q);
+    fe y3 = fe_sub<P>(fe_mul<P>(r, fe_sub<P>(q, x3)), fe_mul<P>(s1, ppp));
+    a.x = x3; a.y = y3;
+    a.zz = fe_mul<P>(fe_mul<P>(a.zz, b.zz), pp2);
+    a.zzz = fe_mul<P>(fe_mul<P>(a.zzz, b.zzz), ppp);
+}
+
+// XYZZ -> Jacobian without inversion: (X*ZZ, Y*ZZZ, ZZ) since (ZZ)^2 * x = X*ZZ and
+// (ZZ)^3 * y = ZZZ^2 * y = Y*ZZZ.  Identity maps to z = 0 (pasta: (0, 1, 0)-like).
+template <class P> H2_HD jacobian xyzz_to_jacobian(const xyzz &p) {
+    jacobian j;
+    if (xyzz_is_identity(p)) { j.x = fe_zero(); j.y = fe_one<P>(); j.z = fe_zero(); return j; }
+    j.x = fe_mul<P>(p.x, p.zz);
+    j.y = fe_mul<P>(p.y, p.zzz);
+    j.z = p.zz;
+    return j;
+}
+template <class P> H2_HD affine jacobian_to_affine(const jacobian &j) {
+    affine r;
+    if (fe_is_zero(j.z)) { r.x = fe_zero(); r.y = fe_zero(); return r; }
+    fe zi = fe_inv<P>(j.z);
+    fe zi2 = fe_sqr<P>(zi);
+    r.x = fe_mul<P>(j.x, zi2);
+    r.y = fe_mul<P>(j.y, fe_mul<P>(zi2, zi));
+    return r;
+}
+
+// k * p by left-to-right double-and-add; k = 8 x u32 little-endian (canonical integer).
+// Used by the synthetic-input generator and the tests, not by the MSM hot path.
+template <class P> H2_HD xyzz xyzz_scalar_mul(const affine &p, const uint32_t (&k)[8]) {
+    xyzz acc = xyzz_identity();
+    for (int i = 7; i >= 0; i--) {
+        for (int b = 31; b >= 0; b--) {
+            xyzz_double<P>(acc);
+            if ((k[i] >> b) & 1u) xyzz_add_mixed<P>(acc, p);
+        }
+    }
+    return acc;
+}
+
+}  // namespace h2

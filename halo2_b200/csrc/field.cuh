@@ -1,0 +1,300 @@
+// Device field library for the Pasta fields Fp / Fq (K0 in SURVEY.md section 2.1).
+//
+// Replaces the limb arithmetic of the un-vendored crate pasta_curves 0.5.1 that the
+// reference reaches through ff::Field / PrimeField (halo2_proofs/src/arithmetic.rs:4-10,
+// used at :243-246, :289-292 and throughout Bucket::add_assign :37-46).
+//
+// Representation: Montgomery form, R = 2^256, 8 x 32-bit limbs held in registers, always
+// fully reduced to [0, m).  Both moduli have the shape
+//     m = 2^254 + t,  t < 2^126,  limb0 = 1, limbs 4..6 = 0, limb7 = 0x40000000
+// so  -m^-1 mod 2^32 = 0xffffffff (the Montgomery quotient digit is a negation) and the
+// q*m product needs 3 real 32x32 multiplies + one "multiply" by 2^30.
+//
+// Multiplication is CIOS with the product rows split into even/odd 64-bit columns so that
+// every mad.lo.cc / madc.hi.cc pair maps onto one IMAD.WIDE.U32(.X) in SASS and the carry
+// chains never ripple (the sliding window's top limb is fresh every iteration).
+//
+// The same source compiles for the host (g++, no nvcc) with the PTX carry-flag instructions
+// emulated; tests/kernel_emul uses that build to check kernel logic without a GPU.  The
+// product path is the sm_100a build only.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define H2_HD __host__ __device__ __forceinline__
+#define H2_D __device__ __forceinline__
+#else
+#define H2_HD inline
+#define H2_D inline
+// host-only build (tests/kernel_emul): minimal stand-ins for the CUDA vector types
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+#endif
+
+namespace h2 {
+
+// ------------------------------------------------------------------ carry-flag primitives
+namespace ptx {
+#if defined(__CUDA_ARCH__)
+H2_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+H2_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+H2_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+H2_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+H2_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// Host emulation of the PTX CC.CF flag (one per thread).
+static thread_local uint32_t cf_ = 0;
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; cf_ = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + cf_; cf_ = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cf_; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b; cf_ = (uint32_t)(d >> 63); return (uint32_t)d; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b - cf_; cf_ = (uint32_t)(d >> 63); return (uint32_t)d; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cf_; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_lo(a, b) + c; cf_ = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_lo(a, b) + c + cf_; cf_ = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_hi(a, b) + c + cf_; cf_ = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + cf_; }
+#endif
+}  // namespace ptx
+
+// ------------------------------------------------------------------ field parameters
+// Values checked against the reference goldens in tests/test_oracle_golden.py
+// (moduli: halo2_proofs/tests/plonk_api.rs:591-592).
+struct FpParams {   // Pallas base field / Vesta scalar field
+    static constexpr int ID = 0;
+    static constexpr uint32_t M1 = 0x992d30edu, M2 = 0x094cf91bu, M3 = 0x224698fcu;
+    static H2_HD uint32_t one(int i) {   // R mod m
+        constexpr uint32_t v[8] = {0xfffffffdu, 0x34786d38u, 0xe41914adu, 0x992c350bu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
+        return v[i];
+    }
+    static H2_HD uint32_t r2(int i) {    // R^2 mod m
+        constexpr uint32_t v[8] = {0x0000000fu, 0x8c78ecb3u, 0x8b0de0e7u, 0xd7d30dbdu, 0xc3c95d18u, 0x7797a99bu, 0x7b9cb714u, 0x096d41afu};
+        return v[i];
+    }
+};
+struct FqParams {   // Vesta base field / Pallas scalar field
+    static constexpr int ID = 1;
+    static constexpr uint32_t M1 = 0x8c46eb21u, M2 = 0x0994a8ddu, M3 = 0x224698fcu;
+    static H2_HD uint32_t one(int i) {
+        constexpr uint32_t v[8] = {0xfffffffdu, 0x5b2b3e9cu, 0xe3420567u, 0x992c350bu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x3fffffffu};
+        return v[i];
+    }
+    static H2_HD uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0x0000000fu, 0xfc9678ffu, 0x891a16e3u, 0x67bb433du, 0x04ccf590u, 0x7fae2310u, 0x7ccfdaa9u, 0x096d41afu};
+        return v[i];
+    }
+};
+static constexpr uint32_t H2_M7 = 0x40000000u;   // top limb of both moduli
+
+template <class P> H2_HD uint32_t mod_limb(int i) {
+    return i == 0 ? 1u : i == 1 ? P::M1 : i == 2 ? P::M2 : i == 3 ? P::M3 : i == 7 ? H2_M7 : 0u;
+}
+
+// ------------------------------------------------------------------ element type
+struct alignas(16) fe {
+    uint32_t v[8];
+};
+
+H2_HD fe fe_zero() { fe r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+template <class P> H2_HD fe fe_one() { fe r; for (int i = 0; i < 8; i++) r.v[i] = P::one(i); return r; }
+template <class P> H2_HD fe fe_r2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = P::r2(i); return r; }
+
+H2_HD bool fe_is_zero(const fe &a) {
+    uint32_t t = a.v[0];
+    for (int i = 1; i < 8; i++) t |= a.v[i];
+    return t == 0;
+}
+H2_HD bool fe_eq(const fe &a, const fe &b) {
+    uint32_t t = a.v[0] ^ b.v[0];
+    for (int i = 1; i < 8; i++) t |= a.v[i] ^ b.v[i];
+    return t == 0;
+}
+
+// r = a - m if a >= m else a   (a < 2^256)
+template <class P> H2_HD void fe_cond_sub_mod(fe &a) {
+    uint32_t s[8];
+    s[0] = ptx::sub_cc(a.v[0], 1u);
+    s[1] = ptx::subc_cc(a.v[1], P::M1);
+    s[2] = ptx::subc_cc(a.v[2], P::M2);
+    s[3] = ptx::subc_cc(a.v[3], P::M3);
+    s[4] = ptx::subc_cc(a.v[4], 0u);
+    s[5] = ptx::subc_cc(a.v[5], 0u);
+    s[6] = ptx::subc_cc(a.v[6], 0u);
+    s[7] = ptx::subc_cc(a.v[7], H2_M7);
+    uint32_t borrow = ptx::subc(0u, 0u);   // 0xffffffff if a < m
+    for (int i = 0; i < 8; i++) a.v[i] = borrow ? a.v[i] : s[i];
+}
+
+template <class P> H2_HD fe fe_add(const fe &a, const fe &b) {
+    fe r;
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+    for (int i = 1; i < 7; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    r.v[7] = ptx::addc(a.v[7], b.v[7]);    // a + b < 2m < 2^256
+    fe_cond_sub_mod<P>(r);
+    return r;
+}
+template <class P> H2_HD fe fe_dbl(const fe &a) { return fe_add<P>(a, a); }
+
+template <class P> H2_HD fe fe_sub(const fe &a, const fe &b) {
+    fe r;
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+    for (int i = 1; i < 8; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t mask = ptx::subc(0u, 0u);     // all ones if borrow
+    r.v[0] = ptx::add_cc(r.v[0], mask & 1u);
+    r.v[1] = ptx::addc_cc(r.v[1], mask & P::M1);
+    r.v[2] = ptx::addc_cc(r.v[2], mask & P::M2);
+    r.v[3] = ptx::addc_cc(r.v[3], mask & P::M3);
+    r.v[4] = ptx::addc_cc(r.v[4], 0u);
+    r.v[5] = ptx::addc_cc(r.v[5], 0u);
+    r.v[6] = ptx::addc_cc(r.v[6], 0u);
+    r.v[7] = ptx::addc(r.v[7], mask & H2_M7);
+    return r;
+}
+template <class P> H2_HD fe fe_neg(const fe &a) {
+    return fe_sub<P>(fe_zero(), a);
+}
+
+// ------------------------------------------------------------------ Montgomery multiplication
+// One CIOS iteration on the even/odd split accumulator.
+//   ev[k] sits at limb position k      (pairs (0,1)(2,3)(4,5)(6,7))
+//   od[k] sits at limb position k + 1  (pairs (1,2)(3,4)(5,6)(7,8))
+// Adds a * bi, then q * m with q = -ev[0], leaving ev[0] == 0.
+template <class P, bool FIRST> H2_HD void mont_iter(uint32_t (&ev)[8], uint32_t (&od)[8], const fe &a, uint32_t bi) {
+    using namespace ptx;
+    if (FIRST) {
+        for (int k = 0; k < 4; k++) {
+            od[2 * k] = mul_lo(a.v[2 * k + 1], bi);
+            od[2 * k + 1] = mul_hi(a.v[2 * k + 1], bi);
+            ev[2 * k] = mul_lo(a.v[2 * k], bi);
+            ev[2 * k + 1] = mul_hi(a.v[2 * k], bi);
+        }
+    } else {
+        // (the caller has just issued add.cc ev[0] += leftover; its carry enters here)
+        od[0] = madc_lo_cc(a.v[1], bi, od[0]);
+        od[1] = madc_hi_cc(a.v[1], bi, od[1]);
+        od[2] = madc_lo_cc(a.v[3], bi, od[2]);
+        od[3] = madc_hi_cc(a.v[3], bi, od[3]);
+        od[4] = madc_lo_cc(a.v[5], bi, od[4]);
+        od[5] = madc_hi_cc(a.v[5], bi, od[5]);
+        od[6] = madc_lo_cc(a.v[7], bi, od[6]);
+        od[7] = madc_hi(a.v[7], bi, od[7]);          // no carry out: od <= A / 2^32 < 2^256
+        ev[0] = mad_lo_cc(a.v[0], bi, ev[0]);
+        ev[1] = madc_hi_cc(a.v[0], bi, ev[1]);
+        ev[2] = madc_lo_cc(a.v[2], bi, ev[2]);
+        ev[3] = madc_hi_cc(a.v[2], bi, ev[3]);
+        ev[4] = madc_lo_cc(a.v[4], bi, ev[4]);
+        ev[5] = madc_hi_cc(a.v[4], bi, ev[5]);
+        ev[6] = madc_lo_cc(a.v[6], bi, ev[6]);
+        ev[7] = madc_hi_cc(a.v[6], bi, ev[7]);
+        od[7] = addc(od[7], 0u);                     // carry out of position 7 lands on position 8
+    }
+    uint32_t q = 0u - ev[0];
+    // q * m, odd columns: m1 @1, m3 @3, 2^30 @7
+    od[0] = mad_lo_cc(q, P::M1, od[0]);
+    od[1] = madc_hi_cc(q, P::M1, od[1]);
+    od[2] = madc_lo_cc(q, P::M3, od[2]);
+    od[3] = madc_hi_cc(q, P::M3, od[3]);
+    od[4] = addc_cc(od[4], 0u);
+    od[5] = addc_cc(od[5], 0u);
+    od[6] = madc_lo_cc(q, H2_M7, od[6]);
+    od[7] = madc_hi(q, H2_M7, od[7]);
+    // even columns: 1 @0, m2 @2
+    ev[0] = add_cc(ev[0], q);                        // == 0, carry = (old ev[0] != 0)
+    ev[1] = addc_cc(ev[1], 0u);
+    ev[2] = madc_lo_cc(q, P::M2, ev[2]);
+    ev[3] = madc_hi_cc(q, P::M2, ev[3]);
+    ev[4] = addc_cc(ev[4], 0u);
+    ev[5] = addc_cc(ev[5], 0u);
+    ev[6] = addc_cc(ev[6], 0u);
+    ev[7] = addc_cc(ev[7], 0u);
+    od[7] = addc(od[7], 0u);
+}
+
+// Shift the window down one limb: position 0 (== 0) drops out, ev <- od, od <- ev >> 2 limbs,
+// and the left-over ev[1] (new position 0) is folded into the new ev[0]; the carry of that
+// add is consumed by the first madc of the next iteration (position 1 = new od[0]).
+template <class P, bool FIRST> H2_HD void mont_iter_pair(uint32_t (&x)[8], uint32_t (&y)[8], const fe &a, uint32_t b0, uint32_t b1) {
+    // iteration with (ev, od) = (x, y)
+    mont_iter<P, FIRST>(x, y, a, b0);
+    // after shift: ev' = y, od' = {x[2..7], 0, 0}, leftover = x[1]
+    uint32_t left = x[1];
+    for (int k = 0; k < 6; k++) x[k] = x[k + 2];
+    x[6] = 0; x[7] = 0;
+    y[0] = ptx::add_cc(y[0], left);
+    mont_iter<P, false>(y, x, a, b1);
+    // after shift: ev'' = x, od'' = {y[2..7], 0, 0}, leftover = y[1]
+    left = y[1];
+    for (int k = 0; k < 6; k++) y[k] = y[k + 2];
+    y[6] = 0; y[7] = 0;
+    x[0] = ptx::add_cc(x[0], left);
+}
+
+template <class P> H2_HD fe fe_mul(const fe &a, const fe &b) {
+    uint32_t x[8], y[8];
+    mont_iter_pair<P, true>(x, y, a, b.v[0], b.v[1]);
+    mont_iter_pair<P, false>(x, y, a, b.v[2], b.v[3]);
+    mont_iter_pair<P, false>(x, y, a, b.v[4], b.v[5]);
+    mont_iter_pair<P, false>(x, y, a, b.v[6], b.v[7]);
+    // After the last shift the result is ev (x, positions 0..7) + od (y, positions 1..8 with
+    // y[7] == 0 because the value is < 2m < 2^256); x[0] already holds x[0] + leftover and
+    // its carry is still in CC.
+    fe r;
+    r.v[0] = x[0];
+    r.v[1] = ptx::addc_cc(x[1], y[0]);
+    r.v[2] = ptx::addc_cc(x[2], y[1]);
+    r.v[3] = ptx::addc_cc(x[3], y[2]);
+    r.v[4] = ptx::addc_cc(x[4], y[3]);
+    r.v[5] = ptx::addc_cc(x[5], y[4]);
+    r.v[6] = ptx::addc_cc(x[6], y[5]);
+    r.v[7] = ptx::addc(x[7], y[6]);
+    fe_cond_sub_mod<P>(r);
+    return r;
+}
+template <class P> H2_HD fe fe_sqr(const fe &a) { return fe_mul<P>(a, a); }
+
+// canonical <-> Montgomery
+template <class P> H2_HD fe fe_to_mont(const fe &a) { return fe_mul<P>(a, fe_r2<P>()); }
+template <class P> H2_HD fe fe_from_mont(const fe &a) {
+    fe one = fe_zero(); one.v[0] = 1u;
+    return fe_mul<P>(a, one);
+}
+
+// a^(m-2) by square-and-multiply over the fixed exponent (m - 2 = 2^254 + t - 2).
+template <class P> H2_HD fe fe_inv(const fe &a) {
+    fe acc = fe_one<P>();
+    // exponent limbs of m - 2 (limb0 = 0xffffffff after the borrow from limb1)
+    const uint32_t e[8] = {0xffffffffu, P::M1 - 1u, P::M2, P::M3, 0u, 0u, 0u, H2_M7};
+    for (int i = 7; i >= 0; i--) {
+        for (int b = 31; b >= 0; b--) {
+            acc = fe_sqr<P>(acc);
+            if ((e[i] >> b) & 1u) acc = fe_mul<P>(acc, a);
+        }
+    }
+    return acc;
+}
+
+// 128-bit global/shared memory access helpers
+H2_HD fe fe_load(const fe *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fe r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+H2_HD void fe_store(fe *p, const fe &a) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+}  // namespace h2

@@ -1,0 +1,215 @@
+// NTT kernels (K7/K8/K9 in SURVEY.md section 2.1) for Fp / Fq.
+//
+// Computes exactly the butterfly NETWORK of best_fft
+// (/root/reference/halo2_proofs/src/arithmetic.rs:192-295): bit-reversal, twiddles w^i,
+// log_n radix-2 DIT stages with  t = b * tw; b = a - t; a = a + t.  No step assumes
+// w^n = 1 (benches/fft.rs:17 passes a random w), so the output is bit-identical to the
+// reference for ANY omega.
+//
+// Data movement.  The data stays at its natural index j through all passes; the network's
+// "position" p = bitrev(j) is only materialised by the last pass, which stores out[p].
+// Stage s (1-based) pairs positions that differ in bit s-1 of p, i.e. elements that differ
+// in bit log_n-s of j, with twiddle exponent (p mod 2^(s-1)) * 2^(log_n-s).
+// A pass handles `sp` consecutive stages on a tile of R = 2^sp rows x C = 2^logc columns held
+// in shared memory (two uint4 planes, row stride C+1 -> conflict-free for both row-fastest
+// and column-fastest access):
+//   geometry A (not last pass): rows = the sp bits of j being transformed, columns = C
+//       adjacent j (coalesced C*32 B runs); all columns of a tile share their twiddles.
+//   geometry B (last pass): rows = the low sp bits of j (contiguous in memory), columns = C
+//       blocks whose outputs p are adjacent, so the bit-reversed store is coalesced too.
+// Fusions: first pass can zero-pad (coeff_to_extended's resize, poly/domain.rs:248) and
+// multiply element j by in_scale[j mod 3] (distribute_powers_zeta, :357-373, and/or the
+// canonical->Montgomery factor); last pass can multiply output p by out_scale[p mod 3]
+// (ifft divisor :375-383, coset un-scale :303-325, and/or Montgomery->canonical).
+#pragma once
+#include "field.cuh"
+
+namespace h2 {
+
+enum : uint32_t { NTT_FIRST = 1u, NTT_LAST = 2u, NTT_IN_SCALE = 4u, NTT_OUT_SCALE = 8u };
+
+struct NttPassArgs {
+    const fe *in;
+    fe *out;
+    const fe *tw;        // w^i for i < n/2, Montgomery form
+    uint32_t log_n;      // transform size
+    uint32_t s0;         // stages completed before this pass
+    uint32_t sp;         // stages in this pass
+    uint32_t logc;       // log2(columns per tile)
+    uint32_t flags;
+    uint32_t in_log_n;   // elements with j >= 2^in_log_n read as zero (first pass)
+    uint64_t out_len;    // last pass: outputs with p >= out_len are dropped (truncate)
+    fe in_scale[3];
+    fe out_scale[3];
+};
+
+H2_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
+    // bits in [0, 32]
+    if (bits == 0) return 0;
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    x = ((x & 0x33333333u) << 2) | ((x >> 2) & 0x33333333u);
+    x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+    x = ((x & 0x00ff00ffu) << 8) | ((x >> 8) & 0x00ff00ffu);
+    x = (x << 16) | (x >> 16);
+    return x >> (32 - bits);
+}
+
+H2_HD uint32_t ntt_smem_stride(uint32_t logc) { return (1u << logc) + (logc ? 1u : 0u); }
+H2_HD uint32_t ntt_smem_bytes(uint32_t sp, uint32_t logc) { return 2u * 16u * (ntt_smem_stride(logc) << sp); }
+
+H2_HD fe sm_load(const uint4 *sm, uint32_t plane, uint32_t idx) {
+    uint4 lo = sm[idx], hi = sm[plane + idx];
+    fe r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+H2_HD void sm_store(uint4 *sm, uint32_t plane, uint32_t idx, const fe &a) {
+    sm[idx] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    sm[plane + idx] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+template <class P> struct NttPass {
+    // global natural index j of tile element (r, col)
+    static H2_HD uint64_t elem_j(const NttPassArgs &A, uint32_t tile, uint32_t r, uint32_t col) {
+        const uint32_t lo = A.log_n - A.s0 - A.sp;
+        if (A.flags & NTT_LAST) {     // geometry B (lo == 0)
+            uint32_t p_low = (tile << A.logc) | col;
+            uint64_t j_high = bitrev32(p_low, A.s0);
+            return (j_high << A.sp) | r;
+        }
+        uint32_t tiles_per_high = 1u << (lo - A.logc);
+        uint64_t j_high = tile / tiles_per_high;
+        uint64_t jl_block = tile % tiles_per_high;
+        return (j_high << (lo + A.sp)) | ((uint64_t)r << lo) | (jl_block << A.logc) | col;
+    }
+    // low s0 bits of the network position for tile column `col`
+    static H2_HD uint32_t p_low_of(const NttPassArgs &A, uint32_t tile, uint32_t col) {
+        const uint32_t lo = A.log_n - A.s0 - A.sp;
+        if (A.flags & NTT_LAST) return (tile << A.logc) | col;
+        uint32_t j_high = tile >> (lo - A.logc);
+        return bitrev32(j_high, A.s0);
+    }
+
+    static H2_HD void load_phase(const NttPassArgs &A, uint32_t tile, uint32_t tid, uint32_t nthr, uint4 *sm) {
+        const uint32_t R = 1u << A.sp, C = 1u << A.logc, stride = ntt_smem_stride(A.logc), plane = stride << A.sp;
+        const bool geomB = (A.flags & NTT_LAST) != 0;
+        for (uint32_t e = tid; e < R * C; e += nthr) {
+            uint32_t r, col;
+            if (geomB) { r = e & (R - 1); col = e >> A.sp; } else { col = e & (C - 1); r = e >> A.logc; }
+            uint64_t j = elem_j(A, tile, r, col);
+            fe x;
+            if ((A.flags & NTT_FIRST) && (j >> A.in_log_n) != 0) {
+                x = fe_zero();
+            } else {
+                x = fe_load(A.in + j);
+                if ((A.flags & NTT_FIRST) && (A.flags & NTT_IN_SCALE)) x = fe_mul<P>(x, A.in_scale[j % 3]);
+            }
+            sm_store(sm, plane, r * stride + col, x);
+        }
+    }
+
+    // one radix-2 stage; sl = 1..sp is the stage number inside this pass
+    static H2_HD void stage_phase(const NttPassArgs &A, uint32_t tile, uint32_t sl, uint32_t tid, uint32_t nthr, uint4 *sm) {
+        const uint32_t R = 1u << A.sp, C = 1u << A.logc, stride = ntt_smem_stride(A.logc), plane = stride << A.sp;
+        const uint32_t d = A.sp - sl;                    // bit of r that this stage pairs on
+        const uint32_t tw_shift = A.log_n - A.s0 - sl;   // exponent scale 2^(log_n - s)
+        for (uint32_t w = tid; w < (R >> 1) * C; w += nthr) {
+            uint32_t col = w & (C - 1), pr = w >> A.logc;
+            uint32_t r0 = ((pr >> d) << (d + 1)) | (pr & ((1u << d) - 1u));
+            uint32_t r1 = r0 | (1u << d);
+            uint32_t k = bitrev32(r0 >> (d + 1), sl - 1);   // p'' mod 2^(sl-1)
+            uint64_t e = (((uint64_t)k << A.s0) | p_low_of(A, tile, col)) << tw_shift;
+            fe a = sm_load(sm, plane, r0 * stride + col);
+            fe b = sm_load(sm, plane, r1 * stride + col);
+            fe t = (e == 0) ? b : fe_mul<P>(b, fe_load(A.tw + e));   // tw[0] = 1 (arithmetic.rs:229-236)
+            sm_store(sm, plane, r0 * stride + col, fe_add<P>(a, t));
+            sm_store(sm, plane, r1 * stride + col, fe_sub<P>(a, t));
+        }
+    }
+
+    static H2_HD void store_phase(const NttPassArgs &A, uint32_t tile, uint32_t tid, uint32_t nthr, const uint4 *sm) {
+        const uint32_t R = 1u << A.sp, C = 1u << A.logc, stride = ntt_smem_stride(A.logc), plane = stride << A.sp;
+        const bool last = (A.flags & NTT_LAST) != 0;
+        for (uint32_t e = tid; e < R * C; e += nthr) {
+            uint32_t col = e & (C - 1), r = e >> A.logc;
+            fe x = sm_load(sm, plane, r * stride + col);
+            if (last) {
+                uint64_t p = ((uint64_t)bitrev32(r, A.sp) << A.s0) | p_low_of(A, tile, col);
+                if (p >= A.out_len) continue;
+                if (A.flags & NTT_OUT_SCALE) x = fe_mul<P>(x, A.out_scale[p % 3]);
+                fe_store(A.out + p, x);
+            } else {
+                fe_store(A.out + elem_j(A, tile, r, col), x);
+            }
+        }
+    }
+};
+
+// Twiddle table: tw[i] = w^i for i < half.  pow2[b] = w^(2^b) (Montgomery), b < 32.
+// Thread t produces entries [32 t, 32 t + 32).
+template <class P> struct TwiddleGen {
+    static H2_HD void pow2_body(fe *pow2, fe omega, uint32_t count) {
+        fe w = omega;
+        for (uint32_t b = 0; b < count; b++) { fe_store(pow2 + b, w); w = fe_sqr<P>(w); }
+    }
+    static H2_HD void fill_body(fe *tw, const fe *pow2, uint64_t half, uint64_t t) {
+        uint64_t start = t * 32;
+        if (start >= half) return;
+        fe acc = fe_one<P>();
+        uint64_t e = start;
+        for (uint32_t b = 5; e >> b; b++)
+            if ((e >> b) & 1) acc = fe_mul<P>(acc, fe_load(pow2 + b));
+        fe w = fe_load(pow2);
+        uint64_t end = start + 32 < half ? start + 32 : half;
+        for (uint64_t i = start; i < end; i++) { fe_store(tw + i, acc); acc = fe_mul<P>(acc, w); }
+    }
+};
+
+#if defined(__CUDACC__)
+template <class P> __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const NttPassArgs A) {
+    extern __shared__ uint4 h2_ntt_smem[];
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    NttPass<P>::load_phase(A, tile, tid, nthr, h2_ntt_smem);
+    __syncthreads();
+    for (uint32_t sl = 1; sl <= A.sp; sl++) {
+        NttPass<P>::stage_phase(A, tile, sl, tid, nthr, h2_ntt_smem);
+        __syncthreads();
+    }
+    NttPass<P>::store_phase(A, tile, tid, nthr, h2_ntt_smem);
+}
+template <class P> __global__ void twiddle_pow2_kernel(fe *pow2, fe omega, uint32_t count) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) TwiddleGen<P>::pow2_body(pow2, omega, count);
+}
+template <class P> __global__ void twiddle_fill_kernel(fe *tw, const fe *pow2, uint64_t half) {
+    TwiddleGen<P>::fill_body(tw, pow2, half, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+// elementwise conversions used at the ABI boundary
+template <class P> __global__ void fe_scale_kernel(fe *a, uint64_t n, fe c) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fe_store(a + i, fe_mul<P>(fe_load(a + i), c));
+}
+#endif
+
+// Host-side pass planning (shared with the emulation).  Returns the number of passes and fills
+// sp[] / logc[]; tiles hold at most 2^H2_NTT_TILE_LOG elements.
+#define H2_NTT_TILE_LOG 10
+#define H2_NTT_MAX_SP 7
+inline int ntt_plan(uint32_t log_n, uint32_t sp[8], uint32_t logc[8]) {
+    if (log_n == 0) return 0;
+    if (log_n <= H2_NTT_TILE_LOG) { sp[0] = log_n; logc[0] = 0; return 1; }
+    int passes = (int)((log_n + H2_NTT_MAX_SP - 1) / H2_NTT_MAX_SP);
+    uint32_t base = log_n / passes, rem = log_n % passes, s0 = 0;
+    for (int i = 0; i < passes; i++) {
+        sp[i] = base + ((uint32_t)i < rem ? 1u : 0u);
+        uint32_t lo = log_n - s0 - sp[i];
+        uint32_t lc = H2_NTT_TILE_LOG - sp[i];
+        if (lc > 4) lc = 4;
+        if (i == passes - 1) { if (lc > s0) lc = s0; } else { if (lc > lo) lc = lo; }
+        logc[i] = lc;
+        s0 += sp[i];
+    }
+    return passes;
+}
+
+}  // namespace h2
