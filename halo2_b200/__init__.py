@@ -1,0 +1,13 @@
+"""halo2_b200 -- B200-native MSM + NTT engine behind halo2's best_multiexp / best_fft /
+Params::commit* / EvaluationDomain transforms.
+
+The compute path is the sm_100a CUDA library `_lib/libhalo2_b200.so` (C ABI:
+include/halo2_b200.h).  There is no CPU fallback: importing works anywhere, but every
+operation raises `H2Error` unless the library is built and a B200 is visible.
+"""
+from .lib import H2Error, lib_path, load, init, launch_count  # noqa: F401
+from .arithmetic import best_multiexp, best_fft, multiexp_window_bits  # noqa: F401
+from .poly import Params, EvaluationDomain, Blind  # noqa: F401
+
+__all__ = ["H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "best_fft",
+           "multiexp_window_bits", "Params", "EvaluationDomain", "Blind"]

@@ -1,0 +1,53 @@
+"""Host-side mirror of halo2_proofs::arithmetic::{best_multiexp, best_fft}
+(/root/reference/halo2_proofs/src/arithmetic.rs:143-180, :192-255) over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference; elements are numpy uint8
+arrays in canonical little-endian form (32 B scalars, 64 B affine points, identity = zeros),
+i.e. what `to_repr()` / `coordinates()` give on the Rust side.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import lib as _l
+
+
+def multiexp_window_bits(n: int) -> int:
+    """The reference's window choice (arithmetic.rs:146-152); the engine picks its own c
+    (msm_default_window in csrc/msm.cuh) -- the result does not depend on it."""
+    if n < 4:
+        return 1
+    if n < 32:
+        return 3
+    return int(math.ceil(math.log(float(n))))
+
+
+def best_multiexp(coeffs, bases, curve: str = "vesta", repr: int = _l.REPR_CANONICAL) -> np.ndarray:
+    """sum_i coeffs[i] * bases[i] as a Jacobian point (96 bytes x||y||z, z = 0 for the identity).
+
+    Panics (AssertionError) when the lengths differ, like assert_eq! at arithmetic.rs:144."""
+    lib = _l.init()
+    c = _l.as_u8(coeffs, 32)
+    b = _l.as_u8(bases, 64)
+    assert c.shape[0] == b.shape[0], "best_multiexp: coeffs.len() != bases.len()"
+    out = np.zeros(96, dtype=np.uint8)
+    _l.check(lib.h2_msm(_l.CURVE_ID[curve], _l.ptr(c), _l.ptr(b), ctypes.c_size_t(c.shape[0]), int(repr), _l.ptr(out)))
+    return out
+
+
+def best_fft(a, omega, log_n: int, field: str = "fp", repr: int = _l.REPR_CANONICAL) -> np.ndarray:
+    """In-place radix-2 network of arithmetic.rs:192-255 on a (2^log_n, 32) uint8 array.
+
+    Panics (AssertionError) when a.len() != 1 << log_n, like assert_eq! at arithmetic.rs:205.
+    Only G = Scalar is accelerated; the G = curve-point use in Params::new
+    (poly/commitment.rs:81-82) stays on the caller's generic path."""
+    lib = _l.init()
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]):
+        raise ValueError("best_fft operates in place on a C-contiguous uint8 array")
+    arr = a.reshape(-1, 32)
+    assert arr.shape[0] == 1 << log_n, "best_fft: a.len() != 1 << log_n"
+    _l.check(lib.h2_ntt(_l.FIELD_ID[field], _l.ptr(arr), _l.ptr(_l.fe_bytes(omega)), ctypes.c_uint32(log_n), int(repr)))
+    return a

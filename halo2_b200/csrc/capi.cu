@@ -1,0 +1,687 @@
+// C ABI of the engine (include/halo2_b200.h): context, scratch management, kernel launch
+// sequences for the MSM and NTT pipelines, host<->device staging.  No torch types.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/halo2_b200.h"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace h2;
+
+// ------------------------------------------------------------------------------------------------
+// errors, context
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct TwiddleEntry { int field; uint32_t log_n; uint8_t omega[32]; DevBuf buf; uint64_t stamp; };
+struct BaseSet { int curve; size_t n; DevBuf buf; };
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t last_use = nullptr;
+    bool have_last = false;
+    uint32_t window_override = 0;
+    // MSM scratch
+    DevBuf scal_in, bases_in, scal_canon, counts, cursor, refs, keys, bucket_sum, pkey, pstart, pend, ppt, red_sums, red_e,
+        scan_blocks, result, misc;
+    // NTT scratch
+    DevBuf ntt_io, ntt_out, ntt_work, pow2;
+    std::vector<TwiddleEntry *> twiddles;
+    uint64_t tw_stamp = 0;
+    std::map<uint64_t, BaseSet *> bases;
+    uint64_t next_handle = 1;
+};
+static Context g_ctx;
+static std::mutex g_mu;
+static std::atomic<uint64_t> g_launches{0};
+
+#define LAUNCH(kernel, grid, block, smem, stream, ...)                                                   \
+    do {                                                                                                 \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess) return fail(std::string(#kernel) + " launch: " + cudaGetErrorString(e_)); \
+    } while (0)
+
+static int require_ready() {
+    if (!g_ctx.ready) return fail("h2_init has not been called (or failed): no CUDA device bound; there is no CPU fallback");
+    CU(cudaSetDevice(g_ctx.device));
+    return 0;
+}
+// make `s` wait for whatever last used the shared scratch
+static int scratch_acquire(cudaStream_t s) {
+    if (g_ctx.have_last) CU(cudaStreamWaitEvent(s, g_ctx.last_use, 0));
+    return 0;
+}
+static int scratch_release(cudaStream_t s) {
+    CU(cudaEventRecord(g_ctx.last_use, s));
+    g_ctx.have_last = true;
+    return 0;
+}
+
+extern "C" const char *h2_last_error(void) { return g_err.c_str(); }
+extern "C" uint32_t h2_abi_version(void) { return 1; }
+extern "C" uint64_t h2_launch_count(void) { return g_launches.load(); }
+extern "C" int h2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" int h2_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.ready && g_ctx.device == device) return 0;
+    if (g_ctx.ready) return fail("h2_init: already bound to another device (one process per GPU)");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(std::string("h2_init: no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("h2_init: device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("h2_init: this library is built for sm_100a (B200) only");
+    CU(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g_ctx.last_use, cudaEventDisableTiming));
+    g_ctx.device = device;
+    g_ctx.ready = true;
+    return 0;
+}
+extern "C" int h2_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return 0;
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.keys,
+                     &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.red_sums, &g_ctx.red_e,
+                     &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out, &g_ctx.ntt_work, &g_ctx.pow2};
+    for (DevBuf *b : all) b->release();
+    for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
+    g_ctx.twiddles.clear();
+    for (auto &kv : g_ctx.bases) { kv.second->buf.release(); delete kv.second; }
+    g_ctx.bases.clear();
+    cudaEventDestroy(g_ctx.last_use);
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Context();
+    return 0;
+}
+extern "C" int h2_set_window_bits(uint32_t c) {
+    if (c > 24) return fail("h2_set_window_bits: c must be <= 24");
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ctx.window_override = c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels: conversions, generators, self-tests
+// ------------------------------------------------------------------------------------------------
+template <class P> __global__ void convert_kernel(fe *a, uint64_t n, int to_mont) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = fe_load(a + i);
+    fe_store(a + i, to_mont ? fe_to_mont<P>(x) : fe_from_mont<P>(x));
+}
+// affine points: identity (0,0) maps to itself under both conversions
+template <class P> __global__ void convert_points_kernel(affine *a, uint64_t n, int to_mont) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine p = ld_affine(a + i);
+    if (to_mont) { p.x = fe_to_mont<P>(p.x); p.y = fe_to_mont<P>(p.y); }
+    else { p.x = fe_from_mont<P>(p.x); p.y = fe_from_mont<P>(p.y); }
+    st_affine(a + i, p);
+}
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+template <class P> __device__ affine xyzz_to_affine_dev(const xyzz &p) {
+    affine r;
+    if (xyzz_is_identity(p)) { r.x = fe_zero(); r.y = fe_zero(); return r; }
+    fe t = fe_inv<P>(fe_mul<P>(p.zz, p.zzz));
+    r.x = fe_mul<P>(p.x, fe_mul<P>(t, p.zzz));   // X / ZZ
+    r.y = fe_mul<P>(p.y, fe_mul<P>(t, p.zz));    // Y / ZZZ
+    return r;
+}
+template <class P> __global__ void __launch_bounds__(128) gen_points_kernel(affine *out, uint64_t seed, uint64_t first, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = splitmix64(seed ^ splitmix64(first + i)) | 1ULL;
+    affine g;
+    g.x = fe_neg<P>(fe_one<P>());
+    g.y = fe_dbl<P>(fe_one<P>());
+    xyzz acc = xyzz_identity();
+    for (int b = 63; b >= 0; b--) {
+        xyzz_double<P>(acc);
+        if ((s >> b) & 1ULL) xyzz_add_mixed<P>(acc, g);
+    }
+    st_affine(out + i, xyzz_to_affine_dev<P>(acc));
+}
+template <class P> __global__ void test_field_kernel(const fe *a, const fe *b, fe *out, uint64_t n, int op) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = fe_to_mont<P>(fe_load(a + i)), y = fe_to_mont<P>(fe_load(b + i)), r;
+    switch (op) {
+    case 0: r = fe_add<P>(x, y); break;
+    case 1: r = fe_sub<P>(x, y); break;
+    case 2: r = fe_mul<P>(x, y); break;
+    case 3: r = fe_inv<P>(x); break;
+    default: r = fe_sqr<P>(x); break;
+    }
+    fe_store(out + i, fe_from_mont<P>(r));
+}
+template <class P> __global__ void __launch_bounds__(64) test_curve_kernel(const affine *a, const affine *b, affine *out, uint64_t n, int op) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine pa = ld_affine(a + i), pb = ld_affine(b + i);
+    if (!affine_is_identity(pa)) { pa.x = fe_to_mont<P>(pa.x); pa.y = fe_to_mont<P>(pa.y); }
+    xyzz r = xyzz_from_affine<P>(pa);
+    if (op == 0) {
+        if (!affine_is_identity(pb)) { pb.x = fe_to_mont<P>(pb.x); pb.y = fe_to_mont<P>(pb.y); }
+        xyzz t = r;
+        xyzz_add_mixed<P>(r, pb);                         // mixed path
+        xyzz full = xyzz_from_affine<P>(pb);
+        xyzz_add<P>(t, full);                             // full-add path must agree
+        affine r1 = xyzz_to_affine_dev<P>(r), r2 = xyzz_to_affine_dev<P>(t);
+        if (!(fe_eq(r1.x, r2.x) && fe_eq(r1.y, r2.y))) { r1.x = fe_one<P>(); r1.y = fe_zero(); }   // poison
+        r1.x = fe_from_mont<P>(r1.x); r1.y = fe_from_mont<P>(r1.y);
+        st_affine(out + i, r1);
+        return;
+    } else if (op == 1) {
+        xyzz_double<P>(r);
+    } else {
+        uint32_t k[8];
+        for (int j = 0; j < 8; j++) k[j] = pb.x.v[j];
+        r = xyzz_scalar_mul<P>(pa, k);
+    }
+    affine o = xyzz_to_affine_dev<P>(r);
+    o.x = fe_from_mont<P>(o.x); o.y = fe_from_mont<P>(o.y);
+    st_affine(out + i, o);
+}
+// throughput microbenchmark: 4 independent dependent-chains per thread
+template <class P> __global__ void bench_mul_kernel(fe *io, uint32_t iters) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fe a = fe_load(io + 4 * i), b = fe_load(io + 4 * i + 1), c = fe_load(io + 4 * i + 2), d = fe_load(io + 4 * i + 3);
+    for (uint32_t k = 0; k < iters; k++) {
+        a = fe_mul<P>(a, b); b = fe_mul<P>(b, c); c = fe_mul<P>(c, d); d = fe_mul<P>(d, a);
+    }
+    fe_store(io + 4 * i, a); fe_store(io + 4 * i + 1, b); fe_store(io + 4 * i + 2, c); fe_store(io + 4 * i + 3, d);
+}
+template <class P> __global__ void point_sum_kernel(const jacobian *pts, uint32_t g, int canonical, jacobian *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    xyzz acc = xyzz_identity();
+    for (uint32_t i = 0; i < g; i++) {
+        jacobian j;
+        j.x = fe_load(&pts[i].x); j.y = fe_load(&pts[i].y); j.z = fe_load(&pts[i].z);
+        if (canonical) { j.x = fe_to_mont<P>(j.x); j.y = fe_to_mont<P>(j.y); j.z = fe_to_mont<P>(j.z); }
+        xyzz t;
+        if (fe_is_zero(j.z)) t = xyzz_identity();
+        else { t.x = j.x; t.y = j.y; t.zz = fe_sqr<P>(j.z); t.zzz = fe_mul<P>(t.zz, j.z); }
+        xyzz_add<P>(acc, t);
+    }
+    jacobian r = xyzz_to_jacobian<P>(acc);
+    if (canonical) { r.x = fe_from_mont<P>(r.x); r.y = fe_from_mont<P>(r.y); r.z = fe_from_mont<P>(r.z); }
+    st_jacobian(out, r);
+}
+
+static inline uint32_t blocks_for(uint64_t n, uint32_t bs) { return (uint32_t)((n + bs - 1) / bs); }
+
+// ------------------------------------------------------------------------------------------------
+// MSM pipeline
+// ------------------------------------------------------------------------------------------------
+static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s) {
+    const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
+    uint32_t nb = (uint32_t)((n + per_block - 1) / per_block);
+    if (g_ctx.scan_blocks.ensure((size_t)nb * 4 + 16)) return 1;
+    uint32_t *bs = g_ctx.scan_blocks.as<uint32_t>();
+    LAUNCH(scan_block_sums_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs);
+    LAUNCH(scan_single_block_kernel, 1, H2_SCAN_BLOCK, 0, s, bs, nb);
+    LAUNCH(scan_apply_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs);
+    return 0;
+}
+
+template <class P, class PS>
+static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, jacobian *d_out,
+                   int out_canonical, cudaStream_t s) {
+    Context &X = g_ctx;
+    if (n == 0) {   // empty sum = identity
+        jacobian id;
+        id.x = fe_zero(); id.y = out_canonical ? fe_zero() : fe_one<P>(); id.z = fe_zero();
+        if (out_canonical) id.y.v[0] = 1;
+        CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        return 0;
+    }
+    MsmPlan p;
+    if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n);
+    if (c > 24) return fail("msm: window bits > 24");
+    msm_make_plan(p, n, c);
+    if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
+    if (scalars_mont && X.scal_canon.ensure(n * sizeof(fe))) return 1;
+    if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(p.G * 4) || X.refs.ensure(p.max_refs * 4) || X.keys.ensure(p.max_refs * 4) ||
+        X.bucket_sum.ensure(p.G * sizeof(xyzz)) || X.pkey.ensure((p.part_total + 1) * 4) || X.pstart.ensure((p.part_total + 1) * 4) ||
+        X.pend.ensure((p.part_total + 1) * 4) || X.ppt.ensure((p.part_total + 1) * sizeof(xyzz)) ||
+        X.red_sums.ensure(p.red_total * sizeof(xyzz)) || X.red_e.ensure(p.red_total * sizeof(xyzz)))
+        return 1;
+    MsmBuffers M;
+    M.scalars = d_scalars; M.bases = d_bases; M.scalars_mont = scalars_mont ? 1u : 0u;
+    M.scal_canon = X.scal_canon.as<fe>();
+    M.counts = X.counts.as<uint32_t>(); M.cursor = X.cursor.as<uint32_t>();
+    M.refs = X.refs.as<uint32_t>(); M.keys = X.keys.as<uint32_t>();
+    M.bucket_sum = X.bucket_sum.as<xyzz>();
+    M.pkey = X.pkey.as<uint32_t>(); M.pstart = X.pstart.as<uint32_t>(); M.pend = X.pend.as<uint32_t>(); M.ppt = X.ppt.as<xyzz>();
+    M.red_sums = X.red_sums.as<xyzz>(); M.red_e = X.red_e.as<xyzz>();
+    M.win_sums = nullptr; M.result = d_out;
+
+    CU(cudaMemsetAsync(M.counts, 0, (p.G + 1) * 4, s));
+    CU(cudaMemsetAsync(M.cursor, 0, p.G * 4, s));
+    CU(cudaMemsetAsync(M.bucket_sum, 0, p.G * sizeof(xyzz), s));
+    if (p.part_total) CU(cudaMemsetAsync(M.pkey, 0xff, p.part_total * 4, s));
+
+    auto k_hist = msm_hist_kernel<P, PS>;
+    auto k_scatter = msm_scatter_kernel<P, PS>;
+    auto k_accum0 = msm_accum0_kernel<P, PS>;
+    auto k_accumN = msm_accumN_kernel<P, PS>;
+    auto k_reduce = msm_reduce_kernel<P, PS>;
+    auto k_combine = msm_combine_kernel<P, PS>;
+    LAUNCH(k_hist, blocks_for(n, 256), 256, 0, s, p, M);
+    if (exclusive_scan_u32(M.counts, p.G + 1, s)) return 1;
+    LAUNCH(k_scatter, blocks_for(n, 256), 256, 0, s, p, M);
+    LAUNCH(k_accum0, blocks_for(p.acc_threads[0], 128), 128, 0, s, p, M);
+    for (uint32_t lv = 1; lv < p.acc_levels; lv++)
+        LAUNCH(k_accumN, blocks_for(p.acc_threads[lv], 128), 128, 0, s, p, M, lv);
+    for (uint32_t lv = 0; lv < p.red_levels; lv++) {
+        uint32_t m_out = (p.red_m_in[lv] + (1u << p.red_log_l[lv]) - 1) >> p.red_log_l[lv];
+        LAUNCH(k_reduce, blocks_for((uint64_t)p.W * m_out, 128), 128, 0, s, p, M, lv);
+    }
+    LAUNCH(k_combine, 1, 32, 0, s, p, M, (uint32_t)out_canonical);
+    return 0;
+}
+
+static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
+                        jacobian *d_out, int out_canonical, cudaStream_t s) {
+    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, d_out, out_canonical, s);
+    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, d_out, out_canonical, s);
+    return fail("unknown curve id");
+}
+static int convert_points(int curve, affine *d, size_t n, int to_mont, cudaStream_t s) {
+    if (n == 0) return 0;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(convert_points_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, d, (uint64_t)n, to_mont);
+    else LAUNCH(convert_points_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, d, (uint64_t)n, to_mont);
+    return 0;
+}
+
+extern "C" int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, const void *d_bases, size_t n, uint32_t window_bits,
+                          void *d_out_xyz, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (scratch_acquire(s)) return 1;
+    int rc = msm_dispatch(curve, (const fe *)d_scalars, scalars_repr == H2_REPR_MONTGOMERY, (const affine *)d_bases, n, window_bits,
+                          (jacobian *)d_out_xyz, 0, s);
+    if (rc) return rc;
+    return scratch_release(s);
+}
+
+static int msm_host_common(int curve, const void *scalars, size_t n_scalars, const void *extra_scalar, const affine *d_bases,
+                           size_t n_total, int repr, void *out_xyz) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
+    if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
+    int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, 0, X.result.as<jacobian>(),
+                          repr == H2_REPR_CANONICAL, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int h2_msm(int curve, const void *scalars, const void *bases_xy, size_t n, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.bases_in.ensure((n + 1) * sizeof(affine))) return 1;
+    if (n) CU(cudaMemcpyAsync(X.bases_in.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL && convert_points(curve, X.bases_in.as<affine>(), n, 1, s)) return 1;
+    return msm_host_common(curve, scalars, n, nullptr, X.bases_in.as<affine>(), n, repr, out_xyz);
+}
+
+extern "C" int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    BaseSet *b = new BaseSet();
+    b->curve = curve; b->n = n;
+    if (b->buf.ensure((n + 1) * sizeof(affine))) { delete b; return 1; }
+    cudaStream_t s = g_ctx.stream;
+    if (n) CU(cudaMemcpyAsync(b->buf.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), n, 1, s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    uint64_t h = g_ctx.next_handle++;
+    g_ctx.bases[h] = b;
+    *handle = h;
+    return 0;
+}
+extern "C" int h2_bases_release(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.bases.find(handle);
+    if (it == g_ctx.bases.end()) return fail("h2_bases_release: unknown handle");
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    it->second->buf.release();
+    delete it->second;
+    g_ctx.bases.erase(it);
+    return 0;
+}
+extern "C" int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void *extra_scalar, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(handle);
+    if (it == g_ctx.bases.end()) return fail("h2_msm_registered: unknown handle");
+    BaseSet *b = it->second;
+    size_t total = n + (extra_scalar ? 1 : 0);
+    if (total > b->n) return fail("h2_msm_registered: more scalars than registered bases");
+    return msm_host_common(b->curve, scalars, n, extra_scalar, b->buf.as<affine>(), total, repr, out_xyz);
+}
+
+extern "C" int h2_point_sum(int curve, const void *points_xyz, size_t g, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.misc.ensure((g + 1) * sizeof(jacobian)) || X.result.ensure(sizeof(jacobian))) return 1;
+    if (g) CU(cudaMemcpyAsync(X.misc.p, points_xyz, g * sizeof(jacobian), cudaMemcpyHostToDevice, s));
+    int canon = repr == H2_REPR_CANONICAL;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(point_sum_kernel<FpParams>, 1, 32, 0, s, X.misc.as<jacobian>(), (uint32_t)g, canon, X.result.as<jacobian>());
+    else if (curve == H2_CURVE_VESTA) LAUNCH(point_sum_kernel<FqParams>, 1, 32, 0, s, X.misc.as<jacobian>(), (uint32_t)g, canon, X.result.as<jacobian>());
+    else return fail("unknown curve id");
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NTT pipeline
+// ------------------------------------------------------------------------------------------------
+template <class P> static fe host_to_mont(const void *bytes, int repr) {
+    fe x;
+    memcpy(x.v, bytes, 32);
+    return repr == H2_REPR_MONTGOMERY ? x : fe_to_mont<P>(x);
+}
+
+template <class P> static int get_twiddles(int field, const fe &omega_mont, uint32_t log_n, cudaStream_t s, const fe **out) {
+    Context &X = g_ctx;
+    fe canon = fe_from_mont<P>(omega_mont);
+    for (auto *t : X.twiddles)
+        if (t->field == field && t->log_n == log_n && memcmp(t->omega, canon.v, 32) == 0) {
+            t->stamp = ++X.tw_stamp;
+            *out = t->buf.as<fe>();
+            return 0;
+        }
+    TwiddleEntry *e = nullptr;
+    if (X.twiddles.size() >= 8) {   // evict least recently used
+        size_t victim = 0;
+        for (size_t i = 1; i < X.twiddles.size(); i++)
+            if (X.twiddles[i]->stamp < X.twiddles[victim]->stamp) victim = i;
+        e = X.twiddles[victim];
+        X.twiddles.erase(X.twiddles.begin() + victim);
+        CU(cudaStreamSynchronize(s));
+    } else e = new TwiddleEntry();
+    uint64_t half = log_n ? (1ull << (log_n - 1)) : 1;
+    if (e->buf.ensure(half * sizeof(fe)) || X.pow2.ensure(64 * sizeof(fe))) { delete e; return 1; }
+    e->field = field; e->log_n = log_n; memcpy(e->omega, canon.v, 32); e->stamp = ++X.tw_stamp;
+    LAUNCH(twiddle_pow2_kernel<P>, 1, 32, 0, s, X.pow2.as<fe>(), omega_mont, log_n ? log_n : 1u);
+    LAUNCH(twiddle_fill_kernel<P>, blocks_for((half + 31) / 32, 128), 128, 0, s, e->buf.as<fe>(), X.pow2.as<fe>(), half);
+    X.twiddles.push_back(e);
+    *out = e->buf.as<fe>();
+    return 0;
+}
+
+struct NttScales {
+    bool in_scale = false, out_scale = false;
+    fe in_s[3], out_s[3];
+};
+
+// d_in: 2^in_log_n elements; d_out: min(out_len, 2^log_n) elements written.  d_out may alias d_in.
+template <class P>
+static int ntt_run(int field, const fe *d_in, uint32_t in_log_n, fe *d_out, uint32_t log_n, const fe &omega_mont, const NttScales &sc,
+                   uint64_t out_len, cudaStream_t s) {
+    Context &X = g_ctx;
+    if (log_n > 30) return fail("ntt: log_n > 30 not supported");
+    uint64_t n = 1ull << log_n;
+    const fe *tw = nullptr;
+    if (get_twiddles<P>(field, omega_mont, log_n, s, &tw)) return 1;
+    uint32_t sp[8], logc[8];
+    int passes = ntt_plan(log_n, sp, logc);
+    if (passes == 0) {   // n == 1: the network is empty; only the scalings apply
+        sp[0] = 0; logc[0] = 0; passes = 1;
+    }
+    if (passes > 1 && X.ntt_work.ensure(n * sizeof(fe))) return 1;
+    uint32_t s0 = 0;
+    for (int i = 0; i < passes; i++) {
+        NttPassArgs A;
+        A.in = i == 0 ? d_in : X.ntt_work.as<fe>();
+        A.out = i == passes - 1 ? d_out : X.ntt_work.as<fe>();
+        A.tw = tw; A.log_n = log_n; A.s0 = s0; A.sp = sp[i]; A.logc = logc[i];
+        A.flags = 0;
+        if (i == 0) A.flags |= NTT_FIRST | (sc.in_scale ? NTT_IN_SCALE : 0u);
+        if (i == passes - 1) A.flags |= NTT_LAST | (sc.out_scale ? NTT_OUT_SCALE : 0u);
+        A.in_log_n = in_log_n; A.out_len = out_len;
+        for (int k = 0; k < 3; k++) { A.in_scale[k] = sc.in_s[k]; A.out_scale[k] = sc.out_s[k]; }
+        uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
+        uint32_t smem = ntt_smem_bytes(sp[i], logc[i]);
+        LAUNCH(ntt_pass_kernel<P>, tiles, 256, smem, s, A);
+        s0 += sp[i];
+    }
+    return 0;
+}
+
+// Builds the in/out scale constants.  data_repr is the encoding of the data entering and leaving.
+//   zeta_in  != null : multiply element j by zeta^(j mod 3)            (coeff_to_extended)
+//   divisor  != null : multiply every output by divisor                (ifft)
+//   zeta_out != null : multiply output p by [1, zeta^2, zeta][p mod 3] (extended_to_coeff)
+template <class P>
+static NttScales make_scales(int data_repr, const fe *zeta_in, const fe *divisor, const fe *zeta_out) {
+    NttScales sc;
+    fe one = fe_one<P>();
+    fe in_c[3] = {one, one, one}, out_c[3] = {one, one, one};
+    bool in_needed = false, out_needed = false;
+    if (zeta_in) { in_c[1] = *zeta_in; in_c[2] = fe_sqr<P>(*zeta_in); in_needed = true; }
+    if (divisor) { for (int k = 0; k < 3; k++) out_c[k] = *divisor; out_needed = true; }
+    if (zeta_out) { out_c[1] = fe_mul<P>(out_c[1], fe_sqr<P>(*zeta_out)); out_c[2] = fe_mul<P>(out_c[2], *zeta_out); out_needed = true; }
+    if (data_repr == H2_REPR_CANONICAL) {
+        // canonical -> Montgomery on the way in:  mont_mul(a, c R^2) = a c R
+        for (int k = 0; k < 3; k++) in_c[k] = fe_mul<P>(in_c[k], fe_r2<P>());
+        // Montgomery -> canonical on the way out: mont_mul(x R, c) = x c
+        for (int k = 0; k < 3; k++) out_c[k] = fe_from_mont<P>(out_c[k]);
+        in_needed = out_needed = true;
+    }
+    sc.in_scale = in_needed; sc.out_scale = out_needed;
+    for (int k = 0; k < 3; k++) { sc.in_s[k] = in_c[k]; sc.out_s[k] = out_c[k]; }
+    return sc;
+}
+
+template <class P>
+static int ntt_host(int field, int mode, const void *a_in, uint32_t in_log_n, uint32_t log_n, const void *omega, const void *zeta,
+                    const void *divisor, size_t out_len, void *out, int repr) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    uint64_t n = 1ull << log_n, n_in = 1ull << in_log_n;
+    if (out_len > n) out_len = n;
+    if (X.ntt_io.ensure(n_in * sizeof(fe)) || X.ntt_out.ensure(n * sizeof(fe))) return 1;
+    fe w = host_to_mont<P>(omega, repr), z, d;
+    if (zeta) z = host_to_mont<P>(zeta, repr);
+    if (divisor) d = host_to_mont<P>(divisor, repr);
+    NttScales sc = make_scales<P>(repr, mode == 2 ? &z : nullptr, (mode == 1 || mode == 3) ? &d : nullptr, mode == 3 ? &z : nullptr);
+    CU(cudaMemcpyAsync(X.ntt_io.p, a_in, n_in * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (ntt_run<P>(field, X.ntt_io.as<fe>(), in_log_n, X.ntt_out.as<fe>(), log_n, w, sc, out_len, s)) return 1;
+    CU(cudaMemcpyAsync(out, X.ntt_out.p, out_len * sizeof(fe), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+static int ntt_host_dispatch(int field, int mode, const void *a_in, uint32_t in_log_n, uint32_t log_n, const void *omega, const void *zeta,
+                             const void *divisor, size_t out_len, void *out, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (log_n > 30 || in_log_n > log_n) return fail("ntt: bad sizes");
+    if (field == H2_FIELD_FP) return ntt_host<FpParams>(field, mode, a_in, in_log_n, log_n, omega, zeta, divisor, out_len, out, repr);
+    if (field == H2_FIELD_FQ) return ntt_host<FqParams>(field, mode, a_in, in_log_n, log_n, omega, zeta, divisor, out_len, out, repr);
+    return fail("unknown field id");
+}
+extern "C" int h2_ntt(int field, void *a, const void *omega, uint32_t log_n, int repr) {
+    return ntt_host_dispatch(field, 0, a, log_n, log_n, omega, nullptr, nullptr, (size_t)1 << log_n, a, repr);
+}
+extern "C" int h2_intt_scaled(int field, void *a, const void *omega_inv, const void *divisor, uint32_t log_n, int repr) {
+    return ntt_host_dispatch(field, 1, a, log_n, log_n, omega_inv, nullptr, divisor, (size_t)1 << log_n, a, repr);
+}
+extern "C" int h2_coeff_to_extended(int field, const void *a, uint32_t k, uint32_t ext_k, const void *zeta, const void *ext_omega,
+                                    void *out, int repr) {
+    return ntt_host_dispatch(field, 2, a, k, ext_k, ext_omega, zeta, nullptr, (size_t)1 << ext_k, out, repr);
+}
+extern "C" int h2_extended_to_coeff(int field, const void *a, uint32_t ext_k, const void *ext_omega_inv, const void *ext_divisor,
+                                    const void *zeta, size_t out_len, void *out, int repr) {
+    return ntt_host_dispatch(field, 3, a, ext_k, ext_k, ext_omega_inv, zeta, ext_divisor, out_len, out, repr);
+}
+extern "C" int h2_ntt_dev(int field, const void *d_in, void *d_out, const void *omega, int omega_repr, uint32_t log_n, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (scratch_acquire(s)) return 1;
+    NttScales sc;   // Montgomery in, Montgomery out, no scaling
+    int rc;
+    if (field == H2_FIELD_FP) rc = ntt_run<FpParams>(field, (const fe *)d_in, log_n, (fe *)d_out, log_n, host_to_mont<FpParams>(omega, omega_repr), sc, 1ull << log_n, s);
+    else if (field == H2_FIELD_FQ) rc = ntt_run<FqParams>(field, (const fe *)d_in, log_n, (fe *)d_out, log_n, host_to_mont<FqParams>(omega, omega_repr), sc, 1ull << log_n, s);
+    else return fail("unknown field id");
+    if (rc) return rc;
+    return scratch_release(s);
+}
+extern "C" int h2_ntt_clear_cache(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaDeviceSynchronize();
+    for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
+    g_ctx.twiddles.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utilities
+// ------------------------------------------------------------------------------------------------
+extern "C" int h2_dev_gen_points(int curve, uint64_t seed, uint64_t first, size_t n, void *d_out, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(gen_points_kernel<FpParams>, blocks_for(n, 128), 128, 0, s, (affine *)d_out, seed, first, (uint64_t)n);
+    else if (curve == H2_CURVE_VESTA) LAUNCH(gen_points_kernel<FqParams>, blocks_for(n, 128), 128, 0, s, (affine *)d_out, seed, first, (uint64_t)n);
+    else return fail("unknown curve id");
+    return 0;
+}
+extern "C" int h2_dev_convert(int field, void *d_a, size_t n, int to_montgomery, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    if (field == H2_FIELD_FP) LAUNCH(convert_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, (fe *)d_a, (uint64_t)n, to_montgomery);
+    else if (field == H2_FIELD_FQ) LAUNCH(convert_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, (fe *)d_a, (uint64_t)n, to_montgomery);
+    else return fail("unknown field id");
+    return 0;
+}
+extern "C" int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.misc.ensure(3 * n * sizeof(fe) + 64)) return 1;
+    fe *da = X.misc.as<fe>(), *db = da + n, *dout = db + n;
+    CU(cudaMemcpyAsync(da, a, n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(db, b, n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (field == H2_FIELD_FP) LAUNCH(test_field_kernel<FpParams>, blocks_for(n, 128), 128, 0, s, da, db, dout, (uint64_t)n, op);
+    else LAUNCH(test_field_kernel<FqParams>, blocks_for(n, 128), 128, 0, s, da, db, dout, (uint64_t)n, op);
+    CU(cudaMemcpyAsync(out, dout, n * sizeof(fe), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int h2_test_curve_op(int curve, int op, const void *a_xy, const void *b_xy, size_t n, void *out_xy) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.misc.ensure(3 * n * sizeof(affine) + 64)) return 1;
+    affine *da = X.misc.as<affine>(), *db = da + n, *dout = db + n;
+    CU(cudaMemcpyAsync(da, a_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(db, b_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
+    if (curve == H2_CURVE_PALLAS) LAUNCH(test_curve_kernel<FpParams>, blocks_for(n, 64), 64, 0, s, da, db, dout, (uint64_t)n, op);
+    else LAUNCH(test_curve_kernel<FqParams>, blocks_for(n, 64), 64, 0, s, da, db, dout, (uint64_t)n, op);
+    CU(cudaMemcpyAsync(out_xy, dout, n * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_t blocks, uint32_t iters, float *ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    size_t threads = (size_t)threads_per_block * blocks;
+    if (X.misc.ensure(threads * 4 * sizeof(fe))) return 1;
+    CU(cudaMemsetAsync(X.misc.p, 0x11, threads * 4 * sizeof(fe), s));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {   // first repetition warms up
+        CU(cudaEventRecord(e0, s));
+        if (field == H2_FIELD_FP) LAUNCH(bench_mul_kernel<FpParams>, blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        else LAUNCH(bench_mul_kernel<FqParams>, blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        CU(cudaEventRecord(e1, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    CU(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return scratch_release(s);
+}

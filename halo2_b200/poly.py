@@ -1,0 +1,146 @@
+"""Host-side mirror of poly::commitment::Params::{commit, commit_lagrange}
+(/root/reference/halo2_proofs/src/poly/commitment.rs:119-150) and
+poly::EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff}
+(poly/domain.rs:40-146, :227-255, :303-325) over the C ABI.
+
+The domain constants are derived on the host exactly as domain.rs:40-146 does (they are a few
+field elements); the transforms run on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import lib as _l
+
+FIELDS = {
+    "fp": 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001,
+    "fq": 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001,
+}
+S = 32  # two-adicity of both fields
+
+
+class Blind:
+    """poly/commitment.rs:210-216: newtype over a scalar; default = 1."""
+
+    def __init__(self, value: int = 1):
+        self.value = int(value)
+
+
+class Params:
+    """poly/commitment.rs:26-33.  g / g_lagrange / w are uploaded once and stay resident in HBM
+    (they are immutable for the life of a Params); commit / commit_lagrange only ship the
+    polynomial.  Generator DERIVATION (Params::new's hash-to-curve, :38-114) is the caller's:
+    pass the generators in, e.g. as read by Params::read (:185-205)."""
+
+    def __init__(self, curve: str, k: int, g, g_lagrange, w, u=None):
+        assert k < 32  # commitment.rs:41
+        self.curve, self.k, self.n = curve, k, 1 << k
+        self.g = _l.as_u8(g, 64)
+        self.g_lagrange = _l.as_u8(g_lagrange, 64)
+        self.w = _l.as_u8(w, 64)
+        self.u = None if u is None else _l.as_u8(u, 64)
+        assert self.g.shape[0] == self.n and self.g_lagrange.shape[0] == self.n
+        lib = _l.init()
+        self._h_g = ctypes.c_uint64(0)
+        self._h_gl = ctypes.c_uint64(0)
+        cid = _l.CURVE_ID[curve]
+        both = np.concatenate([self.g, self.w])            # tmp_bases = g ++ [w]  (:126-127)
+        _l.check(lib.h2_bases_register(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL, ctypes.byref(self._h_g)))
+        both = np.concatenate([self.g_lagrange, self.w])   # g_lagrange ++ [w]     (:146-147)
+        _l.check(lib.h2_bases_register(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL, ctypes.byref(self._h_gl)))
+
+    def _commit(self, handle, poly, r: Blind) -> np.ndarray:
+        p = _l.as_u8(poly, 32)
+        assert p.shape[0] == self.n, "polynomial length != params.n"
+        out = np.zeros(96, dtype=np.uint8)
+        _l.check(_l.init().h2_msm_registered(handle, _l.ptr(p), ctypes.c_size_t(self.n), _l.ptr(_l.fe_bytes(r.value)),
+                                              _l.REPR_CANONICAL, _l.ptr(out)))
+        return out
+
+    def commit(self, poly, r: Blind) -> np.ndarray:
+        """<poly, g> + r * w   (commitment.rs:119-130)."""
+        return self._commit(self._h_g, poly, r)
+
+    def commit_lagrange(self, poly, r: Blind) -> np.ndarray:
+        """<poly, g_lagrange> + r * w   (commitment.rs:135-150)."""
+        return self._commit(self._h_gl, poly, r)
+
+    def close(self) -> None:
+        lib = _l.load()
+        for h in (self._h_g, self._h_gl):
+            if h.value:
+                lib.h2_bases_release(h)
+                h.value = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EvaluationDomain:
+    """poly/domain.rs:20-146.  `zeta` is F::ZETA (domain.rs:85): pasta_curves' choice of cube root
+    is not pinned by any in-tree golden, so the caller supplies it."""
+
+    def __init__(self, field: str, j: int, k: int, zeta: int):
+        m = FIELDS[field]
+        self.field, self.m, self.k, self.n = field, m, k, 1 << k
+        self.quotient_poly_degree = j - 1
+        ext_k = k
+        while (1 << ext_k) < self.n * self.quotient_poly_degree:
+            ext_k += 1
+        assert ext_k <= S  # domain.rs:56
+        self.extended_k = ext_k
+        ew = pow(5, (m - 1) >> S, m)  # ROOT_OF_UNITY
+        for _ in range(ext_k, S):
+            ew = ew * ew % m
+        self.extended_omega = ew
+        w = ew
+        for _ in range(k, ext_k):
+            w = w * w % m
+        self.omega = w
+        self.omega_inv = pow(w, m - 2, m)
+        self.extended_omega_inv = pow(ew, m - 2, m)
+        assert pow(zeta, 3, m) == 1 and zeta != 1, "zeta must be a primitive cube root of unity"
+        self.g_coset = zeta
+        self.g_coset_inv = zeta * zeta % m
+        self.ifft_divisor = pow((1 << k) % m, m - 2, m)
+        self.extended_ifft_divisor = pow((1 << ext_k) % m, m - 2, m)
+
+    def extended_len(self) -> int:
+        return 1 << self.extended_k
+
+    def lagrange_to_coeff(self, a) -> np.ndarray:
+        """domain.rs:227-237 (+ ifft :375-383)."""
+        arr = _l.as_u8(a, 32).copy()
+        assert arr.shape[0] == 1 << self.k
+        _l.check(_l.init().h2_intt_scaled(_l.FIELD_ID[self.field], _l.ptr(arr), _l.ptr(_l.fe_bytes(self.omega_inv)),
+                                          _l.ptr(_l.fe_bytes(self.ifft_divisor)), ctypes.c_uint32(self.k), _l.REPR_CANONICAL))
+        return arr
+
+    def coeff_to_extended(self, a) -> np.ndarray:
+        """domain.rs:241-255: zeta-scale, zero-pad and transform, fused in the first NTT pass."""
+        arr = _l.as_u8(a, 32)
+        assert arr.shape[0] == 1 << self.k
+        out = np.zeros((self.extended_len(), 32), dtype=np.uint8)
+        _l.check(_l.init().h2_coeff_to_extended(_l.FIELD_ID[self.field], _l.ptr(arr), ctypes.c_uint32(self.k),
+                                                ctypes.c_uint32(self.extended_k), _l.ptr(_l.fe_bytes(self.g_coset)),
+                                                _l.ptr(_l.fe_bytes(self.extended_omega)), _l.ptr(out), _l.REPR_CANONICAL))
+        return out
+
+    def extended_to_coeff(self, a) -> np.ndarray:
+        """domain.rs:303-325: inverse transform, coset un-scale and truncate, fused in the last pass."""
+        arr = _l.as_u8(a, 32)
+        assert arr.shape[0] == self.extended_len()
+        out_len = self.n * self.quotient_poly_degree
+        out = np.zeros((out_len, 32), dtype=np.uint8)
+        _l.check(_l.init().h2_extended_to_coeff(_l.FIELD_ID[self.field], _l.ptr(arr), ctypes.c_uint32(self.extended_k),
+                                                _l.ptr(_l.fe_bytes(self.extended_omega_inv)),
+                                                _l.ptr(_l.fe_bytes(self.extended_ifft_divisor)),
+                                                _l.ptr(_l.fe_bytes(self.g_coset)), ctypes.c_size_t(out_len), _l.ptr(out),
+                                                _l.REPR_CANONICAL))
+        return out

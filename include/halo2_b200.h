@@ -1,0 +1,123 @@
+/*
+ * halo2_b200 -- C ABI of the B200-native MSM + NTT engine for the halo2 prover hot path.
+ *
+ * The reference (zcash/halo2, pure Rust) has no FFI: the boundary is four generic Rust
+ * functions.  Each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference/halo2_proofs/src).  INTEGRATION.md shows the Rust
+ * `halo2-b200-sys` binding and the patched arithmetic.rs dispatch a maintainer would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All functions return 0 on success, non-zero on error;
+ *     h2_last_error() gives the message (thread-local).  The Rust shim panics on non-zero,
+ *     preserving the reference's assert!/panic! error behaviour (arithmetic.rs:144,205).
+ *   - Field element = 32 bytes = 4 x u64 little-endian limbs.  `repr` selects the encoding:
+ *       H2_REPR_CANONICAL   the integer itself (ff::PrimeField::to_repr, arithmetic.rs:77)
+ *       H2_REPR_MONTGOMERY  x * 2^256 mod m (pasta_curves' in-memory form: zero-copy path)
+ *   - Affine point = x || y (64 bytes); the identity is 64 zero bytes
+ *     (book/src/background/curves.md:226-230).  Results are Jacobian x || y || z (96 bytes,
+ *     the layout of pasta's Ep/Eq); identity has z = 0.  Only the group element is defined
+ *     (the reference compares with == on C::Curve, arithmetic.rs:457).
+ *   - curve: H2_CURVE_PALLAS = EpAffine (coordinates Fp, scalars Fq),
+ *            H2_CURVE_VESTA  = EqAffine (coordinates Fq, scalars Fp).
+ *   - Thread-safe and re-entrant (BatchVerifier calls commit_lagrange from many rayon
+ *     workers, plonk/verifier/batch.rs:97-110): calls are serialised on an internal lock.
+ *   - There is NO CPU fallback: every function fails if no CUDA device is usable.
+ *   - Functions suffixed _dev take CUDA device pointers (Montgomery form) and a cudaStream_t
+ *     (passed as void*); they do not synchronise.  The others take host pointers, copy in
+ *     and out, and return when the result is in the caller's buffer.
+ */
+#ifndef HALO2_B200_H
+#define HALO2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { H2_CURVE_PALLAS = 0, H2_CURVE_VESTA = 1 };
+enum { H2_FIELD_FP = 0, H2_FIELD_FQ = 1 };
+enum { H2_REPR_CANONICAL = 0, H2_REPR_MONTGOMERY = 1 };
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* Binds the engine to CUDA device `device` (one process per GPU).  Idempotent. */
+int h2_init(int device);
+int h2_shutdown(void);
+const char *h2_last_error(void);
+int h2_device_count(void);
+/* ABI version of this header (bumped on incompatible change). */
+uint32_t h2_abi_version(void);
+
+/* ---- MSM: replaces best_multiexp, arithmetic.rs:143-180 ------------------------------------ */
+/* out = sum_i scalars[i] * bases[i].  Caller guarantees both arrays hold n entries
+ * (the shim asserts coeffs.len() == bases.len() like arithmetic.rs:144). */
+int h2_msm(int curve, const void *scalars, const void *bases_xy, size_t n, int repr, void *out_xyz);
+
+/* Params::{g, g_lagrange} ++ [w] are immutable for the life of a Params (poly/commitment.rs:26-33):
+ * upload once, commit many times.  Replaces the per-call Vec copies of commit/commit_lagrange
+ * (poly/commitment.rs:119-150). */
+int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle);
+int h2_bases_release(uint64_t handle);
+/* sum_{i<n} scalars[i] * bases[i]  (+ extra_scalar[0] * bases[n] when extra_scalar != NULL):
+ * commit(poly, r) = h2_msm_registered(h(g ++ [w]), poly, n, &r, ...). */
+int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void *extra_scalar, int repr,
+                      void *out_xyz);
+
+/* Window size override for the sweep in BASELINE.json config 3 (0 = automatic). */
+int h2_set_window_bits(uint32_t c);
+
+/* Device-resident MSM: d_scalars (n x 32 B, `scalars_repr`), d_bases (n x 64 B, Montgomery),
+ * d_out_xyz (96 B, Montgomery).  window_bits 0 = automatic. */
+int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, const void *d_bases, size_t n,
+               uint32_t window_bits, void *d_out_xyz, void *stream);
+
+/* Sum of g Jacobian points (host, 96 B each): the combine step after the multi-GPU
+ * all-gather of per-shard partial results. */
+int h2_point_sum(int curve, const void *points_xyz, size_t g, int repr, void *out_xyz);
+
+/* ---- NTT: replaces best_fft for G = Scalar, arithmetic.rs:192-295 --------------------------- */
+/* In-place radix-2 network on 2^log_n elements with the given omega (any field element,
+ * not necessarily a root of unity -- benches/fft.rs:17). */
+int h2_ntt(int field, void *a, const void *omega, uint32_t log_n, int repr);
+/* EvaluationDomain::ifft (poly/domain.rs:375-383) == lagrange_to_coeff (:227-237):
+ * best_fft with omega_inv, then a[i] *= divisor. */
+int h2_intt_scaled(int field, void *a, const void *omega_inv, const void *divisor, uint32_t log_n, int repr);
+/* EvaluationDomain::coeff_to_extended (poly/domain.rs:241-255): a has 2^k elements, out 2^ext_k.
+ * zeta = F::ZETA (g_coset, :85). */
+int h2_coeff_to_extended(int field, const void *a, uint32_t k, uint32_t ext_k, const void *zeta,
+                         const void *ext_omega, void *out, int repr);
+/* EvaluationDomain::extended_to_coeff (poly/domain.rs:303-325): a has 2^ext_k elements,
+ * out receives the first out_len (= n * quotient_poly_degree) coefficients. */
+int h2_extended_to_coeff(int field, const void *a, uint32_t ext_k, const void *ext_omega_inv,
+                         const void *ext_divisor, const void *zeta, size_t out_len, void *out, int repr);
+
+/* Device-resident NTT on Montgomery data; omega is a HOST pointer in `omega_repr`.
+ * d_out may equal d_in.  mode: 0 = plain, see the host variants for the scaled forms. */
+int h2_ntt_dev(int field, const void *d_in, void *d_out, const void *omega, int omega_repr, uint32_t log_n,
+               void *stream);
+/* Drops cached twiddle tables (the next call rebuilds them: "cold" timing). */
+int h2_ntt_clear_cache(void);
+
+/* ---- utilities for synthetic workloads and the tests ---------------------------------------- */
+/* d_out[i] = [s_i] * (-1, 2) for pseudo-random 64-bit s_i derived from seed (distinct points),
+ * affine Montgomery coordinates; i in [first, first + n). */
+int h2_dev_gen_points(int curve, uint64_t seed, uint64_t first, size_t n, void *d_out, void *stream);
+/* In-place canonical <-> Montgomery conversion of n field elements on the device. */
+int h2_dev_convert(int field, void *d_a, size_t n, int to_montgomery, void *stream);
+/* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
+ * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */
+int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out);
+/* out[i] = affine(a[i] + b[i]) (op 0), affine(2 a[i]) (op 1), affine(k[i] * a[i]) with b = 32-byte
+ * scalars padded to 64 B (op 2); canonical affine, host buffers. */
+int h2_test_curve_op(int curve, int op, const void *a_xy, const void *b_xy, size_t n, void *out_xy);
+/* Times `iters` dependent field multiplications per thread over `threads` threads; returns
+ * elapsed milliseconds in *ms (microbenchmark for the roofline discussion in DESIGN.md). */
+int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_t blocks, uint32_t iters, float *ms);
+/* Number of kernels launched by the engine since h2_init (bench.py's gpu_launches). */
+uint64_t h2_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALO2_B200_H */

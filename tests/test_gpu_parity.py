@@ -1,0 +1,299 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bit-exact (integer arithmetic): scalars compare as canonical 32-byte
+elements, MSM results as affine canonical bytes.  Mirrors SURVEY.md section 4.1."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cref, pasta  # noqa: E402
+from tests.poseidon_kat import permute  # noqa: E402
+
+SEED = 0x48414C4F32
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import halo2_b200
+    from halo2_b200 import lib as L
+    L.init()
+    return halo2_b200
+
+
+def _field_op(field, op, a, b=None):
+    from halo2_b200 import lib as L
+    lib = L.init()
+    a = cref.ints_to_bytes(a)
+    b = cref.ints_to_bytes(b if b is not None else [0] * len(a))
+    out = np.zeros_like(a)
+    L.check(lib.h2_test_field_op(L.FIELD_ID[field], op, L.ptr(a), L.ptr(b), ctypes.c_size_t(a.shape[0]), L.ptr(out)))
+    return cref.bytes_to_ints(out)
+
+
+def _curve_op(curve, op, a, b):
+    from halo2_b200 import lib as L
+    lib = L.init()
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    out = np.zeros_like(a)
+    L.check(lib.h2_test_curve_op(L.CURVE_ID[curve], op, L.ptr(a), L.ptr(b), ctypes.c_size_t(a.shape[0]), L.ptr(out)))
+    return out
+
+
+def _affine(curve, xyz):
+    return cref.bytes_to_affine(cref.jac_to_affine(curve, xyz))
+
+
+# ------------------------------------------------------------------------------------------ K0
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_device_field_ops(eng, field):
+    m = pasta.FIELDS[field]
+    xs = pasta.gen_scalars(field, SEED, 2000) + [0, 1, 2, m - 1, m - 2, 1 << 254, (1 << 254) - 1, m - (1 << 32),
+                                                 0xFFFFFFFF, 1 << 32, (1 << 224) - 1, m >> 1, (1 << 255) % m]
+    ys = xs[7:] + xs[:7]
+    assert _field_op(field, 0, xs, ys) == [(a + b) % m for a, b in zip(xs, ys)]
+    assert _field_op(field, 1, xs, ys) == [(a - b) % m for a, b in zip(xs, ys)]
+    assert _field_op(field, 2, xs, ys) == [a * b % m for a, b in zip(xs, ys)]
+    assert _field_op(field, 4, xs) == [a * a % m for a in xs]
+    nz = [x for x in xs if x][:300]
+    assert _field_op(field, 3, nz) == [pow(a, m - 2, m) for a in nz]
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_device_poseidon_kat(eng, goldens, field):
+    """halo2_poseidon/src/test_vectors.rs reproduced with the DEVICE add/mul (field-layer KAT)."""
+    g = goldens["poseidon"][field]
+    rc = [int(x, 16) for x in g["round_constants"]]
+    mds = [int(x, 16) for x in g["mds"]]
+    add = lambda a, b: _field_op(field, 0, [a], [b])[0]  # noqa: E731
+    mul = lambda a, b: _field_op(field, 2, [a], [b])[0]  # noqa: E731
+    pow5 = lambda a: mul(mul(mul(a, a), mul(a, a)), a)   # noqa: E731
+    for tv in g["permute"][:2]:
+        out = permute([int(x, 16) for x in tv["initial_state"]], rc, mds, add, mul, pow5)
+        assert out == [int(x, 16) for x in tv["final_state"]]
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_device_curve_ops(eng, curve):
+    c = pasta.CURVES[curve]
+    n = 64
+    pts = cref.gen_points(curve, SEED, n)
+    other = cref.gen_points(curve, SEED + 1, n)
+    g = pasta.generator(c)
+    a_list = [cref.bytes_to_affine(p) for p in pts]
+    b_list = [cref.bytes_to_affine(p) for p in other]
+    # edge cases: P+P, P+(-P), identity operands
+    a_list[0], b_list[0] = g, g
+    a_list[1], b_list[1] = g, (g[0], c.p - g[1])
+    a_list[2], b_list[2] = None, b_list[2]
+    a_list[3], b_list[3] = a_list[3], None
+    a_list[4], b_list[4] = None, None
+    a = cref.affines_to_bytes(a_list)
+    b = cref.affines_to_bytes(b_list)
+    got = _curve_op(curve, 0, a, b)
+    for i in range(n):
+        assert cref.bytes_to_affine(got[i]) == cref.bytes_to_affine(cref.point_add(curve, a[i], b[i])), i
+    got = _curve_op(curve, 1, a, b)
+    for i in range(n):
+        assert cref.bytes_to_affine(got[i]) == cref.bytes_to_affine(cref.point_add(curve, a[i], a[i])), i
+    ks = pasta.gen_scalars(c.scalar, SEED + 2, n - 4) + [0, 1, 2, c.r - 1]
+    kb = np.zeros((n, 64), dtype=np.uint8)
+    kb[:, :32] = cref.ints_to_bytes(ks)
+    got = _curve_op(curve, 2, a, kb)
+    for i in range(0, n, 3):
+        assert cref.bytes_to_affine(got[i]) == cref.bytes_to_affine(cref.scalar_mul(curve, ks[i], a[i])), i
+
+
+# ------------------------------------------------------------------------------------------ K7-K9
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_best_fft_parity(eng, field):
+    """Direct best_fft parity (the reference has no such test): log_n = 0..16, true root and a
+    random omega (benches/fft.rs:17)."""
+    for log_n in list(range(0, 15)) + [16]:
+        n = 1 << log_n
+        a = cref.gen_scalars(field, SEED + log_n, n)
+        for w in (pasta.omega_for_k(field, log_n), pasta.gen_scalars(field, SEED + 77, 1)[0]):
+            want = cref.best_fft(field, a, w, log_n)
+            got = a.copy()
+            eng.best_fft(got, w, log_n, field)
+            assert (got == want).all(), (field, log_n)
+    with pytest.raises(AssertionError):  # arithmetic.rs:205
+        eng.best_fft(cref.gen_scalars(field, 1, 3), 1, 2, field)
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_best_fft_2pow20(eng, field):
+    """BASELINE.json config 2 at full size against the C restatement."""
+    log_n = 20
+    a = cref.gen_scalars(field, SEED + 2, 1 << log_n)
+    w = pasta.omega_for_k(field, log_n)
+    want = cref.best_fft(field, a, w, log_n)
+    got = a.copy()
+    eng.best_fft(got, w, log_n, field)
+    assert (got == want).all()
+    # Montgomery-form round trip through the same entry point: encode, transform, decode
+    from halo2_b200 import lib as L
+    R = (1 << 256) % pasta.FIELDS[field]
+    m = pasta.FIELDS[field]
+    small = cref.bytes_to_ints(a[:4096])
+    am = cref.ints_to_bytes([x * R % m for x in small])
+    wm = w * R % m
+    eng.best_fft(am, pasta.omega_for_k(field, 12) * R % m, 12, field, repr=L.REPR_MONTGOMERY)
+    want12 = cref.bytes_to_ints(cref.best_fft(field, a[:4096], pasta.omega_for_k(field, 12), 12))
+    assert cref.bytes_to_ints(am) == [x * R % m for x in want12]
+    del wm
+
+
+@pytest.mark.parametrize("field,j,k", [("fp", 5, 14), ("fp", 4, 5), ("fq", 9, 11), ("fq", 3, 8), ("fp", 2, 3)])
+def test_domain_transforms(eng, field, j, k):
+    """lagrange_to_coeff / coeff_to_extended / extended_to_coeff vs the restated
+    poly/domain.rs:227-255,303-325 for (k, ext_k) = (14,16), (5,7), (11,14), ..."""
+    zeta = pasta.zeta_candidates(field)[1]
+    d_or = pasta.EvaluationDomain(field, j, k, zeta)
+    d = eng.EvaluationDomain(field, j, k, zeta)
+    assert (d.omega, d.extended_omega, d.extended_k) == (d_or.omega, d_or.extended_omega, d_or.extended_k)
+    a = cref.gen_scalars(field, SEED + k, 1 << k)
+    co = cref.ifft(field, a, d_or.omega_inv, k, d_or.ifft_divisor)
+    assert (d.lagrange_to_coeff(a) == co).all()
+    ext = cref.coeff_to_extended(field, co, k, d_or.extended_k, zeta, d_or.extended_omega)
+    assert (d.coeff_to_extended(co) == ext).all()
+    out_len = (1 << k) * (j - 1)
+    back = cref.extended_to_coeff(field, ext, d_or.extended_k, d_or.extended_omega_inv, d_or.extended_ifft_divisor, zeta, out_len)
+    got = d.extended_to_coeff(ext)
+    assert got.shape == back.shape and (got == back).all()
+    # round trip: truncation keeps the low 2^k coefficients, the rest are zero
+    assert (got[: 1 << k] == co).all() and not got[1 << k:].any()
+
+
+# ------------------------------------------------------------------------------------------ K2-K5
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_best_multiexp_parity(eng, curve):
+    """arithmetic.rs:440-458 widened: n = 1 .. 2^14+1 (the commit size at k=14)."""
+    c = pasta.CURVES[curve]
+    for n in (1, 2, 3, 4, 31, 32, 33, 256, 1024, 4097, 16385):
+        kb = cref.gen_scalars(c.scalar, SEED + n, n)
+        pb = cref.gen_points(curve, SEED + 3 * n, n)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want, (curve, n)
+    with pytest.raises(AssertionError):  # arithmetic.rs:144
+        eng.best_multiexp(kb[:5], pb[:4], curve)
+    # empty input: identity
+    assert _affine(curve, eng.best_multiexp(kb[:0], pb[:0], curve)) is None
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_best_multiexp_edge_and_skew(eng, curve):
+    """Duplicates, negations, identity bases (msm.rs:179-219) and the skewed scalar
+    distributions real provers produce."""
+    from halo2_b200 import lib as L
+    c = pasta.CURVES[curve]
+    r = c.r
+    g = pasta.generator(c)
+    pts = [cref.bytes_to_affine(x) for x in cref.gen_points(curve, SEED, 8)]
+    pts2 = [g, g, (g[0], c.p - g[1]), None, pts[3], pts[3], pts[4], (pts[4][0], c.p - pts[4][1]), None, g] * 40
+    ks = pasta.gen_scalars(c.scalar, SEED + 4, len(pts2))
+    ks[0] = ks[1] = ks[2] = 5
+    ks[6] = ks[7]
+    kb, pb = cref.ints_to_bytes(ks), cref.affines_to_bytes(pts2)
+    assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    out = eng.best_multiexp(cref.ints_to_bytes([5, 7, 12, 99, r - 1, 1]),
+                            cref.affines_to_bytes([g, g, (g[0], c.p - g[1]), None, pts[3], pts[3]]), curve)
+    assert _affine(curve, out) is None
+    n = 5000
+    pb = cref.gen_points(curve, SEED + 9, n)
+    one = pasta.gen_scalars(c.scalar, 1, 1)[0]
+    cases = {
+        "zeros": [0] * n, "ones": [1] * n, "equal": [one] * n, "mix01": [i & 1 for i in range(n)],
+        "rminus1": [r - 1] * n, "topheavy": [(r - 1) - (i << 3) for i in range(n)], "small": [i % 1000 for i in range(n)],
+        "pow2": [(1 << (i % 255)) % r for i in range(n)], "half": [(1 << 254) - 1 + i for i in range(n)],
+    }
+    lib = L.init()
+    try:
+        for name, ks in cases.items():
+            kb = cref.ints_to_bytes(ks)
+            want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+            for cbits in (0, 7, 13):
+                L.check(lib.h2_set_window_bits(cbits))
+                assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want, (name, cbits)
+    finally:
+        lib.h2_set_window_bits(0)
+
+
+def test_window_sweep_and_montgomery_inputs(eng):
+    """BASELINE.json config 3's sweep dimension: every window size gives the same point;
+    Montgomery-encoded inputs (pasta's in-memory form) give the same point too."""
+    from halo2_b200 import lib as L
+    curve, c = "pallas", pasta.PALLAS
+    n = 4096
+    kb = cref.gen_scalars(c.scalar, SEED + 5, n)
+    pb = cref.gen_points(curve, SEED + 6, n)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    lib = L.init()
+    try:
+        for cbits in list(range(1, 21)):
+            L.check(lib.h2_set_window_bits(cbits))
+            assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want, cbits
+    finally:
+        lib.h2_set_window_bits(0)
+    Rr, Rp = (1 << 256) % c.r, (1 << 256) % c.p
+    km = cref.ints_to_bytes([k * Rr % c.r for k in cref.bytes_to_ints(kb)])
+    coords = cref.bytes_to_ints(pb.reshape(-1, 32))
+    pm = cref.ints_to_bytes([v * Rp % c.p for v in coords]).reshape(-1, 64)
+    out = eng.best_multiexp(km, pm, curve, repr=L.REPR_MONTGOMERY)
+    Rinv = pow(Rp, c.p - 2, c.p)
+    xyz = cref.ints_to_bytes([v * Rinv % c.p for v in cref.bytes_to_ints(out.reshape(3, 32))]).reshape(-1)
+    assert _affine(curve, xyz) == want
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_commit_lagrange_equals_commit(eng, curve):
+    """poly/commitment.rs:258-302 at k=6: commit(lagrange_to_coeff(a)) == commit_lagrange(a), with
+    g_lagrange from the oracle's EC-FFT (commitment.rs:77-94) -- ties NTT, MSM and resident bases."""
+    c = pasta.CURVES[curve]
+    k = 6
+    po = pasta.Params(c, k)
+    params = eng.Params(curve, k, cref.affines_to_bytes(po.g), cref.affines_to_bytes(po.g_lagrange),
+                        cref.affines_to_bytes([po.w]))
+    zeta = pasta.zeta_candidates(c.scalar)[0]
+    dom = eng.EvaluationDomain(c.scalar, 2, k, zeta)
+    a = cref.gen_scalars(c.scalar, SEED + 8, 1 << k)
+    alpha = pasta.gen_scalars(c.scalar, SEED + 9, 1)[0]
+    lhs = _affine(curve, params.commit_lagrange(a, eng.Blind(alpha)))
+    rhs = _affine(curve, params.commit(dom.lagrange_to_coeff(a), eng.Blind(alpha)))
+    assert lhs == rhs
+    assert lhs == pasta.to_affine(c, po.commit_lagrange(cref.bytes_to_ints(a), alpha))
+    # Blind::default() == 1 (commitment.rs:212-216): all-zero column commits to w
+    zero = np.zeros((1 << k, 32), dtype=np.uint8)
+    assert _affine(curve, params.commit_lagrange(zero, eng.Blind())) == po.w
+    params.close()
+
+
+def test_best_multiexp_2pow20(eng):
+    """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
+    curve, c = "pallas", pasta.PALLAS
+    n = 1 << 20
+    kb = cref.gen_scalars(c.scalar, SEED + 3, n)
+    pb = cref.gen_points(curve, SEED + 33, n)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want
+
+
+def test_point_sum(eng):
+    """The multi-GPU combine step: sum of per-shard Jacobian partials == MSM of the whole."""
+    from halo2_b200 import lib as L
+    curve, c = "vesta", pasta.VESTA
+    n, shards = 3000, 4
+    kb = cref.gen_scalars(c.scalar, SEED + 11, n)
+    pb = cref.gen_points(curve, SEED + 12, n)
+    parts = np.zeros((shards, 96), dtype=np.uint8)
+    step = n // shards
+    for s in range(shards):
+        lo, hi = s * step, n if s == shards - 1 else (s + 1) * step
+        parts[s] = eng.best_multiexp(kb[lo:hi], pb[lo:hi], curve)
+    out = np.zeros(96, dtype=np.uint8)
+    lib = L.init()
+    L.check(lib.h2_point_sum(L.CURVE_ID[curve], L.ptr(parts), ctypes.c_size_t(shards), L.REPR_CANONICAL, L.ptr(out)))
+    assert _affine(curve, out) == cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))

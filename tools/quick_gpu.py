@@ -1,0 +1,82 @@
+"""Ad-hoc GPU timing used during development (not part of bench.py's contract)."""
+import ctypes
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from halo2_b200 import lib as L  # noqa: E402
+
+lib = L.init()
+
+
+def mulbench():
+    for field in (0, 1):
+        for tpb, blocks in ((128, 148 * 4), (256, 148 * 4), (256, 148 * 8)):
+            ms = ctypes.c_float()
+            iters = 2000
+            L.check(lib.h2_bench_field_mul(field, tpb, blocks, iters, ctypes.byref(ms)))
+            muls = tpb * blocks * iters * 4
+            print(f"field={field} tpb={tpb} blocks={blocks}: {ms.value:.3f} ms  {muls / ms.value / 1e6:.1f} G mulmod/s", flush=True)
+
+
+def rand_scalars(n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    x[:, 7] &= 0x3FFFFFFF  # < 2^254 < modulus: canonical
+    return x
+
+
+def ntt_time(log_n, field=0, reps=10):
+    n = 1 << log_n
+    a = rand_scalars(n, 1)
+    out = torch.empty_like(a)
+    omega = np.frombuffer((5).to_bytes(32, "little"), dtype=np.uint8).copy()
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        L.check(lib.h2_ntt_dev(field, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(out.data_ptr()), L.ptr(omega), 0, log_n, ctypes.c_void_p(s)))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        L.check(lib.h2_ntt_dev(field, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(out.data_ptr()), L.ptr(omega), 0, log_n, ctypes.c_void_p(s)))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"ntt 2^{log_n}: {ms:.3f} ms  {n / ms / 1e6:.2f} G elem/s", flush=True)
+
+
+def msm_time(log_n, curve=0, c=0, reps=5, extra=0):
+    n = (1 << log_n) + extra
+    sc = rand_scalars(n, 2)
+    bases = torch.empty((n, 16), dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.h2_dev_gen_points(curve, 7, 0, ctypes.c_size_t(n), ctypes.c_void_p(bases.data_ptr()), ctypes.c_void_p(s)))
+    out = torch.empty(24, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        L.check(lib.h2_msm_dev(curve, ctypes.c_void_p(sc.data_ptr()), 0, ctypes.c_void_p(bases.data_ptr()), ctypes.c_size_t(n), c, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(s)))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        L.check(lib.h2_msm_dev(curve, ctypes.c_void_p(sc.data_ptr()), 0, ctypes.c_void_p(bases.data_ptr()), ctypes.c_size_t(n), c, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(s)))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"msm n=2^{log_n}+{extra} c={c}: {ms:.3f} ms  {n / ms / 1e3:.2f} M pairs/s", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["mul", "ntt", "msm"]
+    if "mul" in what:
+        mulbench()
+    if "ntt" in what:
+        for k in (14, 16, 20, 24):
+            ntt_time(k)
+    if "msm" in what:
+        msm_time(14, extra=1)
+        msm_time(16)
+        for c in (0, 13, 15, 17):
+            msm_time(20, c=c)
