@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of BASELINE.json on N B200s of one node.
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  * headline (`value`): best_multiexp over 2^20 (scalar, base) pairs per GPU on Pallas
+    (BASELINE.json configs[2]; for N > 1 each rank owns its own contiguous 2^20-pair shard --
+    weak scaling -- and the per-rank 96-byte partial points are all-gathered over NCCL and summed,
+    SURVEY.md section 8(e)).  Inputs are resident in HBM when the timed region starts.
+  * `extra.ntt`: best_fft at 2^20 over Fp (configs[1]; single GPU by the north star).
+  * `e2e`: the same MSM through the reference-facing C-ABI call h2_msm with HOST (pinned)
+    buffers -- H2D of scalars + bases and D2H of the result inside the timed region.
+  * `roofline`: the dominant kernel (msm_accum0_kernel), algorithmic bytes (96 B per pair,
+    SURVEY.md section 8(d)) / its CUDA-event duration measured live, against the measured HBM peak.
+  * `cpu_baseline`: the C restatement of the reference algorithm (oracle/halo2_oracle.c, "port":
+    the Rust reference cannot be built here) on all host cores, same workload.
+
+`--impl reference` times that CPU restatement alone (the reference arm).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 20
+SEED = 0x48414C4F32
+CURVE, SCALAR_FIELD = "pallas", "fq"
+MSM_BYTES_PER_PAIR = 96      # 32 B scalar + 64 B affine base, each read once
+NTT_BYTES_PER_ELEM = 64      # 32 B read + 32 B written, one ideal pass
+
+Q_MOD = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+P_MOD = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rand_canonical_scalars(torch, n, seed, device):
+    """n uniform-ish canonical scalars (< 2^254 < modulus) as an (n, 8) int32 tensor."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device=device, generator=g)
+    x[:, 7] &= 0x3FFFFFFF
+    return x
+
+
+# =================================================================================================
+# reference arm: the reference's CPU algorithm (C restatement) on the host cores
+# =================================================================================================
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import cref
+    n = 1 << LOG_N
+    threads = os.cpu_count() or 1
+    kb = cref.gen_scalars(SCALAR_FIELD, SEED + 3, n)
+    pb = cref.gen_points(CURVE, SEED + 33, n)
+    for _ in range(min(args.warmup, 1)):
+        cref.best_multiexp(CURVE, kb, pb, threads)
+    t0 = time.time()
+    for _ in range(args.steps):
+        cref.best_multiexp(CURVE, kb, pb, threads)
+    dt = (time.time() - t0) / max(args.steps, 1)
+    value = n / dt
+    sample = f"{args.steps} x full 2^{LOG_N}-pair best_multiexp (window-parallel, c=ceil(ln n)=14, 19 window tasks)"
+    line = {
+        "impl": "reference", "metric": "msm_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"best_multiexp 2^{LOG_N} pairs, Pallas (configs[2]), CPU restatement of arithmetic.rs:143-180"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from halo2_b200 import lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (halo2_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.init(local_rank)
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    cid, n = L.CURVE_ID[CURVE], 1 << LOG_N
+
+    # ---- synthetic inputs, resident in HBM.  Rotating 4 scalar sets + 2 base sets = 256 MiB > L2.
+    n_sc, n_bs = 4, 2
+    scal = [rand_canonical_scalars(torch, n, SEED + 100 * rank + i, dev) for i in range(n_sc)]
+    bases = []
+    for i in range(n_bs):
+        b = torch.empty((n, 16), dtype=torch.int32, device=dev)
+        L.check(lib.h2_dev_gen_points(cid, SEED + 7 + i, ctypes.c_uint64(rank * n), ctypes.c_size_t(n),
+                                      ctypes.c_void_p(b.data_ptr()), sp))
+        bases.append(b)
+    out_dev = torch.zeros(24, dtype=torch.int32, device=dev)
+    gathered = [torch.zeros(24, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+    gathered_host = np.zeros((max(world, 1), 96), dtype=np.uint8)
+    final = np.zeros(96, dtype=np.uint8)
+
+    def step(i):
+        L.check(lib.h2_msm_dev(cid, ctypes.c_void_p(scal[i % n_sc].data_ptr()), L.REPR_CANONICAL,
+                               ctypes.c_void_p(bases[i % n_bs].data_ptr()), ctypes.c_size_t(n), 0,
+                               ctypes.c_void_p(out_dev.data_ptr()), sp))
+        if world > 1:
+            # the path's one exchange: 96-byte Jacobian partials over NCCL, then a G-term EC sum
+            dist.all_gather(gathered, out_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = L.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    launches = L.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+
+    # multi-GPU combine (outside the loop once, to show the whole path produces one point)
+    if world > 1:
+        for r in range(world):
+            gathered_host[r] = gathered[r].cpu().numpy().view(np.uint8)
+        L.check(lib.h2_point_sum(cid, L.ptr(gathered_host), ctypes.c_size_t(world), L.REPR_MONTGOMERY, L.ptr(final)))
+
+    # ---- roofline of the dominant kernel, CUDA events on its launch stream
+    L.check(lib.h2_profile_enable(1))
+    for i in range(5):
+        step(i)
+    torch.cuda.synchronize()
+    tot, cnt = ctypes.c_float(), ctypes.c_uint32()
+    L.check(lib.h2_profile_read(0, ctypes.byref(tot), ctypes.byref(cnt)))
+    L.check(lib.h2_profile_enable(0))
+    hbm_peak, peak_src = measured_peaks()
+    k_ms = tot.value / max(cnt.value, 1)
+    achieved = MSM_BYTES_PER_PAIR * n / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "msm_accum0_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+                "peak_source": peak_src,
+                "note": "255-bit modular integer work: the limiter is the INT32 multiply-add pipe, not HBM (DESIGN.md section 5)"}
+
+    # ---- e2e: reference-facing host call, pinned host buffers, copies inside the timed region;
+    # every rank pushes its own shard through h2_msm, then the 96 B partials are exchanged
+    sc_host = [torch.empty((n, 8), dtype=torch.int32).pin_memory() for _ in range(2)]
+    bs_host = [torch.empty((n, 16), dtype=torch.int32).pin_memory() for _ in range(2)]
+    for i in range(2):
+        sc_host[i].copy_(scal[i])
+        tmp = bases[i].clone()   # generator output is Montgomery; the reference hands over canonical coordinates
+        L.check(lib.h2_dev_convert(L.FIELD_ID[L.BASE_FIELD[CURVE]], ctypes.c_void_p(tmp.data_ptr()), ctypes.c_size_t(2 * n), 0, sp))
+        bs_host[i].copy_(tmp)
+    torch.cuda.synchronize()
+    res = np.zeros(96, dtype=np.uint8)
+    res_t = torch.zeros(96, dtype=torch.uint8, device=dev)
+    res_all = [torch.zeros(96, dtype=torch.uint8, device=dev) for _ in range(world)] if world > 1 else None
+
+    def e2e_step(i):
+        L.check(lib.h2_msm(cid, ctypes.c_void_p(sc_host[i % 2].data_ptr()), ctypes.c_void_p(bs_host[i % 2].data_ptr()),
+                           ctypes.c_size_t(n), L.REPR_CANONICAL, L.ptr(res)))
+        if world > 1:
+            res_t.copy_(torch.from_numpy(res))
+            dist.all_gather(res_all, res_t)
+            torch.cuda.synchronize()
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.time()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_dt = (time.time() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e = {"value": world * n / e2e_dt, "unit": "pairs/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 96,
+           "ms_per_step": e2e_dt * 1e3, "api": "h2_msm (host buffers, canonical repr) per rank + all-gather of results",
+           "n_gpus": world}
+
+    if rank == 0:
+        # ---- NTT (configs[1]) on this GPU
+        extra = {}
+        a = rand_canonical_scalars(torch, n, SEED + 1, dev)
+        L.check(lib.h2_dev_convert(L.FIELD_ID["fp"], ctypes.c_void_p(a.data_ptr()), ctypes.c_size_t(n), 1, sp))
+        bufs = [a.clone() for _ in range(5)]   # 5 x 32 MiB rotating > L2
+        outs = [torch.empty_like(a) for _ in range(5)]
+        omega = pow(5, (P_MOD - 1) >> 32, P_MOD)
+        for _ in range(LOG_N, 32):
+            omega = omega * omega % P_MOD
+        ob = L.fe_bytes(omega)
+
+        def ntt_step(i):
+            L.check(lib.h2_ntt_dev(L.FIELD_ID["fp"], ctypes.c_void_p(bufs[i % 5].data_ptr()), ctypes.c_void_p(outs[i % 5].data_ptr()),
+                                   L.ptr(ob), L.REPR_CANONICAL, LOG_N, sp))
+        for i in range(3):
+            ntt_step(i)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(args.steps):
+            ntt_step(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ntt_ms = e0.elapsed_time(e1) / args.steps
+        L.check(lib.h2_profile_enable(1))
+        for i in range(5):
+            ntt_step(i)
+        torch.cuda.synchronize()
+        L.check(lib.h2_profile_read(1, ctypes.byref(tot), ctypes.byref(cnt)))
+        L.check(lib.h2_profile_enable(0))
+        pass_ms = tot.value / max(cnt.value, 1)
+        ntt_ach = NTT_BYTES_PER_ELEM * n / (pass_ms * 1e-3) / 1e9
+        # host-buffer e2e for the NTT
+        ah = torch.empty((n, 8), dtype=torch.int32).pin_memory()
+        ah.copy_(rand_canonical_scalars(torch, n, SEED + 2, dev))
+        torch.cuda.synchronize()
+        for _ in range(2):
+            L.check(lib.h2_ntt(L.FIELD_ID["fp"], ctypes.c_void_p(ah.data_ptr()), L.ptr(ob), LOG_N, L.REPR_CANONICAL))
+        t0 = time.time()
+        for _ in range(5):
+            L.check(lib.h2_ntt(L.FIELD_ID["fp"], ctypes.c_void_p(ah.data_ptr()), L.ptr(ob), LOG_N, L.REPR_CANONICAL))
+        ntt_e2e = (time.time() - t0) / 5
+        extra["ntt"] = {
+            "metric": "ntt_elems_per_s", "value": n / (ntt_ms * 1e-3), "unit": "elems/s", "ms_per_step": ntt_ms,
+            "config": {"workload": f"best_fft 2^{LOG_N} over Fp (configs[1]), twiddles cached per (omega, log_n), "
+                                   "5 rotating 32 MiB buffers (> L2)"},
+            "roofline": {"kernel": "ntt_pass_kernel", "bound": "hbm", "achieved": ntt_ach, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ntt_ach / hbm_peak, "traffic": None, "kernel_ms": pass_ms, "passes_per_step": 3},
+            "e2e": {"value": n / ntt_e2e, "unit": "elems/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
+                    "ms_per_step": ntt_e2e * 1e3, "api": "h2_ntt (host buffers, canonical repr)"},
+        }
+
+        # ---- CPU baseline: the reference algorithm restated in C, all host cores, same workload
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import cref
+            threads = os.cpu_count() or 1
+            kb = cref.gen_scalars(SCALAR_FIELD, SEED + 3, n)
+            pb = cref.gen_points(CURVE, SEED + 33, n)
+            cref.best_multiexp(CURVE, kb[:4096], pb[:4096], threads)
+            t0 = time.time()
+            reps = 2
+            for _ in range(reps):
+                want = cref.best_multiexp(CURVE, kb, pb, threads)
+            cdt = (time.time() - t0) / reps
+            cpu = {"value": n / cdt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                   "sample": f"{reps} x full 2^{LOG_N}-pair best_multiexp (reference algorithm, C restatement, "
+                             f"{threads} threads; window-parallel so at most 19 are busy)", "ms_per_step": cdt * 1e3}
+            # and a parity spot check of the e2e path on the very same input
+            got = np.zeros(96, dtype=np.uint8)
+            L.check(lib.h2_msm(cid, L.ptr(kb), L.ptr(pb), ctypes.c_size_t(n), L.REPR_CANONICAL, L.ptr(got)))
+            cpu["parity_vs_gpu"] = bool((cref.jac_to_affine(CURVE, got) == want).all())
+            a_c = cref.gen_scalars("fp", SEED + 2, n)
+            t0 = time.time()
+            cref.best_fft("fp", a_c, omega, LOG_N, threads)
+            extra["ntt"]["cpu_baseline"] = {"value": n / (time.time() - t0), "unit": "elems/s", "cores": threads, "kind": "port",
+                                            "sample": f"1 x full 2^{LOG_N} best_fft (serial bit-reversal + twiddle scan, "
+                                                      "join-recursion; includes canonical<->Montgomery conversion)"}
+
+        line = {
+            "metric": "msm_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32x8 (255-bit modular integers)", "data": "synthetic",
+            "config": {"workload": f"best_multiexp 2^{LOG_N} pairs per GPU, Pallas (BASELINE configs[2]); "
+                                   f"N>1: contiguous 2^{LOG_N}-pair shard per rank + NCCL all-gather of 96 B partials",
+                       "pairs_per_gpu": n, "window_bits": "auto", "l2": "inputs rotate over 4 scalar + 2 base buffers (256 MiB > L2)",
+                       "parallelism": f"shard x{world}"},
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": int(launches),
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

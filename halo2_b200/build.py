@@ -14,7 +14,7 @@ LIB = os.path.join(LIB_DIR, "libhalo2_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-split-compile", "0",
 ]
 
 

@@ -65,6 +65,22 @@ struct Context {
 };
 static Context g_ctx;
 static std::mutex g_mu;
+// optional per-kernel timing (bench.py's roofline leg): event pairs recorded on the launch stream
+struct ProfSpan { int kind; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof;
+enum { PROF_MSM_ACCUM0 = 0, PROF_NTT_PASS = 1, PROF_KINDS = 2 };
+static void prof_begin(int kind, cudaStream_t s) {
+    if (!g_prof_on) return;
+    ProfSpan sp; sp.kind = kind;
+    cudaEventCreate(&sp.e0); cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, s);
+    g_prof.push_back(sp);
+}
+static void prof_end(cudaStream_t s) {
+    if (!g_prof_on || g_prof.empty()) return;
+    cudaEventRecord(g_prof.back().e1, s);
+}
 static std::atomic<uint64_t> g_launches{0};
 
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                                   \
@@ -318,7 +334,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     LAUNCH(k_hist, blocks_for(n, 256), 256, 0, s, p, M);
     if (exclusive_scan_u32(M.counts, p.G + 1, s)) return 1;
     LAUNCH(k_scatter, blocks_for(n, 256), 256, 0, s, p, M);
+    prof_begin(PROF_MSM_ACCUM0, s);
     LAUNCH(k_accum0, blocks_for(p.acc_threads[0], 128), 128, 0, s, p, M);
+    prof_end(s);
     for (uint32_t lv = 1; lv < p.acc_levels; lv++)
         LAUNCH(k_accumN, blocks_for(p.acc_threads[lv], 128), 128, 0, s, p, M, lv);
     for (uint32_t lv = 0; lv < p.red_levels; lv++) {
@@ -510,7 +528,9 @@ static int ntt_run(int field, const fe *d_in, uint32_t in_log_n, fe *d_out, uint
         for (int k = 0; k < 3; k++) { A.in_scale[k] = sc.in_s[k]; A.out_scale[k] = sc.out_s[k]; }
         uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
         uint32_t smem = ntt_smem_bytes(sp[i], logc[i]);
+        prof_begin(PROF_NTT_PASS, s);
         LAUNCH(ntt_pass_kernel<P>, tiles, 256, smem, s, A);
+        prof_end(s);
         s0 += sp[i];
     }
     return 0;
@@ -684,4 +704,32 @@ extern "C" int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_
     CU(cudaEventElapsedTime(ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return scratch_release(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel timing for the roofline leg of bench.py
+// ------------------------------------------------------------------------------------------------
+extern "C" int h2_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaDeviceSynchronize();
+    for (auto &sp : g_prof) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return 0;
+}
+// kind 0 = msm_accum0_kernel, 1 = ntt_pass_kernel.  Returns summed device time and launch count.
+extern "C" int h2_profile_read(int kind, float *total_ms, uint32_t *launches) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    CU(cudaDeviceSynchronize());
+    float tot = 0; uint32_t cnt = 0;
+    for (auto &sp : g_prof) {
+        if (sp.kind != kind) continue;
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+        tot += ms; cnt++;
+    }
+    *total_ms = tot; *launches = cnt;
+    return 0;
 }

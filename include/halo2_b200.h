@@ -116,6 +116,11 @@ int h2_test_curve_op(int curve, int op, const void *a_xy, const void *b_xy, size
 int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_t blocks, uint32_t iters, float *ms);
 /* Number of kernels launched by the engine since h2_init (bench.py's gpu_launches). */
 uint64_t h2_launch_count(void);
+/* Per-kernel device timing for the roofline report: while enabled, CUDA-event pairs bracket the
+ * dominant kernels on their launch stream.  kind 0 = MSM bucket-accumulate kernel, 1 = NTT pass
+ * kernel.  h2_profile_enable(0/1) also clears the recorded spans. */
+int h2_profile_enable(int on);
+int h2_profile_read(int kind, float *total_ms, uint32_t *launches);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,138 @@
+"""CPU checks of the DEVICE code's logic: halo2_b200/csrc/*.cuh compiled for the host
+(tests/kernel_emul, PTX carry flag emulated) and run serially against the oracle.  Covers the
+Montgomery multiply, the XYZZ group law, the NTT pass geometry (single and multi-pass, all fused
+modes) and the whole MSM pipeline (digits, counting sort, chunked accumulation with multi-level
+partial merging, hierarchical bucket reduce) including skewed scalars and degenerate bases."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import cref, pasta
+from tests.kernel_emul import build as emul_build
+
+SEED = 0x48414C4F32
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return ctypes.CDLL(emul_build.build())
+
+
+def _fop(emu, f, op, a, b=0):
+    out = np.zeros(32, dtype=np.uint8)
+    emu.emu_field_op(cref.FIELD_ID[f], op, cref._p(cref._fe(a)), cref._p(cref._fe(b)), cref._p(out))
+    return int.from_bytes(out.tobytes(), "little")
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_emul_field(emu, field):
+    m = pasta.FIELDS[field]
+    xs = pasta.gen_scalars(field, SEED, 200) + [0, 1, 2, m - 1, m - 2, 1 << 254, (1 << 254) - 1, m - (1 << 32),
+                                                0xFFFFFFFF, 1 << 32, (1 << 224) - 1, m >> 1]
+    for i, a in enumerate(xs):
+        b = xs[(i * 7 + 3) % len(xs)]
+        assert _fop(emu, field, 0, a, b) == (a + b) % m
+        assert _fop(emu, field, 1, a, b) == (a - b) % m
+        assert _fop(emu, field, 2, a, b) == a * b % m
+        assert _fop(emu, field, 4, a) == a * a % m
+        assert _fop(emu, field, 5, a) == (-a) % m
+    for a in xs[:10] + xs[-6:]:
+        if a:
+            assert _fop(emu, field, 3, a) == pow(a, m - 2, m)
+
+
+def _cop(emu, curve, op, a, b):
+    out = np.zeros(64, dtype=np.uint8)
+    emu.emu_curve_op(cref.CURVE_ID[curve], op, cref._p(np.ascontiguousarray(a)), cref._p(np.ascontiguousarray(b)), cref._p(out))
+    return cref.bytes_to_affine(out)
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_curve(emu, curve):
+    c = pasta.CURVES[curve]
+    pts = pasta.gen_points(c, 5, 8)
+    g = pasta.generator(c)
+    cases = [(pts[0], pts[1]), (pts[2], pts[2]), (pts[3], (pts[3][0], c.p - pts[3][1])), (None, pts[4]), (pts[5], None),
+             (None, None), (g, g)]
+    for a, b in cases:
+        A, B = cref.affines_to_bytes([a])[0], cref.affines_to_bytes([b])[0]
+        want = pasta.to_affine(c, pasta.jac_add(c, pasta.to_jac(a), pasta.to_jac(b)))
+        assert _cop(emu, curve, 0, A, B) == want
+        assert _cop(emu, curve, 1, A, B) == want
+        assert _cop(emu, curve, 2, A, B) == pasta.to_affine(c, pasta.jac_double(c, pasta.to_jac(a)))
+    for k in pasta.gen_scalars(c.scalar, 3, 3) + [0, 1, c.r - 1]:
+        kb = np.zeros(64, dtype=np.uint8)
+        kb[:32] = cref._fe(k)
+        assert _cop(emu, curve, 4, cref.affines_to_bytes([pts[7]])[0], kb) == pasta.to_affine(c, pasta.scalar_mul(c, k, pts[7]))
+
+
+def _ntt(emu, f, mode, a, in_log, log_n, omega, zeta=None, div=None, out_len=None, nthr=64):
+    n = 1 << log_n
+    out_len = n if out_len is None else out_len
+    out = np.zeros((out_len, 32), dtype=np.uint8)
+    emu.emu_ntt(cref.FIELD_ID[f], mode, cref._p(np.ascontiguousarray(a)), in_log, log_n, cref._p(cref._fe(omega)),
+                cref._p(cref._fe(zeta)) if zeta is not None else None, cref._p(cref._fe(div)) if div is not None else None,
+                ctypes.c_uint64(out_len), cref._p(out), nthr)
+    return out
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_emul_ntt(emu, field):
+    for log_n in (1, 2, 3, 5, 8, 10, 11, 12, 13, 15):
+        a = cref.gen_scalars(field, 100 + log_n, 1 << log_n)
+        for w in (pasta.omega_for_k(field, log_n), pasta.gen_scalars(field, 77, 1)[0]):
+            got = _ntt(emu, field, 0, a, log_n, log_n, w, nthr=(7 if log_n < 8 else 64))
+            assert (got == cref.best_fft(field, a, w, log_n)).all(), (field, log_n)
+    for (j, k) in ((5, 5), (3, 6), (4, 9), (5, 11)):
+        d = pasta.EvaluationDomain(field, j, k)
+        a = cref.gen_scalars(field, 5, 1 << k)
+        co = cref.ifft(field, a, d.omega_inv, k, d.ifft_divisor)
+        assert (_ntt(emu, field, 1, a, k, k, d.omega_inv, div=d.ifft_divisor) == co).all()
+        ext = cref.coeff_to_extended(field, co, k, d.extended_k, d.g_coset, d.extended_omega)
+        assert (_ntt(emu, field, 2, co, k, d.extended_k, d.extended_omega, zeta=d.g_coset) == ext).all()
+        ol = (1 << k) * (j - 1)
+        back = cref.extended_to_coeff(field, ext, d.extended_k, d.extended_omega_inv, d.extended_ifft_divisor, d.g_coset, ol)
+        got = _ntt(emu, field, 3, ext, d.extended_k, d.extended_k, d.extended_omega_inv, zeta=d.g_coset,
+                   div=d.extended_ifft_divisor, out_len=ol)
+        assert (got == back).all()
+
+
+def _msm(emu, curve, kb, pb, c=0, mont=0, k0=0):
+    out = np.zeros(96, dtype=np.uint8)
+    r = emu.emu_msm(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(kb)), cref._p(np.ascontiguousarray(pb)),
+                    ctypes.c_size_t(kb.shape[0]), c, mont, k0, cref._p(out))
+    assert r > 0, r
+    return cref.bytes_to_affine(cref.jac_to_affine(curve, out))
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_msm(emu, curve):
+    c = pasta.CURVES[curve]
+    for n in (1, 2, 3, 7, 33, 100, 257):
+        kb = cref.gen_scalars(c.scalar, n, n)
+        pb = cref.gen_points(curve, n + 1, n)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        for cb, k0 in ((0, 0), (1, 0), (5, 3), (11, 5), (16, 0)):
+            assert _msm(emu, curve, kb, pb, cb, 0, k0) == want, (n, cb, k0)
+        assert _msm(emu, curve, kb, pb, 0, 1, 0) == want   # Montgomery-encoded scalars
+    n, r = 200, c.r
+    pb = cref.gen_points(curve, 9, n)
+    cases = {"zeros": [0] * n, "ones": [1] * n, "equal": [pasta.gen_scalars(c.scalar, 1, 1)[0]] * n,
+             "mix01": [i & 1 for i in range(n)], "rminus1": [r - 1] * n, "pow2": [(1 << (i % 255)) % r for i in range(n)],
+             "half": [(1 << 254) - 1 + i for i in range(n)]}
+    for name, ks in cases.items():
+        kb = cref.ints_to_bytes(ks)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        for cb, k0 in ((0, 0), (4, 3), (16, 4)):
+            assert _msm(emu, curve, kb, pb, cb, 0, k0) == want, (name, cb, k0)
+    g = pasta.generator(c)
+    pts = [cref.bytes_to_affine(x) for x in pb[:6]]
+    pts2 = [g, g, (g[0], c.p - g[1]), None, pts[3], pts[3], pts[4], (pts[4][0], c.p - pts[4][1]), None, g] * 5
+    ks = pasta.gen_scalars(c.scalar, 4, len(pts2))
+    ks[0] = ks[1] = ks[2] = 5
+    ks[6] = ks[7]
+    kb, pb2 = cref.ints_to_bytes(ks), cref.affines_to_bytes(pts2)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb2))
+    for cb, k0 in ((0, 0), (3, 2), (13, 0)):
+        assert _msm(emu, curve, kb, pb2, cb, 0, k0) == want
