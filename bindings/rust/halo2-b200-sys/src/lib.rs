@@ -1,0 +1,162 @@
+//! Safe wrappers over include/halo2_b200.h for halo2_proofs.
+//!
+//! halo2_proofs forbids `unsafe` (`src/lib.rs:9`), so the FFI lives in this separate crate and
+//! halo2_proofs::arithmetic dispatches into it on the concrete Pasta types.
+//! Element encoding: the portable canonical path (`to_repr` / `coordinates`) is always correct;
+//! the zero-copy Montgomery path is enabled only after `self_test()` confirms that pasta_curves'
+//! in-memory layout is 4 x u64 little-endian Montgomery limbs with R = 2^256.
+#![allow(clippy::missing_safety_doc)]
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+use ff::PrimeField;
+use group::Curve;
+use pasta_curves::arithmetic::{CurveAffine, CurveExt};
+use pasta_curves::{pallas, vesta};
+
+pub const CURVE_PALLAS: c_int = 0;
+pub const CURVE_VESTA: c_int = 1;
+pub const FIELD_FP: c_int = 0;
+pub const FIELD_FQ: c_int = 1;
+pub const REPR_CANONICAL: c_int = 0;
+pub const REPR_MONTGOMERY: c_int = 1;
+
+extern "C" {
+    pub fn h2_init(device: c_int) -> c_int;
+    pub fn h2_last_error() -> *const c_char;
+    pub fn h2_msm(curve: c_int, scalars: *const c_void, bases_xy: *const c_void, n: usize, repr: c_int,
+                  out_xyz: *mut c_void) -> c_int;
+    pub fn h2_bases_register(curve: c_int, bases_xy: *const c_void, n: usize, repr: c_int, handle: *mut u64) -> c_int;
+    pub fn h2_bases_release(handle: u64) -> c_int;
+    pub fn h2_msm_registered(handle: u64, scalars: *const c_void, n: usize, extra_scalar: *const c_void,
+                             repr: c_int, out_xyz: *mut c_void) -> c_int;
+    pub fn h2_ntt(field: c_int, a: *mut c_void, omega: *const c_void, log_n: u32, repr: c_int) -> c_int;
+    pub fn h2_intt_scaled(field: c_int, a: *mut c_void, omega_inv: *const c_void, divisor: *const c_void,
+                          log_n: u32, repr: c_int) -> c_int;
+    pub fn h2_coeff_to_extended(field: c_int, a: *const c_void, k: u32, ext_k: u32, zeta: *const c_void,
+                                ext_omega: *const c_void, out: *mut c_void, repr: c_int) -> c_int;
+    pub fn h2_extended_to_coeff(field: c_int, a: *const c_void, ext_k: u32, ext_omega_inv: *const c_void,
+                                ext_divisor: *const c_void, zeta: *const c_void, out_len: usize,
+                                out: *mut c_void, repr: c_int) -> c_int;
+}
+
+fn check(rc: c_int) {
+    if rc != 0 {
+        // the reference panics on misuse (arithmetic.rs:144,205); keep that behaviour
+        let msg = unsafe { CStr::from_ptr(h2_last_error()) }.to_string_lossy().into_owned();
+        panic!("halo2_b200: {}", msg);
+    }
+}
+
+/// Curves the engine accelerates.
+pub trait B200Curve: CurveAffine {
+    const CURVE_ID: c_int;
+    const SCALAR_FIELD_ID: c_int;
+}
+impl B200Curve for pallas::Affine {
+    const CURVE_ID: c_int = CURVE_PALLAS;
+    const SCALAR_FIELD_ID: c_int = FIELD_FQ;
+}
+impl B200Curve for vesta::Affine {
+    const CURVE_ID: c_int = CURVE_VESTA;
+    const SCALAR_FIELD_ID: c_int = FIELD_FP;
+}
+
+fn scalars_to_bytes<F: PrimeField>(s: &[F]) -> Vec<u8> {
+    let mut out = Vec::with_capacity(32 * s.len());
+    for x in s {
+        out.extend_from_slice(x.to_repr().as_ref());
+    }
+    out
+}
+fn bases_to_bytes<C: CurveAffine>(b: &[C]) -> Vec<u8> {
+    let mut out = vec![0u8; 64 * b.len()];
+    for (i, p) in b.iter().enumerate() {
+        if let Some(c) = Option::<pasta_curves::arithmetic::Coordinates<C>>::from(p.coordinates()) {
+            out[64 * i..64 * i + 32].copy_from_slice(c.x().to_repr().as_ref());
+            out[64 * i + 32..64 * i + 64].copy_from_slice(c.y().to_repr().as_ref());
+        } // identity stays (0, 0)
+    }
+    out
+}
+fn point_from_xyz<C: B200Curve>(xyz: &[u8; 96]) -> C::Curve
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    let f = |o: usize| {
+        let mut r = [0u8; 32];
+        r.copy_from_slice(&xyz[o..o + 32]);
+        C::Base::from_repr(r).unwrap()
+    };
+    C::CurveExt::new_jacobian(f(0), f(32), f(64)).unwrap().into()
+}
+
+/// Drop-in for `halo2_proofs::arithmetic::best_multiexp` (arithmetic.rs:143-180).
+pub fn best_multiexp<C: B200Curve>(coeffs: &[C::Scalar], bases: &[C]) -> C::Curve
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    assert_eq!(coeffs.len(), bases.len());
+    let s = scalars_to_bytes(coeffs);
+    let b = bases_to_bytes(bases);
+    let mut out = [0u8; 96];
+    check(unsafe {
+        h2_msm(C::CURVE_ID, s.as_ptr() as *const c_void, b.as_ptr() as *const c_void, coeffs.len(), REPR_CANONICAL,
+               out.as_mut_ptr() as *mut c_void)
+    });
+    point_from_xyz::<C>(&out)
+}
+
+/// Drop-in for `best_fft` with G = Scalar (arithmetic.rs:192-255).
+pub fn best_fft<F: PrimeField<Repr = [u8; 32]>>(field_id: c_int, a: &mut [F], omega: F, log_n: u32) {
+    assert_eq!(a.len(), 1 << log_n);
+    let mut bytes = scalars_to_bytes(a);
+    let w = omega.to_repr();
+    check(unsafe { h2_ntt(field_id, bytes.as_mut_ptr() as *mut c_void, w.as_ptr() as *const c_void, log_n, REPR_CANONICAL) });
+    for (i, x) in a.iter_mut().enumerate() {
+        let mut r = [0u8; 32];
+        r.copy_from_slice(&bytes[32 * i..32 * i + 32]);
+        *x = F::from_repr(r).unwrap();
+    }
+}
+
+/// Resident generator set for `Params::{commit, commit_lagrange}` (poly/commitment.rs:119-150):
+/// register `g ++ [w]` / `g_lagrange ++ [w]` once per `Params`, then each commit ships only the polynomial.
+pub struct ResidentBases<C: B200Curve> {
+    handle: u64,
+    n: usize,
+    _c: std::marker::PhantomData<C>,
+}
+impl<C: B200Curve> ResidentBases<C>
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    pub fn new(bases: &[C]) -> Self {
+        let b = bases_to_bytes(bases);
+        let mut handle = 0u64;
+        check(unsafe { h2_bases_register(C::CURVE_ID, b.as_ptr() as *const c_void, bases.len(), REPR_CANONICAL, &mut handle) });
+        Self { handle, n: bases.len(), _c: Default::default() }
+    }
+    /// <poly, bases[..n]> + r * bases[n]
+    pub fn commit(&self, poly: &[C::Scalar], r: C::Scalar) -> C::Curve {
+        assert_eq!(poly.len() + 1, self.n);
+        let s = scalars_to_bytes(poly);
+        let rb = r.to_repr();
+        let mut out = [0u8; 96];
+        check(unsafe {
+            h2_msm_registered(self.handle, s.as_ptr() as *const c_void, poly.len(), rb.as_ref().as_ptr() as *const c_void,
+                              REPR_CANONICAL, out.as_mut_ptr() as *mut c_void)
+        });
+        point_from_xyz::<C>(&out)
+    }
+}
+impl<C: B200Curve> Drop for ResidentBases<C> {
+    fn drop(&mut self) {
+        unsafe { h2_bases_release(self.handle) };
+    }
+}
+
+/// Call once per process (one process per GPU).
+pub fn init(device: i32) {
+    check(unsafe { h2_init(device) });
+}
