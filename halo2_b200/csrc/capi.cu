@@ -54,8 +54,8 @@ struct Context {
     bool have_last = false;
     uint32_t window_override = 0;
     // MSM scratch
-    DevBuf scal_in, bases_in, scal_canon, counts, cursor, refs, keys, bucket_sum, pkey, pstart, pend, ppt, red_sums, red_e,
-        scan_blocks, result, misc;
+    DevBuf scal_in, bases_in, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
+        wsum, scan_blocks, result, misc;
     // NTT scratch
     DevBuf ntt_io, ntt_out, ntt_work, pow2;
     std::vector<TwiddleEntry *> twiddles;
@@ -138,9 +138,10 @@ extern "C" int h2_shutdown(void) {
     if (!g_ctx.ready) return 0;
     cudaSetDevice(g_ctx.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.keys,
-                     &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.red_sums, &g_ctx.red_e,
-                     &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out, &g_ctx.ntt_work, &g_ctx.pow2};
+    DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
+                     &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
+                     &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
+                     &g_ctx.ntt_work, &g_ctx.pow2};
     for (DevBuf *b : all) b->release();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
@@ -254,6 +255,25 @@ template <class P> __global__ void bench_mul_kernel(fe *io, uint32_t iters) {
     }
     fe_store(io + 4 * i, a); fe_store(io + 4 * i + 1, b); fe_store(io + 4 * i + 2, c); fe_store(io + 4 * i + 3, d);
 }
+// single-warp latency microbenchmark of the serial building blocks (tails of the MSM)
+template <class P> __global__ void bench_latency_kernel(fe *io, uint32_t iters, int mode) {
+    uint32_t i = threadIdx.x;
+    fe a = fe_load(io + 4 * i), b = fe_load(io + 4 * i + 1), c = fe_load(io + 4 * i + 2), d = fe_load(io + 4 * i + 3);
+    a.v[7] &= 0x3fffffffu; b.v[7] &= 0x3fffffffu; c.v[7] &= 0x3fffffffu; d.v[7] &= 0x3fffffffu;
+    if (mode == 0) { for (uint32_t k = 0; k < iters; k++) a = fe_mul<P>(a, b); }
+    else if (mode == 1) { for (uint32_t k = 0; k < iters; k++) { a = fe_mul<P>(a, b); c = fe_mul<P>(c, d); } }
+    else if (mode == 2) { for (uint32_t k = 0; k < iters; k++) { a = fe_mul<P>(a, b); b = fe_mul<P>(b, c); c = fe_mul<P>(c, d); d = fe_mul<P>(d, a); } }
+    else if (mode == 6) { for (uint32_t k = 0; k < iters; k++) { fe_mul2<P>(a, a, b, c, c, d); } }
+    else {
+        affine g; g.x = fe_neg<P>(fe_one<P>()); g.y = fe_dbl<P>(fe_one<P>());
+        xyzz acc = xyzz_double_affine<P>(g), other = acc; xyzz_double<P>(other);
+        if (mode == 3) { for (uint32_t k = 0; k < iters; k++) xyzz_double<P>(acc); }
+        else if (mode == 4) { for (uint32_t k = 0; k < iters; k++) xyzz_add<P>(acc, other); }
+        else { for (uint32_t k = 0; k < iters; k++) xyzz_add_mixed<P>(acc, g); }
+        a = acc.x; b = acc.y; c = acc.zz; d = acc.zzz;
+    }
+    fe_store(io + 4 * i, a); fe_store(io + 4 * i + 1, b); fe_store(io + 4 * i + 2, c); fe_store(io + 4 * i + 3, d);
+}
 template <class P> __global__ void point_sum_kernel(const jacobian *pts, uint32_t g, int canonical, jacobian *out) {
     if (threadIdx.x || blockIdx.x) return;
     xyzz acc = xyzz_identity();
@@ -305,45 +325,65 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     msm_make_plan(p, n, c);
     if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
     if (scalars_mont && X.scal_canon.ensure(n * sizeof(fe))) return 1;
-    if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(p.G * 4) || X.refs.ensure(p.max_refs * 4) || X.keys.ensure(p.max_refs * 4) ||
+    const size_t small_words = 2 * (p.T + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
+    if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(p.G * 4) || X.refs.ensure(p.max_refs * 4) ||
+        X.size_hist.ensure(small_words * 4) || X.items.ensure(p.max_items * sizeof(uint2)) ||
         X.bucket_sum.ensure(p.G * sizeof(xyzz)) || X.pkey.ensure((p.part_total + 1) * 4) || X.pstart.ensure((p.part_total + 1) * 4) ||
         X.pend.ensure((p.part_total + 1) * 4) || X.ppt.ensure((p.part_total + 1) * sizeof(xyzz)) ||
-        X.red_sums.ensure(p.red_total * sizeof(xyzz)) || X.red_e.ensure(p.red_total * sizeof(xyzz)))
+        X.ra_t.ensure((size_t)p.W * p.m1 * sizeof(xyzz)) || X.ra_e.ensure((size_t)p.W * p.m1 * sizeof(xyzz)) ||
+        X.r0.ensure((size_t)p.W * p.nb0 * H2_R0_ROWS * sizeof(xyzz)) || X.r1.ensure((size_t)p.W * p.r1_rows * sizeof(xyzz)) ||
+        X.wsum.ensure((size_t)p.W * sizeof(xyzz)))
         return 1;
     MsmBuffers M;
     M.scalars = d_scalars; M.bases = d_bases; M.scalars_mont = scalars_mont ? 1u : 0u;
     M.scal_canon = X.scal_canon.as<fe>();
     M.counts = X.counts.as<uint32_t>(); M.cursor = X.cursor.as<uint32_t>();
-    M.refs = X.refs.as<uint32_t>(); M.keys = X.keys.as<uint32_t>();
+    M.refs = X.refs.as<uint32_t>();
+    M.size_hist = X.size_hist.as<uint32_t>(); M.size_cursor = M.size_hist + (p.T + 2); M.flags = M.size_cursor + (p.T + 2);
+    M.items = X.items.as<uint2>();
     M.bucket_sum = X.bucket_sum.as<xyzz>();
     M.pkey = X.pkey.as<uint32_t>(); M.pstart = X.pstart.as<uint32_t>(); M.pend = X.pend.as<uint32_t>(); M.ppt = X.ppt.as<xyzz>();
-    M.red_sums = X.red_sums.as<xyzz>(); M.red_e = X.red_e.as<xyzz>();
-    M.win_sums = nullptr; M.result = d_out;
+    M.ra_t = X.ra_t.as<xyzz>(); M.ra_e = X.ra_e.as<xyzz>(); M.r0 = X.r0.as<xyzz>(); M.r1 = X.r1.as<xyzz>();
+    M.wsum = X.wsum.as<xyzz>(); M.result = d_out;
 
     CU(cudaMemsetAsync(M.counts, 0, (p.G + 1) * 4, s));
     CU(cudaMemsetAsync(M.cursor, 0, p.G * 4, s));
+    CU(cudaMemsetAsync(M.size_hist, 0, small_words * 4, s));
     CU(cudaMemsetAsync(M.bucket_sum, 0, p.G * sizeof(xyzz), s));
-    if (p.part_total) CU(cudaMemsetAsync(M.pkey, 0xff, p.part_total * 4, s));
+    CU(cudaMemsetAsync(M.pkey, 0xff, p.part_total * 4, s));
 
     auto k_hist = msm_hist_kernel<P, PS>;
     auto k_scatter = msm_scatter_kernel<P, PS>;
+    auto k_ihist = msm_item_hist_kernel<P, PS>;
+    auto k_ibases = msm_item_bases_kernel<P, PS>;
+    auto k_iplace = msm_item_place_kernel<P, PS>;
     auto k_accum0 = msm_accum0_kernel<P, PS>;
     auto k_accumN = msm_accumN_kernel<P, PS>;
-    auto k_reduce = msm_reduce_kernel<P, PS>;
-    auto k_combine = msm_combine_kernel<P, PS>;
+    auto k_rest = msm_accum_rest_kernel<P, PS>;
+    auto k_reduceA = msm_reduceA_kernel<P, PS>;
+    auto k_r0 = msm_r0_kernel<P, PS>;
+    auto k_r1 = msm_r1_kernel<P, PS>;
+    auto k_wsum = msm_wsum_kernel<P, PS>;
+    auto k_final = msm_final_kernel<P, PS>;
+    // K2/K3: counting sort of the (point, window) references by bucket
     LAUNCH(k_hist, blocks_for(n, 256), 256, 0, s, p, M);
     if (exclusive_scan_u32(M.counts, p.G + 1, s)) return 1;
     LAUNCH(k_scatter, blocks_for(n, 256), 256, 0, s, p, M);
+    // K4: work items (one per bucket, oversized buckets split), largest first
+    LAUNCH(k_ihist, blocks_for(p.G, 256), 256, 0, s, p, M);
+    LAUNCH(k_ibases, 1, 32, 0, s, p, M);
+    LAUNCH(k_iplace, blocks_for(p.G, 256), 256, 0, s, p, M);
     prof_begin(PROF_MSM_ACCUM0, s);
-    LAUNCH(k_accum0, blocks_for(p.acc_threads[0], 128), 128, 0, s, p, M);
+    LAUNCH(k_accum0, blocks_for(p.max_items, 128), 128, 0, s, p, M);
     prof_end(s);
-    for (uint32_t lv = 1; lv < p.acc_levels; lv++)
-        LAUNCH(k_accumN, blocks_for(p.acc_threads[lv], 128), 128, 0, s, p, M, lv);
-    for (uint32_t lv = 0; lv < p.red_levels; lv++) {
-        uint32_t m_out = (p.red_m_in[lv] + (1u << p.red_log_l[lv]) - 1) >> p.red_log_l[lv];
-        LAUNCH(k_reduce, blocks_for((uint64_t)p.W * m_out, 128), 128, 0, s, p, M, lv);
-    }
-    LAUNCH(k_combine, 1, 32, 0, s, p, M, (uint32_t)out_canonical);
+    if (p.acc_levels > 1) LAUNCH(k_accumN, blocks_for(p.acc_threads[1], 128), 128, 0, s, p, M, 1u);
+    if (p.acc_levels > 2) LAUNCH(k_rest, 1, 256, 0, s, p, M);
+    // K5: bucket reduce and window combine
+    LAUNCH(k_reduceA, blocks_for((uint64_t)p.W * p.m1, 128), 128, 0, s, p, M);
+    LAUNCH(k_r0, blocks_for((uint64_t)p.W * p.nb0 * (2 + p.bits0), 128), 128, 0, s, p, M);
+    LAUNCH(k_r1, p.W * p.r1_rows, 128, 0, s, p, M);
+    LAUNCH(k_wsum, p.W, 32, 0, s, p, M);
+    LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
     return 0;
 }
 
@@ -698,6 +738,29 @@ extern "C" int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_
         CU(cudaEventRecord(e0, s));
         if (field == H2_FIELD_FP) LAUNCH(bench_mul_kernel<FpParams>, blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
         else LAUNCH(bench_mul_kernel<FqParams>, blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        CU(cudaEventRecord(e1, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    CU(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return scratch_release(s);
+}
+
+// mode: 0 dependent mul chain, 1 two chains, 2 four chains, 3 xyzz_double, 4 xyzz_add, 5 xyzz_add_mixed;
+// one warp, `iters` iterations; *ms = elapsed.
+extern "C" int h2_bench_latency(int mode, uint32_t iters, float *ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.misc.ensure(32 * 4 * sizeof(fe))) return 1;
+    CU(cudaMemsetAsync(X.misc.p, 0x11, 32 * 4 * sizeof(fe), s));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {
+        CU(cudaEventRecord(e0, s));
+        LAUNCH(bench_latency_kernel<FpParams>, 1, 32, 0, s, X.misc.as<fe>(), iters, mode);
         CU(cudaEventRecord(e1, s));
         CU(cudaStreamSynchronize(s));
     }

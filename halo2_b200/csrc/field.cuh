@@ -29,6 +29,8 @@
 // host-only build (tests/kernel_emul): minimal stand-ins for the CUDA vector types
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+struct alignas(8) uint2 { uint32_t x, y; };
+inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
 #endif
 
 namespace h2 {
@@ -164,21 +166,23 @@ template <class P> H2_HD fe fe_neg(const fe &a) {
 }
 
 // ------------------------------------------------------------------ Montgomery multiplication
-// One CIOS iteration on the even/odd split accumulator.
+// CIOS on an even/odd split accumulator:
 //   ev[k] sits at limb position k      (pairs (0,1)(2,3)(4,5)(6,7))
 //   od[k] sits at limb position k + 1  (pairs (1,2)(3,4)(5,6)(7,8))
-// Adds a * bi, then q * m with q = -ev[0], leaving ev[0] == 0.
-template <class P, bool FIRST> H2_HD void mont_iter(uint32_t (&ev)[8], uint32_t (&od)[8], const fe &a, uint32_t bi) {
-    using namespace ptx;
+// One iteration adds a * bi, then q * m with q = -ev[0] (leaving ev[0] == 0), then the window
+// slides down one limb.  The iteration is cut into four carry chains (product odd/even,
+// reduction odd/even) so that fe_mul2 can interleave the chains of two INDEPENDENT
+// multiplications in program order: ptxas overlaps adjacent independent chains but does not
+// reorder across whole multiplications, and a lone warp (the MSM's serial tails) otherwise
+// runs at ~0.36 IPC.
+namespace mont {
+using namespace ptx;
+// a * bi, odd columns.  CARRY_IN: the caller has just issued the add.cc that folds the
+// left-over limb into ev[0]; its carry enters at position 1 = od[0].
+template <bool FIRST> H2_HD void prod_od(uint32_t (&od)[8], const fe &a, uint32_t bi) {
     if (FIRST) {
-        for (int k = 0; k < 4; k++) {
-            od[2 * k] = mul_lo(a.v[2 * k + 1], bi);
-            od[2 * k + 1] = mul_hi(a.v[2 * k + 1], bi);
-            ev[2 * k] = mul_lo(a.v[2 * k], bi);
-            ev[2 * k + 1] = mul_hi(a.v[2 * k], bi);
-        }
+        for (int k = 0; k < 4; k++) { od[2 * k] = mul_lo(a.v[2 * k + 1], bi); od[2 * k + 1] = mul_hi(a.v[2 * k + 1], bi); }
     } else {
-        // (the caller has just issued add.cc ev[0] += leftover; its carry enters here)
         od[0] = madc_lo_cc(a.v[1], bi, od[0]);
         od[1] = madc_hi_cc(a.v[1], bi, od[1]);
         od[2] = madc_lo_cc(a.v[3], bi, od[2]);
@@ -187,6 +191,12 @@ template <class P, bool FIRST> H2_HD void mont_iter(uint32_t (&ev)[8], uint32_t 
         od[5] = madc_hi_cc(a.v[5], bi, od[5]);
         od[6] = madc_lo_cc(a.v[7], bi, od[6]);
         od[7] = madc_hi(a.v[7], bi, od[7]);          // no carry out: od <= A / 2^32 < 2^256
+    }
+}
+template <bool FIRST> H2_HD void prod_ev(uint32_t (&ev)[8], uint32_t (&od)[8], const fe &a, uint32_t bi) {
+    if (FIRST) {
+        for (int k = 0; k < 4; k++) { ev[2 * k] = mul_lo(a.v[2 * k], bi); ev[2 * k + 1] = mul_hi(a.v[2 * k], bi); }
+    } else {
         ev[0] = mad_lo_cc(a.v[0], bi, ev[0]);
         ev[1] = madc_hi_cc(a.v[0], bi, ev[1]);
         ev[2] = madc_lo_cc(a.v[2], bi, ev[2]);
@@ -197,8 +207,9 @@ template <class P, bool FIRST> H2_HD void mont_iter(uint32_t (&ev)[8], uint32_t 
         ev[7] = madc_hi_cc(a.v[6], bi, ev[7]);
         od[7] = addc(od[7], 0u);                     // carry out of position 7 lands on position 8
     }
-    uint32_t q = 0u - ev[0];
-    // q * m, odd columns: m1 @1, m3 @3, 2^30 @7
+}
+// q * m, odd columns: m1 @1, m3 @3, 2^30 @7
+template <class P> H2_HD void red_od(uint32_t (&od)[8], uint32_t q) {
     od[0] = mad_lo_cc(q, P::M1, od[0]);
     od[1] = madc_hi_cc(q, P::M1, od[1]);
     od[2] = madc_lo_cc(q, P::M3, od[2]);
@@ -207,7 +218,9 @@ template <class P, bool FIRST> H2_HD void mont_iter(uint32_t (&ev)[8], uint32_t 
     od[5] = addc_cc(od[5], 0u);
     od[6] = madc_lo_cc(q, H2_M7, od[6]);
     od[7] = madc_hi(q, H2_M7, od[7]);
-    // even columns: 1 @0, m2 @2
+}
+// q * m, even columns: 1 @0, m2 @2
+template <class P> H2_HD void red_ev(uint32_t (&ev)[8], uint32_t (&od)[8], uint32_t q) {
     ev[0] = add_cc(ev[0], q);                        // == 0, carry = (old ev[0] != 0)
     ev[1] = addc_cc(ev[1], 0u);
     ev[2] = madc_lo_cc(q, P::M2, ev[2]);
@@ -218,46 +231,94 @@ template <class P, bool FIRST> H2_HD void mont_iter(uint32_t (&ev)[8], uint32_t 
     ev[7] = addc_cc(ev[7], 0u);
     od[7] = addc(od[7], 0u);
 }
-
-// Shift the window down one limb: position 0 (== 0) drops out, ev <- od, od <- ev >> 2 limbs,
-// and the left-over ev[1] (new position 0) is folded into the new ev[0]; the carry of that
-// add is consumed by the first madc of the next iteration (position 1 = new od[0]).
-template <class P, bool FIRST> H2_HD void mont_iter_pair(uint32_t (&x)[8], uint32_t (&y)[8], const fe &a, uint32_t b0, uint32_t b1) {
-    // iteration with (ev, od) = (x, y)
-    mont_iter<P, FIRST>(x, y, a, b0);
-    // after shift: ev' = y, od' = {x[2..7], 0, 0}, leftover = x[1]
+// window slide: position 0 (== 0) drops out, ev <- od, od <- ev >> 2 limbs; returns the
+// left-over limb (new position 0) that the next iteration folds into its ev[0].
+H2_HD uint32_t slide(uint32_t (&x)[8]) {
     uint32_t left = x[1];
     for (int k = 0; k < 6; k++) x[k] = x[k + 2];
     x[6] = 0; x[7] = 0;
-    y[0] = ptx::add_cc(y[0], left);
-    mont_iter<P, false>(y, x, a, b1);
-    // after shift: ev'' = x, od'' = {y[2..7], 0, 0}, leftover = y[1]
-    left = y[1];
-    for (int k = 0; k < 6; k++) y[k] = y[k + 2];
-    y[6] = 0; y[7] = 0;
-    x[0] = ptx::add_cc(x[0], left);
+    return left;
 }
-
-template <class P> H2_HD fe fe_mul(const fe &a, const fe &b) {
-    uint32_t x[8], y[8];
-    mont_iter_pair<P, true>(x, y, a, b.v[0], b.v[1]);
-    mont_iter_pair<P, false>(x, y, a, b.v[2], b.v[3]);
-    mont_iter_pair<P, false>(x, y, a, b.v[4], b.v[5]);
-    mont_iter_pair<P, false>(x, y, a, b.v[6], b.v[7]);
-    // After the last shift the result is ev (x, positions 0..7) + od (y, positions 1..8 with
-    // y[7] == 0 because the value is < 2m < 2^256); x[0] already holds x[0] + leftover and
-    // its carry is still in CC.
+// result = ev (positions 0..7) + od (positions 1..8, od[7] == 0 since the value is < 2m);
+// the carry of the last fold-in add is still pending in CC.
+template <class P> H2_HD fe finish(const uint32_t (&x)[8], const uint32_t (&y)[8]) {
     fe r;
     r.v[0] = x[0];
-    r.v[1] = ptx::addc_cc(x[1], y[0]);
-    r.v[2] = ptx::addc_cc(x[2], y[1]);
-    r.v[3] = ptx::addc_cc(x[3], y[2]);
-    r.v[4] = ptx::addc_cc(x[4], y[3]);
-    r.v[5] = ptx::addc_cc(x[5], y[4]);
-    r.v[6] = ptx::addc_cc(x[6], y[5]);
-    r.v[7] = ptx::addc(x[7], y[6]);
+    r.v[1] = addc_cc(x[1], y[0]);
+    r.v[2] = addc_cc(x[2], y[1]);
+    r.v[3] = addc_cc(x[3], y[2]);
+    r.v[4] = addc_cc(x[4], y[3]);
+    r.v[5] = addc_cc(x[5], y[4]);
+    r.v[6] = addc_cc(x[6], y[5]);
+    r.v[7] = addc(x[7], y[6]);
+    return r;
+}
+// one iteration; (ev, od) on entry, roles swapped on exit
+template <class P, bool FIRST> H2_HD void iter(uint32_t (&ev)[8], uint32_t (&od)[8], const fe &a, uint32_t bi, uint32_t left) {
+    if (!FIRST) ev[0] = add_cc(ev[0], left);
+    prod_od<FIRST>(od, a, bi);
+    prod_ev<FIRST>(ev, od, a, bi);
+    uint32_t q = 0u - ev[0];
+    red_od<P>(od, q);
+    red_ev<P>(ev, od, q);
+}
+}  // namespace mont
+
+template <class P> H2_HD fe fe_mul(const fe &a, const fe &b) {
+    uint32_t x[8], y[8], left;
+    mont::iter<P, true>(x, y, a, b.v[0], 0u);  left = mont::slide(x);
+    mont::iter<P, false>(y, x, a, b.v[1], left); left = mont::slide(y);
+    mont::iter<P, false>(x, y, a, b.v[2], left); left = mont::slide(x);
+    mont::iter<P, false>(y, x, a, b.v[3], left); left = mont::slide(y);
+    mont::iter<P, false>(x, y, a, b.v[4], left); left = mont::slide(x);
+    mont::iter<P, false>(y, x, a, b.v[5], left); left = mont::slide(y);
+    mont::iter<P, false>(x, y, a, b.v[6], left); left = mont::slide(x);
+    mont::iter<P, false>(y, x, a, b.v[7], left); left = mont::slide(y);
+    x[0] = ptx::add_cc(x[0], left);
+    fe r = mont::finish<P>(x, y);
     fe_cond_sub_mod<P>(r);
     return r;
+}
+
+// Two independent products r0 = a0 * b0, r1 = a1 * b1 with their carry chains interleaved.
+template <class P, bool FIRST>
+H2_HD void mont_iter2(uint32_t (&ev0)[8], uint32_t (&od0)[8], const fe &a0, uint32_t b0, uint32_t l0,
+                      uint32_t (&ev1)[8], uint32_t (&od1)[8], const fe &a1, uint32_t b1, uint32_t l1) {
+    using namespace mont;
+    if (!FIRST) ev0[0] = ptx::add_cc(ev0[0], l0);
+    prod_od<FIRST>(od0, a0, b0);
+    if (!FIRST) ev1[0] = ptx::add_cc(ev1[0], l1);
+    prod_od<FIRST>(od1, a1, b1);
+    prod_ev<FIRST>(ev0, od0, a0, b0);
+    prod_ev<FIRST>(ev1, od1, a1, b1);
+    uint32_t q0 = 0u - ev0[0], q1 = 0u - ev1[0];
+    red_od<P>(od0, q0);
+    red_od<P>(od1, q1);
+    red_ev<P>(ev0, od0, q0);
+    red_ev<P>(ev1, od1, q1);
+}
+template <class P> H2_HD void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1, const fe &a1, const fe &b1) {
+    uint32_t x0[8], y0[8], x1[8], y1[8], l0, l1;
+    mont_iter2<P, true>(x0, y0, a0, b0.v[0], 0u, x1, y1, a1, b1.v[0], 0u);
+    l0 = mont::slide(x0); l1 = mont::slide(x1);
+#define H2_IT2(EV0, OD0, EV1, OD1, K)                                                  \
+    mont_iter2<P, false>(EV0, OD0, a0, b0.v[K], l0, EV1, OD1, a1, b1.v[K], l1);        \
+    l0 = mont::slide(EV0); l1 = mont::slide(EV1);
+    H2_IT2(y0, x0, y1, x1, 1)
+    H2_IT2(x0, y0, x1, y1, 2)
+    H2_IT2(y0, x0, y1, x1, 3)
+    H2_IT2(x0, y0, x1, y1, 4)
+    H2_IT2(y0, x0, y1, x1, 5)
+    H2_IT2(x0, y0, x1, y1, 6)
+    H2_IT2(y0, x0, y1, x1, 7)
+#undef H2_IT2
+    x0[0] = ptx::add_cc(x0[0], l0);
+    fe t0 = mont::finish<P>(x0, y0);
+    x1[0] = ptx::add_cc(x1[0], l1);
+    fe t1 = mont::finish<P>(x1, y1);
+    fe_cond_sub_mod<P>(t0);
+    fe_cond_sub_mod<P>(t1);
+    r0 = t0; r1 = t1;
 }
 template <class P> H2_HD fe fe_sqr(const fe &a) { return fe_mul<P>(a, a); }
 

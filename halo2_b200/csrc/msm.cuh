@@ -7,16 +7,19 @@
 //   K2  digits + histogram   canonical scalar -> signed c-bit digits (zero digits skipped,
 //                            like arithmetic.rs:78); count per (window, |digit|) bucket
 //   K3  scan + scatter       counting sort of point references by global bucket id
-//   K4  accumulate           fixed-size chunks of the sorted reference list, one chunk per
-//                            thread, mixed XYZZ adds; a chunk is cut at bucket boundaries;
-//                            pieces that do not cover a whole bucket become "partials" that
-//                            the next (16x smaller) level merges.  Work per thread is
-//                            constant, so skewed scalars (0/1 selector columns, all-equal
-//                            scalars: SURVEY.md section 7 "MSM load imbalance") cost the same
-//                            as uniform ones.
-//   K5  bucket reduce        sum_b b * B[b] per window by hierarchical running sums (the
-//                            parallel form of arithmetic.rs:86-92), then the window combine
-//                            sum_w 2^(c w) S_w (arithmetic.rs:163,166).
+//   K4  accumulate           one work item per bucket (mixed XYZZ adds over its references), items
+//                            ordered by size, largest first, so the lanes of a warp carry equal
+//                            work and long items start early.  A bucket with more than T
+//                            references is split into T-sized items whose results ("partials")
+//                            are merged by 8x-shrinking levels: 0/1 selector columns, all-equal
+//                            scalars etc. (SURVEY.md section 7 "MSM load imbalance") stay
+//                            parallel, while ordinary inputs produce no partials at all.
+//   K5  bucket reduce        S_w = sum_b b * B[b] per window (the parallel form of
+//                            arithmetic.rs:86-92): chunked running sums (level A), then masked
+//                            tree sums D_k = sum of chunk totals whose index has bit k set, so
+//                            that S_w = E + T + 2^l0 * sum_k 2^k D_k needs one short Horner.
+//       window combine       R = sum_w 2^(c w) S_w (arithmetic.rs:163,166): every (window, row)
+//                            term shifted in parallel, then tree sums.
 //
 // Signed digits halve the bucket count: digit d in [-(2^(c-1) - 1), 2^(c-1)], a negative digit
 // adds the negated base to bucket |d|.  The group element computed is identical to the
@@ -35,6 +38,7 @@ H2_HD void st_jacobian(jacobian *p, const jacobian &a) { fe_store(&p->x, a.x); f
 
 #define H2_MSM_INVALID_KEY 0xffffffffu
 #define H2_MSM_MAX_LEVELS 12
+#define H2_R0_ROWS 7          // per 32-entry block: T, E, D_0..D_4
 
 struct MsmPlan {
     uint64_t n;          // number of (scalar, base) pairs
@@ -43,24 +47,28 @@ struct MsmPlan {
     uint32_t B;          // buckets per window = 2^(c-1)
     uint64_t G;          // total buckets = W * B
     uint64_t max_refs;   // n * W
-    // accumulate levels: level 0 consumes refs, level i>0 consumes partial slots
-    uint32_t acc_levels;
-    uint32_t acc_chunk[H2_MSM_MAX_LEVELS];     // items per thread
-    uint64_t acc_threads[H2_MSM_MAX_LEVELS];   // threads at that level
-    uint64_t acc_slots[H2_MSM_MAX_LEVELS];     // INPUT slots of level i (level 0: max_refs)
-    uint64_t part_offset[H2_MSM_MAX_LEVELS];   // offset of level-i input slots in the partial arrays (i >= 1)
-    uint64_t part_total;                       // total partial slots
-    // bucket-reduce levels
-    uint32_t red_levels;
-    uint32_t red_log_l[H2_MSM_MAX_LEVELS];     // log2 chunk length of level i
-    uint32_t red_m_in[H2_MSM_MAX_LEVELS];      // entries per window entering level i
-    uint32_t red_dbl[H2_MSM_MAX_LEVELS];       // doublings applied to acc at level i
-    uint64_t red_offset[H2_MSM_MAX_LEVELS];    // offset of level-i OUTPUT in sums/E arrays
-    uint64_t red_total;
+    uint32_t T;          // references per work item (larger buckets are split)
+    uint64_t max_items;  // upper bound of work items = G + max_refs / T
+    // partial-merge levels: level 1 consumes the slots written by split buckets
+    uint32_t acc_levels;                       // level 0 = the bucket items
+    uint32_t acc_chunk[H2_MSM_MAX_LEVELS];     // slots per thread (levels >= 1)
+    uint64_t acc_threads[H2_MSM_MAX_LEVELS];   // threads at that level (upper bound)
+    uint64_t acc_slots[H2_MSM_MAX_LEVELS];     // INPUT slots of level i (i >= 1)
+    uint64_t part_offset[H2_MSM_MAX_LEVELS];   // offset of level-i input slots in the partial arrays
+    uint64_t part_total;
+    // bucket reduce
+    uint32_t l0;         // log2 of the level-A chunk
+    uint32_t m1;         // entries per window after level A = B >> l0   (power of two)
+    uint32_t nb0;        // 32-entry blocks per window = ceil(m1 / 32)   (power of two)
+    uint32_t bits0;      // bits produced by R0 = min(5, log2 m1)
+    uint32_t bits1;      // bits produced by R1 = log2 nb0
+    uint32_t r1_rows;    // 2 + bits0 + bits1
 };
 
+inline uint32_t ilog2_u32(uint32_t v) { uint32_t r = 0; while (r < 31 && (1u << (r + 1)) <= v) r++; return r; }
+
 inline uint32_t msm_default_window(uint64_t n) {
-    // Tuned for XYZZ cost model: n*W mixed adds (10 M) + 2*W*2^(c-1) full adds (14 M).
+    // Cost model (XYZZ): n * W mixed adds (10 M) + 2 * W * 2^(c-1) full adds (14 M).
     if (n < 32) return 3;
     uint32_t lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
@@ -70,48 +78,41 @@ inline uint32_t msm_default_window(uint64_t n) {
     return c;
 }
 
-inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c) {
+inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0) {
     p.n = n; p.c = c;
     p.W = (256 + c - 1) / c;
     p.B = 1u << (c - 1);
     p.G = (uint64_t)p.W * p.B;
     p.max_refs = n * p.W;
-    // level 0 chunk: aim for >= 64K threads, between 4 and 32 refs each
-    uint64_t k0 = p.max_refs / 65536;
-    if (k0 < 4) k0 = 4;
-    if (k0 > 32) k0 = 32;
-    uint32_t lv = 0;
-    uint64_t slots = p.max_refs;
-    p.part_total = 0;
-    p.part_offset[0] = 0;            // level 0 reads refs/keys, not partial slots
+    p.T = force_t ? force_t : 128u;
+    p.max_items = p.G + p.max_refs / p.T + 1;
+    // partial slots: slot(start, chunk) = 2 * (start / T) + (chunk > 0), see item_slot()
+    uint32_t lv = 1;
+    uint64_t slots = 2 * (p.max_refs / p.T + 1);
+    p.acc_chunk[0] = p.T; p.acc_threads[0] = p.max_items; p.acc_slots[0] = p.max_refs; p.part_offset[0] = 0;
+    p.part_offset[1] = 0;
+    p.part_total = slots;
     for (;;) {
-        uint32_t chunk = lv == 0 ? (uint32_t)k0 : 16u;
+        uint32_t chunk = force_kn ? force_kn : 16u;
+        if (lv == H2_MSM_MAX_LEVELS - 1) chunk = (uint32_t)slots;   // last allowed level: one thread takes the rest
         uint64_t threads = (slots + chunk - 1) / chunk;
         if (threads == 0) threads = 1;
         p.acc_chunk[lv] = chunk; p.acc_threads[lv] = threads; p.acc_slots[lv] = slots;
         lv++;
         if (threads == 1) break;     // a single thread sees every remaining piece: all flushes complete
-        // the 2 output slots per thread of this level are the input of the next
         p.part_offset[lv] = p.part_total;
-        slots = 2 * threads;
+        slots = 2 * threads;         // the 2 output slots per thread are the input of the next level
         p.part_total += slots;
     }
     p.acc_levels = lv;
-    // bucket reduce: level 0 chunks of 8 (parallel), deeper levels of 4 (short serial chains)
-    uint32_t m = p.B, rl = 0, dbl = 0;
-    p.red_total = 0;
-    while (true) {
-        uint32_t l = rl == 0 ? 3u : 2u;
-        p.red_log_l[rl] = l; p.red_m_in[rl] = m; p.red_dbl[rl] = dbl;
-        uint32_t m_out = (m + (1u << l) - 1) >> l;
-        p.red_offset[rl] = p.red_total;
-        p.red_total += (uint64_t)p.W * m_out;
-        dbl += l;
-        rl++;
-        m = m_out;
-        if (m == 1) break;
-    }
-    p.red_levels = rl;
+    // bucket reduce
+    p.l0 = c - 1 < 3 ? c - 1 : 3;
+    p.m1 = p.B >> p.l0;
+    p.nb0 = (p.m1 + 31) / 32;
+    uint32_t lm = ilog2_u32(p.m1);
+    p.bits0 = lm < 5 ? lm : 5;
+    p.bits1 = ilog2_u32(p.nb0);
+    p.r1_rows = 2 + p.bits0 + p.bits1;
 }
 
 struct MsmBuffers {
@@ -123,13 +124,18 @@ struct MsmBuffers {
     fe *scal_canon;           // n (only when scalars_mont)
     uint32_t *counts;         // G + 1  (histogram, then exclusive offsets after the scan)
     uint32_t *cursor;         // G
-    uint32_t *refs;           // max_refs   point index | sign << 31
-    uint32_t *keys;           // max_refs   global bucket id
+    uint32_t *refs;           // max_refs   point index | sign << 31, sorted by bucket id
+    uint32_t *size_hist;      // T + 2: [s] = number of work items of s references; [T + 1] = item count
+    uint32_t *size_cursor;    // T + 1
+    uint32_t *flags;          // [0] = some bucket exceeded T references (partials exist)
+    uint2 *items;             // max_items  (bucket id, first reference), sorted by size descending
     xyzz *bucket_sum;         // G
     uint32_t *pkey, *pstart, *pend;   // part_total
     xyzz *ppt;                // part_total
-    xyzz *red_sums, *red_e;   // red_total
-    xyzz *win_sums;           // W
+    xyzz *ra_t, *ra_e;        // W * m1            level A: chunk totals / weighted sums
+    xyzz *r0;                 // W * nb0 * 7       R0: per 32-block T, E, D_0..4
+    xyzz *r1;                 // W * r1_rows       R1: per window T, E, D_0..
+    xyzz *wsum;               // W                 2^(c w) S_w
     jacobian *result;         // 1
 };
 
@@ -139,8 +145,7 @@ template <class P, class PS> struct Msm {
     static H2_HD int32_t next_digit(const uint32_t (&s)[8], uint32_t w, uint32_t c, uint32_t &carry) {
         uint32_t bit = w * c, idx = bit >> 5, sh = bit & 31;
         uint64_t v = 0;
-        // register-resident select instead of dynamic indexing
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 8; i++) {   // register-resident select instead of dynamic indexing
             if ((uint32_t)i == idx) v |= s[i];
             if ((uint32_t)i == idx + 1) v |= (uint64_t)s[i] << 32;
         }
@@ -160,59 +165,75 @@ template <class P, class PS> struct Msm {
         for (int k = 0; k < 8; k++) s[k] = x.v[k];
     }
 
-    // ---- K4 helpers
+    // ---- K4: work items.  Bucket g with cnt references yields ceil(cnt / T) items; item k covers
+    // references [counts[g] + k T, min(+T, counts[g+1])).
+    // Partial slot of a piece that does not cover its whole bucket: 2 * (start / T) + (k == 0).
+    // Collision-free (a split bucket holds > T references, so two first-pieces never share a
+    // T-aligned block, nor do two later pieces) and increasing with `start` (inside one block a
+    // later piece of bucket g precedes the first piece of a bucket g' > g), which is what the merge
+    // levels need: same-bucket partials in position order, no other key in between.
+    static H2_HD uint64_t item_slot(const MsmPlan &p, uint32_t start, bool first_piece) {
+        return 2ull * (start / p.T) + (first_piece ? 1 : 0);
+    }
+    // size histogram: thread per bucket
+    static H2_HD void count_items(const MsmPlan &p, const MsmBuffers &M, uint64_t g, uint32_t &nfull, uint32_t &rem) {
+        uint32_t cnt = M.counts[g + 1] - M.counts[g];
+        nfull = cnt / p.T; rem = cnt % p.T;
+        if (cnt > p.T) M.flags[0] = 1;
+    }
+    // descending-size base offsets from the histogram (single thread): base[s] = #items larger than s
+    static H2_HD void size_bases_body(const MsmPlan &p, const MsmBuffers &M) {
+        uint32_t run = 0;
+        for (uint32_t sz = p.T; sz >= 1; sz--) {
+            uint32_t c = M.size_hist[sz];
+            M.size_cursor[sz] = run;
+            run += c;
+        }
+        M.size_cursor[0] = run;
+        M.size_hist[p.T + 1] = run;     // total number of items
+    }
+
     struct Flusher {
-        const MsmPlan *plan; const MsmBuffers *M;
-        uint64_t out_base;     // first output slot of this thread (2 per thread), or ~0 if last level
-        uint32_t used;
-        H2_HD void flush(uint32_t g, uint32_t a, uint32_t b, const xyzz &acc) {
+        const MsmBuffers *M;
+        H2_HD void flush(uint32_t g, uint32_t a, uint32_t b, const xyzz &acc, uint64_t slot) {
             uint32_t lo = M->counts[g], hi = M->counts[g + 1];
             if (a == lo && b == hi) {
                 st_xyzz(M->bucket_sum + g, acc);
             } else {
-                uint64_t slot = out_base + used;
-                used++;
                 M->pkey[slot] = g; M->pstart[slot] = a; M->pend[slot] = b;
                 st_xyzz(M->ppt + slot, acc);
             }
         }
     };
 
-    // level 0: chunk of the sorted reference list
+    // level 0: one work item
     static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
-        const uint64_t total = M.counts[p.G];
-        const uint32_t K = p.acc_chunk[0];
-        uint64_t start = t * K;
-        if (start >= total) return;
-        uint64_t end = start + K < total ? start + K : total;
-        Flusher F; F.plan = &p; F.M = &M; F.used = 0;
-        F.out_base = p.acc_levels > 1 ? p.part_offset[1] + 2 * t : 0;
+        if (t >= M.size_hist[p.T + 1]) return;
+        uint2 it = M.items[t];
+        const uint32_t g = it.x, start = it.y, lo = M.counts[g], hi = M.counts[g + 1];
+        const uint32_t end = start + p.T < hi ? start + p.T : hi;
         xyzz acc = xyzz_identity();
-        uint32_t cur = M.keys[start];
-        uint32_t seg = (uint32_t)start;
-        for (uint64_t pos = start; pos < end; pos++) {
-            uint32_t g = M.keys[pos];
-            if (g != cur) {
-                F.flush(cur, seg, (uint32_t)pos, acc);
-                acc = xyzz_identity(); cur = g; seg = (uint32_t)pos;
-            }
+        for (uint32_t pos = start; pos < end; pos++) {
             uint32_t ref = M.refs[pos];
             affine b = ld_affine(M.bases + (ref & 0x7fffffffu));
             if (ref >> 31) b.y = fe_neg<P>(b.y);
             xyzz_add_mixed<P>(acc, b);
         }
-        F.flush(cur, seg, (uint32_t)end, acc);
+        Flusher F; F.M = &M;
+        F.flush(g, start, end, acc, p.part_offset[1] + item_slot(p, start, start == lo));
     }
 
-    // level >= 1: chunk of partial slots
+    // level >= 1: chunk of partial slots; merged pieces go to 2 output slots per thread: slot 0 if
+    // the piece lacks its bucket's start (it continues the previous thread's), slot 1 otherwise.
     static H2_HD void accumN_body(const MsmPlan &p, const MsmBuffers &M, uint32_t lv, uint64_t t) {
+        if (!M.flags[0]) return;     // no bucket was split: nothing to merge
         const uint32_t K = p.acc_chunk[lv];
         const uint64_t in_base = p.part_offset[lv], slots = p.acc_slots[lv];
         uint64_t start = t * K;
-        if (start >= slots) return;
         uint64_t end = start + K < slots ? start + K : slots;
-        Flusher F; F.plan = &p; F.M = &M; F.used = 0;
-        F.out_base = lv + 1 < p.acc_levels ? p.part_offset[lv + 1] + 2 * t : 0;
+        if (start >= end) return;
+        Flusher F; F.M = &M;
+        const uint64_t out_base = (lv + 1 < p.acc_levels ? p.part_offset[lv + 1] : 0) + 2 * t;
         bool have = false;
         xyzz acc = xyzz_identity();
         uint32_t cur = 0, a = 0, b = 0;
@@ -223,46 +244,59 @@ template <class P, class PS> struct Msm {
                 xyzz_add<P>(acc, ld_xyzz(M.ppt + s));
                 b = M.pend[s];
             } else {
-                if (have) F.flush(cur, a, b, acc);
+                if (have) F.flush(cur, a, b, acc, out_base + (a > M.counts[cur] ? 0 : 1));
                 have = true; cur = g; a = M.pstart[s]; b = M.pend[s]; acc = ld_xyzz(M.ppt + s);
             }
         }
-        if (have) F.flush(cur, a, b, acc);
+        if (have) F.flush(cur, a, b, acc, out_base + (a > M.counts[cur] ? 0 : 1));
     }
 
-    // ---- K5: one level of the hierarchical weighted sum.  Thread u of window w reduces
-    // entries [u L, u L + L) of its input.
-    static H2_HD void reduce_body(const MsmPlan &p, const MsmBuffers &M, uint32_t lv, uint64_t tid) {
-        const uint32_t l = p.red_log_l[lv], L = 1u << l, m = p.red_m_in[lv];
-        const uint32_t m_out = (m + L - 1) >> l;
-        if (tid >= (uint64_t)p.W * m_out) return;
-        uint32_t w = (uint32_t)(tid / m_out), u = (uint32_t)(tid % m_out);
-        const xyzz *A = lv == 0 ? M.bucket_sum + (uint64_t)w * p.B
-                                : M.red_sums + p.red_offset[lv - 1] + (uint64_t)w * m;
-        uint32_t lo = u * L, hi = lo + L < m ? lo + L : m;
+    // ---- K5 level A: thread (w, u) reduces buckets [u L, u L + L) of window w:
+    //   T = sum B[i],  E = sum (i - uL) B[i]    (running sums, no scalar multiplication)
+    static H2_HD void reduceA_body(const MsmPlan &p, const MsmBuffers &M, uint64_t tid) {
+        if (tid >= (uint64_t)p.W * p.m1) return;
+        uint32_t w = (uint32_t)(tid / p.m1), u = (uint32_t)(tid % p.m1);
+        const uint32_t L = 1u << p.l0;
+        const xyzz *A = M.bucket_sum + (uint64_t)w * p.B + (uint64_t)u * L;
         xyzz run = xyzz_identity(), acc = xyzz_identity();
-        for (uint32_t i = hi - 1; i > lo; i--) {
+        for (uint32_t i = L - 1; i > 0; i--) {
             xyzz_add<P>(run, ld_xyzz(A + i));
             xyzz_add<P>(acc, run);
         }
-        xyzz_add<P>(run, ld_xyzz(A + lo));
-        for (uint32_t d = 0; d < p.red_dbl[lv]; d++) xyzz_double<P>(acc);
-        if (lv > 0) {
-            const xyzz *E = M.red_e + p.red_offset[lv - 1] + (uint64_t)w * m;
-            for (uint32_t i = lo; i < hi; i++) xyzz_add<P>(acc, ld_xyzz(E + i));
-        }
-        uint64_t o = p.red_offset[lv] + (uint64_t)w * m_out + u;
-        st_xyzz(M.red_sums + o, run);
-        st_xyzz(M.red_e + o, acc);
+        xyzz_add<P>(run, ld_xyzz(A));
+        uint64_t o = (uint64_t)w * p.m1 + u;
+        st_xyzz(M.ra_t + o, run);
+        st_xyzz(M.ra_e + o, acc);
     }
 
-    // window sum S_w = F + total (bucket weights are idx + 1), then 2^(c w) S_w
-    static H2_HD xyzz window_value(const MsmPlan &p, const MsmBuffers &M, uint32_t w) {
-        uint64_t o = p.red_offset[p.red_levels - 1] + w;
-        xyzz s = ld_xyzz(M.red_e + o);
-        xyzz_add<P>(s, ld_xyzz(M.red_sums + o));
-        for (uint32_t d = 0; d < p.c * w; d++) xyzz_double<P>(s);
-        return s;
+    // Row semantics shared by R0 and R1: the value entry `idx` contributes to output row j.
+    //   R0 (entries = level-A chunks of one 32-block): row 0 = T, row 1 = E, row 2+k = T if bit k of lane
+    static H2_HD xyzz r0_contrib(const MsmPlan &p, const MsmBuffers &M, uint32_t w, uint32_t blk, uint32_t row, uint32_t lane) {
+        uint32_t u = blk * 32 + lane;
+        if (u >= p.m1) return xyzz_identity();
+        uint64_t o = (uint64_t)w * p.m1 + u;
+        if (row == 1) return ld_xyzz(M.ra_e + o);
+        if (row >= 2 && !((lane >> (row - 2)) & 1u)) return xyzz_identity();
+        return ld_xyzz(M.ra_t + o);
+    }
+    //   R1 (entries = 32-blocks of one window): rows 0..1+bits0 = plain sums of the R0 rows,
+    //   row 2+bits0+k = R0 row 0 (T) of blocks whose index has bit k set
+    static H2_HD xyzz r1_contrib(const MsmPlan &p, const MsmBuffers &M, uint32_t w, uint32_t row, uint32_t blk) {
+        if (blk >= p.nb0) return xyzz_identity();
+        const xyzz *e = M.r0 + ((uint64_t)w * p.nb0 + blk) * H2_R0_ROWS;
+        const uint32_t plain = 2 + p.bits0;
+        if (row < plain) return ld_xyzz(e + row);
+        if (!((blk >> (row - plain)) & 1u)) return xyzz_identity();
+        return ld_xyzz(e);
+    }
+    // 2^(c w) S_w with S_w = E + T + 2^l0 * sum_k 2^k D_k is a flat sum over the R1 rows of window w:
+    // row r contributes R1[w][r] doubled c*w (+ k + l0 for the D_k row r = 2 + k) times.
+    static H2_HD xyzz wsum_item(const MsmPlan &p, const MsmBuffers &M, uint32_t w, uint32_t r) {
+        if (r >= p.r1_rows) return xyzz_identity();
+        xyzz v = ld_xyzz(M.r1 + (uint64_t)w * p.r1_rows + r);
+        uint32_t shift = p.c * w + (r >= 2 ? (r - 2) + p.l0 : 0);
+        for (uint32_t d = 0; d < shift; d++) xyzz_double<P>(v);
+        return v;
     }
     static H2_HD void finish(const MsmBuffers &M, const xyzz &total, uint32_t out_canonical) {
         jacobian j = xyzz_to_jacobian<P>(total);
@@ -272,20 +306,27 @@ template <class P, class PS> struct Msm {
 };
 
 #if defined(__CUDACC__)
-// Warp-aggregated "fetch and add 1" on per-lane addresses: lanes that hit the same counter
-// elect a leader that does one atomicAdd for the group (all-equal scalars would otherwise
-// serialise n atomics on one L2 address).
-__device__ __forceinline__ uint32_t agg_inc(uint32_t *ctr, bool active) {
-    unsigned mask = __ballot_sync(0xffffffffu, active);
-    if (!active) return 0;
-    unsigned peers = __match_any_sync(mask, (unsigned long long)ctr);
+// "fetch and add 1" on per-lane addresses with a fast path for the skewed case: if every active
+// lane of the warp hits the same counter (all-equal scalars, 0/1 columns), one lane adds the
+// population count.  Returns the lane's slot (old value + rank) when WANT is set.
+template <bool WANT> __device__ __forceinline__ uint32_t warp_inc(uint32_t *ctr, bool active) {
+    const unsigned full = 0xffffffffu;
+    unsigned mask = __ballot_sync(full, active);
+    if (mask == 0) return 0;
     unsigned lane = threadIdx.x & 31u;
-    int leader = __ffs(peers) - 1;
-    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(ctr, (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    return base + rank;
+    int first = __ffs(mask) - 1;
+    unsigned long long a0 = __shfl_sync(full, (unsigned long long)ctr, first);
+    bool same = !active || (unsigned long long)ctr == a0;
+    if (__all_sync(full, same)) {
+        uint32_t base = 0;
+        if ((int)lane == first) base = atomicAdd(ctr, (uint32_t)__popc(mask));
+        if (WANT) base = __shfl_sync(full, base, first);
+        return base + __popc(mask & ((1u << lane) - 1u));
+    }
+    if (!active) return 0;
+    if (WANT) return atomicAdd(ctr, 1u);
+    atomicAdd(ctr, 1u);
+    return 0;
 }
 
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_kernel(const MsmPlan p, const MsmBuffers M) {
@@ -299,7 +340,7 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_ker
         bool act = in && d != 0;
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         uint64_t g = (uint64_t)w * p.B + (act ? mag - 1 : 0);
-        agg_inc(M.counts + g, act);
+        warp_inc<false>(M.counts + g, act);
     }
 }
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_kernel(const MsmPlan p, const MsmBuffers M) {
@@ -308,45 +349,126 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (in) Msm<P, PS>::load_scalar(M, i, s, false);
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < p.W; w++) {
-        int32_t d = Msm<P, PS>::next_digit(s, w, p.c, carry);
-        bool act = in && d != 0;
-        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        uint64_t g = (uint64_t)w * p.B + (act ? mag - 1 : 0);
-        uint32_t r = agg_inc(M.cursor + g, act);
-        if (act) {
-            uint32_t pos = M.counts[g] + r;
-            M.refs[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
-            M.keys[pos] = (uint32_t)g;
+    for (uint32_t w0 = 0; w0 < p.W; w0 += 4) {
+        // four windows in flight so the returning atomics overlap
+        uint32_t slot[4], gid[4], neg[4];
+        bool act[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t w = w0 + k;
+            int32_t d = w < p.W ? Msm<P, PS>::next_digit(s, w, p.c, carry) : 0;
+            act[k] = in && d != 0;
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            gid[k] = (uint32_t)((uint64_t)(w < p.W ? w : 0) * p.B + (act[k] ? mag - 1 : 0));
+            neg[k] = d < 0 ? 0x80000000u : 0u;
+            slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (act[k]) M.refs[M.counts[gid[k]] + slot[k]] = (uint32_t)i | neg[k];
     }
+}
+// work-item construction: size histogram, bases, then placement (descending size)
+template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_hist_kernel(const MsmPlan p, const MsmBuffers M) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nfull = 0, rem = 0;
+    if (g < p.G) Msm<P, PS>::count_items(p, M, g, nfull, rem);
+    if (nfull) atomicAdd(M.size_hist + p.T, nfull);
+    warp_inc<false>(M.size_hist + rem, rem != 0);
+}
+template <class P, class PS> __global__ void msm_item_bases_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) Msm<P, PS>::size_bases_body(p, M);
+}
+template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_place_kernel(const MsmPlan p, const MsmBuffers M) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nfull = 0, rem = 0, lo = 0;
+    if (g < p.G) { Msm<P, PS>::count_items(p, M, g, nfull, rem); lo = M.counts[g]; }
+    if (nfull) {
+        uint32_t at = atomicAdd(M.size_cursor + p.T, nfull);
+        for (uint32_t k = 0; k < nfull; k++) M.items[at + k] = make_uint2((uint32_t)g, lo + k * p.T);
+    }
+    uint32_t at = warp_inc<true>(M.size_cursor + rem, rem != 0);
+    if (rem) M.items[at] = make_uint2((uint32_t)g, lo + nfull * p.T);
 }
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < p.acc_threads[0]) Msm<P, PS>::accum0_body(p, M, t);
+    Msm<P, PS>::accum0_body(p, M, t);
 }
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accumN_kernel(const MsmPlan p, const MsmBuffers M, uint32_t lv) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < p.acc_threads[lv]) Msm<P, PS>::accumN_body(p, M, lv, t);
 }
-template <class P, class PS> __global__ void __launch_bounds__(128) msm_reduce_kernel(const MsmPlan p, const MsmBuffers M, uint32_t lv) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    Msm<P, PS>::reduce_body(p, M, lv, t);
-}
-// one CTA of 32 threads: thread w shifts its window, then a shared-memory tree adds them
-template <class P, class PS> __global__ void __launch_bounds__(32) msm_combine_kernel(const MsmPlan p, const MsmBuffers M, uint32_t out_canonical) {
-    __shared__ xyzz sh[32];
-    uint32_t w = threadIdx.x;
-    xyzz v = xyzz_identity();
-    // W can exceed 32 for tiny windows: thread w takes windows w, w+32, ...
-    for (uint32_t ww = w; ww < p.W; ww += 32) { xyzz t = Msm<P, PS>::window_value(p, M, ww); xyzz_add<P>(v, t); }
-    sh[w] = v;
-    __syncwarp();
-    for (uint32_t off = 16; off > 0; off >>= 1) {
-        if (w < off) { xyzz a = sh[w]; xyzz_add<P>(a, sh[w + off]); sh[w] = a; }
-        __syncwarp();
+// Partial-merge levels >= 2 in a single CTA (empty unless some bucket exceeded T references)
+template <class P, class PS> __global__ void __launch_bounds__(256) msm_accum_rest_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (!M.flags[0]) return;
+    for (uint32_t lv = 2; lv < p.acc_levels; lv++) {
+        for (uint64_t t = threadIdx.x; t < p.acc_threads[lv]; t += blockDim.x) Msm<P, PS>::accumN_body(p, M, lv, t);
+        __threadfence();
+        __syncthreads();
     }
-    if (w == 0) Msm<P, PS>::finish(M, sh[0], out_canonical);
+}
+template <class P, class PS> __global__ void __launch_bounds__(128) msm_reduceA_kernel(const MsmPlan p, const MsmBuffers M) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Msm<P, PS>::reduceA_body(p, M, t);
+}
+
+// Shared-memory tree sum of one value per thread over the `width` (power of two) lanes of a row;
+// rows are laid out [row][lane].  Every thread of the CTA must call it.  Total lands in lane 0.
+template <class P> __device__ __forceinline__ void block_tree_sum(xyzz *sh, xyzz &v, uint32_t row, uint32_t lane, uint32_t width) {
+    st_xyzz(sh + row * width + lane, v);
+    __syncthreads();
+    for (uint32_t off = width >> 1; off > 0; off >>= 1) {
+        if (lane < off) {
+            xyzz o = ld_xyzz(sh + row * width + lane + off);
+            xyzz_add<P>(v, o);
+            st_xyzz(sh + row * width + lane, v);
+        }
+        __syncthreads();
+    }
+}
+// R0: one thread per (window, 32-block, row): a serial sum of <= 32 entries keeps every lane busy
+// (a shared-memory tree would run 31 adds in 5 SIMT steps at 1/2 .. 1/32 lane utilisation).
+template <class P, class PS> __global__ void __launch_bounds__(128) msm_r0_kernel(const MsmPlan p, const MsmBuffers M) {
+    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rows = 2 + p.bits0;
+    if (tid >= (uint64_t)p.W * p.nb0 * rows) return;
+    uint32_t row = (uint32_t)(tid % rows);
+    uint64_t wb = tid / rows;
+    uint32_t w = (uint32_t)(wb / p.nb0), blk = (uint32_t)(wb % p.nb0);
+    xyzz v = xyzz_identity();
+    for (uint32_t lane = 0; lane < 32; lane++) {
+        if (row >= 2 && !((lane >> (row - 2)) & 1u)) continue;
+        xyzz c = Msm<P, PS>::r0_contrib(p, M, w, blk, row, lane);
+        xyzz_add<P>(v, c);
+    }
+    st_xyzz(M.r0 + ((uint64_t)w * p.nb0 + blk) * H2_R0_ROWS + row, v);
+}
+// R1: one CTA per (window, output row): 128 threads stride over the window's nb0 blocks
+template <class P, class PS> __global__ void __launch_bounds__(128) msm_r1_kernel(const MsmPlan p, const MsmBuffers M) {
+    __shared__ xyzz sh[128];
+    uint32_t w = blockIdx.x / p.r1_rows, row = blockIdx.x % p.r1_rows;
+    xyzz v = xyzz_identity();
+    for (uint32_t blk = threadIdx.x; blk < p.nb0; blk += 128) {
+        xyzz c = Msm<P, PS>::r1_contrib(p, M, w, row, blk);
+        xyzz_add<P>(v, c);
+    }
+    block_tree_sum<P>(sh, v, 0, threadIdx.x, 128);
+    if (threadIdx.x == 0) st_xyzz(M.r1 + (uint64_t)w * p.r1_rows + row, v);
+}
+// Window value 2^(c w) S_w: one CTA per window, one thread per R1 row (<= 32 rows), tree sum.
+template <class P, class PS> __global__ void __launch_bounds__(32) msm_wsum_kernel(const MsmPlan p, const MsmBuffers M) {
+    __shared__ xyzz sh[32];
+    xyzz v = Msm<P, PS>::wsum_item(p, M, blockIdx.x, threadIdx.x);
+    block_tree_sum<P>(sh, v, 0, threadIdx.x, 32);
+    if (threadIdx.x == 0) st_xyzz(M.wsum + blockIdx.x, v);
+}
+// Final: tree sum of the W window values
+template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_kernel(const MsmPlan p, const MsmBuffers M, uint32_t out_canonical) {
+    __shared__ xyzz sh[64];
+    xyzz v = xyzz_identity();
+    for (uint32_t w = threadIdx.x; w < p.W; w += 64) { xyzz c = ld_xyzz(M.wsum + w); xyzz_add<P>(v, c); }
+    block_tree_sum<P>(sh, v, 0, threadIdx.x, 64);
+    if (threadIdx.x == 0) Msm<P, PS>::finish(M, v, out_canonical);
 }
 
 // exclusive scan of counts[0..G] in place (counts[G] becomes the total), three small kernels

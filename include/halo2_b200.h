@@ -114,6 +114,9 @@ int h2_test_curve_op(int curve, int op, const void *a_xy, const void *b_xy, size
 /* Times `iters` dependent field multiplications per thread over `threads` threads; returns
  * elapsed milliseconds in *ms (microbenchmark for the roofline discussion in DESIGN.md). */
 int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_t blocks, uint32_t iters, float *ms);
+/* Single-warp latency of the serial building blocks: mode 0 dependent multiply chain, 1 two
+ * independent chains, 2 four chains, 3 xyzz double, 4 xyzz add, 5 xyzz mixed add. */
+int h2_bench_latency(int mode, uint32_t iters, float *ms);
 /* Number of kernels launched by the engine since h2_init (bench.py's gpu_launches). */
 uint64_t h2_launch_count(void);
 /* Per-kernel device timing for the roofline report: while enabled, CUDA-event pairs bracket the

@@ -1,5 +1,5 @@
 // TEST-ONLY serial execution of the MSM kernel bodies (msm.cuh) on the host: checks the
-// digit/sort/chunk/partial/reduce index logic against the oracle without a GPU.
+// digit/sort/work-item/partial/reduce/combine index logic against the oracle without a GPU.
 #include <cstring>
 #include <vector>
 #include "msm.cuh"
@@ -7,22 +7,10 @@ using namespace h2;
 
 template <class P, class PS>
 static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c, int scalars_mont,
-                   uint32_t force_k0, uint8_t *out_xyz) {
+                   uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
     MsmPlan p;
-    msm_make_plan(p, n, c ? c : msm_default_window(n));
-    if (force_k0) {   // re-plan with a forced level-0 chunk to exercise multi-level partial merging
-        p.acc_chunk[0] = force_k0;
-        uint32_t lv = 0; uint64_t slots = p.max_refs; p.part_total = 0;
-        for (;;) {
-            uint32_t chunk = lv == 0 ? force_k0 : 8u;
-            uint64_t threads = (slots + chunk - 1) / chunk; if (!threads) threads = 1;
-            p.acc_chunk[lv] = chunk; p.acc_threads[lv] = threads; p.acc_slots[lv] = slots; lv++;
-            if (threads == 1) break;
-            p.part_offset[lv] = p.part_total; slots = 2 * threads; p.part_total += slots;
-            if (lv >= H2_MSM_MAX_LEVELS) return -2;
-        }
-        p.acc_levels = lv;
-    }
+    msm_make_plan(p, n, c ? c : msm_default_window(n), force_t, force_kn);
+    if (p.acc_levels > H2_MSM_MAX_LEVELS) return -2;
     std::vector<fe> sc(n ? n : 1), sc_canon(n ? n : 1);
     std::vector<affine> bs(n ? n : 1);
     for (size_t i = 0; i < n; i++) {
@@ -32,17 +20,22 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         if (!affine_is_identity(a)) { a.x = fe_to_mont<P>(a.x); a.y = fe_to_mont<P>(a.y); }
         bs[i] = a;
     }
-    std::vector<uint32_t> counts(p.G + 1, 0), cursor(p.G, 0), refs(p.max_refs ? p.max_refs : 1), keys(p.max_refs ? p.max_refs : 1);
+    std::vector<uint32_t> counts(p.G + 1, 0), cursor(p.G, 0), refs(p.max_refs ? p.max_refs : 1), size_hist(p.T + 2, 0),
+        size_cursor(p.T + 1, 0), flags(4, 0);
+    std::vector<uint2> items(p.max_items);
     std::vector<xyzz> bucket_sum(p.G, xyzz_identity());
     size_t pt = p.part_total ? p.part_total : 1;
     std::vector<uint32_t> pkey(pt, H2_MSM_INVALID_KEY), pstart(pt), pend(pt);
-    std::vector<xyzz> ppt(pt), red_sums(p.red_total), red_e(p.red_total);
+    std::vector<xyzz> ppt(pt), ra_t((size_t)p.W * p.m1), ra_e((size_t)p.W * p.m1), r0((size_t)p.W * p.nb0 * H2_R0_ROWS),
+        r1((size_t)p.W * p.r1_rows), wsum(p.W);
     jacobian result;
     MsmBuffers M;
     M.scalars = sc.data(); M.bases = bs.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
-    M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data(); M.keys = keys.data();
+    M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data();
+    M.size_hist = size_hist.data(); M.size_cursor = size_cursor.data(); M.flags = flags.data(); M.items = items.data();
     M.bucket_sum = bucket_sum.data(); M.pkey = pkey.data(); M.pstart = pstart.data(); M.pend = pend.data();
-    M.ppt = ppt.data(); M.red_sums = red_sums.data(); M.red_e = red_e.data(); M.win_sums = nullptr; M.result = &result;
+    M.ppt = ppt.data(); M.ra_t = ra_t.data(); M.ra_e = ra_e.data(); M.r0 = r0.data(); M.r1 = r1.data();
+    M.wsum = wsum.data(); M.result = &result;
     typedef Msm<P, PS> K;
     // K2 histogram
     for (size_t i = 0; i < n; i++) {
@@ -54,7 +47,6 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         }
         if (carry) return -3;    // top window must absorb the carry
     }
-    // scan
     uint32_t run = 0;
     for (uint64_t g = 0; g <= p.G; g++) { uint32_t v = counts[g]; counts[g] = run; run += v; }
     // K3 scatter (reverse order to mimic the arbitrary order atomics give)
@@ -65,30 +57,52 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
             int32_t d = K::next_digit(s, w, p.c, carry);
             if (!d) continue;
             uint64_t g = (uint64_t)w * p.B + (uint32_t)(d < 0 ? -d : d) - 1;
-            uint32_t pos = counts[g] + cursor[g]++;
-            refs[pos] = (uint32_t)ii | (d < 0 ? 0x80000000u : 0u);
-            keys[pos] = (uint32_t)g;
+            refs[counts[g] + cursor[g]++] = (uint32_t)ii | (d < 0 ? 0x80000000u : 0u);
         }
     }
-    // K4 accumulate levels
-    for (uint64_t t = 0; t < p.acc_threads[0]; t++) K::accum0_body(p, M, t);
+    // work items
+    for (uint64_t g = 0; g < p.G; g++) {
+        uint32_t nfull, rem; K::count_items(p, M, g, nfull, rem);
+        size_hist[p.T] += nfull; if (rem) size_hist[rem]++;
+    }
+    K::size_bases_body(p, M);
+    for (uint64_t g = p.G; g-- > 0;) {
+        uint32_t nfull, rem; K::count_items(p, M, g, nfull, rem);
+        for (uint32_t k = 0; k < nfull; k++) items[size_cursor[p.T]++] = make_uint2((uint32_t)g, counts[g] + k * p.T);
+        if (rem) items[size_cursor[rem]++] = make_uint2((uint32_t)g, counts[g] + nfull * p.T);
+    }
+    if (size_hist[p.T + 1] > p.max_items) return -4;
+    // K4
+    for (uint64_t t = 0; t < p.max_items; t++) K::accum0_body(p, M, t);
     for (uint32_t lv = 1; lv < p.acc_levels; lv++)
         for (uint64_t t = 0; t < p.acc_threads[lv]; t++) K::accumN_body(p, M, lv, t);
-    // K5 reduce + combine
-    for (uint32_t lv = 0; lv < p.red_levels; lv++) {
-        uint32_t m_out = (p.red_m_in[lv] + (1u << p.red_log_l[lv]) - 1) >> p.red_log_l[lv];
-        for (uint64_t t = 0; t < (uint64_t)p.W * m_out; t++) K::reduce_body(p, M, lv, t);
-    }
+    // K5
+    for (uint64_t t = 0; t < (uint64_t)p.W * p.m1; t++) K::reduceA_body(p, M, t);
+    for (uint32_t w = 0; w < p.W; w++)
+        for (uint32_t blk = 0; blk < p.nb0; blk++)
+            for (uint32_t row = 0; row < H2_R0_ROWS; row++) {
+                xyzz v = xyzz_identity();
+                if (row < 2 + p.bits0)
+                    for (uint32_t lane = 0; lane < 32; lane++) { xyzz cc = K::r0_contrib(p, M, w, blk, row, lane); xyzz_add<P>(v, cc); }
+                r0[((size_t)w * p.nb0 + blk) * H2_R0_ROWS + row] = v;
+            }
+    for (uint32_t w = 0; w < p.W; w++)
+        for (uint32_t row = 0; row < p.r1_rows; row++) {
+            xyzz v = xyzz_identity();
+            for (uint32_t blk = 0; blk < p.nb0; blk++) { xyzz cc = K::r1_contrib(p, M, w, row, blk); xyzz_add<P>(v, cc); }
+            r1[(size_t)w * p.r1_rows + row] = v;
+        }
     xyzz total = xyzz_identity();
-    for (uint32_t w = 0; w < p.W; w++) { xyzz v = K::window_value(p, M, w); xyzz_add<P>(total, v); }
+    for (uint32_t w = 0; w < p.W; w++)
+        for (uint32_t r = 0; r < 32; r++) { xyzz cc = K::wsum_item(p, M, w, r); xyzz_add<P>(total, cc); }
     K::finish(M, total, 1);
     memcpy(out_xyz, result.x.v, 32); memcpy(out_xyz + 32, result.y.v, 32); memcpy(out_xyz + 64, result.z.v, 32);
-    return (int)p.acc_levels;
+    return (int)p.acc_levels + (flags[0] ? 100 : 0);
 }
 
-// curve 0 = Pallas (coords Fp, scalars Fq), 1 = Vesta.  Returns the number of accumulate levels (>0) or <0.
+// curve 0 = Pallas (coords Fp, scalars Fq), 1 = Vesta.  Returns acc_levels (+100 if some bucket was split) or <0.
 extern "C" int emu_msm(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
-                       int scalars_mont, uint32_t force_k0, uint8_t *out_xyz) {
-    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_k0, out_xyz);
-    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_k0, out_xyz);
+                       int scalars_mont, uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, out_xyz);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, out_xyz);
 }

@@ -98,10 +98,11 @@ def test_emul_ntt(emu, field):
         assert (got == back).all()
 
 
-def _msm(emu, curve, kb, pb, c=0, mont=0, k0=0):
+def _msm(emu, curve, kb, pb, c=0, mont=0, k0=0, gs=0):
+    # k0 = forced references per work item (T), gs = forced merge-level chunk
     out = np.zeros(96, dtype=np.uint8)
     r = emu.emu_msm(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(kb)), cref._p(np.ascontiguousarray(pb)),
-                    ctypes.c_size_t(kb.shape[0]), c, mont, k0, cref._p(out))
+                    ctypes.c_size_t(kb.shape[0]), c, mont, k0, gs, cref._p(out))
     assert r > 0, r
     return cref.bytes_to_affine(cref.jac_to_affine(curve, out))
 
@@ -113,8 +114,8 @@ def test_emul_msm(emu, curve):
         kb = cref.gen_scalars(c.scalar, n, n)
         pb = cref.gen_points(curve, n + 1, n)
         want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
-        for cb, k0 in ((0, 0), (1, 0), (5, 3), (11, 5), (16, 0)):
-            assert _msm(emu, curve, kb, pb, cb, 0, k0) == want, (n, cb, k0)
+        for cb, k0, gs in ((0, 0, 0), (1, 0, 0), (5, 3, 4), (11, 5, 8), (16, 0, 0), (2, 4, 4), (9, 2, 4), (3, 1, 4)):
+            assert _msm(emu, curve, kb, pb, cb, 0, k0, gs) == want, (n, cb, k0, gs)
         assert _msm(emu, curve, kb, pb, 0, 1, 0) == want   # Montgomery-encoded scalars
     n, r = 200, c.r
     pb = cref.gen_points(curve, 9, n)
@@ -124,8 +125,8 @@ def test_emul_msm(emu, curve):
     for name, ks in cases.items():
         kb = cref.ints_to_bytes(ks)
         want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
-        for cb, k0 in ((0, 0), (4, 3), (16, 4)):
-            assert _msm(emu, curve, kb, pb, cb, 0, k0) == want, (name, cb, k0)
+        for cb, k0, gs in ((0, 0, 0), (4, 3, 4), (16, 4, 8), (7, 2, 4), (6, 1, 4)):
+            assert _msm(emu, curve, kb, pb, cb, 0, k0, gs) == want, (name, cb, k0, gs)
     g = pasta.generator(c)
     pts = [cref.bytes_to_affine(x) for x in pb[:6]]
     pts2 = [g, g, (g[0], c.p - g[1]), None, pts[3], pts[3], pts[4], (pts[4][0], c.p - pts[4][1]), None, g] * 5
@@ -134,5 +135,5 @@ def test_emul_msm(emu, curve):
     ks[6] = ks[7]
     kb, pb2 = cref.ints_to_bytes(ks), cref.affines_to_bytes(pts2)
     want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb2))
-    for cb, k0 in ((0, 0), (3, 2), (13, 0)):
-        assert _msm(emu, curve, kb, pb2, cb, 0, k0) == want
+    for cb, k0, gs in ((0, 0, 0), (3, 2, 4), (13, 0, 0)):
+        assert _msm(emu, curve, kb, pb2, cb, 0, k0, gs) == want

@@ -22,6 +22,16 @@ def mulbench():
             print(f"field={field} tpb={tpb} blocks={blocks}: {ms.value:.3f} ms  {muls / ms.value / 1e6:.1f} G mulmod/s", flush=True)
 
 
+def latbench():
+    names = ["mul x1 chain", "mul x2 chains", "mul x4 chains", "xyzz_double", "xyzz_add", "xyzz_add_mixed", "fe_mul2 pair"]
+    per = [1, 2, 4, 1, 1, 1, 2]
+    for mode in range(7):
+        ms = ctypes.c_float()
+        iters = 2000
+        L.check(lib.h2_bench_latency(mode, iters, ctypes.byref(ms)))
+        print(f"latency {names[mode]:16s}: {ms.value * 1e3 / iters:.3f} us/iter  ({ms.value * 1e3 / iters / per[mode]:.3f} us per op)", flush=True)
+
+
 def rand_scalars(n, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
@@ -72,6 +82,8 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["mul", "ntt", "msm"]
     if "mul" in what:
         mulbench()
+    if "lat" in what:
+        latbench()
     if "ntt" in what:
         for k in (14, 16, 20, 24):
             ntt_time(k)
