@@ -141,6 +141,31 @@ template <class P> H2_HD affine jacobian_to_affine(const jacobian &j) {
     return r;
 }
 
+// acc = 2^k * acc through Jacobian coordinates: the a = 0 doubling dbl-2009-l costs 2M + 5S
+// (XYZZ doubling: 6M + 3S), which pays off on the long shift chains of the window combine.
+template <class P> H2_HD void xyzz_shift(xyzz &a, uint32_t k) {
+    if (k == 0 || xyzz_is_identity(a)) return;
+    if (k < 4) { for (uint32_t d = 0; d < k; d++) xyzz_double<P>(a); return; }
+    fe X = fe_mul<P>(a.x, a.zz), Y = fe_mul<P>(a.y, a.zzz), Z = a.zz;   // (X ZZ, Y ZZZ, ZZ)
+    for (uint32_t d = 0; d < k; d++) {
+        fe A = fe_sqr<P>(X), B = fe_sqr<P>(Y), C = fe_sqr<P>(B);
+        fe t = fe_add<P>(X, B);
+        fe D = fe_sub<P>(fe_sub<P>(fe_sqr<P>(t), A), C);
+        D = fe_dbl<P>(D);
+        fe E = fe_add<P>(fe_dbl<P>(A), A);
+        fe F = fe_sqr<P>(E);
+        fe Z3 = fe_dbl<P>(fe_mul<P>(Y, Z));
+        X = fe_sub<P>(fe_sub<P>(F, D), D);
+        fe C8 = fe_dbl<P>(fe_dbl<P>(fe_dbl<P>(C)));
+        Y = fe_sub<P>(fe_mul<P>(E, fe_sub<P>(D, X)), C8);
+        Z = Z3;
+    }
+    // Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3); Y == 0 cannot occur on a prime-order curve
+    a.x = X; a.y = Y;
+    a.zz = fe_sqr<P>(Z);
+    a.zzz = fe_mul<P>(a.zz, Z);
+}
+
 // k * p by left-to-right double-and-add; k = 8 x u32 little-endian (canonical integer).
 // Used by the synthetic-input generator and the tests, not by the MSM hot path.
 template <class P> H2_HD xyzz xyzz_scalar_mul(const affine &p, const uint32_t (&k)[8]) {

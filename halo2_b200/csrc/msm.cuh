@@ -295,7 +295,7 @@ template <class P, class PS> struct Msm {
         if (r >= p.r1_rows) return xyzz_identity();
         xyzz v = ld_xyzz(M.r1 + (uint64_t)w * p.r1_rows + r);
         uint32_t shift = p.c * w + (r >= 2 ? (r - 2) + p.l0 : 0);
-        for (uint32_t d = 0; d < shift; d++) xyzz_double<P>(v);
+        xyzz_shift<P>(v, shift);
         return v;
     }
     static H2_HD void finish(const MsmBuffers &M, const xyzz &total, uint32_t out_canonical) {
@@ -390,7 +390,7 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_pla
     uint32_t at = warp_inc<true>(M.size_cursor + rem, rem != 0);
     if (rem) M.items[at] = make_uint2((uint32_t)g, lo + nfull * p.T);
 }
-template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_kernel(const MsmPlan p, const MsmBuffers M) {
+template <class P, class PS> __global__ void __launch_bounds__(128, 5) msm_accum0_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Msm<P, PS>::accum0_body(p, M, t);
 }
