@@ -44,7 +44,7 @@ struct DevBuf {
 };
 
 struct TwiddleEntry { int field; uint32_t log_n; uint8_t omega[32]; DevBuf buf; uint64_t stamp; };
-struct BaseSet { int curve; size_t n; DevBuf buf; };
+struct BaseSet { int curve; size_t n; DevBuf buf; DevBuf table; uint32_t c = 0, W = 0; };   // table: W x n window multiples
 
 struct Context {
     bool ready = false;
@@ -145,7 +145,7 @@ extern "C" int h2_shutdown(void) {
     for (DevBuf *b : all) b->release();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
-    for (auto &kv : g_ctx.bases) { kv.second->buf.release(); delete kv.second; }
+    for (auto &kv : g_ctx.bases) { kv.second->buf.release(); kv.second->table.release(); delete kv.second; }
     g_ctx.bases.clear();
     cudaEventDestroy(g_ctx.last_use);
     cudaStreamDestroy(g_ctx.stream);
@@ -307,9 +307,10 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s) {
     return 0;
 }
 
+// fixed != 0: d_bases is a window table (stride points per window) built with window size c
 template <class P, class PS>
-static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, jacobian *d_out,
-                   int out_canonical, cudaStream_t s) {
+static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, uint32_t fixed, uint64_t stride,
+                   jacobian *d_out, int out_canonical, cudaStream_t s) {
     Context &X = g_ctx;
     if (n == 0) {   // empty sum = identity
         jacobian id;
@@ -322,7 +323,8 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     MsmPlan p;
     if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n);
     if (c > 24) return fail("msm: window bits > 24");
-    msm_make_plan(p, n, c);
+    msm_make_plan(p, n, c, 0, 0, fixed, stride);
+    if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
     if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
     if (scalars_mont && X.scal_canon.ensure(n * sizeof(fe))) return 1;
     const size_t small_words = 2 * (p.T + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
@@ -330,9 +332,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         X.size_hist.ensure(small_words * 4) || X.items.ensure(p.max_items * sizeof(uint2)) ||
         X.bucket_sum.ensure(p.G * sizeof(xyzz)) || X.pkey.ensure((p.part_total + 1) * 4) || X.pstart.ensure((p.part_total + 1) * 4) ||
         X.pend.ensure((p.part_total + 1) * 4) || X.ppt.ensure((p.part_total + 1) * sizeof(xyzz)) ||
-        X.ra_t.ensure((size_t)p.W * p.m1 * sizeof(xyzz)) || X.ra_e.ensure((size_t)p.W * p.m1 * sizeof(xyzz)) ||
-        X.r0.ensure((size_t)p.W * p.nb0 * H2_R0_ROWS * sizeof(xyzz)) || X.r1.ensure((size_t)p.W * p.r1_rows * sizeof(xyzz)) ||
-        X.wsum.ensure((size_t)p.W * sizeof(xyzz)))
+        X.ra_t.ensure((size_t)p.Wb * p.m1 * sizeof(xyzz)) || X.ra_e.ensure((size_t)p.Wb * p.m1 * sizeof(xyzz)) ||
+        X.r0.ensure((size_t)p.Wb * p.nb0 * H2_R0_ROWS * sizeof(xyzz)) || X.r1.ensure((size_t)p.Wb * p.r1_rows * sizeof(xyzz)) ||
+        X.wsum.ensure((size_t)p.Wb * sizeof(xyzz)))
         return 1;
     MsmBuffers M;
     M.scalars = d_scalars; M.bases = d_bases; M.scalars_mont = scalars_mont ? 1u : 0u;
@@ -379,19 +381,45 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     if (p.acc_levels > 1) LAUNCH(k_accumN, blocks_for(p.acc_threads[1], 128), 128, 0, s, p, M, 1u);
     if (p.acc_levels > 2) LAUNCH(k_rest, 1, 256, 0, s, p, M);
     // K5: bucket reduce and window combine
-    LAUNCH(k_reduceA, blocks_for((uint64_t)p.W * p.m1, 128), 128, 0, s, p, M);
-    LAUNCH(k_r0, blocks_for((uint64_t)p.W * p.nb0 * (2 + p.bits0), 128), 128, 0, s, p, M);
-    LAUNCH(k_r1, p.W * p.r1_rows, 128, 0, s, p, M);
-    LAUNCH(k_wsum, p.W, 32, 0, s, p, M);
+    LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1, 128), 128, 0, s, p, M);
+    LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0), 128), 128, 0, s, p, M);
+    LAUNCH(k_r1, p.Wb * p.r1_rows, 128, 0, s, p, M);
+    LAUNCH(k_wsum, p.Wb, 32, 0, s, p, M);
     LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
     return 0;
 }
 
 static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
-                        jacobian *d_out, int out_canonical, cudaStream_t s) {
-    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, d_out, out_canonical, s);
-    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, d_out, out_canonical, s);
+                        jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0) {
+    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s);
+    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s);
     return fail("unknown curve id");
+}
+// window size for a precomputed table over n bases: few references per bucket (short serial chains)
+// for small n, fewer windows for large n
+static uint32_t table_window(size_t n) {
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    uint32_t c = lg + 2;
+    if (c < 8) c = 8;
+    if (c > 20) c = 20;
+    return c;
+}
+static int build_table(BaseSet *b, uint32_t c, cudaStream_t s) {
+    if (c == 0) c = table_window(b->n);
+    if (c < 4 || c > 24) return fail("window table: window bits must be in [4, 24]");
+    uint32_t W = (256 + c - 1) / c;
+    if ((uint64_t)W * b->n >= (1ull << 31)) return fail("window table: too many points");
+    if (b->table.ensure((size_t)W * b->n * sizeof(affine))) return 1;
+    if (b->curve == H2_CURVE_PALLAS) {
+        auto k = msm_table_kernel<FpParams, FqParams>;
+        LAUNCH(k, blocks_for(b->n, 128), 128, 0, s, b->buf.as<affine>(), b->table.as<affine>(), (uint64_t)b->n, (uint64_t)b->n, c, W);
+    } else {
+        auto k = msm_table_kernel<FqParams, FpParams>;
+        LAUNCH(k, blocks_for(b->n, 128), 128, 0, s, b->buf.as<affine>(), b->table.as<affine>(), (uint64_t)b->n, (uint64_t)b->n, c, W);
+    }
+    b->c = c; b->W = W;
+    return 0;
 }
 static int convert_points(int curve, affine *d, size_t n, int to_mont, cudaStream_t s) {
     if (n == 0) return 0;
@@ -413,15 +441,15 @@ extern "C" int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, co
 }
 
 static int msm_host_common(int curve, const void *scalars, size_t n_scalars, const void *extra_scalar, const affine *d_bases,
-                           size_t n_total, int repr, void *out_xyz) {
+                           size_t n_total, int repr, void *out_xyz, uint32_t c = 0, uint32_t fixed = 0, uint64_t stride = 0) {
     Context &X = g_ctx;
     cudaStream_t s = X.stream;
     if (scratch_acquire(s)) return 1;
     if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
     if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
     if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
-    int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, 0, X.result.as<jacobian>(),
-                          repr == H2_REPR_CANONICAL, s);
+    int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
+                          repr == H2_REPR_CANONICAL, s, fixed, stride);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
     if (scratch_release(s)) return 1;
@@ -442,7 +470,14 @@ extern "C" int h2_msm(int curve, const void *scalars, const void *bases_xy, size
     return msm_host_common(curve, scalars, n, nullptr, X.bases_in.as<affine>(), n, repr, out_xyz);
 }
 
+static int bases_register_impl(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle);
 extern "C" int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle) {
+    return bases_register_impl(curve, bases_xy, n, repr, 0, 0, handle);
+}
+extern "C" int h2_bases_register_ex(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle) {
+    return bases_register_impl(curve, bases_xy, n, repr, window_bits, flags, handle);
+}
+static int bases_register_impl(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;
     if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
@@ -452,6 +487,7 @@ extern "C" int h2_bases_register(int curve, const void *bases_xy, size_t n, int 
     cudaStream_t s = g_ctx.stream;
     if (n) CU(cudaMemcpyAsync(b->buf.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
     if (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), n, 1, s)) return 1;
+    if ((flags & H2_BASES_PRECOMPUTE) && n > 0 && build_table(b, window_bits, s)) return 1;
     CU(cudaStreamSynchronize(s));
     uint64_t h = g_ctx.next_handle++;
     g_ctx.bases[h] = b;
@@ -465,6 +501,7 @@ extern "C" int h2_bases_release(uint64_t handle) {
     cudaSetDevice(g_ctx.device);
     cudaDeviceSynchronize();
     it->second->buf.release();
+    it->second->table.release();
     delete it->second;
     g_ctx.bases.erase(it);
     return 0;
@@ -477,6 +514,8 @@ extern "C" int h2_msm_registered(uint64_t handle, const void *scalars, size_t n,
     BaseSet *b = it->second;
     size_t total = n + (extra_scalar ? 1 : 0);
     if (total > b->n) return fail("h2_msm_registered: more scalars than registered bases");
+    if (b->table.p)   // fixed-base path: window table, one shared bucket set
+        return msm_host_common(b->curve, scalars, n, extra_scalar, b->table.as<affine>(), total, repr, out_xyz, b->c, 1, b->n);
     return msm_host_common(b->curve, scalars, n, extra_scalar, b->buf.as<affine>(), total, repr, out_xyz);
 }
 

@@ -38,14 +38,19 @@ H2_HD void st_jacobian(jacobian *p, const jacobian &a) { fe_store(&p->x, a.x); f
 
 #define H2_MSM_INVALID_KEY 0xffffffffu
 #define H2_MSM_MAX_LEVELS 12
-#define H2_R0_ROWS 7          // per 32-entry block: T, E, D_0..D_4
+#define H2_R0_LOG 3           // R0 block = 8 level-A entries
+#define H2_R0_ROWS 5          // per block: T, E, D_0..D_2
 
 struct MsmPlan {
     uint64_t n;          // number of (scalar, base) pairs
     uint32_t c;          // window bits
     uint32_t W;          // windows = ceil(256 / c)
     uint32_t B;          // buckets per window = 2^(c-1)
-    uint64_t G;          // total buckets = W * B
+    uint32_t fixed;      // 1: bases come from a precomputed table T[w][i] = 2^(c w) G_i (resident Params
+                         //    generators): every window's digits share ONE bucket set, no window combine
+    uint32_t Wb;         // bucket sets = fixed ? 1 : W
+    uint64_t stride;     // fixed: points per table window
+    uint64_t G;          // total buckets = Wb * B
     uint64_t max_refs;   // n * W
     uint32_t T;          // references per work item (larger buckets are split)
     uint64_t max_items;  // upper bound of work items = G + max_refs / T
@@ -59,8 +64,8 @@ struct MsmPlan {
     // bucket reduce
     uint32_t l0;         // log2 of the level-A chunk
     uint32_t m1;         // entries per window after level A = B >> l0   (power of two)
-    uint32_t nb0;        // 32-entry blocks per window = ceil(m1 / 32)   (power of two)
-    uint32_t bits0;      // bits produced by R0 = min(5, log2 m1)
+    uint32_t nb0;        // R0 blocks (8 entries) per window = ceil(m1 / 8)   (power of two)
+    uint32_t bits0;      // bits produced by R0 = min(3, log2 m1)
     uint32_t bits1;      // bits produced by R1 = log2 nb0
     uint32_t r1_rows;    // 2 + bits0 + bits1
 };
@@ -78,13 +83,18 @@ inline uint32_t msm_default_window(uint64_t n) {
     return c;
 }
 
-inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0) {
+inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
+                          uint64_t stride = 0) {
     p.n = n; p.c = c;
     p.W = (256 + c - 1) / c;
     p.B = 1u << (c - 1);
-    p.G = (uint64_t)p.W * p.B;
+    p.fixed = fixed; p.Wb = fixed ? 1u : p.W; p.stride = stride;
+    p.G = (uint64_t)p.Wb * p.B;
     p.max_refs = n * p.W;
-    p.T = force_t ? force_t : 128u;
+    // references per work item: 128 for big problems; shorter chains when there is little parallelism
+    uint32_t T = 128;
+    while (T > 32 && p.max_refs / T < 32768) T >>= 1;
+    p.T = force_t ? force_t : T;
     p.max_items = p.G + p.max_refs / p.T + 1;
     // partial slots: slot(start, chunk) = 2 * (start / T) + (chunk > 0), see item_slot()
     uint32_t lv = 1;
@@ -106,11 +116,13 @@ inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t =
     }
     p.acc_levels = lv;
     // bucket reduce
-    p.l0 = c - 1 < 3 ? c - 1 : 3;
+    // level-A chunk: 8 buckets when there is plenty of parallel work, 4 (shorter serial chain) otherwise
+    uint32_t want_l0 = p.G >= (1ull << 18) ? 3u : 2u;
+    p.l0 = c - 1 < want_l0 ? c - 1 : want_l0;
     p.m1 = p.B >> p.l0;
-    p.nb0 = (p.m1 + 31) / 32;
+    p.nb0 = (p.m1 + (1u << H2_R0_LOG) - 1) >> H2_R0_LOG;
     uint32_t lm = ilog2_u32(p.m1);
-    p.bits0 = lm < 5 ? lm : 5;
+    p.bits0 = lm < H2_R0_LOG ? lm : H2_R0_LOG;
     p.bits1 = ilog2_u32(p.nb0);
     p.r1_rows = 2 + p.bits0 + p.bits1;
 }
@@ -133,7 +145,7 @@ struct MsmBuffers {
     uint32_t *pkey, *pstart, *pend;   // part_total
     xyzz *ppt;                // part_total
     xyzz *ra_t, *ra_e;        // W * m1            level A: chunk totals / weighted sums
-    xyzz *r0;                 // W * nb0 * 7       R0: per 32-block T, E, D_0..4
+    xyzz *r0;                 // Wb * nb0 * 5      R0: per 8-entry block T, E, D_0..2
     xyzz *r1;                 // W * r1_rows       R1: per window T, E, D_0..
     xyzz *wsum;               // W                 2^(c w) S_w
     jacobian *result;         // 1
@@ -254,7 +266,7 @@ template <class P, class PS> struct Msm {
     // ---- K5 level A: thread (w, u) reduces buckets [u L, u L + L) of window w:
     //   T = sum B[i],  E = sum (i - uL) B[i]    (running sums, no scalar multiplication)
     static H2_HD void reduceA_body(const MsmPlan &p, const MsmBuffers &M, uint64_t tid) {
-        if (tid >= (uint64_t)p.W * p.m1) return;
+        if (tid >= (uint64_t)p.Wb * p.m1) return;
         uint32_t w = (uint32_t)(tid / p.m1), u = (uint32_t)(tid % p.m1);
         const uint32_t L = 1u << p.l0;
         const xyzz *A = M.bucket_sum + (uint64_t)w * p.B + (uint64_t)u * L;
@@ -270,16 +282,16 @@ template <class P, class PS> struct Msm {
     }
 
     // Row semantics shared by R0 and R1: the value entry `idx` contributes to output row j.
-    //   R0 (entries = level-A chunks of one 32-block): row 0 = T, row 1 = E, row 2+k = T if bit k of lane
+    //   R0 (entries = level-A chunks of one 8-block): row 0 = T, row 1 = E, row 2+k = T if bit k of lane
     static H2_HD xyzz r0_contrib(const MsmPlan &p, const MsmBuffers &M, uint32_t w, uint32_t blk, uint32_t row, uint32_t lane) {
-        uint32_t u = blk * 32 + lane;
+        uint32_t u = (blk << H2_R0_LOG) + lane;
         if (u >= p.m1) return xyzz_identity();
         uint64_t o = (uint64_t)w * p.m1 + u;
         if (row == 1) return ld_xyzz(M.ra_e + o);
         if (row >= 2 && !((lane >> (row - 2)) & 1u)) return xyzz_identity();
         return ld_xyzz(M.ra_t + o);
     }
-    //   R1 (entries = 32-blocks of one window): rows 0..1+bits0 = plain sums of the R0 rows,
+    //   R1 (entries = R0 blocks of one window): rows 0..1+bits0 = plain sums of the R0 rows,
     //   row 2+bits0+k = R0 row 0 (T) of blocks whose index has bit k set
     static H2_HD xyzz r1_contrib(const MsmPlan &p, const MsmBuffers &M, uint32_t w, uint32_t row, uint32_t blk) {
         if (blk >= p.nb0) return xyzz_identity();
@@ -297,6 +309,47 @@ template <class P, class PS> struct Msm {
         uint32_t shift = p.c * w + (r >= 2 ? (r - 2) + p.l0 : 0);
         xyzz_shift<P>(v, shift);
         return v;
+    }
+    // Window table of a resident base set: table[w * stride + i] = affine(2^(c w) * base[i]).
+    // One thread per base: W - 1 shifts of c Jacobian doublings each, then ONE inversion shared by
+    // the thread's W - 1 points (Montgomery's trick) to bring them back to affine.  W <= 64 (c >= 4).
+    static H2_HD void table_body(const affine *bases, affine *table, uint64_t count, uint64_t stride, uint32_t c, uint32_t W, uint64_t i) {
+        if (i >= count) return;
+        affine g = ld_affine(bases + i);
+        st_affine(table + i, g);
+        if (affine_is_identity(g) || W > 64) {
+            for (uint32_t w = 1; w < W; w++) st_affine(table + (uint64_t)w * stride + i, g);   // identity stays identity
+            return;
+        }
+        fe zs[64], pre[64];               // Z_w and Z_1 ... Z_(w-1)
+        fe X = g.x, Y = g.y, Z = fe_one<P>(), run = fe_one<P>();
+        for (uint32_t w = 1; w < W; w++) {
+            for (uint32_t d = 0; d < c; d++) {      // dbl-2009-l, a = 0
+                fe A = fe_sqr<P>(X), B = fe_sqr<P>(Y), C = fe_sqr<P>(B);
+                fe t = fe_add<P>(X, B);
+                fe D = fe_dbl<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(t), A), C));
+                fe E = fe_add<P>(fe_dbl<P>(A), A);
+                fe F = fe_sqr<P>(E);
+                fe Z3 = fe_dbl<P>(fe_mul<P>(Y, Z));
+                X = fe_sub<P>(fe_sub<P>(F, D), D);
+                Y = fe_sub<P>(fe_mul<P>(E, fe_sub<P>(D, X)), fe_dbl<P>(fe_dbl<P>(fe_dbl<P>(C))));
+                Z = Z3;
+            }
+            affine tmp; tmp.x = X; tmp.y = Y;   // Jacobian X_w, Y_w parked in the slot
+            st_affine(table + (uint64_t)w * stride + i, tmp);
+            zs[w] = Z; pre[w] = run;
+            run = fe_mul<P>(run, Z);
+        }
+        fe inv = fe_inv<P>(run);          // Z != 0: a prime-order curve has no 2-torsion
+        for (uint32_t w = W - 1; w >= 1; w--) {
+            fe zi = fe_mul<P>(inv, pre[w]);
+            inv = fe_mul<P>(inv, zs[w]);
+            fe zi2 = fe_sqr<P>(zi);
+            affine a = ld_affine(table + (uint64_t)w * stride + i);
+            a.x = fe_mul<P>(a.x, zi2);
+            a.y = fe_mul<P>(a.y, fe_mul<P>(zi2, zi));
+            st_affine(table + (uint64_t)w * stride + i, a);
+        }
     }
     static H2_HD void finish(const MsmBuffers &M, const xyzz &total, uint32_t out_canonical) {
         jacobian j = xyzz_to_jacobian<P>(total);
@@ -339,7 +392,7 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_ker
         int32_t d = Msm<P, PS>::next_digit(s, w, p.c, carry);
         bool act = in && d != 0;
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        uint64_t g = (uint64_t)w * p.B + (act ? mag - 1 : 0);
+        uint64_t g = (uint64_t)(p.fixed ? 0 : w) * p.B + (act ? mag - 1 : 0);
         warp_inc<false>(M.counts + g, act);
     }
 }
@@ -359,13 +412,13 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_
             int32_t d = w < p.W ? Msm<P, PS>::next_digit(s, w, p.c, carry) : 0;
             act[k] = in && d != 0;
             uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            gid[k] = (uint32_t)((uint64_t)(w < p.W ? w : 0) * p.B + (act[k] ? mag - 1 : 0));
-            neg[k] = d < 0 ? 0x80000000u : 0u;
+            gid[k] = (uint32_t)((uint64_t)(w < p.W && !p.fixed ? w : 0) * p.B + (act[k] ? mag - 1 : 0));
+            neg[k] = (d < 0 ? 0x80000000u : 0u) | (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0);
             slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
         }
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (act[k]) M.refs[M.counts[gid[k]] + slot[k]] = (uint32_t)i | neg[k];
+            if (act[k]) M.refs[M.counts[gid[k]] + slot[k]] = (uint32_t)i + neg[k];   // sign bit | table offset + index
     }
 }
 // work-item construction: size histogram, bases, then placement (descending size)
@@ -389,6 +442,10 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_pla
     }
     uint32_t at = warp_inc<true>(M.size_cursor + rem, rem != 0);
     if (rem) M.items[at] = make_uint2((uint32_t)g, lo + nfull * p.T);
+}
+template <class P, class PS> __global__ void __launch_bounds__(128) msm_table_kernel(const affine *bases, affine *table, uint64_t count, uint64_t stride,
+                                                                                    uint32_t c, uint32_t W) {
+    Msm<P, PS>::table_body(bases, table, count, stride, c, W, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 template <class P, class PS> __global__ void __launch_bounds__(128, 5) msm_accum0_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -426,17 +483,17 @@ template <class P> __device__ __forceinline__ void block_tree_sum(xyzz *sh, xyzz
         __syncthreads();
     }
 }
-// R0: one thread per (window, 32-block, row): a serial sum of <= 32 entries keeps every lane busy
-// (a shared-memory tree would run 31 adds in 5 SIMT steps at 1/2 .. 1/32 lane utilisation).
+// R0: one thread per (window, 8-block, row): a short serial sum keeps every lane busy (a shared-memory
+// tree runs its adds at 1/2 .. 1/32 lane utilisation).
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_r0_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t rows = 2 + p.bits0;
-    if (tid >= (uint64_t)p.W * p.nb0 * rows) return;
+    if (tid >= (uint64_t)p.Wb * p.nb0 * rows) return;
     uint32_t row = (uint32_t)(tid % rows);
     uint64_t wb = tid / rows;
     uint32_t w = (uint32_t)(wb / p.nb0), blk = (uint32_t)(wb % p.nb0);
     xyzz v = xyzz_identity();
-    for (uint32_t lane = 0; lane < 32; lane++) {
+    for (uint32_t lane = 0; lane < (1u << H2_R0_LOG); lane++) {
         if (row >= 2 && !((lane >> (row - 2)) & 1u)) continue;
         xyzz c = Msm<P, PS>::r0_contrib(p, M, w, blk, row, lane);
         xyzz_add<P>(v, c);
@@ -466,7 +523,7 @@ template <class P, class PS> __global__ void __launch_bounds__(32) msm_wsum_kern
 template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_kernel(const MsmPlan p, const MsmBuffers M, uint32_t out_canonical) {
     __shared__ xyzz sh[64];
     xyzz v = xyzz_identity();
-    for (uint32_t w = threadIdx.x; w < p.W; w += 64) { xyzz c = ld_xyzz(M.wsum + w); xyzz_add<P>(v, c); }
+    for (uint32_t w = threadIdx.x; w < p.Wb; w += 64) { xyzz c = ld_xyzz(M.wsum + w); xyzz_add<P>(v, c); }
     block_tree_sum<P>(sh, v, 0, threadIdx.x, 64);
     if (threadIdx.x == 0) Msm<P, PS>::finish(M, v, out_canonical);
 }

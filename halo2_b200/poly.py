@@ -35,7 +35,7 @@ class Params:
     polynomial.  Generator DERIVATION (Params::new's hash-to-curve, :38-114) is the caller's:
     pass the generators in, e.g. as read by Params::read (:185-205)."""
 
-    def __init__(self, curve: str, k: int, g, g_lagrange, w, u=None):
+    def __init__(self, curve: str, k: int, g, g_lagrange, w, u=None, precompute: bool = True, window_bits: int = 0):
         assert k < 32  # commitment.rs:41
         self.curve, self.k, self.n = curve, k, 1 << k
         self.g = _l.as_u8(g, 64)
@@ -48,9 +48,12 @@ class Params:
         self._h_gl = ctypes.c_uint64(0)
         cid = _l.CURVE_ID[curve]
         both = np.concatenate([self.g, self.w])            # tmp_bases = g ++ [w]  (:126-127)
-        _l.check(lib.h2_bases_register(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL, ctypes.byref(self._h_g)))
+        flags = 1 if precompute else 0   # H2_BASES_PRECOMPUTE: window tables, fixed-base MSM
+        _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL,
+                                          ctypes.c_uint32(window_bits), ctypes.c_uint32(flags), ctypes.byref(self._h_g)))
         both = np.concatenate([self.g_lagrange, self.w])   # g_lagrange ++ [w]     (:146-147)
-        _l.check(lib.h2_bases_register(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL, ctypes.byref(self._h_gl)))
+        _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL,
+                                          ctypes.c_uint32(window_bits), ctypes.c_uint32(flags), ctypes.byref(self._h_gl)))
 
     def _commit(self, handle, poly, r: Blind) -> np.ndarray:
         p = _l.as_u8(poly, 32)

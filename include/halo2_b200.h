@@ -58,6 +58,13 @@ int h2_msm(int curve, const void *scalars, const void *bases_xy, size_t n, int r
  * upload once, commit many times.  Replaces the per-call Vec copies of commit/commit_lagrange
  * (poly/commitment.rs:119-150). */
 int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle);
+/* Same, with options.  flags & H2_BASES_PRECOMPUTE: also build the window table
+ * T[w][i] = 2^(c w) * bases[i] (W = ceil(256/c) affine copies, c = window_bits or automatic when 0).
+ * h2_msm_registered then drops every window's digits into ONE bucket set: no window combine, 1/W of
+ * the bucket reduce -- what makes k = 14 sized commits latency-friendly. */
+enum { H2_BASES_PRECOMPUTE = 1 };
+int h2_bases_register_ex(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags,
+                         uint64_t *handle);
 int h2_bases_release(uint64_t handle);
 /* sum_{i<n} scalars[i] * bases[i]  (+ extra_scalar[0] * bases[n] when extra_scalar != NULL):
  * commit(poly, r) = h2_msm_registered(h(g ++ [w]), poly, n, &r, ...). */

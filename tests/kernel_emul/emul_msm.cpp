@@ -7,9 +7,11 @@ using namespace h2;
 
 template <class P, class PS>
 static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c, int scalars_mont,
-                   uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
+                   uint32_t force_t, uint32_t force_kn, int fixed, uint8_t *out_xyz) {
     MsmPlan p;
-    msm_make_plan(p, n, c ? c : msm_default_window(n), force_t, force_kn);
+    if (!c) c = msm_default_window(n);
+    if (fixed && c < 4) c = 4;      // table windows: W = ceil(256 / c) <= 64
+    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3);
     if (p.acc_levels > H2_MSM_MAX_LEVELS) return -2;
     std::vector<fe> sc(n ? n : 1), sc_canon(n ? n : 1);
     std::vector<affine> bs(n ? n : 1);
@@ -19,6 +21,11 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         affine a; memcpy(a.x.v, bases + 64 * i, 32); memcpy(a.y.v, bases + 64 * i + 32, 32);
         if (!affine_is_identity(a)) { a.x = fe_to_mont<P>(a.x); a.y = fe_to_mont<P>(a.y); }
         bs[i] = a;
+    }
+    std::vector<affine> table;
+    if (fixed) {   // table[w * stride + i] = 2^(c w) * base[i]; stride > n on purpose
+        table.resize((size_t)p.W * p.stride);
+        for (size_t i = 0; i < n; i++) Msm<P, PS>::table_body(bs.data(), table.data(), n, p.stride, p.c, p.W, i);
     }
     std::vector<uint32_t> counts(p.G + 1, 0), cursor(p.G, 0), refs(p.max_refs ? p.max_refs : 1), size_hist(p.T + 2, 0),
         size_cursor(p.T + 1, 0), flags(4, 0);
@@ -30,7 +37,7 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         r1((size_t)p.W * p.r1_rows), wsum(p.W);
     jacobian result;
     MsmBuffers M;
-    M.scalars = sc.data(); M.bases = bs.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
+    M.scalars = sc.data(); M.bases = fixed ? table.data() : bs.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
     M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data();
     M.size_hist = size_hist.data(); M.size_cursor = size_cursor.data(); M.flags = flags.data(); M.items = items.data();
     M.bucket_sum = bucket_sum.data(); M.pkey = pkey.data(); M.pstart = pstart.data(); M.pend = pend.data();
@@ -43,7 +50,7 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         uint32_t carry = 0;
         for (uint32_t w = 0; w < p.W; w++) {
             int32_t d = K::next_digit(s, w, p.c, carry);
-            if (d) counts[(uint64_t)w * p.B + (uint32_t)(d < 0 ? -d : d) - 1]++;
+            if (d) counts[(uint64_t)(p.fixed ? 0 : w) * p.B + (uint32_t)(d < 0 ? -d : d) - 1]++;
         }
         if (carry) return -3;    // top window must absorb the carry
     }
@@ -56,8 +63,8 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         for (uint32_t w = 0; w < p.W; w++) {
             int32_t d = K::next_digit(s, w, p.c, carry);
             if (!d) continue;
-            uint64_t g = (uint64_t)w * p.B + (uint32_t)(d < 0 ? -d : d) - 1;
-            refs[counts[g] + cursor[g]++] = (uint32_t)ii | (d < 0 ? 0x80000000u : 0u);
+            uint64_t g = (uint64_t)(p.fixed ? 0 : w) * p.B + (uint32_t)(d < 0 ? -d : d) - 1;
+            refs[counts[g] + cursor[g]++] = ((uint32_t)ii + (uint32_t)(p.fixed ? (uint64_t)w * p.stride : 0)) | (d < 0 ? 0x80000000u : 0u);
         }
     }
     // work items
@@ -77,23 +84,23 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     for (uint32_t lv = 1; lv < p.acc_levels; lv++)
         for (uint64_t t = 0; t < p.acc_threads[lv]; t++) K::accumN_body(p, M, lv, t);
     // K5
-    for (uint64_t t = 0; t < (uint64_t)p.W * p.m1; t++) K::reduceA_body(p, M, t);
-    for (uint32_t w = 0; w < p.W; w++)
+    for (uint64_t t = 0; t < (uint64_t)p.Wb * p.m1; t++) K::reduceA_body(p, M, t);
+    for (uint32_t w = 0; w < p.Wb; w++)
         for (uint32_t blk = 0; blk < p.nb0; blk++)
             for (uint32_t row = 0; row < H2_R0_ROWS; row++) {
                 xyzz v = xyzz_identity();
                 if (row < 2 + p.bits0)
-                    for (uint32_t lane = 0; lane < 32; lane++) { xyzz cc = K::r0_contrib(p, M, w, blk, row, lane); xyzz_add<P>(v, cc); }
+                    for (uint32_t lane = 0; lane < (1u << H2_R0_LOG); lane++) { xyzz cc = K::r0_contrib(p, M, w, blk, row, lane); xyzz_add<P>(v, cc); }
                 r0[((size_t)w * p.nb0 + blk) * H2_R0_ROWS + row] = v;
             }
-    for (uint32_t w = 0; w < p.W; w++)
+    for (uint32_t w = 0; w < p.Wb; w++)
         for (uint32_t row = 0; row < p.r1_rows; row++) {
             xyzz v = xyzz_identity();
             for (uint32_t blk = 0; blk < p.nb0; blk++) { xyzz cc = K::r1_contrib(p, M, w, row, blk); xyzz_add<P>(v, cc); }
             r1[(size_t)w * p.r1_rows + row] = v;
         }
     xyzz total = xyzz_identity();
-    for (uint32_t w = 0; w < p.W; w++)
+    for (uint32_t w = 0; w < p.Wb; w++)
         for (uint32_t r = 0; r < 32; r++) { xyzz cc = K::wsum_item(p, M, w, r); xyzz_add<P>(total, cc); }
     K::finish(M, total, 1);
     memcpy(out_xyz, result.x.v, 32); memcpy(out_xyz + 32, result.y.v, 32); memcpy(out_xyz + 64, result.z.v, 32);
@@ -103,6 +110,12 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
 // curve 0 = Pallas (coords Fp, scalars Fq), 1 = Vesta.  Returns acc_levels (+100 if some bucket was split) or <0.
 extern "C" int emu_msm(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
                        int scalars_mont, uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
-    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, out_xyz);
-    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, out_xyz);
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, out_xyz);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, out_xyz);
+}
+// same MSM through the precomputed window table (resident-bases path of Params::commit*)
+extern "C" int emu_msm_fixed(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
+                             uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, out_xyz);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, out_xyz);
 }

@@ -271,6 +271,46 @@ def test_commit_lagrange_equals_commit(eng, curve):
     params.close()
 
 
+@pytest.mark.parametrize("curve,k", [("vesta", 14), ("pallas", 10)])
+def test_resident_bases_with_window_table(eng, curve, k):
+    """Params::commit on resident generators with the precomputed window table (fixed-base MSM) ==
+    the reference algorithm on the same n+1 terms (poly/commitment.rs:119-130); with and without the
+    table, several window sizes, skewed polynomials (0/1 selector columns, constant columns)."""
+    import ctypes
+    from halo2_b200 import lib as L
+    c = pasta.CURVES[curve]
+    n = 1 << k
+    g = cref.gen_points(curve, SEED + 21, n + 1)      # g_0..g_(n-1), w
+    lib = L.init()
+    polys = {
+        "random": cref.gen_scalars(c.scalar, SEED + 22, n),
+        "zero": np.zeros((n, 32), dtype=np.uint8),
+        "sel01": cref.ints_to_bytes([i & 1 for i in range(n)]),
+        "const": cref.ints_to_bytes([pasta.gen_scalars(c.scalar, 5, 1)[0]] * n),
+        "small": cref.ints_to_bytes([i % 251 for i in range(n)]),
+    }
+    blind = pasta.gen_scalars(c.scalar, SEED + 23, 1)[0]
+    wants = {}
+    for name, poly in polys.items():
+        kb = np.concatenate([poly, cref.ints_to_bytes([blind])])
+        wants[name] = cref.bytes_to_affine(cref.best_multiexp(curve, kb, g))
+    for flags, wbits in ((1, 0), (1, 9), (1, 13), (0, 0)):
+        h = ctypes.c_uint64(0)
+        L.check(lib.h2_bases_register_ex(L.CURVE_ID[curve], L.ptr(g), ctypes.c_size_t(n + 1), L.REPR_CANONICAL,
+                                         ctypes.c_uint32(wbits), ctypes.c_uint32(flags), ctypes.byref(h)))
+        try:
+            for name, poly in polys.items():
+                out = np.zeros(96, dtype=np.uint8)
+                L.check(lib.h2_msm_registered(h, L.ptr(poly), ctypes.c_size_t(n), L.ptr(L.fe_bytes(blind)), L.REPR_CANONICAL, L.ptr(out)))
+                assert _affine(curve, out) == wants[name], (name, flags, wbits)
+            # fewer scalars than bases (IPA-style prefix) and no blind
+            out = np.zeros(96, dtype=np.uint8)
+            L.check(lib.h2_msm_registered(h, L.ptr(polys["random"]), ctypes.c_size_t(n // 2), None, L.REPR_CANONICAL, L.ptr(out)))
+            assert _affine(curve, out) == cref.bytes_to_affine(cref.best_multiexp(curve, polys["random"][: n // 2], g[: n // 2]))
+        finally:
+            L.check(lib.h2_bases_release(h))
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS

@@ -137,3 +137,36 @@ def test_emul_msm(emu, curve):
     want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb2))
     for cb, k0, gs in ((0, 0, 0), (3, 2, 4), (13, 0, 0)):
         assert _msm(emu, curve, kb, pb2, cb, 0, k0, gs) == want
+
+
+def _msm_fixed(emu, curve, kb, pb, c=0, t=0, kn=0):
+    out = np.zeros(96, dtype=np.uint8)
+    r = emu.emu_msm_fixed(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(kb)), cref._p(np.ascontiguousarray(pb)),
+                          ctypes.c_size_t(kb.shape[0]), c, t, kn, cref._p(out))
+    assert r > 0, r
+    return cref.bytes_to_affine(cref.jac_to_affine(curve, out))
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_msm_fixed_base_table(emu, curve):
+    """Resident-bases path: precomputed table T[w][i] = 2^(c w) G_i, one shared bucket set."""
+    c = pasta.CURVES[curve]
+    g = pasta.generator(c)
+    for n in (1, 2, 9, 65, 130):
+        kb = cref.gen_scalars(c.scalar, 40 + n, n)
+        pts = [cref.bytes_to_affine(x) for x in cref.gen_points(curve, 41 + n, n)]
+        if n >= 9:
+            pts[3] = None            # identity base
+            pts[5] = pts[4]          # duplicate
+            pts[7] = (g[0], c.p - g[1])
+        pb = cref.affines_to_bytes(pts)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        for cb, t, kn in ((0, 0, 0), (4, 2, 4), (7, 0, 0), (13, 3, 8), (16, 0, 0)):
+            assert _msm_fixed(emu, curve, kb, pb, cb, t, kn) == want, (n, cb, t, kn)
+    n = 64
+    pb = cref.gen_points(curve, 9, n)
+    for ks in ([0] * n, [1] * n, [c.r - 1] * n, [i & 1 for i in range(n)], [(1 << (i * 4 % 255)) % c.r for i in range(n)]):
+        kb = cref.ints_to_bytes(ks)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        for cb in (5, 16):
+            assert _msm_fixed(emu, curve, kb, pb, cb) == want

@@ -78,12 +78,41 @@ def msm_time(log_n, curve=0, c=0, reps=5, extra=0):
     print(f"msm n=2^{log_n}+{extra} c={c}: {ms:.3f} ms  {n / ms / 1e3:.2f} M pairs/s", flush=True)
 
 
+def commit_time(k, curve=1, reps=20):
+    """Host-buffer commits against resident bases (the Params::commit path), with / without the window table."""
+    n = (1 << k) + 1
+    bases = torch.empty((n, 16), dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.h2_dev_gen_points(curve, 11, 0, ctypes.c_size_t(n), ctypes.c_void_p(bases.data_ptr()), ctypes.c_void_p(s)))
+    torch.cuda.synchronize()
+    hb = bases.cpu().numpy().view(np.uint8).reshape(n, 64)
+    sc = rand_scalars(n - 1, 3).cpu().numpy().view(np.uint8).reshape(n - 1, 32)
+    blind = np.frombuffer((7).to_bytes(32, "little"), dtype=np.uint8).copy()
+    for flags in (0, 1):
+        h = ctypes.c_uint64(0)
+        t0 = time.time()
+        L.check(lib.h2_bases_register_ex(curve, L.ptr(hb), ctypes.c_size_t(n), 1, 0, flags, ctypes.byref(h)))
+        treg = time.time() - t0
+        out = np.zeros(96, dtype=np.uint8)
+        for _ in range(3):
+            L.check(lib.h2_msm_registered(h, L.ptr(sc), ctypes.c_size_t(n - 1), L.ptr(blind), 0, L.ptr(out)))
+        t0 = time.time()
+        for _ in range(reps):
+            L.check(lib.h2_msm_registered(h, L.ptr(sc), ctypes.c_size_t(n - 1), L.ptr(blind), 0, L.ptr(out)))
+        dt = (time.time() - t0) / reps
+        print(f"commit k={k} table={flags}: {dt * 1e3:.3f} ms per commit (register {treg * 1e3:.1f} ms)", flush=True)
+        L.check(lib.h2_bases_release(h))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["mul", "ntt", "msm"]
     if "mul" in what:
         mulbench()
     if "lat" in what:
         latbench()
+    if "commit" in what:
+        for k in (10, 14, 16, 20):
+            commit_time(k)
     if "ntt" in what:
         for k in (14, 16, 20, 24):
             ntt_time(k)
