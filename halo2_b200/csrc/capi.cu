@@ -50,6 +50,8 @@ struct Context {
     bool ready = false;
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // uploads that may overlap compute (bases of a one-shot MSM)
+    cudaEvent_t ev_scalars_up = nullptr, ev_bases_up = nullptr;
     cudaEvent_t last_use = nullptr;
     bool have_last = false;
     uint32_t window_override = 0;
@@ -129,6 +131,9 @@ extern "C" int h2_init(int device) {
     if (prop.major < 10) return fail("h2_init: this library is built for sm_100a (B200) only");
     CU(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&g_ctx.last_use, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g_ctx.ev_scalars_up, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g_ctx.ev_bases_up, cudaEventDisableTiming));
     g_ctx.device = device;
     g_ctx.ready = true;
     return 0;
@@ -147,6 +152,8 @@ extern "C" int h2_shutdown(void) {
     g_ctx.twiddles.clear();
     for (auto &kv : g_ctx.bases) { kv.second->buf.release(); kv.second->table.release(); delete kv.second; }
     g_ctx.bases.clear();
+    cudaEventDestroy(g_ctx.ev_scalars_up); cudaEventDestroy(g_ctx.ev_bases_up);
+    cudaStreamDestroy(g_ctx.copy_stream);
     cudaEventDestroy(g_ctx.last_use);
     cudaStreamDestroy(g_ctx.stream);
     g_ctx = Context();
@@ -310,7 +317,7 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s) {
 // fixed != 0: d_bases is a window table (stride points per window) built with window size c
 template <class P, class PS>
 static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, uint32_t fixed, uint64_t stride,
-                   jacobian *d_out, int out_canonical, cudaStream_t s) {
+                   jacobian *d_out, int out_canonical, cudaStream_t s, cudaEvent_t bases_ready = nullptr) {
     Context &X = g_ctx;
     if (n == 0) {   // empty sum = identity
         jacobian id;
@@ -375,6 +382,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     LAUNCH(k_ihist, blocks_for(p.G, 256), 256, 0, s, p, M);
     LAUNCH(k_ibases, 1, 32, 0, s, p, M);
     LAUNCH(k_iplace, blocks_for(p.G, 256), 256, 0, s, p, M);
+    if (bases_ready) CU(cudaStreamWaitEvent(s, bases_ready, 0));   // the sort above only needed the scalars
     prof_begin(PROF_MSM_ACCUM0, s);
     LAUNCH(k_accum0, blocks_for(p.max_items, 128), 128, 0, s, p, M);
     prof_end(s);
@@ -390,9 +398,10 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
 }
 
 static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
-                        jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0) {
-    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s);
-    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s);
+                        jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0,
+                        cudaEvent_t bases_ready = nullptr) {
+    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready);
+    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready);
     return fail("unknown curve id");
 }
 // window size for a precomputed table over n bases: few references per bucket (short serial chains)
@@ -440,16 +449,29 @@ extern "C" int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, co
     return scratch_release(s);
 }
 
+// host_bases != nullptr: one-shot MSM -- the bases are uploaded (and converted) on the copy stream AFTER the
+// scalars, overlapping the digit/sort kernels, which only read scalars.
 static int msm_host_common(int curve, const void *scalars, size_t n_scalars, const void *extra_scalar, const affine *d_bases,
-                           size_t n_total, int repr, void *out_xyz, uint32_t c = 0, uint32_t fixed = 0, uint64_t stride = 0) {
+                           size_t n_total, int repr, void *out_xyz, uint32_t c = 0, uint32_t fixed = 0, uint64_t stride = 0,
+                           const void *host_bases = nullptr) {
     Context &X = g_ctx;
     cudaStream_t s = X.stream;
     if (scratch_acquire(s)) return 1;
     if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
     if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
     if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
+    cudaEvent_t bases_ready = nullptr;
+    if (host_bases && n_total) {
+        cudaStream_t cs = X.copy_stream;
+        CU(cudaEventRecord(X.ev_scalars_up, s));
+        CU(cudaStreamWaitEvent(cs, X.ev_scalars_up, 0));      // scalars first on the PCIe link (and after prior scratch users)
+        CU(cudaMemcpyAsync(const_cast<affine *>(d_bases), host_bases, n_total * sizeof(affine), cudaMemcpyHostToDevice, cs));
+        if (repr == H2_REPR_CANONICAL && convert_points(curve, const_cast<affine *>(d_bases), n_total, 1, cs)) return 1;
+        CU(cudaEventRecord(X.ev_bases_up, cs));
+        bases_ready = X.ev_bases_up;
+    }
     int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
-                          repr == H2_REPR_CANONICAL, s, fixed, stride);
+                          repr == H2_REPR_CANONICAL, s, fixed, stride, bases_ready);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
     if (scratch_release(s)) return 1;
@@ -465,9 +487,7 @@ extern "C" int h2_msm(int curve, const void *scalars, const void *bases_xy, size
     cudaStream_t s = X.stream;
     if (scratch_acquire(s)) return 1;
     if (X.bases_in.ensure((n + 1) * sizeof(affine))) return 1;
-    if (n) CU(cudaMemcpyAsync(X.bases_in.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
-    if (repr == H2_REPR_CANONICAL && convert_points(curve, X.bases_in.as<affine>(), n, 1, s)) return 1;
-    return msm_host_common(curve, scalars, n, nullptr, X.bases_in.as<affine>(), n, repr, out_xyz);
+    return msm_host_common(curve, scalars, n, nullptr, X.bases_in.as<affine>(), n, repr, out_xyz, 0, 0, 0, bases_xy);
 }
 
 static int bases_register_impl(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle);
