@@ -55,8 +55,9 @@ struct Context {
     cudaEvent_t last_use = nullptr;
     bool have_last = false;
     uint32_t window_override = 0;
+    uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
     // MSM scratch
-    DevBuf scal_in, bases_in, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
+    DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
         wsum, scan_blocks, result, misc;
     // NTT scratch
     DevBuf ntt_io, ntt_out, ntt_work, pow2;
@@ -143,7 +144,7 @@ extern "C" int h2_shutdown(void) {
     if (!g_ctx.ready) return 0;
     cudaSetDevice(g_ctx.device);
     cudaDeviceSynchronize();
-    DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
+    DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.bases_phi, &g_ctx.glv_parts, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
                      &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
                      &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
                      &g_ctx.ntt_work, &g_ctx.pow2};
@@ -157,6 +158,11 @@ extern "C" int h2_shutdown(void) {
     cudaEventDestroy(g_ctx.last_use);
     cudaStreamDestroy(g_ctx.stream);
     g_ctx = Context();
+    return 0;
+}
+extern "C" int h2_set_glv(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ctx.glv_on = on ? 1u : 0u;
     return 0;
 }
 extern "C" int h2_set_window_bits(uint32_t c) {
@@ -328,9 +334,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         return 0;
     }
     MsmPlan p;
-    if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n);
+    const uint32_t glv = (!fixed && X.glv_on && n < (1ull << 30)) ? 1u : 0u;
+    if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
     if (c > 24) return fail("msm: window bits > 24");
-    msm_make_plan(p, n, c, 0, 0, fixed, stride);
+    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv);
+    if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 40))) return 1;
     if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
     if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
     if (scalars_mont && X.scal_canon.ensure(n * sizeof(fe))) return 1;
@@ -344,7 +352,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         X.wsum.ensure((size_t)p.Wb * sizeof(xyzz)))
         return 1;
     MsmBuffers M;
-    M.scalars = d_scalars; M.bases = d_bases; M.scalars_mont = scalars_mont ? 1u : 0u;
+    M.scalars = d_scalars; M.bases = d_bases; M.bases_phi = X.bases_phi.as<affine>(); M.glv_parts = X.glv_parts.as<uint32_t>(); M.scalars_mont = scalars_mont ? 1u : 0u;
     M.scal_canon = X.scal_canon.as<fe>();
     M.counts = X.counts.as<uint32_t>(); M.cursor = X.cursor.as<uint32_t>();
     M.refs = X.refs.as<uint32_t>();
@@ -383,11 +391,16 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     LAUNCH(k_ibases, 1, 32, 0, s, p, M);
     LAUNCH(k_iplace, blocks_for(p.G, 256), 256, 0, s, p, M);
     if (bases_ready) CU(cudaStreamWaitEvent(s, bases_ready, 0));   // the sort above only needed the scalars
+    if (p.glv) {
+        auto k_phi = msm_phi_kernel<P, PS>;
+        LAUNCH(k_phi, blocks_for(n, 256), 256, 0, s, d_bases, M.bases_phi, (uint64_t)n);
+    }
     prof_begin(PROF_MSM_ACCUM0, s);
     LAUNCH(k_accum0, blocks_for(p.max_items, 128), 128, 0, s, p, M);
     prof_end(s);
     if (p.acc_levels > 1) LAUNCH(k_accumN, blocks_for(p.acc_threads[1], 128), 128, 0, s, p, M, 1u);
-    if (p.acc_levels > 2) LAUNCH(k_rest, 1, 256, 0, s, p, M);
+    if (p.acc_levels > 2) LAUNCH(k_accumN, blocks_for(p.acc_threads[2], 128), 128, 0, s, p, M, 2u);
+    if (p.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, p, M);
     // K5: bucket reduce and window combine
     LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1, 128), 128, 0, s, p, M);
     LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0), 128), 128, 0, s, p, M);

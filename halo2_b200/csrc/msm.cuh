@@ -27,6 +27,7 @@
 // bytes.
 #pragma once
 #include "curve.cuh"
+#include "glv.cuh"
 
 namespace h2 {
 
@@ -44,14 +45,15 @@ H2_HD void st_jacobian(jacobian *p, const jacobian &a) { fe_store(&p->x, a.x); f
 struct MsmPlan {
     uint64_t n;          // number of (scalar, base) pairs
     uint32_t c;          // window bits
-    uint32_t W;          // windows = ceil(256 / c)
+    uint32_t glv;        // 1: scalars are split k = k1 + k2 lambda (glv.cuh); point i contributes P_i (k1) and phi(P_i) (k2)
+    uint32_t W;          // windows = ceil(256 / c), or ceil(130 / c) with the GLV split
     uint32_t B;          // buckets per window = 2^(c-1)
     uint32_t fixed;      // 1: bases come from a precomputed table T[w][i] = 2^(c w) G_i (resident Params
                          //    generators): every window's digits share ONE bucket set, no window combine
     uint32_t Wb;         // bucket sets = fixed ? 1 : W
     uint64_t stride;     // fixed: points per table window
     uint64_t G;          // total buckets = Wb * B
-    uint64_t max_refs;   // n * W
+    uint64_t max_refs;   // n * W (x 2 with the GLV split)
     uint32_t T;          // references per work item (larger buckets are split)
     uint64_t max_items;  // upper bound of work items = G + max_refs / T
     // partial-merge levels: level 1 consumes the slots written by split buckets
@@ -72,28 +74,31 @@ struct MsmPlan {
 
 inline uint32_t ilog2_u32(uint32_t v) { uint32_t r = 0; while (r < 31 && (1u << (r + 1)) <= v) r++; return r; }
 
-inline uint32_t msm_default_window(uint64_t n) {
-    // Cost model (XYZZ): n * W mixed adds (10 M) + 2 * W * 2^(c-1) full adds (14 M).
-    if (n < 32) return 3;
-    uint32_t lg = 0;
-    while ((1ull << (lg + 1)) <= n) lg++;
-    uint32_t c = lg > 4 ? lg - 4 : 1;
-    if (c < 4) c = 4;
-    if (c > 20) c = 20;
-    return c;
+// Window size.  Besides the usual work balance (n W mixed adds vs 2 W 2^(c-1) reduce adds) the TOP window
+// matters: it only holds (bits mod c) real bits, so its references crowd into few buckets unless that
+// remainder is close to c.  255 = 15*16 + 15 = 19*13 + 8 = 31*8 + 7 and (GLV halves) 127 = 7*16 + 15 =
+// 9*13 + 10 = 15*8 + 7: c in {8, 13, 16} keeps the top window well filled for both scalar widths.
+inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
+    uint64_t n_eff = glv ? 2 * n : n;
+    if (n_eff < 64) return 4;
+    if (n_eff < (1ull << 10)) return 8;
+    if (n_eff < (1ull << 14)) return 13;
+    return 16;
 }
 
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
-                          uint64_t stride = 0) {
+                          uint64_t stride = 0, uint32_t glv = 0) {
     p.n = n; p.c = c;
-    p.W = (256 + c - 1) / c;
+    p.glv = fixed ? 0u : glv;
+    // sub-scalars are < 2^129; one spare bit lets the top window absorb the signed-digit carry
+    p.W = p.glv ? (130 + c - 1) / c : (256 + c - 1) / c;
     p.B = 1u << (c - 1);
     p.fixed = fixed; p.Wb = fixed ? 1u : p.W; p.stride = stride;
     p.G = (uint64_t)p.Wb * p.B;
-    p.max_refs = n * p.W;
+    p.max_refs = n * p.W * (p.glv ? 2 : 1);
     // references per work item: 128 for big problems; shorter chains when there is little parallelism
-    uint32_t T = 128;
-    while (T > 32 && p.max_refs / T < 32768) T >>= 1;
+    uint32_t T = 256;
+    while (T > 32 && p.max_refs / T < 65536) T >>= 1;
     p.T = force_t ? force_t : T;
     p.max_items = p.G + p.max_refs / p.T + 1;
     // partial slots: slot(start, chunk) = 2 * (start / T) + (chunk > 0), see item_slot()
@@ -131,9 +136,11 @@ struct MsmBuffers {
     // inputs
     const fe *scalars;        // n, canonical or Montgomery (see scalars_mont)
     const affine *bases;      // n, Montgomery coordinates
+    affine *bases_phi;        // n, phi(bases) = (zeta x, y)   (GLV only)
     uint32_t scalars_mont;
     // scratch
     fe *scal_canon;           // n (only when scalars_mont)
+    uint32_t *glv_parts;      // n x 10 words: |k1| (5 limbs, sign in bit 31 of limb 4) then |k2|   (GLV only)
     uint32_t *counts;         // G + 1  (histogram, then exclusive offsets after the scan)
     uint32_t *cursor;         // G
     uint32_t *refs;           // max_refs   point index | sign << 31, sorted by bucket id
@@ -175,6 +182,51 @@ template <class P, class PS> struct Msm {
             else x = fe_load(M.scal_canon + i);
         } else x = fe_load(M.scalars + i);
         for (int k = 0; k < 8; k++) s[k] = x.v[k];
+    }
+
+    // GLV halves of scalar i: computed (and stored) by the first pass, re-loaded by the second
+    static H2_HD void load_parts(const MsmPlan &p, const MsmBuffers &M, uint64_t i, bool first_pass, uint32_t (&part)[2][8], uint32_t (&neg)[2]) {
+        neg[0] = neg[1] = 0;
+        if (!p.glv) { uint32_t s[8]; load_scalar(M, i, s, first_pass); for (int k = 0; k < 8; k++) part[0][k] = s[k]; return; }
+        uint32_t *q = M.glv_parts + i * 10;
+        if (first_pass) {
+            uint32_t s[8];
+            load_scalar(M, i, s, true);
+            glv_decompose<P>(s, part[0], neg[0], part[1], neg[1]);
+            for (int e = 0; e < 2; e++) {
+                for (int k = 0; k < 4; k++) q[5 * e + k] = part[e][k];
+                q[5 * e + 4] = part[e][4] | (neg[e] << 31);       // |k_e| < 2^129: limb 4 has 1 bit
+            }
+        } else {
+            for (int e = 0; e < 2; e++) {
+                for (int k = 0; k < 4; k++) part[e][k] = q[5 * e + k];
+                part[e][4] = q[5 * e + 4] & 0x7fffffffu; neg[e] = q[5 * e + 4] >> 31;
+                part[e][5] = part[e][6] = part[e][7] = 0;
+            }
+        }
+    }
+
+    // Enumerates the (bucket, reference) pairs of scalar i: f(g, ref) for every non-zero digit.
+    // ref = point index | endo << 30 (phi(P) instead of P) | negate << 31; fixed-base: index into the table.
+    template <class F> static H2_HD bool for_each_digit(const MsmPlan &p, const MsmBuffers &M, uint64_t i, bool first_pass, F &&f) {
+        uint32_t part[2][8], neg[2];
+        const uint32_t halves = p.glv ? 2u : 1u;
+        load_parts(p, M, i, first_pass, part, neg);
+        bool ok = true;
+        for (uint32_t e = 0; e < halves; e++) {
+            uint32_t carry = 0;
+            for (uint32_t w = 0; w < p.W; w++) {
+                int32_t d = next_digit(part[e], w, p.c, carry);
+                if (d == 0) continue;
+                uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                uint32_t g = (uint32_t)((uint64_t)(p.fixed ? 0 : w) * p.B + (mag - 1));
+                uint32_t ref = (uint32_t)i + (uint32_t)(p.fixed ? (uint64_t)w * p.stride : 0);
+                ref |= (e << 30) | ((((uint32_t)(d < 0)) ^ neg[e]) << 31);
+                f(g, ref);
+            }
+            ok = ok && carry == 0;      // the top window must absorb the carry
+        }
+        return ok;
     }
 
     // ---- K4: work items.  Bucket g with cnt references yields ceil(cnt / T) items; item k covers
@@ -227,7 +279,9 @@ template <class P, class PS> struct Msm {
         xyzz acc = xyzz_identity();
         for (uint32_t pos = start; pos < end; pos++) {
             uint32_t ref = M.refs[pos];
-            affine b = ld_affine(M.bases + (ref & 0x7fffffffu));
+            affine b;
+            if (p.glv) b = ld_affine(((ref >> 30) & 1u ? M.bases_phi : M.bases) + (ref & 0x3fffffffu));
+            else b = ld_affine(M.bases + (ref & 0x7fffffffu));
             if (ref >> 31) b.y = fe_neg<P>(b.y);
             xyzz_add_mixed<P>(acc, b);
         }
@@ -382,44 +436,61 @@ template <bool WANT> __device__ __forceinline__ uint32_t warp_inc(uint32_t *ctr,
     return 0;
 }
 
+// digit loops are written out (not through for_each_digit) because the warp-synchronous atomics need
+// every lane to execute every (half, window) step
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool in = i < p.n;
-    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (in) Msm<P, PS>::load_scalar(M, i, s, true);
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < p.W; w++) {
-        int32_t d = Msm<P, PS>::next_digit(s, w, p.c, carry);
-        bool act = in && d != 0;
-        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        uint64_t g = (uint64_t)(p.fixed ? 0 : w) * p.B + (act ? mag - 1 : 0);
-        warp_inc<false>(M.counts + g, act);
+    uint32_t part[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}}, sneg[2] = {0, 0};
+    const uint32_t halves = p.glv ? 2u : 1u;
+    if (in) Msm<P, PS>::load_parts(p, M, i, true, part, sneg);
+    for (uint32_t e = 0; e < halves; e++) {
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < p.W; w++) {
+            int32_t d = Msm<P, PS>::next_digit(part[e], w, p.c, carry);
+            bool act = in && d != 0;
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            uint64_t g = (uint64_t)(p.fixed ? 0 : w) * p.B + (act ? mag - 1 : 0);
+            warp_inc<false>(M.counts + g, act);
+        }
     }
 }
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool in = i < p.n;
-    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (in) Msm<P, PS>::load_scalar(M, i, s, false);
-    uint32_t carry = 0;
-    for (uint32_t w0 = 0; w0 < p.W; w0 += 4) {
-        // four windows in flight so the returning atomics overlap
-        uint32_t slot[4], gid[4], neg[4];
-        bool act[4];
+    uint32_t part[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}}, sneg[2] = {0, 0};
+    const uint32_t halves = p.glv ? 2u : 1u;
+    if (in) Msm<P, PS>::load_parts(p, M, i, false, part, sneg);
+    for (uint32_t e = 0; e < halves; e++) {
+        uint32_t carry = 0;
+        for (uint32_t w0 = 0; w0 < p.W; w0 += 4) {
+            // four windows in flight so the returning atomics overlap
+            uint32_t slot[4], gid[4], ref[4];
+            bool act[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t w = w0 + k;
-            int32_t d = w < p.W ? Msm<P, PS>::next_digit(s, w, p.c, carry) : 0;
-            act[k] = in && d != 0;
-            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            gid[k] = (uint32_t)((uint64_t)(w < p.W && !p.fixed ? w : 0) * p.B + (act[k] ? mag - 1 : 0));
-            neg[k] = (d < 0 ? 0x80000000u : 0u) | (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0);
-            slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
+            for (int k = 0; k < 4; k++) {
+                uint32_t w = w0 + k;
+                int32_t d = w < p.W ? Msm<P, PS>::next_digit(part[e], w, p.c, carry) : 0;
+                act[k] = in && d != 0;
+                uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                gid[k] = (uint32_t)((uint64_t)(w < p.W && !p.fixed ? w : 0) * p.B + (act[k] ? mag - 1 : 0));
+                ref[k] = ((uint32_t)i + (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0)) | (e << 30) |
+                         ((((uint32_t)(d < 0)) ^ sneg[e]) << 31);
+                slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (act[k]) M.refs[M.counts[gid[k]] + slot[k]] = ref[k];
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (act[k]) M.refs[M.counts[gid[k]] + slot[k]] = (uint32_t)i + neg[k];   // sign bit | table offset + index
     }
+}
+// phi(P) = (zeta x, y) for the GLV split (the identity (0, 0) maps to itself)
+template <class P, class PS> __global__ void __launch_bounds__(256) msm_phi_kernel(const affine *bases, affine *out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine b = ld_affine(bases + i);
+    b.x = fe_mul<P>(b.x, glv_zeta<P>());
+    st_affine(out + i, b);
 }
 // work-item construction: size histogram, bases, then placement (descending size)
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_hist_kernel(const MsmPlan p, const MsmBuffers M) {
@@ -455,10 +526,10 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_accumN_k
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < p.acc_threads[lv]) Msm<P, PS>::accumN_body(p, M, lv, t);
 }
-// Partial-merge levels >= 2 in a single CTA (empty unless some bucket exceeded T references)
+// Partial-merge levels >= 3 in a single CTA (empty unless some bucket exceeded T references)
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_accum_rest_kernel(const MsmPlan p, const MsmBuffers M) {
     if (!M.flags[0]) return;
-    for (uint32_t lv = 2; lv < p.acc_levels; lv++) {
+    for (uint32_t lv = 3; lv < p.acc_levels; lv++) {
         for (uint64_t t = threadIdx.x; t < p.acc_threads[lv]; t += blockDim.x) Msm<P, PS>::accumN_body(p, M, lv, t);
         __threadfence();
         __syncthreads();

@@ -73,6 +73,9 @@ int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void
 
 /* Window size override for the sweep in BASELINE.json config 3 (0 = automatic). */
 int h2_set_window_bits(uint32_t c);
+/* GLV endomorphism split (k = k1 + k2 lambda, 129-bit halves; on by default) for MSMs without a
+ * window table.  Same result; switchable for A/B measurements and tests. */
+int h2_set_glv(int on);
 
 /* Device-resident MSM: d_scalars (n x 32 B, `scalars_repr`), d_bases (n x 64 B, Montgomery),
  * d_out_xyz (96 B, Montgomery).  window_bits 0 = automatic. */

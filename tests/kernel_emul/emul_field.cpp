@@ -60,3 +60,21 @@ extern "C" int emu_curve_op(int curve, int op, const uint8_t *a, const uint8_t *
     if (curve == 0) curve_op<FpParams>(op, a, b, out); else curve_op<FqParams>(op, a, b, out);
     return 0;
 }
+
+#include "glv.cuh"
+// GLV split of a canonical scalar: out = |k1| (32 B) || |k2| (32 B) || neg1 || neg2
+extern "C" int emu_glv(int curve, const uint8_t *k, uint8_t *out) {
+    uint32_t kk[8], k1[8], k2[8], n1, n2;
+    memcpy(kk, k, 32);
+    if (curve == 0) glv_decompose<FpParams>(kk, k1, n1, k2, n2); else glv_decompose<FqParams>(kk, k1, n1, k2, n2);
+    memcpy(out, k1, 32); memcpy(out + 32, k2, 32); out[64] = (uint8_t)n1; out[65] = (uint8_t)n2;
+    return 0;
+}
+// phi(P) = (zeta x, y) on canonical affine bytes
+extern "C" int emu_phi(int curve, const uint8_t *xy, uint8_t *out) {
+    fe x; memcpy(x.v, xy, 32);
+    if (curve == 0) x = fe_from_mont<FpParams>(fe_mul<FpParams>(fe_to_mont<FpParams>(x), glv_zeta<FpParams>()));
+    else x = fe_from_mont<FqParams>(fe_mul<FqParams>(fe_to_mont<FqParams>(x), glv_zeta<FqParams>()));
+    memcpy(out, x.v, 32); memcpy(out + 32, xy + 32, 32);
+    return 0;
+}

@@ -7,11 +7,11 @@ using namespace h2;
 
 template <class P, class PS>
 static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c, int scalars_mont,
-                   uint32_t force_t, uint32_t force_kn, int fixed, uint8_t *out_xyz) {
+                   uint32_t force_t, uint32_t force_kn, int fixed, int glv, uint8_t *out_xyz) {
     MsmPlan p;
-    if (!c) c = msm_default_window(n);
+    if (!c) c = msm_default_window(n, glv ? 1u : 0u);
     if (fixed && c < 4) c = 4;      // table windows: W = ceil(256 / c) <= 64
-    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3);
+    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u);
     if (p.acc_levels > H2_MSM_MAX_LEVELS) return -2;
     std::vector<fe> sc(n ? n : 1), sc_canon(n ? n : 1);
     std::vector<affine> bs(n ? n : 1);
@@ -22,6 +22,8 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         if (!affine_is_identity(a)) { a.x = fe_to_mont<P>(a.x); a.y = fe_to_mont<P>(a.y); }
         bs[i] = a;
     }
+    std::vector<affine> phi(n ? n : 1);
+    for (size_t i = 0; i < n; i++) { phi[i] = bs[i]; phi[i].x = fe_mul<P>(bs[i].x, glv_zeta<P>()); }
     std::vector<affine> table;
     if (fixed) {   // table[w * stride + i] = 2^(c w) * base[i]; stride > n on purpose
         table.resize((size_t)p.W * p.stride);
@@ -37,7 +39,9 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         r1((size_t)p.W * p.r1_rows), wsum(p.W);
     jacobian result;
     MsmBuffers M;
-    M.scalars = sc.data(); M.bases = fixed ? table.data() : bs.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
+    std::vector<uint32_t> glv_parts((n ? n : 1) * 10);
+    M.glv_parts = glv_parts.data();
+    M.scalars = sc.data(); M.bases = fixed ? table.data() : bs.data(); M.bases_phi = phi.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
     M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data();
     M.size_hist = size_hist.data(); M.size_cursor = size_cursor.data(); M.flags = flags.data(); M.items = items.data();
     M.bucket_sum = bucket_sum.data(); M.pkey = pkey.data(); M.pstart = pstart.data(); M.pend = pend.data();
@@ -46,26 +50,14 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     typedef Msm<P, PS> K;
     // K2 histogram
     for (size_t i = 0; i < n; i++) {
-        uint32_t s[8]; K::load_scalar(M, i, s, true);
-        uint32_t carry = 0;
-        for (uint32_t w = 0; w < p.W; w++) {
-            int32_t d = K::next_digit(s, w, p.c, carry);
-            if (d) counts[(uint64_t)(p.fixed ? 0 : w) * p.B + (uint32_t)(d < 0 ? -d : d) - 1]++;
-        }
-        if (carry) return -3;    // top window must absorb the carry
+        bool ok = K::for_each_digit(p, M, i, true, [&](uint32_t g, uint32_t) { counts[g]++; });
+        if (!ok) return -3;
     }
     uint32_t run = 0;
     for (uint64_t g = 0; g <= p.G; g++) { uint32_t v = counts[g]; counts[g] = run; run += v; }
     // K3 scatter (reverse order to mimic the arbitrary order atomics give)
     for (size_t ii = n; ii-- > 0;) {
-        uint32_t s[8]; K::load_scalar(M, ii, s, false);
-        uint32_t carry = 0;
-        for (uint32_t w = 0; w < p.W; w++) {
-            int32_t d = K::next_digit(s, w, p.c, carry);
-            if (!d) continue;
-            uint64_t g = (uint64_t)(p.fixed ? 0 : w) * p.B + (uint32_t)(d < 0 ? -d : d) - 1;
-            refs[counts[g] + cursor[g]++] = ((uint32_t)ii + (uint32_t)(p.fixed ? (uint64_t)w * p.stride : 0)) | (d < 0 ? 0x80000000u : 0u);
-        }
+        K::for_each_digit(p, M, ii, false, [&](uint32_t g, uint32_t ref) { refs[counts[g] + cursor[g]++] = ref; });
     }
     // work items
     for (uint64_t g = 0; g < p.G; g++) {
@@ -110,12 +102,18 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
 // curve 0 = Pallas (coords Fp, scalars Fq), 1 = Vesta.  Returns acc_levels (+100 if some bucket was split) or <0.
 extern "C" int emu_msm(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
                        int scalars_mont, uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
-    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, out_xyz);
-    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, out_xyz);
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, 0, out_xyz);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, 0, out_xyz);
+}
+// same MSM with the GLV endomorphism split
+extern "C" int emu_msm_glv(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
+                           int scalars_mont, uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, 1, out_xyz);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, 1, out_xyz);
 }
 // same MSM through the precomputed window table (resident-bases path of Params::commit*)
 extern "C" int emu_msm_fixed(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
                              uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
-    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, out_xyz);
-    return run_msm<FqParams, FpParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, out_xyz);
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, 0, out_xyz);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, 0, out_xyz);
 }

@@ -222,6 +222,29 @@ def test_best_multiexp_edge_and_skew(eng, curve):
         lib.h2_set_window_bits(0)
 
 
+def test_glv_on_off_agree(eng):
+    """The GLV split (default) and the plain 255-bit path give the same point, also on skewed scalars."""
+    from halo2_b200 import lib as L
+    curve, c = "vesta", pasta.VESTA
+    n = 3000
+    pb = cref.gen_points(curve, SEED + 40, n)
+    lam = 0x2d33357cb532458ed3552a23a8554e5005270d29d19fc7d27b7fd22f0201b547
+    sets = [cref.gen_scalars(c.scalar, SEED + 41, n), cref.ints_to_bytes([lam] * n), cref.ints_to_bytes([c.r - lam + (i % 3) for i in range(n)]),
+            cref.ints_to_bytes([(1 << 128) - 1 + (i & 1) for i in range(n)])]
+    lib = L.init()
+    try:
+        for kb in sets:
+            want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+            for on in (1, 0):
+                L.check(lib.h2_set_glv(on))
+                for cbits in (0, 5, 12):
+                    L.check(lib.h2_set_window_bits(cbits))
+                    assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want, (on, cbits)
+    finally:
+        lib.h2_set_glv(1)
+        lib.h2_set_window_bits(0)
+
+
 def test_window_sweep_and_montgomery_inputs(eng):
     """BASELINE.json config 3's sweep dimension: every window size gives the same point;
     Montgomery-encoded inputs (pasta's in-memory form) give the same point too."""

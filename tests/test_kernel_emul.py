@@ -98,10 +98,10 @@ def test_emul_ntt(emu, field):
         assert (got == back).all()
 
 
-def _msm(emu, curve, kb, pb, c=0, mont=0, k0=0, gs=0):
+def _msm(emu, curve, kb, pb, c=0, mont=0, k0=0, gs=0, glv=False):
     # k0 = forced references per work item (T), gs = forced merge-level chunk
     out = np.zeros(96, dtype=np.uint8)
-    r = emu.emu_msm(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(kb)), cref._p(np.ascontiguousarray(pb)),
+    r = (emu.emu_msm_glv if glv else emu.emu_msm)(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(kb)), cref._p(np.ascontiguousarray(pb)),
                     ctypes.c_size_t(kb.shape[0]), c, mont, k0, gs, cref._p(out))
     assert r > 0, r
     return cref.bytes_to_affine(cref.jac_to_affine(curve, out))
@@ -116,7 +116,9 @@ def test_emul_msm(emu, curve):
         want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
         for cb, k0, gs in ((0, 0, 0), (1, 0, 0), (5, 3, 4), (11, 5, 8), (16, 0, 0), (2, 4, 4), (9, 2, 4), (3, 1, 4)):
             assert _msm(emu, curve, kb, pb, cb, 0, k0, gs) == want, (n, cb, k0, gs)
+            assert _msm(emu, curve, kb, pb, cb, 0, k0, gs, glv=True) == want, ("glv", n, cb, k0, gs)
         assert _msm(emu, curve, kb, pb, 0, 1, 0) == want   # Montgomery-encoded scalars
+        assert _msm(emu, curve, kb, pb, 0, 1, 0, glv=True) == want
     n, r = 200, c.r
     pb = cref.gen_points(curve, 9, n)
     cases = {"zeros": [0] * n, "ones": [1] * n, "equal": [pasta.gen_scalars(c.scalar, 1, 1)[0]] * n,
@@ -127,6 +129,7 @@ def test_emul_msm(emu, curve):
         want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
         for cb, k0, gs in ((0, 0, 0), (4, 3, 4), (16, 4, 8), (7, 2, 4), (6, 1, 4)):
             assert _msm(emu, curve, kb, pb, cb, 0, k0, gs) == want, (name, cb, k0, gs)
+            assert _msm(emu, curve, kb, pb, cb, 0, k0, gs, glv=True) == want, ("glv", name, cb, k0, gs)
     g = pasta.generator(c)
     pts = [cref.bytes_to_affine(x) for x in pb[:6]]
     pts2 = [g, g, (g[0], c.p - g[1]), None, pts[3], pts[3], pts[4], (pts[4][0], c.p - pts[4][1]), None, g] * 5
@@ -137,6 +140,7 @@ def test_emul_msm(emu, curve):
     want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb2))
     for cb, k0, gs in ((0, 0, 0), (3, 2, 4), (13, 0, 0)):
         assert _msm(emu, curve, kb, pb2, cb, 0, k0, gs) == want
+        assert _msm(emu, curve, kb, pb2, cb, 0, k0, gs, glv=True) == want
 
 
 def _msm_fixed(emu, curve, kb, pb, c=0, t=0, kn=0):
