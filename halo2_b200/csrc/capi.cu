@@ -641,7 +641,7 @@ static int ntt_run(int field, const fe *d_in, uint32_t in_log_n, fe *d_out, uint
         uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
         uint32_t smem = ntt_smem_bytes(sp[i], logc[i]);
         prof_begin(PROF_NTT_PASS, s);
-        LAUNCH(ntt_pass_kernel<P>, tiles, 256, smem, s, A);
+        LAUNCH(ntt_pass_kernel<P>, tiles, 128, smem, s, A);
         prof_end(s);
         s0 += sp[i];
     }

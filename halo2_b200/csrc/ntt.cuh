@@ -167,7 +167,7 @@ template <class P> struct TwiddleGen {
 };
 
 #if defined(__CUDACC__)
-template <class P> __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const NttPassArgs A) {
+template <class P> __global__ void __launch_bounds__(128, 7) ntt_pass_kernel(const NttPassArgs A) {
     extern __shared__ uint4 h2_ntt_smem[];
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     NttPass<P>::load_phase(A, tile, tid, nthr, h2_ntt_smem);
@@ -193,11 +193,11 @@ template <class P> __global__ void fe_scale_kernel(fe *a, uint64_t n, fe c) {
 
 // Host-side pass planning (shared with the emulation).  Returns the number of passes and fills
 // sp[] / logc[]; tiles hold at most 2^H2_NTT_TILE_LOG elements.
-#define H2_NTT_TILE_LOG 10
+#define H2_NTT_TILE_LOG 9     // 512-element tiles, 128 threads: ~7 CTAs/SM, 2^20 -> 2048 tiles = 2.0 waves of 148 x 7
 #define H2_NTT_MAX_SP 7
 inline int ntt_plan(uint32_t log_n, uint32_t sp[8], uint32_t logc[8]) {
     if (log_n == 0) return 0;
-    if (log_n <= H2_NTT_TILE_LOG) { sp[0] = log_n; logc[0] = 0; return 1; }
+    if (log_n <= H2_NTT_TILE_LOG + 1) { sp[0] = log_n; logc[0] = 0; return 1; }   // single CTA, up to 1024 elements
     int passes = (int)((log_n + H2_NTT_MAX_SP - 1) / H2_NTT_MAX_SP);
     uint32_t base = log_n / passes, rem = log_n % passes, s0 = 0;
     for (int i = 0; i < passes; i++) {
