@@ -323,7 +323,7 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s) {
 // fixed != 0: d_bases is a window table (stride points per window) built with window size c
 template <class P, class PS>
 static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, uint32_t fixed, uint64_t stride,
-                   jacobian *d_out, int out_canonical, cudaStream_t s, cudaEvent_t bases_ready = nullptr) {
+                   jacobian *d_out, int out_canonical, cudaStream_t s, cudaEvent_t bases_ready = nullptr, uint32_t sets = 1) {
     Context &X = g_ctx;
     if (n == 0) {   // empty sum = identity
         jacobian id;
@@ -337,11 +337,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     const uint32_t glv = (!fixed && X.glv_on && n < (1ull << 30)) ? 1u : 0u;
     if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
     if (c > 24) return fail("msm: window bits > 24");
-    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv);
+    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets);
     if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 40))) return 1;
     if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
     if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
-    if (scalars_mont && X.scal_canon.ensure(n * sizeof(fe))) return 1;
+    if (scalars_mont && X.scal_canon.ensure(n * p.sets * sizeof(fe))) return 1;
     const size_t small_words = 2 * (p.T + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
     if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(p.G * 4) || X.refs.ensure(p.max_refs * 4) ||
         X.size_hist.ensure(small_words * 4) || X.items.ensure(p.max_items * sizeof(uint2)) ||
@@ -383,9 +383,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     auto k_wsum = msm_wsum_kernel<P, PS>;
     auto k_final = msm_final_kernel<P, PS>;
     // K2/K3: counting sort of the (point, window) references by bucket
-    LAUNCH(k_hist, blocks_for(n, 256), 256, 0, s, p, M);
+    LAUNCH(k_hist, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
     if (exclusive_scan_u32(M.counts, p.G + 1, s)) return 1;
-    LAUNCH(k_scatter, blocks_for(n, 256), 256, 0, s, p, M);
+    LAUNCH(k_scatter, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
     // K4: work items (one per bucket, oversized buckets split), largest first
     LAUNCH(k_ihist, blocks_for(p.G, 256), 256, 0, s, p, M);
     LAUNCH(k_ibases, 1, 32, 0, s, p, M);
@@ -412,9 +412,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
 
 static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
                         jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0,
-                        cudaEvent_t bases_ready = nullptr) {
-    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready);
-    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready);
+                        cudaEvent_t bases_ready = nullptr, uint32_t sets = 1) {
+    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready, sets);
+    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready, sets);
     return fail("unknown curve id");
 }
 // window size for a precomputed table over n bases: few references per bucket (short serial chains)
@@ -550,6 +550,40 @@ extern "C" int h2_msm_registered(uint64_t handle, const void *scalars, size_t n,
     if (b->table.p)   // fixed-base path: window table, one shared bucket set
         return msm_host_common(b->curve, scalars, n, extra_scalar, b->table.as<affine>(), total, repr, out_xyz, b->c, 1, b->n);
     return msm_host_common(b->curve, scalars, n, extra_scalar, b->buf.as<affine>(), total, repr, out_xyz);
+}
+
+// `batch` scalar vectors of n entries (+ one extra scalar each, the blinds) against a registered base set with a
+// window table: one pass, one bucket set per vector.
+extern "C" int h2_msm_registered_batch(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                       void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(handle);
+    if (it == g_ctx.bases.end()) return fail("h2_msm_registered_batch: unknown handle");
+    BaseSet *b = it->second;
+    if (!b->table.p) return fail("h2_msm_registered_batch: the base set has no window table (register with H2_BASES_PRECOMPUTE)");
+    if (batch == 0) return 0;
+    if (batch > 64) return fail("h2_msm_registered_batch: batch > 64");
+    size_t total = n + (extra_scalars ? 1 : 0);
+    if (total > b->n) return fail("h2_msm_registered_batch: more scalars than registered bases");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.scal_in.ensure(batch * total * sizeof(fe)) || X.result.ensure(batch * sizeof(jacobian))) return 1;
+    fe *d = X.scal_in.as<fe>();
+    if (!extra_scalars) {
+        CU(cudaMemcpyAsync(d, scalars, batch * n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    } else {   // interleave: [poly_k (n) | blind_k] per vector
+        CU(cudaMemcpy2DAsync(d, total * sizeof(fe), scalars, n * sizeof(fe), n * sizeof(fe), batch, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpy2DAsync(d + n, total * sizeof(fe), extra_scalars, sizeof(fe), sizeof(fe), batch, cudaMemcpyHostToDevice, s));
+    }
+    int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, b->table.as<affine>(), total, b->c, X.result.as<jacobian>(),
+                          repr == H2_REPR_CANONICAL, s, 1, b->n, nullptr, (uint32_t)batch);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
 }
 
 extern "C" int h2_point_sum(int curve, const void *points_xyz, size_t g, int repr, void *out_xyz) {

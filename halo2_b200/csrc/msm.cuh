@@ -50,7 +50,9 @@ struct MsmPlan {
     uint32_t B;          // buckets per window = 2^(c-1)
     uint32_t fixed;      // 1: bases come from a precomputed table T[w][i] = 2^(c w) G_i (resident Params
                          //    generators): every window's digits share ONE bucket set, no window combine
-    uint32_t Wb;         // bucket sets = fixed ? 1 : W
+    uint32_t sets;       // fixed: independent MSMs over the same table in one pass (polynomial batch); scalars
+                         //    are laid out [set][n], results [set]
+    uint32_t Wb;         // bucket sets = fixed ? sets : W
     uint64_t stride;     // fixed: points per table window
     uint64_t G;          // total buckets = Wb * B
     uint64_t max_refs;   // n * W (x 2 with the GLV split)
@@ -87,15 +89,16 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
 }
 
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
-                          uint64_t stride = 0, uint32_t glv = 0) {
+                          uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1) {
     p.n = n; p.c = c;
     p.glv = fixed ? 0u : glv;
     // sub-scalars are < 2^129; one spare bit lets the top window absorb the signed-digit carry
     p.W = p.glv ? (130 + c - 1) / c : (256 + c - 1) / c;
     p.B = 1u << (c - 1);
-    p.fixed = fixed; p.Wb = fixed ? 1u : p.W; p.stride = stride;
+    p.sets = fixed && sets ? sets : 1u;
+    p.fixed = fixed; p.Wb = fixed ? p.sets : p.W; p.stride = stride;
     p.G = (uint64_t)p.Wb * p.B;
-    p.max_refs = n * p.W * (p.glv ? 2 : 1);
+    p.max_refs = n * p.W * (p.glv ? 2 : 1) * p.sets;
     // references per work item: 128 for big problems; shorter chains when there is little parallelism
     uint32_t T = 256;
     while (T > 32 && p.max_refs / T < 65536) T >>= 1;
@@ -155,7 +158,7 @@ struct MsmBuffers {
     xyzz *r0;                 // Wb * nb0 * 5      R0: per 8-entry block T, E, D_0..2
     xyzz *r1;                 // W * r1_rows       R1: per window T, E, D_0..
     xyzz *wsum;               // W                 2^(c w) S_w
-    jacobian *result;         // 1
+    jacobian *result;         // 1 (sets in the batched fixed-base mode)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -219,8 +222,8 @@ template <class P, class PS> struct Msm {
                 int32_t d = next_digit(part[e], w, p.c, carry);
                 if (d == 0) continue;
                 uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-                uint32_t g = (uint32_t)((uint64_t)(p.fixed ? 0 : w) * p.B + (mag - 1));
-                uint32_t ref = (uint32_t)i + (uint32_t)(p.fixed ? (uint64_t)w * p.stride : 0);
+                uint32_t g = (uint32_t)((uint64_t)(p.fixed ? i / p.n : w) * p.B + (mag - 1));
+                uint32_t ref = (uint32_t)(p.fixed ? i % p.n + (uint64_t)w * p.stride : i);
                 ref |= (e << 30) | ((((uint32_t)(d < 0)) ^ neg[e]) << 31);
                 f(g, ref);
             }
@@ -360,7 +363,7 @@ template <class P, class PS> struct Msm {
     static H2_HD xyzz wsum_item(const MsmPlan &p, const MsmBuffers &M, uint32_t w, uint32_t r) {
         if (r >= p.r1_rows) return xyzz_identity();
         xyzz v = ld_xyzz(M.r1 + (uint64_t)w * p.r1_rows + r);
-        uint32_t shift = p.c * w + (r >= 2 ? (r - 2) + p.l0 : 0);
+        uint32_t shift = (p.fixed ? 0 : p.c * w) + (r >= 2 ? (r - 2) + p.l0 : 0);   // fixed: w is a set index, not a window
         xyzz_shift<P>(v, shift);
         return v;
     }
@@ -405,10 +408,10 @@ template <class P, class PS> struct Msm {
             st_affine(table + (uint64_t)w * stride + i, a);
         }
     }
-    static H2_HD void finish(const MsmBuffers &M, const xyzz &total, uint32_t out_canonical) {
+    static H2_HD void finish(const MsmBuffers &M, const xyzz &total, uint32_t out_canonical, uint32_t set = 0) {
         jacobian j = xyzz_to_jacobian<P>(total);
         if (out_canonical) { j.x = fe_from_mont<P>(j.x); j.y = fe_from_mont<P>(j.y); j.z = fe_from_mont<P>(j.z); }
-        st_jacobian(M.result, j);
+        st_jacobian(M.result + set, j);
     }
 };
 
@@ -440,7 +443,8 @@ template <bool WANT> __device__ __forceinline__ uint32_t warp_inc(uint32_t *ctr,
 // every lane to execute every (half, window) step
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool in = i < p.n;
+    bool in = i < p.n * p.sets;
+    const uint64_t set = p.fixed && in ? i / p.n : 0;
     uint32_t part[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}}, sneg[2] = {0, 0};
     const uint32_t halves = p.glv ? 2u : 1u;
     if (in) Msm<P, PS>::load_parts(p, M, i, true, part, sneg);
@@ -450,14 +454,15 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_ker
             int32_t d = Msm<P, PS>::next_digit(part[e], w, p.c, carry);
             bool act = in && d != 0;
             uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            uint64_t g = (uint64_t)(p.fixed ? 0 : w) * p.B + (act ? mag - 1 : 0);
+            uint64_t g = (uint64_t)(p.fixed ? set : w) * p.B + (act ? mag - 1 : 0);
             warp_inc<false>(M.counts + g, act);
         }
     }
 }
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool in = i < p.n;
+    bool in = i < p.n * p.sets;
+    const uint64_t set = p.fixed && in ? i / p.n : 0, idx = p.fixed && in ? i % p.n : i;
     uint32_t part[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}}, sneg[2] = {0, 0};
     const uint32_t halves = p.glv ? 2u : 1u;
     if (in) Msm<P, PS>::load_parts(p, M, i, false, part, sneg);
@@ -473,8 +478,8 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_
                 int32_t d = w < p.W ? Msm<P, PS>::next_digit(part[e], w, p.c, carry) : 0;
                 act[k] = in && d != 0;
                 uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-                gid[k] = (uint32_t)((uint64_t)(w < p.W && !p.fixed ? w : 0) * p.B + (act[k] ? mag - 1 : 0));
-                ref[k] = ((uint32_t)i + (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0)) | (e << 30) |
+                gid[k] = (uint32_t)((uint64_t)(p.fixed ? set : (w < p.W ? w : 0)) * p.B + (act[k] ? mag - 1 : 0));
+                ref[k] = ((uint32_t)idx + (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0)) | (e << 30) |
                          ((((uint32_t)(d < 0)) ^ sneg[e]) << 31);
                 slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
             }
@@ -593,6 +598,10 @@ template <class P, class PS> __global__ void __launch_bounds__(32) msm_wsum_kern
 // Final: tree sum of the W window values
 template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_kernel(const MsmPlan p, const MsmBuffers M, uint32_t out_canonical) {
     __shared__ xyzz sh[64];
+    if (p.fixed) {   // one result per set (the sets are independent MSMs)
+        for (uint32_t set = threadIdx.x; set < p.sets; set += 64) Msm<P, PS>::finish(M, ld_xyzz(M.wsum + set), out_canonical, set);
+        return;
+    }
     xyzz v = xyzz_identity();
     for (uint32_t w = threadIdx.x; w < p.Wb; w += 64) { xyzz c = ld_xyzz(M.wsum + w); xyzz_add<P>(v, c); }
     block_tree_sum<P>(sh, v, 0, threadIdx.x, 64);

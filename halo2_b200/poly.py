@@ -71,6 +71,25 @@ class Params:
         """<poly, g_lagrange> + r * w   (commitment.rs:135-150)."""
         return self._commit(self._h_gl, poly, r)
 
+    def _commit_many(self, handle, polys, blinds: Sequence[Blind]) -> np.ndarray:
+        batch = len(polys)
+        assert batch == len(blinds) and batch >= 1
+        stack = np.ascontiguousarray(np.stack([_l.as_u8(p, 32) for p in polys]))
+        assert stack.shape[1] == self.n, "polynomial length != params.n"
+        bl = np.ascontiguousarray(np.stack([_l.fe_bytes(b.value) for b in blinds]))
+        out = np.zeros((batch, 96), dtype=np.uint8)
+        _l.check(_l.init().h2_msm_registered_batch(handle, _l.ptr(stack), ctypes.c_size_t(self.n), _l.ptr(bl), ctypes.c_size_t(batch),
+                                                    _l.REPR_CANONICAL, _l.ptr(out)))
+        return out
+
+    def commit_many(self, polys, blinds: Sequence[Blind]) -> np.ndarray:
+        """[commit(p, r) for p, r in zip(polys, blinds)] in one pass over the resident table -- the shape
+        of the prover's per-column loops (plonk/prover.rs:305-309, vanishing/prover.rs:102-106)."""
+        return self._commit_many(self._h_g, polys, blinds)
+
+    def commit_lagrange_many(self, polys, blinds: Sequence[Blind]) -> np.ndarray:
+        return self._commit_many(self._h_gl, polys, blinds)
+
     def close(self) -> None:
         lib = _l.load()
         for h in (self._h_g, self._h_gl):

@@ -71,6 +71,13 @@ int h2_bases_release(uint64_t handle);
 int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void *extra_scalar, int repr,
                       void *out_xyz);
 
+/* `batch` polynomials against the same resident table in ONE pass (bucket set = polynomial index):
+ * the advice-column commits (plonk/prover.rs:305-309), the h(X) pieces (vanishing/prover.rs:102-106), ...
+ * scalars: batch x n contiguous; extra_scalars: batch blinds or NULL; out_xyz: batch x 96 bytes.
+ * Needs a base set registered with H2_BASES_PRECOMPUTE. */
+int h2_msm_registered_batch(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                            void *out_xyz);
+
 /* Window size override for the sweep in BASELINE.json config 3 (0 = automatic). */
 int h2_set_window_bits(uint32_t c);
 /* GLV endomorphism split (k = k1 + k2 lambda, 129-bit halves; on by default) for MSMs without a

@@ -7,17 +7,21 @@ using namespace h2;
 
 template <class P, class PS>
 static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c, int scalars_mont,
-                   uint32_t force_t, uint32_t force_kn, int fixed, int glv, uint8_t *out_xyz) {
+                   uint32_t force_t, uint32_t force_kn, int fixed, int glv, uint8_t *out_xyz, uint32_t sets = 1) {
+    // batched fixed-base mode: `scalars` holds sets * n scalars, `out_xyz` receives sets * 96 bytes
+    const size_t ns = n * sets;
     MsmPlan p;
     if (!c) c = msm_default_window(n, glv ? 1u : 0u);
     if (fixed && c < 4) c = 4;      // table windows: W = ceil(256 / c) <= 64
-    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u);
+    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u, sets);
     if (p.acc_levels > H2_MSM_MAX_LEVELS) return -2;
-    std::vector<fe> sc(n ? n : 1), sc_canon(n ? n : 1);
+    std::vector<fe> sc(ns ? ns : 1), sc_canon(ns ? ns : 1);
     std::vector<affine> bs(n ? n : 1);
-    for (size_t i = 0; i < n; i++) {
+    for (size_t i = 0; i < ns; i++) {
         memcpy(sc[i].v, scalars + 32 * i, 32);
         if (scalars_mont) sc[i] = fe_to_mont<PS>(sc[i]);
+    }
+    for (size_t i = 0; i < n; i++) {
         affine a; memcpy(a.x.v, bases + 64 * i, 32); memcpy(a.y.v, bases + 64 * i + 32, 32);
         if (!affine_is_identity(a)) { a.x = fe_to_mont<P>(a.x); a.y = fe_to_mont<P>(a.y); }
         bs[i] = a;
@@ -37,26 +41,26 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     std::vector<uint32_t> pkey(pt, H2_MSM_INVALID_KEY), pstart(pt), pend(pt);
     std::vector<xyzz> ppt(pt), ra_t((size_t)p.W * p.m1), ra_e((size_t)p.W * p.m1), r0((size_t)p.W * p.nb0 * H2_R0_ROWS),
         r1((size_t)p.W * p.r1_rows), wsum(p.W);
-    jacobian result;
+    std::vector<jacobian> result(sets);
     MsmBuffers M;
-    std::vector<uint32_t> glv_parts((n ? n : 1) * 10);
+    std::vector<uint32_t> glv_parts((ns ? ns : 1) * 10);
     M.glv_parts = glv_parts.data();
     M.scalars = sc.data(); M.bases = fixed ? table.data() : bs.data(); M.bases_phi = phi.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
     M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data();
     M.size_hist = size_hist.data(); M.size_cursor = size_cursor.data(); M.flags = flags.data(); M.items = items.data();
     M.bucket_sum = bucket_sum.data(); M.pkey = pkey.data(); M.pstart = pstart.data(); M.pend = pend.data();
     M.ppt = ppt.data(); M.ra_t = ra_t.data(); M.ra_e = ra_e.data(); M.r0 = r0.data(); M.r1 = r1.data();
-    M.wsum = wsum.data(); M.result = &result;
+    M.wsum = wsum.data(); M.result = result.data();
     typedef Msm<P, PS> K;
     // K2 histogram
-    for (size_t i = 0; i < n; i++) {
+    for (size_t i = 0; i < ns; i++) {
         bool ok = K::for_each_digit(p, M, i, true, [&](uint32_t g, uint32_t) { counts[g]++; });
         if (!ok) return -3;
     }
     uint32_t run = 0;
     for (uint64_t g = 0; g <= p.G; g++) { uint32_t v = counts[g]; counts[g] = run; run += v; }
     // K3 scatter (reverse order to mimic the arbitrary order atomics give)
-    for (size_t ii = n; ii-- > 0;) {
+    for (size_t ii = ns; ii-- > 0;) {
         K::for_each_digit(p, M, ii, false, [&](uint32_t g, uint32_t ref) { refs[counts[g] + cursor[g]++] = ref; });
     }
     // work items
@@ -92,10 +96,15 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
             r1[(size_t)w * p.r1_rows + row] = v;
         }
     xyzz total = xyzz_identity();
-    for (uint32_t w = 0; w < p.Wb; w++)
-        for (uint32_t r = 0; r < 32; r++) { xyzz cc = K::wsum_item(p, M, w, r); xyzz_add<P>(total, cc); }
-    K::finish(M, total, 1);
-    memcpy(out_xyz, result.x.v, 32); memcpy(out_xyz + 32, result.y.v, 32); memcpy(out_xyz + 64, result.z.v, 32);
+    for (uint32_t w = 0; w < p.Wb; w++) {
+        xyzz ws = xyzz_identity();
+        for (uint32_t r = 0; r < 32; r++) { xyzz cc = K::wsum_item(p, M, w, r); xyzz_add<P>(ws, cc); }
+        if (p.fixed) K::finish(M, ws, 1, w); else xyzz_add<P>(total, ws);
+    }
+    if (!p.fixed) K::finish(M, total, 1);
+    for (uint32_t k = 0; k < sets; k++) {
+        memcpy(out_xyz + 96 * k, result[k].x.v, 32); memcpy(out_xyz + 96 * k + 32, result[k].y.v, 32); memcpy(out_xyz + 96 * k + 64, result[k].z.v, 32);
+    }
     return (int)p.acc_levels + (flags[0] ? 100 : 0);
 }
 
@@ -116,4 +125,10 @@ extern "C" int emu_msm_fixed(int curve, const uint8_t *scalars, const uint8_t *b
                              uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
     if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, 0, out_xyz);
     return run_msm<FqParams, FpParams>(scalars, bases, n, c, 0, force_t, force_kn, 1, 0, out_xyz);
+}
+// batched: `sets` scalar vectors of n entries against the same table
+extern "C" int emu_msm_fixed_batch(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t sets, uint32_t c,
+                                   uint8_t *out_xyz) {
+    if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, 0, 0, 0, 1, 0, out_xyz, sets);
+    return run_msm<FqParams, FpParams>(scalars, bases, n, c, 0, 0, 0, 1, 0, out_xyz, sets);
 }

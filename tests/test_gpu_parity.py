@@ -334,6 +334,24 @@ def test_resident_bases_with_window_table(eng, curve, k):
             L.check(lib.h2_bases_release(h))
 
 
+def test_commit_many_batched(eng):
+    """Batched commits (one pass, one bucket set per polynomial) == the individual commits == the oracle."""
+    curve, c, k = "vesta", pasta.VESTA, 12
+    n = 1 << k
+    g = cref.gen_points(curve, SEED + 31, n + 1)
+    params = eng.Params(curve, k, g[:n], g[:n], g[n:n + 1])
+    polys = [cref.gen_scalars(c.scalar, SEED + 32 + i, n) for i in range(4)]
+    polys[2] = cref.ints_to_bytes([i & 1 for i in range(n)])
+    polys[3] = np.zeros((n, 32), dtype=np.uint8)
+    blinds = [eng.Blind(pasta.gen_scalars(c.scalar, SEED + 40 + i, 1)[0]) for i in range(4)]
+    many = params.commit_many(polys, blinds)
+    for i in range(4):
+        single = params.commit(polys[i], blinds[i])
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([polys[i], cref.ints_to_bytes([blinds[i].value])]), g))
+        assert _affine(curve, many[i]) == want == _affine(curve, single), i
+    params.close()
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS

@@ -174,3 +174,21 @@ def test_emul_msm_fixed_base_table(emu, curve):
         want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
         for cb in (5, 16):
             assert _msm_fixed(emu, curve, kb, pb, cb) == want
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_msm_fixed_batch(emu, curve):
+    """Several scalar vectors against one table in a single pass (bucket set = vector index)."""
+    c = pasta.CURVES[curve]
+    n, sets = 70, 3
+    pb = cref.gen_points(curve, 77, n)
+    kbs = [cref.gen_scalars(c.scalar, 80 + k, n) for k in range(sets)]
+    kbs[1] = cref.ints_to_bytes([i & 1 for i in range(n)])
+    out = np.zeros(96 * sets, dtype=np.uint8)
+    for cb in (5, 13):
+        r = emu.emu_msm_fixed_batch(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(np.concatenate(kbs))), cref._p(pb),
+                                    ctypes.c_size_t(n), sets, cb, cref._p(out))
+        assert r > 0
+        for k in range(sets):
+            got = cref.bytes_to_affine(cref.jac_to_affine(curve, out[96 * k:96 * k + 96]))
+            assert got == cref.bytes_to_affine(cref.best_multiexp(curve, kbs[k], pb)), (cb, k)
