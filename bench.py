@@ -138,12 +138,12 @@ def run_reference(args, rank, world):
 # the IPA generator fold and the 2-term MSMs stay on the CPU in the real prover and are not timed.
 # =================================================================================================
 PROVER_K, PROVER_J = 14, 5
-GPU_MSM_MIN = 512   # the shim keeps smaller best_multiexp calls on the CPU
 
 
 def prover_schedule():
     """(kind, size) list.  commit_l = commit_lagrange, commit = commit, intt/coset/ext_intt = the three
-    EvaluationDomain transforms, msm = IPA round best_multiexp with that round's folded bases."""
+    EvaluationDomain transforms, ipa = the k-round loop of commitment::create_proof (poly/commitment/prover.rs:100-142:
+    2k best_multiexp over the folded generators, the inner products, the scalar folds and parallel_generator_collapse)."""
     sched = []
     sched += [("commit_l_many", 3)]                      # advice columns: one batched pass, plonk/prover.rs:305-309
     for _ in range(3):                                   # ... then per column, plonk/prover.rs:319-328
@@ -152,17 +152,23 @@ def prover_schedule():
     sched += [("commit", None)]                          # vanishing random poly, vanishing/prover.rs:53
     sched += [("ext_intt", None), ("commit_many", 4)]    # h(X) pieces: vanishing/prover.rs:88,102-106
     sched += [("commit", None), ("commit", None)]        # multiopen q', IPA s_poly
-    for j in range(PROVER_K):                            # IPA rounds, poly/commitment/prover.rs:107-108
-        half = 1 << (PROVER_K - 1 - j)
-        if half >= GPU_MSM_MIN:
-            sched += [("msm", half), ("msm", half)]
+    sched += [("ipa", PROVER_K)]                         # IPA rounds, poly/commitment/prover.rs:100-142
     return sched
+
+
+def ipa_inputs(cref):
+    k = PROVER_K
+    ch = cref.gen_scalars("fp", SEED + 90, k)
+    lr = cref.gen_scalars("fp", SEED + 91, k)
+    rr = cref.gen_scalars("fp", SEED + 92, k)
+    x3, z = cref.bytes_to_ints(cref.gen_scalars("fp", SEED + 93, 2))
+    return ch, lr, rr, x3, z
 
 
 def prover_replay_inputs(cref):
     n = 1 << PROVER_K
     gl = cref.gen_points("vesta", SEED + 50, n + 1)      # stand-in generators (hash_to_curve is out of scope)
-    g = cref.gen_points("vesta", SEED + 51, n + 1)
+    g = cref.gen_points("vesta", SEED + 51, n + 2)       # g || w || u
     g[n] = gl[n]                                         # same w
     polys = [cref.gen_scalars("fp", SEED + 60 + i, n) for i in range(4)]
     ext = cref.gen_scalars("fp", SEED + 70, n << 2)
@@ -174,17 +180,21 @@ def prover_replay_gpu(h2, cref, reps=3):
     n, k = 1 << PROVER_K, PROVER_K
     g, gl, polys, ext = prover_replay_inputs(cref)
     zeta = pow(5, (P_MOD - 1) // 3, P_MOD)
+    ch, lr, rr, x3, z = ipa_inputs(cref)
+    ch_i, lr_i, rr_i = cref.bytes_to_ints(ch), cref.bytes_to_ints(lr), cref.bytes_to_ints(rr)
     t0 = time.time()
-    params = h2.Params("vesta", k, g[:n], gl[:n], g[n:n + 1])          # uploads + window tables, once per Params
+    params = h2.Params("vesta", k, g[:n], gl[:n], g[n:n + 1], u=g[n + 1:n + 2])   # uploads + window tables, once per Params
     setup_s = time.time() - t0
     dom = h2.EvaluationDomain("fp", PROVER_J, k, zeta)
     blind = h2.Blind(7)
     sched = prover_schedule()
-    ipa_bases = {half: cref.gen_points("vesta", SEED + 80, half) for (kind, half) in sched if kind == "msm"}
+
+    by_kind = {}
 
     def run():
         for i, (kind, half) in enumerate(sched):
             poly = polys[i % 4]
+            tk = time.time()
             if kind == "commit_l_many":
                 params.commit_lagrange_many([polys[j % 4] for j in range(half)], [blind] * half)
             elif kind == "commit_many":
@@ -199,15 +209,17 @@ def prover_replay_gpu(h2, cref, reps=3):
                 dom.coeff_to_extended(poly)
             elif kind == "ext_intt":
                 dom.extended_to_coeff(ext)
-            else:
-                h2.best_multiexp(poly[:half], ipa_bases[half], "vesta")
+            else:   # the challenge callback stands in for the transcript (hash of 2 points per round, not timed in either arm)
+                params.ipa_rounds(poly, x3, z, lambda j, l_j, r_j: ch_i[j], lr_i, rr_i)
+            by_kind[kind] = by_kind.get(kind, 0.0) + (time.time() - tk)
     run()
+    by_kind.clear()
     t0 = time.time()
     for _ in range(reps):
         run()
     dt = (time.time() - t0) / reps
     params.close()
-    return dt, setup_s, sched
+    return dt, setup_s, sched, {k_: v * 1e3 / reps for k_, v in by_kind.items()}
 
 
 def prover_replay_cpu(cref, threads):
@@ -217,16 +229,18 @@ def prover_replay_cpu(cref, threads):
     zeta = pasta.zeta_candidates("fp")[0]
     d = pasta.EvaluationDomain("fp", PROVER_J, k, zeta)
     sched = prover_schedule()
-    ipa_bases = {half: cref.gen_points("vesta", SEED + 80, half) for (kind, half) in sched if kind == "msm"}
+    ch, lr, rr, x3, z = ipa_inputs(cref)
     blind = cref.ints_to_bytes([7])
-    t0 = time.time()
+    by_kind = {}
+    ipa_threads = threads
     for i, (kind, half) in enumerate(sched):
         poly = polys[i % 4]
+        tk = time.time()
         if kind in ("commit_l_many", "commit_many"):
             for j in range(half):
-                cref.best_multiexp("vesta", np.concatenate([polys[j % 4], blind]), gl if kind == "commit_l_many" else g, threads)
+                cref.best_multiexp("vesta", np.concatenate([polys[j % 4], blind]), gl if kind == "commit_l_many" else g[:n + 1], threads)
         elif kind in ("commit_l", "commit"):
-            cref.best_multiexp("vesta", np.concatenate([poly, blind]), gl if kind == "commit_l" else g, threads)
+            cref.best_multiexp("vesta", np.concatenate([poly, blind]), gl if kind == "commit_l" else g[:n + 1], threads)
         elif kind == "intt":
             cref.ifft("fp", poly, d.omega_inv, k, d.ifft_divisor, threads)
         elif kind == "coset":
@@ -234,8 +248,19 @@ def prover_replay_cpu(cref, threads):
         elif kind == "ext_intt":
             cref.extended_to_coeff("fp", ext, d.extended_k, d.extended_omega_inv, d.extended_ifft_divisor, zeta, n * (PROVER_J - 1), threads)
         else:
-            cref.best_multiexp("vesta", poly[:half], ipa_bases[half], threads)
-    return time.time() - t0
+            # parallelize() (arithmetic.rs:345-362) falls back to ONE chunk when len / threads < threads, which serialises
+            # parallel_generator_collapse on a many-core host; give the CPU arm its best thread count instead
+            best = None
+            for th in sorted({threads, min(threads, 64), min(threads, 32), min(threads, 16)}, reverse=True):
+                t1 = time.time()
+                cref.ipa_rounds("vesta", g, k, poly, x3, z, ch, lr, rr, th)
+                t1 = time.time() - t1
+                if best is None or t1 < best:
+                    best, ipa_threads = t1, th
+            tk = time.time() - best      # only the best run counts
+        by_kind[kind] = by_kind.get(kind, 0.0) + (time.time() - tk)
+    total = sum(by_kind.values())
+    return total, {k_: v * 1e3 for k_, v in by_kind.items()}, ipa_threads
 
 
 # =================================================================================================
@@ -472,18 +497,20 @@ def main():
                                                       "join-recursion; includes canonical<->Montgomery conversion)"}
             # ---- create_proof k=14: replay of the prover's hot-path calls (host API, copies included)
             import halo2_b200 as h2
-            gdt, setup_s, sched = prover_replay_gpu(h2, cref)
-            cdt = prover_replay_cpu(cref, threads)
+            gdt, setup_s, sched, by_kind = prover_replay_gpu(h2, cref)
+            cdt, cpu_by_kind, ipa_threads = prover_replay_cpu(cref, threads)
             kinds = {}
             for kind, cnt in sched:
                 kinds[kind] = kinds.get(kind, 0) + (cnt if kind.endswith("_many") else 1)
             extra["create_proof_k14_replay"] = {
                 "metric": "hot_path_ms_per_proof", "value": gdt * 1e3, "unit": "ms", "higher_is_better": False,
-                "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port"},
-                "params_setup_ms": setup_s * 1e3, "calls": kinds,
+                "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": cpu_by_kind,
+                                 "ipa_threads": ipa_threads},
+                "params_setup_ms": setup_s * 1e3, "calls": kinds, "gpu_ms_by_kind": by_kind,
                 "note": "replay of SURVEY.md Appendix C call schedule (benches/plonk.rs circuit, Vesta, k=14, ext_k=16) through the "
-                        "reference-facing host API; NOT the Rust prover: witness synthesis, h(X) evaluation, transcript, IPA generator "
-                        f"fold and best_multiexp calls below {GPU_MSM_MIN} terms run on the CPU in both arms and are not timed"}
+                        "reference-facing host API; NOT the Rust prover: witness synthesis, h(X) evaluation and the transcript run on the CPU "
+                        "in both arms and are not timed.  ipa = all k rounds of poly/commitment/prover.rs:100-142 (CPU arm: 2k "
+                        "best_multiexp + parallel_generator_collapse; GPU arm: fold-free rounds over the resident table)"}
 
         line = {
             "metric": "msm_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

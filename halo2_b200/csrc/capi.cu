@@ -12,6 +12,7 @@
 
 #include "../../include/halo2_b200.h"
 #include "msm.cuh"
+#include "ipa.cuh"
 #include "ntt.cuh"
 
 using namespace h2;
@@ -46,6 +47,8 @@ struct DevBuf {
 struct TwiddleEntry { int field; uint32_t log_n; uint8_t omega[32]; DevBuf buf; uint64_t stamp; };
 struct BaseSet { int curve; size_t n; DevBuf buf; DevBuf table; uint32_t c = 0, W = 0; };   // table: W x n window multiples
 
+struct IpaSession { uint64_t bases; uint32_t k, round; int folded; DevBuf p, b, s, scal, out; };
+
 struct Context {
     bool ready = false;
     int device = -1;
@@ -64,6 +67,8 @@ struct Context {
     std::vector<TwiddleEntry *> twiddles;
     uint64_t tw_stamp = 0;
     std::map<uint64_t, BaseSet *> bases;
+    std::map<uint64_t, IpaSession *> ipa;
+    std::vector<IpaSession *> ipa_pool;      // finished sessions keep their buffers for the next proof (no cudaMalloc per opening)
     uint64_t next_handle = 1;
 };
 static Context g_ctx;
@@ -153,6 +158,10 @@ extern "C" int h2_shutdown(void) {
     g_ctx.twiddles.clear();
     for (auto &kv : g_ctx.bases) { kv.second->buf.release(); kv.second->table.release(); delete kv.second; }
     g_ctx.bases.clear();
+    for (auto &kv : g_ctx.ipa) { IpaSession *q = kv.second; q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
+    g_ctx.ipa.clear();
+    for (IpaSession *q : g_ctx.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
+    g_ctx.ipa_pool.clear();
     cudaEventDestroy(g_ctx.ev_scalars_up); cudaEventDestroy(g_ctx.ev_bases_up);
     cudaStreamDestroy(g_ctx.copy_stream);
     cudaEventDestroy(g_ctx.last_use);
@@ -775,6 +784,134 @@ extern "C" int h2_ntt_clear_cache(void) {
 // ------------------------------------------------------------------------------------------------
 // utilities
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// IPA round loop (ipa.cuh): poly/commitment/prover.rs:100-142 with resident generators
+// ------------------------------------------------------------------------------------------------
+static void ipa_free(IpaSession *q) {   // back to the pool (the caller has synchronised the stream)
+    if (g_ctx.ipa_pool.size() < 2) { g_ctx.ipa_pool.push_back(q); return; }
+    q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q;
+}
+static IpaState ipa_state(IpaSession *q) {
+    IpaState S;
+    S.p = q->p.as<fe>(); S.b = q->b.as<fe>(); S.s = q->s.as<fe>(); S.scal = q->scal.as<fe>(); S.n = 1ull << q->k;
+    return S;
+}
+template <class PS> static int ipa_begin_impl(IpaSession *q, const void *p_prime, const void *x3, int repr, cudaStream_t s) {
+    Context &X = g_ctx;
+    const uint64_t n = 1ull << q->k;
+    if (q->p.ensure(n * sizeof(fe)) || q->b.ensure(n * sizeof(fe)) || q->s.ensure(n * sizeof(fe)) || q->scal.ensure(2 * (n + 2) * sizeof(fe)) ||
+        q->out.ensure(2 * sizeof(jacobian)) || X.pow2.ensure(64 * sizeof(fe)))
+        return 1;
+    CU(cudaMemcpyAsync(q->p.p, p_prime, n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    IpaState S = ipa_state(q);
+    LAUNCH(ipa_init_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, repr == H2_REPR_MONTGOMERY);
+    // b_t = x3^t (prover.rs:86-93) with the NTT twiddle generator
+    fe x = host_to_mont<PS>(x3, repr);
+    LAUNCH(twiddle_pow2_kernel<PS>, 1, 32, 0, s, X.pow2.as<fe>(), x, q->k + 1);
+    LAUNCH(twiddle_fill_kernel<PS>, blocks_for((n + 31) / 32, 128), 128, 0, s, S.b, X.pow2.as<fe>(), n);
+    return 0;
+}
+extern "C" int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_prime, const void *x3, int repr, uint64_t *session) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(bases_handle);
+    if (it == g_ctx.bases.end()) return fail("h2_ipa_begin: unknown bases handle");
+    BaseSet *b = it->second;
+    if (k == 0 || k > 28) return fail("h2_ipa_begin: k out of range");
+    if (b->n != (1ull << k) + 2) return fail("h2_ipa_begin: the base set must hold g[0..2^k) || w || u");
+    if (!b->table.p) return fail("h2_ipa_begin: the base set has no window table (register with H2_BASES_PRECOMPUTE)");
+    IpaSession *q;
+    if (!g_ctx.ipa_pool.empty()) { q = g_ctx.ipa_pool.back(); g_ctx.ipa_pool.pop_back(); }
+    else q = new IpaSession();
+    q->bases = bases_handle; q->k = k; q->round = 0; q->folded = 1;
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) { ipa_free(q); return 1; }   // pow2 is shared scratch
+    int rc = b->curve == H2_CURVE_PALLAS ? ipa_begin_impl<FqParams>(q, p_prime, x3, repr, s) : ipa_begin_impl<FpParams>(q, p_prime, x3, repr, s);
+    if (rc) { ipa_free(q); return 1; }
+    if (scratch_release(s)) { ipa_free(q); return 1; }
+    cudaError_t e = cudaStreamSynchronize(s);   // p_prime may be pageable host memory
+    if (e != cudaSuccess) { ipa_free(q); return fail(std::string("h2_ipa_begin: ") + cudaGetErrorString(e)); }
+    uint64_t h = g_ctx.next_handle++;
+    g_ctx.ipa[h] = q;
+    *session = h;
+    return 0;
+}
+template <class PS> static int ipa_round_impl(IpaSession *q, BaseSet *b, const void *z, const void *l_rand, const void *r_rand, int repr, cudaStream_t s) {
+    const uint64_t n = 1ull << q->k;
+    const uint32_t bit = q->k - 1 - q->round;
+    IpaState S = ipa_state(q);
+    LAUNCH(ipa_prep_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, bit);
+    LAUNCH(ipa_inner_kernel<PS>, 1, 512, 0, s, S, bit, host_to_mont<PS>(z, repr), host_to_mont<PS>(l_rand, repr), host_to_mont<PS>(r_rand, repr));
+    return msm_dispatch(b->curve, S.scal, 1, b->table.as<affine>(), n + 2, b->c, q->out.as<jacobian>(), repr == H2_REPR_CANONICAL, s, 1, b->n, nullptr, 2);
+}
+extern "C" int h2_ipa_round(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.ipa.find(session);
+    if (it == g_ctx.ipa.end()) return fail("h2_ipa_round: unknown session");
+    IpaSession *q = it->second;
+    auto ib = g_ctx.bases.find(q->bases);
+    if (ib == g_ctx.bases.end()) return fail("h2_ipa_round: the session's base set was released");
+    if (q->round >= q->k) return fail("h2_ipa_round: all k rounds are done");
+    if (!q->folded) return fail("h2_ipa_round: h2_ipa_fold must follow each round");
+    BaseSet *b = ib->second;
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) return 1;
+    int rc = b->curve == H2_CURVE_PALLAS ? ipa_round_impl<FqParams>(q, b, z, l_rand, r_rand, repr, s) : ipa_round_impl<FpParams>(q, b, z, l_rand, r_rand, repr, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_lr_xyz, q->out.p, 2 * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    q->folded = 0;
+    return 0;
+}
+extern "C" int h2_ipa_fold(uint64_t session, const void *u, const void *u_inv, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.ipa.find(session);
+    if (it == g_ctx.ipa.end()) return fail("h2_ipa_fold: unknown session");
+    IpaSession *q = it->second;
+    auto ib = g_ctx.bases.find(q->bases);
+    if (ib == g_ctx.bases.end()) return fail("h2_ipa_fold: the session's base set was released");
+    if (q->folded) return fail("h2_ipa_fold: no round to fold");
+    const uint64_t n = 1ull << q->k;
+    const uint32_t bit = q->k - 1 - q->round;
+    cudaStream_t s = g_ctx.stream;
+    IpaState S = ipa_state(q);
+    if (ib->second->curve == H2_CURVE_PALLAS) LAUNCH(ipa_fold_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, S, bit, host_to_mont<FqParams>(u, repr), host_to_mont<FqParams>(u_inv, repr));
+    else LAUNCH(ipa_fold_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, S, bit, host_to_mont<FpParams>(u, repr), host_to_mont<FpParams>(u_inv, repr));
+    q->round++; q->folded = 1;   // asynchronous: the next round (or finish) is ordered behind it on the stream
+    return 0;
+}
+extern "C" int h2_ipa_finish(uint64_t session, int repr, void *out_c_b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.ipa.find(session);
+    if (it == g_ctx.ipa.end()) return fail("h2_ipa_finish: unknown session");
+    IpaSession *q = it->second;
+    auto ib = g_ctx.bases.find(q->bases);
+    int rc = 0;
+    cudaStream_t s = g_ctx.stream;
+    if (out_c_b) {
+        if (ib == g_ctx.bases.end()) rc = fail("h2_ipa_finish: the session's base set was released");
+        else if (q->round != q->k || !q->folded) rc = fail("h2_ipa_finish: the k rounds are not complete");
+        else {
+            IpaState S = ipa_state(q);
+            fe *out = q->scal.as<fe>();
+            if (ib->second->curve == H2_CURVE_PALLAS) ipa_result_kernel<FqParams><<<1, 32, 0, s>>>(S, repr == H2_REPR_CANONICAL, out);
+            else ipa_result_kernel<FpParams><<<1, 32, 0, s>>>(S, repr == H2_REPR_CANONICAL, out);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t e = cudaMemcpyAsync(out_c_b, out, 2 * sizeof(fe), cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = fail(std::string("h2_ipa_finish: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && !rc) rc = fail(std::string("h2_ipa_finish: ") + cudaGetErrorString(e));
+    ipa_free(q);
+    g_ctx.ipa.erase(it);
+    return rc;
+}
+
 extern "C" int h2_dev_gen_points(int curve, uint64_t seed, uint64_t first, size_t n, void *d_out, void *stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;

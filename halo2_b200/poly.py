@@ -47,9 +47,11 @@ class Params:
         self._h_g = ctypes.c_uint64(0)
         self._h_gl = ctypes.c_uint64(0)
         cid = _l.CURVE_ID[curve]
-        both = np.concatenate([self.g, self.w])            # tmp_bases = g ++ [w]  (:126-127)
+        # tmp_bases = g ++ [w]  (:126-127); u rides along at index n + 1 for the IPA rounds (prover.rs:118-119)
+        both = np.concatenate([self.g, self.w] + ([] if self.u is None else [self.u]))
         flags = 1 if precompute else 0   # H2_BASES_PRECOMPUTE: window tables, fixed-base MSM
-        _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL,
+        self._has_table = bool(precompute)
+        _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(both.shape[0]), _l.REPR_CANONICAL,
                                           ctypes.c_uint32(window_bits), ctypes.c_uint32(flags), ctypes.byref(self._h_g)))
         both = np.concatenate([self.g_lagrange, self.w])   # g_lagrange ++ [w]     (:146-147)
         _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL,
@@ -89,6 +91,39 @@ class Params:
 
     def commit_lagrange_many(self, polys, blinds: Sequence[Blind]) -> np.ndarray:
         return self._commit_many(self._h_gl, polys, blinds)
+
+    def ipa_rounds(self, p_prime, x3: int, z: int, challenge, l_rand: Sequence[int], r_rand: Sequence[int]):
+        """The round loop of commitment::create_proof (poly/commitment/prover.rs:100-142) on the device.
+        `p_prime` (:80) is the blinded polynomial with P(x3) removed; `challenge(j, L_j, R_j) -> u_j` is the
+        caller's transcript (write L_j, R_j; squeeze u_j); l_rand / r_rand are the per-round blinds (:112-113).
+        Returns (L (k, 96), R (k, 96), c) -- c is what :147 writes to the transcript."""
+        if self.u is None or not self._has_table:
+            raise _l.H2Error("ipa_rounds needs Params(u=..., precompute=True)")
+        m = FIELDS[{"pallas": "fq", "vesta": "fp"}[self.curve]]
+        lib = _l.init()
+        pp = _l.as_u8(p_prime, 32)
+        assert pp.shape[0] == self.n and len(l_rand) == self.k and len(r_rand) == self.k
+        sess = ctypes.c_uint64(0)
+        _l.check(lib.h2_ipa_begin(self._h_g, ctypes.c_uint32(self.k), _l.ptr(pp), _l.ptr(_l.fe_bytes(x3 % m)), _l.REPR_CANONICAL,
+                                  ctypes.byref(sess)))
+        ls = np.zeros((self.k, 96), dtype=np.uint8)
+        rs = np.zeros((self.k, 96), dtype=np.uint8)
+        lr = np.zeros((2, 96), dtype=np.uint8)
+        zb = _l.fe_bytes(z % m)
+        try:
+            for j in range(self.k):
+                _l.check(lib.h2_ipa_round(sess, _l.ptr(zb), _l.ptr(_l.fe_bytes(l_rand[j] % m)), _l.ptr(_l.fe_bytes(r_rand[j] % m)),
+                                          _l.REPR_CANONICAL, _l.ptr(lr)))
+                ls[j], rs[j] = lr[0], lr[1]
+                u_j = int(challenge(j, ls[j], rs[j])) % m
+                _l.check(lib.h2_ipa_fold(sess, _l.ptr(_l.fe_bytes(u_j)), _l.ptr(_l.fe_bytes(pow(u_j, m - 2, m))), _l.REPR_CANONICAL))
+            cb = np.zeros((2, 32), dtype=np.uint8)
+            _l.check(lib.h2_ipa_finish(sess, _l.REPR_CANONICAL, _l.ptr(cb)))
+            sess.value = 0
+        finally:
+            if sess.value:
+                lib.h2_ipa_finish(sess, _l.REPR_CANONICAL, None)
+        return ls, rs, int.from_bytes(cb[0].tobytes(), "little")
 
     def close(self) -> None:
         lib = _l.load()

@@ -78,6 +78,29 @@ int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void
 int h2_msm_registered_batch(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
                             void *out_xyz);
 
+/* ---- IPA opening: the round loop of commitment::create_proof, poly/commitment/prover.rs:100-142 ----
+ * Replaces, per round j: the two best_multiexp calls over the folded generators (:107-108), the two
+ * compute_inner_product calls (:110-111), the [value z]U + [rand]W terms (:113-119), the folds of p' and b
+ * (:134-139) and parallel_generator_collapse (:140, :154-166).  The generators are never folded on the device:
+ * L_j and R_j are fixed-base MSMs over the resident table with the accumulated challenge products folded into
+ * the scalars (halo2_b200/csrc/ipa.cuh) -- same group elements, same affine encodings.
+ * The transcript (challenges) and the randomness stay with the caller:
+ *
+ *   h2_ipa_begin(h, k, p_prime, x3, repr, &s);           // p_prime: prover.rs:80, b = powers of x3: :86-93
+ *   for j in 0..k {
+ *       h2_ipa_round(s, z, l_rand_j, r_rand_j, repr, LR); // LR = L_j || R_j, 2 x 96 bytes (x, y, z), :107-119
+ *       ... write to_affine(L_j), to_affine(R_j) to the transcript, squeeze u_j ...
+ *       h2_ipa_fold(s, u_j, u_j_inv, repr);               // :134-140 (asynchronous)
+ *   }
+ *   h2_ipa_finish(s, repr, cb);                           // cb = c (= p_prime[0], :147) || b[0], 2 x 32 bytes
+ *
+ * `bases_handle` must be a set of 2^k + 2 points g[0..2^k) || w || u registered with H2_BASES_PRECOMPUTE
+ * (the same set serves commit(): w sits at index n).  h2_ipa_finish with out_c_b == NULL aborts a session. */
+int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_prime, const void *x3, int repr, uint64_t *session);
+int h2_ipa_round(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz);
+int h2_ipa_fold(uint64_t session, const void *u, const void *u_inv, int repr);
+int h2_ipa_finish(uint64_t session, int repr, void *out_c_b);
+
 /* Window size override for the sweep in BASELINE.json config 3 (0 = automatic). */
 int h2_set_window_bits(uint32_t c);
 /* GLV endomorphism split (k = k1 + k2 lambda, 129-bit halves; on by default) for MSMs without a

@@ -177,3 +177,15 @@ def bytes_to_affine(a: np.ndarray):
     x = int.from_bytes(b[:32], "little")
     y = int.from_bytes(b[32:], "little")
     return None if (x == 0 and y == 0) else (x, y)
+
+
+def ipa_rounds(curve: str, bases: np.ndarray, k: int, p_prime: np.ndarray, x3, z, challenges: np.ndarray, l_rand: np.ndarray,
+               r_rand: np.ndarray, threads: Optional[int] = None):
+    """poly/commitment/prover.rs:100-142 (see orc_ipa_rounds).  bases = g || w || u.  Returns (L (k,64), R (k,64), c int)."""
+    out_l = np.zeros((k, 64), dtype=np.uint8)
+    out_r = np.zeros((k, 64), dtype=np.uint8)
+    out_c = np.zeros(32, dtype=np.uint8)
+    lib().orc_ipa_rounds(CURVE_ID[curve], _p(np.ascontiguousarray(bases)), ctypes.c_uint32(k), _p(np.ascontiguousarray(p_prime)),
+                         _p(_fe(x3)), _p(_fe(z)), _p(np.ascontiguousarray(challenges)), _p(np.ascontiguousarray(l_rand)),
+                         _p(np.ascontiguousarray(r_rand)), threads or default_threads(), _p(out_l), _p(out_r), _p(out_c))
+    return out_l, out_r, int.from_bytes(out_c.tobytes(), "little")

@@ -320,6 +320,7 @@ static size_t window_bits(size_t n) {               /* arithmetic.rs:146-152 */
 
 /* scalars: n x 32 B canonical; bases: n x 64 B canonical affine; out: 64 B affine.
  * threads plays the role of rayon's current_num_threads(). */
+static void msm_core(const field_t *F, const uint8_t *scalars, const aff *pts, size_t n, int threads, jac *out);
 int orc_best_multiexp(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, int threads,
                       uint8_t *out_xy) {
     ensure_init();
@@ -327,6 +328,14 @@ int orc_best_multiexp(int curve, const uint8_t *scalars, const uint8_t *bases, s
     const field_t *F = base_field(curve);
     aff *pts = (aff *)malloc(sizeof(aff) * (n ? n : 1));
     for (size_t i = 0; i < n; i++) aff_from_bytes(F, &pts[i], bases + 64 * i);
+    jac total;
+    msm_core(F, scalars, pts, n, threads, &total);
+    aff r; jac_to_aff(F, &r, &total); aff_to_bytes(F, out_xy, &r);
+    free(pts);
+    return 0;
+}
+/* best_multiexp proper, arithmetic.rs:143-180, on decoded bases */
+static void msm_core(const field_t *F, const uint8_t *scalars, const aff *pts, size_t n, int threads, jac *out) {
     size_t c = window_bits(n), windows = 256 / c + 1;
     jac total; jac_identity(F, &total);
     if (n > (size_t)threads) {
@@ -349,9 +358,7 @@ int orc_best_multiexp(int curve, const uint8_t *scalars, const uint8_t *bases, s
         }
         free(buckets);
     }
-    aff r; jac_to_aff(F, &r, &total); aff_to_bytes(F, out_xy, &r);
-    free(pts);
-    return 0;
+    *out = total;
 }
 
 /* naive sum_i k_i * P_i, the other side of test_multiexp (arithmetic.rs:440-458) */
@@ -603,5 +610,92 @@ int orc_gen_points(int curve, uint64_t seed, size_t n, uint8_t *out) {
         aff_to_bytes(F, out + 64 * i, &r);
     }
     free(pts); free(pre);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- IPA round loop
+ * poly/commitment/prover.rs:100-142 with the transcript factored out (challenges and randomness are
+ * inputs).  bases: g[0..n) || w || u (canonical affine).  Outputs: L_j, R_j affine (k x 64 B each), c (32 B). */
+typedef struct { const field_t *F; aff *lo; const aff *hi; size_t len; const uint8_t *u; } collapse_task;
+static void *collapse_worker(void *arg) {              /* prover.rs:158-165: one parallelize chunk */
+    collapse_task *T = (collapse_task *)arg;
+    const field_t *F = T->F;
+    size_t len = T->len;
+    jac *tmp = (jac *)malloc(sizeof(jac) * (len ? len : 1));
+    fe *pre = (fe *)malloc(sizeof(fe) * (len ? len : 1));
+    for (size_t i = 0; i < len; i++) {
+        jac t; scalar_mul_bytes(F, &t, T->u, &T->hi[i]);
+        jac_add_mixed(F, &tmp[i], &t, &T->lo[i]);
+    }
+    /* batch_normalize: Montgomery's trick over the non-identity z's */
+    fe acc = F->r;
+    for (size_t i = 0; i < len; i++) { pre[i] = acc; if (!jac_is_id(&tmp[i])) fe_mul(F, &acc, &acc, &tmp[i].z); }
+    fe inv; fe_inv(F, &inv, &acc);
+    for (size_t i = len; i-- > 0;) {
+        if (jac_is_id(&tmp[i])) { memset(&T->lo[i], 0, sizeof(aff)); T->lo[i].inf = 1; continue; }
+        fe zi, zi2; fe_mul(F, &zi, &inv, &pre[i]); fe_mul(F, &inv, &inv, &tmp[i].z);
+        fe_sqr(F, &zi2, &zi);
+        fe_mul(F, &T->lo[i].x, &tmp[i].x, &zi2); fe_mul(F, &zi2, &zi2, &zi); fe_mul(F, &T->lo[i].y, &tmp[i].y, &zi2);
+        T->lo[i].inf = 0;
+    }
+    free(tmp); free(pre);
+    return NULL;
+}
+static void generator_collapse(const field_t *F, aff *g, size_t len, const uint8_t *u, int threads) {
+    size_t half = len / 2, chunk = half / (size_t)threads;
+    if (chunk < (size_t)threads) chunk = half;          /* arithmetic.rs:347-351 */
+    size_t nchunks = chunk ? (half + chunk - 1) / chunk : 0;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (nchunks ? nchunks : 1));
+    collapse_task *ts = (collapse_task *)malloc(sizeof(collapse_task) * (nchunks ? nchunks : 1));
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t start = c * chunk, l = (start + chunk <= half) ? chunk : half - start;
+        ts[c] = (collapse_task){F, g + start, g + half + start, l, u};
+        if (c + 1 < nchunks) pthread_create(&th[c], NULL, collapse_worker, &ts[c]); else collapse_worker(&ts[c]);
+    }
+    for (size_t c = 0; c + 1 < nchunks; c++) pthread_join(th[c], NULL);
+    free(th); free(ts);
+}
+int orc_ipa_rounds(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z,
+                   const uint8_t *challenges, const uint8_t *l_rand, const uint8_t *r_rand, int threads,
+                   uint8_t *out_l_xy, uint8_t *out_r_xy, uint8_t *out_c) {
+    ensure_init();
+    if (threads < 1) threads = 1;
+    const field_t *F = base_field(curve), *S = scalar_field(curve);
+    size_t n = (size_t)1 << k;
+    aff *g = (aff *)malloc(sizeof(aff) * n), wu[2];
+    for (size_t i = 0; i < n; i++) aff_from_bytes(F, &g[i], bases + 64 * i);
+    aff_from_bytes(F, &wu[1], bases + 64 * n);           /* [u, w] order of prover.rs:118 */
+    aff_from_bytes(F, &wu[0], bases + 64 * (n + 1));
+    fe *p = load_vec(S, p_prime, n, n), *b = (fe *)malloc(sizeof(fe) * n);
+    fe x, zz; fe_from_bytes(S, &x, x3); fe_from_bytes(S, &zz, z);
+    fe cur = S->r;
+    for (size_t i = 0; i < n; i++) { b[i] = cur; fe_mul(S, &cur, &cur, &x); }      /* :86-93 */
+    uint8_t *sc = (uint8_t *)malloc(32 * n);
+    for (uint32_t j = 0; j < k; j++) {
+        size_t half = (size_t)1 << (k - j - 1);
+        jac lj, rj, t;
+        store_vec(S, sc, p + half, half); msm_core(F, sc, g, half, threads, &lj);            /* :107 */
+        store_vec(S, sc, p, half); msm_core(F, sc, g + half, half, threads, &rj);            /* :108 */
+        fe vl, vr, m; memset(&vl, 0, sizeof vl); memset(&vr, 0, sizeof vr);
+        for (size_t i = 0; i < half; i++) {                                                  /* :110-111 */
+            fe_mul(S, &m, &p[i + half], &b[i]); fe_add(S, &vl, &vl, &m);
+            fe_mul(S, &m, &p[i], &b[i + half]); fe_add(S, &vr, &vr, &m);
+        }
+        uint8_t two[64];
+        fe_mul(S, &m, &vl, &zz); fe_to_bytes(S, two, &m); memcpy(two + 32, l_rand + 32 * j, 32);
+        msm_core(F, two, wu, 2, threads, &t); jac_add(F, &lj, &lj, &t);                      /* :118 */
+        fe_mul(S, &m, &vr, &zz); fe_to_bytes(S, two, &m); memcpy(two + 32, r_rand + 32 * j, 32);
+        msm_core(F, two, wu, 2, threads, &t); jac_add(F, &rj, &rj, &t);                      /* :119 */
+        aff a; jac_to_aff(F, &a, &lj); aff_to_bytes(F, out_l_xy + 64 * j, &a);
+        jac_to_aff(F, &a, &rj); aff_to_bytes(F, out_r_xy + 64 * j, &a);
+        fe u, ui; fe_from_bytes(S, &u, challenges + 32 * j); fe_inv(S, &ui, &u);
+        for (size_t i = 0; i < half; i++) {                                                  /* :134-137 */
+            fe_mul(S, &m, &p[i + half], &ui); fe_add(S, &p[i], &p[i], &m);
+            fe_mul(S, &m, &b[i + half], &u); fe_add(S, &b[i], &b[i], &m);
+        }
+        generator_collapse(F, g, 2 * half, challenges + 32 * j, threads);                    /* :140 */
+    }
+    fe_to_bytes(S, out_c, &p[0]);
+    free(g); free(p); free(b); free(sc);
     return 0;
 }

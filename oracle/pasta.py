@@ -658,3 +658,61 @@ def affine_from_bytes(b: bytes) -> Affine:
     if x == 0 and y == 0:
         return None
     return (x, y)
+
+
+# --------------------------------------------------------------------------------------
+# IPA opening proof -- poly/commitment/prover.rs:27-152, with the transcript factored out:
+# the Fiat-Shamir challenges (xi, z, u_j) and the prover's randomness are INPUTS, the points
+# and scalars the prover would write to the transcript are OUTPUTS.  (The Blake2b transcript
+# itself, transcript.rs, is out of scope -- SURVEY.md section 2.)
+# --------------------------------------------------------------------------------------
+def compute_inner_product(m: int, a: Sequence[int], b: Sequence[int]) -> int:
+    """arithmetic.rs:308-319."""
+    assert len(a) == len(b)
+    return sum(x * y for x, y in zip(a, b)) % m
+
+
+def parallel_generator_collapse(c: Curve, g: List[Affine], challenge: int) -> List[Affine]:
+    """poly/commitment/prover.rs:154-166: g_lo[i] + [challenge] g_hi[i], batch-normalised."""
+    half = len(g) // 2
+    tmp = [jac_add(c, to_jac(g[i]), scalar_mul(c, challenge, g[i + half])) for i in range(half)]
+    return batch_normalize(c, tmp)
+
+
+def ipa_rounds(c: Curve, g: Sequence[Affine], w: Affine, u: Affine, p_prime: Sequence[int], x3: int, z: int,
+               challenges: Sequence[int], l_rand: Sequence[int], r_rand: Sequence[int]):
+    """The round loop of commitment::create_proof (prover.rs:100-142) for a given p_prime (prover.rs:80),
+    evaluation point x3, challenge z and per-round challenges u_j / randomness.  Returns
+    ([L_j affine], [R_j affine], c = final p_prime[0], sum_j (l_rand_j / u_j + r_rand_j u_j))."""
+    r = c.r
+    n = len(g)
+    k = n.bit_length() - 1
+    assert n == 1 << k and len(p_prime) == n and len(challenges) == k
+    p_prime = [x % r for x in p_prime]
+    b = [1] * n
+    for i in range(1, n):
+        b[i] = b[i - 1] * x3 % r
+    g_prime = list(g)
+    ls, rs = [], []
+    f_delta = 0
+    for j in range(k):
+        half = 1 << (k - j - 1)
+        l_j = best_multiexp(c, p_prime[half:], g_prime[:half])
+        r_j = best_multiexp(c, p_prime[:half], g_prime[half:])
+        value_l = compute_inner_product(r, p_prime[half:], b[:half])
+        value_r = compute_inner_product(r, p_prime[:half], b[half:])
+        l_j = jac_add(c, l_j, best_multiexp(c, [value_l * z % r, l_rand[j]], [u, w]))
+        r_j = jac_add(c, r_j, best_multiexp(c, [value_r * z % r, r_rand[j]], [u, w]))
+        ls.append(to_affine(c, l_j))
+        rs.append(to_affine(c, r_j))
+        u_j = challenges[j] % r
+        u_inv = inv(u_j, r)
+        for i in range(half):
+            p_prime[i] = (p_prime[i] + p_prime[i + half] * u_inv) % r
+            b[i] = (b[i] + b[i + half] * u_j) % r
+        p_prime = p_prime[:half]
+        b = b[:half]
+        g_prime = parallel_generator_collapse(c, g_prime, u_j)
+        f_delta = (f_delta + l_rand[j] * u_inv + r_rand[j] * u_j) % r
+    assert len(p_prime) == 1
+    return ls, rs, p_prime[0], f_delta

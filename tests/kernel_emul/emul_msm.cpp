@@ -132,3 +132,42 @@ extern "C" int emu_msm_fixed_batch(int curve, const uint8_t *scalars, const uint
     if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, 0, 0, 0, 1, 0, out_xyz, sets);
     return run_msm<FqParams, FpParams>(scalars, bases, n, c, 0, 0, 0, 1, 0, out_xyz, sets);
 }
+
+// ---- IPA round loop (ipa.cuh bodies + the 2-set fixed-base MSM above) ------------------------------
+#include "ipa.cuh"
+template <class P, class PS>
+static int run_ipa(const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z, const uint8_t *chal,
+                   const uint8_t *chal_inv, const uint8_t *l_rand, const uint8_t *r_rand, uint32_t c, uint8_t *out_l, uint8_t *out_r, uint8_t *out_c) {
+    const uint64_t n = 1ull << k;
+    auto rd = [](const uint8_t *b) { fe x; memcpy(x.v, b, 32); return fe_to_mont<PS>(x); };
+    std::vector<fe> p(n), b(n), s(n), scal(2 * (n + 2));
+    for (uint64_t i = 0; i < n; i++) memcpy(p[i].v, p_prime + 32 * i, 32);
+    IpaState S; S.p = p.data(); S.b = b.data(); S.s = s.data(); S.scal = scal.data(); S.n = n;
+    for (uint64_t t = 0; t < n; t++) Ipa<PS>::init_body(S, 0, t);
+    fe x = rd(x3), cur = fe_one<PS>();
+    for (uint64_t t = 0; t < n; t++) { b[t] = cur; cur = fe_mul<PS>(cur, x); }
+    fe zz = rd(z);
+    std::vector<uint8_t> sc_bytes(2 * (n + 2) * 32), lr(2 * 96);
+    for (uint32_t j = 0; j < k; j++) {
+        const uint32_t bit = k - 1 - j;
+        for (uint64_t t = 0; t < n; t++) Ipa<PS>::prep_body(S, bit, t);
+        fe vl = fe_zero(), vr = fe_zero();
+        const uint32_t nthr = 7;
+        for (uint32_t tid = 0; tid < nthr; tid++) { fe a, bb; Ipa<PS>::inner_partial(S, bit, tid, nthr, a, bb); vl = fe_add<PS>(vl, a); vr = fe_add<PS>(vr, bb); }
+        Ipa<PS>::inner_finish(S, vl, vr, zz, rd(l_rand + 32 * j), rd(r_rand + 32 * j));
+        for (uint64_t i = 0; i < 2 * (n + 2); i++) { fe v = fe_from_mont<PS>(scal[i]); memcpy(&sc_bytes[32 * i], v.v, 32); }
+        int rc = run_msm<P, PS>(sc_bytes.data(), bases, n + 2, c, 0, 0, 0, 1, 0, lr.data(), 2);
+        if (rc < 0) return rc;
+        memcpy(out_l + 96 * j, lr.data(), 96); memcpy(out_r + 96 * j, lr.data() + 96, 96);
+        fe u = rd(chal + 32 * j), ui = rd(chal_inv + 32 * j);
+        for (uint64_t t = 0; t < n; t++) Ipa<PS>::fold_body(S, bit, u, ui, t);
+    }
+    fe cc = fe_from_mont<PS>(p[0]);
+    memcpy(out_c, cc.v, 32);
+    return 0;
+}
+extern "C" int emu_ipa(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z, const uint8_t *chal,
+                       const uint8_t *chal_inv, const uint8_t *l_rand, const uint8_t *r_rand, uint32_t c, uint8_t *out_l, uint8_t *out_r, uint8_t *out_c) {
+    if (curve == 0) return run_ipa<FpParams, FqParams>(bases, k, p_prime, x3, z, chal, chal_inv, l_rand, r_rand, c, out_l, out_r, out_c);
+    return run_ipa<FqParams, FpParams>(bases, k, p_prime, x3, z, chal, chal_inv, l_rand, r_rand, c, out_l, out_r, out_c);
+}

@@ -352,6 +352,65 @@ def test_commit_many_batched(eng):
     params.close()
 
 
+def test_ipa_rounds(eng):
+    """The device IPA round loop (fold-free, resident generators) == the reference loop restated in the oracle
+    (poly/commitment/prover.rs:100-142): every L_j, R_j and the final c, on both curves; commit() keeps working
+    on the same base set (w at index n, u at n + 1)."""
+    for curve, k in (("vesta", 10), ("pallas", 7), ("vesta", 1)):
+        c = pasta.CURVES[curve]
+        n, r = 1 << k, c.r
+        bases = cref.gen_points(curve, SEED + 200 + k, n + 2)
+        params = eng.Params(curve, k, bases[:n], bases[:n], bases[n:n + 1], u=bases[n + 1:n + 2])
+        pp = cref.gen_scalars(c.scalar, SEED + 210 + k, n)
+        ch = pasta.gen_scalars(c.scalar, SEED + 220 + k, k)
+        lr = pasta.gen_scalars(c.scalar, SEED + 230 + k, k)
+        rr = pasta.gen_scalars(c.scalar, SEED + 240 + k, k)
+        x3, z = pasta.gen_scalars(c.scalar, SEED + 250 + k, 2)
+        want_l, want_r, want_c = cref.ipa_rounds(curve, bases, k, pp, x3, z, cref.ints_to_bytes(ch), cref.ints_to_bytes(lr),
+                                                 cref.ints_to_bytes(rr))
+        seen = []
+        def challenge(j, l_j, r_j):
+            seen.append((l_j.copy(), r_j.copy()))
+            return ch[j]
+        got_l, got_r, got_c = params.ipa_rounds(pp, x3, z, challenge, lr, rr)
+        assert got_c == want_c
+        for j in range(k):
+            assert cref.jac_to_affine(curve, got_l[j]).tobytes() == want_l[j].tobytes(), (curve, k, j)
+            assert cref.jac_to_affine(curve, got_r[j]).tobytes() == want_r[j].tobytes(), (curve, k, j)
+        assert len(seen) == k
+        blind = eng.Blind(lr[0])
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([pp, cref.ints_to_bytes([blind.value])]), bases[:n + 1]))
+        assert _affine(curve, params.commit(pp, blind)) == want
+        params.close()
+
+
+def test_ipa_errors(eng):
+    """Misuse fails loudly: no u / no table, fold without round, round without fold."""
+    import ctypes
+    from halo2_b200 import lib as L
+    curve, k = "vesta", 4
+    n = 1 << k
+    bases = cref.gen_points(curve, SEED + 260, n + 2)
+    params = eng.Params(curve, k, bases[:n], bases[:n], bases[n:n + 1])
+    with pytest.raises(L.H2Error):
+        params.ipa_rounds(np.zeros((n, 32), dtype=np.uint8), 1, 1, lambda j, a, b: 1, [1] * k, [1] * k)
+    params.close()
+    params = eng.Params(curve, k, bases[:n], bases[:n], bases[n:n + 1], u=bases[n + 1:n + 2])
+    lib = L.init()
+    sess = ctypes.c_uint64(0)
+    one = L.fe_bytes(1)
+    L.check(lib.h2_ipa_begin(params._h_g, ctypes.c_uint32(k), L.ptr(np.zeros((n, 32), dtype=np.uint8)), L.ptr(one), L.REPR_CANONICAL, ctypes.byref(sess)))
+    assert lib.h2_ipa_fold(sess, L.ptr(one), L.ptr(one), L.REPR_CANONICAL) != 0
+    out = np.zeros((2, 96), dtype=np.uint8)
+    L.check(lib.h2_ipa_round(sess, L.ptr(one), L.ptr(one), L.ptr(one), L.REPR_CANONICAL, L.ptr(out)))
+    assert lib.h2_ipa_round(sess, L.ptr(one), L.ptr(one), L.ptr(one), L.REPR_CANONICAL, L.ptr(out)) != 0
+    cb = np.zeros((2, 32), dtype=np.uint8)
+    assert lib.h2_ipa_finish(sess, L.REPR_CANONICAL, L.ptr(cb)) != 0          # rounds incomplete: error, session freed
+    assert lib.h2_ipa_finish(sess, L.REPR_CANONICAL, None) != 0               # already gone
+    assert lib.h2_ipa_begin(params._h_gl, ctypes.c_uint32(k), L.ptr(np.zeros((n, 32), dtype=np.uint8)), L.ptr(one), L.REPR_CANONICAL, ctypes.byref(sess)) != 0
+    params.close()
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS

@@ -192,3 +192,31 @@ def test_emul_msm_fixed_batch(emu, curve):
         for k in range(sets):
             got = cref.bytes_to_affine(cref.jac_to_affine(curve, out[96 * k:96 * k + 96]))
             assert got == cref.bytes_to_affine(cref.best_multiexp(curve, kbs[k], pb)), (cb, k)
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_ipa_rounds(emu, curve):
+    """The fold-free IPA round loop (ipa.cuh: resident generators, challenge products folded into the scalars,
+    L_j / R_j as a 2-set fixed-base MSM) yields the reference loop's L_j, R_j and c (prover.rs:100-142)."""
+    c = pasta.CURVES[curve]
+    r = c.r
+    for k, cb in ((1, 5), (4, 6), (6, 9)):
+        n = 1 << k
+        bases = cref.gen_points(curve, 300 + k, n + 2)
+        pp = cref.gen_scalars(c.scalar, 310 + k, n)
+        ch = pasta.gen_scalars(c.scalar, 320 + k, k)
+        lr = cref.gen_scalars(c.scalar, 330 + k, k)
+        rr = cref.gen_scalars(c.scalar, 340 + k, k)
+        x3, z = pasta.gen_scalars(c.scalar, 350 + k, 2)
+        want_l, want_r, want_c = cref.ipa_rounds(curve, bases, k, pp, x3, z, cref.ints_to_bytes(ch), lr, rr, threads=2)
+        out_l = np.zeros((k, 96), dtype=np.uint8)
+        out_r = np.zeros((k, 96), dtype=np.uint8)
+        out_c = np.zeros(32, dtype=np.uint8)
+        rc = emu.emu_ipa(cref.CURVE_ID[curve], cref._p(bases), k, cref._p(pp), cref._p(cref._fe(x3)), cref._p(cref._fe(z)),
+                         cref._p(cref.ints_to_bytes(ch)), cref._p(cref.ints_to_bytes([pow(u, r - 2, r) for u in ch])),
+                         cref._p(lr), cref._p(rr), cb, cref._p(out_l), cref._p(out_r), cref._p(out_c))
+        assert rc == 0
+        assert int.from_bytes(out_c.tobytes(), "little") == want_c
+        for j in range(k):
+            assert cref.jac_to_affine(curve, out_l[j]).tobytes() == want_l[j].tobytes(), (k, j)
+            assert cref.jac_to_affine(curve, out_r[j]).tobytes() == want_r[j].tobytes(), (k, j)
