@@ -27,7 +27,16 @@ extern "C" {
     pub fn h2_msm(curve: c_int, scalars: *const c_void, bases_xy: *const c_void, n: usize, repr: c_int,
                   out_xyz: *mut c_void) -> c_int;
     pub fn h2_bases_register(curve: c_int, bases_xy: *const c_void, n: usize, repr: c_int, handle: *mut u64) -> c_int;
+    pub fn h2_bases_register_ex(curve: c_int, bases_xy: *const c_void, n: usize, repr: c_int, window_bits: u32, flags: u32,
+                                handle: *mut u64) -> c_int;
     pub fn h2_bases_release(handle: u64) -> c_int;
+    pub fn h2_msm_registered_batch(handle: u64, scalars: *const c_void, n: usize, extra_scalars: *const c_void, batch: usize,
+                                   repr: c_int, out_xyz: *mut c_void) -> c_int;
+    pub fn h2_ipa_begin(bases_handle: u64, k: u32, p_prime: *const c_void, x3: *const c_void, repr: c_int, session: *mut u64) -> c_int;
+    pub fn h2_ipa_round(session: u64, z: *const c_void, l_rand: *const c_void, r_rand: *const c_void, repr: c_int,
+                        out_lr_xyz: *mut c_void) -> c_int;
+    pub fn h2_ipa_fold(session: u64, u: *const c_void, u_inv: *const c_void, repr: c_int) -> c_int;
+    pub fn h2_ipa_finish(session: u64, repr: c_int, out_c_b: *mut c_void) -> c_int;
     pub fn h2_msm_registered(handle: u64, scalars: *const c_void, n: usize, extra_scalar: *const c_void,
                              repr: c_int, out_xyz: *mut c_void) -> c_int;
     pub fn h2_ntt(field: c_int, a: *mut c_void, omega: *const c_void, log_n: u32, repr: c_int) -> c_int;
@@ -131,11 +140,56 @@ impl<C: B200Curve> ResidentBases<C>
 where
     C::Base: PrimeField<Repr = [u8; 32]>,
 {
+    /// `bases` = g ++ [w] (commit only) or g ++ [w, u] (commit + IPA rounds).  The window table
+    /// (H2_BASES_PRECOMPUTE = 1) makes every later MSM against this set a fixed-base one.
     pub fn new(bases: &[C]) -> Self {
         let b = bases_to_bytes(bases);
         let mut handle = 0u64;
-        check(unsafe { h2_bases_register(C::CURVE_ID, b.as_ptr() as *const c_void, bases.len(), REPR_CANONICAL, &mut handle) });
+        check(unsafe { h2_bases_register_ex(C::CURVE_ID, b.as_ptr() as *const c_void, bases.len(), REPR_CANONICAL, 0, 1, &mut handle) });
         Self { handle, n: bases.len(), _c: Default::default() }
+    }
+    /// [commit(p, r)] for several polynomials in one pass (plonk/prover.rs:305-309, vanishing/prover.rs:102-106).
+    pub fn commit_many(&self, polys: &[&[C::Scalar]], blinds: &[C::Scalar]) -> Vec<C::Curve> {
+        assert_eq!(polys.len(), blinds.len());
+        let n = polys[0].len();
+        let mut s = Vec::with_capacity(polys.len() * n * 32);
+        for p in polys { assert_eq!(p.len(), n); s.extend_from_slice(&scalars_to_bytes(p)); }
+        let r = scalars_to_bytes(blinds);
+        let mut out = vec![0u8; 96 * polys.len()];
+        check(unsafe {
+            h2_msm_registered_batch(self.handle, s.as_ptr() as *const c_void, n, r.as_ptr() as *const c_void, polys.len(),
+                                    REPR_CANONICAL, out.as_mut_ptr() as *mut c_void)
+        });
+        out.chunks(96).map(|c| point_from_xyz::<C>(c.try_into().unwrap())).collect()
+    }
+    /// The round loop of commitment::create_proof (poly/commitment/prover.rs:100-142).  `round` receives (L_j, R_j)
+    /// and returns the challenge u_j (the caller's transcript); returns c = p_prime[0] after the last fold.
+    pub fn ipa_rounds(&self, k: u32, p_prime: &[C::Scalar], x3: C::Scalar, z: C::Scalar,
+                      mut rand: impl FnMut() -> (C::Scalar, C::Scalar),
+                      mut round: impl FnMut(C::Curve, C::Curve, C::Scalar, C::Scalar) -> C::Scalar) -> C::Scalar {
+        assert_eq!(self.n, (1usize << k) + 2);
+        let pp = scalars_to_bytes(p_prime);
+        let mut sess = 0u64;
+        check(unsafe { h2_ipa_begin(self.handle, k, pp.as_ptr() as *const c_void, x3.to_repr().as_ref().as_ptr() as *const c_void,
+                                    REPR_CANONICAL, &mut sess) });
+        let zb = z.to_repr();
+        for _ in 0..k {
+            let (l_rand, r_rand) = rand();
+            let mut lr = [0u8; 192];
+            check(unsafe { h2_ipa_round(sess, zb.as_ref().as_ptr() as *const c_void, l_rand.to_repr().as_ref().as_ptr() as *const c_void,
+                                        r_rand.to_repr().as_ref().as_ptr() as *const c_void, REPR_CANONICAL, lr.as_mut_ptr() as *mut c_void) });
+            let l_j = point_from_xyz::<C>(lr[..96].try_into().unwrap());
+            let r_j = point_from_xyz::<C>(lr[96..].try_into().unwrap());
+            let u_j = round(l_j, r_j, l_rand, r_rand);
+            let u_inv = u_j.invert().unwrap();
+            check(unsafe { h2_ipa_fold(sess, u_j.to_repr().as_ref().as_ptr() as *const c_void,
+                                       u_inv.to_repr().as_ref().as_ptr() as *const c_void, REPR_CANONICAL) });
+        }
+        let mut cb = [0u8; 64];
+        check(unsafe { h2_ipa_finish(sess, REPR_CANONICAL, cb.as_mut_ptr() as *mut c_void) });
+        let mut repr = <C::Scalar as PrimeField>::Repr::default();
+        repr.as_mut().copy_from_slice(&cb[..32]);
+        C::Scalar::from_repr(repr).unwrap()
     }
     /// <poly, bases[..n]> + r * bases[n]
     pub fn commit(&self, poly: &[C::Scalar], r: C::Scalar) -> C::Curve {
