@@ -269,11 +269,12 @@ template <class P> __global__ void __launch_bounds__(64) test_curve_kernel(const
     st_affine(out + i, o);
 }
 // throughput microbenchmark: 4 independent dependent-chains per thread
-template <class P> __global__ void bench_mul_kernel(fe *io, uint32_t iters) {
+template <class P, bool SQR> __global__ void bench_mul_kernel(fe *io, uint32_t iters) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     fe a = fe_load(io + 4 * i), b = fe_load(io + 4 * i + 1), c = fe_load(io + 4 * i + 2), d = fe_load(io + 4 * i + 3);
     for (uint32_t k = 0; k < iters; k++) {
-        a = fe_mul<P>(a, b); b = fe_mul<P>(b, c); c = fe_mul<P>(c, d); d = fe_mul<P>(d, a);
+        if (SQR) { a = fe_sqr<P>(a); b = fe_sqr<P>(b); c = fe_sqr<P>(c); d = fe_sqr<P>(d); }
+        else { a = fe_mul<P>(a, b); b = fe_mul<P>(b, c); c = fe_mul<P>(c, d); d = fe_mul<P>(d, a); }
     }
     fe_store(io + 4 * i, a); fe_store(io + 4 * i + 1, b); fe_store(io + 4 * i + 2, c); fe_store(io + 4 * i + 3, d);
 }
@@ -347,7 +348,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
     if (c > 24) return fail("msm: window bits > 24");
     msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets);
-    if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 40))) return 1;
+    if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 32))) return 1;
     if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
     if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
     if (scalars_mont && X.scal_canon.ensure(n * p.sets * sizeof(fe))) return 1;
@@ -979,8 +980,11 @@ extern "C" int h2_bench_field_mul(int field, uint32_t threads_per_block, uint32_
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {   // first repetition warms up
         CU(cudaEventRecord(e0, s));
-        if (field == H2_FIELD_FP) LAUNCH(bench_mul_kernel<FpParams>, blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
-        else LAUNCH(bench_mul_kernel<FqParams>, blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        // field | 0x100: the same loop with fe_sqr
+        if (field == H2_FIELD_FP) LAUNCH((bench_mul_kernel<FpParams, false>), blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        else if (field == H2_FIELD_FQ) LAUNCH((bench_mul_kernel<FqParams, false>), blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        else if (field == (H2_FIELD_FP | 0x100)) LAUNCH((bench_mul_kernel<FpParams, true>), blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
+        else LAUNCH((bench_mul_kernel<FqParams, true>), blocks, threads_per_block, 0, s, X.misc.as<fe>(), iters);
         CU(cudaEventRecord(e1, s));
         CU(cudaStreamSynchronize(s));
     }

@@ -44,6 +44,9 @@ H2_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 
 H2_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 H2_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 H2_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// funnel shifts (ALU pipe); written as asm so that ptxas does not turn the pair q << 30, q >> 2 back into an IMAD.WIDE
+H2_D uint32_t shl30(uint32_t a) { uint32_t r; asm volatile("shf.l.clamp.b32 %0, %1, %2, 30;" : "=r"(r) : "r"(0u), "r"(a)); return r; }
+H2_D uint32_t shr2(uint32_t a) { uint32_t r; asm volatile("shf.r.clamp.b32 %0, %1, %2, 2;" : "=r"(r) : "r"(a), "r"(0u)); return r; }
 H2_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 H2_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 H2_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -59,6 +62,8 @@ inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cf_; }
 inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b; cf_ = (uint32_t)(d >> 63); return (uint32_t)d; }
 inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t d = (uint64_t)a - b - cf_; cf_ = (uint32_t)(d >> 63); return (uint32_t)d; }
 inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cf_; }
+inline uint32_t shl30(uint32_t a) { return a << 30; }
+inline uint32_t shr2(uint32_t a) { return a >> 2; }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
 inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t s = (uint64_t)mul_lo(a, b) + c; cf_ = (uint32_t)(s >> 32); return (uint32_t)s; }
@@ -208,16 +213,17 @@ template <bool FIRST> H2_HD void prod_ev(uint32_t (&ev)[8], uint32_t (&od)[8], c
         od[7] = addc(od[7], 0u);                     // carry out of position 7 lands on position 8
     }
 }
-// q * m, odd columns: m1 @1, m3 @3, 2^30 @7
-template <class P> H2_HD void red_od(uint32_t (&od)[8], uint32_t q) {
-    od[0] = mad_lo_cc(q, P::M1, od[0]);
+// q * m, odd columns: m1 @1, m3 @3, 2^30 @7.  CIN: a carry into position 1 is pending in CC (fe_sqr's
+// product-free iterations, where no prod_od chain has consumed the fold-in carry).
+template <class P, bool CIN = false> H2_HD void red_od(uint32_t (&od)[8], uint32_t q) {
+    od[0] = CIN ? madc_lo_cc(q, P::M1, od[0]) : mad_lo_cc(q, P::M1, od[0]);
     od[1] = madc_hi_cc(q, P::M1, od[1]);
     od[2] = madc_lo_cc(q, P::M3, od[2]);
     od[3] = madc_hi_cc(q, P::M3, od[3]);
     od[4] = addc_cc(od[4], 0u);
     od[5] = addc_cc(od[5], 0u);
-    od[6] = madc_lo_cc(q, H2_M7, od[6]);
-    od[7] = madc_hi(q, H2_M7, od[7]);
+    od[6] = addc_cc(od[6], shl30(q));                // q * 2^30 with shifts: keeps 2 of 8 multiplies per round
+    od[7] = addc(od[7], shr2(q));                    // off the IMAD pipe, the one that bounds the MSM
 }
 // q * m, even columns: 1 @0, m2 @2
 template <class P> H2_HD void red_ev(uint32_t (&ev)[8], uint32_t (&od)[8], uint32_t q) {
@@ -320,7 +326,75 @@ template <class P> H2_HD void fe_mul2(fe &r0, const fe &a0, const fe &b0, fe &r1
     fe_cond_sub_mod<P>(t1);
     r0 = t0; r1 = t1;
 }
-template <class P> H2_HD fe fe_sqr(const fe &a) { return fe_mul<P>(a, a); }
+// Dedicated squaring: the 28 off-diagonal products once (rows of IMAD.WIDE carry chains into an even- and an
+// odd-position accumulator, E and O, indexed by absolute limb position), doubled, plus the 8 diagonal squares:
+// 36 wide multiplies instead of 64.  The low half then runs through the same sliding-window reduction as fe_mul
+// with no products to add, and the high half is added at the end:
+//   (T + Q m) / 2^256 = T_hi + (T_lo + Q m) / 2^256 <= T_hi + m < 2m      (T_hi < m^2 / 2^256 < m / 2).
+template <class P> H2_HD fe fe_sqr(const fe &a) {
+    using namespace ptx;
+    const uint32_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3], a4 = a.v[4], a5 = a.v[5], a6 = a.v[6], a7 = a.v[7];
+    uint32_t E[14], O[15];
+    // row 0 opens both accumulators
+    O[1] = mul_lo(a0, a1); O[2] = mul_hi(a0, a1); O[3] = mul_lo(a0, a3); O[4] = mul_hi(a0, a3);
+    O[5] = mul_lo(a0, a5); O[6] = mul_hi(a0, a5); O[7] = mul_lo(a0, a7); O[8] = mul_hi(a0, a7);
+    E[2] = mul_lo(a0, a2); E[3] = mul_hi(a0, a2); E[4] = mul_lo(a0, a4); E[5] = mul_hi(a0, a4);
+    E[6] = mul_lo(a0, a6); E[7] = mul_hi(a0, a6);
+    // row 1
+    O[3] = mad_lo_cc(a1, a2, O[3]); O[4] = madc_hi_cc(a1, a2, O[4]); O[5] = madc_lo_cc(a1, a4, O[5]); O[6] = madc_hi_cc(a1, a4, O[6]);
+    O[7] = madc_lo_cc(a1, a6, O[7]); O[8] = madc_hi_cc(a1, a6, O[8]); O[9] = addc(0u, 0u);
+    E[4] = mad_lo_cc(a1, a3, E[4]); E[5] = madc_hi_cc(a1, a3, E[5]); E[6] = madc_lo_cc(a1, a5, E[6]); E[7] = madc_hi_cc(a1, a5, E[7]);
+    E[8] = madc_lo_cc(a1, a7, 0u); E[9] = madc_hi(a1, a7, 0u);
+    // row 2
+    O[5] = mad_lo_cc(a2, a3, O[5]); O[6] = madc_hi_cc(a2, a3, O[6]); O[7] = madc_lo_cc(a2, a5, O[7]); O[8] = madc_hi_cc(a2, a5, O[8]);
+    O[9] = madc_lo_cc(a2, a7, O[9]); O[10] = madc_hi(a2, a7, 0u);
+    E[6] = mad_lo_cc(a2, a4, E[6]); E[7] = madc_hi_cc(a2, a4, E[7]); E[8] = madc_lo_cc(a2, a6, E[8]); E[9] = madc_hi_cc(a2, a6, E[9]);
+    E[10] = addc(0u, 0u);
+    // row 3
+    O[7] = mad_lo_cc(a3, a4, O[7]); O[8] = madc_hi_cc(a3, a4, O[8]); O[9] = madc_lo_cc(a3, a6, O[9]); O[10] = madc_hi_cc(a3, a6, O[10]);
+    O[11] = addc(0u, 0u);
+    E[8] = mad_lo_cc(a3, a5, E[8]); E[9] = madc_hi_cc(a3, a5, E[9]); E[10] = madc_lo_cc(a3, a7, E[10]); E[11] = madc_hi(a3, a7, 0u);
+    // row 4
+    O[9] = mad_lo_cc(a4, a5, O[9]); O[10] = madc_hi_cc(a4, a5, O[10]); O[11] = madc_lo_cc(a4, a7, O[11]); O[12] = madc_hi(a4, a7, 0u);
+    E[10] = mad_lo_cc(a4, a6, E[10]); E[11] = madc_hi_cc(a4, a6, E[11]); E[12] = addc(0u, 0u);
+    // row 5
+    O[11] = mad_lo_cc(a5, a6, O[11]); O[12] = madc_hi_cc(a5, a6, O[12]); O[13] = addc(0u, 0u);
+    E[12] = mad_lo_cc(a5, a7, E[12]); E[13] = madc_hi(a5, a7, 0u);
+    // row 6
+    O[13] = mad_lo_cc(a6, a7, O[13]); O[14] = madc_hi(a6, a7, 0u);
+    // U = E + O (positions 1..14; U < 2^479 so nothing leaves limb 14)
+    uint32_t U[15];
+    U[1] = O[1];
+    U[2] = add_cc(E[2], O[2]);
+    for (int p = 3; p <= 13; p++) U[p] = addc_cc(E[p], O[p]);
+    U[14] = addc(O[14], 0u);
+    // T = 2 U + sum_i a_i^2 2^(64 i)
+    uint32_t T[16];
+    T[0] = mul_lo(a0, a0);
+    T[1] = add_cc((U[1] << 1), mul_hi(a0, a0));
+    for (int i = 1; i < 8; i++) {
+        const uint32_t ai = a.v[i];
+        T[2 * i] = addc_cc((U[2 * i] << 1) | (U[2 * i - 1] >> 31), mul_lo(ai, ai));
+        if (i < 7) T[2 * i + 1] = addc_cc((U[2 * i + 1] << 1) | (U[2 * i] >> 31), mul_hi(ai, ai));
+        else T[15] = addc(U[14] >> 31, mul_hi(ai, ai));
+    }
+    // Montgomery reduction of T[0..8) with the sliding window of fe_mul (ev = x, od = y, roles swap each round)
+    uint32_t x[8], y[8], left, q;
+    for (int k = 0; k < 8; k++) { x[k] = T[k]; y[k] = 0u; }
+    q = 0u - x[0]; mont::red_od<P>(y, q); mont::red_ev<P>(x, y, q); left = mont::slide(x);
+#define H2_RED(EV, OD)                                                                   \
+    EV[0] = add_cc(EV[0], left); q = 0u - EV[0];                                         \
+    mont::red_od<P, true>(OD, q); mont::red_ev<P>(EV, OD, q); left = mont::slide(EV);
+    H2_RED(y, x) H2_RED(x, y) H2_RED(y, x) H2_RED(x, y) H2_RED(y, x) H2_RED(x, y) H2_RED(y, x)
+#undef H2_RED
+    x[0] = add_cc(x[0], left);
+    fe r = mont::finish<P>(x, y);
+    r.v[0] = add_cc(r.v[0], T[8]);
+    for (int k = 1; k < 7; k++) r.v[k] = addc_cc(r.v[k], T[8 + k]);
+    r.v[7] = addc(r.v[7], T[15]);
+    fe_cond_sub_mod<P>(r);
+    return r;
+}
 
 // canonical <-> Montgomery
 template <class P> H2_HD fe fe_to_mont(const fe &a) { return fe_mul<P>(a, fe_r2<P>()); }

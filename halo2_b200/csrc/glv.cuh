@@ -1,7 +1,7 @@
 // GLV endomorphism split for the j = 0 Pasta curves (generated constants: tools/gen_glv_constants.py).
 //
 // phi(x, y) = (zeta x, y) equals multiplication by lambda, so  k P = k1 P + k2 phi(P)  with
-// k = k1 + k2 lambda (mod r) and |k1|, |k2| < 2^129.  A 255-bit MSM over n points becomes a 129-bit
+// k = k1 + k2 lambda (mod r) and |k1|, |k2| < 2^127.  A 255-bit MSM over n points becomes a 127-bit
 // MSM over 2n points: the same number of (point, window) references, but half the windows --
 // half the bucket sets to reduce and half the serial doubling chain of the window combine
 // (arithmetic.rs:163 does c*i doublings per window; that chain is the latency floor of an MSM).
@@ -9,9 +9,11 @@
 //
 // k1 = k - c1 a1 - c2 a2,  k2 = c1 |b1| - c2 b2  with (a1, b1), (a2, b2) a reduced lattice basis
 // (b1 < 0 < a1, a2, b2) and c_i = floor((k g_i + 2^383) / 2^384), g1 = round(2^384 b2 / r), g2 = round(2^384 |b1| / r):
-// exact rounding up to a ~2^-125 sliver, hence |k_i| < 2^127 (8 windows of 16 bits) except in that sliver,
-// where |k_i| < 2^128 and a spare top window takes the carry.  The identity k1 + k2 lambda = k holds for
-// any integers c1, c2; the rounding only bounds the size.
+// c_i differs from the real k b / r by at most 1/2 + eps, eps < 2^-130 (|g_i - 2^384 b / r| <= 1/2 and k < 2^255), so
+// |k1| <= (1/2 + eps)(a1 + a2) and |k2| <= (1/2 + eps)(|b1| + b2); for both curves these sums are 0.577 / 0.866 x 2^128,
+// hence |k_i| < 0.867 x 2^127 < 2^127 ALWAYS: four limbs per half with a free top bit (it carries the sign in the stored
+// form), and W = ceil(128 / c) windows (tests/test_kernel_emul.py::test_emul_glv_split_bounds).  The identity
+// k1 + k2 lambda = k holds for any integers c1, c2; the rounding only bounds the size.
 #pragma once
 #include "field.cuh"
 
@@ -75,7 +77,7 @@ H2_HD uint32_t abs8(uint32_t *r) {
 }
 }  // namespace glv
 
-// k (canonical, 8 limbs) -> |k1|, |k2| as 8-limb arrays (< 2^129) and their signs
+// k (canonical, 8 limbs) -> |k1|, |k2| as 8-limb arrays (< 2^127) and their signs
 template <class P> H2_HD void glv_decompose(const uint32_t (&k)[8], uint32_t (&k1)[8], uint32_t &neg1, uint32_t (&k2)[8], uint32_t &neg2) {
     typedef GlvConst<P> C;
     uint32_t g1[9], g2[9], a1[4], nb1[4], a2[4], b2[4];

@@ -46,7 +46,7 @@ struct MsmPlan {
     uint64_t n;          // number of (scalar, base) pairs
     uint32_t c;          // window bits
     uint32_t glv;        // 1: scalars are split k = k1 + k2 lambda (glv.cuh); point i contributes P_i (k1) and phi(P_i) (k2)
-    uint32_t W;          // windows = ceil(256 / c), or ceil(130 / c) with the GLV split
+    uint32_t W;          // windows = ceil(256 / c), or ceil(128 / c) with the GLV split
     uint32_t B;          // buckets per window = 2^(c-1)
     uint32_t fixed;      // 1: bases come from a precomputed table T[w][i] = 2^(c w) G_i (resident Params
                          //    generators): every window's digits share ONE bucket set, no window combine
@@ -92,8 +92,9 @@ inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t =
                           uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1) {
     p.n = n; p.c = c;
     p.glv = fixed ? 0u : glv;
-    // sub-scalars are < 2^129; one spare bit lets the top window absorb the signed-digit carry
-    p.W = p.glv ? (130 + c - 1) / c : (256 + c - 1) / c;
+    // GLV sub-scalars are < 2^127 (glv.cuh): with W c >= 128 the top window's raw digit is < 2^(c-1), so it
+    // absorbs the signed-digit carry without opening another window
+    p.W = p.glv ? (128 + c - 1) / c : (256 + c - 1) / c;
     p.B = 1u << (c - 1);
     p.sets = fixed && sets ? sets : 1u;
     p.fixed = fixed; p.Wb = fixed ? p.sets : p.W; p.stride = stride;
@@ -143,7 +144,7 @@ struct MsmBuffers {
     uint32_t scalars_mont;
     // scratch
     fe *scal_canon;           // n (only when scalars_mont)
-    uint32_t *glv_parts;      // n x 10 words: |k1| (5 limbs, sign in bit 31 of limb 4) then |k2|   (GLV only)
+    uint32_t *glv_parts;      // n x 8 words: |k1| (4 limbs, sign in bit 127) then |k2|   (GLV only)
     uint32_t *counts;         // G + 1  (histogram, then exclusive offsets after the scan)
     uint32_t *cursor;         // G
     uint32_t *refs;           // max_refs   point index | sign << 31, sorted by bucket id
@@ -191,20 +192,18 @@ template <class P, class PS> struct Msm {
     static H2_HD void load_parts(const MsmPlan &p, const MsmBuffers &M, uint64_t i, bool first_pass, uint32_t (&part)[2][8], uint32_t (&neg)[2]) {
         neg[0] = neg[1] = 0;
         if (!p.glv) { uint32_t s[8]; load_scalar(M, i, s, first_pass); for (int k = 0; k < 8; k++) part[0][k] = s[k]; return; }
-        uint32_t *q = M.glv_parts + i * 10;
+        uint4 *q = reinterpret_cast<uint4 *>(M.glv_parts) + i * 2;
         if (first_pass) {
             uint32_t s[8];
             load_scalar(M, i, s, true);
             glv_decompose<P>(s, part[0], neg[0], part[1], neg[1]);
-            for (int e = 0; e < 2; e++) {
-                for (int k = 0; k < 4; k++) q[5 * e + k] = part[e][k];
-                q[5 * e + 4] = part[e][4] | (neg[e] << 31);       // |k_e| < 2^129: limb 4 has 1 bit
-            }
+            for (int e = 0; e < 2; e++)   // |k_e| < 2^127: four limbs, the sign rides in bit 127
+                q[e] = make_uint4(part[e][0], part[e][1], part[e][2], part[e][3] | (neg[e] << 31));
         } else {
             for (int e = 0; e < 2; e++) {
-                for (int k = 0; k < 4; k++) part[e][k] = q[5 * e + k];
-                part[e][4] = q[5 * e + 4] & 0x7fffffffu; neg[e] = q[5 * e + 4] >> 31;
-                part[e][5] = part[e][6] = part[e][7] = 0;
+                uint4 v = q[e];
+                part[e][0] = v.x; part[e][1] = v.y; part[e][2] = v.z; part[e][3] = v.w & 0x7fffffffu; neg[e] = v.w >> 31;
+                part[e][4] = part[e][5] = part[e][6] = part[e][7] = 0;
             }
         }
     }

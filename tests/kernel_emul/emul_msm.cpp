@@ -43,7 +43,7 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         r1((size_t)p.W * p.r1_rows), wsum(p.W);
     std::vector<jacobian> result(sets);
     MsmBuffers M;
-    std::vector<uint32_t> glv_parts((ns ? ns : 1) * 10);
+    std::vector<uint32_t> glv_parts((ns ? ns : 1) * 8 + 4);
     M.glv_parts = glv_parts.data();
     M.scalars = sc.data(); M.bases = fixed ? table.data() : bs.data(); M.bases_phi = phi.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
     M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data();

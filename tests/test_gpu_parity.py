@@ -47,6 +47,18 @@ def _affine(curve, xyz):
 
 
 # ------------------------------------------------------------------------------------------ K0
+def _structured_limbs(m):
+    import random
+    rnd = random.Random(6)
+    raws = [0, 1, m - 1, m - 2, 1 << 254, (1 << 254) - 1, (1 << 254) + 1, m >> 1]
+    for mask in range(256):
+        v = sum(0xFFFFFFFF << (32 * i) for i in range(8) if (mask >> i) & 1)
+        raws += [v % m, v & ((1 << 254) - 1)]
+    for _ in range(1500):
+        raws.append(sum(rnd.choice([0, 0xFFFFFFFF, 1, 0x80000000, 0x7FFFFFFF, rnd.getrandbits(32)]) << (32 * i) for i in range(8)) % m)
+    return raws
+
+
 @pytest.mark.parametrize("field", ["fp", "fq"])
 def test_device_field_ops(eng, field):
     m = pasta.FIELDS[field]
@@ -59,6 +71,12 @@ def test_device_field_ops(eng, field):
     assert _field_op(field, 4, xs) == [a * a % m for a in xs]
     nz = [x for x in xs if x][:300]
     assert _field_op(field, 3, nz) == [pow(a, m - 2, m) for a in nz]
+    # structured MONTGOMERY operands (all-ones / zero / single-bit limbs): the carry edges of the dedicated squaring
+    raws = _structured_limbs(m)
+    rinv = pow(1 << 256, -1, m)
+    zs = [x * rinv % m for x in raws]              # to_mont(z) == x
+    assert _field_op(field, 4, zs) == [a * a % m for a in zs]
+    assert _field_op(field, 2, zs, zs[5:] + zs[:5]) == [a * b % m for a, b in zip(zs, zs[5:] + zs[:5])]
 
 
 @pytest.mark.parametrize("field", ["fp", "fq"])

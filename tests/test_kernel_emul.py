@@ -220,3 +220,58 @@ def test_emul_ipa_rounds(emu, curve):
         for j in range(k):
             assert cref.jac_to_affine(curve, out_l[j]).tobytes() == want_l[j].tobytes(), (k, j)
             assert cref.jac_to_affine(curve, out_r[j]).tobytes() == want_r[j].tobytes(), (k, j)
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_glv_split_bounds(emu, curve):
+    """glv_decompose: k1 + k2 lambda = k (mod r) and |k1|, |k2| < 2^127 -- the bound the plan's W = ceil(128 / c) and
+    the 4-limb stored halves rely on -- on random scalars and on scalars placed at the rounding boundaries of c1 / c2
+    (k b / r within one unit of a half-integer), where the device's 2^384 fixed-point rounding could differ from exact."""
+    import random
+    import sys
+    sys.path.insert(0, "tools")
+    import gen_glv_constants as gg
+    c = pasta.CURVES[curve]
+    r = c.r
+    lam, _ = gg.find_lambda_zeta(c)
+    (a1, b1), (a2, b2) = gg.lattice(r, lam)
+    # rigorous: |k1| <= (1/2 + eps)(a1 + a2), |k2| <= (1/2 + eps)(|b1| + b2), eps < 2^-130
+    assert (a1 + a2) * 1001 // 2000 < 1 << 127 and (abs(b1) + b2) * 1001 // 2000 < 1 << 127
+    rnd = random.Random(99)
+    ks = [0, 1, 2, r - 1, r - 2, lam, r - lam, (r - 1) // 2, (r + 1) // 2]
+    ks += [rnd.randrange(r) for _ in range(3000)]
+    for b in (b2, abs(b1)):
+        for _ in range(300):
+            j = rnd.randrange(b)
+            k0 = ((2 * j + 1) * r) // (2 * b)          # k b / r ~ j + 1/2
+            ks += [(k0 + d) % r for d in (-2, -1, 0, 1, 2)]
+    out = np.zeros(66, dtype=np.uint8)
+    worst = 0
+    for k in ks:
+        emu.emu_glv(cref.CURVE_ID[curve], cref._p(cref._fe(k)), cref._p(out))
+        k1 = int.from_bytes(out[:32].tobytes(), "little") * (-1 if out[64] else 1)
+        k2 = int.from_bytes(out[32:64].tobytes(), "little") * (-1 if out[65] else 1)
+        assert (k1 + k2 * lam - k) % r == 0
+        worst = max(worst, abs(k1).bit_length(), abs(k2).bit_length())
+    assert worst <= 127, worst
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_emul_field_structured_limbs(emu, field):
+    """fe_sqr (dedicated squaring: 36 products + product-free reduction rounds) and fe_mul on operands whose MONTGOMERY
+    limbs are all-ones / zero / single-bit patterns -- the carry edges random inputs never reach."""
+    import random
+    m = pasta.FIELDS[field]
+    rnd = random.Random(6)
+    raws = [0, 1, m - 1, m - 2, 1 << 254, (1 << 254) - 1, (1 << 254) + 1, m >> 1]
+    for mask in range(256):
+        v = sum(0xFFFFFFFF << (32 * i) for i in range(8) if (mask >> i) & 1)
+        raws += [v % m, v & ((1 << 254) - 1)]
+    for _ in range(1500):
+        raws.append(sum(rnd.choice([0, 0xFFFFFFFF, 1, 0x80000000, 0x7FFFFFFF, rnd.getrandbits(32)]) << (32 * i) for i in range(8)) % m)
+    rinv = pow(1 << 256, -1, m)
+    for i, x in enumerate(raws):
+        a = x * rinv % m                     # to_mont(a) == x
+        b = raws[(i * 7 + 3) % len(raws)] * rinv % m
+        assert _fop(emu, field, 4, a) == a * a % m, hex(x)
+        assert _fop(emu, field, 2, a, b) == a * b % m, hex(x)

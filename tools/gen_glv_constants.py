@@ -5,9 +5,8 @@ zeta^3 = 1 in the base field and lambda^2 + lambda + 1 = 0 mod r.  (a1, b1), (a2
 basis of the lattice {(a, b): a + b lambda = 0 mod r} (extended Euclid on (r, lambda)); a scalar k
 splits as k = k1 + k2 lambda with k1 = k - c1 a1 - c2 a2, k2 = -c1 b1 - c2 b2, c1 = round(k b2 / r),
 c2 = round(-k b1 / r), |k1|, |k2| < 2^127.  The device uses g_i = round(2^384 |b_j| / r) and
-c_i = floor((k g_i + 2^383) / 2^384): exact rounding except when k b / r is within ~2^-125 of a
-half-integer, where it is off by one and |k_i| may reach 2^128 -- the plan keeps one spare window for
-that.  The identity k1 + k2 lambda = k (mod r) holds for ANY integers c1, c2 because the basis vectors
+c_i = floor((k g_i + 2^383) / 2^384): within 1/2 + 2^-130 of the real quotient, so
+|k1| <= (1/2 + eps)(a1 + a2), |k2| <= (1/2 + eps)(|b1| + b2) < 0.867 x 2^127 (asserted below).  The identity k1 + k2 lambda = k (mod r) holds for ANY integers c1, c2 because the basis vectors
 are in the lattice, so correctness never depends on the rounding.
 """
 import sys
@@ -58,6 +57,7 @@ def main():
         (a1, b1), (a2, b2) = lattice(r, lam)
         assert (a1 + b1 * lam) % r == 0 and (a2 + b2 * lam) % r == 0 and a1 * b2 - a2 * b1 == r
         assert a1 > 0 and a2 > 0 and b1 < 0 and b2 > 0
+        assert (a1 + a2) * 1001 // 2000 < 1 << 127 and (b2 - b1) * 1001 // 2000 < 1 << 127   # |k_i| < 2^127 rigorously
         g1 = ((b2 << 384) + r // 2) // r       # c1 ~ k b2 / r
         g2 = (((-b1) << 384) + r // 2) // r    # c2 ~ k |b1| / r
         # exhaustive-ish self check of the device formula

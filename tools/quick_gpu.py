@@ -13,7 +13,7 @@ lib = L.init()
 
 
 def mulbench():
-    for field in (0, 1):
+    for field in (0, 1, 0x100, 0x101):
         for tpb, blocks in ((128, 148 * 4), (256, 148 * 4), (256, 148 * 8)):
             ms = ctypes.c_float()
             iters = 2000
