@@ -19,6 +19,21 @@ struct affine { fe x, y; };              // 64 B, Montgomery coordinates; (0,0) 
 struct xyzz { fe x, y, zz, zzz; };       // 128 B
 struct jacobian { fe x, y, z; };         // 96 B, the layout of pasta's Ep/Eq (x, y, z)
 
+// Out-of-line multiply / square for the group law.  Inlined, one mixed add is ~45 KB of straight-line SASS (a full add
+// ~60 KB); with ~20 resident warps at unrelated program counters the instruction caches thrash (ncu on the inlined
+// accumulate kernel: `stalled_no_instruction` was the largest stall reason, fmaheavy 70 % busy vs 82 % for a
+// 4-multiply loop).  Called, a kernel's group law is a few KB plus the two callees.  Arguments and result travel in
+// registers.  cm / cs are what the formulas below use; the host (emulation) build inlines.
+#ifdef __CUDA_ARCH__
+template <class P> __device__ __noinline__ fe fe_mul_call(fe a, fe b) { return fe_mul<P>(a, b); }
+template <class P> __device__ __noinline__ fe fe_sqr_call(fe a) { return fe_sqr<P>(a); }
+#else
+template <class P> inline fe fe_mul_call(const fe &a, const fe &b) { return fe_mul<P>(a, b); }
+template <class P> inline fe fe_sqr_call(const fe &a) { return fe_sqr<P>(a); }
+#endif
+#define cm fe_mul_call
+#define cs fe_sqr_call
+
 H2_HD bool affine_is_identity(const affine &p) {
     uint32_t t = 0;
     for (int i = 0; i < 8; i++) t |= p.x.v[i] | p.y.v[i];
@@ -46,13 +61,13 @@ template <class P> H2_HD affine affine_neg(const affine &p) {
 template <class P> H2_HD xyzz xyzz_double_affine(const affine &p) {
     xyzz r;
     fe u = fe_dbl<P>(p.y);
-    fe v = fe_sqr<P>(u);
-    fe w = fe_mul<P>(u, v);
-    fe s = fe_mul<P>(p.x, v);
-    fe m = fe_sqr<P>(p.x);
+    fe v = cs<P>(u);
+    fe w = cm<P>(u, v);
+    fe s = cm<P>(p.x, v);
+    fe m = cs<P>(p.x);
     m = fe_add<P>(fe_dbl<P>(m), m);
-    r.x = fe_sub<P>(fe_sub<P>(fe_sqr<P>(m), s), s);
-    r.y = fe_sub<P>(fe_mul<P>(m, fe_sub<P>(s, r.x)), fe_mul<P>(w, p.y));
+    r.x = fe_sub<P>(fe_sub<P>(cs<P>(m), s), s);
+    r.y = fe_sub<P>(cm<P>(m, fe_sub<P>(s, r.x)), cm<P>(w, p.y));
     r.zz = v; r.zzz = w;
     return r;
 }
@@ -61,24 +76,24 @@ template <class P> H2_HD xyzz xyzz_double_affine(const affine &p) {
 template <class P> H2_HD void xyzz_double(xyzz &a) {
     if (xyzz_is_identity(a)) return;
     fe u = fe_dbl<P>(a.y);
-    fe v = fe_sqr<P>(u);
-    fe w = fe_mul<P>(u, v);
-    fe s = fe_mul<P>(a.x, v);
-    fe m = fe_sqr<P>(a.x);
+    fe v = cs<P>(u);
+    fe w = cm<P>(u, v);
+    fe s = cm<P>(a.x, v);
+    fe m = cs<P>(a.x);
     m = fe_add<P>(fe_dbl<P>(m), m);
-    fe x3 = fe_sub<P>(fe_sub<P>(fe_sqr<P>(m), s), s);
-    fe y3 = fe_sub<P>(fe_mul<P>(m, fe_sub<P>(s, x3)), fe_mul<P>(w, a.y));
+    fe x3 = fe_sub<P>(fe_sub<P>(cs<P>(m), s), s);
+    fe y3 = fe_sub<P>(cm<P>(m, fe_sub<P>(s, x3)), cm<P>(w, a.y));
     a.x = x3; a.y = y3;
-    a.zz = fe_mul<P>(v, a.zz);
-    a.zzz = fe_mul<P>(w, a.zzz);
+    a.zz = cm<P>(v, a.zz);
+    a.zzz = cm<P>(w, a.zzz);
 }
 
 // acc += affine p   (madd-2008-s); the hot operation of the bucket accumulation
 template <class P> H2_HD void xyzz_add_mixed(xyzz &a, const affine &p) {
     if (affine_is_identity(p)) return;
     if (xyzz_is_identity(a)) { a = xyzz_from_affine<P>(p); return; }
-    fe u2 = fe_mul<P>(p.x, a.zz);
-    fe s2 = fe_mul<P>(p.y, a.zzz);
+    fe u2 = cm<P>(p.x, a.zz);
+    fe s2 = cm<P>(p.y, a.zzz);
     fe pp = fe_sub<P>(u2, a.x);
     fe r = fe_sub<P>(s2, a.y);
     if (fe_is_zero(pp)) {
@@ -86,24 +101,24 @@ template <class P> H2_HD void xyzz_add_mixed(xyzz &a, const affine &p) {
         else a = xyzz_identity();                          // opposite points
         return;
     }
-    fe pp2 = fe_sqr<P>(pp);
-    fe ppp = fe_mul<P>(pp, pp2);
-    fe q = fe_mul<P>(a.x, pp2);
-    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(r), ppp), q), q);
-    fe y3 = fe_sub<P>(fe_mul<P>(r, fe_sub<P>(q, x3)), fe_mul<P>(a.y, ppp));
+    fe pp2 = cs<P>(pp);
+    fe ppp = cm<P>(pp, pp2);
+    fe q = cm<P>(a.x, pp2);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(cs<P>(r), ppp), q), q);
+    fe y3 = fe_sub<P>(cm<P>(r, fe_sub<P>(q, x3)), cm<P>(a.y, ppp));
     a.x = x3; a.y = y3;
-    a.zz = fe_mul<P>(a.zz, pp2);
-    a.zzz = fe_mul<P>(a.zzz, ppp);
+    a.zz = cm<P>(a.zz, pp2);
+    a.zzz = cm<P>(a.zzz, ppp);
 }
 
 // acc += b   (add-2008-s)
 template <class P> H2_HD void xyzz_add(xyzz &a, const xyzz &b) {
     if (xyzz_is_identity(b)) return;
     if (xyzz_is_identity(a)) { a = b; return; }
-    fe u1 = fe_mul<P>(a.x, b.zz);
-    fe u2 = fe_mul<P>(b.x, a.zz);
-    fe s1 = fe_mul<P>(a.y, b.zzz);
-    fe s2 = fe_mul<P>(b.y, a.zzz);
+    fe u1 = cm<P>(a.x, b.zz);
+    fe u2 = cm<P>(b.x, a.zz);
+    fe s1 = cm<P>(a.y, b.zzz);
+    fe s2 = cm<P>(b.y, a.zzz);
     fe pp = fe_sub<P>(u2, u1);
     fe r = fe_sub<P>(s2, s1);
     if (fe_is_zero(pp)) {
@@ -111,14 +126,14 @@ template <class P> H2_HD void xyzz_add(xyzz &a, const xyzz &b) {
         else a = xyzz_identity();
         return;
     }
-    fe pp2 = fe_sqr<P>(pp);
-    fe ppp = fe_mul<P>(pp, pp2);
-    fe q = fe_mul<P>(u1, pp2);
-    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(r), ppp), q), q);
-    fe y3 = fe_sub<P>(fe_mul<P>(r, fe_sub<P>(q, x3)), fe_mul<P>(s1, ppp));
+    fe pp2 = cs<P>(pp);
+    fe ppp = cm<P>(pp, pp2);
+    fe q = cm<P>(u1, pp2);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(cs<P>(r), ppp), q), q);
+    fe y3 = fe_sub<P>(cm<P>(r, fe_sub<P>(q, x3)), cm<P>(s1, ppp));
     a.x = x3; a.y = y3;
-    a.zz = fe_mul<P>(fe_mul<P>(a.zz, b.zz), pp2);
-    a.zzz = fe_mul<P>(fe_mul<P>(a.zzz, b.zzz), ppp);
+    a.zz = cm<P>(cm<P>(a.zz, b.zz), pp2);
+    a.zzz = cm<P>(cm<P>(a.zzz, b.zzz), ppp);
 }
 
 // XYZZ -> Jacobian without inversion: (X*ZZ, Y*ZZZ, ZZ) since (ZZ)^2 * x = X*ZZ and
@@ -126,8 +141,8 @@ template <class P> H2_HD void xyzz_add(xyzz &a, const xyzz &b) {
 template <class P> H2_HD jacobian xyzz_to_jacobian(const xyzz &p) {
     jacobian j;
     if (xyzz_is_identity(p)) { j.x = fe_zero(); j.y = fe_one<P>(); j.z = fe_zero(); return j; }
-    j.x = fe_mul<P>(p.x, p.zz);
-    j.y = fe_mul<P>(p.y, p.zzz);
+    j.x = cm<P>(p.x, p.zz);
+    j.y = cm<P>(p.y, p.zzz);
     j.z = p.zz;
     return j;
 }
@@ -135,14 +150,15 @@ template <class P> H2_HD affine jacobian_to_affine(const jacobian &j) {
     affine r;
     if (fe_is_zero(j.z)) { r.x = fe_zero(); r.y = fe_zero(); return r; }
     fe zi = fe_inv<P>(j.z);
-    fe zi2 = fe_sqr<P>(zi);
-    r.x = fe_mul<P>(j.x, zi2);
-    r.y = fe_mul<P>(j.y, fe_mul<P>(zi2, zi));
+    fe zi2 = cs<P>(zi);
+    r.x = cm<P>(j.x, zi2);
+    r.y = cm<P>(j.y, cm<P>(zi2, zi));
     return r;
 }
 
 // acc = 2^k * acc through Jacobian coordinates: the a = 0 doubling dbl-2009-l costs 2M + 5S
-// (XYZZ doubling: 6M + 3S), which pays off on the long shift chains of the window combine.
+// (XYZZ doubling: 6M + 3S), which pays off on the long shift chains of the window combine.  That chain is run by lone
+// warps (pure latency), so its multiplies stay inlined: a call costs ~15 % per multiply when nothing else hides it.
 template <class P> H2_HD void xyzz_shift(xyzz &a, uint32_t k) {
     if (k == 0 || xyzz_is_identity(a)) return;
     if (k < 4) { for (uint32_t d = 0; d < k; d++) xyzz_double<P>(a); return; }
@@ -178,5 +194,8 @@ template <class P> H2_HD xyzz xyzz_scalar_mul(const affine &p, const uint32_t (&
     }
     return acc;
 }
+
+#undef cm
+#undef cs
 
 }  // namespace h2
