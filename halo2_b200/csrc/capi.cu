@@ -416,7 +416,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1, 128), 128, 0, s, p, M);
     LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0), 128), 128, 0, s, p, M);
     LAUNCH(k_r1, p.Wb * p.r1_rows, 128, 0, s, p, M);
-    LAUNCH(k_wsum, p.Wb, 32, 0, s, p, M);
+    LAUNCH(k_wsum, p.Wb, 128, 0, s, p, M);
     LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
     return 0;
 }

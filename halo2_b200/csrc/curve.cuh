@@ -182,6 +182,47 @@ template <class P> H2_HD void xyzz_shift(xyzz &a, uint32_t k) {
     a.zzz = fe_mul<P>(a.zz, Z);
 }
 
+#ifdef __CUDACC__
+// xyzz_shift for a QUAD: four consecutive lanes hold the same point and call this together.  A Jacobian doubling is
+// 7 multiplies but only 3 deep -- (X^2, Y^2, Y Z) -> (B^2, (X + B)^2, E^2) -> E (D - X3) -- so lanes 0..2 each take one
+// product of a level and the quad exchanges the results by shuffle; the last product is computed redundantly.  The
+// serial doubling chain of the window combine (c (W - 1) + ~15 doublings for the top window, nothing else to overlap
+// it with) shortens from 7 to 3 multiply latencies per step.
+H2_D fe quad_bcast(const fe &v, uint32_t src, uint32_t mask) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(mask, v.v[i], src, 4);
+    return r;
+}
+H2_D fe fe_select(bool c, const fe &a, const fe &b) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+    return r;
+}
+template <class P> H2_D void xyzz_shift_quad(xyzz &a, uint32_t k) {
+    if (k == 0 || xyzz_is_identity(a)) return;          // uniform within the quad
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);
+    fe X = fe_mul<P>(a.x, a.zz), Y = fe_mul<P>(a.y, a.zzz), Z = a.zz;   // Jacobian (X ZZ, Y ZZZ, ZZ)
+    for (uint32_t d = 0; d < k; d++) {
+        fe r = fe_mul<P>(fe_select(sub == 0, X, Y), fe_select(sub == 0, X, fe_select(sub == 1, Y, Z)));
+        fe A = quad_bcast(r, 0, mask), B = quad_bcast(r, 1, mask), YZ = quad_bcast(r, 2, mask);
+        fe E = fe_add<P>(fe_dbl<P>(A), A);
+        fe t = fe_add<P>(X, B);
+        r = fe_sqr<P>(fe_select(sub == 0, B, fe_select(sub == 1, t, E)));
+        fe C = quad_bcast(r, 0, mask), T2 = quad_bcast(r, 1, mask), F = quad_bcast(r, 2, mask);
+        fe D = fe_dbl<P>(fe_sub<P>(fe_sub<P>(T2, A), C));
+        X = fe_sub<P>(fe_sub<P>(F, D), D);
+        fe C8 = fe_dbl<P>(fe_dbl<P>(fe_dbl<P>(C)));
+        Y = fe_sub<P>(fe_mul<P>(E, fe_sub<P>(D, X)), C8);
+        Z = fe_dbl<P>(YZ);
+    }
+    a.x = X; a.y = Y;
+    a.zz = fe_sqr<P>(Z);
+    a.zzz = fe_mul<P>(a.zz, Z);
+}
+#endif
+
 // k * p by left-to-right double-and-add; k = 8 x u32 little-endian (canonical integer).
 // Used by the synthetic-input generator and the tests, not by the MSM hot path.
 template <class P> H2_HD xyzz xyzz_scalar_mul(const affine &p, const uint32_t (&k)[8]) {

@@ -587,12 +587,29 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_r1_kerne
     block_tree_sum<P>(sh, v, 0, threadIdx.x, 128);
     if (threadIdx.x == 0) st_xyzz(M.r1 + (uint64_t)w * p.r1_rows + row, v);
 }
-// Window value 2^(c w) S_w: one CTA per window, one thread per R1 row (<= 32 rows), tree sum.
-template <class P, class PS> __global__ void __launch_bounds__(32) msm_wsum_kernel(const MsmPlan p, const MsmBuffers M) {
+// Window value 2^(c w) S_w: one CTA per window, one QUAD of lanes per R1 row (<= 32 rows) for the shift
+// (xyzz_shift_quad), then a shared-memory tree sum over the rows.  (Msm::wsum_item is the serial form the host
+// emulation runs.)
+template <class P, class PS> __global__ void __launch_bounds__(128) msm_wsum_kernel(const MsmPlan p, const MsmBuffers M) {
     __shared__ xyzz sh[32];
-    xyzz v = Msm<P, PS>::wsum_item(p, M, blockIdx.x, threadIdx.x);
-    block_tree_sum<P>(sh, v, 0, threadIdx.x, 32);
-    if (threadIdx.x == 0) st_xyzz(M.wsum + blockIdx.x, v);
+    const uint32_t w = blockIdx.x, r = threadIdx.x >> 2;
+    xyzz v = xyzz_identity();
+    if (r < p.r1_rows) {
+        v = ld_xyzz(M.r1 + (uint64_t)w * p.r1_rows + r);
+        uint32_t shift = (p.fixed ? 0 : p.c * w) + (r >= 2 ? (r - 2) + p.l0 : 0);   // fixed: w is a set index, not a window
+        xyzz_shift_quad<P>(v, shift);
+    }
+    if ((threadIdx.x & 3u) == 0) st_xyzz(sh + r, v);
+    __syncthreads();
+    for (uint32_t off = 16; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            xyzz x = ld_xyzz(sh + threadIdx.x), o = ld_xyzz(sh + threadIdx.x + off);
+            xyzz_add<P>(x, o);
+            st_xyzz(sh + threadIdx.x, x);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(M.wsum + w, ld_xyzz(sh));
 }
 // Final: tree sum of the W window values
 template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_kernel(const MsmPlan p, const MsmBuffers M, uint32_t out_canonical) {
