@@ -413,9 +413,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     if (p.acc_levels > 2) LAUNCH(k_accumN, blocks_for(p.acc_threads[2], 128), 128, 0, s, p, M, 2u);
     if (p.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, p, M);
     // K5: bucket reduce and window combine
-    LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1, 128), 128, 0, s, p, M);
-    LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0), 128), 128, 0, s, p, M);
-    LAUNCH(k_r1, p.Wb * p.r1_rows, 128, 0, s, p, M);
+    LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1 * 4, 128), 128, 0, s, p, M);                    // quads
+    LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0) * 4, 128), 128, 0, s, p, M);
+    LAUNCH(k_r1, p.Wb * p.r1_rows, 4 * H2_R1_QUADS, 0, s, p, M);
     LAUNCH(k_wsum, p.Wb, 128, 0, s, p, M);
     LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
     return 0;

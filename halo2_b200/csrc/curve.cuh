@@ -200,6 +200,40 @@ H2_D fe fe_select(bool c, const fe &a, const fe &b) {
     for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
     return r;
 }
+// acc += b for a QUAD (four consecutive lanes holding the same a and b).  The 14 multiplies of add-2008-s are 4 deep:
+//   (u1, u2, s1, s2) -> (pp^2, r^2, zz zz', zzz zzz') -> (pp^3, q, zz3) -> (r (q - x3), s1 pp^3, zzz3)
+// one product per lane and level, results exchanged by shuffle.  Same lane-multiplies as the serial form, 4 multiply
+// latencies instead of 14 -- for the bucket-reduce / tree kernels, whose serial chains of additions are latency-bound.
+template <class P> H2_D void xyzz_add_quad(xyzz &a, const xyzz &b) {
+    if (xyzz_is_identity(b)) return;                     // all tests are uniform within the quad
+    if (xyzz_is_identity(a)) { a = b; return; }
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);
+    const bool s0 = sub == 0, s1_ = sub == 1, s2_ = sub == 2;
+    // level 1: u1 = a.x b.zz | u2 = b.x a.zz | s1 = a.y b.zzz | s2 = b.y a.zzz
+    fe r_ = fe_mul<P>(fe_select(s0, a.x, fe_select(s1_, b.x, fe_select(s2_, a.y, b.y))),
+                      fe_select(s0, b.zz, fe_select(s1_, a.zz, fe_select(s2_, b.zzz, a.zzz))));
+    fe u1 = quad_bcast(r_, 0, mask), u2 = quad_bcast(r_, 1, mask), s1 = quad_bcast(r_, 2, mask), s2 = quad_bcast(r_, 3, mask);
+    fe pp = fe_sub<P>(u2, u1);
+    fe r = fe_sub<P>(s2, s1);
+    if (fe_is_zero(pp)) {
+        if (fe_is_zero(r)) xyzz_double<P>(a);
+        else a = xyzz_identity();
+        return;
+    }
+    // level 2: pp^2 | r^2 | a.zz b.zz | a.zzz b.zzz
+    r_ = fe_mul<P>(fe_select(s0, pp, fe_select(s1_, r, fe_select(s2_, a.zz, a.zzz))),
+                   fe_select(s0, pp, fe_select(s1_, r, fe_select(s2_, b.zz, b.zzz))));
+    fe pp2 = quad_bcast(r_, 0, mask), rr = quad_bcast(r_, 1, mask), zz12 = quad_bcast(r_, 2, mask), zzz12 = quad_bcast(r_, 3, mask);
+    // level 3: pp^3 | q = u1 pp^2 | zz3 = zz12 pp^2
+    r_ = fe_mul<P>(fe_select(s0, pp, fe_select(s1_, u1, zz12)), pp2);
+    fe ppp = quad_bcast(r_, 0, mask), q = quad_bcast(r_, 1, mask), zz3 = quad_bcast(r_, 2, mask);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(rr, ppp), q), q);
+    // level 4: r (q - x3) | s1 pp^3 | zzz3 = zzz12 pp^3
+    r_ = fe_mul<P>(fe_select(s0, r, fe_select(s1_, s1, zzz12)), fe_select(s0, fe_sub<P>(q, x3), ppp));
+    fe t1 = quad_bcast(r_, 0, mask), t2 = quad_bcast(r_, 1, mask), zzz3 = quad_bcast(r_, 2, mask);
+    a.x = x3; a.y = fe_sub<P>(t1, t2);
+    a.zz = zz3; a.zzz = zzz3;
+}
 template <class P> H2_D void xyzz_shift_quad(xyzz &a, uint32_t k) {
     if (k == 0 || xyzz_is_identity(a)) return;          // uniform within the quad
     const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);

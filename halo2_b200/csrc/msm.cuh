@@ -162,6 +162,14 @@ struct MsmBuffers {
     jacobian *result;         // 1 (sets in the batched fixed-base mode)
 };
 
+// Addition policies of the reduce kernels: a serial chain of XYZZ additions is latency-bound (5.5 us per add for a
+// lone warp), so the device runs every chain on a QUAD of lanes (xyzz_add_quad: 4 multiply latencies instead of 14, same
+// lane-multiplies); all four lanes hold the same values and execute the same loads / stores.
+struct SerialAdd { template <class P> static H2_HD void add(xyzz &a, const xyzz &b) { xyzz_add<P>(a, b); } };
+#ifdef __CUDACC__
+struct QuadAdd { template <class P> static H2_D void add(xyzz &a, const xyzz &b) { xyzz_add_quad<P>(a, b); } };
+#endif
+
 // ---------------------------------------------------------------------------------------------
 template <class P, class PS> struct Msm {
     // signed window digit; `carry` threads through the windows in increasing order
@@ -321,17 +329,18 @@ template <class P, class PS> struct Msm {
 
     // ---- K5 level A: thread (w, u) reduces buckets [u L, u L + L) of window w:
     //   T = sum B[i],  E = sum (i - uL) B[i]    (running sums, no scalar multiplication)
-    static H2_HD void reduceA_body(const MsmPlan &p, const MsmBuffers &M, uint64_t tid) {
+    // ADD: SerialAdd (one thread per item; the host emulation) or QuadAdd (four lanes per item, device kernels)
+    template <class ADD = SerialAdd> static H2_HD void reduceA_body(const MsmPlan &p, const MsmBuffers &M, uint64_t tid) {
         if (tid >= (uint64_t)p.Wb * p.m1) return;
         uint32_t w = (uint32_t)(tid / p.m1), u = (uint32_t)(tid % p.m1);
         const uint32_t L = 1u << p.l0;
         const xyzz *A = M.bucket_sum + (uint64_t)w * p.B + (uint64_t)u * L;
         xyzz run = xyzz_identity(), acc = xyzz_identity();
         for (uint32_t i = L - 1; i > 0; i--) {
-            xyzz_add<P>(run, ld_xyzz(A + i));
-            xyzz_add<P>(acc, run);
+            ADD::template add<P>(run, ld_xyzz(A + i));
+            ADD::template add<P>(acc, run);
         }
-        xyzz_add<P>(run, ld_xyzz(A));
+        ADD::template add<P>(run, ld_xyzz(A));
         uint64_t o = (uint64_t)w * p.m1 + u;
         st_xyzz(M.ra_t + o, run);
         st_xyzz(M.ra_e + o, acc);
@@ -540,8 +549,8 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_accum_re
     }
 }
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_reduceA_kernel(const MsmPlan p, const MsmBuffers M) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    Msm<P, PS>::reduceA_body(p, M, t);
+    uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;       // one quad per chunk
+    Msm<P, PS>::template reduceA_body<QuadAdd>(p, M, t);
 }
 
 // Shared-memory tree sum of one value per thread over the `width` (power of two) lanes of a row;
@@ -558,10 +567,23 @@ template <class P> __device__ __forceinline__ void block_tree_sum(xyzz *sh, xyzz
         __syncthreads();
     }
 }
-// R0: one thread per (window, 8-block, row): a short serial sum keeps every lane busy (a shared-memory
+// The same for quads: entry `qd` is held by the four lanes of quad qd; every thread of the CTA must call it.
+template <class P> __device__ __forceinline__ void quad_tree_sum(xyzz *sh, xyzz &v, uint32_t qd, uint32_t quads) {
+    st_xyzz(sh + qd, v);
+    __syncthreads();
+    for (uint32_t off = quads >> 1; off > 0; off >>= 1) {
+        if (qd < off) {
+            xyzz o = ld_xyzz(sh + qd + off);
+            xyzz_add_quad<P>(v, o);
+            st_xyzz(sh + qd, v);
+        }
+        __syncthreads();
+    }
+}
+// R0: one QUAD per (window, 8-block, row): a short serial sum keeps every quad busy (a shared-memory
 // tree runs its adds at 1/2 .. 1/32 lane utilisation).
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_r0_kernel(const MsmPlan p, const MsmBuffers M) {
-    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t tid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const uint32_t rows = 2 + p.bits0;
     if (tid >= (uint64_t)p.Wb * p.nb0 * rows) return;
     uint32_t row = (uint32_t)(tid % rows);
@@ -571,20 +593,21 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_r0_kerne
     for (uint32_t lane = 0; lane < (1u << H2_R0_LOG); lane++) {
         if (row >= 2 && !((lane >> (row - 2)) & 1u)) continue;
         xyzz c = Msm<P, PS>::r0_contrib(p, M, w, blk, row, lane);
-        xyzz_add<P>(v, c);
+        xyzz_add_quad<P>(v, c);
     }
     st_xyzz(M.r0 + ((uint64_t)w * p.nb0 + blk) * H2_R0_ROWS + row, v);
 }
-// R1: one CTA per (window, output row): 128 threads stride over the window's nb0 blocks
-template <class P, class PS> __global__ void __launch_bounds__(128) msm_r1_kernel(const MsmPlan p, const MsmBuffers M) {
-    __shared__ xyzz sh[128];
-    uint32_t w = blockIdx.x / p.r1_rows, row = blockIdx.x % p.r1_rows;
+// R1: one CTA per (window, output row): 128 quads stride over the window's nb0 blocks, then a tree over the quads
+#define H2_R1_QUADS 128
+template <class P, class PS> __global__ void __launch_bounds__(4 * H2_R1_QUADS) msm_r1_kernel(const MsmPlan p, const MsmBuffers M) {
+    __shared__ xyzz sh[H2_R1_QUADS];
+    const uint32_t w = blockIdx.x / p.r1_rows, row = blockIdx.x % p.r1_rows, qd = threadIdx.x >> 2;
     xyzz v = xyzz_identity();
-    for (uint32_t blk = threadIdx.x; blk < p.nb0; blk += 128) {
+    for (uint32_t blk = qd; blk < p.nb0; blk += H2_R1_QUADS) {
         xyzz c = Msm<P, PS>::r1_contrib(p, M, w, row, blk);
-        xyzz_add<P>(v, c);
+        xyzz_add_quad<P>(v, c);
     }
-    block_tree_sum<P>(sh, v, 0, threadIdx.x, 128);
+    quad_tree_sum<P>(sh, v, qd, H2_R1_QUADS);
     if (threadIdx.x == 0) st_xyzz(M.r1 + (uint64_t)w * p.r1_rows + row, v);
 }
 // Window value 2^(c w) S_w: one CTA per window, one QUAD of lanes per R1 row (<= 32 rows) for the shift
@@ -599,28 +622,20 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_wsum_ker
         uint32_t shift = (p.fixed ? 0 : p.c * w) + (r >= 2 ? (r - 2) + p.l0 : 0);   // fixed: w is a set index, not a window
         xyzz_shift_quad<P>(v, shift);
     }
-    if ((threadIdx.x & 3u) == 0) st_xyzz(sh + r, v);
-    __syncthreads();
-    for (uint32_t off = 16; off > 0; off >>= 1) {
-        if (threadIdx.x < off) {
-            xyzz x = ld_xyzz(sh + threadIdx.x), o = ld_xyzz(sh + threadIdx.x + off);
-            xyzz_add<P>(x, o);
-            st_xyzz(sh + threadIdx.x, x);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) st_xyzz(M.wsum + w, ld_xyzz(sh));
+    quad_tree_sum<P>(sh, v, r, 32);
+    if (threadIdx.x == 0) st_xyzz(M.wsum + w, v);
 }
-// Final: tree sum of the W window values
+// Final: tree sum of the W window values (16 quads)
 template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_kernel(const MsmPlan p, const MsmBuffers M, uint32_t out_canonical) {
-    __shared__ xyzz sh[64];
+    __shared__ xyzz sh[16];
     if (p.fixed) {   // one result per set (the sets are independent MSMs)
         for (uint32_t set = threadIdx.x; set < p.sets; set += 64) Msm<P, PS>::finish(M, ld_xyzz(M.wsum + set), out_canonical, set);
         return;
     }
+    const uint32_t qd = threadIdx.x >> 2;
     xyzz v = xyzz_identity();
-    for (uint32_t w = threadIdx.x; w < p.Wb; w += 64) { xyzz c = ld_xyzz(M.wsum + w); xyzz_add<P>(v, c); }
-    block_tree_sum<P>(sh, v, 0, threadIdx.x, 64);
+    for (uint32_t w = qd; w < p.Wb; w += 16) { xyzz c = ld_xyzz(M.wsum + w); xyzz_add_quad<P>(v, c); }
+    quad_tree_sum<P>(sh, v, qd, 16);
     if (threadIdx.x == 0) Msm<P, PS>::finish(M, v, out_canonical);
 }
 
