@@ -59,6 +59,8 @@ struct Context {
     cudaEvent_t last_use = nullptr;
     bool have_last = false;
     uint32_t window_override = 0;
+    const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
+    uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
     // MSM scratch
     DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
@@ -173,6 +175,23 @@ extern "C" int h2_shutdown(void) {
 extern "C" int h2_set_glv(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_ctx.glv_on = on ? 1u : 0u;
+    return 0;
+}
+extern "C" int h2_set_sort_mode(int exact_only) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ctx.sort_bins = exact_only ? 0u : 1u;
+    return 0;
+}
+// test hook: flags of the most recent MSM -- bit 0: some bucket was split into several work items, bit 1: the exact
+// sort ran (bin overflow, or no bins).  Synchronises the device.
+extern "C" int h2_test_last_msm_flags(uint32_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (!g_ctx.last_flags) return fail("h2_test_last_msm_flags: no MSM has run");
+    uint32_t f[2];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(f, g_ctx.last_flags, sizeof f, cudaMemcpyDeviceToHost));
+    *out = (f[0] ? 1u : 0u) | (f[1] ? 2u : 0u);
     return 0;
 }
 extern "C" int h2_set_window_bits(uint32_t c) {
@@ -320,14 +339,14 @@ static inline uint32_t blocks_for(uint64_t n, uint32_t bs) { return (uint32_t)((
 // ------------------------------------------------------------------------------------------------
 // MSM pipeline
 // ------------------------------------------------------------------------------------------------
-static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s) {
+static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s, const uint32_t *only_if = nullptr) {
     const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
     uint32_t nb = (uint32_t)((n + per_block - 1) / per_block);
     if (g_ctx.scan_blocks.ensure((size_t)nb * 4 + 16)) return 1;
     uint32_t *bs = g_ctx.scan_blocks.as<uint32_t>();
-    LAUNCH(scan_block_sums_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs);
-    LAUNCH(scan_single_block_kernel, 1, H2_SCAN_BLOCK, 0, s, bs, nb);
-    LAUNCH(scan_apply_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs);
+    LAUNCH(scan_block_sums_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs, only_if);
+    LAUNCH(scan_single_block_kernel, 1, H2_SCAN_BLOCK, 0, s, bs, nb, only_if);
+    LAUNCH(scan_apply_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs, only_if);
     return 0;
 }
 
@@ -348,13 +367,13 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     const uint32_t glv = (!fixed && X.glv_on && n < (1ull << 30)) ? 1u : 0u;
     if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
     if (c > 24) return fail("msm: window bits > 24");
-    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets);
+    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets, X.sort_bins ? 0u : H2_MSM_NO_BINS);
     if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 32))) return 1;
     if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
-    if (p.max_refs >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
+    if (p.ref_space >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
     if (scalars_mont && X.scal_canon.ensure(n * p.sets * sizeof(fe))) return 1;
     const size_t small_words = 2 * (p.T + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
-    if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(p.G * 4) || X.refs.ensure(p.max_refs * 4) ||
+    if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(2 * p.G * 4) || X.refs.ensure(p.ref_space * 4) ||
         X.size_hist.ensure(small_words * 4) || X.items.ensure(p.max_items * sizeof(uint2)) ||
         X.bucket_sum.ensure(p.G * sizeof(xyzz)) || X.pkey.ensure((p.part_total + 1) * 4) || X.pstart.ensure((p.part_total + 1) * 4) ||
         X.pend.ensure((p.part_total + 1) * 4) || X.ppt.ensure((p.part_total + 1) * sizeof(xyzz)) ||
@@ -365,9 +384,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     MsmBuffers M;
     M.scalars = d_scalars; M.bases = d_bases; M.bases_phi = X.bases_phi.as<affine>(); M.glv_parts = X.glv_parts.as<uint32_t>(); M.scalars_mont = scalars_mont ? 1u : 0u;
     M.scal_canon = X.scal_canon.as<fe>();
-    M.counts = X.counts.as<uint32_t>(); M.cursor = X.cursor.as<uint32_t>();
+    M.counts = X.counts.as<uint32_t>(); M.cursor = X.cursor.as<uint32_t>(); M.cursor2 = M.cursor + p.G;
     M.refs = X.refs.as<uint32_t>();
-    M.size_hist = X.size_hist.as<uint32_t>(); M.size_cursor = M.size_hist + (p.T + 2); M.flags = M.size_cursor + (p.T + 2);
+    M.size_hist = X.size_hist.as<uint32_t>(); M.size_cursor = M.size_hist + (p.T + 2); M.flags = M.size_cursor + (p.T + 2); X.last_flags = M.flags;
     M.items = X.items.as<uint2>();
     M.bucket_sum = X.bucket_sum.as<xyzz>();
     M.pkey = X.pkey.as<uint32_t>(); M.pstart = X.pstart.as<uint32_t>(); M.pend = X.pend.as<uint32_t>(); M.ppt = X.ppt.as<xyzz>();
@@ -375,11 +394,12 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     M.wsum = X.wsum.as<xyzz>(); M.result = d_out;
 
     CU(cudaMemsetAsync(M.counts, 0, (p.G + 1) * 4, s));
-    CU(cudaMemsetAsync(M.cursor, 0, p.G * 4, s));
+    CU(cudaMemsetAsync(M.cursor, 0, 2 * p.G * 4, s));
     CU(cudaMemsetAsync(M.size_hist, 0, small_words * 4, s));
     CU(cudaMemsetAsync(M.bucket_sum, 0, p.G * sizeof(xyzz), s));
     CU(cudaMemsetAsync(M.pkey, 0xff, p.part_total * 4, s));
 
+    auto k_bin = msm_bin_kernel<P, PS>;
     auto k_hist = msm_hist_kernel<P, PS>;
     auto k_scatter = msm_scatter_kernel<P, PS>;
     auto k_ihist = msm_item_hist_kernel<P, PS>;
@@ -394,8 +414,12 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     auto k_wsum = msm_wsum_kernel<P, PS>;
     auto k_final = msm_final_kernel<P, PS>;
     // K2/K3: counting sort of the (point, window) references by bucket
+    // single pass into per-bucket bins; the exact histogram / scan / scatter kernels run only if a bin overflowed
+    // (flags[1], set by the bin kernel) or if there are no bins (set here)
+    if (p.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
+    else LAUNCH(k_bin, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
     LAUNCH(k_hist, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
-    if (exclusive_scan_u32(M.counts, p.G + 1, s)) return 1;
+    if (exclusive_scan_u32(M.counts, p.G + 1, s, M.flags + 1)) return 1;
     LAUNCH(k_scatter, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
     // K4: work items (one per bucket, oversized buckets split), largest first
     LAUNCH(k_ihist, blocks_for(p.G, 256), 256, 0, s, p, M);
@@ -433,10 +457,15 @@ static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const 
 static uint32_t table_window(size_t n) {
     uint32_t lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
-    uint32_t c = lg + 2;
-    if (c < 8) c = 8;
-    if (c > 20) c = 20;
-    return c;
+    // candidates are the window sizes whose TOP window is well filled (scalars have 254 significant bits:
+    // 254 - (W - 1) c = 6, 14, 14, 16, 14 bits for c = 8, 15, 16, 17, 20): a top window of 1-2 bits would send n / 4
+    // references to a handful of shared buckets and defeat the single-pass sort
+    uint32_t want = lg + 2;
+    if (want <= 9) return 8;
+    if (want <= 15) return 15;
+    if (want == 16) return 16;
+    if (want <= 18) return 17;
+    return 20;
 }
 static int build_table(BaseSet *b, uint32_t c, cudaStream_t s) {
     if (c == 0) c = table_window(b->n);

@@ -46,6 +46,11 @@ struct MsmPlan {
     uint64_t n;          // number of (scalar, base) pairs
     uint32_t c;          // window bits
     uint32_t glv;        // 1: scalars are split k = k1 + k2 lambda (glv.cuh); point i contributes P_i (k1) and phi(P_i) (k2)
+    uint32_t cap;        // bin capacity of the single-pass sort (0: exact two-pass sort only)
+    uint32_t cap_top;    // ... of the top window's bins (its digits are fewer bits wide and, with GLV, not uniform)
+    uint64_t g_top;      // first bucket of the top window (= G in the fixed-base mode: no separate top region)
+    uint32_t top_bins;   // populated buckets of the top window: digits 1 .. top_bins
+    uint64_t ref_space;  // entries of the refs array
     uint32_t W;          // windows = ceil(256 / c), or ceil(128 / c) with the GLV split
     uint32_t B;          // buckets per window = 2^(c-1)
     uint32_t fixed;      // 1: bases come from a precomputed table T[w][i] = 2^(c w) G_i (resident Params
@@ -84,12 +89,13 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
     uint64_t n_eff = glv ? 2 * n : n;
     if (n_eff < 64) return 4;
     if (n_eff < (1ull << 10)) return 8;
-    if (n_eff < (1ull << 14)) return 13;
+    if (n_eff < (1ull << 17)) return 13;     // measured: 13 beats 16 up to n = 2^15 (GLV), tools/sweep_window.py
     return 16;
 }
 
+#define H2_MSM_NO_BINS 0xffffffffu
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
-                          uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1) {
+                          uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1, uint32_t force_cap = 0) {
     p.n = n; p.c = c;
     p.glv = fixed ? 0u : glv;
     // GLV sub-scalars are < 2^127 (glv.cuh): with W c >= 128 the top window's raw digit is < 2^(c-1), so it
@@ -105,9 +111,46 @@ inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t =
     while (T > 32 && p.max_refs / T < 65536) T >>= 1;
     p.T = force_t ? force_t : T;
     p.max_items = p.G + p.max_refs / p.T + 1;
+    // Single-pass sort: bucket g owns a bin of `cap` references (see Msm::bucket_lo).  With mean load lambda the capacity
+    // lambda + 8 sqrt(lambda) + 16 is never reached by uniformly random digits; inputs that do overflow a bin
+    // (repeated scalars, 0/1 columns) fall back to the exact histogram / scan / scatter sort (flags[1]).
+    // The top window of a one-shot MSM is different: it holds top_bits < c bits, so its digits crowd into 2^top_bits
+    // buckets, and GLV halves (alpha v1 + beta v2, alpha, beta uniform in [-1/2, 1/2)) have trapezoid densities peaking
+    // near zero -- its low buckets receive 2^127 (1 / max(a1, a2) + 1 / max(|b1|, b2)) = 2.6 x the load of a uniform
+    // 127-bit value.  It gets its own bin count and capacity.
+    {
+        auto capacity = [](uint64_t lam) { uint64_t rt = 0; while ((rt + 1) * (rt + 1) <= lam) rt++; return (lam + 8 * rt + 16 + 7) & ~7ull; };
+        const uint64_t n_eff = (p.glv ? 2 : 1) * n;
+        uint64_t cap, cap_top = 0, top_bins = 0;
+        p.g_top = p.G;
+        if (fixed || p.W < 2) {
+            // all windows share one bucket set; the top window (254 - (W - 1) c bits) adds n >> top_bits references to
+            // each of its low buckets.  (When that is far above the mean the bins overflow and the exact sort runs:
+            // table_window() avoids such window sizes.)
+            uint64_t lam = (p.max_refs + p.G - 1) / p.G;
+            const int tb = 254 - (int)((p.W - 1) * c);
+            if (fixed && tb > 0 && tb < (int)c - 1 && (n >> tb) <= 4 * lam + 16) lam += (n >> tb) + 1;
+            cap = capacity(lam);
+        } else {
+            // scalars are < 2^254 (1 + 2^-129): 254 significant bits; GLV halves < 2^127
+            const int bits = p.glv ? 127 : 254, tb = bits - (int)((p.W - 1) * c), top_bits = tb < 0 ? 0 : (tb > (int)c - 1 ? (int)c - 1 : tb);
+            cap = capacity((n_eff + p.B - 1) / p.B);
+            top_bins = (1ull << top_bits) + 1 < p.B ? (1ull << top_bits) + 1 : p.B;
+            uint64_t lam_top = ((p.glv ? n * 53 / 10 : n) >> top_bits) + 1;
+            cap_top = capacity(lam_top);
+            if (cap_top > n_eff + 8) cap_top = (n_eff + 8) & ~7ull;
+            p.g_top = (uint64_t)(p.W - 1) * p.B;
+        }
+        uint64_t space = p.g_top * cap + top_bins * cap_top;
+        if (force_cap == H2_MSM_NO_BINS || space >= (1ull << 32)) { cap = 0; cap_top = 0; }
+        else if (force_cap) { cap = force_cap; cap_top = cap_top ? force_cap : 0; }
+        p.cap = (uint32_t)cap; p.cap_top = (uint32_t)cap_top; p.top_bins = (uint32_t)top_bins;
+        space = p.g_top * p.cap + (uint64_t)p.top_bins * p.cap_top;
+        p.ref_space = space > p.max_refs ? space : p.max_refs;
+    }
     // partial slots: slot(start, chunk) = 2 * (start / T) + (chunk > 0), see item_slot()
     uint32_t lv = 1;
-    uint64_t slots = 2 * (p.max_refs / p.T + 1);
+    uint64_t slots = 2 * (p.ref_space / p.T + 1);
     p.acc_chunk[0] = p.T; p.acc_threads[0] = p.max_items; p.acc_slots[0] = p.max_refs; p.part_offset[0] = 0;
     p.part_offset[1] = 0;
     p.part_total = slots;
@@ -146,7 +189,8 @@ struct MsmBuffers {
     fe *scal_canon;           // n (only when scalars_mont)
     uint32_t *glv_parts;      // n x 8 words: |k1| (4 limbs, sign in bit 127) then |k2|   (GLV only)
     uint32_t *counts;         // G + 1  (histogram, then exclusive offsets after the scan)
-    uint32_t *cursor;         // G
+    uint32_t *cursor;         // G   single-pass sort: bin fill (= bucket size)
+    uint32_t *cursor2;        // G   exact sort: scatter cursor
     uint32_t *refs;           // max_refs   point index | sign << 31, sorted by bucket id
     uint32_t *size_hist;      // T + 2: [s] = number of work items of s references; [T + 1] = item count
     uint32_t *size_cursor;    // T + 1
@@ -249,9 +293,28 @@ template <class P, class PS> struct Msm {
     static H2_HD uint64_t item_slot(const MsmPlan &p, uint32_t start, bool first_piece) {
         return 2ull * (start / p.T) + (first_piece ? 1 : 0);
     }
+    // references of bucket g: refs[bucket_lo, bucket_hi).  flags[1] == 0: binned layout of the single-pass sort
+    // (cursor[g] = size); flags[1] != 0: compact layout of the exact sort (counts = exclusive offsets).
+    // bin of bucket g in the single-pass layout; false if g has no bin (a top-window digit beyond top_bins)
+    static H2_HD bool bin_of(const MsmPlan &p, uint64_t g, uint32_t &lo, uint32_t &cap) {
+        if (g < p.g_top) { lo = (uint32_t)(g * p.cap); cap = p.cap; return true; }
+        const uint64_t b = g - p.g_top;
+        lo = (uint32_t)(p.g_top * p.cap + b * p.cap_top); cap = p.cap_top;
+        return b < p.top_bins;
+    }
+    static H2_HD uint32_t bucket_lo(const MsmPlan &p, const MsmBuffers &M, uint64_t g) {
+        if (M.flags[1]) return M.counts[g];
+        uint32_t lo, cap;
+        return bin_of(p, g, lo, cap) ? lo : 0u;
+    }
+    static H2_HD uint32_t bucket_hi(const MsmPlan &p, const MsmBuffers &M, uint64_t g) {
+        if (M.flags[1]) return M.counts[g + 1];
+        uint32_t lo, cap;
+        return bin_of(p, g, lo, cap) ? lo + M.cursor[g] : 0u;   // (a bucket without a bin is empty unless the sort overflowed)
+    }
     // size histogram: thread per bucket
     static H2_HD void count_items(const MsmPlan &p, const MsmBuffers &M, uint64_t g, uint32_t &nfull, uint32_t &rem) {
-        uint32_t cnt = M.counts[g + 1] - M.counts[g];
+        uint32_t cnt = bucket_hi(p, M, g) - bucket_lo(p, M, g);
         nfull = cnt / p.T; rem = cnt % p.T;
         if (cnt > p.T) M.flags[0] = 1;
     }
@@ -269,8 +332,9 @@ template <class P, class PS> struct Msm {
 
     struct Flusher {
         const MsmBuffers *M;
+        const MsmPlan *p;
         H2_HD void flush(uint32_t g, uint32_t a, uint32_t b, const xyzz &acc, uint64_t slot) {
-            uint32_t lo = M->counts[g], hi = M->counts[g + 1];
+            uint32_t lo = bucket_lo(*p, *M, g), hi = bucket_hi(*p, *M, g);
             if (a == lo && b == hi) {
                 st_xyzz(M->bucket_sum + g, acc);
             } else {
@@ -284,7 +348,7 @@ template <class P, class PS> struct Msm {
     static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
         if (t >= M.size_hist[p.T + 1]) return;
         uint2 it = M.items[t];
-        const uint32_t g = it.x, start = it.y, lo = M.counts[g], hi = M.counts[g + 1];
+        const uint32_t g = it.x, start = it.y, lo = bucket_lo(p, M, g), hi = bucket_hi(p, M, g);
         const uint32_t end = start + p.T < hi ? start + p.T : hi;
         xyzz acc = xyzz_identity();
         for (uint32_t pos = start; pos < end; pos++) {
@@ -295,7 +359,7 @@ template <class P, class PS> struct Msm {
             if (ref >> 31) b.y = fe_neg<P>(b.y);
             xyzz_add_mixed<P>(acc, b);
         }
-        Flusher F; F.M = &M;
+        Flusher F; F.M = &M; F.p = &p;
         F.flush(g, start, end, acc, p.part_offset[1] + item_slot(p, start, start == lo));
     }
 
@@ -308,7 +372,7 @@ template <class P, class PS> struct Msm {
         uint64_t start = t * K;
         uint64_t end = start + K < slots ? start + K : slots;
         if (start >= end) return;
-        Flusher F; F.M = &M;
+        Flusher F; F.M = &M; F.p = &p;
         const uint64_t out_base = (lv + 1 < p.acc_levels ? p.part_offset[lv + 1] : 0) + 2 * t;
         bool have = false;
         xyzz acc = xyzz_identity();
@@ -320,11 +384,11 @@ template <class P, class PS> struct Msm {
                 xyzz_add<P>(acc, ld_xyzz(M.ppt + s));
                 b = M.pend[s];
             } else {
-                if (have) F.flush(cur, a, b, acc, out_base + (a > M.counts[cur] ? 0 : 1));
+                if (have) F.flush(cur, a, b, acc, out_base + (a > bucket_lo(p, M, cur) ? 0 : 1));
                 have = true; cur = g; a = M.pstart[s]; b = M.pend[s]; acc = ld_xyzz(M.ppt + s);
             }
         }
-        if (have) F.flush(cur, a, b, acc, out_base + (a > M.counts[cur] ? 0 : 1));
+        if (have) F.flush(cur, a, b, acc, out_base + (a > bucket_lo(p, M, cur) ? 0 : 1));
     }
 
     // ---- K5 level A: thread (w, u) reduces buckets [u L, u L + L) of window w:
@@ -449,7 +513,46 @@ template <bool WANT> __device__ __forceinline__ uint32_t warp_inc(uint32_t *ctr,
 
 // digit loops are written out (not through for_each_digit) because the warp-synchronous atomics need
 // every lane to execute every (half, window) step
+// Single-pass sort: every (point, window) reference goes straight to its bucket's bin.  A full bin raises flags[1];
+// the exact-sort kernels below then redo the job (they return at once otherwise).
+template <class P, class PS> __global__ void __launch_bounds__(256) msm_bin_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (M.flags[1]) return;                      // exact sort requested by the host
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = i < p.n * p.sets;
+    const uint64_t set = p.fixed && in ? i / p.n : 0, idx = p.fixed && in ? i % p.n : i;
+    uint32_t part[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}}, sneg[2] = {0, 0};
+    const uint32_t halves = p.glv ? 2u : 1u;
+    if (in) Msm<P, PS>::load_parts(p, M, i, true, part, sneg);
+    bool full = false;
+    for (uint32_t e = 0; e < halves; e++) {
+        uint32_t carry = 0;
+        for (uint32_t w0 = 0; w0 < p.W; w0 += 4) {
+            uint32_t slot[4], gid[4], ref[4];
+            bool act[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t w = w0 + k;
+                int32_t d = w < p.W ? Msm<P, PS>::next_digit(part[e], w, p.c, carry) : 0;
+                act[k] = in && d != 0;
+                uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                gid[k] = (uint32_t)((uint64_t)(p.fixed ? set : (w < p.W ? w : 0)) * p.B + (act[k] ? mag - 1 : 0));
+                ref[k] = ((uint32_t)idx + (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0)) | (e << 30) |
+                         ((((uint32_t)(d < 0)) ^ sneg[e]) << 31);
+                slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (act[k]) {
+                    uint32_t lo, cap;
+                    if (Msm<P, PS>::bin_of(p, gid[k], lo, cap) && slot[k] < cap) M.refs[lo + slot[k]] = ref[k];
+                    else full = true;
+                }
+        }
+    }
+    if (full) M.flags[1] = 1;
+}
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (!M.flags[1]) return;                     // the single-pass sort succeeded
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool in = i < p.n * p.sets;
     const uint64_t set = p.fixed && in ? i / p.n : 0;
@@ -468,6 +571,7 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_hist_ker
     }
 }
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (!M.flags[1]) return;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool in = i < p.n * p.sets;
     const uint64_t set = p.fixed && in ? i / p.n : 0, idx = p.fixed && in ? i % p.n : i;
@@ -489,7 +593,7 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_scatter_
                 gid[k] = (uint32_t)((uint64_t)(p.fixed ? set : (w < p.W ? w : 0)) * p.B + (act[k] ? mag - 1 : 0));
                 ref[k] = ((uint32_t)idx + (uint32_t)(p.fixed && w < p.W ? (uint64_t)w * p.stride : 0)) | (e << 30) |
                          ((((uint32_t)(d < 0)) ^ sneg[e]) << 31);
-                slot[k] = warp_inc<true>(M.cursor + gid[k], act[k]);
+                slot[k] = warp_inc<true>(M.cursor2 + gid[k], act[k]);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -519,7 +623,7 @@ template <class P, class PS> __global__ void msm_item_bases_kernel(const MsmPlan
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_place_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nfull = 0, rem = 0, lo = 0;
-    if (g < p.G) { Msm<P, PS>::count_items(p, M, g, nfull, rem); lo = M.counts[g]; }
+    if (g < p.G) { Msm<P, PS>::count_items(p, M, g, nfull, rem); lo = Msm<P, PS>::bucket_lo(p, M, g); }
     if (nfull) {
         uint32_t at = atomicAdd(M.size_cursor + p.T, nfull);
         for (uint32_t k = 0; k < nfull; k++) M.items[at + k] = make_uint2((uint32_t)g, lo + k * p.T);
@@ -642,8 +746,9 @@ template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_ker
 // exclusive scan of counts[0..G] in place (counts[G] becomes the total), three small kernels
 #define H2_SCAN_BLOCK 1024
 #define H2_SCAN_ITEMS 8
-__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_block_sums_kernel(const uint32_t *in, uint64_t n, uint32_t *block_sums) {
+__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_block_sums_kernel(const uint32_t *in, uint64_t n, uint32_t *block_sums, const uint32_t *only_if) {
     __shared__ uint32_t sh[32];
+    if (only_if && !*only_if) return;
     uint64_t base = (uint64_t)blockIdx.x * H2_SCAN_BLOCK * H2_SCAN_ITEMS;
     uint32_t s = 0;
     for (int k = 0; k < H2_SCAN_ITEMS; k++) {
@@ -659,10 +764,11 @@ __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_block_sums_kernel(const ui
         if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
     }
 }
-__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_single_block_kernel(uint32_t *a, uint32_t n) {
+__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_single_block_kernel(uint32_t *a, uint32_t n, const uint32_t *only_if) {
     // exclusive scan of a[0..n) by one block, n arbitrary (loops in tiles of blockDim)
     __shared__ uint32_t sh[H2_SCAN_BLOCK];
     __shared__ uint32_t carry_s;
+    if (only_if && !*only_if) return;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     for (uint32_t base = 0; base < n; base += H2_SCAN_BLOCK) {
@@ -683,8 +789,9 @@ __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_single_block_kernel(uint32
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_apply_kernel(uint32_t *a, uint64_t n, const uint32_t *block_offsets) {
+__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_apply_kernel(uint32_t *a, uint64_t n, const uint32_t *block_offsets, const uint32_t *only_if) {
     __shared__ uint32_t sh[H2_SCAN_BLOCK];
+    if (only_if && !*only_if) return;
     uint64_t base = (uint64_t)blockIdx.x * H2_SCAN_BLOCK * H2_SCAN_ITEMS + (uint64_t)threadIdx.x * H2_SCAN_ITEMS;
     uint32_t v[H2_SCAN_ITEMS], s = 0;
     for (int k = 0; k < H2_SCAN_ITEMS; k++) { v[k] = base + k < n ? a[base + k] : 0; s += v[k]; }

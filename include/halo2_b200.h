@@ -103,6 +103,10 @@ int h2_ipa_finish(uint64_t session, int repr, void *out_c_b);
 
 /* Window size override for the sweep in BASELINE.json config 3 (0 = automatic). */
 int h2_set_window_bits(uint32_t c);
+/* Reference sort of the MSM: by default every (point, window) reference is binned in ONE pass into fixed-capacity
+ * per-bucket bins, with an automatic fallback to the exact histogram / scan / scatter sort when a bin overflows
+ * (heavily repeated scalars).  exact_only != 0 forces the exact sort.  Same result; for A/B runs and tests. */
+int h2_set_sort_mode(int exact_only);
 /* GLV endomorphism split (k = k1 + k2 lambda, 129-bit halves; on by default) for MSMs without a
  * window table.  Same result; switchable for A/B measurements and tests. */
 int h2_set_glv(int on);
@@ -145,6 +149,9 @@ int h2_ntt_clear_cache(void);
 int h2_dev_gen_points(int curve, uint64_t seed, uint64_t first, size_t n, void *d_out, void *stream);
 /* In-place canonical <-> Montgomery conversion of n field elements on the device. */
 int h2_dev_convert(int field, void *d_a, size_t n, int to_montgomery, void *stream);
+/* Test hook: bit 0 = the most recent MSM split some bucket over several work items, bit 1 = it used the exact
+ * (two-pass) sort.  Synchronises the device. */
+int h2_test_last_msm_flags(uint32_t *out);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */
 int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out);

@@ -5,6 +5,8 @@
 #include "msm.cuh"
 using namespace h2;
 
+static uint32_t g_force_cap = 0;      // 0 auto, H2_MSM_NO_BINS exact sort only, else the bin capacity (tests force overflows)
+extern "C" void emu_msm_set_cap(uint32_t cap) { g_force_cap = cap; }
 template <class P, class PS>
 static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c, int scalars_mont,
                    uint32_t force_t, uint32_t force_kn, int fixed, int glv, uint8_t *out_xyz, uint32_t sets = 1) {
@@ -13,7 +15,7 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     MsmPlan p;
     if (!c) c = msm_default_window(n, glv ? 1u : 0u);
     if (fixed && c < 4) c = 4;      // table windows: W = ceil(256 / c) <= 64
-    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u, sets);
+    msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u, sets, g_force_cap);
     if (p.acc_levels > H2_MSM_MAX_LEVELS) return -2;
     std::vector<fe> sc(ns ? ns : 1), sc_canon(ns ? ns : 1);
     std::vector<affine> bs(n ? n : 1);
@@ -33,8 +35,8 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         table.resize((size_t)p.W * p.stride);
         for (size_t i = 0; i < n; i++) Msm<P, PS>::table_body(bs.data(), table.data(), n, p.stride, p.c, p.W, i);
     }
-    std::vector<uint32_t> counts(p.G + 1, 0), cursor(p.G, 0), refs(p.max_refs ? p.max_refs : 1), size_hist(p.T + 2, 0),
-        size_cursor(p.T + 1, 0), flags(4, 0);
+    std::vector<uint32_t> counts(p.G + 1, 0), cursor(p.G, 0), cursor2(p.G, 0), refs(p.ref_space ? p.ref_space : 1), size_hist(p.T + 2, 0),
+        size_cursor(p.T + 1, 0), flags(8, 0);
     std::vector<uint2> items(p.max_items);
     std::vector<xyzz> bucket_sum(p.G, xyzz_identity());
     size_t pt = p.part_total ? p.part_total : 1;
@@ -46,22 +48,32 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     std::vector<uint32_t> glv_parts((ns ? ns : 1) * 8 + 4);
     M.glv_parts = glv_parts.data();
     M.scalars = sc.data(); M.bases = fixed ? table.data() : bs.data(); M.bases_phi = phi.data(); M.scalars_mont = scalars_mont; M.scal_canon = sc_canon.data();
-    M.counts = counts.data(); M.cursor = cursor.data(); M.refs = refs.data();
+    M.counts = counts.data(); M.cursor = cursor.data(); M.cursor2 = cursor2.data(); M.refs = refs.data();
     M.size_hist = size_hist.data(); M.size_cursor = size_cursor.data(); M.flags = flags.data(); M.items = items.data();
     M.bucket_sum = bucket_sum.data(); M.pkey = pkey.data(); M.pstart = pstart.data(); M.pend = pend.data();
     M.ppt = ppt.data(); M.ra_t = ra_t.data(); M.ra_e = ra_e.data(); M.r0 = r0.data(); M.r1 = r1.data();
     M.wsum = wsum.data(); M.result = result.data();
     typedef Msm<P, PS> K;
-    // K2 histogram
-    for (size_t i = 0; i < ns; i++) {
-        bool ok = K::for_each_digit(p, M, i, true, [&](uint32_t g, uint32_t) { counts[g]++; });
-        if (!ok) return -3;
-    }
-    uint32_t run = 0;
-    for (uint64_t g = 0; g <= p.G; g++) { uint32_t v = counts[g]; counts[g] = run; run += v; }
-    // K3 scatter (reverse order to mimic the arbitrary order atomics give)
-    for (size_t ii = ns; ii-- > 0;) {
-        K::for_each_digit(p, M, ii, false, [&](uint32_t g, uint32_t ref) { refs[counts[g] + cursor[g]++] = ref; });
+    // single-pass binned sort (reverse order to mimic the arbitrary order atomics give); a full bin -> flags[1]
+    if (p.cap == 0) flags[1] = 1;
+    else
+        for (size_t ii = ns; ii-- > 0;) {
+            bool ok = K::for_each_digit(p, M, ii, true, [&](uint32_t g, uint32_t ref) {
+                uint32_t slot = cursor[g]++, lo, cap;
+                if (K::bin_of(p, g, lo, cap) && slot < cap) refs[lo + slot] = ref; else flags[1] = 1;
+            });
+            if (!ok) return -3;
+        }
+    if (flags[1]) {   // exact sort: K2 histogram, scan, K3 scatter
+        for (size_t i = 0; i < ns; i++) {
+            bool ok = K::for_each_digit(p, M, i, true, [&](uint32_t g, uint32_t) { counts[g]++; });
+            if (!ok) return -3;
+        }
+        uint32_t run = 0;
+        for (uint64_t g = 0; g <= p.G; g++) { uint32_t v = counts[g]; counts[g] = run; run += v; }
+        for (size_t ii = ns; ii-- > 0;) {
+            K::for_each_digit(p, M, ii, false, [&](uint32_t g, uint32_t ref) { refs[counts[g] + cursor2[g]++] = ref; });
+        }
     }
     // work items
     for (uint64_t g = 0; g < p.G; g++) {
@@ -71,8 +83,8 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     K::size_bases_body(p, M);
     for (uint64_t g = p.G; g-- > 0;) {
         uint32_t nfull, rem; K::count_items(p, M, g, nfull, rem);
-        for (uint32_t k = 0; k < nfull; k++) items[size_cursor[p.T]++] = make_uint2((uint32_t)g, counts[g] + k * p.T);
-        if (rem) items[size_cursor[rem]++] = make_uint2((uint32_t)g, counts[g] + nfull * p.T);
+        for (uint32_t k = 0; k < nfull; k++) items[size_cursor[p.T]++] = make_uint2((uint32_t)g, K::bucket_lo(p, M, g) + k * p.T);
+        if (rem) items[size_cursor[rem]++] = make_uint2((uint32_t)g, K::bucket_lo(p, M, g) + nfull * p.T);
     }
     if (size_hist[p.T + 1] > p.max_items) return -4;
     // K4
@@ -105,10 +117,11 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     for (uint32_t k = 0; k < sets; k++) {
         memcpy(out_xyz + 96 * k, result[k].x.v, 32); memcpy(out_xyz + 96 * k + 32, result[k].y.v, 32); memcpy(out_xyz + 96 * k + 64, result[k].z.v, 32);
     }
-    return (int)p.acc_levels + (flags[0] ? 100 : 0);
+    return (int)p.acc_levels + (flags[0] ? 100 : 0) + (flags[1] ? 1000 : 0);
 }
 
-// curve 0 = Pallas (coords Fp, scalars Fq), 1 = Vesta.  Returns acc_levels (+100 if some bucket was split) or <0.
+// curve 0 = Pallas (coords Fp, scalars Fq), 1 = Vesta.  Returns acc_levels (+100 if some bucket was split, +1000 if the
+// exact sort ran) or <0.
 extern "C" int emu_msm(int curve, const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c,
                        int scalars_mont, uint32_t force_t, uint32_t force_kn, uint8_t *out_xyz) {
     if (curve == 0) return run_msm<FpParams, FqParams>(scalars, bases, n, c, scalars_mont, force_t, force_kn, 0, 0, out_xyz);
@@ -170,4 +183,11 @@ extern "C" int emu_ipa(int curve, const uint8_t *bases, uint32_t k, const uint8_
                        const uint8_t *chal_inv, const uint8_t *l_rand, const uint8_t *r_rand, uint32_t c, uint8_t *out_l, uint8_t *out_r, uint8_t *out_c) {
     if (curve == 0) return run_ipa<FpParams, FqParams>(bases, k, p_prime, x3, z, chal, chal_inv, l_rand, r_rand, c, out_l, out_r, out_c);
     return run_ipa<FqParams, FpParams>(bases, k, p_prime, x3, z, chal, chal_inv, l_rand, r_rand, c, out_l, out_r, out_c);
+}
+
+// plan introspection for the tests: out = {W, B, G, T, cap, l0, cap_top, top_bins}
+extern "C" void emu_msm_plan(size_t n, uint32_t c, int fixed, int glv, uint32_t sets, uint32_t force_cap, uint64_t *out) {
+    MsmPlan p;
+    msm_make_plan(p, n, c, 0, 0, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u, sets, force_cap);
+    out[0] = p.W; out[1] = p.B; out[2] = p.G; out[3] = p.T; out[4] = p.cap; out[5] = p.l0; out[6] = p.cap_top; out[7] = p.top_bins;
 }

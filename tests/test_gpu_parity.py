@@ -429,6 +429,52 @@ def test_ipa_errors(eng):
     params.close()
 
 
+def _msm_flags():
+    from halo2_b200 import lib as L
+    f = ctypes.c_uint32(0)
+    L.check(L.init().h2_test_last_msm_flags(ctypes.byref(f)))
+    return f.value
+
+
+def test_msm_sort_paths(eng):
+    """Uniform scalars take the single-pass binned sort (no bin overflows at the automatic capacity -- at 2^12, 2^16
+    and, in test_best_multiexp_2pow20, at 2^20); all-equal scalars overflow and fall back to the exact sort; forcing
+    the exact sort gives the same point."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    curve, c = "pallas", pasta.PALLAS
+    for k in (12, 16):
+        n = 1 << k
+        kb = cref.gen_scalars(c.scalar, SEED + 300 + k, n)
+        pb = cref.gen_points(curve, SEED + 310 + k, n)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        for glv in (1, 0):
+            L.check(lib.h2_set_glv(glv))
+            try:
+                assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want
+                assert _msm_flags() & 2 == 0, ("uniform scalars overflowed a bin", k, glv)
+                L.check(lib.h2_set_sort_mode(1))
+                assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want
+                assert _msm_flags() & 2 == 2
+            finally:
+                L.check(lib.h2_set_sort_mode(0))
+                L.check(lib.h2_set_glv(1))
+    n = 1 << 12
+    pb = cref.gen_points(curve, SEED + 320, n)
+    kb = cref.ints_to_bytes([pasta.gen_scalars(c.scalar, 5, 1)[0]] * n)
+    assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    assert _msm_flags() & 2 == 2          # every reference of a window in one bucket: overflow -> exact sort
+    # resident (fixed-base) path: commits of uniform polynomials stay on the fast path
+    k = 12
+    g = cref.gen_points("vesta", SEED + 330, (1 << k) + 1)
+    params = eng.Params("vesta", k, g[:-1], g[:-1], g[-1:])
+    poly = cref.gen_scalars("fp", SEED + 331, 1 << k)
+    want = cref.bytes_to_affine(cref.best_multiexp("vesta", np.concatenate([poly, cref.ints_to_bytes([9])]), g))
+    assert _affine("vesta", params.commit(poly, eng.Blind(9))) == want
+    assert _msm_flags() & 2 == 0
+    params.close()
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS
@@ -437,6 +483,7 @@ def test_best_multiexp_2pow20(eng):
     pb = cref.gen_points(curve, SEED + 33, n)
     want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
     assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want
+    assert _msm_flags() & 2 == 0          # the binned single-pass sort held (no bin overflow)
 
 
 def test_point_sum(eng):

@@ -275,3 +275,43 @@ def test_emul_field_structured_limbs(emu, field):
         b = raws[(i * 7 + 3) % len(raws)] * rinv % m
         assert _fop(emu, field, 4, a) == a * a % m, hex(x)
         assert _fop(emu, field, 2, a, b) == a * b % m, hex(x)
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_msm_sort_paths(emu, curve):
+    """The single-pass binned sort, its overflow fallback to the exact sort, and the exact sort alone give the same
+    point; splits of oversized buckets (forced T < bin capacity) work in the binned layout too."""
+    NO_BINS = 0xFFFFFFFF
+    c = pasta.CURVES[curve]
+    n = 300
+    kb = cref.gen_scalars(c.scalar, 41, n)
+    pb = cref.gen_points(curve, 42, n)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    skew = cref.ints_to_bytes([7] * n)                      # every digit of every scalar lands in the same buckets
+    want_skew = cref.bytes_to_affine(cref.best_multiexp(curve, skew, pb))
+
+    def run(kbytes, cb, cap, k0=0, gs=0, glv=False):
+        emu.emu_msm_set_cap(cap)
+        try:
+            out = np.zeros(96, dtype=np.uint8)
+            fn = emu.emu_msm_glv if glv else emu.emu_msm
+            r = fn(cref.CURVE_ID[curve], cref._p(kbytes), cref._p(pb), ctypes.c_size_t(n), cb, 0, k0, gs, cref._p(out))
+            assert r > 0, r
+            return r, cref.bytes_to_affine(cref.jac_to_affine(curve, out))
+        finally:
+            emu.emu_msm_set_cap(0)
+
+    for glv in (False, True):
+        for cb in ((4, 8, 7) if glv else (3, 5, 7)):        # full and sparse (c = 7) top windows
+            r, got = run(kb, cb, 0, glv=glv)                # automatic capacity: random digits never overflow
+            assert r < 1000 and got == want, (glv, cb)
+            r, got = run(kb, cb, NO_BINS, glv=glv)          # exact sort only
+            assert r >= 1000 and got == want
+            r, got = run(kb, cb, 8, 3, 4, glv=glv)          # tiny bins: overflow -> fallback (with splits)
+            assert got == want
+            r, got = run(skew, cb, 0, glv=glv)              # all-equal scalars: n references in one bucket
+            plan = (ctypes.c_uint64 * 8)()
+            emu.emu_msm_plan(ctypes.c_size_t(n), cb, 0, int(glv), 1, 0, plan)
+            assert got == want_skew and (r >= 1000) == (plan[4] < n), (glv, cb, list(plan))   # 7 = low digits only: lower windows
+            r, got = run(kb, cb, 512, 4, 4, glv=glv)        # roomy bins, T = 4 < sizes: splits in the binned layout
+            assert r < 1000 and (r % 1000 >= 100 or cb >= 7) and got == want
