@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/halo2_b200.h"
+#define H2_MAX_UPLOAD_CHUNKS 4
 #include "msm.cuh"
 #include "ipa.cuh"
 #include "ntt.cuh"
@@ -55,7 +56,8 @@ struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // uploads that may overlap compute (bases of a one-shot MSM)
-    cudaEvent_t ev_scalars_up = nullptr, ev_bases_up = nullptr;
+    cudaEvent_t ev_scalars_up = nullptr, ev_bases_up[H2_MAX_UPLOAD_CHUNKS] = {};
+    uint32_t chunk_min_log = 19;             // one-shot MSMs of >= 2^19 points upload their bases in chunks
     cudaEvent_t last_use = nullptr;
     bool have_last = false;
     uint32_t window_override = 0;
@@ -142,7 +144,7 @@ extern "C" int h2_init(int device) {
     CU(cudaEventCreateWithFlags(&g_ctx.last_use, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&g_ctx.ev_scalars_up, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&g_ctx.ev_bases_up, cudaEventDisableTiming));
+    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) CU(cudaEventCreateWithFlags(&g_ctx.ev_bases_up[j], cudaEventDisableTiming));
     g_ctx.device = device;
     g_ctx.ready = true;
     return 0;
@@ -165,7 +167,8 @@ extern "C" int h2_shutdown(void) {
     g_ctx.ipa.clear();
     for (IpaSession *q : g_ctx.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     g_ctx.ipa_pool.clear();
-    cudaEventDestroy(g_ctx.ev_scalars_up); cudaEventDestroy(g_ctx.ev_bases_up);
+    cudaEventDestroy(g_ctx.ev_scalars_up);
+    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) cudaEventDestroy(g_ctx.ev_bases_up[j]);
     cudaStreamDestroy(g_ctx.copy_stream);
     cudaEventDestroy(g_ctx.last_use);
     cudaStreamDestroy(g_ctx.stream);
@@ -192,6 +195,13 @@ extern "C" int h2_test_last_msm_flags(uint32_t *out) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(f, g_ctx.last_flags, sizeof f, cudaMemcpyDeviceToHost));
     *out = (f[0] ? 1u : 0u) | (f[1] ? 2u : 0u);
+    return 0;
+}
+// test hook: one-shot MSMs (h2_msm) of >= 2^log2_n points upload their bases in chunks (default 19)
+extern "C" int h2_test_set_chunk_threshold(uint32_t log2_n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (log2_n > 40) return fail("h2_test_set_chunk_threshold: log2_n > 40");
+    g_ctx.chunk_min_log = log2_n;
     return 0;
 }
 extern "C" int h2_set_window_bits(uint32_t c) {
@@ -350,10 +360,16 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s, const uin
     return 0;
 }
 
-// fixed != 0: d_bases is a window table (stride points per window) built with window size c
+// Arrival of the bases of a one-shot MSM in `k` chunks (events on the copy stream): chunk j = points [j n / k, (j + 1) n / k).
+struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS]; };
+
+// fixed != 0: d_bases is a window table (stride points per window) built with window size c.
+// bc != nullptr: the bases arrive chunk by chunk while this runs.  Each chunk is then sorted and accumulated on its own
+// (own bins, work items and bucket sums) as soon as it has landed, and the bucket reduce adds the per-chunk bucket sums:
+// the upload of all but the first chunk hides behind the accumulation.
 template <class P, class PS>
 static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, uint32_t fixed, uint64_t stride,
-                   jacobian *d_out, int out_canonical, cudaStream_t s, cudaEvent_t bases_ready = nullptr, uint32_t sets = 1) {
+                   jacobian *d_out, int out_canonical, cudaStream_t s, const BasesChunks *bc = nullptr, uint32_t sets = 1) {
     Context &X = g_ctx;
     if (n == 0) {   // empty sum = identity
         jacobian id;
@@ -363,41 +379,66 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         CU(cudaStreamSynchronize(s));
         return 0;
     }
-    MsmPlan p;
     const uint32_t glv = (!fixed && X.glv_on && n < (1ull << 30)) ? 1u : 0u;
     if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
     if (c > 24) return fail("msm: window bits > 24");
-    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets, X.sort_bins ? 0u : H2_MSM_NO_BINS);
+    const uint32_t K = (bc && !fixed && bc->k > 1) ? bc->k : 1u;
+    const uint32_t force_cap = X.sort_bins ? 0u : H2_MSM_NO_BINS;
+    MsmPlan p;                       // the whole problem: bucket reduce and window combine
+    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets, force_cap);
+    p.chunks = K;
+    MsmPlan pk[H2_MAX_UPLOAD_CHUNKS];   // one chunk of points: sort, work items, accumulation
+    size_t first[H2_MAX_UPLOAD_CHUNKS + 1];
+    for (uint32_t j = 0; j <= K; j++) first[j] = (size_t)((unsigned __int128)n * j / K);
+    uint64_t ref_space = 0, max_items = 0, part_total = 0;
+    uint32_t t_max = 0;
+    for (uint32_t j = 0; j < K; j++) {
+        if (K == 1) pk[0] = p;
+        else msm_make_plan(pk[j], first[j + 1] - first[j], c, 0, 0, fixed, stride, glv, sets, force_cap);
+        if (pk[j].ref_space >= (1ull << 32)) return fail("msm: n * windows exceeds 2^32 references");
+        ref_space = pk[j].ref_space > ref_space ? pk[j].ref_space : ref_space;
+        max_items = pk[j].max_items > max_items ? pk[j].max_items : max_items;
+        part_total = pk[j].part_total > part_total ? pk[j].part_total : part_total;
+        t_max = pk[j].T > t_max ? pk[j].T : t_max;
+    }
     if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 32))) return 1;
     if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
-    if (p.ref_space >= (1ull << 32) || p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
+    if (p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
     if (scalars_mont && X.scal_canon.ensure(n * p.sets * sizeof(fe))) return 1;
-    const size_t small_words = 2 * (p.T + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
-    if (X.counts.ensure((p.G + 1) * 4) || X.cursor.ensure(2 * p.G * 4) || X.refs.ensure(p.ref_space * 4) ||
-        X.size_hist.ensure(small_words * 4) || X.items.ensure(p.max_items * sizeof(uint2)) ||
-        X.bucket_sum.ensure(p.G * sizeof(xyzz)) || X.pkey.ensure((p.part_total + 1) * 4) || X.pstart.ensure((p.part_total + 1) * 4) ||
-        X.pend.ensure((p.part_total + 1) * 4) || X.ppt.ensure((p.part_total + 1) * sizeof(xyzz)) ||
+    const size_t small_words = 2 * (t_max + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
+    part_total += 1;
+    if (X.counts.ensure(K * (p.G + 1) * 4) || X.cursor.ensure(K * 2 * p.G * 4) || X.refs.ensure(K * ref_space * 4) ||
+        X.size_hist.ensure(K * small_words * 4) || X.items.ensure(K * max_items * sizeof(uint2)) ||
+        X.bucket_sum.ensure(K * p.G * sizeof(xyzz)) || X.pkey.ensure(K * part_total * 4) || X.pstart.ensure(K * part_total * 4) ||
+        X.pend.ensure(K * part_total * 4) || X.ppt.ensure(K * part_total * sizeof(xyzz)) ||
         X.ra_t.ensure((size_t)p.Wb * p.m1 * sizeof(xyzz)) || X.ra_e.ensure((size_t)p.Wb * p.m1 * sizeof(xyzz)) ||
         X.r0.ensure((size_t)p.Wb * p.nb0 * H2_R0_ROWS * sizeof(xyzz)) || X.r1.ensure((size_t)p.Wb * p.r1_rows * sizeof(xyzz)) ||
         X.wsum.ensure((size_t)p.Wb * sizeof(xyzz)))
         return 1;
-    MsmBuffers M;
-    M.scalars = d_scalars; M.bases = d_bases; M.bases_phi = X.bases_phi.as<affine>(); M.glv_parts = X.glv_parts.as<uint32_t>(); M.scalars_mont = scalars_mont ? 1u : 0u;
-    M.scal_canon = X.scal_canon.as<fe>();
-    M.counts = X.counts.as<uint32_t>(); M.cursor = X.cursor.as<uint32_t>(); M.cursor2 = M.cursor + p.G;
-    M.refs = X.refs.as<uint32_t>();
-    M.size_hist = X.size_hist.as<uint32_t>(); M.size_cursor = M.size_hist + (p.T + 2); M.flags = M.size_cursor + (p.T + 2); X.last_flags = M.flags;
-    M.items = X.items.as<uint2>();
-    M.bucket_sum = X.bucket_sum.as<xyzz>();
-    M.pkey = X.pkey.as<uint32_t>(); M.pstart = X.pstart.as<uint32_t>(); M.pend = X.pend.as<uint32_t>(); M.ppt = X.ppt.as<xyzz>();
-    M.ra_t = X.ra_t.as<xyzz>(); M.ra_e = X.ra_e.as<xyzz>(); M.r0 = X.r0.as<xyzz>(); M.r1 = X.r1.as<xyzz>();
-    M.wsum = X.wsum.as<xyzz>(); M.result = d_out;
+    MsmBuffers Mk[H2_MAX_UPLOAD_CHUNKS];
+    for (uint32_t j = 0; j < K; j++) {
+        MsmBuffers &M = Mk[j];
+        const size_t o = first[j];
+        M.scalars = d_scalars + o; M.bases = d_bases + o; M.bases_phi = X.bases_phi.as<affine>() + o;
+        M.glv_parts = X.glv_parts.as<uint32_t>() + 8 * o; M.scalars_mont = scalars_mont ? 1u : 0u;
+        M.scal_canon = X.scal_canon.as<fe>() + o;
+        M.counts = X.counts.as<uint32_t>() + j * (p.G + 1); M.cursor = X.cursor.as<uint32_t>() + j * 2 * p.G; M.cursor2 = M.cursor + p.G;
+        M.refs = X.refs.as<uint32_t>() + j * ref_space;
+        M.size_hist = X.size_hist.as<uint32_t>() + j * small_words; M.size_cursor = M.size_hist + (pk[j].T + 2); M.flags = M.size_cursor + (pk[j].T + 2);
+        M.items = X.items.as<uint2>() + j * max_items;
+        M.bucket_sum = X.bucket_sum.as<xyzz>() + j * p.G;
+        M.pkey = X.pkey.as<uint32_t>() + j * part_total; M.pstart = X.pstart.as<uint32_t>() + j * part_total;
+        M.pend = X.pend.as<uint32_t>() + j * part_total; M.ppt = X.ppt.as<xyzz>() + j * part_total;
+        M.ra_t = X.ra_t.as<xyzz>(); M.ra_e = X.ra_e.as<xyzz>(); M.r0 = X.r0.as<xyzz>(); M.r1 = X.r1.as<xyzz>();
+        M.wsum = X.wsum.as<xyzz>(); M.result = d_out;
+    }
+    X.last_flags = Mk[0].flags;
 
-    CU(cudaMemsetAsync(M.counts, 0, (p.G + 1) * 4, s));
-    CU(cudaMemsetAsync(M.cursor, 0, 2 * p.G * 4, s));
-    CU(cudaMemsetAsync(M.size_hist, 0, small_words * 4, s));
-    CU(cudaMemsetAsync(M.bucket_sum, 0, p.G * sizeof(xyzz), s));
-    CU(cudaMemsetAsync(M.pkey, 0xff, p.part_total * 4, s));
+    CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
+    CU(cudaMemsetAsync(X.cursor.p, 0, K * 2 * p.G * 4, s));
+    CU(cudaMemsetAsync(X.size_hist.p, 0, K * small_words * 4, s));
+    CU(cudaMemsetAsync(X.bucket_sum.p, 0, K * p.G * sizeof(xyzz), s));
+    CU(cudaMemsetAsync(X.pkey.p, 0xff, K * part_total * 4, s));
 
     auto k_bin = msm_bin_kernel<P, PS>;
     auto k_hist = msm_hist_kernel<P, PS>;
@@ -413,30 +454,39 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     auto k_r1 = msm_r1_kernel<P, PS>;
     auto k_wsum = msm_wsum_kernel<P, PS>;
     auto k_final = msm_final_kernel<P, PS>;
-    // K2/K3: counting sort of the (point, window) references by bucket
-    // single pass into per-bucket bins; the exact histogram / scan / scatter kernels run only if a bin overflowed
-    // (flags[1], set by the bin kernel) or if there are no bins (set here)
-    if (p.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
-    else LAUNCH(k_bin, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
-    LAUNCH(k_hist, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
-    if (exclusive_scan_u32(M.counts, p.G + 1, s, M.flags + 1)) return 1;
-    LAUNCH(k_scatter, blocks_for(n * p.sets, 256), 256, 0, s, p, M);
-    // K4: work items (one per bucket, oversized buckets split), largest first
-    LAUNCH(k_ihist, blocks_for(p.G, 256), 256, 0, s, p, M);
-    LAUNCH(k_ibases, 1, 32, 0, s, p, M);
-    LAUNCH(k_iplace, blocks_for(p.G, 256), 256, 0, s, p, M);
-    if (bases_ready) CU(cudaStreamWaitEvent(s, bases_ready, 0));   // the sort above only needed the scalars
-    if (p.glv) {
-        auto k_phi = msm_phi_kernel<P, PS>;
-        LAUNCH(k_phi, blocks_for(n, 256), 256, 0, s, d_bases, M.bases_phi, (uint64_t)n);
+    for (uint32_t j = 0; j < K; j++) {
+        const MsmPlan &q = pk[j];
+        const MsmBuffers &M = Mk[j];
+        // K2/K3: the (point, window) references sorted by bucket -- a single pass into per-bucket bins; the exact
+        // histogram / scan / scatter kernels run only if a bin overflowed (flags[1], set by the bin kernel) or if there
+        // are no bins (set here)
+        if (q.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
+        else LAUNCH(k_bin, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+        LAUNCH(k_hist, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+        if (exclusive_scan_u32(M.counts, q.G + 1, s, M.flags + 1)) return 1;
+        LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+        // K4: work items (one per bucket, oversized buckets split), largest first
+        LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
+        LAUNCH(k_ibases, 1, 32, 0, s, q, M);
+        LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
     }
-    prof_begin(PROF_MSM_ACCUM0, s);
-    LAUNCH(k_accum0, blocks_for(p.max_items, 128), 128, 0, s, p, M);
-    prof_end(s);
-    if (p.acc_levels > 1) LAUNCH(k_accumN, blocks_for(p.acc_threads[1], 128), 128, 0, s, p, M, 1u);
-    if (p.acc_levels > 2) LAUNCH(k_accumN, blocks_for(p.acc_threads[2], 128), 128, 0, s, p, M, 2u);
-    if (p.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, p, M);
-    // K5: bucket reduce and window combine
+    for (uint32_t j = 0; j < K; j++) {
+        const MsmPlan &q = pk[j];
+        const MsmBuffers &M = Mk[j];
+        if (bc && bc->k) CU(cudaStreamWaitEvent(s, bc->ev[bc->k > 1 ? j : 0], 0));   // the sort above only needed the scalars
+        if (q.glv) {
+            auto k_phi = msm_phi_kernel<P, PS>;
+            LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
+        }
+        prof_begin(PROF_MSM_ACCUM0, s);
+        LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+        prof_end(s);
+        if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
+        if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);
+        if (q.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, q, M);
+    }
+    // K5: bucket reduce (adds the per-chunk bucket sums) and window combine
+    const MsmBuffers &M = Mk[0];
     LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1 * 4, 128), 128, 0, s, p, M);                    // quads
     LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0) * 4, 128), 128, 0, s, p, M);
     LAUNCH(k_r1, p.Wb * p.r1_rows, 4 * H2_R1_QUADS, 0, s, p, M);
@@ -447,9 +497,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
 
 static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
                         jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0,
-                        cudaEvent_t bases_ready = nullptr, uint32_t sets = 1) {
-    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready, sets);
-    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bases_ready, sets);
+                        const BasesChunks *bc = nullptr, uint32_t sets = 1) {
+    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bc, sets);
+    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bc, sets);
     return fail("unknown curve id");
 }
 // window size for a precomputed table over n bases: few references per bucket (short serial chains)
@@ -513,18 +563,27 @@ static int msm_host_common(int curve, const void *scalars, size_t n_scalars, con
     if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
     if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
     if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
-    cudaEvent_t bases_ready = nullptr;
+    BasesChunks bc;
     if (host_bases && n_total) {
         cudaStream_t cs = X.copy_stream;
         CU(cudaEventRecord(X.ev_scalars_up, s));
         CU(cudaStreamWaitEvent(cs, X.ev_scalars_up, 0));      // scalars first on the PCIe link (and after prior scratch users)
-        CU(cudaMemcpyAsync(const_cast<affine *>(d_bases), host_bases, n_total * sizeof(affine), cudaMemcpyHostToDevice, cs));
-        if (repr == H2_REPR_CANONICAL && convert_points(curve, const_cast<affine *>(d_bases), n_total, 1, cs)) return 1;
-        CU(cudaEventRecord(X.ev_bases_up, cs));
-        bases_ready = X.ev_bases_up;
+        // large inputs go up in chunks: the engine accumulates chunk j while chunk j + 1 is on the link
+        // (2 chunks from 2^chunk_min_log points, 4 from 8x that: every chunk pays its own sort / work-item launches)
+        bc.k = 1;
+        if (n_total >= ((size_t)1 << X.chunk_min_log) && n_total >= 4 * H2_MAX_UPLOAD_CHUNKS)
+            bc.k = n_total >= ((size_t)8 << X.chunk_min_log) ? H2_MAX_UPLOAD_CHUNKS : 2u;
+        affine *db = const_cast<affine *>(d_bases);
+        for (uint32_t j = 0; j < bc.k; j++) {
+            size_t lo = (size_t)((unsigned __int128)n_total * j / bc.k), hi = (size_t)((unsigned __int128)n_total * (j + 1) / bc.k);
+            CU(cudaMemcpyAsync(db + lo, (const affine *)host_bases + lo, (hi - lo) * sizeof(affine), cudaMemcpyHostToDevice, cs));
+            if (repr == H2_REPR_CANONICAL && convert_points(curve, db + lo, hi - lo, 1, cs)) return 1;
+            CU(cudaEventRecord(X.ev_bases_up[j], cs));
+            bc.ev[j] = X.ev_bases_up[j];
+        }
     }
     int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
-                          repr == H2_REPR_CANONICAL, s, fixed, stride, bases_ready);
+                          repr == H2_REPR_CANONICAL, s, fixed, stride, bc.k ? &bc : nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
     if (scratch_release(s)) return 1;

@@ -46,6 +46,7 @@ struct MsmPlan {
     uint64_t n;          // number of (scalar, base) pairs
     uint32_t c;          // window bits
     uint32_t glv;        // 1: scalars are split k = k1 + k2 lambda (glv.cuh); point i contributes P_i (k1) and phi(P_i) (k2)
+    uint32_t chunks;     // bucket_sum holds `chunks` arrays of G partial bucket sums (one per upload chunk of the bases), summed by level A
     uint32_t cap;        // bin capacity of the single-pass sort (0: exact two-pass sort only)
     uint32_t cap_top;    // ... of the top window's bins (its digits are fewer bits wide and, with GLV, not uniform)
     uint64_t g_top;      // first bucket of the top window (= G in the fixed-base mode: no separate top region)
@@ -96,7 +97,7 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
 #define H2_MSM_NO_BINS 0xffffffffu
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
                           uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1, uint32_t force_cap = 0) {
-    p.n = n; p.c = c;
+    p.n = n; p.c = c; p.chunks = 1;
     p.glv = fixed ? 0u : glv;
     // GLV sub-scalars are < 2^127 (glv.cuh): with W c >= 128 the top window's raw digit is < 2^(c-1), so it
     // absorbs the signed-digit carry without opening another window
@@ -401,10 +402,10 @@ template <class P, class PS> struct Msm {
         const xyzz *A = M.bucket_sum + (uint64_t)w * p.B + (uint64_t)u * L;
         xyzz run = xyzz_identity(), acc = xyzz_identity();
         for (uint32_t i = L - 1; i > 0; i--) {
-            ADD::template add<P>(run, ld_xyzz(A + i));
+            for (uint32_t k = 0; k < p.chunks; k++) ADD::template add<P>(run, ld_xyzz(A + k * p.G + i));
             ADD::template add<P>(acc, run);
         }
-        ADD::template add<P>(run, ld_xyzz(A));
+        for (uint32_t k = 0; k < p.chunks; k++) ADD::template add<P>(run, ld_xyzz(A + k * p.G));
         uint64_t o = (uint64_t)w * p.m1 + u;
         st_xyzz(M.ra_t + o, run);
         st_xyzz(M.ra_e + o, acc);

@@ -475,6 +475,28 @@ def test_msm_sort_paths(eng):
     params.close()
 
 
+def test_msm_chunked_upload(eng):
+    """h2_msm with the bases uploaded, sorted and accumulated in chunks (forced at small n): same point, including
+    skewed scalars (exact-sort fallback per chunk), sizes that do not divide by the chunk count, and both curves."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    try:
+        for curve, n, thr in (("pallas", 4099, 4), ("vesta", 1 << 12, 11), ("pallas", 17, 4), ("vesta", 5, 1)):   # 4, 2, 2, 1 chunks
+            L.check(lib.h2_test_set_chunk_threshold(thr))
+            c = pasta.CURVES[curve]
+            pb = cref.gen_points(curve, SEED + 400 + n, n)
+            for name, kb in (("random", cref.gen_scalars(c.scalar, SEED + 401 + n, n)),
+                             ("equal", cref.ints_to_bytes([pasta.gen_scalars(c.scalar, 3, 1)[0]] * n)),
+                             ("mix01", cref.ints_to_bytes([i & 1 for i in range(n)]))):
+                want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+                for glv in (1, 0):
+                    L.check(lib.h2_set_glv(glv))
+                    assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want, (curve, n, name, glv)
+    finally:
+        L.check(lib.h2_set_glv(1))
+        L.check(lib.h2_test_set_chunk_threshold(19))
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS
