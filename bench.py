@@ -292,6 +292,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = L.init(local_rank)
     stream = torch.cuda.current_stream()

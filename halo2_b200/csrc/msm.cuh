@@ -91,7 +91,8 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
     if (n_eff < 64) return 4;
     if (n_eff < (1ull << 10)) return 8;
     if (n_eff < (1ull << 17)) return 13;     // measured: 13 beats 16 up to n = 2^15 (GLV), tools/sweep_window.py
-    return 16;
+    if (n_eff < (1ull << 25)) return 16;     // ... 16 wins from 2^16 to 2^22 (8 full windows with GLV)
+    return 19;                               // ... 19 (7 windows) from 2^24
 }
 
 #define H2_MSM_NO_BINS 0xffffffffu
