@@ -222,6 +222,48 @@ def prover_replay_gpu(h2, cref, reps=3):
     return dt, setup_s, sched, {k_: v * 1e3 / reps for k_, v in by_kind.items()}
 
 
+def resident_column_ms(h2, cref, reps=5):
+    """One advice column's trip through the hot path at k=14 -- commit_lagrange, lagrange_to_coeff, commit,
+    coeff_to_extended, extended values back to the host -- with host buffers per call vs device-resident handles."""
+    n, k = 1 << PROVER_K, PROVER_K
+    g, gl, polys, _ = prover_replay_inputs(cref)
+    params = h2.Params("vesta", k, g[:n], gl[:n], g[n:n + 1])
+    dom = h2.EvaluationDomain("fp", PROVER_J, k, pow(5, (P_MOD - 1) // 3, P_MOD))
+    blind = h2.Blind(7)
+    ext_buf = h2.ResidentPoly("fp", dom.extended_len())
+
+    def host():
+        v = polys[0]
+        params.commit_lagrange(v, blind)
+        cf = dom.lagrange_to_coeff(v)
+        params.commit(cf, blind)
+        return dom.coeff_to_extended(cf)
+
+    def resident():
+        r = h2.ResidentPoly("fp", n, polys[0])
+        params.commit_resident([r], [blind], lagrange=True)
+        dom.lagrange_to_coeff_resident(r)
+        params.commit_resident([r], [blind])
+        out = dom.coeff_to_extended_resident(r, ext_buf).download()
+        r.close()
+        return out
+
+    res = {}
+    ref_out = None
+    for name, fn in (("host_buffers", host), ("resident", resident)):
+        out = fn()
+        if ref_out is None:
+            ref_out = out
+        same = bool((out == ref_out).all())
+        t0 = time.time()
+        for _ in range(reps):
+            fn()
+        res[name] = {"ms": (time.time() - t0) / reps * 1e3, "same_result": same}
+    ext_buf.close()
+    params.close()
+    return res
+
+
 def prover_replay_cpu(cref, threads):
     n, k = 1 << PROVER_K, PROVER_K
     g, gl, polys, ext = prover_replay_inputs(cref)
@@ -504,6 +546,7 @@ def main():
             kinds = {}
             for kind, cnt in sched:
                 kinds[kind] = kinds.get(kind, 0) + (cnt if kind.endswith("_many") else 1)
+            extra["resident_column_k14"] = resident_column_ms(h2, cref)
             extra["create_proof_k14_replay"] = {
                 "metric": "hot_path_ms_per_proof", "value": gdt * 1e3, "unit": "ms", "higher_is_better": False,
                 "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": cpu_by_kind,

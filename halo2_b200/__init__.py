@@ -7,7 +7,7 @@ operation raises `H2Error` unless the library is built and a B200 is visible.
 """
 from .lib import H2Error, lib_path, load, init, launch_count  # noqa: F401
 from .arithmetic import best_multiexp, best_fft, multiexp_window_bits  # noqa: F401
-from .poly import Params, EvaluationDomain, Blind  # noqa: F401
+from .poly import Params, EvaluationDomain, Blind, ResidentPoly  # noqa: F401
 
 __all__ = ["H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "best_fft",
-           "multiexp_window_bits", "Params", "EvaluationDomain", "Blind"]
+           "multiexp_window_bits", "Params", "EvaluationDomain", "Blind", "ResidentPoly"]

@@ -49,6 +49,7 @@ struct DevBuf {
 struct TwiddleEntry { int field; uint32_t log_n; uint8_t omega[32]; DevBuf buf; uint64_t stamp; };
 struct BaseSet { int curve; size_t n; DevBuf buf; DevBuf table; uint32_t c = 0, W = 0; };   // table: W x n window multiples
 
+struct PolyBuf { int field; size_t len; DevBuf buf; };   // device-resident polynomial, Montgomery form, len + 1 slots
 struct IpaSession { uint64_t bases; uint32_t k, round; int folded; DevBuf p, b, s, scal, out; };
 
 struct Context {
@@ -73,6 +74,7 @@ struct Context {
     uint64_t tw_stamp = 0;
     std::map<uint64_t, BaseSet *> bases;
     std::map<uint64_t, IpaSession *> ipa;
+    std::map<uint64_t, PolyBuf *> polys;
     std::vector<IpaSession *> ipa_pool;      // finished sessions keep their buffers for the next proof (no cudaMalloc per opening)
     uint64_t next_handle = 1;
 };
@@ -165,6 +167,8 @@ extern "C" int h2_shutdown(void) {
     g_ctx.bases.clear();
     for (auto &kv : g_ctx.ipa) { IpaSession *q = kv.second; q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     g_ctx.ipa.clear();
+    for (auto &kv : g_ctx.polys) { kv.second->buf.release(); delete kv.second; }
+    g_ctx.polys.clear();
     for (IpaSession *q : g_ctx.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     g_ctx.ipa_pool.clear();
     cudaEventDestroy(g_ctx.ev_scalars_up);
@@ -1000,6 +1004,158 @@ extern "C" int h2_ipa_finish(uint64_t session, int repr, void *out_c_b) {
     ipa_free(q);
     g_ctx.ipa.erase(it);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident polynomials: the transforms and commits of the quotient
+// pipeline without a PCIe round trip per call.  Data is kept in Montgomery form; every buffer has one spare
+// slot so that a commit can append the blind.
+// ------------------------------------------------------------------------------------------------
+static PolyBuf *find_poly(uint64_t h) {
+    auto it = g_ctx.polys.find(h);
+    return it == g_ctx.polys.end() ? nullptr : it->second;
+}
+extern "C" int h2_poly_alloc(int field, size_t len, uint64_t *poly) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (field != H2_FIELD_FP && field != H2_FIELD_FQ) return fail("unknown field id");
+    PolyBuf *b = new PolyBuf();
+    b->field = field; b->len = len;
+    if (b->buf.ensure((len + 1) * sizeof(fe))) { delete b; return 1; }
+    uint64_t h = g_ctx.next_handle++;
+    g_ctx.polys[h] = b;
+    *poly = h;
+    return 0;
+}
+extern "C" int h2_poly_free(uint64_t poly) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.polys.find(poly);
+    if (it == g_ctx.polys.end()) return fail("h2_poly_free: unknown handle");
+    cudaSetDevice(g_ctx.device);
+    cudaStreamSynchronize(g_ctx.stream);
+    it->second->buf.release();
+    delete it->second;
+    g_ctx.polys.erase(it);
+    return 0;
+}
+static int convert_field(int field, fe *d, size_t n, int to_mont, cudaStream_t s) {
+    if (n == 0) return 0;
+    if (field == H2_FIELD_FP) LAUNCH(convert_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, d, (uint64_t)n, to_mont);
+    else LAUNCH(convert_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, d, (uint64_t)n, to_mont);
+    return 0;
+}
+extern "C" int h2_poly_upload(uint64_t poly, const void *src, size_t len, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *b = find_poly(poly);
+    if (!b) return fail("h2_poly_upload: unknown handle");
+    if (len > b->len) return fail("h2_poly_upload: more elements than the polynomial holds");
+    cudaStream_t s = g_ctx.stream;
+    CU(cudaMemcpyAsync(b->buf.p, src, len * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL && convert_field(b->field, b->buf.as<fe>(), len, 1, s)) return 1;
+    CU(cudaStreamSynchronize(s));      // src may be pageable
+    return 0;
+}
+extern "C" int h2_poly_download(uint64_t poly, void *dst, size_t len, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *b = find_poly(poly);
+    if (!b) return fail("h2_poly_download: unknown handle");
+    if (len > b->len) return fail("h2_poly_download: more elements than the polynomial holds");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const fe *from = b->buf.as<fe>();
+    if (repr == H2_REPR_CANONICAL) {   // convert a copy: the resident data stays in Montgomery form
+        if (scratch_acquire(s)) return 1;
+        if (X.ntt_out.ensure(len * sizeof(fe))) return 1;
+        CU(cudaMemcpyAsync(X.ntt_out.p, from, len * sizeof(fe), cudaMemcpyDeviceToDevice, s));
+        if (convert_field(b->field, X.ntt_out.as<fe>(), len, 0, s)) return 1;
+        from = X.ntt_out.as<fe>();
+    }
+    CU(cudaMemcpyAsync(dst, from, len * sizeof(fe), cudaMemcpyDeviceToHost, s));
+    if (repr == H2_REPR_CANONICAL && scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+// mode as in ntt_host: 1 = inverse transform with divisor, 2 = coeff_to_extended, 3 = extended_to_coeff
+template <class P>
+static int poly_transform(PolyBuf *dst, PolyBuf *src, int mode, uint32_t in_log_n, uint32_t log_n, const void *omega, const void *zeta,
+                          const void *divisor, size_t out_len, int repr) {
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) return 1;
+    fe w = host_to_mont<P>(omega, repr), z, d;
+    if (zeta) z = host_to_mont<P>(zeta, repr);
+    if (divisor) d = host_to_mont<P>(divisor, repr);
+    NttScales sc = make_scales<P>(H2_REPR_MONTGOMERY, mode == 2 ? &z : nullptr, (mode == 1 || mode == 3) ? &d : nullptr, mode == 3 ? &z : nullptr);
+    if (ntt_run<P>(src->field, src->buf.as<fe>(), in_log_n, dst->buf.as<fe>(), log_n, w, sc, out_len, s)) return 1;
+    return scratch_release(s);       // asynchronous: later calls are ordered behind it on the stream
+}
+static int poly_transform_dispatch(uint64_t dst, uint64_t src, int mode, uint32_t in_log_n, uint32_t log_n, const void *omega, const void *zeta,
+                                   const void *divisor, size_t out_len, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *d = find_poly(dst), *a = find_poly(src);
+    if (!d || !a) return fail("resident transform: unknown polynomial handle");
+    if (d->field != a->field) return fail("resident transform: the polynomials live in different fields");
+    if (log_n > 30 || in_log_n > log_n) return fail("ntt: bad sizes");
+    if (a->len < ((size_t)1 << in_log_n)) return fail("resident transform: the source holds fewer than 2^k elements");
+    if (out_len > ((size_t)1 << log_n)) out_len = (size_t)1 << log_n;
+    if (d->len < out_len) return fail("resident transform: the destination is too short");
+    if (d == a && out_len != ((size_t)1 << log_n)) return fail("resident transform: in place needs out_len == 2^log_n");
+    if (d == a && in_log_n != log_n) return fail("resident transform: in place needs equal input and output sizes");
+    if (a->field == H2_FIELD_FP) return poly_transform<FpParams>(d, a, mode, in_log_n, log_n, omega, zeta, divisor, out_len, repr);
+    return poly_transform<FqParams>(d, a, mode, in_log_n, log_n, omega, zeta, divisor, out_len, repr);
+}
+extern "C" int h2_poly_lagrange_to_coeff(uint64_t dst, uint64_t src, uint32_t k, const void *omega_inv, const void *divisor, int repr) {
+    return poly_transform_dispatch(dst, src, 1, k, k, omega_inv, nullptr, divisor, (size_t)1 << k, repr);
+}
+extern "C" int h2_poly_coeff_to_extended(uint64_t dst, uint64_t src, uint32_t k, uint32_t ext_k, const void *zeta, const void *ext_omega, int repr) {
+    return poly_transform_dispatch(dst, src, 2, k, ext_k, ext_omega, zeta, nullptr, (size_t)1 << ext_k, repr);
+}
+extern "C" int h2_poly_extended_to_coeff(uint64_t dst, uint64_t src, uint32_t ext_k, const void *ext_omega_inv, const void *ext_divisor,
+                                         const void *zeta, size_t out_len, int repr) {
+    return poly_transform_dispatch(dst, src, 3, ext_k, ext_k, ext_omega_inv, zeta, ext_divisor, out_len, repr);
+}
+// commit(poly, blind) = <poly[0..n), bases[0..n)> + blind * bases[n] for `batch` resident polynomials in one pass
+extern "C" int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
+                                       void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(bases_handle);
+    if (it == g_ctx.bases.end()) return fail("h2_msm_registered_polys: unknown bases handle");
+    BaseSet *b = it->second;
+    if (batch == 0) return 0;
+    if (batch > 64) return fail("h2_msm_registered_polys: batch > 64");
+    if (batch > 1 && !b->table.p) return fail("h2_msm_registered_polys: a batch needs a base set with a window table (H2_BASES_PRECOMPUTE)");
+    const size_t total = n + (extra_scalars ? 1 : 0);
+    if (total > b->n) return fail("h2_msm_registered_polys: more scalars than registered bases");
+    const int scalar_field = b->curve == H2_CURVE_PALLAS ? H2_FIELD_FQ : H2_FIELD_FP;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.scal_in.ensure(batch * total * sizeof(fe)) || X.result.ensure(batch * sizeof(jacobian)) || X.misc.ensure(batch * sizeof(fe) + 64)) return 1;
+    fe *d = X.scal_in.as<fe>();
+    if (extra_scalars) {   // the blinds: Montgomery form like the resident data
+        CU(cudaMemcpyAsync(X.misc.p, extra_scalars, batch * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (repr == H2_REPR_CANONICAL && convert_field(scalar_field, X.misc.as<fe>(), batch, 1, s)) return 1;
+    }
+    for (size_t j = 0; j < batch; j++) {
+        PolyBuf *q = find_poly(polys[j]);
+        if (!q) return fail("h2_msm_registered_polys: unknown polynomial handle");
+        if (q->field != scalar_field) return fail("h2_msm_registered_polys: the polynomial is not over the curve's scalar field");
+        if (q->len < n) return fail("h2_msm_registered_polys: the polynomial holds fewer than n elements");
+        CU(cudaMemcpyAsync(d + j * total, q->buf.p, n * sizeof(fe), cudaMemcpyDeviceToDevice, s));
+        if (extra_scalars) CU(cudaMemcpyAsync(d + j * total + n, X.misc.as<fe>() + j, sizeof(fe), cudaMemcpyDeviceToDevice, s));
+    }
+    int rc;
+    if (b->table.p) rc = msm_dispatch(b->curve, d, 1, b->table.as<affine>(), total, b->c, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s, 1, b->n,
+                                      nullptr, (uint32_t)batch);
+    else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
 }
 
 extern "C" int h2_dev_gen_points(int curve, uint64_t seed, uint64_t first, size_t n, void *d_out, void *stream) {

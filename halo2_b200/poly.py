@@ -92,6 +92,18 @@ class Params:
     def commit_lagrange_many(self, polys, blinds: Sequence[Blind]) -> np.ndarray:
         return self._commit_many(self._h_gl, polys, blinds)
 
+    def commit_resident(self, polys: Sequence["ResidentPoly"], blinds: Sequence[Blind], lagrange: bool = False) -> np.ndarray:
+        """[commit(p, r)] (or commit_lagrange with lagrange=True) for device-resident polynomials: nothing but the
+        blinds goes up, nothing but the points comes back."""
+        batch = len(polys)
+        assert batch == len(blinds) and batch >= 1
+        hs = (ctypes.c_uint64 * batch)(*[p._h.value for p in polys])
+        bl = np.ascontiguousarray(np.stack([_l.fe_bytes(b.value) for b in blinds]))
+        out = np.zeros((batch, 96), dtype=np.uint8)
+        _l.check(_l.init().h2_msm_registered_polys(self._h_gl if lagrange else self._h_g, hs, ctypes.c_size_t(batch), ctypes.c_size_t(self.n),
+                                                    _l.ptr(bl), _l.REPR_CANONICAL, _l.ptr(out)))
+        return out
+
     def ipa_rounds(self, p_prime, x3: int, z: int, challenge, l_rand: Sequence[int], r_rand: Sequence[int]):
         """The round loop of commitment::create_proof (poly/commitment/prover.rs:100-142) on the device.
         `p_prime` (:80) is the blinded polynomial with P(x3) removed; `challenge(j, L_j, R_j) -> u_j` is the
@@ -131,6 +143,41 @@ class Params:
             if h.value:
                 lib.h2_bases_release(h)
                 h.value = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ResidentPoly:
+    """A polynomial kept in HBM (Montgomery form) between transforms and commits -- SURVEY.md section 8(f) row 3.
+    The reference keeps every Polynomial<F, B> in host memory (poly.rs:56-71); this is the handle a patched prover
+    would hold instead while a column travels lagrange -> coeff -> extended."""
+
+    def __init__(self, field: str, length: int, values=None):
+        self.field, self.len = field, int(length)
+        self._h = ctypes.c_uint64(0)
+        _l.check(_l.init().h2_poly_alloc(_l.FIELD_ID[field], ctypes.c_size_t(self.len), ctypes.byref(self._h)))
+        if values is not None:
+            self.upload(values)
+
+    def upload(self, values) -> None:
+        arr = _l.as_u8(values, 32)
+        assert arr.shape[0] <= self.len
+        _l.check(_l.init().h2_poly_upload(self._h, _l.ptr(arr), ctypes.c_size_t(arr.shape[0]), _l.REPR_CANONICAL))
+
+    def download(self, length: Optional[int] = None) -> np.ndarray:
+        n = self.len if length is None else int(length)
+        out = np.zeros((n, 32), dtype=np.uint8)
+        _l.check(_l.init().h2_poly_download(self._h, _l.ptr(out), ctypes.c_size_t(n), _l.REPR_CANONICAL))
+        return out
+
+    def close(self) -> None:
+        if self._h.value:
+            _l.load().h2_poly_free(self._h)
+            self._h.value = 0
 
     def __del__(self):
         try:
@@ -200,4 +247,27 @@ class EvaluationDomain:
                                                 _l.ptr(_l.fe_bytes(self.extended_ifft_divisor)),
                                                 _l.ptr(_l.fe_bytes(self.g_coset)), ctypes.c_size_t(out_len), _l.ptr(out),
                                                 _l.REPR_CANONICAL))
+        return out
+
+    # ---- device-resident forms: asynchronous, no host copies
+    def lagrange_to_coeff_resident(self, a: "ResidentPoly", out: Optional["ResidentPoly"] = None) -> "ResidentPoly":
+        out = a if out is None else out
+        _l.check(_l.init().h2_poly_lagrange_to_coeff(out._h, a._h, ctypes.c_uint32(self.k), _l.ptr(_l.fe_bytes(self.omega_inv)),
+                                                     _l.ptr(_l.fe_bytes(self.ifft_divisor)), _l.REPR_CANONICAL))
+        return out
+
+    def coeff_to_extended_resident(self, a: "ResidentPoly", out: Optional["ResidentPoly"] = None) -> "ResidentPoly":
+        out = ResidentPoly(self.field, self.extended_len()) if out is None else out
+        _l.check(_l.init().h2_poly_coeff_to_extended(out._h, a._h, ctypes.c_uint32(self.k), ctypes.c_uint32(self.extended_k),
+                                                     _l.ptr(_l.fe_bytes(self.g_coset)), _l.ptr(_l.fe_bytes(self.extended_omega)),
+                                                     _l.REPR_CANONICAL))
+        return out
+
+    def extended_to_coeff_resident(self, a: "ResidentPoly", out: Optional["ResidentPoly"] = None) -> "ResidentPoly":
+        out_len = self.n * self.quotient_poly_degree
+        out = ResidentPoly(self.field, out_len) if out is None else out
+        _l.check(_l.init().h2_poly_extended_to_coeff(out._h, a._h, ctypes.c_uint32(self.extended_k),
+                                                     _l.ptr(_l.fe_bytes(self.extended_omega_inv)),
+                                                     _l.ptr(_l.fe_bytes(self.extended_ifft_divisor)), _l.ptr(_l.fe_bytes(self.g_coset)),
+                                                     ctypes.c_size_t(out_len), _l.REPR_CANONICAL))
         return out

@@ -103,6 +103,29 @@ int h2_ipa_finish(uint64_t session, int repr, void *out_c_b);
 
 /* Window size override for the sweep in BASELINE.json config 3 (0 = automatic). */
 int h2_set_window_bits(uint32_t c);
+/* ---- Device-resident polynomials (the quotient pipeline without a PCIe round trip per
+ * call).  A polynomial lives in HBM in Montgomery form; the transforms below are the resident forms of
+ * h2_intt_scaled / h2_coeff_to_extended / h2_extended_to_coeff (poly/domain.rs:227-255, :303-325) and are asynchronous
+ * (stream-ordered); h2_msm_registered_polys is Params::commit / commit_lagrange (poly/commitment.rs:119-150) of `batch`
+ * resident polynomials in one pass.  `repr` is the encoding of the host-side constants / blinds / results.
+ *
+ *   h2_poly_alloc(field, n, &v); h2_poly_upload(v, values, n, repr);          // Lagrange values, once
+ *   h2_poly_lagrange_to_coeff(v, v, k, omega_inv, ifft_divisor, repr);        // in place
+ *   h2_msm_registered_polys(params_g, &v, 1, n, &blind, repr, commitment);
+ *   h2_poly_alloc(field, 4 n, &e); h2_poly_coeff_to_extended(e, v, k, k + 2, zeta, ext_omega, repr);
+ *   h2_poly_download(e, evals, 4 n, repr);                                    // for the h(X) evaluation on the host
+ */
+int h2_poly_alloc(int field, size_t len, uint64_t *poly);
+int h2_poly_free(uint64_t poly);
+int h2_poly_upload(uint64_t poly, const void *src, size_t len, int repr);
+int h2_poly_download(uint64_t poly, void *dst, size_t len, int repr);
+int h2_poly_lagrange_to_coeff(uint64_t dst, uint64_t src, uint32_t k, const void *omega_inv, const void *divisor, int repr);
+int h2_poly_coeff_to_extended(uint64_t dst, uint64_t src, uint32_t k, uint32_t ext_k, const void *zeta, const void *ext_omega, int repr);
+int h2_poly_extended_to_coeff(uint64_t dst, uint64_t src, uint32_t ext_k, const void *ext_omega_inv, const void *ext_divisor,
+                              const void *zeta, size_t out_len, int repr);
+int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
+                            void *out_xyz);
+
 /* Reference sort of the MSM: by default every (point, window) reference is binned in ONE pass into fixed-capacity
  * per-bucket bins, with an automatic fallback to the exact histogram / scan / scatter sort when a bin overflows
  * (heavily repeated scalars).  exact_only != 0 forces the exact sort.  Same result; for A/B runs and tests. */

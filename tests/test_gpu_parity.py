@@ -497,6 +497,49 @@ def test_msm_chunked_upload(eng):
         L.check(lib.h2_test_set_chunk_threshold(19))
 
 
+def test_resident_polynomials(eng):
+    """The device-resident pipeline (upload once; lagrange -> coeff -> extended -> coeff and commits on handles) gives
+    exactly what the host-buffer calls -- and therefore the oracle -- give."""
+    field, curve, k, j = "fp", "vesta", 9, 5
+    n = 1 << k
+    zeta = pasta.zeta_candidates(field)[0]
+    dom = eng.EvaluationDomain(field, j, k, zeta)
+    g = cref.gen_points(curve, SEED + 500, n + 1)
+    params = eng.Params(curve, k, g[:n], g[:n], g[n:])
+    vals = [cref.gen_scalars(field, SEED + 501 + i, n) for i in range(3)]
+    vals[2] = cref.ints_to_bytes([i & 1 for i in range(n)])
+    blinds = [eng.Blind(3 + i) for i in range(3)]
+    res = [eng.ResidentPoly(field, n, v) for v in vals]
+    assert (res[0].download() == vals[0]).all()
+    # commit_lagrange on the values, then to coefficients in place, commit again, extend, come back
+    want = params.commit_lagrange_many(vals, blinds)
+    got = params.commit_resident(res, blinds, lagrange=True)
+    assert (got == want).all()
+    for r in res:
+        dom.lagrange_to_coeff_resident(r)
+    coeffs = [dom.lagrange_to_coeff(v) for v in vals]
+    for r, cf in zip(res, coeffs):
+        assert (r.download() == cf).all()
+    assert (params.commit_resident(res, blinds) == params.commit_many(coeffs, blinds)).all()
+    assert (params.commit_resident(res[:1], blinds[:1])[0] == params.commit(coeffs[0], blinds[0])).all()
+    ext = dom.coeff_to_extended_resident(res[0])
+    want_ext = dom.coeff_to_extended(coeffs[0])
+    assert (ext.download() == want_ext).all()
+    back = dom.extended_to_coeff_resident(ext)
+    assert (back.download() == dom.extended_to_coeff(want_ext)).all()
+    o = pasta.EvaluationDomain(field, j, k, zeta)
+    assert cref.bytes_to_ints(res[1].download()) == o.lagrange_to_coeff(cref.bytes_to_ints(vals[1]))   # and the oracle
+    # misuse fails loudly
+    from halo2_b200 import lib as L
+    with pytest.raises(L.H2Error):
+        dom.lagrange_to_coeff_resident(eng.ResidentPoly(field, n // 2))
+    with pytest.raises(L.H2Error):
+        params.commit_resident([eng.ResidentPoly("fq", n)], blinds[:1])
+    for r in res + [ext, back]:
+        r.close()
+    params.close()
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS
