@@ -32,6 +32,17 @@ extern "C" {
     pub fn h2_bases_release(handle: u64) -> c_int;
     pub fn h2_msm_registered_batch(handle: u64, scalars: *const c_void, n: usize, extra_scalars: *const c_void, batch: usize,
                                    repr: c_int, out_xyz: *mut c_void) -> c_int;
+    pub fn h2_poly_alloc(field: c_int, len: usize, poly: *mut u64) -> c_int;
+    pub fn h2_poly_free(poly: u64) -> c_int;
+    pub fn h2_poly_upload(poly: u64, src: *const c_void, len: usize, repr: c_int) -> c_int;
+    pub fn h2_poly_download(poly: u64, dst: *mut c_void, len: usize, repr: c_int) -> c_int;
+    pub fn h2_poly_lagrange_to_coeff(dst: u64, src: u64, k: u32, omega_inv: *const c_void, divisor: *const c_void, repr: c_int) -> c_int;
+    pub fn h2_poly_coeff_to_extended(dst: u64, src: u64, k: u32, ext_k: u32, zeta: *const c_void, ext_omega: *const c_void,
+                                     repr: c_int) -> c_int;
+    pub fn h2_poly_extended_to_coeff(dst: u64, src: u64, ext_k: u32, ext_omega_inv: *const c_void, ext_divisor: *const c_void,
+                                     zeta: *const c_void, out_len: usize, repr: c_int) -> c_int;
+    pub fn h2_msm_registered_polys(bases_handle: u64, polys: *const u64, batch: usize, n: usize, extra_scalars: *const c_void,
+                                   repr: c_int, out_xyz: *mut c_void) -> c_int;
     pub fn h2_ipa_begin(bases_handle: u64, k: u32, p_prime: *const c_void, x3: *const c_void, repr: c_int, session: *mut u64) -> c_int;
     pub fn h2_ipa_round(session: u64, z: *const c_void, l_rand: *const c_void, r_rand: *const c_void, repr: c_int,
                         out_lr_xyz: *mut c_void) -> c_int;
