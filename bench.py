@@ -417,7 +417,19 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("msm_accum0_kernel", {}).get("dram_bytes_per_launch")
-    roofline = {"kernel": "msm_accum0_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    # the pipe that actually bounds it: 255-bit modular multiplies on the INT32 multiply-add pipe.  Peak = the multiply
+    # microbenchmark measured live at full occupancy (h2_bench_field_mul: 4 dependent-chain multiplies per thread and
+    # iteration, 64 warps per SM); achieved = multiplies the kernel must execute / its duration.
+    # One mixed addition = 8M + 2S; one addition per (point, window) reference: 2 x 8 windows per pair with the GLV split.
+    mm = ctypes.c_float()
+    L.check(lib.h2_bench_field_mul(0, 256, 148 * 8, 2000, ctypes.byref(mm)))
+    peak_gmul = 256 * 148 * 8 * 2000 * 4 / (mm.value * 1e-3) / 1e9
+    refs_per_pair = 16
+    achieved_gmul = n * refs_per_pair * 10 / (k_ms * 1e-3) / 1e9
+    compute = {"pipe": "INT32 multiply-add (fmaheavy)", "unit": "G modmul/s", "achieved": achieved_gmul, "peak": peak_gmul,
+               "frac": achieved_gmul / peak_gmul, "modmul_per_launch": n * refs_per_pair * 10,
+               "peak_source": "h2_bench_field_mul measured in this run (Montgomery multiply microbenchmark, 64 warps/SM)"}
+    roofline = {"kernel": "msm_accum0_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "compute": compute,
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": MSM_BYTES_PER_PAIR * n, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                 "peak_source": peak_src,
                 "note": "255-bit modular integer work: the limiter is the INT32 multiply-add pipe, not HBM (DESIGN.md section 5)"}
