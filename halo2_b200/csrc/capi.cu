@@ -13,6 +13,7 @@
 
 #include "../../include/halo2_b200.h"
 #define H2_MAX_UPLOAD_CHUNKS 4
+#define H2_MSM_QUAD_ACCUM_REFS (1ull << 20)   // up to this many references the accumulation runs one quad per work item
 #include "msm.cuh"
 #include "ipa.cuh"
 #include "ntt.cuh"
@@ -451,6 +452,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     auto k_ibases = msm_item_bases_kernel<P, PS>;
     auto k_iplace = msm_item_place_kernel<P, PS>;
     auto k_accum0 = msm_accum0_kernel<P, PS>;
+    auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
     auto k_accumN = msm_accumN_kernel<P, PS>;
     auto k_rest = msm_accum_rest_kernel<P, PS>;
     auto k_reduceA = msm_reduceA_kernel<P, PS>;
@@ -483,7 +485,8 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
             LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
         }
         prof_begin(PROF_MSM_ACCUM0, s);
-        LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+        if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);   // latency-bound: quads
+        else LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
         prof_end(s);
         if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
         if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);

@@ -234,6 +234,37 @@ template <class P> H2_D void xyzz_add_quad(xyzz &a, const xyzz &b) {
     a.x = x3; a.y = fe_sub<P>(t1, t2);
     a.zz = zz3; a.zzz = zzz3;
 }
+// acc += affine p for a QUAD (madd-2008-s, 8M + 2S, 4 levels deep):
+//   (u2, s2) -> (pp^2, r^2) -> (pp^3, q, zz3) -> (r (q - x3), y1 pp^3, zzz3)
+// for SMALL accumulations (k <= 16 commits, IPA rounds), where the kernel's duration is the longest bucket's serial chain.
+template <class P> H2_D void xyzz_add_mixed_quad(xyzz &a, const affine &p) {
+    if (affine_is_identity(p)) return;                   // all tests are uniform within the quad
+    if (xyzz_is_identity(a)) { a = xyzz_from_affine<P>(p); return; }
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);
+    const bool s0 = sub == 0, s1_ = sub == 1;
+    // level 1: u2 = p.x a.zz | s2 = p.y a.zzz
+    fe r_ = fe_mul<P>(fe_select(s0, p.x, p.y), fe_select(s0, a.zz, a.zzz));
+    fe u2 = quad_bcast(r_, 0, mask), s2 = quad_bcast(r_, 1, mask);
+    fe pp = fe_sub<P>(u2, a.x);
+    fe r = fe_sub<P>(s2, a.y);
+    if (fe_is_zero(pp)) {
+        if (fe_is_zero(r)) a = xyzz_double_affine<P>(p);   // same point
+        else a = xyzz_identity();                          // opposite points
+        return;
+    }
+    // level 2: pp^2 | r^2
+    r_ = fe_sqr<P>(fe_select(s0, pp, r));
+    fe pp2 = quad_bcast(r_, 0, mask), rr = quad_bcast(r_, 1, mask);
+    // level 3: pp^3 | q = a.x pp^2 | zz3 = a.zz pp^2
+    r_ = fe_mul<P>(fe_select(s0, pp, fe_select(s1_, a.x, a.zz)), pp2);
+    fe ppp = quad_bcast(r_, 0, mask), q = quad_bcast(r_, 1, mask), zz3 = quad_bcast(r_, 2, mask);
+    fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(rr, ppp), q), q);
+    // level 4: r (q - x3) | a.y pp^3 | zzz3 = a.zzz pp^3
+    r_ = fe_mul<P>(fe_select(s0, r, fe_select(s1_, a.y, a.zzz)), fe_select(s0, fe_sub<P>(q, x3), ppp));
+    fe t1 = quad_bcast(r_, 0, mask), t2 = quad_bcast(r_, 1, mask), zzz3 = quad_bcast(r_, 2, mask);
+    a.x = x3; a.y = fe_sub<P>(t1, t2);
+    a.zz = zz3; a.zzz = zzz3;
+}
 template <class P> H2_D void xyzz_shift_quad(xyzz &a, uint32_t k) {
     if (k == 0 || xyzz_is_identity(a)) return;          // uniform within the quad
     const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);
