@@ -58,7 +58,7 @@ struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // uploads that may overlap compute (bases of a one-shot MSM)
-    cudaEvent_t ev_scalars_up = nullptr, ev_bases_up[H2_MAX_UPLOAD_CHUNKS] = {};
+    cudaEvent_t ev_scalars_up = nullptr, ev_bases_up[H2_MAX_UPLOAD_CHUNKS] = {}, ev_scal_up[H2_MAX_UPLOAD_CHUNKS] = {};
     uint32_t chunk_min_log = 19;             // one-shot MSMs of >= 2^19 points upload their bases in chunks
     cudaEvent_t last_use = nullptr;
     bool have_last = false;
@@ -147,7 +147,10 @@ extern "C" int h2_init(int device) {
     CU(cudaEventCreateWithFlags(&g_ctx.last_use, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&g_ctx.ev_scalars_up, cudaEventDisableTiming));
-    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) CU(cudaEventCreateWithFlags(&g_ctx.ev_bases_up[j], cudaEventDisableTiming));
+    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) {
+        CU(cudaEventCreateWithFlags(&g_ctx.ev_bases_up[j], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&g_ctx.ev_scal_up[j], cudaEventDisableTiming));
+    }
     g_ctx.device = device;
     g_ctx.ready = true;
     return 0;
@@ -173,7 +176,7 @@ extern "C" int h2_shutdown(void) {
     for (IpaSession *q : g_ctx.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     g_ctx.ipa_pool.clear();
     cudaEventDestroy(g_ctx.ev_scalars_up);
-    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) cudaEventDestroy(g_ctx.ev_bases_up[j]);
+    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) { cudaEventDestroy(g_ctx.ev_bases_up[j]); cudaEventDestroy(g_ctx.ev_scal_up[j]); }
     cudaStreamDestroy(g_ctx.copy_stream);
     cudaEventDestroy(g_ctx.last_use);
     cudaStreamDestroy(g_ctx.stream);
@@ -366,7 +369,7 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s, const uin
 }
 
 // Arrival of the bases of a one-shot MSM in `k` chunks (events on the copy stream): chunk j = points [j n / k, (j + 1) n / k).
-struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS]; };
+struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS], ev_scal[H2_MAX_UPLOAD_CHUNKS]; };   // bases / scalars of chunk j have landed
 
 // fixed != 0: d_bases is a window table (stride points per window) built with window size c.
 // bc != nullptr: the bases arrive chunk by chunk while this runs.  Each chunk is then sorted and accumulated on its own
@@ -463,6 +466,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     for (uint32_t j = 0; j < K; j++) {
         const MsmPlan &q = pk[j];
         const MsmBuffers &M = Mk[j];
+        if (bc && bc->k) {   // the scalars of this chunk (K == 1: of every chunk of the upload)
+            for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev_scal[e], 0));
+        }
         // K2/K3: the (point, window) references sorted by bucket -- a single pass into per-bucket bins; the exact
         // histogram / scan / scatter kernels run only if a bin overflowed (flags[1], set by the bin kernel) or if there
         // are no bins (set here)
@@ -475,11 +481,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
         LAUNCH(k_ibases, 1, 32, 0, s, q, M);
         LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
-    }
-    for (uint32_t j = 0; j < K; j++) {
-        const MsmPlan &q = pk[j];
-        const MsmBuffers &M = Mk[j];
-        if (bc && bc->k) CU(cudaStreamWaitEvent(s, bc->ev[bc->k > 1 ? j : 0], 0));   // the sort above only needed the scalars
+        if (bc && bc->k) {   // the sort above only needed the scalars
+            for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev[e], 0));
+        }
         if (q.glv) {
             auto k_phi = msm_phi_kernel<P, PS>;
             LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
@@ -568,26 +572,32 @@ static int msm_host_common(int curve, const void *scalars, size_t n_scalars, con
     cudaStream_t s = X.stream;
     if (scratch_acquire(s)) return 1;
     if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
-    if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
-    if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
     BasesChunks bc;
     if (host_bases && n_total) {
+        // One-shot MSM: everything goes up on the copy stream, interleaved per chunk -- scalars of chunk j, then its
+        // bases -- so that the sort of chunk j starts when its scalars have landed and its accumulation when its bases
+        // have, while chunk j + 1 is on the link.
+        // (2 chunks from 2^chunk_min_log points, 4 from 8x that: every chunk pays its own sort / work-item launches)
         cudaStream_t cs = X.copy_stream;
         CU(cudaEventRecord(X.ev_scalars_up, s));
-        CU(cudaStreamWaitEvent(cs, X.ev_scalars_up, 0));      // scalars first on the PCIe link (and after prior scratch users)
-        // large inputs go up in chunks: the engine accumulates chunk j while chunk j + 1 is on the link
-        // (2 chunks from 2^chunk_min_log points, 4 from 8x that: every chunk pays its own sort / work-item launches)
+        CU(cudaStreamWaitEvent(cs, X.ev_scalars_up, 0));      // after the prior users of the scratch buffers
         bc.k = 1;
         if (n_total >= ((size_t)1 << X.chunk_min_log) && n_total >= 4 * H2_MAX_UPLOAD_CHUNKS)
             bc.k = n_total >= ((size_t)8 << X.chunk_min_log) ? H2_MAX_UPLOAD_CHUNKS : 2u;
         affine *db = const_cast<affine *>(d_bases);
         for (uint32_t j = 0; j < bc.k; j++) {
             size_t lo = (size_t)((unsigned __int128)n_total * j / bc.k), hi = (size_t)((unsigned __int128)n_total * (j + 1) / bc.k);
+            CU(cudaMemcpyAsync(X.scal_in.as<fe>() + lo, (const fe *)scalars + lo, (hi - lo) * sizeof(fe), cudaMemcpyHostToDevice, cs));
+            CU(cudaEventRecord(X.ev_scal_up[j], cs));
+            bc.ev_scal[j] = X.ev_scal_up[j];
             CU(cudaMemcpyAsync(db + lo, (const affine *)host_bases + lo, (hi - lo) * sizeof(affine), cudaMemcpyHostToDevice, cs));
             if (repr == H2_REPR_CANONICAL && convert_points(curve, db + lo, hi - lo, 1, cs)) return 1;
             CU(cudaEventRecord(X.ev_bases_up[j], cs));
             bc.ev[j] = X.ev_bases_up[j];
         }
+    } else {
+        if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
     }
     int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
                           repr == H2_REPR_CANONICAL, s, fixed, stride, bc.k ? &bc : nullptr);
