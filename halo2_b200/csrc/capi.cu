@@ -31,11 +31,13 @@ static int fail(const std::string &m) { g_err = m; return 1; }
         if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));          \
     } while (0)
 
+static uint64_t g_alloc_gen = 0;   // bumped by every (re)allocation or release: cached CUDA graphs hold raw pointers
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
+        g_alloc_gen++;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -43,7 +45,7 @@ struct DevBuf {
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); g_alloc_gen++; } p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -52,6 +54,16 @@ struct BaseSet { int curve; size_t n; DevBuf buf; DevBuf table; uint32_t c = 0, 
 
 struct PolyBuf { int field; size_t len; DevBuf buf; };   // device-resident polynomial, Montgomery form, len + 1 slots
 struct IpaSession { uint64_t bases; uint32_t k, round; int folded; DevBuf p, b, s, scal, out; };
+
+// A fixed-base MSM over resident bases is ~25 small launches whose parameters repeat call after call (same table, same
+// scratch, same sizes): the second call with a given key is captured into a CUDA graph, later ones replay it.
+struct MsmGraph {
+    const void *scalars, *bases, *out;
+    size_t n; uint64_t stride, gen;
+    uint32_t c, sets; int scalars_mont, out_canonical;
+    uint32_t seen = 0; uint64_t launches = 0, stamp = 0;
+    cudaGraphExec_t exec = nullptr;
+};
 
 struct Context {
     bool ready = false;
@@ -76,6 +88,9 @@ struct Context {
     std::map<uint64_t, BaseSet *> bases;
     std::map<uint64_t, IpaSession *> ipa;
     std::map<uint64_t, PolyBuf *> polys;
+    std::vector<MsmGraph> graphs;
+    uint64_t graph_stamp = 0;
+    uint32_t graphs_on = 1;
     std::vector<IpaSession *> ipa_pool;      // finished sessions keep their buffers for the next proof (no cudaMalloc per opening)
     uint64_t next_handle = 1;
 };
@@ -173,6 +188,8 @@ extern "C" int h2_shutdown(void) {
     g_ctx.ipa.clear();
     for (auto &kv : g_ctx.polys) { kv.second->buf.release(); delete kv.second; }
     g_ctx.polys.clear();
+    for (auto &ge : g_ctx.graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    g_ctx.graphs.clear();
     for (IpaSession *q : g_ctx.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     g_ctx.ipa_pool.clear();
     cudaEventDestroy(g_ctx.ev_scalars_up);
@@ -203,6 +220,12 @@ extern "C" int h2_test_last_msm_flags(uint32_t *out) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(f, g_ctx.last_flags, sizeof f, cudaMemcpyDeviceToHost));
     *out = (f[0] ? 1u : 0u) | (f[1] ? 2u : 0u);
+    return 0;
+}
+// test hook: CUDA-graph replay of fixed-base MSMs on / off
+extern "C" int h2_test_set_graphs(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ctx.graphs_on = on ? 1u : 0u;
     return 0;
 }
 // test hook: one-shot MSMs (h2_msm) of >= 2^log2_n points upload their bases in chunks (default 19)
@@ -442,67 +465,120 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     }
     X.last_flags = Mk[0].flags;
 
-    CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
-    CU(cudaMemsetAsync(X.cursor.p, 0, K * 2 * p.G * 4, s));
-    CU(cudaMemsetAsync(X.size_hist.p, 0, K * small_words * 4, s));
-    CU(cudaMemsetAsync(X.bucket_sum.p, 0, K * p.G * sizeof(xyzz), s));
-    CU(cudaMemsetAsync(X.pkey.p, 0xff, K * part_total * 4, s));
-
-    auto k_bin = msm_bin_kernel<P, PS>;
-    auto k_hist = msm_hist_kernel<P, PS>;
-    auto k_scatter = msm_scatter_kernel<P, PS>;
-    auto k_ihist = msm_item_hist_kernel<P, PS>;
-    auto k_ibases = msm_item_bases_kernel<P, PS>;
-    auto k_iplace = msm_item_place_kernel<P, PS>;
-    auto k_accum0 = msm_accum0_kernel<P, PS>;
-    auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
-    auto k_accumN = msm_accumN_kernel<P, PS>;
-    auto k_rest = msm_accum_rest_kernel<P, PS>;
-    auto k_reduceA = msm_reduceA_kernel<P, PS>;
-    auto k_r0 = msm_r0_kernel<P, PS>;
-    auto k_r1 = msm_r1_kernel<P, PS>;
-    auto k_wsum = msm_wsum_kernel<P, PS>;
-    auto k_final = msm_final_kernel<P, PS>;
-    for (uint32_t j = 0; j < K; j++) {
-        const MsmPlan &q = pk[j];
-        const MsmBuffers &M = Mk[j];
-        if (bc && bc->k) {   // the scalars of this chunk (K == 1: of every chunk of the upload)
-            for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev_scal[e], 0));
-        }
-        // K2/K3: the (point, window) references sorted by bucket -- a single pass into per-bucket bins; the exact
-        // histogram / scan / scatter kernels run only if a bin overflowed (flags[1], set by the bin kernel) or if there
-        // are no bins (set here)
-        if (q.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
-        else LAUNCH(k_bin, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
-        LAUNCH(k_hist, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
-        if (exclusive_scan_u32(M.counts, q.G + 1, s, M.flags + 1)) return 1;
-        LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
-        // K4: work items (one per bucket, oversized buckets split), largest first
-        LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
-        LAUNCH(k_ibases, 1, 32, 0, s, q, M);
-        LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
-        if (bc && bc->k) {   // the sort above only needed the scalars
-            for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev[e], 0));
-        }
-        if (q.glv) {
-            auto k_phi = msm_phi_kernel<P, PS>;
-            LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
-        }
-        prof_begin(PROF_MSM_ACCUM0, s);
-        if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);   // latency-bound: quads
-        else LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
-        prof_end(s);
-        if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
-        if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);
-        if (q.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, q, M);
+    {   // scratch of the scan (sized here so that nothing allocates while a graph is being captured)
+        const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
+        if (X.scan_blocks.ensure((size_t)((p.G + 1 + per_block - 1) / per_block) * 4 + 16)) return 1;
     }
-    // K5: bucket reduce (adds the per-chunk bucket sums) and window combine
-    const MsmBuffers &M = Mk[0];
-    LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1 * 4, 128), 128, 0, s, p, M);                    // quads
-    LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0) * 4, 128), 128, 0, s, p, M);
-    LAUNCH(k_r1, p.Wb * p.r1_rows, 4 * H2_R1_QUADS, 0, s, p, M);
-    LAUNCH(k_wsum, p.Wb, 128, 0, s, p, M);
-    LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
+    auto issue = [&]() -> int {
+        CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
+        CU(cudaMemsetAsync(X.cursor.p, 0, K * 2 * p.G * 4, s));
+        CU(cudaMemsetAsync(X.size_hist.p, 0, K * small_words * 4, s));
+        CU(cudaMemsetAsync(X.bucket_sum.p, 0, K * p.G * sizeof(xyzz), s));
+        CU(cudaMemsetAsync(X.pkey.p, 0xff, K * part_total * 4, s));
+
+        auto k_bin = msm_bin_kernel<P, PS>;
+        auto k_hist = msm_hist_kernel<P, PS>;
+        auto k_scatter = msm_scatter_kernel<P, PS>;
+        auto k_ihist = msm_item_hist_kernel<P, PS>;
+        auto k_ibases = msm_item_bases_kernel<P, PS>;
+        auto k_iplace = msm_item_place_kernel<P, PS>;
+        auto k_accum0 = msm_accum0_kernel<P, PS>;
+        auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
+        auto k_accumN = msm_accumN_kernel<P, PS>;
+        auto k_rest = msm_accum_rest_kernel<P, PS>;
+        auto k_reduceA = msm_reduceA_kernel<P, PS>;
+        auto k_r0 = msm_r0_kernel<P, PS>;
+        auto k_r1 = msm_r1_kernel<P, PS>;
+        auto k_wsum = msm_wsum_kernel<P, PS>;
+        auto k_final = msm_final_kernel<P, PS>;
+        for (uint32_t j = 0; j < K; j++) {
+            const MsmPlan &q = pk[j];
+            const MsmBuffers &M = Mk[j];
+            if (bc && bc->k) {   // the scalars of this chunk (K == 1: of every chunk of the upload)
+                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev_scal[e], 0));
+            }
+            // K2/K3: the (point, window) references sorted by bucket -- a single pass into per-bucket bins; the exact
+            // histogram / scan / scatter kernels run only if a bin overflowed (flags[1], set by the bin kernel) or if there
+            // are no bins (set here)
+            if (q.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
+            else LAUNCH(k_bin, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            LAUNCH(k_hist, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            if (exclusive_scan_u32(M.counts, q.G + 1, s, M.flags + 1)) return 1;
+            LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            // K4: work items (one per bucket, oversized buckets split), largest first
+            LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
+            LAUNCH(k_ibases, 1, 32, 0, s, q, M);
+            LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
+            if (bc && bc->k) {   // the sort above only needed the scalars
+                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev[e], 0));
+            }
+            if (q.glv) {
+                auto k_phi = msm_phi_kernel<P, PS>;
+                LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
+            }
+            prof_begin(PROF_MSM_ACCUM0, s);
+            if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);   // latency-bound: quads
+            else LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+            prof_end(s);
+            if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
+            if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);
+            if (q.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, q, M);
+        }
+        // K5: bucket reduce (adds the per-chunk bucket sums) and window combine
+        const MsmBuffers &M = Mk[0];
+        LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1 * 4, 128), 128, 0, s, p, M);                    // quads
+        LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0) * 4, 128), 128, 0, s, p, M);
+        LAUNCH(k_r1, p.Wb * p.r1_rows, 4 * H2_R1_QUADS, 0, s, p, M);
+        LAUNCH(k_wsum, p.Wb, 128, 0, s, p, M);
+        LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
+        return 0;
+    };
+    // fixed-base MSM over resident bases: capture the second call with a given set of parameters, replay afterwards
+    if (!(fixed && !bc && X.graphs_on && !g_prof_on)) return issue();
+    MsmGraph *ge = nullptr;
+    for (auto &e : X.graphs)
+        if (e.scalars == d_scalars && e.bases == d_bases && e.out == d_out && e.n == n && e.stride == stride && e.c == c && e.sets == sets &&
+            e.scalars_mont == scalars_mont && e.out_canonical == out_canonical) { ge = &e; break; }
+    if (ge && ge->gen != g_alloc_gen) {   // some buffer moved since the capture
+        if (ge->exec) cudaGraphExecDestroy(ge->exec);
+        ge->exec = nullptr; ge->seen = 0; ge->gen = g_alloc_gen;
+    }
+    if (!ge) {
+        if (X.graphs.size() >= 16) {   // evict the least recently used entry
+            size_t v = 0;
+            for (size_t i = 1; i < X.graphs.size(); i++) if (X.graphs[i].stamp < X.graphs[v].stamp) v = i;
+            if (X.graphs[v].exec) cudaGraphExecDestroy(X.graphs[v].exec);
+            X.graphs.erase(X.graphs.begin() + v);
+        }
+        MsmGraph e;
+        e.scalars = d_scalars; e.bases = d_bases; e.out = d_out; e.n = n; e.stride = stride; e.gen = g_alloc_gen; e.c = c; e.sets = sets;
+        e.scalars_mont = scalars_mont; e.out_canonical = out_canonical;
+        X.graphs.push_back(e);
+        ge = &X.graphs.back();
+    }
+    ge->stamp = ++X.graph_stamp;
+    if (ge->exec) {
+        CU(cudaGraphLaunch(ge->exec, s));
+        g_launches.fetch_add(ge->launches, std::memory_order_relaxed);
+        return 0;
+    }
+    if (ge->seen++ == 0) return issue();     // first sighting: run eagerly (the buffers may still be growing)
+    const uint64_t l0 = g_launches.load();
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return issue(); }
+    int rc = issue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ge->seen = 0;
+        return rc ? rc : issue();            // capture refused: run eagerly
+    }
+    ge->launches = g_launches.load() - l0;
+    ce = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { ge->exec = nullptr; cudaGetLastError(); return issue(); }
+    CU(cudaGraphLaunch(ge->exec, s));
     return 0;
 }
 

@@ -178,6 +178,9 @@ int h2_test_last_msm_flags(uint32_t *out);
 /* Test hook: h2_msm uploads the bases of inputs with >= 2^log2_n points in chunks that are sorted and accumulated
  * separately while the next chunk is on the PCIe link (default 19). */
 int h2_test_set_chunk_threshold(uint32_t log2_n);
+/* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
+ * parameters on (default); 0 issues every launch individually. */
+int h2_test_set_graphs(int on);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */
 int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out);

@@ -543,6 +543,36 @@ def test_resident_polynomials(eng):
     params.close()
 
 
+def test_fixed_base_graph_replay(eng):
+    """Fixed-base MSMs replay a captured CUDA graph from their third call with the same parameters: six different
+    polynomials in a row (and batches of them) still each give their own commitment; switching the replay off gives
+    the same points."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    curve, c, k = "vesta", pasta.VESTA, 11
+    n = 1 << k
+    g = cref.gen_points(curve, SEED + 600, n + 1)
+    params = eng.Params(curve, k, g[:n], g[:n], g[n:])
+    polys = [cref.gen_scalars(c.scalar, SEED + 601 + i, n) for i in range(6)]
+    polys[4] = cref.ints_to_bytes([i % 3 for i in range(n)])          # overflows the bins: exact sort inside the graph
+    blinds = [eng.Blind(11 + i) for i in range(6)]
+    want = [cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([p, cref.ints_to_bytes([b.value])]), g)) for p, b in zip(polys, blinds)]
+    try:
+        for on in (1, 0, 1):
+            L.check(lib.h2_test_set_graphs(on))
+            for rep in range(2):
+                for i in range(6):
+                    assert _affine(curve, params.commit(polys[i], blinds[i])) == want[i], (on, rep, i)
+            for i in range(0, 6, 3):
+                many = params.commit_many(polys[i:i + 3], blinds[i:i + 3])
+                assert [_affine(curve, x) for x in many] == want[i:i + 3], (on, i)
+                many = params.commit_many(polys[i:i + 3][::-1], blinds[i:i + 3][::-1])
+                assert [_affine(curve, x) for x in many] == want[i:i + 3][::-1]
+    finally:
+        L.check(lib.h2_test_set_graphs(1))
+        params.close()
+
+
 def test_best_multiexp_2pow20(eng):
     """BASELINE.json config 3 at full size (Pallas) against the C restatement."""
     curve, c = "pallas", pasta.PALLAS
