@@ -16,6 +16,9 @@
  *   parallelize        arithmetic.rs:345-362 (chunk = n/threads; if chunk < threads one chunk).
  *   ifft / distribute_powers_zeta / coeff_to_extended / extended_to_coeff
  *                      poly/domain.rs:375-383, :357-373, :241-255, :303-325.
+ *   IPA round loop     poly/commitment/prover.rs:100-142 with parallel_generator_collapse :154-166 and
+ *                      compute_inner_product arithmetic.rs:308-319; the transcript is factored out (challenges and
+ *                      randomness are inputs).
  *
  * The limb arithmetic itself lives in the un-vendored crate pasta_curves 0.5.1
  * (Cargo.lock:1303-1306); it is restated from the definition (4x64 Montgomery, R = 2^256).

@@ -13,6 +13,8 @@ What it restates (all file:line relative to /root/reference/halo2_proofs/src):
   * Params::new's EC-FFT      poly/commitment.rs:77-94   (generators are synthetic, see below)
   * EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff,
     distribute_powers_zeta, ifft}   poly/domain.rs:40-146, 227-255, 303-325, 357-383
+  * the IPA round loop       poly/commitment/prover.rs:100-142, :154-166 (transcript factored out: challenges
+    and randomness are inputs, the points / scalar written to the transcript are outputs)
 
 Third-party arithmetic that is NOT in the reference tree: crate `pasta_curves 0.5.1`
 (Cargo.lock:1303-1306), `ff 0.13.0`, `group 0.13.0`.  Its published algorithm is restated
