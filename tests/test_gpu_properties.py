@@ -41,7 +41,7 @@ def _msm_dev(torch, L, lib, curve, sc, bases, c=0):
     return cref.bytes_to_affine(cref.jac_to_affine(curve, canon))
 
 
-@pytest.mark.parametrize("curve,log_n", [("pallas", 22), ("vesta", 20)])
+@pytest.mark.parametrize("curve,log_n", [("pallas", 22), ("vesta", 20), ("vesta", 24)])   # 2^24: default window 19, 9 k-entry bins
 def test_msm_full_size_consistency(dev, curve, log_n):
     torch, L, lib = dev
     n = 1 << log_n
