@@ -222,6 +222,30 @@ def prover_replay_gpu(h2, cref, reps=3):
     return dt, setup_s, sched, {k_: v * 1e3 / reps for k_, v in by_kind.items()}
 
 
+def params_lagrange_ms(h2, cref, threads, reps=3):
+    """Params::new's g -> g_lagrange derivation at k=14 (poly/commitment.rs:74-101: EC-iFFT = best_fft at G = curve point,
+    * 2^-k, batch_normalize) through h2_params_lagrange, host generators in / host g_lagrange out, next to the C
+    restatement on the host cores (at k=12 when the box has < 32 threads, to keep the run bounded)."""
+    from oracle import pasta
+    k = PROVER_K
+    g = cref.gen_points("vesta", SEED + 80, 1 << k)
+    out = h2.lagrange_generators("vesta", k, g)
+    t0 = time.time()
+    for _ in range(reps):
+        out = h2.lagrange_generators("vesta", k, g)
+    gpu_ms = (time.time() - t0) / reps * 1e3
+    kc = k if threads >= 32 else 12
+    r = pasta.VESTA.r
+    t0 = time.time()
+    want = cref.params_lagrange("vesta", g[:1 << kc], kc, pasta.inv(pasta.omega_for_k("fp", kc), r), pow(pasta.inv(2, r), kc, r), threads)
+    cpu_ms = (time.time() - t0) * 1e3
+    res = {"k": k, "gpu_ms": gpu_ms, "scalar_muls": (k << (k - 1)) + 1,   # k n/2 - (n - 1) twiddle products + n scalings
+           "cpu_baseline": {"k": kc, "ms": cpu_ms, "cores": threads, "kind": "port"}}
+    if kc == k:
+        res["same_result"] = bool((out == want).all())
+    return res
+
+
 def resident_column_ms(h2, cref, reps=5):
     """One advice column's trip through the hot path at k=14 -- commit_lagrange, lagrange_to_coeff, commit,
     coeff_to_extended, extended values back to the host -- with host buffers per call vs device-resident handles."""
@@ -559,6 +583,7 @@ def main():
             for kind, cnt in sched:
                 kinds[kind] = kinds.get(kind, 0) + (cnt if kind.endswith("_many") else 1)
             extra["resident_column_k14"] = resident_column_ms(h2, cref)
+            extra["params_lagrange_k14"] = params_lagrange_ms(h2, cref, threads)
             extra["create_proof_k14_replay"] = {
                 "metric": "hot_path_ms_per_proof", "value": gdt * 1e3, "unit": "ms", "higher_is_better": False,
                 "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": cpu_by_kind,

@@ -58,6 +58,10 @@ extern "C" {
     pub fn h2_extended_to_coeff(field: c_int, a: *const c_void, ext_k: u32, ext_omega_inv: *const c_void,
                                 ext_divisor: *const c_void, zeta: *const c_void, out_len: usize,
                                 out: *mut c_void, repr: c_int) -> c_int;
+    pub fn h2_ec_fft(curve: c_int, points_xyz: *mut c_void, omega: *const c_void, log_n: u32, scale: *const c_void, repr: c_int) -> c_int;
+    pub fn h2_batch_normalize(curve: c_int, points_xyz: *const c_void, n: usize, repr: c_int, out_xy: *mut c_void) -> c_int;
+    pub fn h2_params_lagrange(curve: c_int, g_xy: *const c_void, k: u32, omega_inv: *const c_void, minv: *const c_void, repr: c_int,
+                              out_g_lagrange_xy: *mut c_void) -> c_int;
 }
 
 fn check(rc: c_int) {
@@ -138,6 +142,83 @@ pub fn best_fft<F: PrimeField<Repr = [u8; 32]>>(field_id: c_int, a: &mut [F], om
         r.copy_from_slice(&bytes[32 * i..32 * i + 32]);
         *x = F::from_repr(r).unwrap();
     }
+}
+
+fn affine_from_xy<C: B200Curve>(xy: &[u8]) -> C
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    if xy.iter().all(|b| *b == 0) {
+        return C::identity();
+    }
+    let f = |o: usize| {
+        let mut r = [0u8; 32];
+        r.copy_from_slice(&xy[o..o + 32]);
+        C::Base::from_repr(r).unwrap()
+    };
+    C::from_xy(f(0), f(32)).unwrap()
+}
+fn curves_to_bytes<C: B200Curve>(pts: &[C::Curve]) -> Vec<u8>
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    let mut out = vec![0u8; 96 * pts.len()];
+    for (i, p) in pts.iter().enumerate() {
+        let (x, y, z) = p.jacobian_coordinates();
+        out[96 * i..96 * i + 32].copy_from_slice(x.to_repr().as_ref());
+        out[96 * i + 32..96 * i + 64].copy_from_slice(y.to_repr().as_ref());
+        out[96 * i + 64..96 * i + 96].copy_from_slice(z.to_repr().as_ref());
+    }
+    out
+}
+
+/// Drop-in for `best_fft` with G = C::Curve (arithmetic.rs:192-255 through FftGroup, :17-27; Params::new,
+/// poly/commitment.rs:81-82).
+pub fn best_fft_curve<C: B200Curve>(a: &mut [C::Curve], omega: C::Scalar, log_n: u32)
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    assert_eq!(a.len(), 1 << log_n);
+    let mut bytes = curves_to_bytes::<C>(a);
+    let w = omega.to_repr();
+    check(unsafe {
+        h2_ec_fft(C::CURVE_ID, bytes.as_mut_ptr() as *mut c_void, w.as_ref().as_ptr() as *const c_void, log_n, std::ptr::null(), REPR_CANONICAL)
+    });
+    for (i, p) in a.iter_mut().enumerate() {
+        let mut r = [0u8; 96];
+        r.copy_from_slice(&bytes[96 * i..96 * i + 96]);
+        *p = point_from_xyz::<C>(&r);
+    }
+}
+
+/// Drop-in for `C::Curve::batch_normalize` (plonk/prover.rs:99,311; poly/commitment.rs:65,95).
+pub fn batch_normalize<C: B200Curve>(p: &[C::Curve], q: &mut [C])
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    assert_eq!(p.len(), q.len());
+    let bytes = curves_to_bytes::<C>(p);
+    let mut out = vec![0u8; 64 * p.len()];
+    check(unsafe { h2_batch_normalize(C::CURVE_ID, bytes.as_ptr() as *const c_void, p.len(), REPR_CANONICAL, out.as_mut_ptr() as *mut c_void) });
+    for (i, a) in q.iter_mut().enumerate() {
+        *a = affine_from_xy::<C>(&out[64 * i..64 * i + 64]);
+    }
+}
+
+/// The `g -> g_lagrange` derivation of `Params::new` (poly/commitment.rs:74-101): alpha_inv and minv are the values
+/// computed at :77-80 and :83.
+pub fn params_lagrange<C: B200Curve>(g: &[C], k: u32, alpha_inv: C::Scalar, minv: C::Scalar) -> Vec<C>
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    assert_eq!(g.len(), 1 << k);
+    let b = bases_to_bytes(g);
+    let mut out = vec![0u8; 64 * g.len()];
+    check(unsafe {
+        h2_params_lagrange(C::CURVE_ID, b.as_ptr() as *const c_void, k, alpha_inv.to_repr().as_ref().as_ptr() as *const c_void,
+                           minv.to_repr().as_ref().as_ptr() as *const c_void, REPR_CANONICAL, out.as_mut_ptr() as *mut c_void)
+    });
+    (0..g.len()).map(|i| affine_from_xy::<C>(&out[64 * i..64 * i + 64])).collect()
 }
 
 /// Resident generator set for `Params::{commit, commit_lagrange}` (poly/commitment.rs:119-150):

@@ -6,8 +6,9 @@ include/halo2_b200.h).  There is no CPU fallback: importing works anywhere, but 
 operation raises `H2Error` unless the library is built and a B200 is visible.
 """
 from .lib import H2Error, lib_path, load, init, launch_count  # noqa: F401
-from .arithmetic import best_multiexp, best_fft, multiexp_window_bits  # noqa: F401
-from .poly import Params, EvaluationDomain, Blind, ResidentPoly  # noqa: F401
+from .arithmetic import best_multiexp, small_multiexp, best_fft, best_fft_curve, batch_normalize, multiexp_window_bits  # noqa: F401
+from .poly import Params, EvaluationDomain, Blind, ResidentPoly, lagrange_generators  # noqa: F401
 
-__all__ = ["H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "best_fft",
-           "multiexp_window_bits", "Params", "EvaluationDomain", "Blind", "ResidentPoly"]
+__all__ = ["H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "small_multiexp", "best_fft",
+           "best_fft_curve", "batch_normalize", "multiexp_window_bits", "Params", "EvaluationDomain", "Blind", "ResidentPoly",
+           "lagrange_generators"]

@@ -17,6 +17,7 @@
 #include "msm.cuh"
 #include "ipa.cuh"
 #include "ntt.cuh"
+#include "ecfft.cuh"
 
 using namespace h2;
 
@@ -78,11 +79,14 @@ struct Context {
     const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
     uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
+    uint32_t ecfft_quad = 1;                 // EC-FFT butterflies run on quads of lanes (0: one thread each, test hook)
     // MSM scratch
     DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
         wsum, scan_blocks, result, misc;
     // NTT scratch
     DevBuf ntt_io, ntt_out, ntt_work, pow2;
+    // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms
+    DevBuf ec_work, ec_io, ec_out;
     std::vector<TwiddleEntry *> twiddles;
     uint64_t tw_stamp = 0;
     std::map<uint64_t, BaseSet *> bases;
@@ -178,7 +182,7 @@ extern "C" int h2_shutdown(void) {
     DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.bases_phi, &g_ctx.glv_parts, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
                      &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
                      &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
-                     &g_ctx.ntt_work, &g_ctx.pow2};
+                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out};
     for (DevBuf *b : all) b->release();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
@@ -226,6 +230,12 @@ extern "C" int h2_test_last_msm_flags(uint32_t *out) {
 extern "C" int h2_test_set_graphs(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_ctx.graphs_on = on ? 1u : 0u;
+    return 0;
+}
+// test hook: EC-FFT butterflies on quads of lanes (default) or one thread each
+extern "C" int h2_test_set_ecfft_quad(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ctx.ecfft_quad = on ? 1u : 0u;
     return 0;
 }
 // test hook: one-shot MSMs (h2_msm) of >= 2^log2_n points upload their bases in chunks (default 19)
@@ -961,6 +971,101 @@ extern "C" int h2_ntt_clear_cache(void) {
     cudaDeviceSynchronize();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EC-FFT (best_fft with G = curve point) and batch normalisation (ecfft.cuh)
+// ------------------------------------------------------------------------------------------------
+// the log n butterfly stages (+ the optional `*g *= scale` pass) on an XYZZ work array already in network order
+template <class P, class PS>
+static int ecfft_stages(int scalar_field, xyzz *work, uint32_t log_n, const fe &omega_mont, const fe *scale_canon, cudaStream_t s) {
+    const fe *tw = nullptr;
+    if (get_twiddles<PS>(scalar_field, omega_mont, log_n, s, &tw)) return 1;
+    const uint64_t n = 1ull << log_n;
+    // one QUAD of lanes per butterfly (ecfft.cuh) unless the test hook asks for the one-thread form
+    const uint32_t q = g_ctx.ecfft_quad ? 4u : 1u;
+    auto stage = g_ctx.ecfft_quad ? ecfft_stage_quad_kernel<P, PS> : ecfft_stage_kernel<P, PS>;
+    for (uint32_t st = 1; st <= log_n; st++) LAUNCH(stage, blocks_for(n / 2 * q, 64), 64, 0, s, work, tw, log_n, st);
+    if (scale_canon) {
+        auto sc = g_ctx.ecfft_quad ? ecfft_scale_quad_kernel<P, PS> : ecfft_scale_kernel<P, PS>;
+        LAUNCH(sc, blocks_for(n * q, 64), 64, 0, s, work, *scale_canon, n);
+    }
+    return 0;
+}
+// mode 0: Jacobian in -> Jacobian out (h2_ec_fft); mode 1: affine in -> scaled, normalised affine out (h2_params_lagrange)
+template <class P, class PS>
+static int ecfft_host(int scalar_field, int mode, const void *in, uint32_t log_n, const void *omega, const void *scale, int repr, void *out) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const uint64_t n = 1ull << log_n;
+    const int canon = repr == H2_REPR_CANONICAL;
+    const size_t in_sz = mode == 0 ? sizeof(jacobian) : sizeof(affine);
+    if (scratch_acquire(s)) return 1;
+    if (X.ec_io.ensure(n * sizeof(jacobian)) || X.ec_work.ensure(n * sizeof(xyzz)) || X.ec_out.ensure(n * sizeof(affine))) return 1;
+    CU(cudaMemcpyAsync(X.ec_io.p, in, n * in_sz, cudaMemcpyHostToDevice, s));
+    xyzz *work = X.ec_work.as<xyzz>();
+    if (mode == 0) {
+        auto k = ecfft_load_jac_kernel<P, PS>;
+        LAUNCH(k, blocks_for(n, 128), 128, 0, s, X.ec_io.as<jacobian>(), canon, work, log_n);
+    } else {
+        auto k = ecfft_load_affine_kernel<P, PS>;
+        LAUNCH(k, blocks_for(n, 128), 128, 0, s, X.ec_io.as<affine>(), canon, work, log_n);
+    }
+    fe sc, *scp = nullptr;
+    if (scale) {
+        memcpy(sc.v, scale, 32);
+        if (!canon) sc = fe_from_mont<PS>(sc);
+        scp = &sc;
+    }
+    if (ecfft_stages<P, PS>(scalar_field, work, log_n, host_to_mont<PS>(omega, repr), scp, s)) return 1;
+    if (mode == 0) {
+        auto k = ecfft_store_jac_kernel<P, PS>;
+        LAUNCH(k, blocks_for(n, 128), 128, 0, s, work, X.ec_io.as<jacobian>(), canon, n);
+        CU(cudaMemcpyAsync(out, X.ec_io.p, n * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    } else {
+        LAUNCH(normalize_kernel<P>, blocks_for((n + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64), 64, 0, s, work, (const jacobian *)nullptr, 0,
+               X.ec_out.as<affine>(), canon, n);
+        CU(cudaMemcpyAsync(out, X.ec_out.p, n * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    }
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+static int ecfft_host_dispatch(int curve, int mode, const void *in, uint32_t log_n, const void *omega, const void *scale, int repr, void *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (log_n > 26) return fail("ec_fft: log_n > 26 not supported");
+    if (curve == H2_CURVE_PALLAS) return ecfft_host<FpParams, FqParams>(H2_FIELD_FQ, mode, in, log_n, omega, scale, repr, out);
+    if (curve == H2_CURVE_VESTA) return ecfft_host<FqParams, FpParams>(H2_FIELD_FP, mode, in, log_n, omega, scale, repr, out);
+    return fail("unknown curve id");
+}
+extern "C" int h2_ec_fft(int curve, void *points_xyz, const void *omega, uint32_t log_n, const void *scale, int repr) {
+    return ecfft_host_dispatch(curve, 0, points_xyz, log_n, omega, scale, repr, points_xyz);
+}
+extern "C" int h2_params_lagrange(int curve, const void *g_xy, uint32_t k, const void *omega_inv, const void *minv, int repr, void *out_xy) {
+    if (!minv) return fail("h2_params_lagrange: minv is required (poly/commitment.rs:83)");
+    return ecfft_host_dispatch(curve, 1, g_xy, k, omega_inv, minv, repr, out_xy);
+}
+extern "C" int h2_batch_normalize(int curve, const void *points_xyz, size_t n, int repr, void *out_xy) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    if (n == 0) return 0;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const int canon = repr == H2_REPR_CANONICAL;
+    if (scratch_acquire(s)) return 1;
+    if (X.ec_io.ensure(n * sizeof(jacobian)) || X.ec_out.ensure(n * sizeof(affine))) return 1;
+    CU(cudaMemcpyAsync(X.ec_io.p, points_xyz, n * sizeof(jacobian), cudaMemcpyHostToDevice, s));
+    const uint32_t nb = blocks_for((n + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
+    if (curve == H2_CURVE_PALLAS)
+        LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.ec_io.as<jacobian>(), canon, X.ec_out.as<affine>(), canon, (uint64_t)n);
+    else
+        LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.ec_io.as<jacobian>(), canon, X.ec_out.as<affine>(), canon, (uint64_t)n);
+    CU(cudaMemcpyAsync(out_xy, X.ec_out.p, n * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
     return 0;
 }
 

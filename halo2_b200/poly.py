@@ -29,6 +29,21 @@ class Blind:
         self.value = int(value)
 
 
+def lagrange_generators(curve: str, k: int, g) -> np.ndarray:
+    """g -> g_lagrange, poly/commitment.rs:74-101 (h2_params_lagrange: nothing but g goes up and g_lagrange comes back)."""
+    m = FIELDS[_l.SCALAR_FIELD[curve]]
+    alpha_inv = pow(pow(5, (m - 1) >> S, m), m - 2, m)  # ROOT_OF_UNITY_INV
+    for _ in range(k, S):
+        alpha_inv = alpha_inv * alpha_inv % m  # commitment.rs:77-80
+    minv = pow(pow(2, m - 2, m), k, m)  # TWO_INV^k, :83
+    gb = _l.as_u8(g, 64)
+    assert gb.shape[0] == 1 << k
+    out = np.zeros((1 << k, 64), dtype=np.uint8)
+    _l.check(_l.init().h2_params_lagrange(_l.CURVE_ID[curve], _l.ptr(gb), ctypes.c_uint32(k), _l.ptr(_l.fe_bytes(alpha_inv)),
+                                          _l.ptr(_l.fe_bytes(minv)), _l.REPR_CANONICAL, _l.ptr(out)))
+    return out
+
+
 class Params:
     """poly/commitment.rs:26-33.  g / g_lagrange / w are uploaded once and stay resident in HBM
     (they are immutable for the life of a Params); commit / commit_lagrange only ship the
@@ -56,6 +71,18 @@ class Params:
         both = np.concatenate([self.g_lagrange, self.w])   # g_lagrange ++ [w]     (:146-147)
         _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL,
                                           ctypes.c_uint32(window_bits), ctypes.c_uint32(flags), ctypes.byref(self._h_gl)))
+
+    @classmethod
+    def from_generators(cls, curve: str, k: int, g, w, u=None, **kw) -> "Params":
+        """Params::new (commitment.rs:38-114) from its generators on: g_lagrange is derived on the device exactly as
+        :74-101 does -- EC-iFFT of g with alpha_inv = ROOT_OF_UNITY_INV^(2^(S-k)), every output times 2^-k,
+        batch_normalize.  (The hash_to_curve calls that produce g, w, u, :46-58 and :103-105, live in the un-vendored
+        pasta_curves crate: the caller supplies them, e.g. from Params::read, :185-205.)"""
+        assert k < 32  # commitment.rs:41
+        n = 1 << k
+        gb = _l.as_u8(g, 64)
+        assert gb.shape[0] == n
+        return cls(curve, k, gb, lagrange_generators(curve, k, gb), w, u, **kw)
 
     def _commit(self, handle, poly, r: Blind) -> np.ndarray:
         p = _l.as_u8(poly, 32)

@@ -166,6 +166,20 @@ int h2_ntt_dev(int field, const void *d_in, void *d_out, const void *omega, int 
 /* Drops cached twiddle tables (the next call rebuilds them: "cold" timing). */
 int h2_ntt_clear_cache(void);
 
+/* ---- EC-FFT and batch normalisation: SURVEY.md section 8 rows a15 and (f)2 / (f)4 ------------------- */
+/* best_fft at G = C::Curve (arithmetic.rs:192-295 through the FftGroup bound :17-27; call site
+ * poly/commitment.rs:81-82): in-place butterfly network on 2^log_n Jacobian points (96 B x||y||z, z = 0 identity) with
+ * scalar-field twiddles omega^i, then -- when `scale` is not NULL -- every output multiplied by the scalar `scale`
+ * (`*g *= minv`, poly/commitment.rs:84-89).  omega / scale are elements of the curve's SCALAR field. */
+int h2_ec_fft(int curve, void *points_xyz, const void *omega, uint32_t log_n, const void *scale, int repr);
+/* group::Curve::batch_normalize (call sites plonk/prover.rs:99,311; poly/commitment.rs:65,95; vanishing/prover.rs:108):
+ * n Jacobian points -> n affine points (64 B, identity = zeros), one inversion per 16 points. */
+int h2_batch_normalize(int curve, const void *points_xyz, size_t n, int repr, void *out_xy);
+/* The g -> g_lagrange derivation of Params::new (poly/commitment.rs:74-101) without leaving the device: affine g
+ * (2^k x 64 B) -> EC-iFFT with omega_inv (= alpha_inv, :77-80) -> * minv (= 2^-k, :83-89) -> batch_normalize (:91-101)
+ * -> affine g_lagrange.  (hash_to_curve, :46-58, lives in the un-vendored pasta_curves: the generators are the caller's.) */
+int h2_params_lagrange(int curve, const void *g_xy, uint32_t k, const void *omega_inv, const void *minv, int repr, void *out_g_lagrange_xy);
+
 /* ---- utilities for synthetic workloads and the tests ---------------------------------------- */
 /* d_out[i] = [s_i] * (-1, 2) for pseudo-random 64-bit s_i derived from seed (distinct points),
  * affine Montgomery coordinates; i in [first, first + n). */
@@ -181,6 +195,8 @@ int h2_test_set_chunk_threshold(uint32_t log2_n);
 /* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
  * parameters on (default); 0 issues every launch individually. */
 int h2_test_set_graphs(int on);
+/* EC-FFT butterflies on quads of lanes (default) or one thread each. */
+int h2_test_set_ecfft_quad(int on);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */
 int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out);

@@ -35,7 +35,8 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(_SO)
         for name in ("orc_best_multiexp", "orc_naive_msm", "orc_best_fft", "orc_ifft", "orc_coeff_to_extended",
                      "orc_extended_to_coeff", "orc_field_op", "orc_scalar_mul", "orc_point_add",
-                     "orc_jac_to_affine", "orc_on_curve", "orc_gen_scalars", "orc_gen_points"):
+                     "orc_jac_to_affine", "orc_on_curve", "orc_gen_scalars", "orc_gen_points", "orc_ec_fft",
+                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds"):
             getattr(_lib, name).restype = ctypes.c_int
     return _lib
 
@@ -109,6 +110,46 @@ def extended_to_coeff(field: str, a: np.ndarray, ext_k: int, ext_omega_inv, ext_
     lib().orc_extended_to_coeff(FIELD_ID[field], _p(np.ascontiguousarray(a)), ctypes.c_uint32(ext_k),
                                 _p(_fe(ext_omega_inv)), _p(_fe(ext_divisor)), _p(_fe(zeta)),
                                 ctypes.c_size_t(out_len), _p(out), threads or default_threads())
+    return out
+
+
+def ec_fft(curve: str, points_xyz: np.ndarray, omega, log_n: int, scale=None, threads: Optional[int] = None) -> np.ndarray:
+    """best_fft with G = curve point (arithmetic.rs:192-295; call site poly/commitment.rs:81-82) on (n, 96) canonical
+    Jacobian points, then `*g *= scale` (:84-89) when scale is given.  Returns a new array."""
+    if points_xyz.shape[0] != 1 << log_n:  # arithmetic.rs:205
+        raise AssertionError("best_fft: a.len() != 1 << log_n")
+    a = np.ascontiguousarray(points_xyz, dtype=np.uint8).copy()
+    lib().orc_ec_fft(CURVE_ID[curve], _p(a), _p(_fe(omega)), ctypes.c_uint32(log_n), _p(_fe(scale)) if scale is not None else None,
+                     threads or default_threads())
+    return a
+
+
+def batch_normalize(curve: str, points_xyz: np.ndarray) -> np.ndarray:
+    """group::Curve::batch_normalize: (n, 96) canonical Jacobian -> (n, 64) affine, identity = zeros."""
+    a = np.ascontiguousarray(points_xyz, dtype=np.uint8).reshape(-1, 96)
+    out = np.zeros((a.shape[0], 64), dtype=np.uint8)
+    lib().orc_batch_normalize(CURVE_ID[curve], _p(a), ctypes.c_size_t(a.shape[0]), _p(out))
+    return out
+
+
+def params_lagrange(curve: str, g_xy: np.ndarray, k: int, omega_inv, minv, threads: Optional[int] = None) -> np.ndarray:
+    """poly/commitment.rs:74-101: g -> g_lagrange (EC-iFFT, * 2^-k, batch_normalize)."""
+    g = np.ascontiguousarray(g_xy, dtype=np.uint8)
+    assert g.shape == (1 << k, 64)
+    out = np.zeros((1 << k, 64), dtype=np.uint8)
+    lib().orc_params_lagrange(CURVE_ID[curve], _p(g), ctypes.c_uint32(k), _p(_fe(omega_inv)), _p(_fe(minv)),
+                              threads or default_threads(), _p(out))
+    return out
+
+
+def affine_to_jacobian_bytes(xy: np.ndarray) -> np.ndarray:
+    """(n, 64) affine -> (n, 96) Jacobian with z = 1 (identity: z = 0, y = 1 like pasta's Ep::identity)."""
+    a = np.ascontiguousarray(xy, dtype=np.uint8).reshape(-1, 64)
+    out = np.zeros((a.shape[0], 96), dtype=np.uint8)
+    out[:, :64] = a
+    ident = ~a.any(axis=1)
+    out[~ident, 64] = 1
+    out[ident, 32] = 1
     return out
 
 

@@ -16,6 +16,9 @@
  *   parallelize        arithmetic.rs:345-362 (chunk = n/threads; if chunk < threads one chunk).
  *   ifft / distribute_powers_zeta / coeff_to_extended / extended_to_coeff
  *                      poly/domain.rs:375-383, :357-373, :241-255, :303-325.
+ *   best_fft (G = curve point), batch_normalize, g -> g_lagrange
+ *                      arithmetic.rs:192-295 at G = C::Curve; poly/commitment.rs:74-101 (Params::new without
+ *                      hash_to_curve, which lives in the un-vendored pasta_curves).
  *   IPA round loop     poly/commitment/prover.rs:100-142 with parallel_generator_collapse :154-166 and
  *                      compute_inner_product arithmetic.rs:308-319; the transcript is factored out (challenges and
  *                      randomness are inputs).
@@ -516,6 +519,150 @@ int orc_extended_to_coeff(int field, const uint8_t *in, uint32_t ext_k, const ui
     parallelize_mul(F, v, en, &d, 0, threads);
     parallelize_mul(F, v, en, cp, 1, threads);
     store_vec(F, out, v, out_len < en ? out_len : en); free(v);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- best_fft with G = curve point
+ * arithmetic.rs:192-295 instantiated at G = C::Curve (the FftGroup bound, :17-27): group_add / group_sub are point
+ * additions, group_scale is a scalar multiplication.  Its one call site is Params::new (poly/commitment.rs:77-94):
+ * g_lagrange = EC-iFFT of g, every output then scaled by 2^-k (:84-89) and batch-normalised (:91-101). */
+static void scalar_mul_jac(const field_t *F, jac *r, const uint8_t k[32], const jac *base) {
+    jac acc; jac_identity(F, &acc);
+    for (int i = 255; i >= 0; i--) {
+        jac_double(F, &acc, &acc);
+        if ((k[i >> 3] >> (i & 7)) & 1) jac_add(F, &acc, &acc, base);
+    }
+    *r = acc;
+}
+static inline void jac_neg(const field_t *F, jac *r, const jac *a) { *r = *a; fe_neg(F, &r->y, &a->y); }
+typedef struct { const field_t *F; jac *a; size_t n, tc; const uint8_t *tw; int depth; } ecfft_task;
+static void ec_butterflies(const field_t *F, jac *left, jac *right, size_t half, size_t tc, const uint8_t *tw) {
+    for (size_t i = 0; i < half; i++) {                 /* :276-293 */
+        jac t = right[i], nt;
+        if (i) scalar_mul_jac(F, &t, tw + 32 * (i * tc), &right[i]);
+        jac_neg(F, &nt, &t);
+        jac_add(F, &right[i], &left[i], &nt);
+        jac_add(F, &left[i], &left[i], &t);
+    }
+}
+static void *ecfft_rec(void *arg) {                     /* arithmetic.rs:258-295 */
+    ecfft_task *T = (ecfft_task *)arg;
+    if (T->n == 2) { ec_butterflies(T->F, T->a, T->a + 1, 1, T->tc, T->tw); return NULL; }
+    size_t h = T->n / 2;
+    ecfft_task L = {T->F, T->a, h, T->tc * 2, T->tw, T->depth - 1};
+    ecfft_task R = {T->F, T->a + h, h, T->tc * 2, T->tw, T->depth - 1};
+    if (T->depth > 0) {
+        pthread_t th; pthread_create(&th, NULL, ecfft_rec, &L);
+        ecfft_rec(&R); pthread_join(th, NULL);
+    } else { ecfft_rec(&L); ecfft_rec(&R); }
+    ec_butterflies(T->F, T->a, T->a + h, h, T->tc, T->tw);
+    return NULL;
+}
+static void ecfft_core(const field_t *F, const field_t *S, jac *a, const fe *omega, uint32_t log_n, int threads) {
+    size_t n = (size_t)1 << log_n;
+    int log_threads = log2_floor((unsigned)threads);
+    for (size_t k = 0; k < n; k++) {                    /* :207-212 */
+        size_t rk = bitrev(k, log_n);
+        if (k < rk) { jac t = a[k]; a[k] = a[rk]; a[rk] = t; }
+    }
+    size_t nt = n / 2 ? n / 2 : 1;
+    uint8_t *tw = (uint8_t *)malloc(32 * nt);           /* :215-221, kept as canonical bytes (scalar-mul input) */
+    fe w = S->r;
+    for (size_t i = 0; i < nt; i++) { fe_to_bytes(S, tw + 32 * i, &w); fe_mul(S, &w, &w, omega); }
+    if (log_n == 0) { free(tw); return; }
+    if ((int)log_n <= log_threads) {
+        size_t chunk = 2, tc = n / 2;
+        for (uint32_t s = 0; s < log_n; s++) {
+            for (size_t base = 0; base < n; base += chunk) ec_butterflies(F, a + base, a + base + chunk / 2, chunk / 2, tc, tw);
+            chunk *= 2; tc /= 2;
+        }
+    } else {
+        ecfft_task T = {F, a, n, 1, tw, log_threads};
+        ecfft_rec(&T);
+    }
+    free(tw);
+}
+typedef struct { const field_t *F; jac *a; size_t len; const uint8_t *k; } ecscale_task;
+static void *ecscale_worker(void *arg) {
+    ecscale_task *T = (ecscale_task *)arg;
+    for (size_t i = 0; i < T->len; i++) { jac t; scalar_mul_jac(T->F, &t, T->k, &T->a[i]); T->a[i] = t; }
+    return NULL;
+}
+static void ec_scale_all(const field_t *F, jac *a, size_t n, const uint8_t *k, int threads) {   /* parallelize, :345-362 */
+    size_t chunk = n / (size_t)threads;
+    if (chunk < (size_t)threads) chunk = n;
+    size_t nchunks = chunk ? (n + chunk - 1) / chunk : 0;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (nchunks ? nchunks : 1));
+    ecscale_task *ts = (ecscale_task *)malloc(sizeof(ecscale_task) * (nchunks ? nchunks : 1));
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t start = c * chunk, l = (start + chunk <= n) ? chunk : n - start;
+        ts[c] = (ecscale_task){F, a + start, l, k};
+        if (c + 1 < nchunks) pthread_create(&th[c], NULL, ecscale_worker, &ts[c]); else ecscale_worker(&ts[c]);
+    }
+    for (size_t c = 0; c + 1 < nchunks; c++) pthread_join(th[c], NULL);
+    free(th); free(ts);
+}
+/* group::Curve::batch_normalize (Montgomery's trick over the non-identity z's); identity -> 64 zero bytes */
+static void batch_normalize_bytes(const field_t *F, const jac *pts, size_t n, uint8_t *out) {
+    fe *pre = (fe *)malloc(sizeof(fe) * (n ? n : 1)); fe acc = F->r;
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; if (!jac_is_id(&pts[i])) fe_mul(F, &acc, &acc, &pts[i].z); }
+    fe_inv(F, &acc, &acc);
+    for (size_t i = n; i-- > 0;) {
+        if (jac_is_id(&pts[i])) { memset(out + 64 * i, 0, 64); continue; }
+        fe zi, zi2; fe_mul(F, &zi, &acc, &pre[i]); fe_mul(F, &acc, &acc, &pts[i].z);
+        fe_sqr(F, &zi2, &zi); aff r; r.inf = 0;
+        fe_mul(F, &r.x, &pts[i].x, &zi2); fe_mul(F, &zi2, &zi2, &zi); fe_mul(F, &r.y, &pts[i].y, &zi2);
+        aff_to_bytes(F, out + 64 * i, &r);
+    }
+    free(pre);
+}
+static jac *load_jacs(const field_t *F, const uint8_t *xyz, size_t n) {
+    jac *a = (jac *)malloc(sizeof(jac) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        fe_from_bytes(F, &a[i].x, xyz + 96 * i); fe_from_bytes(F, &a[i].y, xyz + 96 * i + 32); fe_from_bytes(F, &a[i].z, xyz + 96 * i + 64);
+    }
+    return a;
+}
+/* in place on n = 2^log_n Jacobian points (x||y||z canonical, 96 B; z = 0 identity); scale may be NULL */
+int orc_ec_fft(int curve, uint8_t *points_xyz, const uint8_t *omega, uint32_t log_n, const uint8_t *scale, int threads) {
+    ensure_init();
+    if (threads < 1) threads = 1;
+    const field_t *F = base_field(curve), *S = scalar_field(curve);
+    size_t n = (size_t)1 << log_n;
+    jac *a = load_jacs(F, points_xyz, n);
+    fe w; fe_from_bytes(S, &w, omega);
+    ecfft_core(F, S, a, &w, log_n, threads);
+    if (scale) ec_scale_all(F, a, n, scale, threads);
+    for (size_t i = 0; i < n; i++) {
+        fe_to_bytes(F, points_xyz + 96 * i, &a[i].x); fe_to_bytes(F, points_xyz + 96 * i + 32, &a[i].y); fe_to_bytes(F, points_xyz + 96 * i + 64, &a[i].z);
+    }
+    free(a);
+    return 0;
+}
+int orc_batch_normalize(int curve, const uint8_t *points_xyz, size_t n, uint8_t *out_xy) {
+    ensure_init(); const field_t *F = base_field(curve);
+    jac *a = load_jacs(F, points_xyz, n);
+    batch_normalize_bytes(F, a, n, out_xy);
+    free(a);
+    return 0;
+}
+/* poly/commitment.rs:74-101: g (affine) -> g_lagrange (affine).  omega_inv = alpha_inv (:77-80), minv = 2^-k (:83). */
+int orc_params_lagrange(int curve, const uint8_t *g_xy, uint32_t k, const uint8_t *omega_inv, const uint8_t *minv, int threads,
+                        uint8_t *out_xy) {
+    ensure_init();
+    if (threads < 1) threads = 1;
+    const field_t *F = base_field(curve), *S = scalar_field(curve);
+    size_t n = (size_t)1 << k;
+    jac *a = (jac *)malloc(sizeof(jac) * n);
+    for (size_t i = 0; i < n; i++) {
+        aff p; aff_from_bytes(F, &p, g_xy + 64 * i);
+        if (p.inf) jac_identity(F, &a[i]); else { a[i].x = p.x; a[i].y = p.y; a[i].z = F->r; }
+    }
+    fe w; fe_from_bytes(S, &w, omega_inv);
+    ecfft_core(F, S, a, &w, k, threads);
+    ec_scale_all(F, a, n, minv, threads);
+    batch_normalize_bytes(F, a, n, out_xy);
+    free(a);
     return 0;
 }
 

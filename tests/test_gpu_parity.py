@@ -600,3 +600,90 @@ def test_point_sum(eng):
     lib = L.init()
     L.check(lib.h2_point_sum(L.CURVE_ID[curve], L.ptr(parts), ctypes.c_size_t(shards), L.REPR_CANONICAL, L.ptr(out)))
     assert _affine(curve, out) == cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+
+
+# ------------------------------------------------------------------------------------------ K10 / K11
+def _ecfft_inputs(curve, k, seed):
+    n = 1 << k
+    g = cref.gen_points(curve, seed, n)
+    if n > 4:
+        g[3] = 0                                   # an identity among the inputs
+        g[n - 1] = g[1]                            # and a repeated point
+    return g
+
+
+@pytest.fixture(params=[1, 0], ids=["quad", "thread"])
+def ecfft_form(request):
+    from halo2_b200 import lib as L
+    L.check(L.init().h2_test_set_ecfft_quad(request.param))
+    yield request.param
+    L.check(L.init().h2_test_set_ecfft_quad(1))
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+@pytest.mark.parametrize("k", [0, 1, 2, 5, 8, 10])
+def test_ec_fft_and_lagrange_generators(eng, curve, k, ecfft_form):
+    """best_fft at G = curve point (arithmetic.rs:192-295 via FftGroup :17-27) and the g -> g_lagrange derivation of
+    Params::new (poly/commitment.rs:74-101), against the oracle's restatement; batch_normalize on its own."""
+    c = pasta.CURVES[curve]
+    r, n = c.r, 1 << k
+    g = _ecfft_inputs(curve, k, 300 + k)
+    omega_inv = pasta.inv(pasta.omega_for_k(c.scalar, k), r) if k else 1
+    minv = pow(pasta.inv(2, r), k, r)
+    want_gl = cref.params_lagrange(curve, g, k, omega_inv, minv)
+    assert (eng.lagrange_generators(curve, k, g) == want_gl).all()
+    # the bare network with a random (non-root) omega like benches/fft.rs:17, Jacobian in / out
+    w = pasta.gen_scalars(c.scalar, 17 + k, 1)[0]
+    jac = cref.affine_to_jacobian_bytes(g)
+    got = eng.best_fft_curve(jac.copy(), w, k, curve)
+    want = cref.batch_normalize(curve, cref.ec_fft(curve, jac, w, k))
+    assert (cref.batch_normalize(curve, got) == want).all()
+    assert (eng.batch_normalize(got, curve) == want).all()
+    if k == 5:
+        with pytest.raises(AssertionError):      # arithmetic.rs:205
+            eng.best_fft_curve(jac.copy(), w, k + 1, curve)
+
+
+def test_params_from_generators_commit_lagrange(eng):
+    """Params built from g alone (g_lagrange derived on the device) satisfies the reference's own property
+    poly/commitment.rs:258-302: commit_lagrange(a) == commit(lagrange_to_coeff(a)); the Montgomery ABI form agrees."""
+    from halo2_b200 import lib as L
+    curve, c, k = "vesta", pasta.VESTA, 9
+    g = cref.gen_points(curve, SEED + 40, 1 << k)
+    wu = cref.gen_points(curve, SEED + 41, 2)
+    params = eng.Params.from_generators(curve, k, g, wu[:1], wu[1:])
+    dom = eng.EvaluationDomain(c.scalar, 2, k, pasta.zeta_candidates(c.scalar)[0])
+    a = cref.gen_scalars(c.scalar, SEED + 42, 1 << k)
+    alpha = pasta.gen_scalars(c.scalar, SEED + 43, 1)[0]
+    lhs = _affine(curve, params.commit_lagrange(a, eng.Blind(alpha)))
+    assert lhs == _affine(curve, params.commit(dom.lagrange_to_coeff(a), eng.Blind(alpha)))
+    assert lhs == cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([a, cref.ints_to_bytes([alpha])]),
+                                                          np.concatenate([params.g_lagrange, wu[:1]])))
+    # Montgomery repr at the ABI (pasta's in-memory form): same points
+    m, R = pasta.FIELDS[c.base], 1 << 256
+    gm = cref.ints_to_bytes([v * R % m for v in cref.bytes_to_ints(g.reshape(-1, 32))]).reshape(-1, 64)
+    ms = pasta.FIELDS[c.scalar]
+    omega_inv = pasta.inv(pasta.omega_for_k(c.scalar, k), ms)
+    minv = pow(pasta.inv(2, ms), k, ms)
+    out = np.zeros((1 << k, 64), dtype=np.uint8)
+    lib = L.init()
+    L.check(lib.h2_params_lagrange(L.CURVE_ID[curve], L.ptr(gm), ctypes.c_uint32(k), L.ptr(L.fe_bytes(omega_inv * R % ms)),
+                                   L.ptr(L.fe_bytes(minv * R % ms)), L.REPR_MONTGOMERY, L.ptr(out)))
+    back = cref.ints_to_bytes([v * pasta.inv(R, m) % m for v in cref.bytes_to_ints(out.reshape(-1, 32))]).reshape(-1, 64)
+    assert (back == params.g_lagrange).all()
+    params.close()
+
+
+def test_small_multiexp_and_batch_normalize(eng):
+    """arithmetic.rs:116-136 (benches/arithmetic.rs:29 uses 2 terms) and the prover's normalisation of its commitments
+    (plonk/prover.rs:305-311): a batch of commits -> affine, identity included."""
+    curve, c = "pallas", pasta.PALLAS
+    kb = cref.gen_scalars(c.scalar, SEED + 50, 5)
+    pb = cref.gen_points(curve, SEED + 51, 5)
+    for m in (0, 1, 2, 5):
+        got = _affine(curve, eng.small_multiexp(kb[:m], pb[:m], curve))
+        assert got == pasta.to_affine(c, pasta.small_multiexp(c, cref.bytes_to_ints(kb[:m]), [cref.bytes_to_affine(p) for p in pb[:m]]))
+    pts = np.stack([eng.best_multiexp(kb[:m], pb[:m], curve) for m in (0, 1, 2, 5, 0, 3)] * 7)   # 42 points: 3 chunks of 16
+    want = np.stack([cref.jac_to_affine(curve, p) for p in pts])
+    assert (eng.batch_normalize(pts, curve) == want).all()
+    assert eng.batch_normalize(np.zeros((0, 96), dtype=np.uint8), curve).shape == (0, 64)

@@ -315,3 +315,71 @@ def test_emul_msm_sort_paths(emu, curve):
             assert got == want_skew and (r >= 1000) == (plan[4] < n), (glv, cb, list(plan))   # 7 = low digits only: lower windows
             r, got = run(kb, cb, 512, 4, 4, glv=glv)        # roomy bins, T = 4 < sizes: splits in the binned layout
             assert r < 1000 and (r % 1000 >= 100 or cb >= 7) and got == want
+
+
+# ---- K10 / K11: EC-FFT (best_fft with G = curve point), scaling, batch_normalize -------------------------------------
+def _ecfft_inputs(curve, k, seed):
+    n = 1 << k
+    g = cref.gen_points(curve, seed, n)
+    if n > 4:
+        g[3] = 0                                   # an identity among the inputs
+        g[n - 1] = g[1]                            # and a repeated point
+    return g
+
+
+@pytest.mark.parametrize("quad", [0, 1])
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_glv_scalar_mul_projective(emu, curve, quad):
+    """xyzz_scalar_mul_glv (the EC butterfly's `tw * b`) on a projective operand against the oracle's double-and-add."""
+    c = pasta.CURVES[curve]
+    base = cref.gen_points(curve, 91, 1)[0]
+    three_b = cref.affines_to_bytes([pasta.to_affine(c, pasta.scalar_mul(c, 3, cref.bytes_to_affine(base)))])[0]
+    ks = pasta.gen_scalars(c.scalar, SEED + 5, 12) + [0, 1, 2, c.r - 1, c.r - 2, (1 << 127) - 1, 1 << 127, 1 << 254, (c.r - 1) // 2]
+    for kk in ks:
+        out = np.zeros(64, dtype=np.uint8)
+        emu.emu_glv_mul3(cref.CURVE_ID[curve], quad, cref._p(np.ascontiguousarray(base)), cref._p(cref._fe(kk)), cref._p(out))
+        assert (out == cref.scalar_mul(curve, kk, three_b)).all(), hex(kk)
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_addsub_butterfly(emu, curve):
+    """xyzz_addsub_q: (3a + 5b, 3a - 5b) including b = ±a multiples, identities and equal points."""
+    c = pasta.CURVES[curve]
+    pts = [cref.bytes_to_affine(p) for p in cref.gen_points(curve, 93, 3)]
+    five_inv_three = 3 * pasta.inv(5, c.r) % c.r        # 5 * (3/5 a) = 3 a: the sum / difference degenerate
+    same = pasta.to_affine(c, pasta.scalar_mul(c, five_inv_three, pts[0]))
+    opp = (same[0], c.p - same[1])
+    for a, b in [(pts[0], pts[1]), (pts[0], same), (pts[0], opp), (None, pts[1]), (pts[0], None), (None, None), (pts[2], pts[2])]:
+        out = np.zeros(128, dtype=np.uint8)
+        emu.emu_addsub35(cref.CURVE_ID[curve], cref._p(cref.affines_to_bytes([a])[0]), cref._p(cref.affines_to_bytes([b])[0]), cref._p(out))
+        A = pasta.scalar_mul(c, 3, a) if a else pasta.JAC_ID
+        B = pasta.scalar_mul(c, 5, b) if b else pasta.JAC_ID
+        assert cref.bytes_to_affine(out[:64]) == pasta.to_affine(c, pasta.jac_add(c, A, B))
+        assert cref.bytes_to_affine(out[64:]) == pasta.to_affine(c, pasta.jac_add(c, A, pasta.jac_neg(c, B)))
+
+
+@pytest.mark.parametrize("quad", [0, 1])
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+@pytest.mark.parametrize("k", [0, 1, 2, 4, 6])
+def test_emul_ec_fft_and_params_lagrange(emu, curve, k, quad):
+    c = pasta.CURVES[curve]
+    r = c.r
+    n = 1 << k
+    g = _ecfft_inputs(curve, k, 300 + k)
+    omega_inv = pasta.inv(pasta.omega_for_k(c.scalar, k), r) if k else 1
+    minv = pow(pasta.inv(2, r), k, r)
+    # mode 1: poly/commitment.rs:74-101 (affine g -> affine g_lagrange)
+    out = np.zeros((n, 64), dtype=np.uint8)
+    emu.emu_ec_fft(cref.CURVE_ID[curve], 1, quad, cref._p(g), k, cref._p(cref._fe(omega_inv)), cref._p(cref._fe(minv)), cref._p(out))
+    assert (out == cref.params_lagrange(curve, g, k, omega_inv, minv, threads=4)).all()
+    # mode 0: the bare network on Jacobian points, random (non-root) omega like benches/fft.rs:17, no scaling
+    w = pasta.gen_scalars(c.scalar, 17 + k, 1)[0]
+    jac = cref.affine_to_jacobian_bytes(g)
+    o = np.zeros((n, 96), dtype=np.uint8)
+    emu.emu_ec_fft(cref.CURVE_ID[curve], 0, quad, cref._p(jac), k, cref._p(cref._fe(w)), None, cref._p(o))
+    want = cref.batch_normalize(curve, cref.ec_fft(curve, jac, w, k, threads=2))
+    assert (cref.batch_normalize(curve, o) == want).all()
+    # K11 on its own (Jacobian in, including identities) -- and through a second chunk when n > H2_NORM_CHUNK
+    got = np.zeros((n, 64), dtype=np.uint8)
+    emu.emu_batch_normalize(cref.CURVE_ID[curve], cref._p(o), ctypes.c_uint64(n), cref._p(got))
+    assert (got == want).all()
