@@ -39,12 +39,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libhalo2_b200.so (and there is no CPU fallback)")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    tmp = LIB + ".tmp.so"   # built aside and renamed: a gpurun snapshot never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libhalo2_b200.so")
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -401,7 +401,18 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s, const uin
     return 0;
 }
 
-// Arrival of the bases of a one-shot MSM in `k` chunks (events on the copy stream): chunk j = points [j n / k, (j + 1) n / k).
+// Arrival of the inputs of a one-shot MSM in `k` chunks (events on the copy stream): chunk j = points
+// [chunk_first(n, k, j), chunk_first(n, k, j + 1)).  The chunks GROW: nothing can run before the first chunk has
+// landed, so it is small (1/16 - 1/4 of the points), and the accumulation of chunk j hides the upload of the larger
+// chunk j + 1 -- the link stays busy from t = 0 and the GPU from the first chunk's arrival.  (Equal chunks left the
+// GPU idle for 1/k of the upload time: 2^20 pairs, 96 MiB at ~50 GB/s, 2 chunks: 0.95 of 4.57 ms.)
+static inline size_t chunk_first(size_t n, uint32_t k, uint32_t j) {
+    static const uint32_t cut[H2_MAX_UPLOAD_CHUNKS + 1][H2_MAX_UPLOAD_CHUNKS + 1] = {
+        {0, 16, 16, 16, 16}, {0, 16, 16, 16, 16}, {0, 4, 16, 16, 16}, {0, 2, 8, 16, 16}, {0, 1, 4, 10, 16}};   // sixteenths
+    if (k > H2_MAX_UPLOAD_CHUNKS) k = H2_MAX_UPLOAD_CHUNKS;
+    if (j >= k) return n;
+    return (size_t)((unsigned __int128)n * cut[k][j] / 16);
+}
 struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS], ev_scal[H2_MAX_UPLOAD_CHUNKS]; };   // bases / scalars of chunk j have landed
 
 // fixed != 0: d_bases is a window table (stride points per window) built with window size c.
@@ -430,7 +441,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     p.chunks = K;
     MsmPlan pk[H2_MAX_UPLOAD_CHUNKS];   // one chunk of points: sort, work items, accumulation
     size_t first[H2_MAX_UPLOAD_CHUNKS + 1];
-    for (uint32_t j = 0; j <= K; j++) first[j] = (size_t)((unsigned __int128)n * j / K);
+    for (uint32_t j = 0; j <= K; j++) first[j] = chunk_first(n, K, j);
     uint64_t ref_space = 0, max_items = 0, part_total = 0;
     uint32_t t_max = 0;
     for (uint32_t j = 0; j < K; j++) {
@@ -663,16 +674,16 @@ static int msm_host_common(int curve, const void *scalars, size_t n_scalars, con
         // One-shot MSM: everything goes up on the copy stream, interleaved per chunk -- scalars of chunk j, then its
         // bases -- so that the sort of chunk j starts when its scalars have landed and its accumulation when its bases
         // have, while chunk j + 1 is on the link.
-        // (2 chunks from 2^chunk_min_log points, 4 from 8x that: every chunk pays its own sort / work-item launches)
+        // (2 chunks from 2^chunk_min_log points, 3 from 2x that, 4 from 8x: every chunk pays its own sort / work-item launches)
         cudaStream_t cs = X.copy_stream;
         CU(cudaEventRecord(X.ev_scalars_up, s));
         CU(cudaStreamWaitEvent(cs, X.ev_scalars_up, 0));      // after the prior users of the scratch buffers
         bc.k = 1;
-        if (n_total >= ((size_t)1 << X.chunk_min_log) && n_total >= 4 * H2_MAX_UPLOAD_CHUNKS)
-            bc.k = n_total >= ((size_t)8 << X.chunk_min_log) ? H2_MAX_UPLOAD_CHUNKS : 2u;
+        if (n_total >= ((size_t)1 << X.chunk_min_log) && n_total >= 16 * H2_MAX_UPLOAD_CHUNKS)
+            bc.k = n_total >= ((size_t)8 << X.chunk_min_log) ? H2_MAX_UPLOAD_CHUNKS : n_total >= ((size_t)2 << X.chunk_min_log) ? 3u : 2u;
         affine *db = const_cast<affine *>(d_bases);
         for (uint32_t j = 0; j < bc.k; j++) {
-            size_t lo = (size_t)((unsigned __int128)n_total * j / bc.k), hi = (size_t)((unsigned __int128)n_total * (j + 1) / bc.k);
+            size_t lo = chunk_first(n_total, bc.k, j), hi = chunk_first(n_total, bc.k, j + 1);
             CU(cudaMemcpyAsync(X.scal_in.as<fe>() + lo, (const fe *)scalars + lo, (hi - lo) * sizeof(fe), cudaMemcpyHostToDevice, cs));
             CU(cudaEventRecord(X.ev_scal_up[j], cs));
             bc.ev_scal[j] = X.ev_scal_up[j];
@@ -756,8 +767,20 @@ extern "C" int h2_msm_registered(uint64_t handle, const void *scalars, size_t n,
 
 // `batch` scalar vectors of n entries (+ one extra scalar each, the blinds) against a registered base set with a
 // window table: one pass, one bucket set per vector.
+static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                     void *out, int affine_out);
 extern "C" int h2_msm_registered_batch(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
                                        void *out_xyz) {
+    return msm_registered_batch_impl(handle, scalars, n, extra_scalars, batch, repr, out_xyz, 0);
+}
+// the same pass followed by batch_normalize on the device (plonk/prover.rs:305-311: commit every column, then
+// C::Curve::batch_normalize): `batch` affine points (64 B) come back instead of Jacobian ones
+extern "C" int h2_msm_registered_batch_affine(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                              void *out_xy) {
+    return msm_registered_batch_impl(handle, scalars, n, extra_scalars, batch, repr, out_xy, 1);
+}
+static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                     void *out_xyz, int affine_out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;
     auto it = g_ctx.bases.find(handle);
@@ -779,10 +802,21 @@ extern "C" int h2_msm_registered_batch(uint64_t handle, const void *scalars, siz
         CU(cudaMemcpy2DAsync(d, total * sizeof(fe), scalars, n * sizeof(fe), n * sizeof(fe), batch, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpy2DAsync(d + n, total * sizeof(fe), extra_scalars, sizeof(fe), sizeof(fe), batch, cudaMemcpyHostToDevice, s));
     }
+    const int canon = repr == H2_REPR_CANONICAL;
     int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, b->table.as<affine>(), total, b->c, X.result.as<jacobian>(),
-                          repr == H2_REPR_CANONICAL, s, 1, b->n, nullptr, (uint32_t)batch);
+                          affine_out ? 0 : canon, s, 1, b->n, nullptr, (uint32_t)batch);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (affine_out) {
+        if (X.ec_out.ensure(batch * sizeof(affine))) return 1;
+        const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
+        if (b->curve == H2_CURVE_PALLAS)
+            LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+        else
+            LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+        CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    } else {
+        CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    }
     if (scratch_release(s)) return 1;
     CU(cudaStreamSynchronize(s));
     return 0;

@@ -73,34 +73,58 @@ template <class P> H2_HD xyzz xyzz_scalar_mul_glv(const xyzz &b, const uint32_t 
 // QUAD) therefore share one butterfly: every level of the formulas below is four INDEPENDENT products, one per lane,
 // exchanged by shuffle (quad_mul4).  XYZZ doubling is 9 products in 3 levels, the general addition 14 in 4, and the
 // butterfly's (a + t, a - t) pair -- which shares u1, u2, s1, pp and therefore ZZ3, ZZZ3 -- 16 in 4 instead of 28 in 8.
-// On the host (tests/kernel_emul) quad_mul4 is four plain multiplies, so the formulas are checked against the oracle
-// there; only the shuffle itself is device-only.
+//
+// Control flow is WARP-UNIFORM by construction: identity operands and skipped additions are handled by selects, the
+// rare P = ±Q case by a per-lane serial fallback behind a warp vote (every lane of a quad holds full copies of its
+// operands, so any lane can finish alone).  All 32 lanes therefore reach every shuffle together and the shuffles use the
+// constant full mask -- with a per-quad runtime mask ptxas wraps each of the 32 shuffles of a level in a
+// MATCH / WARPSYNC / BSSY sequence, and with divergent quads the bit loop was 72 KB of code per iteration: a lone warp
+// then runs at the instruction-fetch rate (first version, measured on B200: 19k cycles per scalar bit).  The multiply is
+// ONE out-of-line body (fe_mul_call) for the same reason.
+// On the host (tests/kernel_emul) quad_mul4 is four plain multiplies and the votes are the lane's own flag, so the
+// formulas and the select logic are checked against the oracle there; only the shuffle itself is device-only.
+H2_HD bool warp_any(bool p) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
+#endif
+}
+H2_HD fe fe_pick(bool c, const fe &a, const fe &b) {
+    fe r;
+    for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+    return r;
+}
+H2_HD xyzz xyzz_pick(bool c, const xyzz &a, const xyzz &b) {
+    xyzz r;
+    r.x = fe_pick(c, a.x, b.x); r.y = fe_pick(c, a.y, b.y); r.zz = fe_pick(c, a.zz, b.zz); r.zzz = fe_pick(c, a.zzz, b.zzz);
+    return r;
+}
 template <class P>
 H2_HD void quad_mul4(const fe &a0, const fe &b0, const fe &a1, const fe &b1, const fe &a2, const fe &b2, const fe &a3, const fe &b3,
                      fe &r0, fe &r1, fe &r2, fe &r3) {
 #ifdef __CUDA_ARCH__
-    const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);
+    const uint32_t sub = threadIdx.x & 3u;
     fe x, y;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         x.v[i] = sub == 0 ? a0.v[i] : sub == 1 ? a1.v[i] : sub == 2 ? a2.v[i] : a3.v[i];
         y.v[i] = sub == 0 ? b0.v[i] : sub == 1 ? b1.v[i] : sub == 2 ? b2.v[i] : b3.v[i];
     }
-    fe r = fe_mul<P>(x, y);
+    fe r = fe_mul_call<P>(x, y);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        r0.v[i] = __shfl_sync(mask, r.v[i], 0, 4);
-        r1.v[i] = __shfl_sync(mask, r.v[i], 1, 4);
-        r2.v[i] = __shfl_sync(mask, r.v[i], 2, 4);
-        r3.v[i] = __shfl_sync(mask, r.v[i], 3, 4);
+        r0.v[i] = __shfl_sync(0xffffffffu, r.v[i], 0, 4);
+        r1.v[i] = __shfl_sync(0xffffffffu, r.v[i], 1, 4);
+        r2.v[i] = __shfl_sync(0xffffffffu, r.v[i], 2, 4);
+        r3.v[i] = __shfl_sync(0xffffffffu, r.v[i], 3, 4);
     }
 #else
     r0 = fe_mul<P>(a0, b0); r1 = fe_mul<P>(a1, b1); r2 = fe_mul<P>(a2, b2); r3 = fe_mul<P>(a3, b3);
 #endif
 }
-// acc = 2 acc (dbl-2008-s-1, a = 0) in 3 levels
+// acc = 2 acc (dbl-2008-s-1, a = 0) in 3 levels.  Branch-free: the identity (0, 0, 0, 0) maps to itself.
 template <class P> H2_HD void xyzz_double_q(xyzz &a) {
-    if (xyzz_is_identity(a)) return;                       // uniform within the quad
     fe u = fe_dbl<P>(a.y), v, xx, w, s, mm, zz3, t0, t1, zzz3, d0, d1;
     quad_mul4<P>(u, u, a.x, a.x, u, u, a.x, a.x, v, xx, d0, d1);
     fe m = fe_add<P>(fe_dbl<P>(xx), xx);
@@ -109,51 +133,62 @@ template <class P> H2_HD void xyzz_double_q(xyzz &a) {
     quad_mul4<P>(m, fe_sub<P>(s, x3), w, a.y, w, a.zzz, w, a.zzz, t0, t1, zzz3, d0);
     a.x = x3; a.y = fe_sub<P>(t0, t1); a.zz = zz3; a.zzz = zzz3;
 }
-// sum = a + b and (when DIFF) diff = a - b (add-2008-s) in 4 levels; a - b shares everything but r = s2 - s1
+// sum = a + b and (when DIFF) diff = a - b (add-2008-s) in 4 levels; a - b shares everything but r = s2 - s1.
+// Must be reached by all lanes of the warp together (see above).
 template <class P, bool DIFF> H2_HD void xyzz_addsub_q(const xyzz &a, const xyzz &b, xyzz &sum, xyzz &diff) {
-    if (xyzz_is_identity(b)) { sum = a; if (DIFF) diff = a; return; }
-    if (xyzz_is_identity(a)) { sum = b; if (DIFF) { diff = b; xyzz_neg<P>(diff); } return; }
+    const bool a_id = xyzz_is_identity(a), b_id = xyzz_is_identity(b);
     fe u1, u2, s1, s2;
     quad_mul4<P>(a.x, b.zz, b.x, a.zz, a.y, b.zzz, b.y, a.zzz, u1, u2, s1, s2);
     fe pp = fe_sub<P>(u2, u1);
     fe r = fe_sub<P>(s2, s1);
     fe rn = fe_neg<P>(fe_add<P>(s2, s1));                  // -s2 - s1: the r of a + (-b)
-    if (fe_is_zero(pp)) {                                  // b = ±a
-        xyzz dbl = a;
-        xyzz_double_q<P>(dbl);
-        if (fe_is_zero(r)) { sum = dbl; if (DIFF) diff = xyzz_identity(); }
-        else { sum = xyzz_identity(); if (DIFF) diff = dbl; }
-        return;
-    }
+    const bool degenerate = !a_id && !b_id && fe_is_zero(pp);   // b = ±a
     fe pp2, rr, rrn, zz12, ppp, q, zz3, zzz12, t1, t1n, t2, zzz3;
     quad_mul4<P>(pp, pp, r, r, rn, rn, a.zz, b.zz, pp2, rr, rrn, zz12);
     quad_mul4<P>(pp, pp2, u1, pp2, zz12, pp2, a.zzz, b.zzz, ppp, q, zz3, zzz12);
     fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(rr, ppp), q), q);
     fe x3n = fe_sub<P>(fe_sub<P>(fe_sub<P>(rrn, ppp), q), q);
     quad_mul4<P>(r, fe_sub<P>(q, x3), rn, fe_sub<P>(q, x3n), s1, ppp, zzz12, ppp, t1, t1n, t2, zzz3);
-    sum.x = x3; sum.y = fe_sub<P>(t1, t2); sum.zz = zz3; sum.zzz = zzz3;
-    if (DIFF) { diff.x = x3n; diff.y = fe_sub<P>(t1n, t2); diff.zz = zz3; diff.zzz = zzz3; }
+    xyzz g;
+    g.x = x3; g.y = fe_sub<P>(t1, t2); g.zz = zz3; g.zzz = zzz3;
+    sum = xyzz_pick(b_id, a, xyzz_pick(a_id, b, g));
+    if (DIFF) {
+        xyzz nb = b;
+        xyzz_neg<P>(nb);
+        g.x = x3n; g.y = fe_sub<P>(t1n, t2);
+        diff = xyzz_pick(b_id, a, xyzz_pick(a_id, nb, g));
+    }
+    if (warp_any(degenerate)) {                            // rare; serial per lane, no shuffles inside
+        if (degenerate) {
+            xyzz dbl = a;
+            xyzz_double<P>(dbl);
+            const bool same = fe_is_zero(r);
+            sum = same ? dbl : xyzz_identity();
+            if (DIFF) diff = same ? xyzz_identity() : dbl;
+        }
+    }
 }
-// xyzz_scalar_mul_glv for a quad: 3 + 4 levels per bit instead of 9 + 14 multiplications
+// xyzz_scalar_mul_glv for a quad: 3 + 4 levels per bit instead of 9 + 14 multiplications.  Warp-uniform: the addition of
+// a bit runs when ANY quad of the warp has a non-zero digit pair (with 8 quads that is 99.99 % of the bits) and quads with
+// a zero pair discard its result.
 template <class P> H2_HD xyzz xyzz_scalar_mul_glv_q(const xyzz &b, const uint32_t (&k)[8]) {
-    if (xyzz_is_identity(b)) return b;
     uint32_t k1[8], k2[8], n1, n2;
     glv_decompose<P>(k, k1, n1, k2, n2);
     xyzz tab[3], unused;
     tab[0] = b;
     if (n1) xyzz_neg<P>(tab[0]);
     tab[1] = b;
-    tab[1].x = fe_mul<P>(b.x, glv_zeta<P>());
+    tab[1].x = fe_mul_call<P>(b.x, glv_zeta<P>());
     if (n2) xyzz_neg<P>(tab[1]);
     xyzz_addsub_q<P, false>(tab[0], tab[1], tab[2], unused);
     xyzz acc = xyzz_identity();
     for (int bit = 126; bit >= 0; bit--) {
         xyzz_double_q<P>(acc);
-        uint32_t sel = ((k1[bit >> 5] >> (bit & 31)) & 1u) | (((k2[bit >> 5] >> (bit & 31)) & 1u) << 1);
-        if (sel) {
-            xyzz op = tab[sel - 1], res;
+        const uint32_t sel = ((k1[bit >> 5] >> (bit & 31)) & 1u) | (((k2[bit >> 5] >> (bit & 31)) & 1u) << 1);
+        if (warp_any(sel != 0)) {
+            xyzz op = xyzz_pick(sel == 2, tab[1], xyzz_pick(sel == 3, tab[2], tab[0])), res;
             xyzz_addsub_q<P, false>(acc, op, res, unused);
-            acc = res;
+            acc = xyzz_pick(sel != 0, res, acc);
         }
     }
     return acc;
@@ -162,7 +197,7 @@ template <class P> H2_HD xyzz xyzz_scalar_mul_glv_q(const xyzz &b, const uint32_
 H2_HD void st_xyzz_q(xyzz *p, const xyzz &a) {
 #ifdef __CUDA_ARCH__
     const uint32_t sub = threadIdx.x & 3u;
-    fe_store(sub == 0 ? &p->x : sub == 1 ? &p->y : sub == 2 ? &p->zz : &p->zzz, sub == 0 ? a.x : sub == 1 ? a.y : sub == 2 ? a.zz : a.zzz);
+    fe_store(sub == 0 ? &p->x : sub == 1 ? &p->y : sub == 2 ? &p->zz : &p->zzz, fe_pick(sub == 0, a.x, fe_pick(sub == 1, a.y, fe_pick(sub == 2, a.zz, a.zzz))));
 #else
     st_xyzz(p, a);
 #endif
@@ -198,24 +233,30 @@ template <class P, class PS> struct EcFft {
         st_xyzz(work + ia, a);
         st_xyzz(work + ib, d);
     }
-    // the same butterfly run by a quad of lanes (t = quad index)
-    static H2_HD void stage_body_q(xyzz *work, const fe *tw, uint32_t log_n, uint32_t s, uint64_t t) {
+    // the same butterfly run by a quad of lanes (t = quad index).  Called by EVERY lane of the warp: quads past the end
+    // (`active` false) compute on butterfly 0 and store nothing; the scalar multiplication runs for the whole warp as
+    // soon as one of its quads has a twiddle exponent != 0 (w^0 = 1 goes through the ladder unchanged).
+    static H2_HD void stage_body_q(xyzz *work, const fe *tw, uint32_t log_n, uint32_t s, uint64_t t, bool active) {
+        if (!active) t = 0;
         const uint64_t half = 1ull << (s - 1);
         const uint64_t i = t & (half - 1);
         const uint64_t ia = ((t >> (s - 1)) << s) + i, ib = ia + half;
         xyzz a = ld_xyzz(work + ia), b = ld_xyzz(work + ib);
-        if (i) {
+        if (warp_any(i != 0)) {
             fe w = fe_from_mont<PS>(fe_load(tw + (i << (log_n - s))));
             b = xyzz_scalar_mul_glv_q<P>(b, w.v);
         }
         xyzz sum, diff;
         xyzz_addsub_q<P, true>(a, b, sum, diff);
-        st_xyzz_q(work + ia, sum);
-        st_xyzz_q(work + ib, diff);
+        if (active) {
+            st_xyzz_q(work + ia, sum);
+            st_xyzz_q(work + ib, diff);
+        }
     }
-    static H2_HD void scale_body_q(xyzz *work, const fe &scale_canon, uint64_t i) {
-        xyzz p = ld_xyzz(work + i);
-        st_xyzz_q(work + i, xyzz_scalar_mul_glv_q<P>(p, scale_canon.v));
+    static H2_HD void scale_body_q(xyzz *work, const fe &scale_canon, uint64_t i, bool active) {
+        xyzz p = ld_xyzz(work + (active ? i : 0));
+        p = xyzz_scalar_mul_glv_q<P>(p, scale_canon.v);
+        if (active) st_xyzz_q(work + i, p);
     }
     // `*g *= scale` (poly/commitment.rs:84-89); scale canonical
     static H2_HD void scale_body(xyzz *work, const fe &scale_canon, uint64_t i) {
@@ -285,14 +326,14 @@ template <class P, class PS> __global__ void __launch_bounds__(64) ecfft_scale_k
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) EcFft<P, PS>::scale_body(work, scale_canon, i);
 }
-// quad forms: 4 lanes per butterfly / point, 64-thread CTAs = 16 quads.  All lanes of a quad take the same branches.
+// quad forms: 4 lanes per butterfly / point, 64-thread CTAs = 16 quads.  Every lane runs the body (uniform control flow).
 template <class P, class PS> __global__ void __launch_bounds__(64) ecfft_stage_quad_kernel(xyzz *work, const fe *tw, uint32_t log_n, uint32_t s) {
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    if (t < (1ull << (log_n - 1))) EcFft<P, PS>::stage_body_q(work, tw, log_n, s, t);
+    EcFft<P, PS>::stage_body_q(work, tw, log_n, s, t, t < (1ull << (log_n - 1)));
 }
 template <class P, class PS> __global__ void __launch_bounds__(64) ecfft_scale_quad_kernel(xyzz *work, fe scale_canon, uint64_t n) {
     uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    if (i < n) EcFft<P, PS>::scale_body_q(work, scale_canon, i);
+    EcFft<P, PS>::scale_body_q(work, scale_canon, i, i < n);
 }
 template <class P, class PS> __global__ void __launch_bounds__(128) ecfft_store_jac_kernel(const xyzz *work, jacobian *out, int canonical, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

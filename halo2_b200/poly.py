@@ -111,6 +111,19 @@ class Params:
                                                     _l.REPR_CANONICAL, _l.ptr(out)))
         return out
 
+    def commit_many_affine(self, polys, blinds: Sequence[Blind], lagrange: bool = False) -> np.ndarray:
+        """commit_many / commit_lagrange_many followed by C::Curve::batch_normalize on the device: the affine points
+        the prover writes to the transcript (plonk/prover.rs:305-316), (batch, 64) uint8."""
+        batch = len(polys)
+        assert batch == len(blinds) and batch >= 1
+        stack = np.ascontiguousarray(np.stack([_l.as_u8(p, 32) for p in polys]))
+        assert stack.shape[1] == self.n, "polynomial length != params.n"
+        bl = np.ascontiguousarray(np.stack([_l.fe_bytes(b.value) for b in blinds]))
+        out = np.zeros((batch, 64), dtype=np.uint8)
+        _l.check(_l.init().h2_msm_registered_batch_affine(self._h_gl if lagrange else self._h_g, _l.ptr(stack), ctypes.c_size_t(self.n),
+                                                           _l.ptr(bl), ctypes.c_size_t(batch), _l.REPR_CANONICAL, _l.ptr(out)))
+        return out
+
     def commit_many(self, polys, blinds: Sequence[Blind]) -> np.ndarray:
         """[commit(p, r) for p, r in zip(polys, blinds)] in one pass over the resident table -- the shape
         of the prover's per-column loops (plonk/prover.rs:305-309, vanishing/prover.rs:102-106)."""

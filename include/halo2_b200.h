@@ -77,6 +77,10 @@ int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void
  * Needs a base set registered with H2_BASES_PRECOMPUTE. */
 int h2_msm_registered_batch(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
                             void *out_xyz);
+/* The same pass followed by C::Curve::batch_normalize on the device -- the shape of plonk/prover.rs:305-311 (commit
+ * every advice column, then normalise the batch for the transcript): out_xy receives `batch` affine points (64 B). */
+int h2_msm_registered_batch_affine(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                   void *out_xy);
 
 /* ---- IPA opening: the round loop of commitment::create_proof, poly/commitment/prover.rs:100-142 ----
  * Replaces, per round j: the two best_multiexp calls over the folded generators (:107-108), the two

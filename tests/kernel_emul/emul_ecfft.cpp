@@ -25,13 +25,13 @@ static int run_ecfft(int mode, int quad, const uint8_t *in, uint32_t log_n, cons
     }
     for (uint32_t s = 1; s <= log_n; s++)
         for (uint64_t t = 0; t < n / 2; t++) {
-            if (quad) EcFft<P, PS>::stage_body_q(work.data(), tw.data(), log_n, s, t);
+            if (quad) EcFft<P, PS>::stage_body_q(work.data(), tw.data(), log_n, s, t, true);
             else EcFft<P, PS>::stage_body(work.data(), tw.data(), log_n, s, t);
         }
     if (scale) {
         fe sc; memcpy(sc.v, scale, 32);
         for (uint64_t i = 0; i < n; i++) {
-            if (quad) EcFft<P, PS>::scale_body_q(work.data(), sc, i);
+            if (quad) EcFft<P, PS>::scale_body_q(work.data(), sc, i, true);
             else EcFft<P, PS>::scale_body(work.data(), sc, i);
         }
     }

@@ -367,6 +367,10 @@ def test_commit_many_batched(eng):
         single = params.commit(polys[i], blinds[i])
         want = cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([polys[i], cref.ints_to_bytes([blinds[i].value])]), g))
         assert _affine(curve, many[i]) == want == _affine(curve, single), i
+    # ... followed by batch_normalize on the device (plonk/prover.rs:305-311); an all-zero column with a zero blind is the identity
+    aff = params.commit_many_affine(polys + [polys[3]], blinds + [eng.Blind(0)])
+    assert [cref.bytes_to_affine(a) for a in aff] == [_affine(curve, m) for m in many] + [None]
+    assert (params.commit_many_affine(polys[:2], blinds[:2], lagrange=True) == aff[:2]).all()   # same generators registered twice here
     params.close()
 
 
@@ -481,7 +485,9 @@ def test_msm_chunked_upload(eng):
     from halo2_b200 import lib as L
     lib = L.init()
     try:
-        for curve, n, thr in (("pallas", 4099, 4), ("vesta", 1 << 12, 11), ("pallas", 17, 4), ("vesta", 5, 1)):   # 4, 2, 2, 1 chunks
+        # 4, 3, 2, 3, 1, 1 chunks (growing sizes: 1/16, 3/16, 6/16, 6/16 | 1/8, 3/8, 1/2 | 1/4, 3/4)
+        for curve, n, thr in (("pallas", 4099, 4), ("vesta", 1 << 12, 11), ("vesta", 3000, 11), ("pallas", 70, 4), ("pallas", 17, 4),
+                              ("vesta", 5, 1)):
             L.check(lib.h2_test_set_chunk_threshold(thr))
             c = pasta.CURVES[curve]
             pb = cref.gen_points(curve, SEED + 400 + n, n)

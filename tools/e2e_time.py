@@ -31,7 +31,7 @@ for _ in range(5):
     dst.copy_(bs_canon, non_blocking=True)
 torch.cuda.synchronize(); dt = (time.time() - t0) / 5
 print(f"H2D 64 MiB: {dt * 1e3:.3f} ms  {bs_canon.numel() * 4 / dt / 1e9:.1f} GB/s", flush=True)
-for thr, name in ((40, "one upload"), (k, "2 chunks"), (k - 3, "4 chunks")):
+for thr, name in ((40, "one upload"), (k, "2 chunks"), (k - 1, "3 chunks"), (k - 3, "4 chunks")):
     L.check(lib.h2_test_set_chunk_threshold(thr))
     for repr_, bs, rname in ((0, bs_canon, "canonical"), (1, bs_mont, "montgomery")):
         for _ in range(3):
