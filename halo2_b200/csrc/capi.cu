@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -18,6 +19,7 @@
 #include "ipa.cuh"
 #include "ntt.cuh"
 #include "ecfft.cuh"
+#include "fixedbase.cuh"
 
 using namespace h2;
 
@@ -51,7 +53,11 @@ struct DevBuf {
 };
 
 struct TwiddleEntry { int field; uint32_t log_n; uint8_t omega[32]; DevBuf buf; uint64_t stamp; };
-struct BaseSet { int curve; size_t n; DevBuf buf; DevBuf table; uint32_t c = 0, W = 0; };   // table: W x n window multiples
+struct BaseSet {
+    int curve; size_t n; DevBuf buf;
+    DevBuf table; uint32_t c = 0, W = 0;   // W x n window shifts 2^(c w) G_i (bucket method over one shared bucket set)
+    DevBuf dtable;                         // 32 x 128 x n digit multiples m 2^(8 w) G_i (fixedbase.cuh: direct sum, small sets)
+};
 
 struct PolyBuf { int field; size_t len; DevBuf buf; };   // device-resident polynomial, Montgomery form, len + 1 slots
 struct IpaSession { uint64_t bases; uint32_t k, round; int folded; DevBuf p, b, s, scal, out; };
@@ -87,6 +93,7 @@ struct Context {
     DevBuf ntt_io, ntt_out, ntt_work, pow2;
     // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms
     DevBuf ec_work, ec_io, ec_out;
+    DevBuf fb_a, fb_b;                       // partial sums of the direct-sum fixed-base MSM (ping-pong)
     std::vector<TwiddleEntry *> twiddles;
     uint64_t tw_stamp = 0;
     std::map<uint64_t, BaseSet *> bases;
@@ -182,11 +189,11 @@ extern "C" int h2_shutdown(void) {
     DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.bases_phi, &g_ctx.glv_parts, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
                      &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
                      &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
-                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out};
+                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out, &g_ctx.fb_a, &g_ctx.fb_b};
     for (DevBuf *b : all) b->release();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
-    for (auto &kv : g_ctx.bases) { kv.second->buf.release(); kv.second->table.release(); delete kv.second; }
+    for (auto &kv : g_ctx.bases) { kv.second->buf.release(); kv.second->table.release(); kv.second->dtable.release(); delete kv.second; }
     g_ctx.bases.clear();
     for (auto &kv : g_ctx.ipa) { IpaSession *q = kv.second; q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     g_ctx.ipa.clear();
@@ -415,6 +422,59 @@ static inline size_t chunk_first(size_t n, uint32_t k, uint32_t j) {
 }
 struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS], ev_scal[H2_MAX_UPLOAD_CHUNKS]; };   // bases / scalars of chunk j have landed
 
+// A fixed-base MSM over resident bases is launched with the same parameters call after call: the second call with a given
+// key is captured into a CUDA graph, later ones replay it.
+static int msm_issue_or_replay(const std::function<int()> &issue, bool graphable, const void *d_scalars, const void *d_bases, const void *d_out,
+                               size_t n, uint64_t stride, uint32_t c, uint32_t sets, int scalars_mont, int out_canonical, cudaStream_t s) {
+    Context &X = g_ctx;
+    if (!(graphable && X.graphs_on && !g_prof_on)) return issue();
+    MsmGraph *ge = nullptr;
+    for (auto &e : X.graphs)
+        if (e.scalars == d_scalars && e.bases == d_bases && e.out == d_out && e.n == n && e.stride == stride && e.c == c && e.sets == sets &&
+            e.scalars_mont == scalars_mont && e.out_canonical == out_canonical) { ge = &e; break; }
+    if (ge && ge->gen != g_alloc_gen) {   // some buffer moved since the capture
+        if (ge->exec) cudaGraphExecDestroy(ge->exec);
+        ge->exec = nullptr; ge->seen = 0; ge->gen = g_alloc_gen;
+    }
+    if (!ge) {
+        if (X.graphs.size() >= 16) {   // evict the least recently used entry
+            size_t v = 0;
+            for (size_t i = 1; i < X.graphs.size(); i++) if (X.graphs[i].stamp < X.graphs[v].stamp) v = i;
+            if (X.graphs[v].exec) cudaGraphExecDestroy(X.graphs[v].exec);
+            X.graphs.erase(X.graphs.begin() + v);
+        }
+        MsmGraph e;
+        e.scalars = d_scalars; e.bases = d_bases; e.out = d_out; e.n = n; e.stride = stride; e.gen = g_alloc_gen; e.c = c; e.sets = sets;
+        e.scalars_mont = scalars_mont; e.out_canonical = out_canonical;
+        X.graphs.push_back(e);
+        ge = &X.graphs.back();
+    }
+    ge->stamp = ++X.graph_stamp;
+    if (ge->exec) {
+        CU(cudaGraphLaunch(ge->exec, s));
+        g_launches.fetch_add(ge->launches, std::memory_order_relaxed);
+        return 0;
+    }
+    if (ge->seen++ == 0) return issue();     // first sighting: run eagerly (the buffers may still be growing)
+    const uint64_t l0 = g_launches.load();
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return issue(); }
+    int rc = issue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ge->seen = 0;
+        return rc ? rc : issue();            // capture refused: run eagerly
+    }
+    ge->launches = g_launches.load() - l0;
+    ce = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { ge->exec = nullptr; cudaGetLastError(); return issue(); }
+    CU(cudaGraphLaunch(ge->exec, s));
+    return 0;
+}
+
 // fixed != 0: d_bases is a window table (stride points per window) built with window size c.
 // bc != nullptr: the bases arrive chunk by chunk while this runs.  Each chunk is then sorted and accumulated on its own
 // (own bins, work items and bucket sums) as soon as it has landed, and the bucket reduce adds the per-chunk bucket sums:
@@ -430,6 +490,33 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
         CU(cudaStreamSynchronize(s));
         return 0;
+    }
+    std::function<int()> issue;
+    if (fixed == 2) {   // direct sum over the digit-multiples table (fixedbase.cuh): accumulate + reduce tree
+        FbPlan fp;
+        fp.total = n; fp.stride = stride; fp.sets = sets ? sets : 1u; fp.split = fb_split(n, fp.sets); fp.scalars_mont = scalars_mont ? 1u : 0u;
+        const uint64_t count0 = n * fp.split;
+        if (X.fb_a.ensure(fp.sets * count0 * sizeof(xyzz)) || X.fb_b.ensure(fp.sets * fb_ctas(count0, fb_fan(count0)) * sizeof(xyzz))) return 1;
+        issue = [&X, fp, count0, d_scalars, d_bases, d_out, out_canonical, s]() -> int {
+            auto k_acc = fb_accum_kernel<P, PS>;
+            auto k_red = fb_reduce_kernel<P, PS>;
+            xyzz *a = X.fb_a.as<xyzz>(), *b = X.fb_b.as<xyzz>();
+            prof_begin(PROF_MSM_ACCUM0, s);
+            LAUNCH(k_acc, blocks_for(fp.sets * count0, 128), 128, 0, s, fp, d_scalars, d_bases, a);
+            prof_end(s);
+            uint64_t count = count0, in_stride = count0;
+            for (;;) {
+                const uint32_t f = fb_fan(count);
+                const uint64_t ctas = fb_ctas(count, f);
+                LAUNCH(k_red, dim3((unsigned)ctas, fp.sets), 4 * H2_FB_QUADS, 0, s, (const xyzz *)a, count, in_stride, f, b, ctas,
+                       ctas == 1 ? d_out : (jacobian *)nullptr, (uint32_t)out_canonical);
+                if (ctas == 1) break;
+                xyzz *t = a; a = b; b = t;
+                count = ctas; in_stride = ctas;
+            }
+            return 0;
+        };
+        return msm_issue_or_replay(issue, !bc, d_scalars, d_bases, d_out, n, stride, H2_FB_BITS, fp.sets, scalars_mont, out_canonical, s);
     }
     const uint32_t glv = (!fixed && X.glv_on && n < (1ull << 30)) ? 1u : 0u;
     if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
@@ -490,7 +577,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
         if (X.scan_blocks.ensure((size_t)((p.G + 1 + per_block - 1) / per_block) * 4 + 16)) return 1;
     }
-    auto issue = [&]() -> int {
+    issue = [&]() -> int {
         CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
         CU(cudaMemsetAsync(X.cursor.p, 0, K * 2 * p.G * 4, s));
         CU(cudaMemsetAsync(X.size_hist.p, 0, K * small_words * 4, s));
@@ -554,53 +641,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
         return 0;
     };
-    // fixed-base MSM over resident bases: capture the second call with a given set of parameters, replay afterwards
-    if (!(fixed && !bc && X.graphs_on && !g_prof_on)) return issue();
-    MsmGraph *ge = nullptr;
-    for (auto &e : X.graphs)
-        if (e.scalars == d_scalars && e.bases == d_bases && e.out == d_out && e.n == n && e.stride == stride && e.c == c && e.sets == sets &&
-            e.scalars_mont == scalars_mont && e.out_canonical == out_canonical) { ge = &e; break; }
-    if (ge && ge->gen != g_alloc_gen) {   // some buffer moved since the capture
-        if (ge->exec) cudaGraphExecDestroy(ge->exec);
-        ge->exec = nullptr; ge->seen = 0; ge->gen = g_alloc_gen;
-    }
-    if (!ge) {
-        if (X.graphs.size() >= 16) {   // evict the least recently used entry
-            size_t v = 0;
-            for (size_t i = 1; i < X.graphs.size(); i++) if (X.graphs[i].stamp < X.graphs[v].stamp) v = i;
-            if (X.graphs[v].exec) cudaGraphExecDestroy(X.graphs[v].exec);
-            X.graphs.erase(X.graphs.begin() + v);
-        }
-        MsmGraph e;
-        e.scalars = d_scalars; e.bases = d_bases; e.out = d_out; e.n = n; e.stride = stride; e.gen = g_alloc_gen; e.c = c; e.sets = sets;
-        e.scalars_mont = scalars_mont; e.out_canonical = out_canonical;
-        X.graphs.push_back(e);
-        ge = &X.graphs.back();
-    }
-    ge->stamp = ++X.graph_stamp;
-    if (ge->exec) {
-        CU(cudaGraphLaunch(ge->exec, s));
-        g_launches.fetch_add(ge->launches, std::memory_order_relaxed);
-        return 0;
-    }
-    if (ge->seen++ == 0) return issue();     // first sighting: run eagerly (the buffers may still be growing)
-    const uint64_t l0 = g_launches.load();
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return issue(); }
-    int rc = issue();
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(s, &graph);
-    if (rc || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        ge->seen = 0;
-        return rc ? rc : issue();            // capture refused: run eagerly
-    }
-    ge->launches = g_launches.load() - l0;
-    ce = cudaGraphInstantiate(&ge->exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { ge->exec = nullptr; cudaGetLastError(); return issue(); }
-    CU(cudaGraphLaunch(ge->exec, s));
-    return 0;
+    return msm_issue_or_replay(issue, fixed && !bc, d_scalars, d_bases, d_out, n, stride, c, sets, scalars_mont, out_canonical, s);
 }
 
 static int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
@@ -640,6 +681,28 @@ static int build_table(BaseSet *b, uint32_t c, cudaStream_t s) {
     }
     b->c = c; b->W = W;
     return 0;
+}
+// digit-multiples table of a small resident set (fixedbase.cuh), from the c = 8 window table
+#define H2_FB_MAX_POINTS ((1u << 15) + 2u)
+static int build_direct(BaseSet *b, cudaStream_t s) {
+    if (b->n > H2_FB_MAX_POINTS) return fail("H2_BASES_DIRECT: at most 2^15 + 2 points (256 KiB of table per point)");
+    if (b->c != H2_FB_BITS || b->W != H2_FB_WINDOWS) return fail("H2_BASES_DIRECT: needs the 8-bit window table");
+    if (b->dtable.ensure((size_t)H2_FB_WINDOWS * H2_FB_MULTIPLES * b->n * sizeof(affine))) return 1;
+    const uint64_t threads = (uint64_t)H2_FB_WINDOWS * b->n;
+    if (b->curve == H2_CURVE_PALLAS) {
+        auto k = fb_table_kernel<FpParams, FqParams>;
+        LAUNCH(k, blocks_for(threads, 128), 128, 0, s, (const affine *)b->table.as<affine>(), b->dtable.as<affine>(), (uint64_t)b->n, (uint64_t)b->n);
+    } else {
+        auto k = fb_table_kernel<FqParams, FpParams>;
+        LAUNCH(k, blocks_for(threads, 128), 128, 0, s, (const affine *)b->table.as<affine>(), b->dtable.as<affine>(), (uint64_t)b->n, (uint64_t)b->n);
+    }
+    return 0;
+}
+// what a fixed-base MSM over `b` runs on: the digit-multiples table (mode 2) when there is one, else the window table (mode 1)
+static inline const affine *fixed_table(const BaseSet *b, uint32_t *c, uint32_t *mode) {
+    if (b->dtable.p) { *c = H2_FB_BITS; *mode = 2; return b->dtable.as<affine>(); }
+    *c = b->c; *mode = 1;
+    return b->table.as<affine>();
 }
 static int convert_points(int curve, affine *d, size_t n, int to_mont, cudaStream_t s) {
     if (n == 0) return 0;
@@ -733,7 +796,9 @@ static int bases_register_impl(int curve, const void *bases_xy, size_t n, int re
     cudaStream_t s = g_ctx.stream;
     if (n) CU(cudaMemcpyAsync(b->buf.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
     if (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), n, 1, s)) return 1;
-    if ((flags & H2_BASES_PRECOMPUTE) && n > 0 && build_table(b, window_bits, s)) return 1;
+    const bool direct = (flags & H2_BASES_DIRECT) && (flags & H2_BASES_PRECOMPUTE) && n > 0;
+    if ((flags & H2_BASES_PRECOMPUTE) && n > 0 && build_table(b, direct ? H2_FB_BITS : window_bits, s)) return 1;
+    if (direct && build_direct(b, s)) return 1;
     CU(cudaStreamSynchronize(s));
     uint64_t h = g_ctx.next_handle++;
     g_ctx.bases[h] = b;
@@ -748,6 +813,7 @@ extern "C" int h2_bases_release(uint64_t handle) {
     cudaDeviceSynchronize();
     it->second->buf.release();
     it->second->table.release();
+    it->second->dtable.release();
     delete it->second;
     g_ctx.bases.erase(it);
     return 0;
@@ -760,8 +826,11 @@ extern "C" int h2_msm_registered(uint64_t handle, const void *scalars, size_t n,
     BaseSet *b = it->second;
     size_t total = n + (extra_scalar ? 1 : 0);
     if (total > b->n) return fail("h2_msm_registered: more scalars than registered bases");
-    if (b->table.p)   // fixed-base path: window table, one shared bucket set
-        return msm_host_common(b->curve, scalars, n, extra_scalar, b->table.as<affine>(), total, repr, out_xyz, b->c, 1, b->n);
+    if (b->table.p) {   // fixed-base path: digit-multiples table (direct sum) or window table (one shared bucket set)
+        uint32_t c, mode;
+        const affine *t = fixed_table(b, &c, &mode);
+        return msm_host_common(b->curve, scalars, n, extra_scalar, t, total, repr, out_xyz, c, mode, b->n);
+    }
     return msm_host_common(b->curve, scalars, n, extra_scalar, b->buf.as<affine>(), total, repr, out_xyz);
 }
 
@@ -803,8 +872,10 @@ static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_
         CU(cudaMemcpy2DAsync(d + n, total * sizeof(fe), extra_scalars, sizeof(fe), sizeof(fe), batch, cudaMemcpyHostToDevice, s));
     }
     const int canon = repr == H2_REPR_CANONICAL;
-    int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, b->table.as<affine>(), total, b->c, X.result.as<jacobian>(),
-                          affine_out ? 0 : canon, s, 1, b->n, nullptr, (uint32_t)batch);
+    uint32_t tc, tmode;
+    const affine *tbl = fixed_table(b, &tc, &tmode);
+    int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, tbl, total, tc, X.result.as<jacobian>(),
+                          affine_out ? 0 : canon, s, tmode, b->n, nullptr, (uint32_t)batch);
     if (rc) return rc;
     if (affine_out) {
         if (X.ec_out.ensure(batch * sizeof(affine))) return 1;
@@ -1164,7 +1235,9 @@ template <class PS> static int ipa_round_impl(IpaSession *q, BaseSet *b, const v
     IpaState S = ipa_state(q);
     LAUNCH(ipa_prep_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, bit);
     LAUNCH(ipa_inner_kernel<PS>, 1, 512, 0, s, S, bit, host_to_mont<PS>(z, repr), host_to_mont<PS>(l_rand, repr), host_to_mont<PS>(r_rand, repr));
-    return msm_dispatch(b->curve, S.scal, 1, b->table.as<affine>(), n + 2, b->c, q->out.as<jacobian>(), repr == H2_REPR_CANONICAL, s, 1, b->n, nullptr, 2);
+    uint32_t tc, tmode;
+    const affine *tbl = fixed_table(b, &tc, &tmode);
+    return msm_dispatch(b->curve, S.scal, 1, tbl, n + 2, tc, q->out.as<jacobian>(), repr == H2_REPR_CANONICAL, s, tmode, b->n, nullptr, 2);
 }
 extern "C" int h2_ipa_round(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1376,8 +1449,10 @@ extern "C" int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *po
         if (extra_scalars) CU(cudaMemcpyAsync(d + j * total + n, X.misc.as<fe>() + j, sizeof(fe), cudaMemcpyDeviceToDevice, s));
     }
     int rc;
-    if (b->table.p) rc = msm_dispatch(b->curve, d, 1, b->table.as<affine>(), total, b->c, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s, 1, b->n,
-                                      nullptr, (uint32_t)batch);
+    uint32_t tc = 0, tmode = 0;
+    const affine *tbl = b->table.p ? fixed_table(b, &tc, &tmode) : nullptr;
+    if (tbl) rc = msm_dispatch(b->curve, d, 1, tbl, total, tc, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s, tmode, b->n,
+                               nullptr, (uint32_t)batch);
     else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));

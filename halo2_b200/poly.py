@@ -20,6 +20,7 @@ FIELDS = {
     "fq": 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001,
 }
 S = 32  # two-adicity of both fields
+DIRECT_DEFAULT: Optional[bool] = None  # None: digit-multiples tables for k <= 14 (Params(direct=...) overrides; tests flip this)
 
 
 class Blind:
@@ -50,7 +51,8 @@ class Params:
     polynomial.  Generator DERIVATION (Params::new's hash-to-curve, :38-114) is the caller's:
     pass the generators in, e.g. as read by Params::read (:185-205)."""
 
-    def __init__(self, curve: str, k: int, g, g_lagrange, w, u=None, precompute: bool = True, window_bits: int = 0):
+    def __init__(self, curve: str, k: int, g, g_lagrange, w, u=None, precompute: bool = True, window_bits: int = 0,
+                 direct: Optional[bool] = None):
         assert k < 32  # commitment.rs:41
         self.curve, self.k, self.n = curve, k, 1 << k
         self.g = _l.as_u8(g, 64)
@@ -65,6 +67,16 @@ class Params:
         # tmp_bases = g ++ [w]  (:126-127); u rides along at index n + 1 for the IPA rounds (prover.rs:118-119)
         both = np.concatenate([self.g, self.w] + ([] if self.u is None else [self.u]))
         flags = 1 if precompute else 0   # H2_BASES_PRECOMPUTE: window tables, fixed-base MSM
+        # H2_BASES_DIRECT: digit-multiples tables (256 KiB per generator) for small sets -- commits and IPA rounds become
+        # plain sums of table entries (csrc/fixedbase.cuh).  Default: on up to k = 14 unless a window size was asked for.
+        if direct is None:
+            direct = DIRECT_DEFAULT
+        if direct is None:
+            direct = bool(precompute) and window_bits == 0 and k <= 14
+        if direct:
+            assert precompute and k <= 15, "direct tables need precompute=True and k <= 15"
+            flags |= 2
+        self.direct = bool(direct)
         self._has_table = bool(precompute)
         _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(both.shape[0]), _l.REPR_CANONICAL,
                                           ctypes.c_uint32(window_bits), ctypes.c_uint32(flags), ctypes.byref(self._h_g)))

@@ -62,7 +62,11 @@ int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint6
  * T[w][i] = 2^(c w) * bases[i] (W = ceil(256/c) affine copies, c = window_bits or automatic when 0).
  * h2_msm_registered then drops every window's digits into ONE bucket set: no window combine, 1/W of
  * the bucket reduce -- what makes k = 14 sized commits latency-friendly. */
-enum { H2_BASES_PRECOMPUTE = 1 };
+enum { H2_BASES_PRECOMPUTE = 1, H2_BASES_DIRECT = 2 };
+/* flags & H2_BASES_DIRECT (with H2_BASES_PRECOMPUTE, sets of at most 2^15 + 2 points): also build the digit-multiples table
+ * D[w][m][i] = m * 2^(8 w) * bases[i] (32 windows x 128 multiples, 256 KiB per point: 4.3 GB at k = 14).  Every fixed-base
+ * MSM over the set -- commits, batches, IPA rounds -- is then a plain sum of the n x 32 entries the signed base-256 digits
+ * select (three launches, no buckets): halo2_b200/csrc/fixedbase.cuh.  Same group element either way. */
 int h2_bases_register_ex(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags,
                          uint64_t *handle);
 int h2_bases_release(uint64_t handle);

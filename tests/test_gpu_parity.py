@@ -22,6 +22,16 @@ def eng():
     return halo2_b200
 
 
+@pytest.fixture(params=["direct", "buckets"])
+def table_mode(request):
+    """Fixed-base MSMs over resident generators run either on the digit-multiples table (direct sum, csrc/fixedbase.cuh:
+    the default up to k = 14) or on the window table with one shared bucket set; both must give the oracle's points."""
+    from halo2_b200 import poly
+    poly.DIRECT_DEFAULT = request.param == "direct"
+    yield request.param
+    poly.DIRECT_DEFAULT = None
+
+
 def _field_op(field, op, a, b=None):
     from halo2_b200 import lib as L
     lib = L.init()
@@ -290,7 +300,7 @@ def test_window_sweep_and_montgomery_inputs(eng):
 
 
 @pytest.mark.parametrize("curve", ["pallas", "vesta"])
-def test_commit_lagrange_equals_commit(eng, curve):
+def test_commit_lagrange_equals_commit(eng, curve, table_mode):
     """poly/commitment.rs:258-302 at k=6: commit(lagrange_to_coeff(a)) == commit_lagrange(a), with
     g_lagrange from the oracle's EC-FFT (commitment.rs:77-94) -- ties NTT, MSM and resident bases."""
     c = pasta.CURVES[curve]
@@ -335,7 +345,7 @@ def test_resident_bases_with_window_table(eng, curve, k):
     for name, poly in polys.items():
         kb = np.concatenate([poly, cref.ints_to_bytes([blind])])
         wants[name] = cref.bytes_to_affine(cref.best_multiexp(curve, kb, g))
-    for flags, wbits in ((1, 0), (1, 9), (1, 13), (0, 0)):
+    for flags, wbits in ((1, 0), (3, 0), (1, 9), (1, 13), (0, 0)):   # 3 = + H2_BASES_DIRECT: digit-multiples table, direct sum
         h = ctypes.c_uint64(0)
         L.check(lib.h2_bases_register_ex(L.CURVE_ID[curve], L.ptr(g), ctypes.c_size_t(n + 1), L.REPR_CANONICAL,
                                          ctypes.c_uint32(wbits), ctypes.c_uint32(flags), ctypes.byref(h)))
@@ -352,7 +362,7 @@ def test_resident_bases_with_window_table(eng, curve, k):
             L.check(lib.h2_bases_release(h))
 
 
-def test_commit_many_batched(eng):
+def test_commit_many_batched(eng, table_mode):
     """Batched commits (one pass, one bucket set per polynomial) == the individual commits == the oracle."""
     curve, c, k = "vesta", pasta.VESTA, 12
     n = 1 << k
@@ -374,7 +384,7 @@ def test_commit_many_batched(eng):
     params.close()
 
 
-def test_ipa_rounds(eng):
+def test_ipa_rounds(eng, table_mode):
     """The device IPA round loop (fold-free, resident generators) == the reference loop restated in the oracle
     (poly/commitment/prover.rs:100-142): every L_j, R_j and the final c, on both curves; commit() keeps working
     on the same base set (w at index n, u at n + 1)."""
@@ -503,7 +513,7 @@ def test_msm_chunked_upload(eng):
         L.check(lib.h2_test_set_chunk_threshold(19))
 
 
-def test_resident_polynomials(eng):
+def test_resident_polynomials(eng, table_mode):
     """The device-resident pipeline (upload once; lagrange -> coeff -> extended -> coeff and commits on handles) gives
     exactly what the host-buffer calls -- and therefore the oracle -- give."""
     field, curve, k, j = "fp", "vesta", 9, 5
@@ -549,7 +559,7 @@ def test_resident_polynomials(eng):
     params.close()
 
 
-def test_fixed_base_graph_replay(eng):
+def test_fixed_base_graph_replay(eng, table_mode):
     """Fixed-base MSMs replay a captured CUDA graph from their third call with the same parameters: six different
     polynomials in a row (and batches of them) still each give their own commitment; switching the replay off gives
     the same points."""

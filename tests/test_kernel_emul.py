@@ -383,3 +383,33 @@ def test_emul_ec_fft_and_params_lagrange(emu, curve, k, quad):
     got = np.zeros((n, 64), dtype=np.uint8)
     emu.emu_batch_normalize(cref.CURVE_ID[curve], cref._p(o), ctypes.c_uint64(n), cref._p(got))
     assert (got == want).all()
+
+
+# ---- K12: direct-sum fixed-base MSM (multiples table, signed base-256 digits, quad reduce tree) -----------------------
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_direct_fixed_base(emu, curve):
+    c = pasta.CURVES[curve]
+    r = c.r
+    n = 70
+    bases = cref.gen_points(curve, 700, n)
+    bases[5] = 0                                                   # an identity generator
+    bases[9] = bases[8]                                            # a repeated one (equal partial sums meet in the tree)
+    rnd = cref.gen_scalars(c.scalar, 701, n)
+    edge = cref.ints_to_bytes([0, 1, 128, 129, 255, 256, 0x80, 0x7F80, r - 1, r - 2, (1 << 254), (1 << 248) * 0x40, 0x8080808080808080,
+                               int("81" * 31, 16), int("80" * 31, 16), int("ff" * 31, 16)] + [7] * (n - 16))
+    same = cref.ints_to_bytes([3] * n)
+    for total, sets, split, name, kb in ((n, 1, 0, "random", rnd), (n, 1, 1, "random/1", rnd), (n, 1, 2, "edge/2", edge), (n, 1, 8, "edge/8", edge),
+                                          (n - 3, 1, 4, "same", same[:n - 3]), (1, 1, 0, "one", rnd[:1]),
+                                          (n // 2, 2, 0, "two sets", rnd)):
+        out = np.zeros((sets, 64), dtype=np.uint8)
+        emu.emu_msm_direct(cref.CURVE_ID[curve], cref._p(np.ascontiguousarray(kb)), cref._p(bases), ctypes.c_size_t(n), ctypes.c_size_t(total),
+                           sets, split, 0, cref._p(out))
+        for s_ in range(sets):
+            want = cref.best_multiexp(curve, np.ascontiguousarray(kb[s_ * total:(s_ + 1) * total]), np.ascontiguousarray(bases[:total]))
+            assert (out[s_] == want).all(), (name, s_)
+    # Montgomery scalars (the IPA session's form)
+    R = 1 << 256
+    km = cref.ints_to_bytes([v * R % r for v in cref.bytes_to_ints(rnd)])
+    out = np.zeros((1, 64), dtype=np.uint8)
+    emu.emu_msm_direct(cref.CURVE_ID[curve], cref._p(km), cref._p(bases), ctypes.c_size_t(n), ctypes.c_size_t(n), 1, 0, 1, cref._p(out))
+    assert (out[0] == cref.best_multiexp(curve, rnd, bases)).all()

@@ -13,9 +13,11 @@ pp = cref.gen_scalars("fp", 2, n)
 polys = [cref.gen_scalars("fp", 10 + i, n) for i in range(4)]
 ch = cref.bytes_to_ints(cref.gen_scalars("fp", 3, k))
 lr = cref.bytes_to_ints(cref.gen_scalars("fp", 4, k))
-for c in [int(a) for a in sys.argv[2:]] or [0, 11, 12, 13, 14, 15, 16, 17]:
+for c in [int(a) for a in sys.argv[2:]] or [-1, 0, 13, 15, 17]:      # -1: digit-multiples table (direct sum); 0: automatic window
     try:
-        params = h2.Params("vesta", k, g[:n], g[:n], g[n:n + 1], u=g[n + 1:n + 2], window_bits=c)
+        t0 = time.perf_counter()
+        params = h2.Params("vesta", k, g[:n], g[:n], g[n:n + 1], u=g[n + 1:n + 2], window_bits=max(c, 0), direct=(c < 0))
+        print(f"c={c:2d}: Params setup {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
     except Exception as e:  # noqa: BLE001
         print(f"c={c}: {e}", flush=True)
         continue
