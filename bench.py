@@ -578,9 +578,9 @@ def main():
             # ---- create_proof k=14: replay of the prover's hot-path calls (host API, copies included)
             import halo2_b200 as h2
             from halo2_b200 import poly as h2poly
-            h2poly.DIRECT_DEFAULT = False      # the window-table / bucket form of the fixed-base MSMs, for comparison
-            gdt_b, setup_b, _, by_kind_b = prover_replay_gpu(h2, cref)
-            h2poly.DIRECT_DEFAULT = None       # default: digit-multiples tables (direct sum) at k = 14
+            h2poly.DIRECT_DEFAULT = True       # opt-in digit-multiples tables (direct sum, csrc/fixedbase.cuh), for comparison
+            gdt_b, setup_b, _, by_kind_b = prover_replay_gpu(h2, cref, reps=2)
+            h2poly.DIRECT_DEFAULT = None       # default: window tables, one shared bucket set
             gdt, setup_s, sched, by_kind = prover_replay_gpu(h2, cref)
             cdt, cpu_by_kind, ipa_threads = prover_replay_cpu(cref, threads)
             kinds = {}
@@ -593,9 +593,9 @@ def main():
                 "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": cpu_by_kind,
                                  "ipa_threads": ipa_threads},
                 "params_setup_ms": setup_s * 1e3, "calls": kinds, "gpu_ms_by_kind": by_kind,
-                "fixed_base_tables": "digit multiples m 2^(8w) G_i, direct sum (csrc/fixedbase.cuh); 2 x 4.3 GB resident",
-                "with_window_tables": {"value": gdt_b * 1e3, "params_setup_ms": setup_b * 1e3, "gpu_ms_by_kind": by_kind_b,
-                                       "fixed_base_tables": "window shifts 2^(16w) G_i, one shared bucket set (csrc/msm.cuh)"},
+                "fixed_base_tables": "window shifts 2^(15w) G_i, one shared bucket set (csrc/msm.cuh)",
+                "with_digit_tables": {"value": gdt_b * 1e3, "params_setup_ms": setup_b * 1e3, "gpu_ms_by_kind": by_kind_b,
+                                      "fixed_base_tables": "opt-in: digit multiples m 2^(8w) G_i, direct sum (csrc/fixedbase.cuh); 2 x 4.3 GB"},
                 "note": "replay of SURVEY.md Appendix C call schedule (benches/plonk.rs circuit, Vesta, k=14, ext_k=16) through the "
                         "reference-facing host API; NOT the Rust prover: witness synthesis, h(X) evaluation and the transcript run on the CPU "
                         "in both arms and are not timed.  ipa = all k rounds of poly/commitment/prover.rs:100-142 (CPU arm: 2k "

@@ -85,7 +85,7 @@ struct Context {
     const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
     uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
-    uint32_t ecfft_quad = 1;                 // EC-FFT butterflies run on quads of lanes (0: one thread each, test hook)
+    uint32_t ecfft_quad = 1;                 // EC-FFT butterfly form: 1 = by size (default), 0 = one thread each, 2 = quads (test hook)
     // MSM scratch
     DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
         wsum, scan_blocks, result, misc;
@@ -239,10 +239,10 @@ extern "C" int h2_test_set_graphs(int on) {
     g_ctx.graphs_on = on ? 1u : 0u;
     return 0;
 }
-// test hook: EC-FFT butterflies on quads of lanes (default) or one thread each
+// test hook: EC-FFT butterfly form -- 1: quads of lanes, 0: one thread each, -1: by size (the default)
 extern "C" int h2_test_set_ecfft_quad(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g_ctx.ecfft_quad = on ? 1u : 0u;
+    g_ctx.ecfft_quad = on < 0 ? 1u : on ? 2u : 0u;   // -1: by size (default), 0: thread form, 1: quad form
     return 0;
 }
 // test hook: one-shot MSMs (h2_msm) of >= 2^log2_n points upload their bases in chunks (default 19)
@@ -494,7 +494,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     std::function<int()> issue;
     if (fixed == 2) {   // direct sum over the digit-multiples table (fixedbase.cuh): accumulate + reduce tree
         FbPlan fp;
-        fp.total = n; fp.stride = stride; fp.sets = sets ? sets : 1u; fp.split = fb_split(n, fp.sets); fp.scalars_mont = scalars_mont ? 1u : 0u;
+        fp.total = n; fp.sets = sets ? sets : 1u; fp.split = fb_split(n, fp.sets); fp.scalars_mont = scalars_mont ? 1u : 0u;
         const uint64_t count0 = n * fp.split;
         if (X.fb_a.ensure(fp.sets * count0 * sizeof(xyzz)) || X.fb_b.ensure(fp.sets * fb_ctas(count0, fb_fan(count0)) * sizeof(xyzz))) return 1;
         issue = [&X, fp, count0, d_scalars, d_bases, d_out, out_canonical, s]() -> int {
@@ -662,7 +662,7 @@ static uint32_t table_window(size_t n) {
     uint32_t want = lg + 2;
     if (want <= 9) return 8;
     if (want <= 15) return 15;
-    if (want == 16) return 16;
+    if (want == 16) return 15;        // k = 14: 15 measured better than 16 (IPA opening 5.5 vs 6.2 ms, commit equal; tools/table_sweep.py)
     if (want <= 18) return 17;
     return 20;
 }
@@ -1089,11 +1089,16 @@ static int ecfft_stages(int scalar_field, xyzz *work, uint32_t log_n, const fe &
     if (get_twiddles<PS>(scalar_field, omega_mont, log_n, s, &tw)) return 1;
     const uint64_t n = 1ull << log_n;
     // one QUAD of lanes per butterfly (ecfft.cuh) unless the test hook asks for the one-thread form
-    const uint32_t q = g_ctx.ecfft_quad ? 4u : 1u;
-    auto stage = g_ctx.ecfft_quad ? ecfft_stage_quad_kernel<P, PS> : ecfft_stage_kernel<P, PS>;
+    // Measured (k = 10 / 12 / 14, g -> g_lagrange): quads 10.3 / 12.4 / 18.2 ms, one thread per butterfly 12.6 / 14.8 /
+    // 17.6 ms -- a quad level costs ~3 multiply latencies (selects, call, 32 shuffles, limb carries), so the quad form only
+    // wins while a stage has too few butterflies to give every SM a warp.  ecfft_quad: 1 = by size (default), 0 / 2 = force
+    // the thread / quad form (test hook).
+    const bool use_quad = g_ctx.ecfft_quad == 2 || (g_ctx.ecfft_quad == 1 && log_n <= 12);
+    const uint32_t q = use_quad ? 4u : 1u;
+    auto stage = use_quad ? ecfft_stage_quad_kernel<P, PS> : ecfft_stage_kernel<P, PS>;
     for (uint32_t st = 1; st <= log_n; st++) LAUNCH(stage, blocks_for(n / 2 * q, 64), 64, 0, s, work, tw, log_n, st);
     if (scale_canon) {
-        auto sc = g_ctx.ecfft_quad ? ecfft_scale_quad_kernel<P, PS> : ecfft_scale_kernel<P, PS>;
+        auto sc = use_quad ? ecfft_scale_quad_kernel<P, PS> : ecfft_scale_kernel<P, PS>;
         LAUNCH(sc, blocks_for(n * q, 64), 64, 0, s, work, *scale_canon, n);
     }
     return 0;

@@ -6,7 +6,11 @@
 // launches of 10-70 us for 40 us worth of multiplies.  The generators of a Params never change
 // (poly/commitment.rs:26-33), so for small sets the table can hold every digit multiple instead of every window shift:
 //
-//     D[w][m][i] = m * 2^(8 w) * G_i      w < 32 windows of 8 bits, m = 1 .. 128 (signed digits), affine
+//     D[i][w][m] = m * 2^(8 w) * G_i      w < 32 windows of 8 bits, m = 1 .. 128 (signed digits), affine
+//
+// (a generator's 4096 entries are contiguous: the 32 gathers of one scalar stay inside one 256 KiB region and the lanes of a
+// warp inside a few MB -- with the generator index innermost every gather of a warp hit a different 2 MB page of the
+// 4.3 GB table and both the build and the accumulation ran at the page-walk rate)
 //
 // 32 x 128 x 64 B = 256 KiB per generator -- 4.3 GB at k = 14, nothing next to 180 GB of HBM -- and a commit is a
 // plain SUM of the n x 32 table entries the signed base-256 digits select: no buckets, no sort, no reduce chain.
@@ -30,7 +34,6 @@ namespace h2 {
 
 struct FbPlan {
     uint64_t total;        // scalars per set (<= the set's registered points)
-    uint64_t stride;       // points per table row
     uint32_t sets;         // scalars are laid out [set][total], results [set]
     uint32_t split;        // threads per scalar: each takes 32 / split windows (1, 2, 4, 8)
     uint32_t scalars_mont;
@@ -44,9 +47,9 @@ template <class P, class PS> struct FixedBase {
         if (t >= (uint64_t)H2_FB_WINDOWS * count) return;
         const uint64_t w = t / count, i = t % count;
         const affine B = ld_affine(wtab + w * stride + i);
-        affine *dst = dtab + (w * H2_FB_MULTIPLES) * stride + i;        // multiple m lives at dst + (m - 1) * stride
+        affine *dst = dtab + (i * H2_FB_WINDOWS + w) * H2_FB_MULTIPLES;   // multiple m lives at dst[m - 1]
         if (affine_is_identity(B)) {
-            for (uint32_t m = 0; m < H2_FB_MULTIPLES; m++) st_affine(dst + (uint64_t)m * stride, B);
+            for (uint32_t m = 0; m < H2_FB_MULTIPLES; m++) st_affine(dst + m, B);
             return;
         }
         xyzz R = xyzz_from_affine<P>(B);
@@ -58,7 +61,7 @@ template <class P, class PS> struct FixedBase {
                 if (m == 2) R = xyzz_double_affine<P>(B);
                 else if (m > 2) xyzz_add_mixed<P>(R, B);               // m * B != identity, != B: the group order is prime
                 affine park; park.x = R.x; park.y = R.y;
-                st_affine(dst + (uint64_t)(m - 1) * stride, park);
+                st_affine(dst + (m - 1), park);
                 zz[j] = R.zz; zzz[j] = R.zzz; pre[j] = run;
                 run = fe_mul_call<P>(run, fe_mul_call<P>(R.zz, R.zzz));
             }
@@ -66,10 +69,10 @@ template <class P, class PS> struct FixedBase {
             for (uint32_t j = H2_FB_NORM; j-- > 0;) {
                 fe id = fe_mul_call<P>(inv, pre[j]);                    // 1 / (zz zzz)
                 inv = fe_mul_call<P>(inv, fe_mul_call<P>(zz[j], zzz[j]));
-                affine a = ld_affine(dst + (uint64_t)(c0 + j) * stride);
+                affine a = ld_affine(dst + (c0 + j));
                 a.x = fe_mul_call<P>(a.x, fe_mul_call<P>(id, zzz[j]));   // X / ZZ
                 a.y = fe_mul_call<P>(a.y, fe_mul_call<P>(id, zz[j]));    // Y / ZZZ
-                st_affine(dst + (uint64_t)(c0 + j) * stride, a);
+                st_affine(dst + (c0 + j), a);
             }
         }
     }
@@ -92,7 +95,7 @@ template <class P, class PS> struct FixedBase {
             carry = d > 128u ? 1u : 0u;
             if (w < w_lo || d == 0 || d == 256u) continue;              // 256 - 256 = 0
             const uint32_t m = carry ? 256u - d : d;                    // |digit| in 1 .. 128
-            affine pt = ld_affine(dtab + ((uint64_t)w * H2_FB_MULTIPLES + (m - 1)) * p.stride + i);
+            affine pt = ld_affine(dtab + (i * H2_FB_WINDOWS + w) * H2_FB_MULTIPLES + (m - 1));
             if (carry) pt.y = fe_neg<P>(pt.y);
             xyzz_add_mixed<P>(acc, pt);
         }
@@ -140,7 +143,7 @@ inline uint32_t fb_split(uint64_t total, uint32_t sets) {
 template <class P, class PS> __global__ void __launch_bounds__(128) fb_table_kernel(const affine *wtab, affine *dtab, uint64_t count, uint64_t stride) {
     FixedBase<P, PS>::table_body(wtab, dtab, count, stride, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-template <class P, class PS> __global__ void __launch_bounds__(128) fb_accum_kernel(const FbPlan p, const fe *scalars, const affine *dtab, xyzz *partial) {
+template <class P, class PS> __global__ void __launch_bounds__(128, 5) fb_accum_kernel(const FbPlan p, const fe *scalars, const affine *dtab, xyzz *partial) {
     FixedBase<P, PS>::accum_body(p, scalars, dtab, partial, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 // grid (ctas, sets); in / out hold `in_stride` / `out_stride` entries per set.  final: the single CTA of a set writes

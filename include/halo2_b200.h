@@ -64,7 +64,7 @@ int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint6
  * the bucket reduce -- what makes k = 14 sized commits latency-friendly. */
 enum { H2_BASES_PRECOMPUTE = 1, H2_BASES_DIRECT = 2 };
 /* flags & H2_BASES_DIRECT (with H2_BASES_PRECOMPUTE, sets of at most 2^15 + 2 points): also build the digit-multiples table
- * D[w][m][i] = m * 2^(8 w) * bases[i] (32 windows x 128 multiples, 256 KiB per point: 4.3 GB at k = 14).  Every fixed-base
+ * D[i][w][m] = m * 2^(8 w) * bases[i] (32 windows x 128 multiples, 256 KiB per point: 4.3 GB at k = 14).  Every fixed-base
  * MSM over the set -- commits, batches, IPA rounds -- is then a plain sum of the n x 32 entries the signed base-256 digits
  * select (three launches, no buckets): halo2_b200/csrc/fixedbase.cuh.  Same group element either way. */
 int h2_bases_register_ex(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags,
@@ -203,7 +203,7 @@ int h2_test_set_chunk_threshold(uint32_t log2_n);
 /* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
  * parameters on (default); 0 issues every launch individually. */
 int h2_test_set_graphs(int on);
-/* EC-FFT butterflies on quads of lanes (default) or one thread each. */
+/* EC-FFT butterfly form: 1 = quads of lanes, 0 = one thread each, -1 = chosen by size (the default). */
 int h2_test_set_ecfft_quad(int on);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */

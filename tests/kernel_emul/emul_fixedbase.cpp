@@ -18,7 +18,7 @@ static int run_fb(const uint8_t *scalars, const uint8_t *bases, size_t n, size_t
     std::vector<fe> sc(sets * total);
     memcpy(sc.data(), scalars, sets * total * 32);
     FbPlan p;
-    p.total = total; p.stride = n; p.sets = sets; p.split = split ? split : fb_split(total, sets); p.scalars_mont = scalars_mont ? 1u : 0u;
+    p.total = total; p.sets = sets; p.split = split ? split : fb_split(total, sets); p.scalars_mont = scalars_mont ? 1u : 0u;
     uint64_t count = total * p.split;
     std::vector<xyzz> a(sets * count), b;
     for (uint64_t u = 0; u < sets * count; u++) FixedBase<P, PS>::accum_body(p, sc.data(), dtab.data(), a.data(), u);

@@ -633,7 +633,7 @@ def ecfft_form(request):
     from halo2_b200 import lib as L
     L.check(L.init().h2_test_set_ecfft_quad(request.param))
     yield request.param
-    L.check(L.init().h2_test_set_ecfft_quad(1))
+    L.check(L.init().h2_test_set_ecfft_quad(-1))
 
 
 @pytest.mark.parametrize("curve", ["pallas", "vesta"])

@@ -12,7 +12,7 @@ $NCU -c 400 --log-file $out/${tag}_launches_msm.csv python tools/prof_run.py msm
 $NCU -c 600 --log-file $out/${tag}_launches_small.csv python tools/prof_run.py small > /dev/null 2>&1
 $NCU -c 1200 --log-file $out/${tag}_launches_ipa.csv python tools/ipa_time.py 14 1 > /dev/null 2>&1
 $NCU -c 200 --log-file $out/${tag}_launches_ecfft.csv python tools/ecfft_time.py 14 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ecfft_stage_quad -s 8 -c 1 -o $out/${tag}_ecfft_stage python tools/ecfft_time.py 14 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ecfft_stage_kernel -s 8 -c 1 -o $out/${tag}_ecfft_stage python tools/ecfft_time.py 14 > /dev/null 2>&1
 ncu -i $out/${tag}_ecfft_stage.ncu-rep --page raw --csv > $out/${tag}_ecfft_stage_ncu_full_raw.csv 2>/dev/null
 rm -f $out/${tag}_ecfft_stage.ncu-rep
 ls -la $out | tail -15

@@ -24,6 +24,7 @@ for k in ks:
             out = halo2_b200.lagrange_generators(curve, k, g)
         gpu_ms = (time.perf_counter() - t) / reps * 1e3
         line += f" GPU {'quad' if form else 'thread'} form {gpu_ms:.2f} ms,"
+    L.check(L.init().h2_test_set_ecfft_quad(-1))
     if k <= int(os.environ.get("ECFFT_CPU_MAX_K", "12")):
         r = c.r
         t = time.perf_counter()

@@ -1,0 +1,47 @@
+"""Assembles profiles/<tag>_summary.md from the files tools/capture.sh left in gpurun_out/ and copies the evidence into profiles/.
+usage: python tools/make_summary.py <tag> "<one-line title>" """
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+tag, title = sys.argv[1], sys.argv[2]
+src, dst = "gpurun_out", "profiles"
+parts = [f"# {title}\n",
+         "`ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/prof_run.py {msm,small}`, `... tools/ipa_time.py 14 1`, "
+         "`... tools/ecfft_time.py 14` (cold-cache, serialised launches: compare shares, not absolutes; gen_points / at:: kernels are input "
+         "generation).  Command list: `tools/capture.sh`.\n"]
+for name, ttl in (("msm", "MSM 2^20 Pallas one-shot (device-resident inputs), 3 calls"), ("small", "MSM 2^14+1 Vesta one-shot, 3 calls"),
+                  ("ipa", "k=14 Vesta: Params setup (window tables), 1 commit, 14 IPA rounds"),
+                  ("ecfft", "k=14 Vesta g -> g_lagrange (EC-iFFT + scale + batch_normalize), thread form then quad form, 4 calls each")):
+    f = f"{src}/{tag}_launches_{name}.csv"
+    if os.path.exists(f):
+        shutil.copy(f, dst)
+        parts.append(subprocess.run([sys.executable, "tools/summarize_launches.py", f, ttl], capture_output=True, text=True).stdout)
+for extra in (f"{tag}_bench_n1.json", f"{tag}_ecfft_stage_ncu_full_raw.csv", f"{tag}_pytest_gpu.txt", f"{tag}_smoke.txt"):
+    if os.path.exists(f"{src}/{extra}") and os.path.getsize(f"{src}/{extra}"):
+        shutil.copy(f"{src}/{extra}", dst)
+b = f"{src}/{tag}_bench_n1.json"
+if os.path.exists(b) and os.path.getsize(b):
+    d = json.loads(open(b).read().strip().splitlines()[-1])
+    r, e, x = d["roofline"], d["e2e"], d["extra"]
+    parts.append("### bench.py line (1 GPU)\n")
+    parts.append(f"* MSM 2^20 device-resident: {d['value'] / 1e6:.1f} M pairs/s ({d['ms_per_step']:.3f} ms); through the host API: "
+                 f"{e['value'] / 1e6:.1f} M pairs/s ({e['ms_per_step']:.3f} ms); CPU restatement {d['cpu_baseline']['value'] / 1e6:.2f} M pairs/s "
+                 f"on {d['cpu_baseline']['cores']} threads.")
+    parts.append(f"* {r['kernel']}: {r['kernel_ms']:.3f} ms per launch, {r['achieved']:.1f} GB/s algorithmic = {100 * r['frac']:.2f} % of the "
+                 f"{r['peak']} GB/s HBM peak; {r['compute']['achieved']:.1f} of {r['compute']['peak']:.1f} G modmul/s ({100 * r['compute']['frac']:.0f} %).")
+    n = x["ntt"]
+    parts.append(f"* NTT 2^20: {n['value'] / 1e9:.2f} G elems/s ({n['ms_per_step']:.3f} ms), host API {n['e2e']['value'] / 1e9:.2f} G elems/s.")
+    c = x["create_proof_k14_replay"]
+    parts.append(f"* create_proof k=14 hot-path replay: {c['value']:.2f} ms (window tables, default) / "
+                 f"{c.get('with_digit_tables', {}).get('value', float('nan')):.2f} ms (opt-in digit-multiples tables) vs {c['cpu_baseline']['value']:.0f} ms CPU; by kind "
+                 f"{json.dumps({k: round(v, 3) for k, v in c['gpu_ms_by_kind'].items()})}; Params setup {c['params_setup_ms']:.0f} ms.")
+    if "params_lagrange_k14" in x:
+        p = x["params_lagrange_k14"]
+        parts.append(f"* g -> g_lagrange at k=14: {p['gpu_ms']:.2f} ms vs CPU restatement {p['cpu_baseline']['ms']:.0f} ms at k={p['cpu_baseline']['k']} "
+                     f"({p['cpu_baseline']['cores']} threads).")
+    parts.append(f"* clocks {d['clocks']}\n")
+open(f"{dst}/{tag}_summary.md", "w").write("\n".join(parts))
+print(open(f"{dst}/{tag}_summary.md").read()[:3000])
