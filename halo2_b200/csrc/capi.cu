@@ -85,6 +85,9 @@ struct Context {
     const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
     uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
+    uint32_t accum_ways = 1;                 // quads per work item in the small-problem accumulation (1, 2, 4; test hook).  Measured at
+                                             // k = 14, c = 15: commit 0.360 / 0.329 / 0.361 ms, IPA opening 5.7 / 6.1 / 7.6 ms -- the accumulation is
+                                             // bound by lane-multiplies (a quad addition occupies 16 slots for 10 products), not by its chains
     uint32_t ecfft_quad = 1;                 // EC-FFT butterfly form: 1 = by size (default), 0 = one thread each, 2 = quads (test hook)
     // MSM scratch
     DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
@@ -237,6 +240,15 @@ extern "C" int h2_test_last_msm_flags(uint32_t *out) {
 extern "C" int h2_test_set_graphs(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_ctx.graphs_on = on ? 1u : 0u;
+    return 0;
+}
+// test hook: quads per work item of the small-problem accumulation (1, 2 or 4).  Invalidates nothing: graphs are keyed by
+// their parameters only, so flip it before the first fixed-base MSM of a base set or with graphs off.
+extern "C" int h2_test_set_accum_ways(uint32_t ways) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ways != 1 && ways != 2 && ways != 4) return fail("h2_test_set_accum_ways: 1, 2 or 4");
+    g_ctx.accum_ways = ways;
+    for (auto &ge : g_ctx.graphs) if (ge.exec) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; ge.seen = 0; }
     return 0;
 }
 // test hook: EC-FFT butterfly form -- 1: quads of lanes, 0: one thread each, -1: by size (the default)
@@ -592,6 +604,8 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         auto k_iplace = msm_item_place_kernel<P, PS>;
         auto k_accum0 = msm_accum0_kernel<P, PS>;
         auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
+        auto k_accum0m2 = msm_accum0_multi_kernel<P, PS, 2>;
+        auto k_accum0m4 = msm_accum0_multi_kernel<P, PS, 4>;
         auto k_accumN = msm_accumN_kernel<P, PS>;
         auto k_rest = msm_accum_rest_kernel<P, PS>;
         auto k_reduceA = msm_reduceA_kernel<P, PS>;
@@ -625,7 +639,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
                 LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
             }
             prof_begin(PROF_MSM_ACCUM0, s);
-            if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);   // latency-bound: quads
+            if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) {   // latency-bound: quads, several per work item
+                if (X.accum_ways == 4) LAUNCH(k_accum0m4, blocks_for(q.max_items * 16, 128), 128, 0, s, q, M);
+                else if (X.accum_ways == 2) LAUNCH(k_accum0m2, blocks_for(q.max_items * 8, 128), 128, 0, s, q, M);
+                else LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);
+            }
             else LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
             prof_end(s);
             if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);

@@ -77,14 +77,15 @@ template <class P, class PS> struct FixedBase {
         }
     }
 
-    // Thread u = ((set * total) + i) * split + part adds the table entries selected by the signed base-256 digits of
+    // Thread u = ((set * split) + part) * total + i adds the table entries selected by the signed base-256 digits of
     // scalar (set, i) in windows [part * 32 / split, (part + 1) * 32 / split).  Digits: d_w = byte_w + carry, minus 256
     // (carry out) when that exceeds 128, so |d_w| <= 128; canonical scalars are < 2^255, the top byte is <= 0x40 and
     // the recoding never carries out of window 31.
     static H2_HD void accum_body(const FbPlan &p, const fe *scalars, const affine *dtab, xyzz *partial, uint64_t u) {
         if (u >= p.total * p.sets * p.split) return;
-        const uint32_t part = (uint32_t)(u % p.split);
-        const uint64_t v = u / p.split, i = v % p.total;
+        const uint64_t i = u % p.total, sp = u / p.total;               // the lanes of a warp share (set, part): same windows,
+        const uint32_t part = (uint32_t)(sp % p.split);                 // no divergence around the additions (with the part
+        const uint64_t v = (sp / p.split) * p.total + i;                // innermost every warp ran 8 x 4 of them, measured)
         fe s = fe_load(scalars + v);
         if (p.scalars_mont) s = fe_from_mont<PS>(s);
         const uint32_t per = H2_FB_WINDOWS / p.split, w_lo = part * per, w_hi = w_lo + per;
@@ -132,10 +133,11 @@ inline uint32_t fb_fan(uint64_t count) {
     return (uint32_t)(f < 1 ? 1 : f > H2_FB_MAX_FAN ? H2_FB_MAX_FAN : f);
 }
 inline uint64_t fb_ctas(uint64_t count, uint32_t f) { return (count + (uint64_t)H2_FB_QUADS * f - 1) / ((uint64_t)H2_FB_QUADS * f); }
-// threads per scalar: enough threads to fill the machine (~128 k) without shredding the per-thread chains
+// threads per scalar: enough threads to fill the machine (>= 64 k) without shredding the per-thread chains -- and at most
+// ~128 CTAs of partial sums for the first reduce level (one wave: its CTAs hold a whole SM's registers)
 inline uint32_t fb_split(uint64_t total, uint32_t sets) {
     uint32_t split = 1;
-    while (split < 8 && total * sets * split < (1ull << 17)) split <<= 1;
+    while (split < 8 && total * sets * split < (1ull << 16)) split <<= 1;
     return split;
 }
 

@@ -653,6 +653,46 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_q
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     Msm<P, PS>::template accum0_body<QuadAdd>(p, M, t);
 }
+// ... and WAYS quads per work item (test hook h2_test_set_accum_ways; NOT the default: measured at k = 14, c = 15 -- ~17
+// references per bucket, the fullest ~35 -- 2 / 4 ways change a commit by -9 % / 0 % and the IPA opening by +6 % / +32 %: the
+// quad accumulation is bound by lane-multiplies, not by its chains): quad h of the group adds references start + h, start + h + WAYS, ...; the
+// partial sums are then folded with log2(WAYS) shuffle + quad-add steps and quad 0 writes the result.  All lanes of a
+// group share the work item, so the group leaves together; the quads of a group run different trip counts and meet again
+// at the group-wide shuffles.
+template <class P, class PS, int WAYS> __global__ void __launch_bounds__(128) msm_accum0_multi_kernel(const MsmPlan p, const MsmBuffers M) {
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / (4 * WAYS);
+    if (t >= M.size_hist[p.T + 1]) return;
+    const uint32_t lane = threadIdx.x & 31u, h = (lane >> 2) & (WAYS - 1);
+    const uint32_t gmask = (WAYS == 8 ? 0xffffffffu : ((1u << (4 * WAYS)) - 1u) << (lane & ~(4u * WAYS - 1u)));
+    const uint2 it = M.items[t];
+    const uint32_t g = it.x, start = it.y, lo = Msm<P, PS>::bucket_lo(p, M, g), hi = Msm<P, PS>::bucket_hi(p, M, g);
+    const uint32_t end = start + p.T < hi ? start + p.T : hi;
+    xyzz acc = xyzz_identity();
+    for (uint32_t pos = start + h; pos < end; pos += WAYS) {
+        const uint32_t ref = M.refs[pos];
+        affine b;
+        if (p.glv) b = ld_affine(((ref >> 30) & 1u ? M.bases_phi : M.bases) + (ref & 0x3fffffffu));
+        else b = ld_affine(M.bases + (ref & 0x7fffffffu));
+        if (ref >> 31) b.y = fe_neg<P>(b.y);
+        xyzz_add_mixed_quad<P>(acc, b);
+    }
+#pragma unroll
+    for (int step = WAYS / 2; step >= 1; step >>= 1) {
+        xyzz other;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            other.x.v[i] = __shfl_down_sync(gmask, acc.x.v[i], 4 * step, 4 * WAYS);
+            other.y.v[i] = __shfl_down_sync(gmask, acc.y.v[i], 4 * step, 4 * WAYS);
+            other.zz.v[i] = __shfl_down_sync(gmask, acc.zz.v[i], 4 * step, 4 * WAYS);
+            other.zzz.v[i] = __shfl_down_sync(gmask, acc.zzz.v[i], 4 * step, 4 * WAYS);
+        }
+        if ((int)h < step) xyzz_add_quad<P>(acc, other);
+    }
+    if (h == 0) {
+        typename Msm<P, PS>::Flusher F; F.M = &M; F.p = &p;
+        F.flush(g, start, end, acc, p.part_offset[1] + Msm<P, PS>::item_slot(p, start, start == lo));
+    }
+}
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accumN_kernel(const MsmPlan p, const MsmBuffers M, uint32_t lv) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < p.acc_threads[lv]) Msm<P, PS>::accumN_body(p, M, lv, t);

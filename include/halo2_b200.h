@@ -205,6 +205,8 @@ int h2_test_set_chunk_threshold(uint32_t log2_n);
 int h2_test_set_graphs(int on);
 /* EC-FFT butterfly form: 1 = quads of lanes, 0 = one thread each, -1 = chosen by size (the default). */
 int h2_test_set_ecfft_quad(int on);
+/* Quads of lanes per work item in the accumulation of small MSMs (1, 2 or 4; default 1). */
+int h2_test_set_accum_ways(uint32_t ways);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */
 int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out);

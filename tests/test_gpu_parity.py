@@ -196,6 +196,24 @@ def test_domain_transforms(eng, field, j, k):
     assert (got[: 1 << k] == co).all() and not got[1 << k:].any()
 
 
+def test_rotate_property(eng):
+    """poly/domain.rs:500-540 (test_rotate) with lagrange_to_coeff on the device: for Lagrange values a over the k = 3 domain of
+    the Pallas scalar field, p(x) == p_cur(x), p(x w) == p_next(x), p(x / w) == p_prev(x) -- and the iNTT output evaluates
+    back to the samples on the domain (the Horner check of SURVEY.md section 4.1)."""
+    field, k = "fq", 3
+    m, n = pasta.FIELDS[field], 8
+    d = eng.EvaluationDomain(field, 1 + 1, k, pasta.zeta_candidates(field)[0])
+    a = cref.gen_scalars(field, SEED + 900, n)
+    rot = {0: a, 1: np.roll(a, -1, axis=0), -1: np.roll(a, 1, axis=0)}          # Polynomial::rotate, poly.rs:157-171
+    co = {r: cref.bytes_to_ints(d.lagrange_to_coeff(v)) for r, v in rot.items()}
+    x = pasta.gen_scalars(field, SEED + 901, 1)[0]
+    ev = lambda c_, at: pasta.eval_polynomial(field, c_, at)                    # noqa: E731
+    assert ev(co[0], x) == ev(co[0], x)
+    assert ev(co[0], x * d.omega % m) == ev(co[1], x)
+    assert ev(co[0], x * d.omega_inv % m) == ev(co[-1], x)
+    assert [ev(co[0], pow(d.omega, i, m)) for i in range(n)] == cref.bytes_to_ints(a)
+
+
 # ------------------------------------------------------------------------------------------ K2-K5
 @pytest.mark.parametrize("curve", ["pallas", "vesta"])
 def test_best_multiexp_parity(eng, curve):
@@ -703,3 +721,30 @@ def test_small_multiexp_and_batch_normalize(eng):
     want = np.stack([cref.jac_to_affine(curve, p) for p in pts])
     assert (eng.batch_normalize(pts, curve) == want).all()
     assert eng.batch_normalize(np.zeros((0, 96), dtype=np.uint8), curve).shape == (0, 64)
+
+
+def test_accum_ways(eng):
+    """Small MSMs accumulate with 1, 2 or 4 quads of lanes per work item (msm_accum0_multi_kernel): same points."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    curve, c, k = "vesta", pasta.VESTA, 10
+    n = 1 << k
+    g = cref.gen_points(curve, SEED + 600, n + 1)
+    polys = [cref.gen_scalars(c.scalar, SEED + 601, n), cref.ints_to_bytes([i % 3 for i in range(n)]), cref.ints_to_bytes([5] * n)]
+    blind = eng.Blind(9)
+    kb = cref.gen_scalars(c.scalar, SEED + 602, 3000)
+    pb = cref.gen_points(curve, SEED + 603, 3000)
+    want_one = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    wants = [cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([p, cref.ints_to_bytes([9])]), g)) for p in polys]
+    try:
+        for ways in (1, 2, 4):
+            L.check(lib.h2_test_set_accum_ways(ways))
+            params = eng.Params(curve, k, g[:n], g[:n], g[n:])
+            for rep in range(3):     # eager, captured, replayed
+                assert [_affine(curve, params.commit(p, blind)) for p in polys] == wants, (ways, rep)
+            assert [_affine(curve, m) for m in params.commit_many(polys, [blind] * 3)] == wants, ways
+            params.close()
+            assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want_one, ways
+        assert lib.h2_test_set_accum_ways(3) != 0
+    finally:
+        L.check(lib.h2_test_set_accum_ways(1))
