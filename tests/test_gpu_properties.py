@@ -138,3 +138,28 @@ def test_ntt_full_size_round_trip_and_linearity(dev, field, log_n):
     fa2h = fa2[sel].cpu().numpy().view(np.uint8).reshape(len(idx), 32)
     for x, y, z in zip(fah, fdh, fa2h):
         assert (int.from_bytes(x.tobytes(), "little") + int.from_bytes(y.tobytes(), "little")) % m == int.from_bytes(z.tobytes(), "little")
+
+
+def test_ec_fft_round_trip_and_commit_2pow13():
+    """best_fft at G = curve point at k = 13 (4x the oracle-checked size; both butterfly forms: quads up to log n = 12, one
+    thread per butterfly above): the inverse transform with the 2^-k scaling brings the generators back, and the reference's
+    own property poly/commitment.rs:258-302 holds for the derived g_lagrange: commit_lagrange(a) == commit(lagrange_to_coeff(a))."""
+    import halo2_b200 as h2
+    curve, c = "vesta", pasta.VESTA
+    for k in (12, 13):
+        n, r = 1 << k, c.r
+        g = cref.gen_points(curve, SEED + 950 + k, n + 1)
+        w = pasta.omega_for_k(c.scalar, k)
+        jac = cref.affine_to_jacobian_bytes(g[:n])
+        fwd = h2.best_fft_curve(jac.copy(), w, k, curve)
+        from halo2_b200 import lib as L
+        L.check(L.init().h2_ec_fft(L.CURVE_ID[curve], L.ptr(fwd), L.ptr(L.fe_bytes(pasta.inv(w, r))), ctypes.c_uint32(k),
+                                   L.ptr(L.fe_bytes(pow(pasta.inv(2, r), k, r))), L.REPR_CANONICAL))
+        assert (h2.batch_normalize(fwd, curve) == g[:n]).all(), k
+        params = h2.Params.from_generators(curve, k, g[:n], g[n:])
+        dom = h2.EvaluationDomain(c.scalar, 2, k, pasta.zeta_candidates(c.scalar)[0])
+        a = cref.gen_scalars(c.scalar, SEED + 960 + k, n)
+        lhs = h2.batch_normalize(params.commit_lagrange(a, h2.Blind(3)).reshape(1, 96), curve)
+        rhs = h2.batch_normalize(params.commit(dom.lagrange_to_coeff(a), h2.Blind(3)).reshape(1, 96), curve)
+        assert (lhs == rhs).all() and lhs.any(), k
+        params.close()

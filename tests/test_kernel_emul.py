@@ -390,7 +390,7 @@ def test_emul_ec_fft_and_params_lagrange(emu, curve, k, quad):
 def test_emul_direct_fixed_base(emu, curve):
     c = pasta.CURVES[curve]
     r = c.r
-    n = 70
+    n = 36
     bases = cref.gen_points(curve, 700, n)
     bases[5] = 0                                                   # an identity generator
     bases[9] = bases[8]                                            # a repeated one (equal partial sums meet in the tree)
