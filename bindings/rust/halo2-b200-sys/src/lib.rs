@@ -60,6 +60,8 @@ extern "C" {
                                 out: *mut c_void, repr: c_int) -> c_int;
     pub fn h2_ec_fft(curve: c_int, points_xyz: *mut c_void, omega: *const c_void, log_n: u32, scale: *const c_void, repr: c_int) -> c_int;
     pub fn h2_batch_normalize(curve: c_int, points_xyz: *const c_void, n: usize, repr: c_int, out_xy: *mut c_void) -> c_int;
+    pub fn h2_points_compress(curve: c_int, points_xy: *const c_void, n: usize, repr: c_int, out_bytes: *mut c_void) -> c_int;
+    pub fn h2_points_decompress(curve: c_int, bytes: *const c_void, n: usize, repr: c_int, out_xy: *mut c_void) -> c_int;
     pub fn h2_params_lagrange(curve: c_int, g_xy: *const c_void, k: u32, omega_inv: *const c_void, minv: *const c_void, repr: c_int,
                               out_g_lagrange_xy: *mut c_void) -> c_int;
 }
@@ -219,6 +221,30 @@ where
                            minv.to_repr().as_ref().as_ptr() as *const c_void, REPR_CANONICAL, out.as_mut_ptr() as *mut c_void)
     });
     (0..g.len()).map(|i| affine_from_xy::<C>(&out[64 * i..64 * i + 64])).collect()
+}
+
+/// Bulk `C::from_bytes` for `Params::read` (poly/commitment.rs:183-205): `Err` where `C::read` would return `io::Error`.
+pub fn read_points<C: B200Curve>(bytes: &[u8]) -> std::io::Result<Vec<C>>
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    assert_eq!(bytes.len() % 32, 0);
+    let n = bytes.len() / 32;
+    let mut out = vec![0u8; 64 * n];
+    let rc = unsafe { h2_points_decompress(C::CURVE_ID, bytes.as_ptr() as *const c_void, n, REPR_CANONICAL, out.as_mut_ptr() as *mut c_void) };
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(h2_last_error()) }.to_string_lossy().into_owned();
+        return Err(std::io::Error::new(std::io::ErrorKind::Other, msg));
+    }
+    Ok((0..n).map(|i| affine_from_xy::<C>(&out[64 * i..64 * i + 64])).collect())
+}
+
+/// Bulk `C::to_bytes` for `Params::write` (poly/commitment.rs:168-181).
+pub fn write_points<C: B200Curve>(points: &[C]) -> Vec<u8> {
+    let b = bases_to_bytes(points);
+    let mut out = vec![0u8; 32 * points.len()];
+    check(unsafe { h2_points_compress(C::CURVE_ID, b.as_ptr() as *const c_void, points.len(), REPR_CANONICAL, out.as_mut_ptr() as *mut c_void) });
+    out
 }
 
 /// Resident generator set for `Params::{commit, commit_lagrange}` (poly/commitment.rs:119-150):

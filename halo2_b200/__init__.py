@@ -7,8 +7,8 @@ operation raises `H2Error` unless the library is built and a B200 is visible.
 """
 from .lib import H2Error, lib_path, load, init, launch_count  # noqa: F401
 from .arithmetic import best_multiexp, small_multiexp, best_fft, best_fft_curve, batch_normalize, multiexp_window_bits  # noqa: F401
-from .poly import Params, EvaluationDomain, Blind, ResidentPoly, lagrange_generators  # noqa: F401
+from .poly import Params, EvaluationDomain, Blind, ResidentPoly, lagrange_generators, compress_points, decompress_points  # noqa: F401
 
 __all__ = ["H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "small_multiexp", "best_fft",
            "best_fft_curve", "batch_normalize", "multiexp_window_bits", "Params", "EvaluationDomain", "Blind", "ResidentPoly",
-           "lagrange_generators"]
+           "lagrange_generators", "compress_points", "decompress_points"]

@@ -20,6 +20,7 @@
 #include "ntt.cuh"
 #include "ecfft.cuh"
 #include "fixedbase.cuh"
+#include "codec.cuh"
 
 using namespace h2;
 
@@ -1195,6 +1196,49 @@ extern "C" int h2_batch_normalize(int curve, const void *points_xyz, size_t n, i
     if (scratch_release(s)) return 1;
     CU(cudaStreamSynchronize(s));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point (de)compression (codec.cuh): C::to_bytes / C::from_bytes, the encoding of Params::{write, read} and of every
+// point in a proof transcript
+// ------------------------------------------------------------------------------------------------
+template <class P> static int points_codec(int decompress, const void *in, size_t n, int repr, void *out) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const int mont = repr == H2_REPR_MONTGOMERY;
+    if (scratch_acquire(s)) return 1;
+    if (X.ec_io.ensure(n * sizeof(affine)) || X.ec_out.ensure(n * sizeof(affine)) || X.misc.ensure(64)) return 1;
+    uint32_t bad = 0xffffffffu;
+    if (!decompress) {
+        CU(cudaMemcpyAsync(X.ec_io.p, in, n * sizeof(affine), cudaMemcpyHostToDevice, s));
+        LAUNCH(compress_kernel<P>, blocks_for(n, 128), 128, 0, s, X.ec_io.as<affine>(), mont, X.ec_out.as<fe>(), (uint64_t)n);
+        CU(cudaMemcpyAsync(out, X.ec_out.p, n * sizeof(fe), cudaMemcpyDeviceToHost, s));
+    } else {
+        static const SqrtConst K = make_sqrt_const<P>();
+        CU(cudaMemcpyAsync(X.ec_io.p, in, n * sizeof(fe), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(X.misc.p, &bad, 4, cudaMemcpyHostToDevice, s));
+        LAUNCH(decompress_kernel<P>, blocks_for(n, 128), 128, 0, s, X.ec_io.as<fe>(), X.ec_out.as<affine>(), mont, K, X.misc.as<uint32_t>(), (uint64_t)n);
+        CU(cudaMemcpyAsync(out, X.ec_out.p, n * sizeof(affine), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&bad, X.misc.p, 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    if (bad != 0xffffffffu) return fail("h2_points_decompress: invalid point encoding at index " + std::to_string(bad));
+    return 0;
+}
+static int points_codec_dispatch(int curve, int decompress, const void *in, size_t n, int repr, void *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    if (n >= (1ull << 32)) return fail("points codec: n >= 2^32");
+    if (n == 0) return 0;
+    return curve == H2_CURVE_PALLAS ? points_codec<FpParams>(decompress, in, n, repr, out) : points_codec<FqParams>(decompress, in, n, repr, out);
+}
+extern "C" int h2_points_compress(int curve, const void *points_xy, size_t n, int repr, void *out_bytes) {
+    return points_codec_dispatch(curve, 0, points_xy, n, repr, out_bytes);
+}
+extern "C" int h2_points_decompress(int curve, const void *bytes, size_t n, int repr, void *out_xy) {
+    return points_codec_dispatch(curve, 1, bytes, n, repr, out_xy);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -45,6 +45,23 @@ def lagrange_generators(curve: str, k: int, g) -> np.ndarray:
     return out
 
 
+def compress_points(points_xy, curve: str) -> np.ndarray:
+    """C::to_bytes for a batch (book/src/background/curves.md:203-225): (n, 64) affine -> (n, 32) uint8."""
+    p = _l.as_u8(points_xy, 64)
+    out = np.zeros((p.shape[0], 32), dtype=np.uint8)
+    _l.check(_l.init().h2_points_compress(_l.CURVE_ID[curve], _l.ptr(p), ctypes.c_size_t(p.shape[0]), _l.REPR_CANONICAL, _l.ptr(out)))
+    return out
+
+
+def decompress_points(data, curve: str) -> np.ndarray:
+    """C::from_bytes for a batch (curves.md:227-240): (n, 32) uint8 -> (n, 64) affine.  Raises H2Error on an invalid
+    encoding (the reference's C::read returns io::Error)."""
+    b = _l.as_u8(data, 32)
+    out = np.zeros((b.shape[0], 64), dtype=np.uint8)
+    _l.check(_l.init().h2_points_decompress(_l.CURVE_ID[curve], _l.ptr(b), ctypes.c_size_t(b.shape[0]), _l.REPR_CANONICAL, _l.ptr(out)))
+    return out
+
+
 class Params:
     """poly/commitment.rs:26-33.  g / g_lagrange / w are uploaded once and stay resident in HBM
     (they are immutable for the life of a Params); commit / commit_lagrange only ship the
@@ -95,6 +112,28 @@ class Params:
         gb = _l.as_u8(g, 64)
         assert gb.shape[0] == n
         return cls(curve, k, gb, lagrange_generators(curve, k, gb), w, u, **kw)
+
+    def write(self, writer) -> None:
+        """Params::write (commitment.rs:168-181): k as u32 LE, then g, g_lagrange, w, u as compressed points."""
+        if self.u is None:
+            raise _l.H2Error("Params.write needs u")
+        writer.write(int(self.k).to_bytes(4, "little"))
+        writer.write(compress_points(np.concatenate([self.g, self.g_lagrange, self.w, self.u]), self.curve).tobytes())
+
+    @classmethod
+    def read(cls, curve: str, reader, **kw) -> "Params":
+        """Params::read (commitment.rs:183-205).  A short file raises EOFError (read_exact), an invalid point H2Error."""
+        head = reader.read(4)
+        if len(head) != 4:
+            raise EOFError("failed to fill whole buffer")
+        k = int.from_bytes(head, "little")
+        assert k < 32
+        n = 1 << k
+        body = reader.read(32 * (2 * n + 2))
+        if len(body) != 32 * (2 * n + 2):
+            raise EOFError("failed to fill whole buffer")
+        pts = decompress_points(np.frombuffer(body, dtype=np.uint8).reshape(-1, 32), curve)
+        return cls(curve, k, pts[:n], pts[n:2 * n], pts[2 * n:2 * n + 1], pts[2 * n + 1:], **kw)
 
     def _commit(self, handle, poly, r: Blind) -> np.ndarray:
         p = _l.as_u8(poly, 32)

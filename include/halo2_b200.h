@@ -188,6 +188,16 @@ int h2_batch_normalize(int curve, const void *points_xyz, size_t n, int repr, vo
  * -> affine g_lagrange.  (hash_to_curve, :46-58, lives in the un-vendored pasta_curves: the generators are the caller's.) */
 int h2_params_lagrange(int curve, const void *g_xy, uint32_t k, const void *omega_inv, const void *minv, int repr, void *out_g_lagrange_xy);
 
+/* ---- point encoding: SURVEY.md section 8(f) row 4 (the wire format either side of the path) ----------------------- */
+/* C::to_bytes (book/src/background/curves.md:203-225): n affine points (64 B) -> n x 32 bytes, x little-endian with the LSB
+ * of y in the top bit of the last byte, identity = zeros.  What Params::write (poly/commitment.rs:168-181) and the
+ * transcript (transcript.rs: write_point) emit for every point. */
+int h2_points_compress(int curve, const void *points_xy, size_t n, int repr, void *out_bytes);
+/* C::from_bytes (curves.md:227-240): y = sqrt(x^3 + 5) with the encoded sign (Tonelli-Shanks on the device).  Fails -- like
+ * C::read's io::Error in Params::read, poly/commitment.rs:183-205 -- when an encoding is invalid (x not canonical, x = 0 with
+ * the sign bit set, x^3 + 5 not a square); h2_last_error() names the first bad index. */
+int h2_points_decompress(int curve, const void *bytes, size_t n, int repr, void *out_xy);
+
 /* ---- utilities for synthetic workloads and the tests ---------------------------------------- */
 /* d_out[i] = [s_i] * (-1, 2) for pseudo-random 64-bit s_i derived from seed (distinct points),
  * affine Montgomery coordinates; i in [first, first + n). */

@@ -13,6 +13,7 @@ What it restates (all file:line relative to /root/reference/halo2_proofs/src):
   * Params::new's EC-FFT      poly/commitment.rs:77-94   (generators are synthetic, see below)
   * EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff,
     distribute_powers_zeta, ifft}   poly/domain.rs:40-146, 227-255, 303-325, 357-383
+  * point compression and Params::{write, read}   book/src/background/curves.md:203-240, poly/commitment.rs:168-205
   * the IPA round loop       poly/commitment/prover.rs:100-142, :154-166 (transcript factored out: challenges
     and randomness are inputs, the points / scalar written to the transcript are outputs)
 
@@ -667,6 +668,83 @@ def affine_from_bytes(b: bytes) -> Affine:
 # the Fiat-Shamir challenges (xi, z, u_j) and the prover's randomness are INPUTS, the points
 # and scalars the prover would write to the transcript are OUTPUTS.  (The Blake2b transcript
 # itself, transcript.rs, is out of scope -- SURVEY.md section 2.)
+# --------------------------------------------------------------------------------------
+# Point compression (C::to_bytes / C::from_bytes; book/src/background/curves.md:203-240) and the
+# Params wire format built on it (poly/commitment.rs:168-205).  The encoding is the x coordinate, 32 bytes
+# little-endian, with the LSB of y in the top bit of the last byte; the identity is 32 zero bytes.
+# --------------------------------------------------------------------------------------
+def fe_sqrt(field: str, a: int) -> Optional[int]:
+    """A square root of a in the field, or None.  Tonelli-Shanks over the 2^32-order subgroup generated by ROOT_OF_UNITY
+    (book/src/background/fields.md: both fields have 2-adicity 32); which of the two roots comes back is irrelevant to the
+    callers, who fix the sign afterwards."""
+    m = FIELDS[field]
+    a %= m
+    if a == 0:
+        return 0
+    t = (m - 1) >> S_2ADICITY
+    w = pow(a, (t - 1) // 2, m)
+    x = a * w % m            # a^((t+1)/2)
+    b = x * w % m            # a^t
+    z = root_of_unity(field)
+    v = S_2ADICITY
+    while b != 1:
+        k, b2 = 0, b
+        while b2 != 1:
+            b2 = b2 * b2 % m
+            k += 1
+            if k == v:
+                return None  # a is not a square
+        zz = z
+        for _ in range(v - k - 1):
+            zz = zz * zz % m
+        x = x * zz % m
+        z = zz * zz % m
+        b = b * z % m
+        v = k
+    assert x * x % m == a
+    return x
+
+
+def compress(pt: Affine) -> bytes:
+    """C::to_bytes (curves.md:203-225)."""
+    if pt is None:
+        return b"\0" * 32
+    return (pt[0] | ((pt[1] & 1) << 255)).to_bytes(32, "little")
+
+
+def decompress(c: Curve, b: bytes) -> Affine:
+    """C::from_bytes (curves.md:227-240).  Raises ValueError on an invalid encoding (C::read returns io::Error)."""
+    v = int.from_bytes(b, "little")
+    ysign, x = v >> 255, v & ((1 << 255) - 1)
+    if x == 0:
+        if ysign:
+            raise ValueError("invalid point encoding: x = 0 with the sign bit set")
+        return None
+    if x >= c.p:
+        raise ValueError("invalid point encoding: x is not a canonical field element")
+    y = fe_sqrt(c.base, (x * x % c.p * x + 5) % c.p)
+    if y is None:
+        raise ValueError("invalid point encoding: x^3 + 5 is not a square")
+    if (y & 1) != ysign:
+        y = c.p - y
+    return (x, y)
+
+
+def params_to_bytes(k: int, g: Sequence[Affine], g_lagrange: Sequence[Affine], w: Affine, u: Affine) -> bytes:
+    """Params::write (poly/commitment.rs:168-181)."""
+    return k.to_bytes(4, "little") + b"".join(compress(p) for p in list(g) + list(g_lagrange) + [w, u])
+
+
+def params_from_bytes(c: Curve, data: bytes):
+    """Params::read (poly/commitment.rs:183-205) -> (k, g, g_lagrange, w, u)."""
+    k = int.from_bytes(data[:4], "little")
+    n = 1 << k
+    if len(data) < 4 + 32 * (2 * n + 2):
+        raise ValueError("unexpected end of file")       # read_exact
+    pts = [decompress(c, data[4 + 32 * i:4 + 32 * (i + 1)]) for i in range(2 * n + 2)]
+    return k, pts[:n], pts[n:2 * n], pts[2 * n], pts[2 * n + 1]
+
+
 # --------------------------------------------------------------------------------------
 def compute_inner_product(m: int, a: Sequence[int], b: Sequence[int]) -> int:
     """arithmetic.rs:308-319."""

@@ -748,3 +748,51 @@ def test_accum_ways(eng):
         assert lib.h2_test_set_accum_ways(3) != 0
     finally:
         L.check(lib.h2_test_set_accum_ways(1))
+
+
+# ------------------------------------------------------------------------------------------ K13
+def test_point_codec_and_params_io(eng, goldens):
+    """C::to_bytes / C::from_bytes on the device (book/src/background/curves.md:203-240) against the oracle and the
+    reference's golden commitments; Params::{write, read} (poly/commitment.rs:168-205) byte-for-byte and round trip; invalid
+    encodings and short files fail like C::read / read_exact."""
+    import io
+    from halo2_b200 import lib as L
+    for curve in ("pallas", "vesta"):
+        c = pasta.CURVES[curve]
+        pts = [cref.bytes_to_affine(p) for p in cref.gen_points(curve, SEED + 700, 300)] + [None, pasta.generator(c)]
+        if curve == "vesta":
+            for vk in (goldens["vk_plonk_api_k5"], goldens["vk_lookup_range_check_k11"]):
+                pts += [(int(x, 16), int(y, 16)) for x, y in vk["fixed_commitments"] + vk["permutation_commitments"]]
+        xy = cref.affines_to_bytes(pts)
+        enc = eng.compress_points(xy, curve)
+        assert enc.tobytes() == b"".join(pasta.compress(p) for p in pts)
+        assert (eng.decompress_points(enc, curve) == xy).all()
+        flipped = enc.copy()
+        flipped[:300, 31] ^= 0x80
+        assert [cref.bytes_to_affine(b) for b in eng.decompress_points(flipped[:300], curve)] == [(p[0], c.p - p[1]) for p in pts[:300]]
+        nonres = next(x for x in range(2, 200) if pasta.fe_sqrt(c.base, (x ** 3 + 5) % c.p) is None)
+        for bad_val in (nonres, c.p, (1 << 255) - 1, 1 << 255):
+            batch = enc[:9].copy()
+            batch[7] = np.frombuffer(bad_val.to_bytes(32, "little"), dtype=np.uint8)
+            with pytest.raises(L.H2Error, match="index 7"):
+                eng.decompress_points(batch, curve)
+        assert eng.compress_points(np.zeros((0, 64), dtype=np.uint8), curve).shape == (0, 32)
+    curve, c, k = "vesta", pasta.VESTA, 5
+    po = pasta.Params(c, k)
+    params = eng.Params(curve, k, cref.affines_to_bytes(po.g), cref.affines_to_bytes(po.g_lagrange), cref.affines_to_bytes([po.w]),
+                        u=cref.affines_to_bytes([po.u]))
+    buf = io.BytesIO()
+    params.write(buf)
+    assert buf.getvalue() == pasta.params_to_bytes(k, po.g, po.g_lagrange, po.w, po.u)
+    back = eng.Params.read(curve, io.BytesIO(buf.getvalue()))
+    assert back.k == k and (back.g == params.g).all() and (back.g_lagrange == params.g_lagrange).all() and (back.w == params.w).all() and (back.u == params.u).all()
+    a = cref.gen_scalars(c.scalar, SEED + 710, 1 << k)
+    assert _affine(curve, back.commit_lagrange(a, eng.Blind(4))) == pasta.to_affine(c, po.commit_lagrange(cref.bytes_to_ints(a), 4))
+    with pytest.raises(EOFError):
+        eng.Params.read(curve, io.BytesIO(buf.getvalue()[:-1]))
+    corrupt = bytearray(buf.getvalue())
+    corrupt[4 + 32 * 3: 4 + 32 * 4] = (c.p).to_bytes(32, "little")
+    with pytest.raises(L.H2Error):
+        eng.Params.read(curve, io.BytesIO(bytes(corrupt)))
+    params.close()
+    back.close()

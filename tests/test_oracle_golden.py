@@ -77,3 +77,31 @@ def test_generator_order():
         assert pasta.to_affine(c, pasta.scalar_mul(c, c.r - 1, g)) == (g[0], c.p - g[1])
         gb = cref.affines_to_bytes([g])[0]
         assert cref.bytes_to_affine(cref.scalar_mul(c.name, c.r - 1, gb)) == (g[0], c.p - g[1])
+
+
+def test_point_compression_on_golden_commitments(goldens):
+    """C::to_bytes / C::from_bytes as specified in book/src/background/curves.md:203-240, on the reference's golden
+    commitments (tests/plonk_api.rs:958-982, circuit_data/vk_lookup_range_check.rdata): decompressing the encoding of (x, y)
+    must find exactly the golden y -- pins the square root and the sign rule of the oracle; the device path is checked against
+    the oracle (tests/test_kernel_emul.py::test_emul_point_codec, tests/test_gpu_parity.py::test_point_codec_and_params_io)."""
+    c = pasta.VESTA
+    n = 0
+    for vk in (goldens["vk_plonk_api_k5"], goldens["vk_lookup_range_check_k11"]):
+        for x, y in vk["fixed_commitments"] + vk["permutation_commitments"]:
+            x, y = int(x, 16), int(y, 16)
+            enc = pasta.compress((x, y))
+            assert len(enc) == 32 and enc[31] >> 7 == (y & 1)
+            assert pasta.decompress(c, enc) == (x, y)
+            flipped = bytearray(enc)
+            flipped[31] ^= 0x80
+            assert pasta.decompress(c, bytes(flipped)) == (x, c.p - y)
+            n += 1
+    assert n == 26
+    assert pasta.compress(None) == b"\0" * 32 and pasta.decompress(c, b"\0" * 32) is None
+    # Params::{write, read} (poly/commitment.rs:168-205) round trip on a tiny synthetic parameter set
+    po = pasta.Params(c, 2)
+    data = pasta.params_to_bytes(po.k, po.g, po.g_lagrange, po.w, po.u)
+    assert len(data) == 4 + 32 * (2 * 4 + 2) and data[:4] == (2).to_bytes(4, "little")
+    assert pasta.params_from_bytes(c, data) == (2, po.g, po.g_lagrange, po.w, po.u)
+    with pytest.raises(ValueError):
+        pasta.params_from_bytes(c, data[:-1])
