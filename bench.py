@@ -246,6 +246,36 @@ def params_lagrange_ms(h2, cref, threads, reps=3):
     return res
 
 
+def poly_reductions_ms(h2, cref, reps=5):
+    """The prover's coefficient-form reductions at k=14 on resident polynomials -- 16 eval_polynomial (one batch, own points) and
+    4 kate_division (arithmetic.rs:297-341; serial loops in the reference, hence 1 core) -- next to the C restatement."""
+    import numpy as np
+    n = 1 << PROVER_K
+    polys = [cref.gen_scalars("fp", SEED + 90 + i, n) for i in range(16)]
+    pts = cref.bytes_to_ints(cref.gen_scalars("fp", SEED + 89, 16))
+    res = [h2.ResidentPoly("fp", n, p) for p in polys]
+    quot = [h2.ResidentPoly("fp", n - 1) for _ in range(4)]
+    out = {}
+    for name, fn in (("eval_x16", lambda: h2.eval_polynomial_resident(res, pts)),
+                     ("kate_division_x4", lambda: (h2.kate_division_resident(res[:4], pts[:4], dst=quot), quot[3].download(1)))):
+        fn()
+        t0 = time.time()
+        for _ in range(reps):
+            got = fn()
+        out[name] = {"gpu_ms": (time.time() - t0) / reps * 1e3}
+    t0 = time.time()
+    want = [cref.eval_polynomial("fp", p, x) for p, x in zip(polys, pts)]
+    out["eval_x16"]["cpu_baseline"] = {"ms": (time.time() - t0) * 1e3, "cores": 1, "kind": "port"}
+    out["eval_x16"]["same_result"] = h2.eval_polynomial_resident(res, pts) == want
+    t0 = time.time()
+    wq = [cref.kate_division("fp", p, x) for p, x in zip(polys[:4], pts[:4])]
+    out["kate_division_x4"]["cpu_baseline"] = {"ms": (time.time() - t0) * 1e3, "cores": 1, "kind": "port"}
+    out["kate_division_x4"]["same_result"] = bool(all((q.download(n - 1) == w).all() for q, w in zip(quot, wq)))
+    for r in res + quot:
+        r.close()
+    return out
+
+
 def resident_column_ms(h2, cref, reps=5):
     """One advice column's trip through the hot path at k=14 -- commit_lagrange, lagrange_to_coeff, commit,
     coeff_to_extended, extended values back to the host -- with host buffers per call vs device-resident handles."""
@@ -588,6 +618,7 @@ def main():
                 kinds[kind] = kinds.get(kind, 0) + (cnt if kind.endswith("_many") else 1)
             extra["resident_column_k14"] = resident_column_ms(h2, cref)
             extra["params_lagrange_k14"] = params_lagrange_ms(h2, cref, threads)
+            extra["poly_reductions_k14"] = poly_reductions_ms(h2, cref)
             extra["create_proof_k14_replay"] = {
                 "metric": "hot_path_ms_per_proof", "value": gdt * 1e3, "unit": "ms", "higher_is_better": False,
                 "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": cpu_by_kind,

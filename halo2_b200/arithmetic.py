@@ -86,3 +86,49 @@ def batch_normalize(points_xyz, curve: str = "vesta", repr: int = _l.REPR_CANONI
     out = np.zeros((p.shape[0], 64), dtype=np.uint8)
     _l.check(lib.h2_batch_normalize(_l.CURVE_ID[curve], _l.ptr(p), ctypes.c_size_t(p.shape[0]), int(repr), _l.ptr(out)))
     return out
+
+
+def eval_polynomial(poly, point: int, field: str = "fp") -> int:
+    """arithmetic.rs:297-303 on a host coefficient vector ((n, 32) uint8 canonical): sum_i poly[i] * point^i."""
+    from .poly import ResidentPoly, eval_polynomial_resident
+    p = _l.as_u8(poly, 32)
+    if p.shape[0] == 0:
+        return 0
+    r = ResidentPoly(field, p.shape[0], p)
+    try:
+        return eval_polynomial_resident([r], [point])[0]
+    finally:
+        r.close()
+
+
+def compute_inner_product(a, b, field: str = "fp") -> int:
+    """arithmetic.rs:308-319; panics (AssertionError) when the lengths differ, like assert_eq! at :311."""
+    from .poly import ResidentPoly, inner_product_resident
+    x, y = _l.as_u8(a, 32), _l.as_u8(b, 32)
+    assert x.shape[0] == y.shape[0], "compute_inner_product: a.len() != b.len()"
+    if x.shape[0] == 0:
+        return 0
+    rx, ry = ResidentPoly(field, x.shape[0], x), ResidentPoly(field, y.shape[0], y)
+    try:
+        return inner_product_resident([rx], [ry])[0]
+    finally:
+        rx.close()
+        ry.close()
+
+
+def kate_division(a, b: int, field: str = "fp") -> np.ndarray:
+    """arithmetic.rs:322-341: the quotient of a(X) by (X - b) as an (n - 1, 32) uint8 array."""
+    from .poly import ResidentPoly, kate_division_resident
+    x = _l.as_u8(a, 32)
+    assert x.shape[0] >= 1, "kate_division: empty polynomial"
+    if x.shape[0] == 1:
+        return np.zeros((0, 32), dtype=np.uint8)
+    r = ResidentPoly(field, x.shape[0], x)
+    try:
+        q = kate_division_resident([r], [b])[0]
+        try:
+            return q.download(x.shape[0] - 1)
+        finally:
+            q.close()
+    finally:
+        r.close()

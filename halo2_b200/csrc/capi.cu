@@ -21,6 +21,7 @@
 #include "ecfft.cuh"
 #include "fixedbase.cuh"
 #include "codec.cuh"
+#include "polyops.cuh"
 
 using namespace h2;
 
@@ -98,6 +99,7 @@ struct Context {
     // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms
     DevBuf ec_work, ec_io, ec_out;
     DevBuf fb_a, fb_b;                       // partial sums of the direct-sum fixed-base MSM (ping-pong)
+    DevBuf po_lvl, po_q, po_pts, po_ptrs;    // polyops.cuh: level arrays, kate carries, per-level points, pointer arrays
     std::vector<TwiddleEntry *> twiddles;
     uint64_t tw_stamp = 0;
     std::map<uint64_t, BaseSet *> bases;
@@ -193,7 +195,7 @@ extern "C" int h2_shutdown(void) {
     DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.bases_phi, &g_ctx.glv_parts, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
                      &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
                      &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
-                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out, &g_ctx.fb_a, &g_ctx.fb_b};
+                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out, &g_ctx.fb_a, &g_ctx.fb_b, &g_ctx.po_lvl, &g_ctx.po_q, &g_ctx.po_pts, &g_ctx.po_ptrs};
     for (DevBuf *b : all) b->release();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
@@ -1246,6 +1248,114 @@ extern "C" int h2_points_decompress(int curve, const void *bytes, size_t n, int 
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // IPA round loop (ipa.cuh): poly/commitment/prover.rs:100-142 with resident generators
+// ------------------------------------------------------------------------------------------------
+// eval_polynomial / compute_inner_product / kate_division on resident polynomials (polyops.cuh)
+// ------------------------------------------------------------------------------------------------
+// mode 0: eval (points: batch x 32 host), 1: inner product of a[i] and c[i], 2: kate division of a[i] by (X - point_i) into c[i]
+static PolyBuf *find_poly(uint64_t h);
+template <class P>
+static int polyops_run(int mode, const std::vector<PolyBuf *> &a, const std::vector<PolyBuf *> &c, size_t n, const void *points, int repr, void *out) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const uint32_t batch = (uint32_t)a.size();
+    // level sizes: m[0] = n, m[l + 1] = ceil(m[l] / CHUNK), down to 1
+    std::vector<uint64_t> m{(uint64_t)n}, off{0};
+    while (m.back() > 1) { off.push_back(off.back() + (m.size() > 1 ? m.back() * batch : 0)); m.push_back((m.back() + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK); }
+    if (mode == 1 && m.size() == 1) { off.push_back(0); m.push_back(1); }   // a length-1 inner product still needs its product level
+    const size_t L = m.size() - 1;                               // levels above the polynomial itself
+    const uint64_t lvl_total = off.back() + m.back() * batch + batch;
+    if (scratch_acquire(s)) return 1;
+    if (X.po_lvl.ensure(lvl_total * sizeof(fe)) || X.po_q.ensure(lvl_total * sizeof(fe)) || X.po_pts.ensure((L + 2) * batch * sizeof(fe)) ||
+        X.po_ptrs.ensure(2 * batch * sizeof(void *)) || X.misc.ensure(batch * sizeof(fe) + 64))
+        return 1;
+    fe *lvl = X.po_lvl.as<fe>(), *qarr = X.po_q.as<fe>(), *pts = X.po_pts.as<fe>();
+    auto level = [&](size_t l) { return lvl + off[l]; };         // values of level l >= 1: [batch][m[l]]
+    auto qlevel = [&](size_t l) { return qarr + off[l]; };
+    std::vector<const fe *> hp(2 * batch);
+    for (uint32_t b = 0; b < batch; b++) { hp[b] = a[b]->buf.as<fe>(); hp[batch + b] = c.empty() ? nullptr : c[b]->buf.as<fe>(); }
+    CU(cudaMemcpyAsync(X.po_ptrs.p, hp.data(), 2 * batch * sizeof(void *), cudaMemcpyHostToDevice, s));
+    const fe *const *d_a = X.po_ptrs.as<const fe *>();
+    const fe *const *d_c = d_a + batch;
+    // points of level 0 (Montgomery): the caller's, or 1 for the plain sums of the inner product
+    if (mode == 1) {
+        LAUNCH(fe_fill_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts, batch, fe_one<P>());
+    } else {
+        CU(cudaMemcpyAsync(pts, points, batch * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts, (uint64_t)batch, 1);
+    }
+    // upward pass: level l + 1 from level l at the point x^(CHUNK^l)
+    for (size_t l = 0; l < L; l++) {
+        const dim3 grid(blocks_for(m[l + 1], 128), batch);
+        if (l == 0 && mode == 1) LAUNCH(poly_inner_level0_kernel<P>, grid, 128, 0, s, d_a, d_c, m[0], level(1), m[1]);
+        else LAUNCH(poly_eval_level_kernel<P>, grid, 128, 0, s, l == 0 ? d_a : (const fe *const *)nullptr, l == 0 ? (const fe *)nullptr : (const fe *)level(l),
+                    m[l], (const fe *)(pts + l * batch), level(l + 1), m[l + 1]);
+        if (mode != 1) LAUNCH(poly_pow_chunk_kernel<P>, blocks_for(batch, 64), 64, 0, s, (const fe *)(pts + l * batch), pts + (l + 1) * batch, batch);
+        else if (l == 0) LAUNCH(fe_fill_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts + batch, batch, fe_one<P>());
+        if (mode == 1 && l >= 1) CU(cudaMemcpyAsync(pts + (l + 1) * batch, pts, batch * sizeof(fe), cudaMemcpyDeviceToDevice, s));
+    }
+    if (mode != 2) {   // the single value of the top level is the result (n == 1: the coefficient itself; n == 0 handled by the caller)
+        fe *res = X.misc.as<fe>();
+        if (L == 0) {
+            for (uint32_t b = 0; b < batch; b++) CU(cudaMemcpyAsync(res + b, hp[b], sizeof(fe), cudaMemcpyDeviceToDevice, s));
+        } else {
+            CU(cudaMemcpyAsync(res, level(L), batch * sizeof(fe), cudaMemcpyDeviceToDevice, s));   // m[L] == 1: [batch][1]
+        }
+        if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(batch, 64), 64, 0, s, res, (uint64_t)batch, 0);
+        CU(cudaMemcpyAsync(out, res, batch * sizeof(fe), cudaMemcpyDeviceToHost, s));
+        if (scratch_release(s)) return 1;
+        CU(cudaStreamSynchronize(s));
+        return 0;
+    }
+    // kate division, downward pass: Q at every position of level l from the carries of level l + 1.  The top level with
+    // more than one value (m[L] == 1 always; start from the highest level that has something to walk) needs no carry.
+    fe *const *d_q = (fe *const *)d_c;
+    for (size_t l = L; l-- > 0;) {
+        const dim3 grid(blocks_for(m[l + 1], 128), batch);
+        const fe *carry = (l + 1 < L) ? (const fe *)qlevel(l + 1) : (const fe *)nullptr;   // Q of level l + 1; the top level's Q(1..) are zero
+        LAUNCH(poly_kate_down_kernel<P>, grid, 128, 0, s, l == 0 ? d_a : (const fe *const *)nullptr, l == 0 ? (const fe *)nullptr : (const fe *)level(l), m[l],
+               (const fe *)(pts + l * batch), carry, m[l + 1], l == 0 ? (fe *)nullptr : qlevel(l), l == 0 ? d_q : (fe *const *)nullptr);
+    }
+    return scratch_release(s);
+}
+static int polyops_dispatch(int mode, const uint64_t *ah, const uint64_t *ch, size_t batch, size_t n, const void *points, int repr, void *out,
+                            const char *who) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (batch == 0) return 0;
+    if (batch > 256) return fail(std::string(who) + ": batch > 256");
+    if (n >= (1ull << 32)) return fail(std::string(who) + ": n >= 2^32");
+    std::vector<PolyBuf *> a(batch), c;
+    if (ch) c.resize(batch);
+    for (size_t b = 0; b < batch; b++) {
+        a[b] = find_poly(ah[b]);
+        if (!a[b]) return fail(std::string(who) + ": unknown polynomial handle");
+        if (a[b]->field != a[0]->field) return fail(std::string(who) + ": the polynomials live in different fields");
+        if (a[b]->len < n) return fail(std::string(who) + ": a polynomial holds fewer than n coefficients");
+        if (ch) {
+            c[b] = find_poly(ch[b]);
+            if (!c[b]) return fail(std::string(who) + ": unknown polynomial handle");
+            if (c[b]->field != a[0]->field) return fail(std::string(who) + ": the polynomials live in different fields");
+            if (c[b]->len + (mode == 2 ? 1 : 0) < n) return fail(std::string(who) + ": the second polynomial is too short");
+            if (mode == 2 && c[b] == a[b]) return fail(std::string(who) + ": the quotient cannot overwrite its dividend");
+        }
+    }
+    if (a[0]->field == H2_FIELD_FP) return polyops_run<FpParams>(mode, a, c, n, points, repr, out);
+    return polyops_run<FqParams>(mode, a, c, n, points, repr, out);
+}
+extern "C" int h2_poly_eval(const uint64_t *polys, size_t batch, size_t n, const void *points, int repr, void *out) {
+    if (n == 0) { memset(out, 0, batch * 32); return 0; }            // the empty sum (fold over nothing, arithmetic.rs:300-302)
+    return polyops_dispatch(0, polys, nullptr, batch, n, points, repr, out, "h2_poly_eval");
+}
+extern "C" int h2_poly_inner_product(const uint64_t *a, const uint64_t *b, size_t batch, size_t n, int repr, void *out) {
+    if (n == 0) { memset(out, 0, batch * 32); return 0; }
+    return polyops_dispatch(1, a, b, batch, n, nullptr, repr, out, "h2_poly_inner_product");
+}
+extern "C" int h2_poly_kate_division(const uint64_t *dst, const uint64_t *src, size_t batch, size_t n, const void *points, int repr) {
+    if (n == 0) return fail("h2_poly_kate_division: empty polynomial (the reference underflows a.len() - 1, arithmetic.rs:329)");
+    if (n == 1) return 0;                                             // quotient of a constant: no coefficients
+    return polyops_dispatch(2, src, dst, batch, n, points, repr, nullptr, "h2_poly_kate_division");
+}
+
 // ------------------------------------------------------------------------------------------------
 static void ipa_free(IpaSession *q) {   // back to the pool (the caller has synchronised the stream)
     if (g_ctx.ipa_pool.size() < 2) { g_ctx.ipa_pool.push_back(q); return; }

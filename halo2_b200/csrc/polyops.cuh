@@ -1,0 +1,94 @@
+// K14: the prover's coefficient-form reductions on resident polynomials -- SURVEY.md section 8(f) row 3.
+//
+//   eval_polynomial        /root/reference/halo2_proofs/src/arithmetic.rs:297-303   sum_i a_i x^i (Horner in the reference)
+//   compute_inner_product  arithmetic.rs:308-319                                     sum_i a_i b_i
+//   kate_division          arithmetic.rs:322-341                                     q = (a - a(b)) / (X - b):  q_i = sum_{j>i} a_j b^(j-i-1)
+//
+// The reference runs all three serially ("TODO: parallelize?"); each is a first-order linear recurrence, so each becomes a
+// tree of CHUNK-sized serial pieces: level l turns m values into ceil(m / CHUNK) by CHUNK multiply-adds per thread with the
+// point raised to CHUNK^l.  k = 14: 16384 -> 512 -> 16 -> 1, three launches of 32 dependent multiplies instead of 16384.
+// Exact field arithmetic: the result is THE field element the reference computes, whatever the association order.
+//
+// Layout: `batch` polynomials of `n` coefficients (Montgomery form, device pointers in an array -- the buffers of h2_poly_*
+// handles), one point per polynomial; partial levels live in one scratch array [batch][m].
+#pragma once
+#include "field.cuh"
+
+namespace h2 {
+
+#define H2_POLY_CHUNK 32
+
+template <class P> struct PolyOps {
+    // level of eval_polynomial: out[b][t] = sum_{i < CHUNK} in_b[t CHUNK + i] x_b^i   (Horner from the top of the chunk)
+    // in_ptrs != nullptr: level 0 reads polynomial b from in_ptrs[b]; else from in_flat + b * m
+    static H2_HD void eval_level_body(const fe *const *in_ptrs, const fe *in_flat, uint64_t m, const fe *points, fe *out, uint64_t out_m, uint32_t b,
+                                      uint64_t t) {
+        if (t >= out_m) return;
+        const fe *src = in_ptrs ? in_ptrs[b] : in_flat + (uint64_t)b * m;
+        const fe x = fe_load(points + b);
+        const uint64_t lo = t * H2_POLY_CHUNK, hi = lo + H2_POLY_CHUNK < m ? lo + H2_POLY_CHUNK : m;
+        fe acc = fe_zero();
+        for (uint64_t i = hi; i-- > lo;) acc = fe_add<P>(fe_mul<P>(acc, x), fe_load(src + i));
+        fe_store(out + (uint64_t)b * out_m + t, acc);
+    }
+    // points_out[b] = points_in[b]^CHUNK (CHUNK = 2^5)
+    static H2_HD void pow_chunk_body(const fe *in, fe *out, uint32_t b) {
+        fe x = fe_load(in + b);
+        for (uint32_t c = H2_POLY_CHUNK; c > 1; c >>= 1) x = fe_sqr<P>(x);
+        fe_store(out + b, x);
+    }
+    // level 0 of compute_inner_product: out[b][t] = sum_{i in chunk t} a_b[i] * c_b[i]; the upper levels are eval levels at x = 1
+    static H2_HD void inner_level0_body(const fe *const *a_ptrs, const fe *const *c_ptrs, uint64_t m, fe *out, uint64_t out_m, uint32_t b, uint64_t t) {
+        if (t >= out_m) return;
+        const fe *a = a_ptrs[b], *c = c_ptrs[b];
+        const uint64_t lo = t * H2_POLY_CHUNK, hi = lo + H2_POLY_CHUNK < m ? lo + H2_POLY_CHUNK : m;
+        fe acc = fe_zero();
+        for (uint64_t i = lo; i < hi; i++) acc = fe_add<P>(acc, fe_mul<P>(fe_load(a + i), fe_load(c + i)));
+        fe_store(out + (uint64_t)b * out_m + t, acc);
+    }
+    // kate_division, downward pass of one level.  With Q(i) = sum_{j >= i} a_j x^(j-i) (so q_i = Q(i + 1)) a chunk [lo, hi)
+    // satisfies Q(lo) = V + x^len Q(hi), V = the chunk's eval-level value: the upward pass IS the eval tree.  Going down,
+    // thread t of a level takes the carry Q(hi) from the level above (carry_in[b][t + 1], zero past the end) and walks its chunk
+    // from the top, writing Q at every position of the level below (or, at level 0, q_i = Q(i + 1) into the quotient).
+    //   vals: the level's own values [b][m] (level 0: the polynomial, via in_ptrs);  carry_in: Q at the chunk boundaries of this
+    //   level = the level above's Q array [b][out_m] (nullptr at the top level: no carry);  q_out: level 0 only.
+    static H2_HD void kate_down_body(const fe *const *in_ptrs, const fe *in_flat, uint64_t m, const fe *points, const fe *carry_in, uint64_t out_m,
+                                     fe *q_below, fe *const *q_out_ptrs, uint32_t b, uint64_t t) {
+        if (t >= out_m) return;
+        const fe *src = in_ptrs ? in_ptrs[b] : in_flat + (uint64_t)b * m;
+        const fe x = fe_load(points + b);
+        const uint64_t lo = t * H2_POLY_CHUNK, hi = lo + H2_POLY_CHUNK < m ? lo + H2_POLY_CHUNK : m;
+        fe acc = (carry_in && t + 1 < out_m) ? fe_load(carry_in + (uint64_t)b * out_m + t + 1) : fe_zero();   // Q(hi)
+        for (uint64_t i = hi; i-- > lo;) {
+            acc = fe_add<P>(fe_mul<P>(acc, x), fe_load(src + i));      // Q(i)
+            if (q_out_ptrs) { if (i >= 1) fe_store(q_out_ptrs[b] + (i - 1), acc); }   // q_(i-1) = Q(i); Q(0) = a(x) is dropped
+            else fe_store(q_below + (uint64_t)b * m + i, acc);
+        }
+    }
+};
+
+#if defined(__CUDACC__)
+template <class P> __global__ void __launch_bounds__(128) poly_eval_level_kernel(const fe *const *in_ptrs, const fe *in_flat, uint64_t m, const fe *points,
+                                                                                 fe *out, uint64_t out_m) {
+    PolyOps<P>::eval_level_body(in_ptrs, in_flat, m, points, out, out_m, blockIdx.y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <class P> __global__ void poly_pow_chunk_kernel(const fe *in, fe *out, uint32_t batch) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) PolyOps<P>::pow_chunk_body(in, out, b);
+}
+template <class P> __global__ void __launch_bounds__(128) poly_inner_level0_kernel(const fe *const *a_ptrs, const fe *const *c_ptrs, uint64_t m, fe *out,
+                                                                                   uint64_t out_m) {
+    PolyOps<P>::inner_level0_body(a_ptrs, c_ptrs, m, out, out_m, blockIdx.y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <class P> __global__ void __launch_bounds__(128) poly_kate_down_kernel(const fe *const *in_ptrs, const fe *in_flat, uint64_t m, const fe *points,
+                                                                                const fe *carry_in, uint64_t out_m, fe *q_below, fe *const *q_out_ptrs) {
+    PolyOps<P>::kate_down_body(in_ptrs, in_flat, m, points, carry_in, out_m, q_below, q_out_ptrs, blockIdx.y,
+                               (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <class P> __global__ void fe_fill_kernel(fe *a, uint32_t n, fe v) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fe_store(a + i, v);
+}
+#endif
+
+}  // namespace h2

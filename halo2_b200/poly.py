@@ -277,6 +277,48 @@ class ResidentPoly:
             pass
 
 
+def _handles(polys: Sequence["ResidentPoly"]):
+    return (ctypes.c_uint64 * len(polys))(*[p._h.value for p in polys])
+
+
+def eval_polynomial_resident(polys: Sequence["ResidentPoly"], points: Sequence[int], n: Optional[int] = None) -> list:
+    """[eval_polynomial(p, x)] (arithmetic.rs:297-303) for device-resident coefficient vectors, one launch tree for the batch."""
+    batch = len(polys)
+    assert batch == len(points) and batch >= 1
+    n = polys[0].len if n is None else int(n)
+    m = FIELDS[polys[0].field]
+    pts = np.ascontiguousarray(np.stack([_l.fe_bytes(int(x) % m) for x in points]))
+    out = np.zeros((batch, 32), dtype=np.uint8)
+    _l.check(_l.init().h2_poly_eval(_handles(polys), ctypes.c_size_t(batch), ctypes.c_size_t(n), _l.ptr(pts), _l.REPR_CANONICAL, _l.ptr(out)))
+    return [int.from_bytes(r.tobytes(), "little") for r in out]
+
+
+def inner_product_resident(a: Sequence["ResidentPoly"], b: Sequence["ResidentPoly"], n: Optional[int] = None) -> list:
+    """[compute_inner_product(a_i, b_i)] (arithmetic.rs:308-319); panics (AssertionError) on unequal lengths like assert_eq! :311."""
+    batch = len(a)
+    assert batch == len(b) and batch >= 1
+    if n is None:
+        assert all(x.len == y.len for x, y in zip(a, b)), "compute_inner_product: a.len() != b.len()"
+        n = a[0].len
+    out = np.zeros((batch, 32), dtype=np.uint8)
+    _l.check(_l.init().h2_poly_inner_product(_handles(a), _handles(b), ctypes.c_size_t(batch), ctypes.c_size_t(int(n)), _l.REPR_CANONICAL, _l.ptr(out)))
+    return [int.from_bytes(r.tobytes(), "little") for r in out]
+
+
+def kate_division_resident(src: Sequence["ResidentPoly"], points: Sequence[int], dst: Optional[Sequence["ResidentPoly"]] = None,
+                           n: Optional[int] = None) -> list:
+    """[kate_division(a, b)] (arithmetic.rs:322-341): quotients by (X - b), n - 1 coefficients each, left on the device."""
+    batch = len(src)
+    assert batch == len(points) and batch >= 1
+    n = src[0].len if n is None else int(n)
+    m = FIELDS[src[0].field]
+    if dst is None:
+        dst = [ResidentPoly(src[0].field, max(n - 1, 1)) for _ in range(batch)]
+    pts = np.ascontiguousarray(np.stack([_l.fe_bytes(int(x) % m) for x in points]))
+    _l.check(_l.init().h2_poly_kate_division(_handles(dst), _handles(src), ctypes.c_size_t(batch), ctypes.c_size_t(n), _l.ptr(pts), _l.REPR_CANONICAL))
+    return list(dst)
+
+
 class EvaluationDomain:
     """poly/domain.rs:20-146.  `zeta` is F::ZETA (domain.rs:85): pasta_curves' choice of cube root
     is not pinned by any in-tree golden, so the caller supplies it."""

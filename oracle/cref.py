@@ -36,7 +36,7 @@ def lib() -> ctypes.CDLL:
         for name in ("orc_best_multiexp", "orc_naive_msm", "orc_best_fft", "orc_ifft", "orc_coeff_to_extended",
                      "orc_extended_to_coeff", "orc_field_op", "orc_scalar_mul", "orc_point_add",
                      "orc_jac_to_affine", "orc_on_curve", "orc_gen_scalars", "orc_gen_points", "orc_ec_fft",
-                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds"):
+                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds", "orc_eval_polynomial", "orc_kate_division"):
             getattr(_lib, name).restype = ctypes.c_int
     return _lib
 
@@ -150,6 +150,22 @@ def affine_to_jacobian_bytes(xy: np.ndarray) -> np.ndarray:
     ident = ~a.any(axis=1)
     out[~ident, 64] = 1
     out[ident, 32] = 1
+    return out
+
+
+def eval_polynomial(field: str, poly: np.ndarray, point) -> int:
+    """arithmetic.rs:297-303 (serial Horner, as the reference runs it)."""
+    p = np.ascontiguousarray(poly, dtype=np.uint8).reshape(-1, 32)
+    out = np.zeros(32, dtype=np.uint8)
+    lib().orc_eval_polynomial(FIELD_ID[field], _p(p), ctypes.c_size_t(p.shape[0]), _p(_fe(point)), _p(out))
+    return int.from_bytes(out.tobytes(), "little")
+
+
+def kate_division(field: str, a: np.ndarray, b) -> np.ndarray:
+    """arithmetic.rs:322-341 (serial)."""
+    p = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+    out = np.zeros((max(p.shape[0] - 1, 0), 32), dtype=np.uint8)
+    lib().orc_kate_division(FIELD_ID[field], _p(p), ctypes.c_size_t(p.shape[0]), _p(_fe(b)), _p(out))
     return out
 
 

@@ -666,6 +666,28 @@ int orc_params_lagrange(int curve, const uint8_t *g_xy, uint32_t k, const uint8_
     return 0;
 }
 
+/* ---------------------------------------------------------------- eval_polynomial / kate_division (serial in the reference)
+ * arithmetic.rs:297-303 and :322-341, "TODO: parallelize?" -- restated as the same serial loops. */
+int orc_eval_polynomial(int field, const uint8_t *poly, size_t n, const uint8_t *point, uint8_t *out) {
+    ensure_init(); const field_t *F = &FLD[field];
+    fe x, acc, c; fe_from_bytes(F, &x, point); memset(&acc, 0, sizeof acc);
+    for (size_t i = n; i-- > 0;) { fe_from_bytes(F, &c, poly + 32 * i); fe_mul(F, &acc, &acc, &x); fe_add(F, &acc, &acc, &c); }
+    fe_to_bytes(F, out, &acc);
+    return 0;
+}
+int orc_kate_division(int field, const uint8_t *a, size_t n, const uint8_t *b, uint8_t *out_q) {
+    ensure_init(); const field_t *F = &FLD[field];
+    if (n < 2) return 0;
+    fe nb, tmp, lead, r; fe_from_bytes(F, &nb, b); fe_neg(F, &nb, &nb); memset(&tmp, 0, sizeof tmp);
+    for (size_t i = n - 1; i >= 1; i--) {            /* q[i-1] from a[i], :332-338 */
+        fe_from_bytes(F, &r, a + 32 * i);
+        fe_sub(F, &lead, &r, &tmp);
+        fe_to_bytes(F, out_q + 32 * (i - 1), &lead);
+        fe_mul(F, &tmp, &lead, &nb);
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- field / curve primitives for KATs */
 /* op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 a^5, 5 neg(a) */
 int orc_field_op(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {

@@ -746,6 +746,19 @@ def params_from_bytes(c: Curve, data: bytes):
 
 
 # --------------------------------------------------------------------------------------
+def kate_division(field: str, a: Sequence[int], b: int) -> List[int]:
+    """arithmetic.rs:322-341: the quotient of a(X) by (X - b), remainder dropped; len(a) - 1 coefficients."""
+    m = FIELDS[field]
+    nb = (-b) % m
+    q = [0] * (len(a) - 1)
+    tmp = 0
+    for qi, r in zip(range(len(q) - 1, -1, -1), reversed(list(a))):
+        lead = (r - tmp) % m
+        q[qi] = lead
+        tmp = lead * nb % m
+    return q
+
+
 def compute_inner_product(m: int, a: Sequence[int], b: Sequence[int]) -> int:
     """arithmetic.rs:308-319."""
     assert len(a) == len(b)

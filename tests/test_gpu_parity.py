@@ -796,3 +796,44 @@ def test_point_codec_and_params_io(eng, goldens):
         eng.Params.read(curve, io.BytesIO(bytes(corrupt)))
     params.close()
     back.close()
+
+
+# ------------------------------------------------------------------------------------------ K14
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_poly_reductions(eng, field):
+    """eval_polynomial / compute_inner_product / kate_division (arithmetic.rs:297-341) on resident and host polynomials against
+    the restated loops, at the chunk-tree's edge sizes and at k = 14; kate_division's defining identity; misuse fails."""
+    from halo2_b200 import lib as L
+    m = pasta.FIELDS[field]
+    for n in (1, 2, 32, 33, 1025, 1 << 14):
+        a = cref.gen_scalars(field, SEED + 800 + n, n)
+        c = cref.gen_scalars(field, SEED + 801 + n, n)
+        ai, ci = cref.bytes_to_ints(a), cref.bytes_to_ints(c)
+        x = pasta.gen_scalars(field, SEED + 802 + n, 1)[0]
+        assert eng.eval_polynomial(a, x, field) == pasta.eval_polynomial(field, ai, x)
+        assert eng.compute_inner_product(a, c, field) == pasta.compute_inner_product(m, ai, ci)
+        q = eng.kate_division(a, x, field)
+        assert cref.bytes_to_ints(q) == pasta.kate_division(field, ai, x)
+    # a batch of resident polynomials, each at its own point (the prover's evaluation loop, plonk/prover.rs: eval_polynomial per
+    # column and rotation), x = 0 and x = 1 included; the quotients stay on the device and evaluate to (a(z) - a(x)) / (z - x)
+    n, batch = 1 << 12, 5
+    polys = [cref.gen_scalars(field, SEED + 810 + b, n) for b in range(batch)]
+    res = [eng.ResidentPoly(field, n, p) for p in polys]
+    pts = pasta.gen_scalars(field, SEED + 820, batch - 2) + [0, 1]
+    want = [pasta.eval_polynomial(field, cref.bytes_to_ints(p), x) for p, x in zip(polys, pts)]
+    assert eng.eval_polynomial_resident(res, pts) == want
+    assert eng.inner_product_resident(res, res[1:] + res[:1]) == [pasta.compute_inner_product(m, cref.bytes_to_ints(p), cref.bytes_to_ints(q_))
+                                                                   for p, q_ in zip(polys, polys[1:] + polys[:1])]
+    quot = eng.kate_division_resident(res, pts)
+    z = pasta.gen_scalars(field, SEED + 830, 1)[0]
+    qz = eng.eval_polynomial_resident(quot, [z] * batch, n=n - 1)
+    az = eng.eval_polynomial_resident(res, [z] * batch)
+    for b in range(batch):
+        assert qz[b] * (z - pts[b]) % m == (az[b] - want[b]) % m, b
+        assert (quot[b].download(n - 1) == cref.ints_to_bytes(pasta.kate_division(field, cref.bytes_to_ints(polys[b]), pts[b]))).all()
+    with pytest.raises(L.H2Error):      # the quotient cannot overwrite its dividend
+        eng.kate_division_resident(res[:1], pts[:1], dst=res[:1])
+    with pytest.raises(AssertionError):  # arithmetic.rs:311
+        eng.compute_inner_product(polys[0], polys[1][:-1], field)
+    for r in res + quot:
+        r.close()

@@ -444,3 +444,32 @@ def test_emul_point_codec(emu, curve):
         out = np.ones((6, 64), dtype=np.uint8)
         assert emu.emu_decompress(cref.CURVE_ID[curve], cref._p(batch), ctypes.c_uint64(6), cref._p(out)) == 4
         assert not out[4].any() and (out[:4] == xy[:4]).all() and (out[5] == xy[5]).all()
+
+
+# ---- K14: eval_polynomial / compute_inner_product / kate_division as chunk trees --------------------------------------
+@pytest.mark.parametrize("field", ["fp", "fq"])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 1024, 1025, 2500])
+def test_emul_polyops(emu, field, n):
+    m = pasta.FIELDS[field]
+    batch = 3
+    a = [pasta.gen_scalars(field, 900 + b, n) for b in range(batch)]
+    c = [pasta.gen_scalars(field, 910 + b, n) for b in range(batch)]
+    a[2] = [0] * n if n > 1 else a[2]
+    pts = [pasta.gen_scalars(field, 920, 1)[0], 0, 1]
+    ab = np.concatenate([cref.ints_to_bytes(v) for v in a])
+    cb = np.concatenate([cref.ints_to_bytes(v) for v in c])
+    pb = cref.ints_to_bytes(pts)
+    out = np.zeros((batch, 32), dtype=np.uint8)
+    emu.emu_polyops(cref.FIELD_ID[field], 0, cref._p(ab), None, batch, ctypes.c_uint64(n), cref._p(pb), cref._p(out))
+    assert cref.bytes_to_ints(out) == [pasta.eval_polynomial(field, a[b], pts[b]) for b in range(batch)]
+    emu.emu_polyops(cref.FIELD_ID[field], 1, cref._p(ab), cref._p(cb), batch, ctypes.c_uint64(n), None, cref._p(out))
+    assert cref.bytes_to_ints(out) == [pasta.compute_inner_product(m, a[b], c[b]) for b in range(batch)]
+    if n >= 2:
+        q = np.zeros((batch, n - 1, 32), dtype=np.uint8)
+        emu.emu_polyops(cref.FIELD_ID[field], 2, cref._p(ab), cref._p(cb), batch, ctypes.c_uint64(n), cref._p(pb), cref._p(q))
+        for b in range(batch):
+            want = pasta.kate_division(field, a[b], pts[b])
+            assert cref.bytes_to_ints(q[b]) == want, b
+            # the defining property: q(X) (X - b) + a(b) == a(X), checked at a random point
+            z = pasta.gen_scalars(field, 930 + b, 1)[0]
+            assert (pasta.eval_polynomial(field, want, z) * (z - pts[b]) + pasta.eval_polynomial(field, a[b], pts[b])) % m == pasta.eval_polynomial(field, a[b], z)

@@ -147,3 +147,17 @@ def test_ipa_rounds_c_vs_python(curve):
         assert gc == cc
         assert [cref.bytes_to_affine(x) for x in gl] == L
         assert [cref.bytes_to_affine(x) for x in gr] == R
+
+
+def test_eval_and_kate_division_restatements_agree():
+    """arithmetic.rs:297-341 in C and in Python, and kate_division's defining identity q(X) (X - b) + a(b) == a(X)."""
+    for field in ("fp", "fq"):
+        m = pasta.FIELDS[field]
+        for n in (1, 2, 3, 64, 257):
+            a = cref.gen_scalars(field, 40 + n, n)
+            ai = cref.bytes_to_ints(a)
+            b, z = pasta.gen_scalars(field, 41 + n, 2)
+            assert cref.eval_polynomial(field, a, b) == pasta.eval_polynomial(field, ai, b)
+            q = pasta.kate_division(field, ai, b)
+            assert cref.bytes_to_ints(cref.kate_division(field, a, b)) == q and len(q) == n - 1
+            assert (pasta.eval_polynomial(field, q, z) * (z - b) + pasta.eval_polynomial(field, ai, b)) % m == pasta.eval_polynomial(field, ai, z)
