@@ -1253,6 +1253,7 @@ extern "C" int h2_points_decompress(int curve, const void *bytes, size_t n, int 
 // ------------------------------------------------------------------------------------------------
 // mode 0: eval (points: batch x 32 host), 1: inner product of a[i] and c[i], 2: kate division of a[i] by (X - point_i) into c[i]
 static PolyBuf *find_poly(uint64_t h);
+static int convert_field(int field, fe *d, size_t n, int to_mont, cudaStream_t s);
 template <class P>
 static int polyops_run(int mode, const std::vector<PolyBuf *> &a, const std::vector<PolyBuf *> &c, size_t n, const void *points, int repr, void *out) {
     Context &X = g_ctx;
@@ -1341,6 +1342,25 @@ static int polyops_dispatch(int mode, const uint64_t *ah, const uint64_t *ch, si
     }
     if (a[0]->field == H2_FIELD_FP) return polyops_run<FpParams>(mode, a, c, n, points, repr, out);
     return polyops_run<FqParams>(mode, a, c, n, points, repr, out);
+}
+// divide_by_vanishing_poly on a resident extended-domain polynomial; t_evals: t_len = 2^(ext_k - k) host elements
+extern "C" int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *a = find_poly(poly);
+    if (!a) return fail("h2_poly_divide_by_vanishing: unknown polynomial handle");
+    if (ext_k > 30 || a->len < ((size_t)1 << ext_k)) return fail("h2_poly_divide_by_vanishing: the polynomial holds fewer than 2^ext_k elements");
+    if (t_len == 0 || (t_len & (t_len - 1)) || t_len > (1u << ext_k)) return fail("h2_poly_divide_by_vanishing: t_len must be a power of two <= 2^ext_k");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.po_pts.ensure((size_t)t_len * sizeof(fe))) return 1;
+    CU(cudaMemcpyAsync(X.po_pts.p, t_evals, (size_t)t_len * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL && convert_field(a->field, X.po_pts.as<fe>(), t_len, 1, s)) return 1;
+    const uint64_t n = 1ull << ext_k;
+    if (a->field == H2_FIELD_FP) LAUNCH(poly_vanish_div_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, a->buf.as<fe>(), n, (const fe *)X.po_pts.as<fe>(), t_len - 1);
+    else LAUNCH(poly_vanish_div_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, a->buf.as<fe>(), n, (const fe *)X.po_pts.as<fe>(), t_len - 1);
+    return scratch_release(s);
 }
 extern "C" int h2_poly_eval(const uint64_t *polys, size_t batch, size_t n, const void *points, int repr, void *out) {
     if (n == 0) { memset(out, 0, batch * 32); return 0; }            // the empty sum (fold over nothing, arithmetic.rs:300-302)

@@ -3,6 +3,7 @@
 //   eval_polynomial        /root/reference/halo2_proofs/src/arithmetic.rs:297-303   sum_i a_i x^i (Horner in the reference)
 //   compute_inner_product  arithmetic.rs:308-319                                     sum_i a_i b_i
 //   kate_division          arithmetic.rs:322-341                                     q = (a - a(b)) / (X - b):  q_i = sum_{j>i} a_j b^(j-i-1)
+//   divide_by_vanishing_poly  poly/domain.rs:329-348                                  h_i *= 1 / t(zeta w^i), elementwise over the extended domain
 //
 // The reference runs all three serially ("TODO: parallelize?"); each is a first-order linear recurrence, so each becomes a
 // tree of CHUNK-sized serial pieces: level l turns m values into ceil(m / CHUNK) by CHUNK multiply-adds per thread with the
@@ -67,7 +68,18 @@ template <class P> struct PolyOps {
     }
 };
 
+// divide_by_vanishing_poly (poly/domain.rs:329-348): h[i] *= t_evaluations[i mod len], len = 2^(extended_k - k) inverses of
+// t(X) = X^n - 1 over the coset (domain.rs:86-128), Montgomery form
+template <class P> struct VanishDiv {
+    static H2_HD void body(fe *a, uint64_t n, const fe *t, uint32_t t_mask, uint64_t i) {
+        if (i < n) fe_store(a + i, fe_mul<P>(fe_load(a + i), fe_load(t + (i & t_mask))));
+    }
+};
+
 #if defined(__CUDACC__)
+template <class P> __global__ void __launch_bounds__(256) poly_vanish_div_kernel(fe *a, uint64_t n, const fe *t, uint32_t t_mask) {
+    VanishDiv<P>::body(a, n, t, t_mask, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
 template <class P> __global__ void __launch_bounds__(128) poly_eval_level_kernel(const fe *const *in_ptrs, const fe *in_flat, uint64_t m, const fe *points,
                                                                                  fe *out, uint64_t out_m) {
     PolyOps<P>::eval_level_body(in_ptrs, in_flat, m, points, out, out_m, blockIdx.y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);

@@ -347,6 +347,16 @@ class EvaluationDomain:
         self.g_coset_inv = zeta * zeta % m
         self.ifft_divisor = pow((1 << k) % m, m - 2, m)
         self.extended_ifft_divisor = pow((1 << ext_k) % m, m - 2, m)
+        # t(X) = X^n - 1 over the coset, inverted (domain.rs:86-128): 2^(ext_k - k) values, then it repeats
+        orig, step = pow(zeta, self.n, m), pow(ew, self.n, m)
+        t, cur = [], orig
+        while True:
+            t.append(cur)
+            cur = cur * step % m
+            if cur == orig:
+                break
+        assert len(t) == 1 << (ext_k - k)
+        self.t_evaluations = [pow((x - 1) % m, m - 2, m) for x in t]
 
     def extended_len(self) -> int:
         return 1 << self.extended_k
@@ -381,6 +391,25 @@ class EvaluationDomain:
                                                 _l.ptr(_l.fe_bytes(self.g_coset)), ctypes.c_size_t(out_len), _l.ptr(out),
                                                 _l.REPR_CANONICAL))
         return out
+
+    def divide_by_vanishing_poly(self, a) -> np.ndarray:
+        """domain.rs:329-348 on a host vector of extended-domain evaluations (through a temporary resident polynomial)."""
+        arr = _l.as_u8(a, 32)
+        assert arr.shape[0] == self.extended_len()
+        r = ResidentPoly(self.field, self.extended_len(), arr)
+        try:
+            return self.divide_by_vanishing_poly_resident(r).download()
+        finally:
+            r.close()
+
+    def divide_by_vanishing_poly_resident(self, a: "ResidentPoly") -> "ResidentPoly":
+        """In place on a resident extended-domain polynomial (the step between the AST evaluation and extended_to_coeff,
+        plonk/vanishing/prover.rs:81-88)."""
+        assert a.len >= self.extended_len()
+        t = np.ascontiguousarray(np.stack([_l.fe_bytes(x) for x in self.t_evaluations]))
+        _l.check(_l.init().h2_poly_divide_by_vanishing(a._h, ctypes.c_uint32(self.extended_k), _l.ptr(t), ctypes.c_uint32(len(self.t_evaluations)),
+                                                       _l.REPR_CANONICAL))
+        return a
 
     # ---- device-resident forms (SURVEY.md section 8(f) row 3): asynchronous, no host copies
     def lagrange_to_coeff_resident(self, a: "ResidentPoly", out: Optional["ResidentPoly"] = None) -> "ResidentPoly":

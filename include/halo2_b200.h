@@ -138,6 +138,9 @@ int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t
  * 32-coefficient serial pieces instead of the reference's serial loop; `batch` polynomials of n coefficients per call.
  * eval_polynomial (arithmetic.rs:297-303): out[i] = polys[i](points[i]); points / out are batch x 32 bytes on the host. */
 int h2_poly_eval(const uint64_t *polys, size_t batch, size_t n, const void *points, int repr, void *out);
+/* EvaluationDomain::divide_by_vanishing_poly (poly/domain.rs:329-348) in place on a resident extended-domain polynomial:
+ * h[i] *= t_evals[i mod t_len]; t_evals = the domain's t_evaluations (domain.rs:86-128), t_len = 2^(ext_k - k).  Asynchronous. */
+int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr);
 /* compute_inner_product (arithmetic.rs:308-319): out[i] = sum_j a[i][j] * b[i][j]. */
 int h2_poly_inner_product(const uint64_t *a, const uint64_t *b, size_t batch, size_t n, int repr, void *out);
 /* kate_division (arithmetic.rs:322-341): dst[i] <- the n - 1 coefficients of (src[i] - src[i](points[i])) / (X - points[i]);

@@ -831,6 +831,21 @@ def test_poly_reductions(eng, field):
     for b in range(batch):
         assert qz[b] * (z - pts[b]) % m == (az[b] - want[b]) % m, b
         assert (quot[b].download(n - 1) == cref.ints_to_bytes(pasta.kate_division(field, cref.bytes_to_ints(polys[b]), pts[b]))).all()
+    # divide_by_vanishing_poly (poly/domain.rs:329-348) on host and resident extended evaluations; the quotient pipeline of
+    # plonk/vanishing/prover.rs:81-88 end to end on the device: coeff_to_extended -> (h = a * a here) -> divide -> extended_to_coeff
+    zeta = pasta.zeta_candidates(field)[0]
+    for j, k in ((3, 5), (5, 9)):
+        d_or = pasta.EvaluationDomain(field, j, k, zeta)
+        d = eng.EvaluationDomain(field, j, k, zeta)
+        assert d.t_evaluations == d_or.t_evaluations
+        ext = cref.gen_scalars(field, SEED + 840 + k, d.extended_len())
+        want_div = cref.ints_to_bytes(d_or.divide_by_vanishing_poly(cref.bytes_to_ints(ext)))
+        assert (d.divide_by_vanishing_poly(ext) == want_div).all()
+        r = eng.ResidentPoly(field, d.extended_len(), ext)
+        d.divide_by_vanishing_poly_resident(r)
+        assert (r.download() == want_div).all()
+        assert (d.extended_to_coeff_resident(r).download() == d.extended_to_coeff(want_div)).all()
+        r.close()
     with pytest.raises(L.H2Error):      # the quotient cannot overwrite its dividend
         eng.kate_division_resident(res[:1], pts[:1], dst=res[:1])
     with pytest.raises(AssertionError):  # arithmetic.rs:311
