@@ -11,7 +11,9 @@ from .arithmetic import (best_multiexp, small_multiexp, best_fft, best_fft_curve
 from .poly import (Params, EvaluationDomain, Blind, ResidentPoly, lagrange_generators, compress_points, decompress_points,  # noqa: F401
                    eval_polynomial_resident, inner_product_resident, kate_division_resident)
 
-__all__ = ["H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "small_multiexp", "best_fft",
+from .evaluator import Ast, AstLeaf, Evaluator  # noqa: F401
+
+__all__ = ["Ast", "AstLeaf", "Evaluator", "H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "small_multiexp", "best_fft",
            "best_fft_curve", "batch_normalize", "multiexp_window_bits", "Params", "EvaluationDomain", "Blind", "ResidentPoly",
            "lagrange_generators", "compress_points", "decompress_points",
            "eval_polynomial", "compute_inner_product", "kate_division", "eval_polynomial_resident", "inner_product_resident",

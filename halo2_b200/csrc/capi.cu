@@ -22,6 +22,7 @@
 #include "fixedbase.cuh"
 #include "codec.cuh"
 #include "polyops.cuh"
+#include "asteval.cuh"
 
 using namespace h2;
 
@@ -99,6 +100,7 @@ struct Context {
     // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms
     DevBuf ec_work, ec_io, ec_out;
     DevBuf fb_a, fb_b;                       // partial sums of the direct-sum fixed-base MSM (ping-pong)
+    DevBuf ast_code, ast_consts;             // asteval.cuh: the postfix program and its constants
     DevBuf po_lvl, po_q, po_pts, po_ptrs;    // polyops.cuh: level arrays, kate carries, per-level points, pointer arrays
     std::vector<TwiddleEntry *> twiddles;
     uint64_t tw_stamp = 0;
@@ -195,7 +197,7 @@ extern "C" int h2_shutdown(void) {
     DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.bases_phi, &g_ctx.glv_parts, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
                      &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
                      &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
-                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out, &g_ctx.fb_a, &g_ctx.fb_b, &g_ctx.po_lvl, &g_ctx.po_q, &g_ctx.po_pts, &g_ctx.po_ptrs};
+                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out, &g_ctx.fb_a, &g_ctx.fb_b, &g_ctx.po_lvl, &g_ctx.po_q, &g_ctx.po_pts, &g_ctx.po_ptrs, &g_ctx.ast_code, &g_ctx.ast_consts};
     for (DevBuf *b : all) b->release();
     for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
     g_ctx.twiddles.clear();
@@ -1342,6 +1344,72 @@ static int polyops_dispatch(int mode, const uint64_t *ah, const uint64_t *ch, si
     }
     if (a[0]->field == H2_FIELD_FP) return polyops_run<FpParams>(mode, a, c, n, points, repr, out);
     return polyops_run<FqParams>(mode, a, c, n, points, repr, out);
+}
+// Evaluator::evaluate (poly/evaluator.rs:129-228) on resident polynomials: `code` is the postfix form of the Ast (asteval.cuh),
+// validated here so that the kernel's operand stack can neither overflow nor underflow.
+template <class P>
+static int ast_run(PolyBuf *out, const std::vector<PolyBuf *> &polys, uint32_t log_n, const AstInstr *code, size_t n_code, const void *consts,
+                   size_t n_consts, const void *omega, const void *lin_base, int repr, bool has_linear) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const uint64_t n = 1ull << log_n;
+    if (scratch_acquire(s)) return 1;
+    if (X.ast_code.ensure(n_code * sizeof(AstInstr)) || X.ast_consts.ensure((n_consts + 1) * sizeof(fe)) || X.po_ptrs.ensure((polys.size() + 1) * sizeof(void *)))
+        return 1;
+    std::vector<const fe *> hp(polys.size() + 1, nullptr);
+    for (size_t i = 0; i < polys.size(); i++) hp[i] = polys[i]->buf.as<fe>();
+    CU(cudaMemcpyAsync(X.po_ptrs.p, hp.data(), hp.size() * sizeof(void *), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(X.ast_code.p, code, n_code * sizeof(AstInstr), cudaMemcpyHostToDevice, s));
+    if (n_consts) {
+        CU(cudaMemcpyAsync(X.ast_consts.p, consts, n_consts * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(n_consts, 64), 64, 0, s, X.ast_consts.as<fe>(), (uint64_t)n_consts, 1);
+    }
+    AstArgs A;
+    A.polys = X.po_ptrs.as<const fe *>(); A.code = X.ast_code.as<AstInstr>(); A.n_code = (uint32_t)n_code; A.consts = X.ast_consts.as<fe>();
+    A.tw = nullptr; A.lin_base = fe_one<P>(); A.log_n = log_n; A.out = out->buf.as<fe>();
+    if (has_linear) {
+        if (get_twiddles<P>(out->field, host_to_mont<P>(omega, repr), log_n, s, &A.tw)) return 1;
+        A.lin_base = host_to_mont<P>(lin_base, repr);
+    }
+    LAUNCH(ast_eval_kernel<P>, blocks_for(n, 128), 128, 0, s, A);
+    return scratch_release(s);
+}
+extern "C" int h2_poly_eval_ast(uint64_t out, const uint64_t *polys, size_t n_polys, uint32_t log_n, const uint32_t *code, size_t n_code,
+                                const void *consts, size_t n_consts, const void *omega, const void *lin_base, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *o = find_poly(out);
+    if (!o) return fail("h2_poly_eval_ast: unknown output handle");
+    if (log_n > 30 || o->len < ((size_t)1 << log_n)) return fail("h2_poly_eval_ast: the output holds fewer than 2^log_n elements");
+    if (n_code == 0 || n_code > (1u << 20)) return fail("h2_poly_eval_ast: empty or oversized program");
+    std::vector<PolyBuf *> ps(n_polys);
+    for (size_t i = 0; i < n_polys; i++) {
+        ps[i] = find_poly(polys[i]);
+        if (!ps[i]) return fail("h2_poly_eval_ast: unknown polynomial handle");
+        if (ps[i]->field != o->field) return fail("h2_poly_eval_ast: the polynomials live in different fields");
+        if (ps[i]->len < ((size_t)1 << log_n)) return fail("h2_poly_eval_ast: a polynomial holds fewer than 2^log_n elements");
+        if (ps[i] == o) return fail("h2_poly_eval_ast: the output cannot be one of the operands (rotated reads)");
+    }
+    const AstInstr *prog = reinterpret_cast<const AstInstr *>(code);
+    int depth = 0;
+    bool has_linear = false;
+    for (size_t pc = 0; pc < n_code; pc++) {
+        const AstInstr &in = prog[pc];
+        switch (in.op) {
+        case AST_POLY: if (in.arg >= n_polys) return fail("h2_poly_eval_ast: polynomial index out of range"); depth++; break;
+        case AST_LINEAR: has_linear = true;   /* fall through */
+        case AST_CONST: if (in.arg >= n_consts) return fail("h2_poly_eval_ast: constant index out of range"); depth++; break;
+        case AST_ADD: case AST_MUL: if (depth < 2) return fail("h2_poly_eval_ast: operand stack underflow"); depth--; break;
+        case AST_SCALE: if (in.arg >= n_consts) return fail("h2_poly_eval_ast: constant index out of range");   /* fall through */
+        case AST_NEG: if (depth < 1) return fail("h2_poly_eval_ast: operand stack underflow"); break;
+        default: return fail("h2_poly_eval_ast: unknown opcode");
+        }
+        if (depth > H2_AST_STACK) return fail("h2_poly_eval_ast: expression deeper than the operand stack (24)");
+    }
+    if (depth != 1) return fail("h2_poly_eval_ast: the program must leave exactly one value");
+    if (has_linear && (!omega || !lin_base)) return fail("h2_poly_eval_ast: a LinearTerm needs omega and the coset generator");
+    if (o->field == H2_FIELD_FP) return ast_run<FpParams>(o, ps, log_n, prog, n_code, consts, n_consts, omega, lin_base, repr, has_linear);
+    return ast_run<FqParams>(o, ps, log_n, prog, n_code, consts, n_consts, omega, lin_base, repr, has_linear);
 }
 // divide_by_vanishing_poly on a resident extended-domain polynomial; t_evals: t_len = 2^(ext_k - k) host elements
 extern "C" int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr) {

@@ -138,6 +138,15 @@ int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t
  * 32-coefficient serial pieces instead of the reference's serial loop; `batch` polynomials of n coefficients per call.
  * eval_polynomial (arithmetic.rs:297-303): out[i] = polys[i](points[i]); points / out are batch x 32 bytes on the host. */
 int h2_poly_eval(const uint64_t *polys, size_t batch, size_t n, const void *points, int repr, void *out);
+/* Evaluator::evaluate (poly/evaluator.rs:129-228) on resident polynomials of one basis: out[i] = Ast(polys)[i] for i < 2^log_n.
+ * `code` is the postfix form of the Ast, n_code instructions of four uint32 {op, arg, shift, 0}:
+ *   0 POLY   push polys[arg][(i + shift) mod 2^log_n]   (shift = rotation * stride; stride = 2^(extended_k - k) in the extended basis)
+ *   1 CONST  push consts[arg]            2 LINEAR push consts[arg] * lin_base * omega^i   (lin_base = 1 | zeta, :538-555, :584-604)
+ *   3 ADD    4 MUL  (two operands -> one)   5 SCALE top *= consts[arg]     6 NEG
+ * (DistributePowers, :182-193, flattens to CONST 0, then SCALE base / term / ADD per term.)  The output cannot be an operand.
+ * omega / lin_base may be NULL when the program has no LINEAR.  Asynchronous. */
+int h2_poly_eval_ast(uint64_t out, const uint64_t *polys, size_t n_polys, uint32_t log_n, const uint32_t *code, size_t n_code,
+                     const void *consts, size_t n_consts, const void *omega, const void *lin_base, int repr);
 /* EvaluationDomain::divide_by_vanishing_poly (poly/domain.rs:329-348) in place on a resident extended-domain polynomial:
  * h[i] *= t_evals[i mod t_len]; t_evals = the domain's t_evaluations (domain.rs:86-128), t_len = 2^(ext_k - k).  Asynchronous. */
 int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr);

@@ -13,6 +13,7 @@ What it restates (all file:line relative to /root/reference/halo2_proofs/src):
   * Params::new's EC-FFT      poly/commitment.rs:77-94   (generators are synthetic, see below)
   * EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff,
     distribute_powers_zeta, ifft}   poly/domain.rs:40-146, 227-255, 303-325, 357-383
+  * Evaluator::evaluate over an Ast              poly/evaluator.rs:129-228 (+ the BasisOps of :522-607)
   * point compression and Params::{write, read}   book/src/background/curves.md:203-240, poly/commitment.rs:168-205
   * the IPA round loop       poly/commitment/prover.rs:100-142, :154-166 (transcript factored out: challenges
     and randomness are inputs, the points / scalar written to the transcript are outputs)
@@ -528,6 +529,49 @@ class EvaluationDomain:
         assert len(a) == self.extended_len()
         t = self.t_evaluations
         return [x * t[i % len(t)] % self.m for i, x in enumerate(a)]
+
+
+def ast_evaluate(d: "EvaluationDomain", basis: str, ast, polys: Sequence[Sequence[int]]) -> List[int]:
+    """Evaluator::evaluate (poly/evaluator.rs:129-228), element by element.  `ast` is a nested tuple:
+    ("poly", index, rotation) | ("add", a, b) | ("mul", a, b) | ("scale", a, s) | ("dp", [terms], base) | ("lin", s) | ("const", s);
+    basis "lagrange" (rotation = 1 position, linear term s w^i, :538-555) or "extended" (rotation = 2^(extended_k - k) positions,
+    poly/domain.rs:286-295; linear term s zeta extended_omega^i, :584-604)."""
+    m = d.m
+    n = d.n if basis == "lagrange" else d.extended_len()
+    stride = 1 if basis == "lagrange" else 1 << (d.extended_k - d.k)
+    w = d.omega if basis == "lagrange" else d.extended_omega
+    lin0 = 1 if basis == "lagrange" else d.g_coset
+
+    def rec(a) -> List[int]:
+        k = a[0]
+        if k == "poly":
+            rot = a[2] * stride                      # rotate_left for rot >= 0, rotate_right for rot < 0 (poly.rs:237-290)
+            return [polys[a[1]][(i + rot) % n] for i in range(n)]
+        if k == "add":
+            x, y = rec(a[1]), rec(a[2])
+            return [(p + q) % m for p, q in zip(x, y)]
+        if k == "mul":
+            x, y = rec(a[1]), rec(a[2])
+            return [p * q % m for p, q in zip(x, y)]
+        if k == "scale":
+            return [p * a[2] % m for p in rec(a[1])]
+        if k == "dp":
+            acc = [0] * n
+            for term in a[1]:
+                t = rec(term)
+                acc = [(p * a[2] + q) % m for p, q in zip(acc, t)]
+            return acc
+        if k == "lin":
+            out, cur = [], lin0 * a[1] % m
+            for _ in range(n):
+                out.append(cur)
+                cur = cur * w % m
+            return out
+        if k == "const":
+            return [a[1] % m] * n
+        raise ValueError(k)
+
+    return rec(ast)
 
 
 def eval_polynomial(field: str, poly: Sequence[int], point: int) -> int:

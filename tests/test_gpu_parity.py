@@ -852,3 +852,77 @@ def test_poly_reductions(eng, field):
         eng.compute_inner_product(polys[0], polys[1][:-1], field)
     for r in res + quot:
         r.close()
+
+
+# ------------------------------------------------------------------------------------------ K15
+def _ast_tuple(node):
+    k, a = node.kind, node.args
+    if k == "poly":
+        return ("poly", a[0], a[1])
+    if k in ("add", "mul"):
+        return (k, _ast_tuple(a[0]), _ast_tuple(a[1]))
+    if k == "scale":
+        return ("scale", _ast_tuple(a[0]), a[1])
+    if k == "dp":
+        return ("dp", [_ast_tuple(t) for t in a[0]], a[1])
+    return (k, a[0])
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_ast_evaluator_and_quotient_pipeline(eng, field):
+    """Evaluator::evaluate (poly/evaluator.rs:129-228) on the device against the restated tree walk, in both bases; then the
+    quotient pipeline of plonk/vanishing/prover.rs:81-88 without leaving HBM: coeff_to_extended of four columns, an h(X)-shaped
+    Ast over them, divide_by_vanishing_poly, extended_to_coeff -- against the same steps on the oracle."""
+    from halo2_b200 import lib as L
+    from halo2_b200.evaluator import Ast
+    zeta = pasta.zeta_candidates(field)[0]
+    y, theta = pasta.gen_scalars(field, SEED + 1010, 2)
+
+    def expr(a, b, c, q):
+        gate0 = (a * b - c) * q
+        gate1 = (a.with_rotation(1) - a) * (b.with_rotation(-1) + Ast.constant_term(7)) * 3
+        perm = (c + Ast.linear_term(theta) + Ast.constant_term(11)) * (a.with_rotation(-2) + b * theta)
+        return Ast.distribute_powers([gate0, gate1, -perm, q.with_rotation(3)], y) + Ast.constant_term(0) * 5
+
+    for basis, j, k in (("extended", 5, 6), ("lagrange", 2, 7), ("extended", 3, 10)):
+        d_or = pasta.EvaluationDomain(field, j, k, zeta)
+        d = eng.EvaluationDomain(field, j, k, zeta)
+        n = d.n if basis == "lagrange" else d.extended_len()
+        polys = [cref.gen_scalars(field, SEED + 1000 + i + k, n) for i in range(4)]
+        ev = eng.Evaluator(d, basis)
+        leaves = [ev.register_poly(p) for p in polys]
+        ast = expr(*leaves)
+        want = pasta.ast_evaluate(d_or, basis, _ast_tuple(ast), [cref.bytes_to_ints(p) for p in polys])
+        got = ev.evaluate(ast)
+        assert cref.bytes_to_ints(got.download()) == want, (basis, k)
+        for node in (Ast.constant_term(0), Ast.linear_term(0), Ast.linear_term(9), leaves[2].with_rotation(-1)):   # evaluator.rs:625-660
+            assert cref.bytes_to_ints(ev.evaluate(node, out=got).download()) == pasta.ast_evaluate(d_or, basis, _ast_tuple(node),
+                                                                                                     [cref.bytes_to_ints(p) for p in polys])
+        with pytest.raises(L.H2Error):       # the output cannot be an operand
+            ev.evaluate(leaves[0], out=ev.polys[0])
+        got.close()
+        ev.close()
+    # resident quotient pipeline at k = 8, degree 5 (extended_k = 10)
+    j, k = 5, 8
+    d_or = pasta.EvaluationDomain(field, j, k, zeta)
+    d = eng.EvaluationDomain(field, j, k, zeta)
+    cols = [cref.gen_scalars(field, SEED + 1100 + i, d.n) for i in range(4)]          # coefficient form
+    res = [eng.ResidentPoly(field, d.n, c_) for c_ in cols]
+    ext = [d.coeff_to_extended_resident(r) for r in res]
+    ev = eng.Evaluator(d, "extended")
+    h = ev.evaluate(expr(*[ev.register_poly(e) for e in ext]))
+    d.divide_by_vanishing_poly_resident(h)
+    got = d.extended_to_coeff_resident(h).download()
+    ext_or = [d_or.coeff_to_extended(cref.bytes_to_ints(c_)) for c_ in cols]
+    h_or = d_or.divide_by_vanishing_poly(pasta.ast_evaluate(d_or, "extended", _ast_tuple(expr(*[eng.AstLeaf(i) for i in range(4)])), ext_or))
+    assert cref.bytes_to_ints(got) == d_or.extended_to_coeff(h_or)
+    # misuse: malformed programs are rejected before anything is launched
+    lib = L.init()
+    out = eng.ResidentPoly(field, d.extended_len())
+    hs = (ctypes.c_uint64 * 1)(ext[0]._h.value)
+    for bad in ([[3, 0, 0, 0]], [[0, 0, 0, 0], [0, 0, 0, 0]], [[0, 5, 0, 0]], [[1, 0, 0, 0]], [[9, 0, 0, 0]], [[0, 0, 0, 0]] * 30):
+        code = np.array(bad, dtype=np.uint32)
+        assert lib.h2_poly_eval_ast(out._h, hs, ctypes.c_size_t(1), ctypes.c_uint32(d.extended_k), code.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.c_size_t(code.shape[0]), None, ctypes.c_size_t(0), None, None, L.REPR_CANONICAL) != 0, bad
+    for r in res + ext + [h, out]:
+        r.close()

@@ -473,3 +473,59 @@ def test_emul_polyops(emu, field, n):
             # the defining property: q(X) (X - b) + a(b) == a(X), checked at a random point
             z = pasta.gen_scalars(field, 930 + b, 1)[0]
             assert (pasta.eval_polynomial(field, want, z) * (z - pts[b]) + pasta.eval_polynomial(field, a[b], pts[b])) % m == pasta.eval_polynomial(field, a[b], z)
+
+
+# ---- K15: Evaluator::evaluate over an Ast (poly/evaluator.rs:129-228) as one postfix program ----------------------------
+def _ast_tuple(node):
+    """halo2_b200.evaluator.Ast -> the oracle's nested-tuple form."""
+    k, a = node.kind, node.args
+    if k == "poly":
+        return ("poly", a[0], a[1])
+    if k in ("add", "mul"):
+        return (k, _ast_tuple(a[0]), _ast_tuple(a[1]))
+    if k == "scale":
+        return ("scale", _ast_tuple(a[0]), a[1])
+    if k == "dp":
+        return ("dp", [_ast_tuple(t) for t in a[0]], a[1])
+    return (k, a[0])
+
+
+def _quotient_like_ast(ev_leaves, y, theta):
+    """An h(X)-shaped expression: gates folded by powers of y (DistributePowers), products of rotated columns, a scaled
+    selector, the identity term of the permutation argument (LinearTerm) and a constant."""
+    from halo2_b200.evaluator import Ast
+    a, b, c, q = ev_leaves
+    gate0 = (a * b - c) * q
+    gate1 = (a.with_rotation(1) - a) * (b.with_rotation(-1) + Ast.constant_term(7)) * 3
+    perm = (c + Ast.linear_term(theta) + Ast.constant_term(11)) * (a.with_rotation(-2) + b * theta)
+    return Ast.distribute_powers([gate0, gate1, -perm, q.with_rotation(3)], y) + Ast.constant_term(0) * 5
+
+
+@pytest.mark.parametrize("basis,j,k", [("extended", 3, 4), ("extended", 5, 3), ("lagrange", 2, 5), ("lagrange", 2, 0)])
+def test_emul_ast_evaluator(emu, basis, j, k):
+    from halo2_b200.evaluator import AstLeaf, compile_ast
+    field = "fp"
+    d = pasta.EvaluationDomain(field, j, k, pasta.zeta_candidates(field)[0])
+    log_n = k if basis == "lagrange" else d.extended_k
+    n = 1 << log_n
+    polys = [pasta.gen_scalars(field, 1000 + i, n) for i in range(4)]
+    y, theta = pasta.gen_scalars(field, 1010, 2)
+    ast = _quotient_like_ast([AstLeaf(i) for i in range(4)], y, theta)
+    want = pasta.ast_evaluate(d, basis, _ast_tuple(ast), polys)
+    stride = 1 if basis == "lagrange" else 1 << (d.extended_k - d.k)
+    code, consts = compile_ast(ast, d.m, stride)
+    pb = np.concatenate([cref.ints_to_bytes(p) for p in polys])
+    cb = cref.ints_to_bytes(consts)
+    omega = d.omega if basis == "lagrange" else d.extended_omega
+    lin = 1 if basis == "lagrange" else d.g_coset
+    out = np.zeros((n, 32), dtype=np.uint8)
+    emu.emu_ast_eval(cref.FIELD_ID[field], cref._p(pb), 4, log_n, code.ctypes.data_as(ctypes.c_void_p), code.shape[0], cref._p(cb), len(consts),
+                     cref._p(cref._fe(omega)), cref._p(cref._fe(lin)), cref._p(out))
+    assert cref.bytes_to_ints(out) == want
+    # the reference's own regression cases (evaluator.rs:625-660): a bare ConstantTerm / LinearTerm of zero
+    from halo2_b200.evaluator import Ast
+    for node in (Ast.constant_term(0), Ast.linear_term(0), Ast.linear_term(9)):
+        code, consts = compile_ast(node, d.m, stride)
+        emu.emu_ast_eval(cref.FIELD_ID[field], cref._p(pb), 4, log_n, code.ctypes.data_as(ctypes.c_void_p), code.shape[0], cref._p(cref.ints_to_bytes(consts)),
+                         len(consts), cref._p(cref._fe(omega)), cref._p(cref._fe(lin)), cref._p(out))
+        assert cref.bytes_to_ints(out) == pasta.ast_evaluate(d, basis, _ast_tuple(node), polys)
