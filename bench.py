@@ -276,6 +276,66 @@ def poly_reductions_ms(h2, cref, reps=5):
     return out
 
 
+def quotient_pipeline_ms(h2, cref, threads, reps=5):
+    """The quotient pipeline of plonk/vanishing/prover.rs:81-88 at k=14, extended_k=16, resident on the device: coeff_to_extended of
+    four columns, an h(X)-shaped Ast over them (two gates, a permutation-style product with the linear term, folded by powers of
+    y: poly/evaluator.rs:129-228), divide_by_vanishing_poly, extended_to_coeff -- next to the same steps on the C restatement
+    (all host threads).  The circuit-specific Ast of benches/plonk.rs is the caller's; this one has its shape and size."""
+    import numpy as np
+    from halo2_b200.evaluator import Ast, AstLeaf, compile_ast
+    zeta = pow(5, (P_MOD - 1) // 3, P_MOD)
+    d = h2.EvaluationDomain("fp", PROVER_J, PROVER_K, zeta)
+    n = d.n
+    cols = [cref.gen_scalars("fp", SEED + 95 + i, n) for i in range(4)]
+    y, theta = cref.bytes_to_ints(cref.gen_scalars("fp", SEED + 99, 2))
+
+    def expr(a, b, c, q):
+        gate0 = (a * b - c) * q
+        gate1 = (a.with_rotation(1) - a) * (b.with_rotation(-1) + Ast.constant_term(7)) * 3
+        perm = (c + Ast.linear_term(theta) + Ast.constant_term(11)) * (a.with_rotation(-2) + b * theta)
+        return Ast.distribute_powers([gate0, gate1, -perm, q.with_rotation(3)], y)
+
+    res = [h2.ResidentPoly("fp", n, c_) for c_ in cols]
+    ext = [h2.ResidentPoly("fp", d.extended_len()) for _ in cols]
+    hx = h2.ResidentPoly("fp", d.extended_len())
+    out = h2.ResidentPoly("fp", n * d.quotient_poly_degree)
+    ev = h2.Evaluator(d, "extended")
+    ast = expr(*[ev.register_poly(e) for e in ext])
+
+    def run():
+        for r, e in zip(res, ext):
+            d.coeff_to_extended_resident(r, out=e)
+        ev.evaluate(ast, out=hx)
+        d.divide_by_vanishing_poly_resident(hx)
+        d.extended_to_coeff_resident(hx, out=out)
+        return out.download(1)          # synchronises
+    run()
+    t0 = time.time()
+    for _ in range(reps):
+        run()
+    gpu_ms = (time.time() - t0) / reps * 1e3
+    got = out.download()
+    # CPU restatement: same steps, all threads
+    code, consts = compile_ast(expr(*[AstLeaf(i) for i in range(4)]), P_MOD, 1 << (d.extended_k - d.k))
+    t0 = time.time()
+    ext_c = np.stack([cref.coeff_to_extended("fp", c_, PROVER_K, d.extended_k, zeta, d.extended_omega, threads) for c_ in cols])
+    h_c = cref.ast_eval("fp", ext_c, d.extended_k, code, consts, d.extended_omega, zeta, threads)
+    tev = cref.ints_to_bytes(d.t_evaluations)
+    h_i = (np.arange(d.extended_len()) % len(d.t_evaluations))
+    t1 = time.time()
+    # divide_by_vanishing_poly: an elementwise multiply (domain.rs:329-348) -- through the same interpreter: POLY 0, POLY 1, MUL
+    tfull = tev[h_i]
+    h_c = cref.ast_eval("fp", np.stack([h_c, tfull]), d.extended_k, np.array([[0, 0, 0, 0], [0, 1, 0, 0], [4, 0, 0, 0]], dtype=np.uint32), [],
+                        d.extended_omega, zeta, threads)
+    want = cref.extended_to_coeff("fp", h_c, d.extended_k, d.extended_omega_inv, d.extended_ifft_divisor, zeta, n * d.quotient_poly_degree, threads)
+    cpu_ms = (time.time() - t0) * 1e3
+    same = bool((got == want).all())
+    for r in res + ext + [hx, out]:
+        r.close()
+    return {"k": PROVER_K, "extended_k": d.extended_k, "columns": 4, "ast_instructions": int(code.shape[0]), "gpu_ms": gpu_ms,
+            "cpu_baseline": {"ms": cpu_ms, "cores": threads, "kind": "port"}, "same_result": same}
+
+
 def resident_column_ms(h2, cref, reps=5):
     """One advice column's trip through the hot path at k=14 -- commit_lagrange, lagrange_to_coeff, commit,
     coeff_to_extended, extended values back to the host -- with host buffers per call vs device-resident handles."""
@@ -617,8 +677,14 @@ def main():
             for kind, cnt in sched:
                 kinds[kind] = kinds.get(kind, 0) + (cnt if kind.endswith("_many") else 1)
             extra["resident_column_k14"] = resident_column_ms(h2, cref)
-            extra["params_lagrange_k14"] = params_lagrange_ms(h2, cref, threads)
-            extra["poly_reductions_k14"] = poly_reductions_ms(h2, cref)
+            def guarded(fn, *a):     # a failing side measurement must not take the headline line down with it
+                try:
+                    return fn(*a)
+                except Exception as e:  # noqa: BLE001
+                    return {"error": f"{type(e).__name__}: {e}"}
+            extra["params_lagrange_k14"] = guarded(params_lagrange_ms, h2, cref, threads)
+            extra["poly_reductions_k14"] = guarded(poly_reductions_ms, h2, cref)
+            extra["quotient_pipeline_k14"] = guarded(quotient_pipeline_ms, h2, cref, threads)
             extra["create_proof_k14_replay"] = {
                 "metric": "hot_path_ms_per_proof", "value": gdt * 1e3, "unit": "ms", "higher_is_better": False,
                 "cpu_baseline": {"value": cdt * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": cpu_by_kind,

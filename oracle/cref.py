@@ -36,7 +36,7 @@ def lib() -> ctypes.CDLL:
         for name in ("orc_best_multiexp", "orc_naive_msm", "orc_best_fft", "orc_ifft", "orc_coeff_to_extended",
                      "orc_extended_to_coeff", "orc_field_op", "orc_scalar_mul", "orc_point_add",
                      "orc_jac_to_affine", "orc_on_curve", "orc_gen_scalars", "orc_gen_points", "orc_ec_fft",
-                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds", "orc_eval_polynomial", "orc_kate_division"):
+                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds", "orc_eval_polynomial", "orc_kate_division", "orc_ast_eval"):
             getattr(_lib, name).restype = ctypes.c_int
     return _lib
 
@@ -166,6 +166,18 @@ def kate_division(field: str, a: np.ndarray, b) -> np.ndarray:
     p = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
     out = np.zeros((max(p.shape[0] - 1, 0), 32), dtype=np.uint8)
     lib().orc_kate_division(FIELD_ID[field], _p(p), ctypes.c_size_t(p.shape[0]), _p(_fe(b)), _p(out))
+    return out
+
+
+def ast_eval(field: str, polys: np.ndarray, log_n: int, code: np.ndarray, consts, omega, lin_base, threads: Optional[int] = None) -> np.ndarray:
+    """Evaluator::evaluate (poly/evaluator.rs:129-228) from the postfix form of the Ast (see orc_ast_eval); polys (n_polys, 2^log_n, 32)."""
+    p = np.ascontiguousarray(polys, dtype=np.uint8).reshape(-1, 1 << log_n, 32)
+    c = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
+    cs = ints_to_bytes(consts) if len(consts) else np.zeros((1, 32), dtype=np.uint8)
+    out = np.zeros((1 << log_n, 32), dtype=np.uint8)
+    lib().orc_ast_eval(FIELD_ID[field], _p(p), ctypes.c_uint32(p.shape[0]), ctypes.c_uint32(log_n), c.ctypes.data_as(ctypes.c_void_p),
+                       ctypes.c_uint32(c.shape[0]), _p(cs), ctypes.c_uint32(len(consts)), _p(_fe(omega)), _p(_fe(lin_base)),
+                       threads or default_threads(), _p(out))
     return out
 
 

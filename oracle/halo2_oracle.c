@@ -688,6 +688,58 @@ int orc_kate_division(int field, const uint8_t *a, size_t n, const uint8_t *b, u
     return 0;
 }
 
+/* ---------------------------------------------------------------- Evaluator::evaluate (poly/evaluator.rs:129-228)
+ * The Ast arrives flattened in postfix form (four uint32 per instruction: op, arg, shift, 0 -- 0 POLY, 1 CONST, 2 LINEAR, 3 ADD,
+ * 4 MUL, 5 SCALE, 6 NEG; DistributePowers = CONST 0 then SCALE base / term / ADD per term); like the reference the work is split
+ * into chunks of elements, one thread each (multicore::scope, :199-216).  Used as the timed CPU baseline of the quotient pipeline. */
+typedef struct { const field_t *F; const fe *const *polys; const uint32_t *code; uint32_t n_code; const fe *consts; fe lin0, omega; uint64_t n, lo, hi; fe *out; } ast_task;
+static void *ast_worker(void *arg) {
+    ast_task *T = (ast_task *)arg; const field_t *F = T->F;
+    fe st[32], lin; uint64_t e[4] = {T->lo, 0, 0, 0};
+    fe_pow(F, &lin, &T->omega, e); fe_mul(F, &lin, &lin, &T->lin0);        /* lin_base * omega^lo, :545-553 */
+    for (uint64_t i = T->lo; i < T->hi; i++) {
+        uint32_t sp = 0;
+        for (uint32_t pc = 0; pc < T->n_code; pc++) {
+            const uint32_t *in = T->code + 4 * pc;
+            switch (in[0]) {
+            case 0: st[sp++] = T->polys[in[1]][(i + (uint64_t)(int64_t)(int32_t)in[2]) & (T->n - 1)]; break;
+            case 1: st[sp++] = T->consts[in[1]]; break;
+            case 2: fe_mul(F, &st[sp], &lin, &T->consts[in[1]]); sp++; break;
+            case 3: sp--; fe_add(F, &st[sp - 1], &st[sp - 1], &st[sp]); break;
+            case 4: sp--; fe_mul(F, &st[sp - 1], &st[sp - 1], &st[sp]); break;
+            case 5: fe_mul(F, &st[sp - 1], &st[sp - 1], &T->consts[in[1]]); break;
+            default: fe_neg(F, &st[sp - 1], &st[sp - 1]); break;
+            }
+        }
+        T->out[i] = st[0];
+        fe_mul(F, &lin, &lin, &T->omega);
+    }
+    return NULL;
+}
+int orc_ast_eval(int field, const uint8_t *polys, uint32_t n_polys, uint32_t log_n, const uint32_t *code, uint32_t n_code, const uint8_t *consts,
+                 uint32_t n_consts, const uint8_t *omega, const uint8_t *lin_base, int threads, uint8_t *out) {
+    ensure_init(); const field_t *F = &FLD[field];
+    if (threads < 1) threads = 1;
+    uint64_t n = (uint64_t)1 << log_n;
+    fe **pp = (fe **)malloc(sizeof(fe *) * (n_polys ? n_polys : 1));
+    for (uint32_t b = 0; b < n_polys; b++) pp[b] = load_vec(F, polys + 32 * n * b, n, n);
+    fe *cs = load_vec(F, consts, n_consts, n_consts ? n_consts : 1), *o = (fe *)malloc(sizeof(fe) * n);
+    fe w, l0; fe_from_bytes(F, &w, omega); fe_from_bytes(F, &l0, lin_base);
+    uint64_t chunks = (uint64_t)threads * 4, cs_len = (n + chunks - 1) / chunks;       /* get_chunk_params, :16-32 */
+    uint64_t nch = (n + cs_len - 1) / cs_len;
+    ast_task *ts = (ast_task *)malloc(sizeof(ast_task) * nch); pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nch);
+    for (uint64_t c = 0; c < nch; c++) {
+        uint64_t lo = c * cs_len, hi = lo + cs_len < n ? lo + cs_len : n;
+        ts[c] = (ast_task){F, (const fe *const *)pp, code, n_code, cs, l0, w, n, lo, hi, o};
+        if (c + 1 < nch) pthread_create(&th[c], NULL, ast_worker, &ts[c]); else ast_worker(&ts[c]);
+    }
+    for (uint64_t c = 0; c + 1 < nch; c++) pthread_join(th[c], NULL);
+    store_vec(F, out, o, n);
+    for (uint32_t b = 0; b < n_polys; b++) free(pp[b]);
+    free(pp); free(cs); free(o); free(ts); free(th);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- field / curve primitives for KATs */
 /* op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 a^5, 5 neg(a) */
 int orc_field_op(int field, int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {

@@ -161,3 +161,24 @@ def test_eval_and_kate_division_restatements_agree():
             q = pasta.kate_division(field, ai, b)
             assert cref.bytes_to_ints(cref.kate_division(field, a, b)) == q and len(q) == n - 1
             assert (pasta.eval_polynomial(field, q, z) * (z - b) + pasta.eval_polynomial(field, ai, b)) % m == pasta.eval_polynomial(field, ai, z)
+
+
+def test_ast_evaluate_restatements_agree():
+    """Evaluator::evaluate (poly/evaluator.rs:129-228): the recursive big-int walk and the C interpreter of the flattened program
+    agree in both bases, for any thread count (chunk boundaries, evaluator.rs:16-32)."""
+    from halo2_b200.evaluator import Ast, AstLeaf, compile_ast     # the flattening only: no GPU, no engine call
+    from tests.test_kernel_emul import _ast_tuple, _quotient_like_ast
+    field = "fq"
+    for basis, j, k in (("extended", 3, 3), ("lagrange", 2, 6), ("extended", 5, 2)):
+        d = pasta.EvaluationDomain(field, j, k, pasta.zeta_candidates(field)[1])
+        log_n = k if basis == "lagrange" else d.extended_k
+        polys = [pasta.gen_scalars(field, 70 + i, 1 << log_n) for i in range(4)]
+        y, theta = pasta.gen_scalars(field, 75, 2)
+        ast = _quotient_like_ast([AstLeaf(i) for i in range(4)], y, theta)
+        code, consts = compile_ast(ast, d.m, 1 if basis == "lagrange" else 1 << (d.extended_k - d.k))
+        want = pasta.ast_evaluate(d, basis, _ast_tuple(ast), polys)
+        pb = np.stack([cref.ints_to_bytes(p) for p in polys])
+        for threads in (1, 3, 64):
+            got = cref.ast_eval(field, pb, log_n, code, consts, d.omega if basis == "lagrange" else d.extended_omega,
+                                1 if basis == "lagrange" else d.g_coset, threads)
+            assert cref.bytes_to_ints(got) == want, (basis, threads)
