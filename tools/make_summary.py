@@ -42,6 +42,14 @@ if os.path.exists(b) and os.path.getsize(b):
         p = x["params_lagrange_k14"]
         parts.append(f"* g -> g_lagrange at k=14: {p['gpu_ms']:.2f} ms vs CPU restatement {p['cpu_baseline']['ms']:.0f} ms at k={p['cpu_baseline']['k']} "
                      f"({p['cpu_baseline']['cores']} threads).")
+    if "quotient_pipeline_k14" in x and "gpu_ms" in x["quotient_pipeline_k14"]:
+        q = x["quotient_pipeline_k14"]
+        parts.append(f"* resident quotient pipeline at k=14 (4 columns -> extended, {q['ast_instructions']}-instruction Ast, / vanishing, -> coefficients): "
+                     f"{q['gpu_ms']:.3f} ms vs {q['cpu_baseline']['ms']:.0f} ms on the C restatement ({q['cpu_baseline']['cores']} threads), same result: {q['same_result']}.")
+    if "poly_reductions_k14" in x and "eval_x16" in x["poly_reductions_k14"]:
+        r_ = x["poly_reductions_k14"]
+        parts.append(f"* k=14 reductions on resident polynomials: 16 eval_polynomial {r_['eval_x16']['gpu_ms']:.3f} ms vs {r_['eval_x16']['cpu_baseline']['ms']:.1f} ms, "
+                     f"4 kate_division {r_['kate_division_x4']['gpu_ms']:.3f} ms vs {r_['kate_division_x4']['cpu_baseline']['ms']:.1f} ms (1 core).")
     parts.append(f"* clocks {d['clocks']}\n")
 open(f"{dst}/{tag}_summary.md", "w").write("\n".join(parts))
 print(open(f"{dst}/{tag}_summary.md").read()[:3000])
