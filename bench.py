@@ -12,7 +12,11 @@ A "step" is one pass of the hot path over one batch of synthetic input:
   * `roofline`: the dominant kernel (msm_accum0_kernel), algorithmic bytes (96 B per pair,
     SURVEY.md section 8(d)) / its CUDA-event duration measured live, against the measured HBM peak.
   * `cpu_baseline`: the C restatement of the reference algorithm (oracle/halo2_oracle.c, "port":
-    the Rust reference cannot be built here) on all host cores, same workload.
+    the Rust reference cannot be built here) on all host cores, same workload (N = 1 only).
+  * more single-GPU side measurements under `extra` (N = 1 only, each next to the C restatement): `create_proof_k14_replay`
+    (the prover's hot-path call schedule), `resident_column_k14`, `params_lagrange_k14` (Params::new's
+    EC-FFT), `poly_reductions_k14` (eval_polynomial / kate_division), `quotient_pipeline_k14` (coeff_to_extended -> Ast ->
+    divide_by_vanishing_poly -> extended_to_coeff on resident polynomials).
 
 `--impl reference` times that CPU restatement alone (the reference arm).
 """
@@ -641,7 +645,7 @@ def main():
 
         # ---- CPU baseline: the reference algorithm restated in C, all host cores, same workload
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU arm and the single-GPU side measurements: N = 1 only
             from oracle import cref
             threads = os.cpu_count() or 1
             kb = cref.gen_scalars(SCALAR_FIELD, SEED + 3, n)
