@@ -229,6 +229,56 @@ where
     (0..g.len()).map(|i| affine_from_xy::<C>(&out[64 * i..64 * i + 64])).collect()
 }
 
+/// Postfix form of `poly::Ast` for `h2_poly_eval_ast` (halo2_b200/csrc/asteval.cuh).  The patched `Evaluator::evaluate`
+/// (poly/evaluator.rs:129-228) calls `flatten(&ast, stride, &mut prog)` once and launches one kernel, instead of `recurse`
+/// per chunk.  `AstView` is the shim's read-only mirror of the crate-private `Ast` enum (the patch adds the `From` impl
+/// next to the enum, evaluator.rs:237-270).
+pub enum AstView<'a, F> {
+    Poly { index: usize, rotation: i32 },
+    Add(&'a AstView<'a, F>, &'a AstView<'a, F>),
+    Mul(&'a AstView<'a, F>, &'a AstView<'a, F>),
+    Scale(&'a AstView<'a, F>, F),
+    DistributePowers(&'a [AstView<'a, F>], F),
+    LinearTerm(F),
+    ConstantTerm(F),
+}
+#[derive(Default)]
+pub struct AstProgram<F> {
+    pub code: Vec<[u32; 4]>, // {op, arg, shift, 0}: 0 POLY 1 CONST 2 LINEAR 3 ADD 4 MUL 5 SCALE 6 NEG
+    pub consts: Vec<F>,
+}
+impl<F: PrimeField> AstProgram<F> {
+    fn konst(&mut self, v: F) -> u32 {
+        if let Some(i) = self.consts.iter().position(|c| *c == v) {
+            return i as u32;
+        }
+        self.consts.push(v);
+        (self.consts.len() - 1) as u32
+    }
+    /// `stride` = 1 in the Lagrange basis, 2^(extended_k - k) in the extended one (poly/domain.rs:286-295).
+    pub fn flatten(&mut self, ast: &AstView<'_, F>, stride: i32) {
+        match ast {
+            AstView::Poly { index, rotation } => self.code.push([0, *index as u32, (rotation * stride) as u32, 0]),
+            AstView::Add(a, b) => { self.flatten(a, stride); self.flatten(b, stride); self.code.push([3, 0, 0, 0]); }
+            AstView::Mul(a, b) => { self.flatten(a, stride); self.flatten(b, stride); self.code.push([4, 0, 0, 0]); }
+            AstView::Scale(a, s) => { self.flatten(a, stride); let c = self.konst(*s); self.code.push([5, c, 0, 0]); }
+            AstView::DistributePowers(terms, base) => {
+                // fold from zero: acc = acc * base + term (evaluator.rs:182-193)
+                let z = self.konst(F::ZERO);
+                self.code.push([1, z, 0, 0]);
+                for t in terms.iter() {
+                    let b = self.konst(*base);
+                    self.code.push([5, b, 0, 0]);
+                    self.flatten(t, stride);
+                    self.code.push([3, 0, 0, 0]);
+                }
+            }
+            AstView::LinearTerm(s) => { let c = self.konst(*s); self.code.push([2, c, 0, 0]); }
+            AstView::ConstantTerm(s) => { let c = self.konst(*s); self.code.push([1, c, 0, 0]); }
+        }
+    }
+}
+
 /// Bulk `C::from_bytes` for `Params::read` (poly/commitment.rs:183-205): `Err` where `C::read` would return `io::Error`.
 pub fn read_points<C: B200Curve>(bytes: &[u8]) -> std::io::Result<Vec<C>>
 where
