@@ -62,6 +62,8 @@ extern "C" {
     pub fn h2_batch_normalize(curve: c_int, points_xyz: *const c_void, n: usize, repr: c_int, out_xy: *mut c_void) -> c_int;
     pub fn h2_poly_eval_ast(out: u64, polys: *const u64, n_polys: usize, log_n: u32, code: *const u32, n_code: usize, consts: *const c_void,
                             n_consts: usize, omega: *const c_void, lin_base: *const c_void, repr: c_int) -> c_int;
+    pub fn h2_poly_batch_invert(poly: u64, n: usize) -> c_int;
+    pub fn h2_poly_running_product(dst: u64, src: u64, n: usize, init: *const c_void, repr: c_int) -> c_int;
     pub fn h2_poly_divide_by_vanishing(poly: u64, ext_k: u32, t_evals: *const c_void, t_len: u32, repr: c_int) -> c_int;
     pub fn h2_poly_eval(polys: *const u64, batch: usize, n: usize, points: *const c_void, repr: c_int, out: *mut c_void) -> c_int;
     pub fn h2_poly_inner_product(a: *const u64, b: *const u64, batch: usize, n: usize, repr: c_int, out: *mut c_void) -> c_int;

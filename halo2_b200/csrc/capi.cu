@@ -1411,6 +1411,56 @@ extern "C" int h2_poly_eval_ast(uint64_t out, const uint64_t *polys, size_t n_po
     if (o->field == H2_FIELD_FP) return ast_run<FpParams>(o, ps, log_n, prog, n_code, consts, n_consts, omega, lin_base, repr, has_linear);
     return ast_run<FqParams>(o, ps, log_n, prog, n_code, consts, n_consts, omega, lin_base, repr, has_linear);
 }
+// ff::BatchInvert on the first n elements of a resident polynomial, in place (zeros stay zero)
+extern "C" int h2_poly_batch_invert(uint64_t poly, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *a = find_poly(poly);
+    if (!a) return fail("h2_poly_batch_invert: unknown polynomial handle");
+    if (a->len < n) return fail("h2_poly_batch_invert: the polynomial holds fewer than n elements");
+    if (n == 0) return 0;
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) return 1;
+    const uint32_t nb = blocks_for((n + 15) / 16, 64);
+    if (a->field == H2_FIELD_FP) LAUNCH(poly_batch_invert_kernel<FpParams>, nb, 64, 0, s, a->buf.as<fe>(), (uint64_t)n);
+    else LAUNCH(poly_batch_invert_kernel<FqParams>, nb, 64, 0, s, a->buf.as<fe>(), (uint64_t)n);
+    return scratch_release(s);
+}
+// dst[0] = init, dst[i] = dst[i - 1] * src[i - 1] for i < n: the running product of plonk/permutation/prover.rs:150-156
+template <class P> static int grand_product_run(PolyBuf *d, PolyBuf *a, size_t n, const void *init, int repr) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    std::vector<uint64_t> m{(uint64_t)n}, off{0};
+    while (m.back() > H2_POLY_CHUNK) { off.push_back(off.back() + (m.size() > 1 ? m.back() : 0)); m.push_back((m.back() + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK); }
+    const size_t L = m.size() - 1;
+    uint64_t total = 1;
+    for (size_t l = 1; l <= L; l++) total += m[l];
+    if (scratch_acquire(s)) return 1;
+    if (X.po_lvl.ensure(total * sizeof(fe)) || X.po_q.ensure(total * sizeof(fe))) return 1;
+    fe *lvl = X.po_lvl.as<fe>(), *ex = X.po_q.as<fe>();
+    const fe *src = a->buf.as<fe>();
+    const fe in0 = host_to_mont<P>(init, repr);
+    for (size_t l = 0; l < L; l++)
+        LAUNCH(poly_product_up_kernel<P>, blocks_for(m[l + 1], 128), 128, 0, s, l == 0 ? src : (const fe *)(lvl + off[l]), m[l], lvl + off[l + 1], m[l + 1]);
+    for (size_t l = L + 1; l-- > 0;) {
+        const uint64_t chunks = (m[l] + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK;
+        LAUNCH(poly_product_down_kernel<P>, blocks_for(chunks, 128), 128, 0, s, l == 0 ? src : (const fe *)(lvl + off[l]), m[l],
+               l == L ? (const fe *)nullptr : (const fe *)(ex + off[l + 1]), in0, l == 0 ? d->buf.as<fe>() : ex + off[l], chunks);
+    }
+    return scratch_release(s);
+}
+extern "C" int h2_poly_running_product(uint64_t dst, uint64_t src, size_t n, const void *init, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *d = find_poly(dst), *a = find_poly(src);
+    if (!d || !a) return fail("h2_poly_running_product: unknown polynomial handle");
+    if (d == a) return fail("h2_poly_running_product: the product cannot overwrite its factors");
+    if (d->field != a->field) return fail("h2_poly_running_product: the polynomials live in different fields");
+    if (a->len < n || d->len < n) return fail("h2_poly_running_product: a polynomial holds fewer than n elements");
+    if (n == 0) return 0;
+    if (a->field == H2_FIELD_FP) return grand_product_run<FpParams>(d, a, n, init, repr);
+    return grand_product_run<FqParams>(d, a, n, init, repr);
+}
 // divide_by_vanishing_poly on a resident extended-domain polynomial; t_evals: t_len = 2^(ext_k - k) host elements
 extern "C" int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -68,6 +68,50 @@ template <class P> struct PolyOps {
     }
 };
 
+// The permutation argument's grand product (plonk/permutation/prover.rs:98-157; the lookup argument has the same shape,
+// plonk/lookup/prover.rs): `modified_values.batch_invert()` and the running product z[0] = last_z, z[i] = z[i-1] * mv[i-1].
+template <class P> struct GrandProduct {
+    // ff::BatchInvert in place: a[i] <- 1 / a[i], zeros stay zero.  Thread t owns 16 elements, one inversion (Montgomery's trick).
+    static H2_HD void invert_body(fe *a, uint64_t n, uint64_t t) {
+        const uint64_t lo = t * 16;
+        if (lo >= n) return;
+        const uint32_t m = (uint32_t)(n - lo < 16 ? n - lo : 16);
+        fe pre[16], v[16];
+        fe acc = fe_one<P>();
+        for (uint32_t i = 0; i < m; i++) {
+            v[i] = fe_load(a + lo + i);
+            pre[i] = acc;
+            if (!fe_is_zero(v[i])) acc = fe_mul<P>(acc, v[i]);
+        }
+        acc = fe_inv<P>(acc);
+        for (uint32_t i = m; i-- > 0;) {
+            if (fe_is_zero(v[i])) continue;
+            fe_store(a + lo + i, fe_mul<P>(acc, pre[i]));
+            acc = fe_mul<P>(acc, v[i]);
+        }
+    }
+    // upward level of the running product: out[t] = prod of chunk t of in (m values)
+    static H2_HD void up_body(const fe *in, uint64_t m, fe *out, uint64_t out_m, uint64_t t) {
+        if (t >= out_m) return;
+        const uint64_t lo = t * H2_POLY_CHUNK, hi = lo + H2_POLY_CHUNK < m ? lo + H2_POLY_CHUNK : m;
+        fe acc = fe_load(in + lo);
+        for (uint64_t i = lo + 1; i < hi; i++) acc = fe_mul<P>(acc, fe_load(in + i));
+        fe_store(out + t, acc);
+    }
+    // downward level: E[i] = carry_t * prod_{lo <= j < i} in[j] for i in chunk t (the exclusive running product), with
+    // carry_t = E_above[t] (or `init` at the top level, where there is one chunk).  `count` positions are written (level 0 writes
+    // n outputs from n - 1... inputs: the last input is never used, plonk/permutation/prover.rs:150-156).
+    static H2_HD void down_body(const fe *in, uint64_t m, const fe *carry_above, const fe &init, fe *out, uint64_t out_m, uint64_t t) {
+        if (t >= out_m) return;
+        const uint64_t lo = t * H2_POLY_CHUNK, hi = lo + H2_POLY_CHUNK < m ? lo + H2_POLY_CHUNK : m;
+        fe acc = carry_above ? fe_load(carry_above + t) : init;
+        for (uint64_t i = lo; i < hi; i++) {
+            fe_store(out + i, acc);
+            acc = fe_mul<P>(acc, fe_load(in + i));
+        }
+    }
+};
+
 // divide_by_vanishing_poly (poly/domain.rs:329-348): h[i] *= t_evaluations[i mod len], len = 2^(extended_k - k) inverses of
 // t(X) = X^n - 1 over the coset (domain.rs:86-128), Montgomery form
 template <class P> struct VanishDiv {
@@ -77,6 +121,16 @@ template <class P> struct VanishDiv {
 };
 
 #if defined(__CUDACC__)
+template <class P> __global__ void __launch_bounds__(64) poly_batch_invert_kernel(fe *a, uint64_t n) {
+    GrandProduct<P>::invert_body(a, n, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <class P> __global__ void __launch_bounds__(128) poly_product_up_kernel(const fe *in, uint64_t m, fe *out, uint64_t out_m) {
+    GrandProduct<P>::up_body(in, m, out, out_m, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <class P> __global__ void __launch_bounds__(128) poly_product_down_kernel(const fe *in, uint64_t m, const fe *carry_above, fe init, fe *out,
+                                                                                   uint64_t out_m) {
+    GrandProduct<P>::down_body(in, m, carry_above, init, out, out_m, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
 template <class P> __global__ void __launch_bounds__(256) poly_vanish_div_kernel(fe *a, uint64_t n, const fe *t, uint32_t t_mask) {
     VanishDiv<P>::body(a, n, t, t_mask, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }

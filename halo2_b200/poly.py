@@ -319,6 +319,20 @@ def kate_division_resident(src: Sequence["ResidentPoly"], points: Sequence[int],
     return list(dst)
 
 
+def batch_invert_resident(a: "ResidentPoly", n: Optional[int] = None) -> "ResidentPoly":
+    """`values.batch_invert()` (ff::BatchInvert) in place on a resident vector: zeros stay zero (plonk/permutation/prover.rs:120)."""
+    _l.check(_l.init().h2_poly_batch_invert(a._h, ctypes.c_size_t(a.len if n is None else int(n))))
+    return a
+
+
+def running_product_resident(src: "ResidentPoly", init: int = 1, dst: Optional["ResidentPoly"] = None, n: Optional[int] = None) -> "ResidentPoly":
+    """z[0] = init, z[i] = z[i-1] * src[i-1] (plonk/permutation/prover.rs:150-156), left on the device."""
+    n = src.len if n is None else int(n)
+    dst = ResidentPoly(src.field, n) if dst is None else dst
+    _l.check(_l.init().h2_poly_running_product(dst._h, src._h, ctypes.c_size_t(n), _l.ptr(_l.fe_bytes(int(init) % FIELDS[src.field])), _l.REPR_CANONICAL))
+    return dst
+
+
 class EvaluationDomain:
     """poly/domain.rs:20-146.  `zeta` is F::ZETA (domain.rs:85): pasta_curves' choice of cube root
     is not pinned by any in-tree golden, so the caller supplies it."""

@@ -147,6 +147,12 @@ int h2_poly_eval(const uint64_t *polys, size_t batch, size_t n, const void *poin
  * omega / lin_base may be NULL when the program has no LINEAR.  Asynchronous. */
 int h2_poly_eval_ast(uint64_t out, const uint64_t *polys, size_t n_polys, uint32_t log_n, const uint32_t *code, size_t n_code,
                      const void *consts, size_t n_consts, const void *omega, const void *lin_base, int repr);
+/* The permutation / lookup arguments' grand product (plonk/permutation/prover.rs:98-157) on resident polynomials:
+ * `modified_values.batch_invert()` (ff::BatchInvert: in place, zeros stay zero) ... */
+int h2_poly_batch_invert(uint64_t poly, size_t n);
+/* ... and the running product dst[0] = init (last_z), dst[i] = dst[i - 1] * src[i - 1], i < n (:150-156).  The elementwise
+ * numerators / denominators before it are Ast programs in the Lagrange basis (h2_poly_eval_ast).  Both asynchronous. */
+int h2_poly_running_product(uint64_t dst, uint64_t src, size_t n, const void *init, int repr);
 /* EvaluationDomain::divide_by_vanishing_poly (poly/domain.rs:329-348) in place on a resident extended-domain polynomial:
  * h[i] *= t_evals[i mod t_len]; t_evals = the domain's t_evaluations (domain.rs:86-128), t_len = 2^(ext_k - k).  Asynchronous. */
 int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr);

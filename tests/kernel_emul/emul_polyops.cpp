@@ -61,3 +61,35 @@ template <class P> static int run_polyops(int mode, const uint8_t *a_in, const u
 extern "C" int emu_polyops(int field, int mode, const uint8_t *a, const uint8_t *c, uint32_t batch, uint64_t n, const uint8_t *points, uint8_t *out) {
     return field == 0 ? run_polyops<FpParams>(mode, a, c, batch, n, points, out) : run_polyops<FqParams>(mode, a, c, batch, n, points, out);
 }
+
+// batch_invert in place (mode 0) / exclusive running product with `init` (mode 1: out[0] = init, out[i] = out[i-1] * a[i-1]), with
+// the level schedule of capi.cu's grand_product_run.  a: n canonical elements.
+template <class P> static int run_grand(int mode, const uint8_t *a_in, uint64_t n, const uint8_t *init, uint8_t *out) {
+    std::vector<fe> a(n);
+    for (uint64_t i = 0; i < n; i++) { memcpy(a[i].v, a_in + 32 * i, 32); a[i] = fe_to_mont<P>(a[i]); }
+    if (mode == 0) {
+        for (uint64_t t = 0; t * 16 < n; t++) GrandProduct<P>::invert_body(a.data(), n, t);
+        for (uint64_t i = 0; i < n; i++) { fe r = fe_from_mont<P>(a[i]); memcpy(out + 32 * i, r.v, 32); }
+        return 0;
+    }
+    fe in0; memcpy(in0.v, init, 32); in0 = fe_to_mont<P>(in0);
+    std::vector<uint64_t> m{n}, off{0};
+    while (m.back() > H2_POLY_CHUNK) { off.push_back(off.back() + (m.size() > 1 ? m.back() : 0)); m.push_back((m.back() + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK); }
+    const size_t L = m.size() - 1;
+    uint64_t total = 1;
+    for (size_t l = 1; l <= L; l++) total += m[l];
+    std::vector<fe> lvl(total), ex(total), o(n);
+    for (size_t l = 0; l < L; l++)
+        for (uint64_t t = 0; t < m[l + 1]; t++) GrandProduct<P>::up_body(l == 0 ? a.data() : lvl.data() + off[l], m[l], lvl.data() + off[l + 1], m[l + 1], t);
+    for (size_t l = L + 1; l-- > 0;) {
+        const uint64_t chunks = (m[l] + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK;
+        const fe *carry = l == L ? nullptr : ex.data() + off[l + 1];
+        for (uint64_t t = 0; t < chunks; t++)
+            GrandProduct<P>::down_body(l == 0 ? a.data() : lvl.data() + off[l], m[l], carry, in0, l == 0 ? o.data() : ex.data() + off[l], chunks, t);
+    }
+    for (uint64_t i = 0; i < n; i++) { fe r = fe_from_mont<P>(o[i]); memcpy(out + 32 * i, r.v, 32); }
+    return (int)L;
+}
+extern "C" int emu_grand_product(int field, int mode, const uint8_t *a, uint64_t n, const uint8_t *init, uint8_t *out) {
+    return field == 0 ? run_grand<FpParams>(mode, a, n, init, out) : run_grand<FqParams>(mode, a, n, init, out);
+}

@@ -529,3 +529,24 @@ def test_emul_ast_evaluator(emu, basis, j, k):
         emu.emu_ast_eval(cref.FIELD_ID[field], cref._p(pb), 4, log_n, code.ctypes.data_as(ctypes.c_void_p), code.shape[0], cref._p(cref.ints_to_bytes(consts)),
                          len(consts), cref._p(cref._fe(omega)), cref._p(cref._fe(lin)), cref._p(out))
         assert cref.bytes_to_ints(out) == pasta.ast_evaluate(d, basis, _ast_tuple(node), polys)
+
+
+# ---- the permutation argument's grand product: batch_invert and the running product (plonk/permutation/prover.rs:98-157) ----
+@pytest.mark.parametrize("field", ["fp", "fq"])
+@pytest.mark.parametrize("n", [1, 2, 16, 17, 32, 33, 1024, 1057])
+def test_emul_grand_product(emu, field, n):
+    m = pasta.FIELDS[field]
+    a = pasta.gen_scalars(field, 1100 + n, n)
+    if n > 3:
+        a[1] = 0                    # batch_invert leaves zeros alone; a zero factor zeroes the rest of the running product
+    ab = cref.ints_to_bytes(a)
+    out = np.zeros((n, 32), dtype=np.uint8)
+    emu.emu_grand_product(cref.FIELD_ID[field], 0, cref._p(ab), ctypes.c_uint64(n), None, cref._p(out))
+    assert cref.bytes_to_ints(out) == [pasta.inv(x, m) if x else 0 for x in a]
+    init = pasta.gen_scalars(field, 1101, 1)[0]
+    for vals in (a, [x or 5 for x in a]):
+        emu.emu_grand_product(cref.FIELD_ID[field], 1, cref._p(cref.ints_to_bytes(vals)), ctypes.c_uint64(n), cref._p(cref._fe(init)), cref._p(out))
+        z = [init]
+        for row in range(1, n):      # permutation/prover.rs:150-156
+            z.append(z[row - 1] * vals[row - 1] % m)
+        assert cref.bytes_to_ints(out) == z
