@@ -39,6 +39,19 @@ def test_no_cpu_fallback():
     a = np.zeros((4, 32), np.uint8)
     with pytest.raises(halo2_b200.H2Error):
         halo2_b200.best_fft(a, 1, 2, "fp")
+    # ... and so must everything either side of the two kernels
+    for call in (lambda: halo2_b200.lagrange_generators("vesta", 2, np.zeros((4, 64), np.uint8)),
+                 lambda: halo2_b200.best_fft_curve(np.zeros((4, 96), np.uint8), 1, 2, "vesta"),
+                 lambda: halo2_b200.batch_normalize(np.zeros((3, 96), np.uint8), "pallas"),
+                 lambda: halo2_b200.compress_points(np.zeros((3, 64), np.uint8), "pallas"),
+                 lambda: halo2_b200.decompress_points(np.zeros((3, 32), np.uint8), "vesta"),
+                 lambda: halo2_b200.eval_polynomial(a, 3, "fp"),
+                 lambda: halo2_b200.kate_division(a, 3, "fq"),
+                 lambda: halo2_b200.compute_inner_product(a, a, "fp"),
+                 lambda: halo2_b200.ResidentPoly("fp", 4),
+                 lambda: halo2_b200.small_multiexp(np.zeros((2, 32), np.uint8), np.zeros((2, 64), np.uint8), "vesta")):
+        with pytest.raises(halo2_b200.H2Error):
+            call()
 
 
 def test_product_does_not_import_oracle():
