@@ -45,6 +45,27 @@ def lagrange_generators(curve: str, k: int, g) -> np.ndarray:
     return out
 
 
+def hash_to_curve(curve: str, domain_prefix: str):
+    """C::CurveExt::hash_to_curve(domain_prefix) (call sites poly/commitment.rs:52,102; benches/hashtocurve.rs:15,18):
+    returns the closure message -> affine point (64 bytes, canonical; identity = zeros).  The closure also takes a LIST of
+    equal-length messages and hashes them in one launch -> (n, 64)."""
+    dom = domain_prefix.encode()
+
+    def hasher(message):
+        single = isinstance(message, (bytes, bytearray))
+        msgs = [bytes(message)] if single else [bytes(m) for m in message]
+        n = len(msgs)
+        ml = len(msgs[0]) if n else 0
+        assert all(len(m) == ml for m in msgs), "batched messages must have equal length"
+        buf = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if n * ml else None
+        out = np.zeros((n, 64), dtype=np.uint8)
+        _l.check(_l.init().h2_hash_to_curve(_l.CURVE_ID[curve], ctypes.c_char_p(dom), _l.ptr(buf), ctypes.c_size_t(ml), ctypes.c_size_t(n),
+                                            _l.REPR_CANONICAL, _l.ptr(out)))
+        return out[0] if single else out
+
+    return hasher
+
+
 def compress_points(points_xy, curve: str) -> np.ndarray:
     """C::to_bytes for a batch (book/src/background/curves.md:203-225): (n, 64) affine -> (n, 32) uint8."""
     p = _l.as_u8(points_xy, 64)
@@ -65,8 +86,8 @@ def decompress_points(data, curve: str) -> np.ndarray:
 class Params:
     """poly/commitment.rs:26-33.  g / g_lagrange / w are uploaded once and stay resident in HBM
     (they are immutable for the life of a Params); commit / commit_lagrange only ship the
-    polynomial.  Generator DERIVATION (Params::new's hash-to-curve, :38-114) is the caller's:
-    pass the generators in, e.g. as read by Params::read (:185-205)."""
+    polynomial.  Params.new(curve, k) is Params::new (:38-114) whole -- hash_to_curve generators and
+    g_lagrange derived on the device; Params.read (:185-205) / the constructor take existing generators."""
 
     def __init__(self, curve: str, k: int, g, g_lagrange, w, u=None, precompute: bool = True, window_bits: int = 0,
                  direct: Optional[bool] = None):
@@ -100,6 +121,19 @@ class Params:
         both = np.concatenate([self.g_lagrange, self.w])   # g_lagrange ++ [w]     (:146-147)
         _l.check(lib.h2_bases_register_ex(cid, _l.ptr(both), ctypes.c_size_t(self.n + 1), _l.REPR_CANONICAL,
                                           ctypes.c_uint32(window_bits), ctypes.c_uint32(flags), ctypes.byref(self._h_gl)))
+
+    @classmethod
+    def new(cls, curve: str, k: int, **kw) -> "Params":
+        """Params::new(k) (commitment.rs:38-114), whole, on the device (h2_params_new): the generators g[i], w, u from
+        hash_to_curve("Halo2-Parameters") (:46-58, :102-105), g_lagrange by EC-iFFT, * 2^-k, batch_normalize (:74-101)."""
+        assert k < 32  # commitment.rs:41
+        n = 1 << k
+        g = np.zeros((n, 64), dtype=np.uint8)
+        gl = np.zeros((n, 64), dtype=np.uint8)
+        w = np.zeros((1, 64), dtype=np.uint8)
+        u = np.zeros((1, 64), dtype=np.uint8)
+        _l.check(_l.init().h2_params_new(_l.CURVE_ID[curve], ctypes.c_uint32(k), _l.REPR_CANONICAL, _l.ptr(g), _l.ptr(gl), _l.ptr(w), _l.ptr(u)))
+        return cls(curve, k, g, gl, w, u, **kw)
 
     @classmethod
     def from_generators(cls, curve: str, k: int, g, w, u=None, **kw) -> "Params":

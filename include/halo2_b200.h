@@ -215,6 +215,16 @@ int h2_batch_normalize(int curve, const void *points_xyz, size_t n, int repr, vo
  * (2^k x 64 B) -> EC-iFFT with omega_inv (= alpha_inv, :77-80) -> * minv (= 2^-k, :83-89) -> batch_normalize (:91-101)
  * -> affine g_lagrange.  (hash_to_curve, :46-58, lives in the un-vendored pasta_curves: the generators are the caller's.) */
 int h2_params_lagrange(int curve, const void *g_xy, uint32_t k, const void *omega_inv, const void *minv, int repr, void *out_g_lagrange_xy);
+/* C::CurveExt::hash_to_curve(domain_prefix)(message) (call sites poly/commitment.rs:52,102; benches/hashtocurve.rs:15,18;
+ * the implementation is pasta_curves 0.5.1 src/hashtocurve.rs, un-vendored): the RFC 9380 suite
+ * "<curve>_XMD:BLAKE2b_SSWU_RO_" -- expand_message_xmd over BLAKE2b-512, simplified SWU onto the 3-isogenous curve
+ * y^2 = x^3 + A x + 1265 (Z = -13), sum of the two images, 3-isogeny back.  n messages of msg_len bytes each (stride
+ * msg_len) -> n affine points (64 B).  Pinned on the reference's golden commitments (tests/plonk_api.rs:958-982). */
+int h2_hash_to_curve(int curve, const char *domain_prefix, const void *messages, size_t msg_len, size_t n, int repr, void *out_xy);
+/* Params::new(k) whole (poly/commitment.rs:38-114): g[i] = H(0 || i as u32 LE) (:46-58), w = H([1]), u = H([2]) (:102-105)
+ * with H = hash_to_curve("Halo2-Parameters"), and g_lagrange = batch_normalize(2^-k * EC-iFFT(g)) (:74-101), all on the
+ * device.  Outputs: g and g_lagrange 2^k x 64 B, w and u 64 B each. */
+int h2_params_new(int curve, uint32_t k, int repr, void *out_g_xy, void *out_g_lagrange_xy, void *out_w_xy, void *out_u_xy);
 
 /* ---- point encoding: SURVEY.md section 8(f) row 4 (the wire format either side of the path) ----------------------- */
 /* C::to_bytes (book/src/background/curves.md:203-225): n affine points (64 B) -> n x 32 bytes, x little-endian with the LSB

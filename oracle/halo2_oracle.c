@@ -28,10 +28,10 @@
  * The reference is Rust-only and cannot be compiled in this image, so there is no
  * oracle/_ref; bench.py reports this library as cpu_baseline.kind = "port".
  *
- * PARITY PINNING: see oracle/pasta.py header.  best_multiexp/best_fft on synthetic inputs:
- * "parity unpinned" (no reference vector exists); this file and pasta.py are two independent
- * restatements that must agree (tests/test_oracle_*.py), and the field layer is pinned by the
- * halo2_poseidon known-answer vectors.
+ * PARITY PINNING: PINNED on reference-held vectors -- this library's EC-FFT (orc_params_lagrange) fed with the
+ * hash_to_curve generators and its threaded best_multiexp reproduce all 19 golden commitments of the plonk_api
+ * verifying key (tests/plonk_api.rs:958-982; tests/test_oracle_golden.py::test_golden_commitments_c_oracle); the field
+ * layer is pinned by the halo2_poseidon known-answer vectors.  See the oracle/pasta.py header for the full status.
  *
  * ABI: every element is canonical 32-byte little-endian; affine point = x||y (64 B),
  * identity = 64 zero bytes.  field: 0 = Fp, 1 = Fq.  curve: 0 = Pallas (coords Fp, scalars

@@ -10,7 +10,7 @@ What it restates (all file:line relative to /root/reference/halo2_proofs/src):
   * best_fft                 arithmetic.rs:192-255  (+ recursive_butterfly_arithmetic :258-295)
   * parallelize              arithmetic.rs:345-362  (chunking only; serial here)
   * Params::commit{,_lagrange}  poly/commitment.rs:119-150
-  * Params::new's EC-FFT      poly/commitment.rs:77-94   (generators are synthetic, see below)
+  * Params::new               poly/commitment.rs:38-114  (hash_to_curve restated from RFC 9380, see below)
   * EvaluationDomain::{new, lagrange_to_coeff, coeff_to_extended, extended_to_coeff,
     distribute_powers_zeta, ifft}   poly/domain.rs:40-146, 227-255, 303-325, 357-383
   * Evaluator::evaluate over an Ast              poly/evaluator.rs:129-228 (+ the BasisOps of :522-607)
@@ -25,15 +25,20 @@ halo2_proofs/tests/plonk_api.rs:591-592; Pallas/Vesta are y^2 = x^3 + 5 over Fp/
 (book/src/background/curves.md); identity is encoded as affine (0, 0)
 (book/src/background/curves.md:226-230).
 
-PARITY PINNING STATUS
-  pinned:   moduli, ROOT_OF_UNITY (via the k=5 / k=11 omegas in the reference goldens),
-            field mul/add/x^5 (halo2_poseidon test vectors), golden commitments lie on Vesta
-            -- see tests/golden/ and tests/test_oracle_golden.py.
-  UNPINNED: best_multiexp / best_fft on synthetic inputs -- the reference holds no
-            input->output vector for either and cannot be built here (no Rust toolchain,
-            pasta_curves not vendored).  "parity unpinned" for those; soundness rests on the
-            uniqueness of canonical encodings (any correct MSM/NTT yields the same bytes) and
-            on two independent restatements (this file and oracle/halo2_oracle.c) agreeing.
+PARITY PINNING STATUS: PINNED on reference-held vectors.
+  * moduli, ROOT_OF_UNITY (via the k=5 / k=11 omegas in the reference goldens), field mul/add/x^5
+    (halo2_poseidon test vectors), point decompression (26 golden points);
+  * best_multiexp + best_fft at G = curve point + hash_to_curve + ZETA + DELTA: all 19 golden
+    commitments of the plonk_api verifying key (tests/plonk_api.rs:958-982) are reproduced from
+    first principles -- Params::new(5) through hash_to_curve("Halo2-Parameters"), the EC-iFFT
+    (ec_fft below), and commit_lagrange = best_multiexp over g_lagrange ++ [w] -- by this file and
+    by oracle/halo2_oracle.c (tests/test_oracle_golden.py), and by the device path
+    (tests/test_gpu_golden.py);
+  * best_fft at G = scalar has no reference-held input->output vector of its own; it is the same
+    butterfly network as the pinned G = curve-point instantiation (one generic function,
+    arithmetic.rs:192-295), checked against the DFT definition for true roots of unity and, through
+    the domain constants it is used with, against the pinned omegas.
+  The reference itself cannot be built here (no Rust toolchain; pasta_curves un-vendored).
 """
 from __future__ import annotations
 
@@ -611,6 +616,31 @@ class Params:
         self.w = to_affine(curve, scalar_mul(curve, rng.field_element(r), g0))
         self.u = to_affine(curve, scalar_mul(curve, rng.field_element(r), g0))
 
+    @classmethod
+    def new(cls, curve: Curve, k: int) -> "Params":
+        """Params::new(k) proper (poly/commitment.rs:38-114): generators from hash_to_curve("Halo2-Parameters")."""
+        g, w, u = params_generators(curve, k)
+        return cls.from_generators(curve, k, g, w, u)
+
+    @classmethod
+    def from_generators(cls, curve: Curve, k: int, g: Sequence[Affine], w: Affine, u: Affine) -> "Params":
+        """commitment.rs:74-101 from given generators: g_lagrange = batch_normalize(2^-k * EC-iFFT(g))."""
+        assert k < 32 and len(g) == 1 << k
+        self = cls.__new__(cls)
+        self.curve, self.k, self.n = curve, k, 1 << k
+        self.g = list(g)
+        r = curve.r
+        alpha_inv = inv(root_of_unity(curve.scalar), r)
+        for _ in range(k, S_2ADICITY):
+            alpha_inv = alpha_inv * alpha_inv % r
+        gl = [to_jac(pt) for pt in g]
+        ec_fft(curve, gl, alpha_inv, k)
+        minv = pow(inv(2, r), k, r)
+        gl = [scalar_mul(curve, minv, to_affine(curve, pt)) for pt in gl]
+        self.g_lagrange = batch_normalize(curve, gl)
+        self.w, self.u = w, u
+        return self
+
     def commit(self, poly: Sequence[int], blind: int) -> Jac:
         """commitment.rs:119-130."""
         return best_multiexp(self.curve, list(poly) + [blind], list(self.g) + [self.w])
@@ -853,3 +883,173 @@ def ipa_rounds(c: Curve, g: Sequence[Affine], w: Affine, u: Affine, p_prime: Seq
         f_delta = (f_delta + l_rand[j] * u_inv + r_rand[j] * u_j) % r
     assert len(p_prime) == 1
     return ls, rs, p_prime[0], f_delta
+
+
+# --------------------------------------------------------------------------------------
+# hash_to_curve -- C::CurveExt::hash_to_curve(domain_prefix)(message), the call at
+# poly/commitment.rs:52,102.  The implementation lives in the un-vendored crate
+# pasta_curves 0.5.1 (src/hashtocurve.rs, src/curves.rs); it is the hash-to-curve suite
+# "<curve>_XMD:BLAKE2b_SSWU_RO_" of the IETF hash-to-curve specification (RFC 9380):
+#   hash_to_field   = expand_message_xmd (section 5.3.1) with BLAKE2b-512 (block 128 B, all-zero
+#                     personalisation), DST = domain_prefix || "-" || curve_id || "_XMD:BLAKE2b_SSWU_RO_",
+#                     two 64-byte chunks, each read big-endian and reduced mod the base field;
+#   map_to_curve    = simplified SWU (section 6.6.2) onto the curve iso-<curve>: y^2 = x^3 + A x + 1265
+#                     that is 3-isogenous to y^2 = x^3 + 5, with Z = -13 and sgn0 = parity;
+#   the two images are ADDED on the iso curve, then mapped through the 3-isogeny (section 6.6.3).
+# Constants are not copied from anywhere: the iso curve is the codomain of Velu's 3-isogeny from
+# y^2 = x^3 + 5 with kernel x0, x0^3 = -20 (giving A = -30 x0^2, B = 5 + 7*180 = 1265), and the isogeny
+# back is its dual (x-leading coefficient 1/9), both derived below.  Which of the three cube roots
+# pasta uses is fixed by `ISO_A`; the whole construction is PINNED by the reference's golden
+# commitments (tests/plonk_api.rs:958-982: fixed_commitments[2] is an all-zero column committed with
+# Blind::default() = 1, i.e. the point w = hasher(&[1]); the other entries are MSMs over g_lagrange,
+# i.e. over all 32 hashed generators) -- tests/test_oracle_golden.py.
+# --------------------------------------------------------------------------------------
+ISO_A = {
+    "pallas": 0x18354A2EB0EA8C9C49BE2D7258370742B74134581A27A59F92BB4B0B657A014B,
+    "vesta": 0x267F9B2EE592271A81639C4D96F787739673928C7D01B212C515AD7242EAA6B1,
+}
+ISO_B = 1265
+SWU_Z = -13
+
+
+def _cube_roots(a: int, m: int) -> List[int]:
+    """All cube roots of a modulo a prime m = 1 (mod 3), m - 1 = 3^s t."""
+    a %= m
+    if pow(a, (m - 1) // 3, m) != 1:
+        return []
+    s, t = 0, m - 1
+    while t % 3 == 0:
+        s, t = s + 1, t // 3
+    e, mult = ((t + 1) // 3, 1) if t % 3 == 2 else ((2 * t + 1) // 3, 2)
+    r = pow(a, e, m)              # r^3 = a * a^(mult t)
+    b = pow(a, mult * t, m)       # in the 3-Sylow subgroup, a cube there
+    z = pow(MULT_GEN, t, m)       # generates the 3-Sylow subgroup (order 3^s)
+    z3, zz, j = z * z * z % m, 1, 0
+    while zz != b:                # b = z^(3j); s is tiny for both Pasta fields
+        zz, j = zz * z3 % m, j + 1
+        assert j < 3 ** s
+    r = r * pow(z, 3 ** s - j, m) % m
+    assert pow(r, 3, m) == a
+    g = pow(MULT_GEN, (m - 1) // 3, m)
+    return [r, r * g % m, r * g * g % m]
+
+
+_ISO_CACHE: dict = {}
+
+
+def iso_constants(c: Curve) -> dict:
+    """Derive iso-<curve> and the 3-isogeny iso-<curve> -> <curve> from first principles.
+
+    E: y^2 = x^3 + 5.  psi_3(E) = 3x(x^3 + 20): the kernels of the 3-isogenies with j != 0 codomain are
+    {O, (x0, +-y0)} with x0^3 = -20 (y0^2 = -15; only y0^2 enters).  Velu: t = 6 x0^2, u = 4 y0^2 = -60,
+    w = u + x0 t = -180, codomain y^2 = x^3 - 5t x + (5 - 7w) = x^3 - 30 x0^2 x + 1265.
+    The dual isogeny has kernel phi(E[3]) = {O, (xk, .)} with xk = phi_x(0) = -t/x0 + u/x0^2; Velu from the iso
+    curve with that kernel lands on y^2 = x^3 + 3^6 * 5, and (x/9, y/27) brings it to E:
+        x' = (x + T/(x - xk) + U/(x - xk)^2) / 9,     y' = y (1 - T/(x - xk)^2 - 2U/(x - xk)^3) / 27.
+    """
+    if c.name in _ISO_CACHE:
+        return _ISO_CACHE[c.name]
+    m = c.p
+    A = ISO_A[c.name]
+    x0 = [x for x in _cube_roots(-20, m) if (-30 * x * x) % m == A]
+    assert len(x0) == 1, "ISO_A is not a Velu codomain of y^2 = x^3 + 5"
+    x0 = x0[0]
+    t, u = 6 * x0 * x0 % m, (-60) % m
+    xk = (-t * inv(x0, m) + u * inv(x0 * x0 % m, m)) % m
+    T = (6 * xk * xk + 2 * A) % m
+    U = 4 * (xk * xk * xk + A * xk + ISO_B) % m
+    W = (U + xk * T) % m
+    assert (A - 5 * T) % m == 0 and (ISO_B - 7 * W) % m == 729 * CURVE_B % m, "dual isogeny does not land on E"
+    k = {"A": A, "B": ISO_B, "xk": xk, "T": T, "U": U, "Z": SWU_Z % m}
+    _ISO_CACHE[c.name] = k
+    return k
+
+
+def hash_to_field(c: Curve, domain_prefix: str, message: bytes) -> Tuple[int, int]:
+    """RFC 9380 section 5.2/5.3.1 for m = 1, count = 2, L = 64, H = BLAKE2b-512 (r_in_bytes = 128)."""
+    import hashlib
+    dst = domain_prefix.encode() + b"-" + c.name.encode() + b"_XMD:BLAKE2b_SSWU_RO_"
+    assert len(dst) < 256
+    dst_prime = dst + bytes([len(dst)])
+    h = lambda data: hashlib.blake2b(data, digest_size=64).digest()
+    b0 = h(bytes(128) + message + bytes([0, 128, 0]) + dst_prime)
+    b1 = h(b0 + b"\x01" + dst_prime)
+    b2 = h(bytes(x ^ y for x, y in zip(b0, b1)) + b"\x02" + dst_prime)
+    return int.from_bytes(b1, "big") % c.p, int.from_bytes(b2, "big") % c.p
+
+
+def map_to_curve_simple_swu(c: Curve, u: int) -> Optional[Tuple[int, int]]:
+    """RFC 9380 section 6.6.2 onto iso-<curve> (affine result; never the identity)."""
+    m = c.p
+    k = iso_constants(c)
+    A, B, Z = k["A"], k["B"], k["Z"]
+    zu2 = Z * u * u % m
+    ta = (zu2 * zu2 + zu2) % m
+    tv1 = inv(ta, m) if ta else 0                       # inv0
+    x1 = (-B * inv(A, m)) % m * (1 + tv1) % m
+    if tv1 == 0:
+        x1 = B * inv(Z * A % m, m) % m
+    gx1 = (x1 * x1 * x1 + A * x1 + B) % m
+    y1 = fe_sqrt(c.base, gx1)
+    if y1 is not None:
+        x, y = x1, y1
+    else:
+        x = zu2 * x1 % m
+        y = fe_sqrt(c.base, (x * x * x + A * x + B) % m)
+        assert y is not None
+    if (u & 1) != (y & 1):                              # sgn0(u) == sgn0(y)
+        y = (m - y) % m
+    return x, y
+
+
+def _iso_add(c: Curve, a: Optional[Tuple[int, int]], b: Optional[Tuple[int, int]]) -> Optional[Tuple[int, int]]:
+    """Affine addition on iso-<curve> (y^2 = x^3 + A x + B, A != 0)."""
+    m = c.p
+    if a is None:
+        return b
+    if b is None:
+        return a
+    (x1, y1), (x2, y2) = a, b
+    if x1 == x2:
+        if (y1 + y2) % m == 0:
+            return None
+        lam = (3 * x1 * x1 + iso_constants(c)["A"]) * inv(2 * y1 % m, m) % m
+    else:
+        lam = (y2 - y1) * inv((x2 - x1) % m, m) % m
+    x3 = (lam * lam - x1 - x2) % m
+    return x3, (lam * (x1 - x3) - y1) % m
+
+
+def iso_map(c: Curve, pt: Optional[Tuple[int, int]]) -> Affine:
+    """The 3-isogeny iso-<curve> -> <curve> (RFC 9380 section 6.6.3; kernel points go to the identity)."""
+    if pt is None:
+        return None
+    m = c.p
+    k = iso_constants(c)
+    x, y = pt
+    d = (x - k["xk"]) % m
+    if d == 0:
+        return None
+    di = inv(d, m)
+    di2 = di * di % m
+    xo = (x + k["T"] * di + k["U"] * di2) % m * inv(9, m) % m
+    yo = y * ((1 - k["T"] * di2 - 2 * k["U"] * di2 % m * di) % m) % m * inv(27, m) % m
+    return xo, yo
+
+
+def hash_to_curve(c: Curve, domain_prefix: str):
+    """C::CurveExt::hash_to_curve(domain_prefix) -> closure over the message (poly/commitment.rs:52,102)."""
+    def hasher(message: bytes) -> Affine:
+        u0, u1 = hash_to_field(c, domain_prefix, message)
+        r = _iso_add(c, map_to_curve_simple_swu(c, u0), map_to_curve_simple_swu(c, u1))
+        out = iso_map(c, r)
+        assert on_curve(c, out)
+        return out
+    return hasher
+
+
+def params_generators(c: Curve, k: int) -> Tuple[List[Affine], Affine, Affine]:
+    """(g, w, u) of Params::new(k): poly/commitment.rs:46-58 (message = 0 || i as u32 LE) and :102-105."""
+    hasher = hash_to_curve(c, "Halo2-Parameters")
+    g = [hasher(b"\0" + i.to_bytes(4, "little")) for i in range(1 << k)]
+    return g, hasher(b"\x01"), hasher(b"\x02")

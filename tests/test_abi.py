@@ -43,6 +43,8 @@ def test_no_cpu_fallback():
     for call in (lambda: halo2_b200.lagrange_generators("vesta", 2, np.zeros((4, 64), np.uint8)),
                  lambda: halo2_b200.best_fft_curve(np.zeros((4, 96), np.uint8), 1, 2, "vesta"),
                  lambda: halo2_b200.batch_normalize(np.zeros((3, 96), np.uint8), "pallas"),
+                 lambda: halo2_b200.hash_to_curve("pallas", "Halo2-Parameters")(b"\x01"),
+                 lambda: halo2_b200.Params.new("vesta", 2),
                  lambda: halo2_b200.compress_points(np.zeros((3, 64), np.uint8), "pallas"),
                  lambda: halo2_b200.decompress_points(np.zeros((3, 32), np.uint8), "vesta"),
                  lambda: halo2_b200.eval_polynomial(a, 3, "fp"),

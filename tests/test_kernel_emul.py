@@ -550,3 +550,35 @@ def test_emul_grand_product(emu, field, n):
         for row in range(1, n):      # permutation/prover.rs:150-156
             z.append(z[row - 1] * vals[row - 1] % m)
         assert cref.bytes_to_ints(out) == z
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_hash_to_curve(emu, curve):
+    """h2c.cuh on the host: BLAKE2b core vs hashlib, expand_message_xmd / SWU / isogeny vs the oracle (itself pinned on the
+    reference's golden commitments, tests/test_oracle_golden.py), generator messages of Params::new."""
+    import hashlib
+    import random
+    rnd = random.Random(5)
+    for ln in (0, 1, 5, 63, 64, 127, 128, 129, 180, 255, 256, 257, 1000):
+        d = bytes(rnd.getrandbits(8) for _ in range(ln))
+        out = (ctypes.c_uint8 * 64)()
+        emu.emu_blake2b(d, ln, out)
+        assert bytes(out) == hashlib.blake2b(d).digest()
+    c = pasta.CURVES[curve]
+    n = 12
+    out = np.zeros((n, 64), dtype=np.uint8)
+    assert emu.emu_hash_to_curve(cref.CURVE_ID[curve], b"Halo2-Parameters", None, 0, 1, ctypes.c_uint64(3), ctypes.c_uint64(n), cref._p(out)) == 0
+    g, w, u = pasta.params_generators(c, 4)
+    assert [cref.bytes_to_affine(o) for o in out] == g[3:3 + n]
+    msgs = np.frombuffer(b"\x01\x02", dtype=np.uint8).copy()
+    out = np.zeros((2, 64), dtype=np.uint8)
+    assert emu.emu_hash_to_curve(cref.CURVE_ID[curve], b"Halo2-Parameters", cref._p(msgs), 1, 0, ctypes.c_uint64(0), ctypes.c_uint64(2), cref._p(out)) == 0
+    assert [cref.bytes_to_affine(o) for o in out] == [w, u]
+    h = pasta.hash_to_curve(c, "z.cash:test")
+    for ml in (0, 44, 84, 85, 200):
+        ms = [bytes(rnd.getrandbits(8) for _ in range(ml)) for _ in range(2)]
+        buf = np.frombuffer(b"".join(ms) or b"\0", dtype=np.uint8).copy()
+        out = np.zeros((2, 64), dtype=np.uint8)
+        assert emu.emu_hash_to_curve(cref.CURVE_ID[curve], b"z.cash:test", cref._p(buf), ml, 0, ctypes.c_uint64(0), ctypes.c_uint64(2), cref._p(out)) == 0
+        assert [cref.bytes_to_affine(o) for o in out] == [h(m) for m in ms]
+    assert emu.emu_hash_to_curve(cref.CURVE_ID[curve], b"p" * 250, None, 0, 1, ctypes.c_uint64(0), ctypes.c_uint64(1), cref._p(out)) == 1

@@ -105,3 +105,71 @@ def test_point_compression_on_golden_commitments(goldens):
     assert pasta.params_from_bytes(c, data) == (2, po.g, po.g_lagrange, po.w, po.u)
     with pytest.raises(ValueError):
         pasta.params_from_bytes(c, data[:-1])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hash_to_curve -> Params::new -> commit_lagrange, pinned on the reference's golden commitments.
+# Every one of the 19 points at tests/plonk_api.rs:958-982 is commit_lagrange(column, Blind::default()) over
+# Params::<EqAffine>::new(5): fixed_commitments[0] is an all-zero column, i.e. the point w = hash_to_curve(..)(&[1]);
+# the others are MSMs over g_lagrange = 2^-5 * EC-iFFT(32 hashed generators) -- so they pin hash_to_curve, the EC-FFT
+# (best_fft at G = curve point) and best_multiexp together.  tests/plonk_api_circuit.py rebuilds the columns.
+# ------------------------------------------------------------------------------------------------------------------
+FP_ZETA_INDEX = 1          # which primitive cube root pasta calls Fp::ZETA -- pinned by fixed_commitments[6]
+
+
+def golden_columns(goldens):
+    from tests import plonk_api_circuit as circ
+    vk = goldens["vk_plonk_api_k5"]
+    m = pasta.P_MOD
+    omega = int(vk["omega"], 16)
+    delta = pow(pasta.MULT_GEN, 1 << pasta.S_2ADICITY, m)     # F::DELTA = g^(2^S) (plonk/permutation/keygen.rs:131)
+    cols = circ.fixed_columns(m, pasta.zeta_candidates("fp")[FP_ZETA_INDEX]) + circ.permutation_columns(m, omega, delta)
+    want = [(int(x, 16), int(y, 16)) for x, y in vk["fixed_commitments"] + vk["permutation_commitments"]]
+    assert len(cols) == len(want) == 19
+    return cols, want
+
+
+def test_hash_to_curve_w_is_golden(goldens):
+    vk = goldens["vk_plonk_api_k5"]
+    h = pasta.hash_to_curve(pasta.VESTA, "Halo2-Parameters")
+    w = h(b"\x01")
+    assert w == (int(vk["fixed_commitments"][0][0], 16), int(vk["fixed_commitments"][0][1], 16))
+    # the same point is the all-zero column's commitment of the k = 11 verifying key
+    assert [hex(w[0]), hex(w[1])] in [[hex(int(a, 16)), hex(int(b, 16))]
+                                      for a, b in goldens["vk_lookup_range_check_k11"]["fixed_commitments"]]
+    # the iso curves and the isogeny are what Velu's formulas say, on both curves; outputs lie on the curve
+    for c in (pasta.PALLAS, pasta.VESTA):
+        k = pasta.iso_constants(c)
+        assert k["B"] == 1265 and (k["A"] * k["A"] * k["A"] * 4 + 27 * 1265 * 1265) % c.p != 0
+        hc = pasta.hash_to_curve(c, "z.cash:test")          # benches/hashtocurve.rs:15,18
+        for msg in (b"", b"Trans rights now!", bytes(range(200))):
+            pt = hc(msg)
+            assert pt is not None and pasta.on_curve(c, pt)
+            assert pasta.jac_eq(c, pasta.scalar_mul(c, c.r, pt), pasta.JAC_ID)
+
+
+def test_golden_commitments_python_oracle(goldens):
+    """All 19 golden commitments through oracle/pasta.py: hash_to_curve, ec_fft, best_multiexp."""
+    cols, want = golden_columns(goldens)
+    prm = pasta.Params.new(pasta.VESTA, 5)
+    for col, pt in zip(cols, want):
+        assert pasta.to_affine(pasta.VESTA, prm.commit_lagrange(col, 1)) == pt
+    # the other ZETA would not do: the lookup-table column contains a = 2834758237 * ZETA
+    from tests import plonk_api_circuit as circ
+    other = circ.fixed_columns(pasta.P_MOD, pasta.zeta_candidates("fp")[1 - FP_ZETA_INDEX])[6]
+    assert pasta.to_affine(pasta.VESTA, prm.commit_lagrange(other, 1)) != want[6]
+
+
+def test_golden_commitments_c_oracle(goldens):
+    """The same 19 points through oracle/halo2_oracle.c (the timed CPU baseline): its EC-FFT from the hashed generators
+    and its threaded best_multiexp."""
+    cols, want = golden_columns(goldens)
+    c = pasta.VESTA
+    g, w, _u = pasta.params_generators(c, 5)
+    r = c.r
+    alpha_inv = pasta.inv(pasta.omega_for_k(c.scalar, 5), r)
+    gl = cref.params_lagrange("vesta", cref.affines_to_bytes(g), 5, alpha_inv, pow(pasta.inv(2, r), 5, r))
+    bases = np.concatenate([gl, cref.affines_to_bytes([w])])
+    for col, pt in zip(cols, want):
+        out = cref.best_multiexp("vesta", cref.ints_to_bytes(list(col) + [1]), bases)
+        assert cref.bytes_to_affine(out) == pt          # cref.best_multiexp returns the affine canonical bytes
