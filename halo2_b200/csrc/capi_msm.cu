@@ -1,0 +1,701 @@
+// C ABI of the engine, part 2 of 5: the MSM pipeline (msm.cuh, fixedbase.cuh), resident base sets, the IPA round loop (ipa.cuh).
+#define H2_MSM_QUAD_ACCUM_REFS (1ull << 20)   // up to this many references the accumulation runs one quad per work item
+#include "util_kernels.cuh"
+#include "msm.cuh"
+#include "ipa.cuh"
+#include "ntt.cuh"
+#include "ecfft.cuh"
+#include "fixedbase.cuh"
+static_assert(H2_FB_BITS == H2_FB_BITS_CTX, "ctx.cuh: fixed_table");
+
+
+// ------------------------------------------------------------------------------------------------
+// MSM pipeline
+// ------------------------------------------------------------------------------------------------
+static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s, const uint32_t *only_if = nullptr) {
+    const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
+    uint32_t nb = (uint32_t)((n + per_block - 1) / per_block);
+    if (g_ctx.scan_blocks.ensure((size_t)nb * 4 + 16)) return 1;
+    uint32_t *bs = g_ctx.scan_blocks.as<uint32_t>();
+    LAUNCH(scan_block_sums_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs, only_if);
+    LAUNCH(scan_single_block_kernel, 1, H2_SCAN_BLOCK, 0, s, bs, nb, only_if);
+    LAUNCH(scan_apply_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs, only_if);
+    return 0;
+}
+
+// Arrival of the inputs of a one-shot MSM in `k` chunks (events on the copy stream): chunk j = points
+// [chunk_first(n, k, j), chunk_first(n, k, j + 1)).  The chunks GROW: nothing can run before the first chunk has
+// landed, so it is small (1/16 - 1/4 of the points), and the accumulation of chunk j hides the upload of the larger
+// chunk j + 1 -- the link stays busy from t = 0 and the GPU from the first chunk's arrival.  (Equal chunks left the
+// GPU idle for 1/k of the upload time: 2^20 pairs, 96 MiB at ~50 GB/s, 2 chunks: 0.95 of 4.57 ms.)
+static inline size_t chunk_first(size_t n, uint32_t k, uint32_t j) {
+    static const uint32_t cut[H2_MAX_UPLOAD_CHUNKS + 1][H2_MAX_UPLOAD_CHUNKS + 1] = {
+        {0, 16, 16, 16, 16}, {0, 16, 16, 16, 16}, {0, 4, 16, 16, 16}, {0, 2, 8, 16, 16}, {0, 1, 4, 10, 16}};   // sixteenths
+    if (k > H2_MAX_UPLOAD_CHUNKS) k = H2_MAX_UPLOAD_CHUNKS;
+    if (j >= k) return n;
+    return (size_t)((unsigned __int128)n * cut[k][j] / 16);
+}
+
+// A fixed-base MSM over resident bases is launched with the same parameters call after call: the second call with a given
+// key is captured into a CUDA graph, later ones replay it.
+static int msm_issue_or_replay(const std::function<int()> &issue, bool graphable, const void *d_scalars, const void *d_bases, const void *d_out,
+                               size_t n, uint64_t stride, uint32_t c, uint32_t sets, int scalars_mont, int out_canonical, cudaStream_t s) {
+    Context &X = g_ctx;
+    if (!(graphable && X.graphs_on && !g_prof_on)) return issue();
+    MsmGraph *ge = nullptr;
+    for (auto &e : X.graphs)
+        if (e.scalars == d_scalars && e.bases == d_bases && e.out == d_out && e.n == n && e.stride == stride && e.c == c && e.sets == sets &&
+            e.scalars_mont == scalars_mont && e.out_canonical == out_canonical) { ge = &e; break; }
+    if (ge && ge->gen != g_alloc_gen) {   // some buffer moved since the capture
+        if (ge->exec) cudaGraphExecDestroy(ge->exec);
+        ge->exec = nullptr; ge->seen = 0; ge->gen = g_alloc_gen;
+    }
+    if (!ge) {
+        if (X.graphs.size() >= 16) {   // evict the least recently used entry
+            size_t v = 0;
+            for (size_t i = 1; i < X.graphs.size(); i++) if (X.graphs[i].stamp < X.graphs[v].stamp) v = i;
+            if (X.graphs[v].exec) cudaGraphExecDestroy(X.graphs[v].exec);
+            X.graphs.erase(X.graphs.begin() + v);
+        }
+        MsmGraph e;
+        e.scalars = d_scalars; e.bases = d_bases; e.out = d_out; e.n = n; e.stride = stride; e.gen = g_alloc_gen; e.c = c; e.sets = sets;
+        e.scalars_mont = scalars_mont; e.out_canonical = out_canonical;
+        X.graphs.push_back(e);
+        ge = &X.graphs.back();
+    }
+    ge->stamp = ++X.graph_stamp;
+    if (ge->exec) {
+        CU(cudaGraphLaunch(ge->exec, s));
+        g_launches.fetch_add(ge->launches, std::memory_order_relaxed);
+        return 0;
+    }
+    if (ge->seen++ == 0) return issue();     // first sighting: run eagerly (the buffers may still be growing)
+    const uint64_t l0 = g_launches.load();
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return issue(); }
+    int rc = issue();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ge->seen = 0;
+        return rc ? rc : issue();            // capture refused: run eagerly
+    }
+    ge->launches = g_launches.load() - l0;
+    ce = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { ge->exec = nullptr; cudaGetLastError(); return issue(); }
+    CU(cudaGraphLaunch(ge->exec, s));
+    return 0;
+}
+
+// fixed != 0: d_bases is a window table (stride points per window) built with window size c.
+// bc != nullptr: the bases arrive chunk by chunk while this runs.  Each chunk is then sorted and accumulated on its own
+// (own bins, work items and bucket sums) as soon as it has landed, and the bucket reduce adds the per-chunk bucket sums:
+// the upload of all but the first chunk hides behind the accumulation.
+template <class P, class PS>
+static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, uint32_t fixed, uint64_t stride,
+                   jacobian *d_out, int out_canonical, cudaStream_t s, const BasesChunks *bc = nullptr, uint32_t sets = 1) {
+    Context &X = g_ctx;
+    if (n == 0) {   // empty sum = identity
+        jacobian id;
+        id.x = fe_zero(); id.y = out_canonical ? fe_zero() : fe_one<P>(); id.z = fe_zero();
+        if (out_canonical) id.y.v[0] = 1;
+        CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        return 0;
+    }
+    std::function<int()> issue;
+    if (fixed == 2) {   // direct sum over the digit-multiples table (fixedbase.cuh): accumulate + reduce tree
+        FbPlan fp;
+        fp.total = n; fp.sets = sets ? sets : 1u; fp.split = fb_split(n, fp.sets); fp.scalars_mont = scalars_mont ? 1u : 0u;
+        const uint64_t count0 = n * fp.split;
+        if (X.fb_a.ensure(fp.sets * count0 * sizeof(xyzz)) || X.fb_b.ensure(fp.sets * fb_ctas(count0, fb_fan(count0)) * sizeof(xyzz))) return 1;
+        issue = [&X, fp, count0, d_scalars, d_bases, d_out, out_canonical, s]() -> int {
+            auto k_acc = fb_accum_kernel<P, PS>;
+            auto k_red = fb_reduce_kernel<P, PS>;
+            xyzz *a = X.fb_a.as<xyzz>(), *b = X.fb_b.as<xyzz>();
+            prof_begin(PROF_MSM_ACCUM0, s);
+            LAUNCH(k_acc, blocks_for(fp.sets * count0, 128), 128, 0, s, fp, d_scalars, d_bases, a);
+            prof_end(s);
+            uint64_t count = count0, in_stride = count0;
+            for (;;) {
+                const uint32_t f = fb_fan(count);
+                const uint64_t ctas = fb_ctas(count, f);
+                LAUNCH(k_red, dim3((unsigned)ctas, fp.sets), 4 * H2_FB_QUADS, 0, s, (const xyzz *)a, count, in_stride, f, b, ctas,
+                       ctas == 1 ? d_out : (jacobian *)nullptr, (uint32_t)out_canonical);
+                if (ctas == 1) break;
+                xyzz *t = a; a = b; b = t;
+                count = ctas; in_stride = ctas;
+            }
+            return 0;
+        };
+        return msm_issue_or_replay(issue, !bc, d_scalars, d_bases, d_out, n, stride, H2_FB_BITS, fp.sets, scalars_mont, out_canonical, s);
+    }
+    const uint32_t glv = (!fixed && X.glv_on && n < (1ull << 30)) ? 1u : 0u;
+    if (c == 0) c = X.window_override ? X.window_override : msm_default_window(n, glv);
+    if (c > 24) return fail("msm: window bits > 24");
+    const uint32_t K = (bc && !fixed && bc->k > 1) ? bc->k : 1u;
+    const uint32_t force_cap = X.sort_bins ? 0u : H2_MSM_NO_BINS;
+    MsmPlan p;                       // the whole problem: bucket reduce and window combine
+    msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets, force_cap);
+    p.chunks = K;
+    MsmPlan pk[H2_MAX_UPLOAD_CHUNKS];   // one chunk of points: sort, work items, accumulation
+    size_t first[H2_MAX_UPLOAD_CHUNKS + 1];
+    for (uint32_t j = 0; j <= K; j++) first[j] = chunk_first(n, K, j);
+    uint64_t ref_space = 0, max_items = 0, part_total = 0;
+    uint32_t t_max = 0;
+    for (uint32_t j = 0; j < K; j++) {
+        if (K == 1) pk[0] = p;
+        else msm_make_plan(pk[j], first[j + 1] - first[j], c, 0, 0, fixed, stride, glv, sets, force_cap);
+        if (pk[j].ref_space >= (1ull << 32)) return fail("msm: n * windows exceeds 2^32 references");
+        ref_space = pk[j].ref_space > ref_space ? pk[j].ref_space : ref_space;
+        max_items = pk[j].max_items > max_items ? pk[j].max_items : max_items;
+        part_total = pk[j].part_total > part_total ? pk[j].part_total : part_total;
+        t_max = pk[j].T > t_max ? pk[j].T : t_max;
+    }
+    if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 32))) return 1;
+    if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
+    if (p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
+    if (scalars_mont && X.scal_canon.ensure(n * p.sets * sizeof(fe))) return 1;
+    const size_t small_words = 2 * (t_max + 2) + 8;   // size_hist (T + 2) | size_cursor (T + 1) | flags
+    part_total += 1;
+    if (X.counts.ensure(K * (p.G + 1) * 4) || X.cursor.ensure(K * 2 * p.G * 4) || X.refs.ensure(K * ref_space * 4) ||
+        X.size_hist.ensure(K * small_words * 4) || X.items.ensure(K * max_items * sizeof(uint2)) ||
+        X.bucket_sum.ensure(K * p.G * sizeof(xyzz)) || X.pkey.ensure(K * part_total * 4) || X.pstart.ensure(K * part_total * 4) ||
+        X.pend.ensure(K * part_total * 4) || X.ppt.ensure(K * part_total * sizeof(xyzz)) ||
+        X.ra_t.ensure((size_t)p.Wb * p.m1 * sizeof(xyzz)) || X.ra_e.ensure((size_t)p.Wb * p.m1 * sizeof(xyzz)) ||
+        X.r0.ensure((size_t)p.Wb * p.nb0 * H2_R0_ROWS * sizeof(xyzz)) || X.r1.ensure((size_t)p.Wb * p.r1_rows * sizeof(xyzz)) ||
+        X.wsum.ensure((size_t)p.Wb * sizeof(xyzz)))
+        return 1;
+    MsmBuffers Mk[H2_MAX_UPLOAD_CHUNKS];
+    for (uint32_t j = 0; j < K; j++) {
+        MsmBuffers &M = Mk[j];
+        const size_t o = first[j];
+        M.scalars = d_scalars + o; M.bases = d_bases + o; M.bases_phi = X.bases_phi.as<affine>() + o;
+        M.glv_parts = X.glv_parts.as<uint32_t>() + 8 * o; M.scalars_mont = scalars_mont ? 1u : 0u;
+        M.scal_canon = X.scal_canon.as<fe>() + o;
+        M.counts = X.counts.as<uint32_t>() + j * (p.G + 1); M.cursor = X.cursor.as<uint32_t>() + j * 2 * p.G; M.cursor2 = M.cursor + p.G;
+        M.refs = X.refs.as<uint32_t>() + j * ref_space;
+        M.size_hist = X.size_hist.as<uint32_t>() + j * small_words; M.size_cursor = M.size_hist + (pk[j].T + 2); M.flags = M.size_cursor + (pk[j].T + 2);
+        M.items = X.items.as<uint2>() + j * max_items;
+        M.bucket_sum = X.bucket_sum.as<xyzz>() + j * p.G;
+        M.pkey = X.pkey.as<uint32_t>() + j * part_total; M.pstart = X.pstart.as<uint32_t>() + j * part_total;
+        M.pend = X.pend.as<uint32_t>() + j * part_total; M.ppt = X.ppt.as<xyzz>() + j * part_total;
+        M.ra_t = X.ra_t.as<xyzz>(); M.ra_e = X.ra_e.as<xyzz>(); M.r0 = X.r0.as<xyzz>(); M.r1 = X.r1.as<xyzz>();
+        M.wsum = X.wsum.as<xyzz>(); M.result = d_out;
+    }
+    X.last_flags = Mk[0].flags;
+
+    {   // scratch of the scan (sized here so that nothing allocates while a graph is being captured)
+        const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
+        if (X.scan_blocks.ensure((size_t)((p.G + 1 + per_block - 1) / per_block) * 4 + 16)) return 1;
+    }
+    issue = [&]() -> int {
+        CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
+        CU(cudaMemsetAsync(X.cursor.p, 0, K * 2 * p.G * 4, s));
+        CU(cudaMemsetAsync(X.size_hist.p, 0, K * small_words * 4, s));
+        CU(cudaMemsetAsync(X.bucket_sum.p, 0, K * p.G * sizeof(xyzz), s));
+        CU(cudaMemsetAsync(X.pkey.p, 0xff, K * part_total * 4, s));
+
+        auto k_bin = msm_bin_kernel<P, PS>;
+        auto k_hist = msm_hist_kernel<P, PS>;
+        auto k_scatter = msm_scatter_kernel<P, PS>;
+        auto k_ihist = msm_item_hist_kernel<P, PS>;
+        auto k_ibases = msm_item_bases_kernel<P, PS>;
+        auto k_iplace = msm_item_place_kernel<P, PS>;
+        auto k_accum0 = msm_accum0_kernel<P, PS>;
+        auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
+        auto k_accum0m2 = msm_accum0_multi_kernel<P, PS, 2>;
+        auto k_accum0m4 = msm_accum0_multi_kernel<P, PS, 4>;
+        auto k_accumN = msm_accumN_kernel<P, PS>;
+        auto k_rest = msm_accum_rest_kernel<P, PS>;
+        auto k_reduceA = msm_reduceA_kernel<P, PS>;
+        auto k_r0 = msm_r0_kernel<P, PS>;
+        auto k_r1 = msm_r1_kernel<P, PS>;
+        auto k_wsum = msm_wsum_kernel<P, PS>;
+        auto k_final = msm_final_kernel<P, PS>;
+        for (uint32_t j = 0; j < K; j++) {
+            const MsmPlan &q = pk[j];
+            const MsmBuffers &M = Mk[j];
+            if (bc && bc->k) {   // the scalars of this chunk (K == 1: of every chunk of the upload)
+                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev_scal[e], 0));
+            }
+            // K2/K3: the (point, window) references sorted by bucket -- a single pass into per-bucket bins; the exact
+            // histogram / scan / scatter kernels run only if a bin overflowed (flags[1], set by the bin kernel) or if there
+            // are no bins (set here)
+            if (q.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
+            else LAUNCH(k_bin, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            LAUNCH(k_hist, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            if (exclusive_scan_u32(M.counts, q.G + 1, s, M.flags + 1)) return 1;
+            LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            // K4: work items (one per bucket, oversized buckets split), largest first
+            LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
+            LAUNCH(k_ibases, 1, 32, 0, s, q, M);
+            LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
+            if (bc && bc->k) {   // the sort above only needed the scalars
+                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev[e], 0));
+            }
+            if (q.glv) {
+                auto k_phi = msm_phi_kernel<P, PS>;
+                LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
+            }
+            prof_begin(PROF_MSM_ACCUM0, s);
+            if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) {   // latency-bound: quads, several per work item
+                if (X.accum_ways == 4) LAUNCH(k_accum0m4, blocks_for(q.max_items * 16, 128), 128, 0, s, q, M);
+                else if (X.accum_ways == 2) LAUNCH(k_accum0m2, blocks_for(q.max_items * 8, 128), 128, 0, s, q, M);
+                else LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);
+            }
+            else LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+            prof_end(s);
+            if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
+            if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);
+            if (q.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, q, M);
+        }
+        // K5: bucket reduce (adds the per-chunk bucket sums) and window combine
+        const MsmBuffers &M = Mk[0];
+        LAUNCH(k_reduceA, blocks_for((uint64_t)p.Wb * p.m1 * 4, 128), 128, 0, s, p, M);                    // quads
+        LAUNCH(k_r0, blocks_for((uint64_t)p.Wb * p.nb0 * (2 + p.bits0) * 4, 128), 128, 0, s, p, M);
+        LAUNCH(k_r1, p.Wb * p.r1_rows, 4 * H2_R1_QUADS, 0, s, p, M);
+        LAUNCH(k_wsum, p.Wb, 128, 0, s, p, M);
+        LAUNCH(k_final, 1, 64, 0, s, p, M, (uint32_t)out_canonical);
+        return 0;
+    };
+    return msm_issue_or_replay(issue, fixed && !bc, d_scalars, d_bases, d_out, n, stride, c, sets, scalars_mont, out_canonical, s);
+}
+
+int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
+                 jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed, uint64_t stride,
+                 const BasesChunks *bc, uint32_t sets) {
+    if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bc, sets);
+    if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bc, sets);
+    return fail("unknown curve id");
+}
+// window size for a precomputed table over n bases: few references per bucket (short serial chains)
+// for small n, fewer windows for large n
+static uint32_t table_window(size_t n) {
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    // candidates are the window sizes whose TOP window is well filled (scalars have 254 significant bits:
+    // 254 - (W - 1) c = 6, 14, 14, 16, 14 bits for c = 8, 15, 16, 17, 20): a top window of 1-2 bits would send n / 4
+    // references to a handful of shared buckets and defeat the single-pass sort
+    uint32_t want = lg + 2;
+    if (want <= 9) return 8;
+    if (want <= 15) return 15;
+    if (want == 16) return 15;        // k = 14: 15 measured better than 16 (IPA opening 5.5 vs 6.2 ms, commit equal; tools/table_sweep.py)
+    if (want <= 18) return 17;
+    return 20;
+}
+static int build_table(BaseSet *b, uint32_t c, cudaStream_t s) {
+    if (c == 0) c = table_window(b->n);
+    if (c < 4 || c > 24) return fail("window table: window bits must be in [4, 24]");
+    uint32_t W = (256 + c - 1) / c;
+    if ((uint64_t)W * b->n >= (1ull << 31)) return fail("window table: too many points");
+    if (b->table.ensure((size_t)W * b->n * sizeof(affine))) return 1;
+    if (b->curve == H2_CURVE_PALLAS) {
+        auto k = msm_table_kernel<FpParams, FqParams>;
+        LAUNCH(k, blocks_for(b->n, 128), 128, 0, s, b->buf.as<affine>(), b->table.as<affine>(), (uint64_t)b->n, (uint64_t)b->n, c, W);
+    } else {
+        auto k = msm_table_kernel<FqParams, FpParams>;
+        LAUNCH(k, blocks_for(b->n, 128), 128, 0, s, b->buf.as<affine>(), b->table.as<affine>(), (uint64_t)b->n, (uint64_t)b->n, c, W);
+    }
+    b->c = c; b->W = W;
+    return 0;
+}
+// digit-multiples table of a small resident set (fixedbase.cuh), from the c = 8 window table
+#define H2_FB_MAX_POINTS ((1u << 15) + 2u)
+static int build_direct(BaseSet *b, cudaStream_t s) {
+    if (b->n > H2_FB_MAX_POINTS) return fail("H2_BASES_DIRECT: at most 2^15 + 2 points (256 KiB of table per point)");
+    if (b->c != H2_FB_BITS || b->W != H2_FB_WINDOWS) return fail("H2_BASES_DIRECT: needs the 8-bit window table");
+    if (b->dtable.ensure((size_t)H2_FB_WINDOWS * H2_FB_MULTIPLES * b->n * sizeof(affine))) return 1;
+    const uint64_t threads = (uint64_t)H2_FB_WINDOWS * b->n;
+    if (b->curve == H2_CURVE_PALLAS) {
+        auto k = fb_table_kernel<FpParams, FqParams>;
+        LAUNCH(k, blocks_for(threads, 128), 128, 0, s, (const affine *)b->table.as<affine>(), b->dtable.as<affine>(), (uint64_t)b->n, (uint64_t)b->n);
+    } else {
+        auto k = fb_table_kernel<FqParams, FpParams>;
+        LAUNCH(k, blocks_for(threads, 128), 128, 0, s, (const affine *)b->table.as<affine>(), b->dtable.as<affine>(), (uint64_t)b->n, (uint64_t)b->n);
+    }
+    return 0;
+}
+int convert_points(int curve, affine *d, size_t n, int to_mont, cudaStream_t s) {
+    if (n == 0) return 0;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(convert_points_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, d, (uint64_t)n, to_mont);
+    else LAUNCH(convert_points_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, d, (uint64_t)n, to_mont);
+    return 0;
+}
+
+extern "C" int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, const void *d_bases, size_t n, uint32_t window_bits,
+                          void *d_out_xyz, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (scratch_acquire(s)) return 1;
+    int rc = msm_dispatch(curve, (const fe *)d_scalars, scalars_repr == H2_REPR_MONTGOMERY, (const affine *)d_bases, n, window_bits,
+                          (jacobian *)d_out_xyz, 0, s);
+    if (rc) return rc;
+    return scratch_release(s);
+}
+
+// host_bases != nullptr: one-shot MSM -- the bases are uploaded (and converted) on the copy stream AFTER the
+// scalars, overlapping the digit/sort kernels, which only read scalars.
+static int msm_host_common(int curve, const void *scalars, size_t n_scalars, const void *extra_scalar, const affine *d_bases,
+                           size_t n_total, int repr, void *out_xyz, uint32_t c = 0, uint32_t fixed = 0, uint64_t stride = 0,
+                           const void *host_bases = nullptr) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
+    BasesChunks bc;
+    if (host_bases && n_total) {
+        // One-shot MSM: everything goes up on the copy stream, interleaved per chunk -- scalars of chunk j, then its
+        // bases -- so that the sort of chunk j starts when its scalars have landed and its accumulation when its bases
+        // have, while chunk j + 1 is on the link.
+        // (2 chunks from 2^chunk_min_log points, 3 from 2x that, 4 from 8x: every chunk pays its own sort / work-item launches)
+        cudaStream_t cs = X.copy_stream;
+        CU(cudaEventRecord(X.ev_scalars_up, s));
+        CU(cudaStreamWaitEvent(cs, X.ev_scalars_up, 0));      // after the prior users of the scratch buffers
+        bc.k = 1;
+        if (n_total >= ((size_t)1 << X.chunk_min_log) && n_total >= 16 * H2_MAX_UPLOAD_CHUNKS)
+            bc.k = n_total >= ((size_t)8 << X.chunk_min_log) ? H2_MAX_UPLOAD_CHUNKS : n_total >= ((size_t)2 << X.chunk_min_log) ? 3u : 2u;
+        affine *db = const_cast<affine *>(d_bases);
+        for (uint32_t j = 0; j < bc.k; j++) {
+            size_t lo = chunk_first(n_total, bc.k, j), hi = chunk_first(n_total, bc.k, j + 1);
+            CU(cudaMemcpyAsync(X.scal_in.as<fe>() + lo, (const fe *)scalars + lo, (hi - lo) * sizeof(fe), cudaMemcpyHostToDevice, cs));
+            CU(cudaEventRecord(X.ev_scal_up[j], cs));
+            bc.ev_scal[j] = X.ev_scal_up[j];
+            CU(cudaMemcpyAsync(db + lo, (const affine *)host_bases + lo, (hi - lo) * sizeof(affine), cudaMemcpyHostToDevice, cs));
+            if (repr == H2_REPR_CANONICAL && convert_points(curve, db + lo, hi - lo, 1, cs)) return 1;
+            CU(cudaEventRecord(X.ev_bases_up[j], cs));
+            bc.ev[j] = X.ev_bases_up[j];
+        }
+    } else {
+        if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
+    }
+    int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
+                          repr == H2_REPR_CANONICAL, s, fixed, stride, bc.k ? &bc : nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int h2_msm(int curve, const void *scalars, const void *bases_xy, size_t n, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.bases_in.ensure((n + 1) * sizeof(affine))) return 1;
+    return msm_host_common(curve, scalars, n, nullptr, X.bases_in.as<affine>(), n, repr, out_xyz, 0, 0, 0, bases_xy);
+}
+
+static int bases_register_impl(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle);
+extern "C" int h2_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle) {
+    return bases_register_impl(curve, bases_xy, n, repr, 0, 0, handle);
+}
+extern "C" int h2_bases_register_ex(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle) {
+    return bases_register_impl(curve, bases_xy, n, repr, window_bits, flags, handle);
+}
+static int bases_register_impl(int curve, const void *bases_xy, size_t n, int repr, uint32_t window_bits, uint32_t flags, uint64_t *handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    BaseSet *b = new BaseSet();
+    b->curve = curve; b->n = n;
+    if (b->buf.ensure((n + 1) * sizeof(affine))) { delete b; return 1; }
+    cudaStream_t s = g_ctx.stream;
+    if (n) CU(cudaMemcpyAsync(b->buf.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), n, 1, s)) return 1;
+    const bool direct = (flags & H2_BASES_DIRECT) && (flags & H2_BASES_PRECOMPUTE) && n > 0;
+    if ((flags & H2_BASES_PRECOMPUTE) && n > 0 && build_table(b, direct ? H2_FB_BITS : window_bits, s)) return 1;
+    if (direct && build_direct(b, s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    uint64_t h = g_ctx.next_handle++;
+    g_ctx.bases[h] = b;
+    *handle = h;
+    return 0;
+}
+extern "C" int h2_bases_release(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.bases.find(handle);
+    if (it == g_ctx.bases.end()) return fail("h2_bases_release: unknown handle");
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    it->second->buf.release();
+    it->second->table.release();
+    it->second->dtable.release();
+    delete it->second;
+    g_ctx.bases.erase(it);
+    return 0;
+}
+extern "C" int h2_msm_registered(uint64_t handle, const void *scalars, size_t n, const void *extra_scalar, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(handle);
+    if (it == g_ctx.bases.end()) return fail("h2_msm_registered: unknown handle");
+    BaseSet *b = it->second;
+    size_t total = n + (extra_scalar ? 1 : 0);
+    if (total > b->n) return fail("h2_msm_registered: more scalars than registered bases");
+    if (b->table.p) {   // fixed-base path: digit-multiples table (direct sum) or window table (one shared bucket set)
+        uint32_t c, mode;
+        const affine *t = fixed_table(b, &c, &mode);
+        return msm_host_common(b->curve, scalars, n, extra_scalar, t, total, repr, out_xyz, c, mode, b->n);
+    }
+    return msm_host_common(b->curve, scalars, n, extra_scalar, b->buf.as<affine>(), total, repr, out_xyz);
+}
+
+// `batch` scalar vectors of n entries (+ one extra scalar each, the blinds) against a registered base set with a
+// window table: one pass, one bucket set per vector.
+static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                     void *out, int affine_out);
+extern "C" int h2_msm_registered_batch(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                       void *out_xyz) {
+    return msm_registered_batch_impl(handle, scalars, n, extra_scalars, batch, repr, out_xyz, 0);
+}
+// the same pass followed by batch_normalize on the device (plonk/prover.rs:305-311: commit every column, then
+// C::Curve::batch_normalize): `batch` affine points (64 B) come back instead of Jacobian ones
+extern "C" int h2_msm_registered_batch_affine(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                              void *out_xy) {
+    return msm_registered_batch_impl(handle, scalars, n, extra_scalars, batch, repr, out_xy, 1);
+}
+static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_t n, const void *extra_scalars, size_t batch, int repr,
+                                     void *out_xyz, int affine_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(handle);
+    if (it == g_ctx.bases.end()) return fail("h2_msm_registered_batch: unknown handle");
+    BaseSet *b = it->second;
+    if (!b->table.p) return fail("h2_msm_registered_batch: the base set has no window table (register with H2_BASES_PRECOMPUTE)");
+    if (batch == 0) return 0;
+    if (batch > 64) return fail("h2_msm_registered_batch: batch > 64");
+    size_t total = n + (extra_scalars ? 1 : 0);
+    if (total > b->n) return fail("h2_msm_registered_batch: more scalars than registered bases");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.scal_in.ensure(batch * total * sizeof(fe)) || X.result.ensure(batch * sizeof(jacobian))) return 1;
+    fe *d = X.scal_in.as<fe>();
+    if (!extra_scalars) {
+        CU(cudaMemcpyAsync(d, scalars, batch * n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    } else {   // interleave: [poly_k (n) | blind_k] per vector
+        CU(cudaMemcpy2DAsync(d, total * sizeof(fe), scalars, n * sizeof(fe), n * sizeof(fe), batch, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpy2DAsync(d + n, total * sizeof(fe), extra_scalars, sizeof(fe), sizeof(fe), batch, cudaMemcpyHostToDevice, s));
+    }
+    const int canon = repr == H2_REPR_CANONICAL;
+    uint32_t tc, tmode;
+    const affine *tbl = fixed_table(b, &tc, &tmode);
+    int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, tbl, total, tc, X.result.as<jacobian>(),
+                          affine_out ? 0 : canon, s, tmode, b->n, nullptr, (uint32_t)batch);
+    if (rc) return rc;
+    if (affine_out) {
+        if (X.ec_out.ensure(batch * sizeof(affine))) return 1;
+        const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
+        if (b->curve == H2_CURVE_PALLAS)
+            LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+        else
+            LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+        CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    } else {
+        CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    }
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int h2_point_sum(int curve, const void *points_xyz, size_t g, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.misc.ensure((g + 1) * sizeof(jacobian)) || X.result.ensure(sizeof(jacobian))) return 1;
+    if (g) CU(cudaMemcpyAsync(X.misc.p, points_xyz, g * sizeof(jacobian), cudaMemcpyHostToDevice, s));
+    int canon = repr == H2_REPR_CANONICAL;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(point_sum_kernel<FpParams>, 1, 32, 0, s, X.misc.as<jacobian>(), (uint32_t)g, canon, X.result.as<jacobian>());
+    else if (curve == H2_CURVE_VESTA) LAUNCH(point_sum_kernel<FqParams>, 1, 32, 0, s, X.misc.as<jacobian>(), (uint32_t)g, canon, X.result.as<jacobian>());
+    else return fail("unknown curve id");
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+static void ipa_free(IpaSession *q) {   // back to the pool (the caller has synchronised the stream)
+    if (g_ctx.ipa_pool.size() < 2) { g_ctx.ipa_pool.push_back(q); return; }
+    q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q;
+}
+static IpaState ipa_state(IpaSession *q) {
+    IpaState S;
+    S.p = q->p.as<fe>(); S.b = q->b.as<fe>(); S.s = q->s.as<fe>(); S.scal = q->scal.as<fe>(); S.n = 1ull << q->k;
+    return S;
+}
+template <class PS> static int ipa_begin_impl(IpaSession *q, const void *p_prime, const void *x3, int repr, cudaStream_t s) {
+    Context &X = g_ctx;
+    const uint64_t n = 1ull << q->k;
+    if (q->p.ensure(n * sizeof(fe)) || q->b.ensure(n * sizeof(fe)) || q->s.ensure(n * sizeof(fe)) || q->scal.ensure(2 * (n + 2) * sizeof(fe)) ||
+        q->out.ensure(2 * sizeof(jacobian)) || X.pow2.ensure(64 * sizeof(fe)))
+        return 1;
+    CU(cudaMemcpyAsync(q->p.p, p_prime, n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    IpaState S = ipa_state(q);
+    LAUNCH(ipa_init_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, repr == H2_REPR_MONTGOMERY);
+    // b_t = x3^t (prover.rs:86-93) with the NTT twiddle generator
+    fe x = host_to_mont<PS>(x3, repr);
+    LAUNCH(twiddle_pow2_kernel<PS>, 1, 32, 0, s, X.pow2.as<fe>(), x, q->k + 1);
+    LAUNCH(twiddle_fill_kernel<PS>, blocks_for((n + 31) / 32, 128), 128, 0, s, S.b, X.pow2.as<fe>(), n);
+    return 0;
+}
+extern "C" int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_prime, const void *x3, int repr, uint64_t *session) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(bases_handle);
+    if (it == g_ctx.bases.end()) return fail("h2_ipa_begin: unknown bases handle");
+    BaseSet *b = it->second;
+    if (k == 0 || k > 28) return fail("h2_ipa_begin: k out of range");
+    if (b->n != (1ull << k) + 2) return fail("h2_ipa_begin: the base set must hold g[0..2^k) || w || u");
+    if (!b->table.p) return fail("h2_ipa_begin: the base set has no window table (register with H2_BASES_PRECOMPUTE)");
+    IpaSession *q;
+    if (!g_ctx.ipa_pool.empty()) { q = g_ctx.ipa_pool.back(); g_ctx.ipa_pool.pop_back(); }
+    else q = new IpaSession();
+    q->bases = bases_handle; q->k = k; q->round = 0; q->folded = 1;
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) { ipa_free(q); return 1; }   // pow2 is shared scratch
+    int rc = b->curve == H2_CURVE_PALLAS ? ipa_begin_impl<FqParams>(q, p_prime, x3, repr, s) : ipa_begin_impl<FpParams>(q, p_prime, x3, repr, s);
+    if (rc) { ipa_free(q); return 1; }
+    if (scratch_release(s)) { ipa_free(q); return 1; }
+    cudaError_t e = cudaStreamSynchronize(s);   // p_prime may be pageable host memory
+    if (e != cudaSuccess) { ipa_free(q); return fail(std::string("h2_ipa_begin: ") + cudaGetErrorString(e)); }
+    uint64_t h = g_ctx.next_handle++;
+    g_ctx.ipa[h] = q;
+    *session = h;
+    return 0;
+}
+template <class PS> static int ipa_round_impl(IpaSession *q, BaseSet *b, const void *z, const void *l_rand, const void *r_rand, int repr, cudaStream_t s) {
+    const uint64_t n = 1ull << q->k;
+    const uint32_t bit = q->k - 1 - q->round;
+    IpaState S = ipa_state(q);
+    LAUNCH(ipa_prep_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, bit);
+    LAUNCH(ipa_inner_kernel<PS>, 1, 512, 0, s, S, bit, host_to_mont<PS>(z, repr), host_to_mont<PS>(l_rand, repr), host_to_mont<PS>(r_rand, repr));
+    uint32_t tc, tmode;
+    const affine *tbl = fixed_table(b, &tc, &tmode);
+    return msm_dispatch(b->curve, S.scal, 1, tbl, n + 2, tc, q->out.as<jacobian>(), repr == H2_REPR_CANONICAL, s, tmode, b->n, nullptr, 2);
+}
+extern "C" int h2_ipa_round(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.ipa.find(session);
+    if (it == g_ctx.ipa.end()) return fail("h2_ipa_round: unknown session");
+    IpaSession *q = it->second;
+    auto ib = g_ctx.bases.find(q->bases);
+    if (ib == g_ctx.bases.end()) return fail("h2_ipa_round: the session's base set was released");
+    if (q->round >= q->k) return fail("h2_ipa_round: all k rounds are done");
+    if (!q->folded) return fail("h2_ipa_round: h2_ipa_fold must follow each round");
+    BaseSet *b = ib->second;
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) return 1;
+    int rc = b->curve == H2_CURVE_PALLAS ? ipa_round_impl<FqParams>(q, b, z, l_rand, r_rand, repr, s) : ipa_round_impl<FpParams>(q, b, z, l_rand, r_rand, repr, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_lr_xyz, q->out.p, 2 * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    q->folded = 0;
+    return 0;
+}
+extern "C" int h2_ipa_fold(uint64_t session, const void *u, const void *u_inv, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.ipa.find(session);
+    if (it == g_ctx.ipa.end()) return fail("h2_ipa_fold: unknown session");
+    IpaSession *q = it->second;
+    auto ib = g_ctx.bases.find(q->bases);
+    if (ib == g_ctx.bases.end()) return fail("h2_ipa_fold: the session's base set was released");
+    if (q->folded) return fail("h2_ipa_fold: no round to fold");
+    const uint64_t n = 1ull << q->k;
+    const uint32_t bit = q->k - 1 - q->round;
+    cudaStream_t s = g_ctx.stream;
+    IpaState S = ipa_state(q);
+    if (ib->second->curve == H2_CURVE_PALLAS) LAUNCH(ipa_fold_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, S, bit, host_to_mont<FqParams>(u, repr), host_to_mont<FqParams>(u_inv, repr));
+    else LAUNCH(ipa_fold_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, S, bit, host_to_mont<FpParams>(u, repr), host_to_mont<FpParams>(u_inv, repr));
+    q->round++; q->folded = 1;   // asynchronous: the next round (or finish) is ordered behind it on the stream
+    return 0;
+}
+extern "C" int h2_ipa_finish(uint64_t session, int repr, void *out_c_b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.ipa.find(session);
+    if (it == g_ctx.ipa.end()) return fail("h2_ipa_finish: unknown session");
+    IpaSession *q = it->second;
+    auto ib = g_ctx.bases.find(q->bases);
+    int rc = 0;
+    cudaStream_t s = g_ctx.stream;
+    if (out_c_b) {
+        if (ib == g_ctx.bases.end()) rc = fail("h2_ipa_finish: the session's base set was released");
+        else if (q->round != q->k || !q->folded) rc = fail("h2_ipa_finish: the k rounds are not complete");
+        else {
+            IpaState S = ipa_state(q);
+            fe *out = q->scal.as<fe>();
+            if (ib->second->curve == H2_CURVE_PALLAS) ipa_result_kernel<FqParams><<<1, 32, 0, s>>>(S, repr == H2_REPR_CANONICAL, out);
+            else ipa_result_kernel<FpParams><<<1, 32, 0, s>>>(S, repr == H2_REPR_CANONICAL, out);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t e = cudaMemcpyAsync(out_c_b, out, 2 * sizeof(fe), cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = fail(std::string("h2_ipa_finish: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess && !rc) rc = fail(std::string("h2_ipa_finish: ") + cudaGetErrorString(e));
+    ipa_free(q);
+    g_ctx.ipa.erase(it);
+    return rc;
+}
+
+
+// commit(poly, blind) = <poly[0..n), bases[0..n)> + blind * bases[n] for `batch` resident polynomials in one pass
+extern "C" int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
+                                       void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_ctx.bases.find(bases_handle);
+    if (it == g_ctx.bases.end()) return fail("h2_msm_registered_polys: unknown bases handle");
+    BaseSet *b = it->second;
+    if (batch == 0) return 0;
+    if (batch > 64) return fail("h2_msm_registered_polys: batch > 64");
+    if (batch > 1 && !b->table.p) return fail("h2_msm_registered_polys: a batch needs a base set with a window table (H2_BASES_PRECOMPUTE)");
+    const size_t total = n + (extra_scalars ? 1 : 0);
+    if (total > b->n) return fail("h2_msm_registered_polys: more scalars than registered bases");
+    const int scalar_field = b->curve == H2_CURVE_PALLAS ? H2_FIELD_FQ : H2_FIELD_FP;
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.scal_in.ensure(batch * total * sizeof(fe)) || X.result.ensure(batch * sizeof(jacobian)) || X.misc.ensure(batch * sizeof(fe) + 64)) return 1;
+    fe *d = X.scal_in.as<fe>();
+    if (extra_scalars) {   // the blinds: Montgomery form like the resident data
+        CU(cudaMemcpyAsync(X.misc.p, extra_scalars, batch * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (repr == H2_REPR_CANONICAL && convert_field(scalar_field, X.misc.as<fe>(), batch, 1, s)) return 1;
+    }
+    for (size_t j = 0; j < batch; j++) {
+        PolyBuf *q = find_poly(polys[j]);
+        if (!q) return fail("h2_msm_registered_polys: unknown polynomial handle");
+        if (q->field != scalar_field) return fail("h2_msm_registered_polys: the polynomial is not over the curve's scalar field");
+        if (q->len < n) return fail("h2_msm_registered_polys: the polynomial holds fewer than n elements");
+        CU(cudaMemcpyAsync(d + j * total, q->buf.p, n * sizeof(fe), cudaMemcpyDeviceToDevice, s));
+        if (extra_scalars) CU(cudaMemcpyAsync(d + j * total + n, X.misc.as<fe>() + j, sizeof(fe), cudaMemcpyDeviceToDevice, s));
+    }
+    int rc;
+    uint32_t tc = 0, tmode = 0;
+    const affine *tbl = b->table.p ? fixed_table(b, &tc, &tmode) : nullptr;
+    if (tbl) rc = msm_dispatch(b->curve, d, 1, tbl, total, tc, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s, tmode, b->n,
+                               nullptr, (uint32_t)batch);
+    else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+

@@ -1,0 +1,247 @@
+// C ABI of the engine, part 5 of 5: reductions and elementwise programs on resident polynomials (polyops.cuh, asteval.cuh).
+#include "util_kernels.cuh"
+#include "polyops.cuh"
+#include "asteval.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// eval_polynomial / compute_inner_product / kate_division on resident polynomials (polyops.cuh)
+// ------------------------------------------------------------------------------------------------
+// mode 0: eval (points: batch x 32 host), 1: inner product of a[i] and c[i], 2: kate division of a[i] by (X - point_i) into c[i]
+template <class P>
+static int polyops_run(int mode, const std::vector<PolyBuf *> &a, const std::vector<PolyBuf *> &c, size_t n, const void *points, int repr, void *out) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const uint32_t batch = (uint32_t)a.size();
+    // level sizes: m[0] = n, m[l + 1] = ceil(m[l] / CHUNK), down to 1
+    std::vector<uint64_t> m{(uint64_t)n}, off{0};
+    while (m.back() > 1) { off.push_back(off.back() + (m.size() > 1 ? m.back() * batch : 0)); m.push_back((m.back() + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK); }
+    if (mode == 1 && m.size() == 1) { off.push_back(0); m.push_back(1); }   // a length-1 inner product still needs its product level
+    const size_t L = m.size() - 1;                               // levels above the polynomial itself
+    const uint64_t lvl_total = off.back() + m.back() * batch + batch;
+    if (scratch_acquire(s)) return 1;
+    if (X.po_lvl.ensure(lvl_total * sizeof(fe)) || X.po_q.ensure(lvl_total * sizeof(fe)) || X.po_pts.ensure((L + 2) * batch * sizeof(fe)) ||
+        X.po_ptrs.ensure(2 * batch * sizeof(void *)) || X.misc.ensure(batch * sizeof(fe) + 64))
+        return 1;
+    fe *lvl = X.po_lvl.as<fe>(), *qarr = X.po_q.as<fe>(), *pts = X.po_pts.as<fe>();
+    auto level = [&](size_t l) { return lvl + off[l]; };         // values of level l >= 1: [batch][m[l]]
+    auto qlevel = [&](size_t l) { return qarr + off[l]; };
+    std::vector<const fe *> hp(2 * batch);
+    for (uint32_t b = 0; b < batch; b++) { hp[b] = a[b]->buf.as<fe>(); hp[batch + b] = c.empty() ? nullptr : c[b]->buf.as<fe>(); }
+    CU(cudaMemcpyAsync(X.po_ptrs.p, hp.data(), 2 * batch * sizeof(void *), cudaMemcpyHostToDevice, s));
+    const fe *const *d_a = X.po_ptrs.as<const fe *>();
+    const fe *const *d_c = d_a + batch;
+    // points of level 0 (Montgomery): the caller's, or 1 for the plain sums of the inner product
+    if (mode == 1) {
+        LAUNCH(fe_fill_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts, batch, fe_one<P>());
+    } else {
+        CU(cudaMemcpyAsync(pts, points, batch * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts, (uint64_t)batch, 1);
+    }
+    // upward pass: level l + 1 from level l at the point x^(CHUNK^l)
+    for (size_t l = 0; l < L; l++) {
+        const dim3 grid(blocks_for(m[l + 1], 128), batch);
+        if (l == 0 && mode == 1) LAUNCH(poly_inner_level0_kernel<P>, grid, 128, 0, s, d_a, d_c, m[0], level(1), m[1]);
+        else LAUNCH(poly_eval_level_kernel<P>, grid, 128, 0, s, l == 0 ? d_a : (const fe *const *)nullptr, l == 0 ? (const fe *)nullptr : (const fe *)level(l),
+                    m[l], (const fe *)(pts + l * batch), level(l + 1), m[l + 1]);
+        if (mode != 1) LAUNCH(poly_pow_chunk_kernel<P>, blocks_for(batch, 64), 64, 0, s, (const fe *)(pts + l * batch), pts + (l + 1) * batch, batch);
+        else if (l == 0) LAUNCH(fe_fill_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts + batch, batch, fe_one<P>());
+        if (mode == 1 && l >= 1) CU(cudaMemcpyAsync(pts + (l + 1) * batch, pts, batch * sizeof(fe), cudaMemcpyDeviceToDevice, s));
+    }
+    if (mode != 2) {   // the single value of the top level is the result (n == 1: the coefficient itself; n == 0 handled by the caller)
+        fe *res = X.misc.as<fe>();
+        if (L == 0) {
+            for (uint32_t b = 0; b < batch; b++) CU(cudaMemcpyAsync(res + b, hp[b], sizeof(fe), cudaMemcpyDeviceToDevice, s));
+        } else {
+            CU(cudaMemcpyAsync(res, level(L), batch * sizeof(fe), cudaMemcpyDeviceToDevice, s));   // m[L] == 1: [batch][1]
+        }
+        if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(batch, 64), 64, 0, s, res, (uint64_t)batch, 0);
+        CU(cudaMemcpyAsync(out, res, batch * sizeof(fe), cudaMemcpyDeviceToHost, s));
+        if (scratch_release(s)) return 1;
+        CU(cudaStreamSynchronize(s));
+        return 0;
+    }
+    // kate division, downward pass: Q at every position of level l from the carries of level l + 1.  The top level with
+    // more than one value (m[L] == 1 always; start from the highest level that has something to walk) needs no carry.
+    fe *const *d_q = (fe *const *)d_c;
+    for (size_t l = L; l-- > 0;) {
+        const dim3 grid(blocks_for(m[l + 1], 128), batch);
+        const fe *carry = (l + 1 < L) ? (const fe *)qlevel(l + 1) : (const fe *)nullptr;   // Q of level l + 1; the top level's Q(1..) are zero
+        LAUNCH(poly_kate_down_kernel<P>, grid, 128, 0, s, l == 0 ? d_a : (const fe *const *)nullptr, l == 0 ? (const fe *)nullptr : (const fe *)level(l), m[l],
+               (const fe *)(pts + l * batch), carry, m[l + 1], l == 0 ? (fe *)nullptr : qlevel(l), l == 0 ? d_q : (fe *const *)nullptr);
+    }
+    return scratch_release(s);
+}
+static int polyops_dispatch(int mode, const uint64_t *ah, const uint64_t *ch, size_t batch, size_t n, const void *points, int repr, void *out,
+                            const char *who) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (batch == 0) return 0;
+    if (batch > 256) return fail(std::string(who) + ": batch > 256");
+    if (n >= (1ull << 32)) return fail(std::string(who) + ": n >= 2^32");
+    std::vector<PolyBuf *> a(batch), c;
+    if (ch) c.resize(batch);
+    for (size_t b = 0; b < batch; b++) {
+        a[b] = find_poly(ah[b]);
+        if (!a[b]) return fail(std::string(who) + ": unknown polynomial handle");
+        if (a[b]->field != a[0]->field) return fail(std::string(who) + ": the polynomials live in different fields");
+        if (a[b]->len < n) return fail(std::string(who) + ": a polynomial holds fewer than n coefficients");
+        if (ch) {
+            c[b] = find_poly(ch[b]);
+            if (!c[b]) return fail(std::string(who) + ": unknown polynomial handle");
+            if (c[b]->field != a[0]->field) return fail(std::string(who) + ": the polynomials live in different fields");
+            if (c[b]->len + (mode == 2 ? 1 : 0) < n) return fail(std::string(who) + ": the second polynomial is too short");
+            if (mode == 2 && c[b] == a[b]) return fail(std::string(who) + ": the quotient cannot overwrite its dividend");
+        }
+    }
+    if (a[0]->field == H2_FIELD_FP) return polyops_run<FpParams>(mode, a, c, n, points, repr, out);
+    return polyops_run<FqParams>(mode, a, c, n, points, repr, out);
+}
+// Evaluator::evaluate (poly/evaluator.rs:129-228) on resident polynomials: `code` is the postfix form of the Ast (asteval.cuh),
+// validated here so that the kernel's operand stack can neither overflow nor underflow.
+template <class P>
+static int ast_run(PolyBuf *out, const std::vector<PolyBuf *> &polys, uint32_t log_n, const AstInstr *code, size_t n_code, const void *consts,
+                   size_t n_consts, const void *omega, const void *lin_base, int repr, bool has_linear) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const uint64_t n = 1ull << log_n;
+    if (scratch_acquire(s)) return 1;
+    if (X.ast_code.ensure(n_code * sizeof(AstInstr)) || X.ast_consts.ensure((n_consts + 1) * sizeof(fe)) || X.po_ptrs.ensure((polys.size() + 1) * sizeof(void *)))
+        return 1;
+    std::vector<const fe *> hp(polys.size() + 1, nullptr);
+    for (size_t i = 0; i < polys.size(); i++) hp[i] = polys[i]->buf.as<fe>();
+    CU(cudaMemcpyAsync(X.po_ptrs.p, hp.data(), hp.size() * sizeof(void *), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(X.ast_code.p, code, n_code * sizeof(AstInstr), cudaMemcpyHostToDevice, s));
+    if (n_consts) {
+        CU(cudaMemcpyAsync(X.ast_consts.p, consts, n_consts * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(n_consts, 64), 64, 0, s, X.ast_consts.as<fe>(), (uint64_t)n_consts, 1);
+    }
+    AstArgs A;
+    A.polys = X.po_ptrs.as<const fe *>(); A.code = X.ast_code.as<AstInstr>(); A.n_code = (uint32_t)n_code; A.consts = X.ast_consts.as<fe>();
+    A.tw = nullptr; A.lin_base = fe_one<P>(); A.log_n = log_n; A.out = out->buf.as<fe>();
+    if (has_linear) {
+        if (get_twiddles_any(out->field, host_to_mont<P>(omega, repr), log_n, s, &A.tw)) return 1;
+        A.lin_base = host_to_mont<P>(lin_base, repr);
+    }
+    LAUNCH(ast_eval_kernel<P>, blocks_for(n, 128), 128, 0, s, A);
+    return scratch_release(s);
+}
+extern "C" int h2_poly_eval_ast(uint64_t out, const uint64_t *polys, size_t n_polys, uint32_t log_n, const uint32_t *code, size_t n_code,
+                                const void *consts, size_t n_consts, const void *omega, const void *lin_base, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *o = find_poly(out);
+    if (!o) return fail("h2_poly_eval_ast: unknown output handle");
+    if (log_n > 30 || o->len < ((size_t)1 << log_n)) return fail("h2_poly_eval_ast: the output holds fewer than 2^log_n elements");
+    if (n_code == 0 || n_code > (1u << 20)) return fail("h2_poly_eval_ast: empty or oversized program");
+    std::vector<PolyBuf *> ps(n_polys);
+    for (size_t i = 0; i < n_polys; i++) {
+        ps[i] = find_poly(polys[i]);
+        if (!ps[i]) return fail("h2_poly_eval_ast: unknown polynomial handle");
+        if (ps[i]->field != o->field) return fail("h2_poly_eval_ast: the polynomials live in different fields");
+        if (ps[i]->len < ((size_t)1 << log_n)) return fail("h2_poly_eval_ast: a polynomial holds fewer than 2^log_n elements");
+        if (ps[i] == o) return fail("h2_poly_eval_ast: the output cannot be one of the operands (rotated reads)");
+    }
+    const AstInstr *prog = reinterpret_cast<const AstInstr *>(code);
+    int depth = 0;
+    bool has_linear = false;
+    for (size_t pc = 0; pc < n_code; pc++) {
+        const AstInstr &in = prog[pc];
+        switch (in.op) {
+        case AST_POLY: if (in.arg >= n_polys) return fail("h2_poly_eval_ast: polynomial index out of range"); depth++; break;
+        case AST_LINEAR: has_linear = true;   /* fall through */
+        case AST_CONST: if (in.arg >= n_consts) return fail("h2_poly_eval_ast: constant index out of range"); depth++; break;
+        case AST_ADD: case AST_MUL: if (depth < 2) return fail("h2_poly_eval_ast: operand stack underflow"); depth--; break;
+        case AST_SCALE: if (in.arg >= n_consts) return fail("h2_poly_eval_ast: constant index out of range");   /* fall through */
+        case AST_NEG: if (depth < 1) return fail("h2_poly_eval_ast: operand stack underflow"); break;
+        default: return fail("h2_poly_eval_ast: unknown opcode");
+        }
+        if (depth > H2_AST_STACK) return fail("h2_poly_eval_ast: expression deeper than the operand stack (24)");
+    }
+    if (depth != 1) return fail("h2_poly_eval_ast: the program must leave exactly one value");
+    if (has_linear && (!omega || !lin_base)) return fail("h2_poly_eval_ast: a LinearTerm needs omega and the coset generator");
+    if (o->field == H2_FIELD_FP) return ast_run<FpParams>(o, ps, log_n, prog, n_code, consts, n_consts, omega, lin_base, repr, has_linear);
+    return ast_run<FqParams>(o, ps, log_n, prog, n_code, consts, n_consts, omega, lin_base, repr, has_linear);
+}
+// ff::BatchInvert on the first n elements of a resident polynomial, in place (zeros stay zero)
+extern "C" int h2_poly_batch_invert(uint64_t poly, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *a = find_poly(poly);
+    if (!a) return fail("h2_poly_batch_invert: unknown polynomial handle");
+    if (a->len < n) return fail("h2_poly_batch_invert: the polynomial holds fewer than n elements");
+    if (n == 0) return 0;
+    cudaStream_t s = g_ctx.stream;
+    if (scratch_acquire(s)) return 1;
+    const uint32_t nb = blocks_for((n + 15) / 16, 64);
+    if (a->field == H2_FIELD_FP) LAUNCH(poly_batch_invert_kernel<FpParams>, nb, 64, 0, s, a->buf.as<fe>(), (uint64_t)n);
+    else LAUNCH(poly_batch_invert_kernel<FqParams>, nb, 64, 0, s, a->buf.as<fe>(), (uint64_t)n);
+    return scratch_release(s);
+}
+// dst[0] = init, dst[i] = dst[i - 1] * src[i - 1] for i < n: the running product of plonk/permutation/prover.rs:150-156
+template <class P> static int grand_product_run(PolyBuf *d, PolyBuf *a, size_t n, const void *init, int repr) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    std::vector<uint64_t> m{(uint64_t)n}, off{0};
+    while (m.back() > H2_POLY_CHUNK) { off.push_back(off.back() + (m.size() > 1 ? m.back() : 0)); m.push_back((m.back() + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK); }
+    const size_t L = m.size() - 1;
+    uint64_t total = 1;
+    for (size_t l = 1; l <= L; l++) total += m[l];
+    if (scratch_acquire(s)) return 1;
+    if (X.po_lvl.ensure(total * sizeof(fe)) || X.po_q.ensure(total * sizeof(fe))) return 1;
+    fe *lvl = X.po_lvl.as<fe>(), *ex = X.po_q.as<fe>();
+    const fe *src = a->buf.as<fe>();
+    const fe in0 = host_to_mont<P>(init, repr);
+    for (size_t l = 0; l < L; l++)
+        LAUNCH(poly_product_up_kernel<P>, blocks_for(m[l + 1], 128), 128, 0, s, l == 0 ? src : (const fe *)(lvl + off[l]), m[l], lvl + off[l + 1], m[l + 1]);
+    for (size_t l = L + 1; l-- > 0;) {
+        const uint64_t chunks = (m[l] + H2_POLY_CHUNK - 1) / H2_POLY_CHUNK;
+        LAUNCH(poly_product_down_kernel<P>, blocks_for(chunks, 128), 128, 0, s, l == 0 ? src : (const fe *)(lvl + off[l]), m[l],
+               l == L ? (const fe *)nullptr : (const fe *)(ex + off[l + 1]), in0, l == 0 ? d->buf.as<fe>() : ex + off[l], chunks);
+    }
+    return scratch_release(s);
+}
+extern "C" int h2_poly_running_product(uint64_t dst, uint64_t src, size_t n, const void *init, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *d = find_poly(dst), *a = find_poly(src);
+    if (!d || !a) return fail("h2_poly_running_product: unknown polynomial handle");
+    if (d == a) return fail("h2_poly_running_product: the product cannot overwrite its factors");
+    if (d->field != a->field) return fail("h2_poly_running_product: the polynomials live in different fields");
+    if (a->len < n || d->len < n) return fail("h2_poly_running_product: a polynomial holds fewer than n elements");
+    if (n == 0) return 0;
+    if (a->field == H2_FIELD_FP) return grand_product_run<FpParams>(d, a, n, init, repr);
+    return grand_product_run<FqParams>(d, a, n, init, repr);
+}
+// divide_by_vanishing_poly on a resident extended-domain polynomial; t_evals: t_len = 2^(ext_k - k) host elements
+extern "C" int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *a = find_poly(poly);
+    if (!a) return fail("h2_poly_divide_by_vanishing: unknown polynomial handle");
+    if (ext_k > 30 || a->len < ((size_t)1 << ext_k)) return fail("h2_poly_divide_by_vanishing: the polynomial holds fewer than 2^ext_k elements");
+    if (t_len == 0 || (t_len & (t_len - 1)) || t_len > (1u << ext_k)) return fail("h2_poly_divide_by_vanishing: t_len must be a power of two <= 2^ext_k");
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.po_pts.ensure((size_t)t_len * sizeof(fe))) return 1;
+    CU(cudaMemcpyAsync(X.po_pts.p, t_evals, (size_t)t_len * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL && convert_field(a->field, X.po_pts.as<fe>(), t_len, 1, s)) return 1;
+    const uint64_t n = 1ull << ext_k;
+    if (a->field == H2_FIELD_FP) LAUNCH(poly_vanish_div_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, a->buf.as<fe>(), n, (const fe *)X.po_pts.as<fe>(), t_len - 1);
+    else LAUNCH(poly_vanish_div_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, a->buf.as<fe>(), n, (const fe *)X.po_pts.as<fe>(), t_len - 1);
+    return scratch_release(s);
+}
+extern "C" int h2_poly_eval(const uint64_t *polys, size_t batch, size_t n, const void *points, int repr, void *out) {
+    if (n == 0) { memset(out, 0, batch * 32); return 0; }            // the empty sum (fold over nothing, arithmetic.rs:300-302)
+    return polyops_dispatch(0, polys, nullptr, batch, n, points, repr, out, "h2_poly_eval");
+}
+extern "C" int h2_poly_inner_product(const uint64_t *a, const uint64_t *b, size_t batch, size_t n, int repr, void *out) {
+    if (n == 0) { memset(out, 0, batch * 32); return 0; }
+    return polyops_dispatch(1, a, b, batch, n, nullptr, repr, out, "h2_poly_inner_product");
+}
+extern "C" int h2_poly_kate_division(const uint64_t *dst, const uint64_t *src, size_t batch, size_t n, const void *points, int repr) {
+    if (n == 0) return fail("h2_poly_kate_division: empty polynomial (the reference underflows a.len() - 1, arithmetic.rs:329)");
+    if (n == 1) return 0;                                             // quotient of a constant: no coefficients
+    return polyops_dispatch(2, src, dst, batch, n, points, repr, nullptr, "h2_poly_kate_division");
+}
+

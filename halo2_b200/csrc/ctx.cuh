@@ -1,0 +1,174 @@
+// Host-side context shared by the translation units of the C ABI (capi_*.cu): error reporting, device buffers, the per-device
+// Context, launch / profiling helpers.  The library is split into several TUs so that they compile in parallel and a change
+// to one kernel family rebuilds one of them; every kernel is a template (or inline) in a header, so each TU instantiates
+// what it launches.  No torch types.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/halo2_b200.h"
+#define H2_MAX_UPLOAD_CHUNKS 4
+#define H2_MAX_DEVICES 16
+#include "curve.cuh"
+
+using namespace h2;
+
+// ------------------------------------------------------------------------------------------------
+// errors, context
+// ------------------------------------------------------------------------------------------------
+int fail(const std::string &m);          // sets the calling thread's last error, returns 1
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+// Cached CUDA graphs (fixed-base MSMs) hold raw pointers into the library's scratch pools and window tables: every
+// (re)allocation or release of a TRACKED buffer bumps the generation and invalidates them.  Buffers a graph can only see
+// through its key (caller polynomials, IPA session vectors: the scalars / out pointers are part of the key) are untracked --
+// allocating a ResidentPoly between two commits must not throw the commit graphs away.
+extern uint64_t g_alloc_gen;
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool tracked = true;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (tracked) g_alloc_gen++;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) { cudaFree(p); if (tracked) g_alloc_gen++; } p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+
+struct TwiddleEntry { int field; uint32_t log_n; uint8_t omega[32]; DevBuf buf; uint64_t stamp; };
+struct BaseSet {
+    int curve; size_t n; DevBuf buf;
+    DevBuf table; uint32_t c = 0, W = 0;   // W x n window shifts 2^(c w) G_i (bucket method over one shared bucket set)
+    DevBuf dtable;                         // 32 x 128 x n digit multiples m 2^(8 w) G_i (fixedbase.cuh: direct sum, small sets)
+};
+
+struct PolyBuf { int field; size_t len; DevBuf buf; PolyBuf() { buf.tracked = false; } };   // device-resident polynomial, Montgomery form, len + 1 slots
+struct IpaSession {
+    uint64_t bases; uint32_t k, round; int folded; DevBuf p, b, s, scal, out;
+    IpaSession() { p.tracked = b.tracked = s.tracked = scal.tracked = out.tracked = false; }
+};
+
+// A fixed-base MSM over resident bases is ~25 small launches whose parameters repeat call after call (same table, same
+// scratch, same sizes): the second call with a given key is captured into a CUDA graph, later ones replay it.
+struct MsmGraph {
+    const void *scalars, *bases, *out;
+    size_t n; uint64_t stride, gen;
+    uint32_t c, sets; int scalars_mont, out_canonical;
+    uint32_t seen = 0; uint64_t launches = 0, stamp = 0;
+    cudaGraphExec_t exec = nullptr;
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // uploads that may overlap compute (bases of a one-shot MSM)
+    cudaEvent_t ev_scalars_up = nullptr, ev_bases_up[H2_MAX_UPLOAD_CHUNKS] = {}, ev_scal_up[H2_MAX_UPLOAD_CHUNKS] = {};
+    uint32_t chunk_min_log = 19;             // one-shot MSMs of >= 2^19 points upload their bases in chunks
+    cudaEvent_t last_use = nullptr;
+    bool have_last = false;
+    uint32_t window_override = 0;
+    const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
+    uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
+    uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
+    uint32_t accum_ways = 1;                 // quads per work item in the small-problem accumulation (1, 2, 4; test hook).  Measured at
+                                             // k = 14, c = 15: commit 0.360 / 0.329 / 0.361 ms, IPA opening 5.7 / 6.1 / 7.6 ms -- the accumulation is
+                                             // bound by lane-multiplies (a quad addition occupies 16 slots for 10 products), not by its chains
+    uint32_t ecfft_quad = 1;                 // EC-FFT butterfly form: 1 = by size (default), 0 = one thread each, 2 = quads (test hook)
+    // MSM scratch
+    DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
+        wsum, scan_blocks, result, misc;
+    // NTT scratch
+    DevBuf ntt_io, ntt_out, ntt_work, pow2;
+    // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms
+    DevBuf ec_work, ec_io, ec_out;
+    DevBuf fb_a, fb_b;                       // partial sums of the direct-sum fixed-base MSM (ping-pong)
+    DevBuf ast_code, ast_consts;             // asteval.cuh: the postfix program and its constants
+    DevBuf po_lvl, po_q, po_pts, po_ptrs;    // polyops.cuh: level arrays, kate carries, per-level points, pointer arrays
+    std::vector<TwiddleEntry *> twiddles;
+    uint64_t tw_stamp = 0;
+    std::map<uint64_t, BaseSet *> bases;
+    std::map<uint64_t, IpaSession *> ipa;
+    std::map<uint64_t, PolyBuf *> polys;
+    std::vector<MsmGraph> graphs;
+    uint64_t graph_stamp = 0;
+    uint32_t graphs_on = 1;
+    std::vector<IpaSession *> ipa_pool;      // finished sessions keep their buffers for the next proof (no cudaMalloc per opening)
+    uint64_t next_handle = 1;
+};
+// One Context per CUDA device.  g_cur is the context the calling API function works on (the primary device bound by
+// h2_init; the multi-GPU entry points switch it, under g_mu, while they issue work to the other devices).
+extern Context g_ctxs[H2_MAX_DEVICES];
+extern Context *g_cur;
+#define g_ctx (*g_cur)
+extern std::mutex g_mu;
+// optional per-kernel timing (bench.py's roofline leg): event pairs recorded on the launch stream
+struct ProfSpan { int kind; cudaEvent_t e0, e1; };
+extern bool g_prof_on;
+extern std::vector<ProfSpan> g_prof;
+enum { PROF_MSM_ACCUM0 = 0, PROF_NTT_PASS = 1, PROF_KINDS = 2 };
+void prof_begin(int kind, cudaStream_t s);
+void prof_end(cudaStream_t s);
+extern std::atomic<uint64_t> g_launches;
+
+#define LAUNCH(kernel, grid, block, smem, stream, ...)                                                   \
+    do {                                                                                                 \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess) return fail(std::string(#kernel) + " launch: " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int require_ready();
+int scratch_acquire(cudaStream_t s);     // make `s` wait for whatever last used the shared scratch
+int scratch_release(cudaStream_t s);
+static inline uint32_t blocks_for(uint64_t n, uint32_t bs) { return (uint32_t)((n + bs - 1) / bs); }
+
+template <class P> static fe host_to_mont(const void *bytes, int repr) {
+    fe x;
+    memcpy(x.v, bytes, 32);
+    return repr == H2_REPR_MONTGOMERY ? x : fe_to_mont<P>(x);
+}
+static inline PolyBuf *find_poly(uint64_t h) {
+    auto it = g_ctx.polys.find(h);
+    return it == g_ctx.polys.end() ? nullptr : it->second;
+}
+// what a fixed-base MSM over `b` runs on: the digit-multiples table (mode 2) when there is one, else the window table (mode 1)
+#define H2_FB_BITS_CTX 8u
+static inline const affine *fixed_table(const BaseSet *b, uint32_t *c, uint32_t *mode) {
+    if (b->dtable.p) { *c = H2_FB_BITS_CTX; *mode = 2; return b->dtable.as<affine>(); }
+    *c = b->c; *mode = 1;
+    return b->table.as<affine>();
+}
+
+// ---- functions one TU defines and others call -------------------------------------------------------------------
+struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS], ev_scal[H2_MAX_UPLOAD_CHUNKS]; };   // bases / scalars of chunk j have landed
+// capi_msm.cu
+int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
+                 jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0,
+                 const BasesChunks *bc = nullptr, uint32_t sets = 1);
+int convert_points(int curve, affine *d, size_t n, int to_mont, cudaStream_t s);
+// capi_ntt.cu
+int get_twiddles_any(int field, const fe &omega_mont, uint32_t log_n, cudaStream_t s, const fe **out);
+int convert_field(int field, fe *d, size_t n, int to_mont, cudaStream_t s);

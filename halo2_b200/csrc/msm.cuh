@@ -800,7 +800,7 @@ template <class P, class PS> __global__ void __launch_bounds__(64) msm_final_ker
 // exclusive scan of counts[0..G] in place (counts[G] becomes the total), three small kernels
 #define H2_SCAN_BLOCK 1024
 #define H2_SCAN_ITEMS 8
-__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_block_sums_kernel(const uint32_t *in, uint64_t n, uint32_t *block_sums, const uint32_t *only_if) {
+static __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_block_sums_kernel(const uint32_t *in, uint64_t n, uint32_t *block_sums, const uint32_t *only_if) {
     __shared__ uint32_t sh[32];
     if (only_if && !*only_if) return;
     uint64_t base = (uint64_t)blockIdx.x * H2_SCAN_BLOCK * H2_SCAN_ITEMS;
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_block_sums_kernel(const ui
         if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
     }
 }
-__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_single_block_kernel(uint32_t *a, uint32_t n, const uint32_t *only_if) {
+static __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_single_block_kernel(uint32_t *a, uint32_t n, const uint32_t *only_if) {
     // exclusive scan of a[0..n) by one block, n arbitrary (loops in tiles of blockDim)
     __shared__ uint32_t sh[H2_SCAN_BLOCK];
     __shared__ uint32_t carry_s;
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_single_block_kernel(uint32
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_apply_kernel(uint32_t *a, uint64_t n, const uint32_t *block_offsets, const uint32_t *only_if) {
+static __global__ void __launch_bounds__(H2_SCAN_BLOCK) scan_apply_kernel(uint32_t *a, uint64_t n, const uint32_t *block_offsets, const uint32_t *only_if) {
     __shared__ uint32_t sh[H2_SCAN_BLOCK];
     if (only_if && !*only_if) return;
     uint64_t base = (uint64_t)blockIdx.x * H2_SCAN_BLOCK * H2_SCAN_ITEMS + (uint64_t)threadIdx.x * H2_SCAN_ITEMS;
