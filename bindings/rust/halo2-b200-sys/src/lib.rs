@@ -369,7 +369,7 @@ where
     }
     /// <poly, bases[..n]> + r * bases[n]
     pub fn commit(&self, poly: &[C::Scalar], r: C::Scalar) -> C::Curve {
-        assert_eq!(poly.len() + 1, self.n);
+        assert!(poly.len() + 1 <= self.n);   // the blind rides on bases[poly.len()]; an IPA-capable set also holds u behind w
         let s = scalars_to_bytes(poly);
         let rb = r.to_repr();
         let mut out = [0u8; 96];

@@ -3,9 +3,12 @@
 
 static thread_local std::string g_err;
 int fail(const std::string &m) { g_err = m; return 1; }
-uint64_t g_alloc_gen = 0;
+const std::string &last_error_string() { return g_err; }
+std::atomic<uint64_t> g_alloc_gen{0};
 Context g_ctxs[H2_MAX_DEVICES];
-Context *g_cur = &g_ctxs[0];
+Context *g_primary = &g_ctxs[0];
+thread_local Context *g_cur = nullptr;
+std::vector<int> g_multi;                // devices of the multi-GPU entry points (h2_multi_init), primary first
 std::mutex g_mu;
 bool g_prof_on = false;
 std::vector<ProfSpan> g_prof;
@@ -21,6 +24,155 @@ void prof_end(cudaStream_t s) {
     cudaEventRecord(g_prof.back().e1, s);
 }
 std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------
+// staged transfers for pageable caller memory
+// ------------------------------------------------------------------------------------------------
+#include <condition_variable>
+#include <thread>
+namespace {
+struct CopyPool {            // a handful of host threads that memcpy slices in parallel
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::vector<std::thread> threads;
+    uint8_t *dst = nullptr; const uint8_t *src = nullptr; size_t bytes = 0;
+    uint32_t parts = 0, next_part = 0, done_parts = 0; uint64_t job = 0;
+    bool stop = false;
+    void start(unsigned n) {
+        for (unsigned i = 0; i < n; i++) threads.emplace_back([this] { run(); });
+    }
+    void run() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return stop || (job != seen && next_part < parts); });
+            if (stop) return;
+            const uint64_t my_job = job;
+            while (next_part < parts && job == my_job) {
+                const uint32_t p = next_part++;
+                const size_t lo = bytes * p / parts, hi = bytes * (p + 1) / parts;
+                uint8_t *d = dst; const uint8_t *s = src;
+                lk.unlock();
+                memcpy(d + lo, s + lo, hi - lo);
+                lk.lock();
+                if (++done_parts == parts) cv_done.notify_all();
+            }
+            seen = my_job;
+        }
+    }
+    // one job at a time (callers serialise on job_mu); the calling thread takes slices too
+    std::mutex job_mu;
+    void copy(void *d, const void *s, size_t n) {
+        if (n < (1u << 20) || threads.empty()) { memcpy(d, s, n); return; }
+        std::lock_guard<std::mutex> jl(job_mu);
+        std::unique_lock<std::mutex> lk(mu);
+        dst = (uint8_t *)d; src = (const uint8_t *)s; bytes = n;
+        parts = (uint32_t)threads.size() + 1; next_part = 0; done_parts = 0; job++;
+        cv.notify_all();
+        while (next_part < parts) {
+            const uint32_t p = next_part++;
+            const size_t lo = bytes * p / parts, hi = bytes * (p + 1) / parts;
+            lk.unlock();
+            memcpy(dst + lo, src + lo, hi - lo);
+            lk.lock();
+            ++done_parts;
+        }
+        cv_done.wait(lk, [&] { return done_parts == parts; });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+CopyPool *copy_pool() {
+    static CopyPool *P = [] {
+        CopyPool *p = new CopyPool();    // leaked on purpose: worker threads must not be joined from a static destructor
+        unsigned hw = std::thread::hardware_concurrency();
+        p->start(hw >= 16 ? 7 : hw >= 4 ? 3 : 0);
+        return p;
+    }();
+    return P;
+}
+std::atomic<int> g_staging{1};
+}  // namespace
+void h2_set_staging(int on) { g_staging.store(on ? 1 : 0); }
+extern "C" int h2_test_set_staging(int on) { h2_set_staging(on); return 0; }
+
+int StageRing::ensure() {
+    if (slot_bytes) return 0;
+    const size_t sb = 8u << 20;
+    for (int i = 0; i < SLOTS; i++) {
+        CU(cudaHostAlloc((void **)&slot[i], sb, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        busy[i] = false;
+    }
+    slot_bytes = sb;
+    return 0;
+}
+void StageRing::destroy() {
+    if (!slot_bytes) return;
+    for (int i = 0; i < SLOTS; i++) { cudaFreeHost(slot[i]); cudaEventDestroy(done[i]); slot[i] = nullptr; }
+    slot_bytes = 0;
+}
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+int upload_async(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return 0;
+    if (bytes < (256u << 10) || !g_staging.load() || !host_is_pageable(h_src)) {
+        CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    StageRing &R = g_ctx.stage;
+    if (R.ensure()) return 1;
+    CopyPool *P = copy_pool();
+    for (size_t off = 0; off < bytes; off += R.slot_bytes) {
+        const size_t len = bytes - off < R.slot_bytes ? bytes - off : R.slot_bytes;
+        const uint32_t i = R.next++ % StageRing::SLOTS;
+        if (R.busy[i]) CU(cudaEventSynchronize(R.done[i]));
+        P->copy(R.slot[i], (const uint8_t *)h_src + off, len);
+        CU(cudaMemcpyAsync((uint8_t *)d_dst + off, R.slot[i], len, cudaMemcpyHostToDevice, s));
+        CU(cudaEventRecord(R.done[i], s));
+        R.busy[i] = true;
+    }
+    return 0;
+}
+int download_sync(void *h_dst, const void *d_src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) { CU(cudaStreamSynchronize(s)); return 0; }
+    if (bytes < (256u << 10) || !g_staging.load() || !host_is_pageable(h_dst)) {
+        CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return 0;
+    }
+    StageRing &R = g_ctx.stage;
+    if (R.ensure()) return 1;
+    CopyPool *P = copy_pool();
+    // DMA into the slots round-robin; a slot is drained into the caller's buffer before it is reused
+    struct Pending { uint32_t slot; size_t off, len; };
+    std::vector<Pending> q;
+    size_t head = 0;
+    auto drain = [&](const Pending &e) -> int {
+        CU(cudaEventSynchronize(R.done[e.slot]));
+        P->copy((uint8_t *)h_dst + e.off, R.slot[e.slot], e.len);
+        R.busy[e.slot] = false;
+        return 0;
+    };
+    for (size_t off = 0; off < bytes; off += R.slot_bytes) {
+        const size_t len = bytes - off < R.slot_bytes ? bytes - off : R.slot_bytes;
+        const uint32_t i = R.next++ % StageRing::SLOTS;
+        while (head < q.size() && q[head].slot == i) { if (drain(q[head])) return 1; head++; }
+        if (R.busy[i]) CU(cudaEventSynchronize(R.done[i]));     // an upload still in flight from this slot
+        CU(cudaMemcpyAsync(R.slot[i], (const uint8_t *)d_src + off, len, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(R.done[i], s));
+        R.busy[i] = true;
+        q.push_back({i, off, len});
+    }
+    for (; head < q.size(); head++) if (drain(q[head])) return 1;
+    return 0;
+}
 
 int require_ready() {
     if (!g_ctx.ready) return fail("h2_init has not been called (or failed): no CUDA device bound; there is no CPU fallback");
@@ -45,58 +197,99 @@ extern "C" int h2_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
-extern "C" int h2_init(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx.ready && g_ctx.device == device) return 0;
-    if (g_ctx.ready) return fail("h2_init: already bound to another device (one process per GPU)");
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) return fail(std::string("h2_init: no CUDA device: ") + cudaGetErrorString(e));
-    if (device < 0 || device >= n) return fail("h2_init: device index out of range");
+static int ctx_create(Context &C, int device) {
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("h2_init: this library is built for sm_100a (B200) only");
-    CU(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&g_ctx.last_use, cudaEventDisableTiming));
-    CU(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&g_ctx.ev_scalars_up, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&C.last_use, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&C.copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&C.ev_scalars_up, cudaEventDisableTiming));
     for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) {
-        CU(cudaEventCreateWithFlags(&g_ctx.ev_bases_up[j], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&g_ctx.ev_scal_up[j], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&C.ev_bases_up[j], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&C.ev_scal_up[j], cudaEventDisableTiming));
     }
-    g_ctx.device = device;
-    g_ctx.ready = true;
+    C.device = device;
+    C.ready = true;
     return 0;
+}
+static void ctx_destroy(Context &C) {
+    if (!C.ready) return;
+    cudaSetDevice(C.device);
+    cudaDeviceSynchronize();
+    DevBuf *all[] = {&C.scal_in, &C.bases_in, &C.bases_phi, &C.glv_parts, &C.scal_canon, &C.counts, &C.cursor, &C.refs, &C.size_hist,
+                     &C.items, &C.bucket_sum, &C.pkey, &C.pstart, &C.pend, &C.ppt, &C.ra_t, &C.ra_e,
+                     &C.r0, &C.r1, &C.wsum, &C.scan_blocks, &C.result, &C.misc, &C.ntt_io, &C.ntt_out,
+                     &C.ntt_work, &C.pow2, &C.ec_work, &C.ec_io, &C.ec_out, &C.fb_a, &C.fb_b, &C.po_lvl, &C.po_q, &C.po_pts, &C.po_ptrs, &C.ast_code, &C.ast_consts,
+                     &C.multi_parts};
+    for (DevBuf *b : all) b->release();
+    for (auto *t : C.twiddles) { t->buf.release(); delete t; }
+    C.twiddles.clear();
+    for (auto &kv : C.bases) { kv.second->buf.release(); kv.second->table.release(); kv.second->dtable.release(); delete kv.second; }
+    C.bases.clear();
+    for (auto &kv : C.ipa) { IpaSession *q = kv.second; q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
+    C.ipa.clear();
+    for (auto &kv : C.polys) { kv.second->buf.release(); delete kv.second; }
+    C.polys.clear();
+    for (auto &ge : C.graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
+    C.graphs.clear();
+    for (IpaSession *q : C.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
+    C.ipa_pool.clear();
+    C.stage.destroy();
+    cudaEventDestroy(C.ev_scalars_up);
+    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) { cudaEventDestroy(C.ev_bases_up[j]); cudaEventDestroy(C.ev_scal_up[j]); }
+    cudaStreamDestroy(C.copy_stream);
+    cudaEventDestroy(C.last_use);
+    cudaStreamDestroy(C.stream);
+    C = Context();
+}
+extern "C" int h2_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_primary->ready && g_primary->device == device) return 0;
+    if (g_primary->ready) return fail("h2_init: already bound to another device (one process per GPU; h2_multi_init adds devices)");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(std::string("h2_init: no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n || device >= H2_MAX_DEVICES) return fail("h2_init: device index out of range");
+    if (ctx_create(g_ctxs[device], device)) { ctx_destroy(g_ctxs[device]); return 1; }
+    g_primary = &g_ctxs[device];
+    return 0;
+}
+// Single-process multi-GPU (a Rust caller of best_multiexp is ONE process): binds contexts to
+// `ngpu` devices -- the primary one first, then the others in index order -- and enables peer access to the primary.
+extern "C" int h2_multi_init(int ngpu) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (ngpu < 1 || ngpu > n || ngpu > H2_MAX_DEVICES) return fail("h2_multi_init: ngpu out of range (" + std::to_string(n) + " devices visible)");
+    const int prim = g_primary->device;
+    std::vector<int> devs{prim};
+    for (int d = 0; d < n && (int)devs.size() < ngpu; d++) if (d != prim) devs.push_back(d);
+    for (int d : devs) {
+        if (g_ctxs[d].ready) continue;
+        if (ctx_create(g_ctxs[d], d)) { ctx_destroy(g_ctxs[d]); cudaSetDevice(prim); return 1; }
+        // settings follow the primary context
+        g_ctxs[d].glv_on = g_primary->glv_on; g_ctxs[d].sort_bins = g_primary->sort_bins; g_ctxs[d].window_override = g_primary->window_override;
+        g_ctxs[d].chunk_min_log = g_primary->chunk_min_log;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, d, prim) == cudaSuccess && can) { cudaSetDevice(d); if (cudaDeviceEnablePeerAccess(prim, 0) != cudaSuccess) cudaGetLastError(); }
+        if (cudaDeviceCanAccessPeer(&can, prim, d) == cudaSuccess && can) { cudaSetDevice(prim); if (cudaDeviceEnablePeerAccess(d, 0) != cudaSuccess) cudaGetLastError(); }
+    }
+    CU(cudaSetDevice(prim));
+    g_multi = devs;
+    return 0;
+}
+extern "C" int h2_multi_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return (int)g_multi.size();
 }
 extern "C" int h2_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return 0;
-    cudaSetDevice(g_ctx.device);
-    cudaDeviceSynchronize();
-    DevBuf *all[] = {&g_ctx.scal_in, &g_ctx.bases_in, &g_ctx.bases_phi, &g_ctx.glv_parts, &g_ctx.scal_canon, &g_ctx.counts, &g_ctx.cursor, &g_ctx.refs, &g_ctx.size_hist,
-                     &g_ctx.items, &g_ctx.bucket_sum, &g_ctx.pkey, &g_ctx.pstart, &g_ctx.pend, &g_ctx.ppt, &g_ctx.ra_t, &g_ctx.ra_e,
-                     &g_ctx.r0, &g_ctx.r1, &g_ctx.wsum, &g_ctx.scan_blocks, &g_ctx.result, &g_ctx.misc, &g_ctx.ntt_io, &g_ctx.ntt_out,
-                     &g_ctx.ntt_work, &g_ctx.pow2, &g_ctx.ec_work, &g_ctx.ec_io, &g_ctx.ec_out, &g_ctx.fb_a, &g_ctx.fb_b, &g_ctx.po_lvl, &g_ctx.po_q, &g_ctx.po_pts, &g_ctx.po_ptrs, &g_ctx.ast_code, &g_ctx.ast_consts};
-    for (DevBuf *b : all) b->release();
-    for (auto *t : g_ctx.twiddles) { t->buf.release(); delete t; }
-    g_ctx.twiddles.clear();
-    for (auto &kv : g_ctx.bases) { kv.second->buf.release(); kv.second->table.release(); kv.second->dtable.release(); delete kv.second; }
-    g_ctx.bases.clear();
-    for (auto &kv : g_ctx.ipa) { IpaSession *q = kv.second; q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
-    g_ctx.ipa.clear();
-    for (auto &kv : g_ctx.polys) { kv.second->buf.release(); delete kv.second; }
-    g_ctx.polys.clear();
-    for (auto &ge : g_ctx.graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
-    g_ctx.graphs.clear();
-    for (IpaSession *q : g_ctx.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
-    g_ctx.ipa_pool.clear();
-    cudaEventDestroy(g_ctx.ev_scalars_up);
-    for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) { cudaEventDestroy(g_ctx.ev_bases_up[j]); cudaEventDestroy(g_ctx.ev_scal_up[j]); }
-    cudaStreamDestroy(g_ctx.copy_stream);
-    cudaEventDestroy(g_ctx.last_use);
-    cudaStreamDestroy(g_ctx.stream);
-    g_ctx = Context();
+    for (int d = 0; d < H2_MAX_DEVICES; d++) ctx_destroy(g_ctxs[d]);
+    g_multi.clear();
+    g_primary = &g_ctxs[0];
     return 0;
 }
 extern "C" int h2_set_glv(int on) {

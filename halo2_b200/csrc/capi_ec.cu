@@ -42,7 +42,7 @@ static int ecfft_host(int scalar_field, int mode, const void *in, uint32_t log_n
     if (in) {
         if (scratch_acquire(s)) return 1;
         if (X.ec_io.ensure(n * sizeof(jacobian))) return 1;
-        CU(cudaMemcpyAsync(X.ec_io.p, in, n * in_sz, cudaMemcpyHostToDevice, s));
+        if (upload_async(X.ec_io.p, in, n * in_sz, s)) return 1;
     }
     if (X.ec_work.ensure(n * sizeof(xyzz)) || X.ec_out.ensure(n * sizeof(affine))) return 1;
     xyzz *work = X.ec_work.as<xyzz>();

@@ -97,11 +97,12 @@ template <class P, class PS>
 static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c, uint32_t fixed, uint64_t stride,
                    jacobian *d_out, int out_canonical, cudaStream_t s, const BasesChunks *bc = nullptr, uint32_t sets = 1) {
     Context &X = g_ctx;
-    if (n == 0) {   // empty sum = identity
+    if (n == 0) {   // empty sum = identity, one per scalar vector
         jacobian id;
         id.x = fe_zero(); id.y = out_canonical ? fe_zero() : fe_one<P>(); id.z = fe_zero();
         if (out_canonical) id.y.v[0] = 1;
-        CU(cudaMemcpyAsync(d_out, &id, sizeof id, cudaMemcpyHostToDevice, s));
+        std::vector<jacobian> ids(sets ? sets : 1u, id);
+        CU(cudaMemcpyAsync(d_out, ids.data(), ids.size() * sizeof id, cudaMemcpyHostToDevice, s));
         CU(cudaStreamSynchronize(s));
         return 0;
     }
@@ -219,7 +220,10 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
             const MsmPlan &q = pk[j];
             const MsmBuffers &M = Mk[j];
             if (bc && bc->k) {   // the scalars of this chunk (K == 1: of every chunk of the upload)
-                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev_scal[e], 0));
+                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) {
+                    if (bc->wait_recorded(2 * e + 1)) return fail("msm: the upload of the inputs failed");
+                    CU(cudaStreamWaitEvent(s, bc->ev_scal[e], 0));
+                }
             }
             // K2/K3: the (point, window) references sorted by bucket -- a single pass into per-bucket bins; the exact
             // histogram / scan / scatter kernels run only if a bin overflowed (flags[1], set by the bin kernel) or if there
@@ -234,7 +238,10 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
             LAUNCH(k_ibases, 1, 32, 0, s, q, M);
             LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
             if (bc && bc->k) {   // the sort above only needed the scalars
-                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) CU(cudaStreamWaitEvent(s, bc->ev[e], 0));
+                for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) {
+                    if (bc->wait_recorded(2 * e + 2)) return fail("msm: the upload of the inputs failed");
+                    CU(cudaStreamWaitEvent(s, bc->ev[e], 0));
+                }
             }
             if (q.glv) {
                 auto k_phi = msm_phi_kernel<P, PS>;
@@ -339,14 +346,19 @@ extern "C" int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, co
 
 // host_bases != nullptr: one-shot MSM -- the bases are uploaded (and converted) on the copy stream AFTER the
 // scalars, overlapping the digit/sort kernels, which only read scalars.
+// d_result_peer != nullptr (multi-GPU worker): the 96-byte result goes to that address on device `peer_dev` instead of the host.
 static int msm_host_common(int curve, const void *scalars, size_t n_scalars, const void *extra_scalar, const affine *d_bases,
                            size_t n_total, int repr, void *out_xyz, uint32_t c = 0, uint32_t fixed = 0, uint64_t stride = 0,
-                           const void *host_bases = nullptr) {
+                           const void *host_bases = nullptr, void *d_result_peer = nullptr, int peer_dev = -1) {
     Context &X = g_ctx;
     cudaStream_t s = X.stream;
     if (scratch_acquire(s)) return 1;
     if (X.scal_in.ensure((n_total + 1) * sizeof(fe)) || X.result.ensure(sizeof(jacobian))) return 1;
     BasesChunks bc;
+    std::atomic<uint32_t> recorded{0};
+    std::atomic<int> up_failed{0};
+    std::string up_err;
+    std::thread uploader;
     if (host_bases && n_total) {
         // One-shot MSM: everything goes up on the copy stream, interleaved per chunk -- scalars of chunk j, then its
         // bases -- so that the sort of chunk j starts when its scalars have landed and its accumulation when its bases
@@ -359,24 +371,43 @@ static int msm_host_common(int curve, const void *scalars, size_t n_scalars, con
         if (n_total >= ((size_t)1 << X.chunk_min_log) && n_total >= 16 * H2_MAX_UPLOAD_CHUNKS)
             bc.k = n_total >= ((size_t)8 << X.chunk_min_log) ? H2_MAX_UPLOAD_CHUNKS : n_total >= ((size_t)2 << X.chunk_min_log) ? 3u : 2u;
         affine *db = const_cast<affine *>(d_bases);
-        for (uint32_t j = 0; j < bc.k; j++) {
-            size_t lo = chunk_first(n_total, bc.k, j), hi = chunk_first(n_total, bc.k, j + 1);
-            CU(cudaMemcpyAsync(X.scal_in.as<fe>() + lo, (const fe *)scalars + lo, (hi - lo) * sizeof(fe), cudaMemcpyHostToDevice, cs));
-            CU(cudaEventRecord(X.ev_scal_up[j], cs));
-            bc.ev_scal[j] = X.ev_scal_up[j];
-            CU(cudaMemcpyAsync(db + lo, (const affine *)host_bases + lo, (hi - lo) * sizeof(affine), cudaMemcpyHostToDevice, cs));
-            if (repr == H2_REPR_CANONICAL && convert_points(curve, db + lo, hi - lo, 1, cs)) return 1;
-            CU(cudaEventRecord(X.ev_bases_up[j], cs));
-            bc.ev[j] = X.ev_bases_up[j];
-        }
+        for (uint32_t j = 0; j < bc.k; j++) { bc.ev_scal[j] = X.ev_scal_up[j]; bc.ev[j] = X.ev_bases_up[j]; }
+        bc.recorded = &recorded; bc.failed = &up_failed;
+        Context *ctx = &X;
+        const uint32_t k = bc.k;
+        // The uploads run on their own host thread: from pageable caller memory they are staged through the pinned ring
+        // (upload_async blocks while it copies), and the kernels of chunk j must be issued while chunk j + 1 is staged.
+        auto upload = [=, &recorded, &up_failed, &up_err]() {
+            g_cur = ctx;
+            auto run = [&]() -> int {
+                CU(cudaSetDevice(ctx->device));
+                for (uint32_t j = 0; j < k; j++) {
+                    size_t lo = chunk_first(n_total, k, j), hi = chunk_first(n_total, k, j + 1);
+                    if (upload_async(ctx->scal_in.as<fe>() + lo, (const fe *)scalars + lo, (hi - lo) * sizeof(fe), cs)) return 1;
+                    CU(cudaEventRecord(ctx->ev_scal_up[j], cs));
+                    recorded.store(2 * j + 1, std::memory_order_release);
+                    if (upload_async(db + lo, (const affine *)host_bases + lo, (hi - lo) * sizeof(affine), cs)) return 1;
+                    if (repr == H2_REPR_CANONICAL && convert_points(curve, db + lo, hi - lo, 1, cs)) return 1;
+                    CU(cudaEventRecord(ctx->ev_bases_up[j], cs));
+                    recorded.store(2 * j + 2, std::memory_order_release);
+                }
+                return 0;
+            };
+            if (run()) { up_err = last_error_string(); up_failed.store(1); }
+        };
+        if (n_total * sizeof(affine) >= (4u << 20)) uploader = std::thread(upload);
+        else upload();                                        // small: not worth a thread
     } else {
-        if (n_scalars) CU(cudaMemcpyAsync(X.scal_in.p, scalars, n_scalars * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (n_scalars && upload_async(X.scal_in.p, scalars, n_scalars * sizeof(fe), s)) return 1;
         if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
     }
     int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
                           repr == H2_REPR_CANONICAL, s, fixed, stride, bc.k ? &bc : nullptr);
+    if (uploader.joinable()) uploader.join();
+    if (up_failed.load()) { cudaStreamSynchronize(s); cudaStreamSynchronize(X.copy_stream); return fail(up_err); }
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (d_result_peer) CU(cudaMemcpyPeerAsync(d_result_peer, peer_dev, X.result.p, X.device, sizeof(jacobian), s));
+    else CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
     if (scratch_release(s)) return 1;
     CU(cudaStreamSynchronize(s));
     return 0;
@@ -408,12 +439,13 @@ static int bases_register_impl(int curve, const void *bases_xy, size_t n, int re
     b->curve = curve; b->n = n;
     if (b->buf.ensure((n + 1) * sizeof(affine))) { delete b; return 1; }
     cudaStream_t s = g_ctx.stream;
-    if (n) CU(cudaMemcpyAsync(b->buf.p, bases_xy, n * sizeof(affine), cudaMemcpyHostToDevice, s));
-    if (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), n, 1, s)) return 1;
+    auto drop = [&]() { cudaStreamSynchronize(s); b->buf.release(); b->table.release(); b->dtable.release(); delete b; return 1; };
+    if (n && upload_async(b->buf.p, bases_xy, n * sizeof(affine), s)) return drop();
+    if (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), n, 1, s)) return drop();
     const bool direct = (flags & H2_BASES_DIRECT) && (flags & H2_BASES_PRECOMPUTE) && n > 0;
-    if ((flags & H2_BASES_PRECOMPUTE) && n > 0 && build_table(b, direct ? H2_FB_BITS : window_bits, s)) return 1;
-    if (direct && build_direct(b, s)) return 1;
-    CU(cudaStreamSynchronize(s));
+    if ((flags & H2_BASES_PRECOMPUTE) && n > 0 && build_table(b, direct ? H2_FB_BITS : window_bits, s)) return drop();
+    if (direct && build_direct(b, s)) return drop();
+    if (cudaStreamSynchronize(s) != cudaSuccess) { fail("h2_bases_register: device error while building the tables"); return drop(); }
     uint64_t h = g_ctx.next_handle++;
     g_ctx.bases[h] = b;
     *handle = h;
@@ -480,7 +512,7 @@ static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_
     if (X.scal_in.ensure(batch * total * sizeof(fe)) || X.result.ensure(batch * sizeof(jacobian))) return 1;
     fe *d = X.scal_in.as<fe>();
     if (!extra_scalars) {
-        CU(cudaMemcpyAsync(d, scalars, batch * n * sizeof(fe), cudaMemcpyHostToDevice, s));
+        if (upload_async(d, scalars, batch * n * sizeof(fe), s)) return 1;
     } else {   // interleave: [poly_k (n) | blind_k] per vector
         CU(cudaMemcpy2DAsync(d, total * sizeof(fe), scalars, n * sizeof(fe), n * sizeof(fe), batch, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpy2DAsync(d + n, total * sizeof(fe), extra_scalars, sizeof(fe), sizeof(fe), batch, cudaMemcpyHostToDevice, s));
@@ -526,6 +558,162 @@ extern "C" int h2_point_sum(int curve, const void *points_xyz, size_t g, int rep
 }
 
 
+// device-pointer form (the partial results of an NCCL all-gather stay on the device): Montgomery in, Montgomery out
+extern "C" int h2_point_sum_dev(int curve, const void *d_points_xyz, size_t g, void *d_out_xyz, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(point_sum_kernel<FpParams>, 1, 32, 0, s, (const jacobian *)d_points_xyz, (uint32_t)g, 0, (jacobian *)d_out_xyz);
+    else if (curve == H2_CURVE_VESTA) LAUNCH(point_sum_kernel<FqParams>, 1, 32, 0, s, (const jacobian *)d_points_xyz, (uint32_t)g, 0, (jacobian *)d_out_xyz);
+    else return fail("unknown curve id");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-process multi-GPU MSM (SURVEY.md section 8(b) `h2_msm_multi_gpu`, section 8(e)): contiguous shards of the
+// (scalar, base) arrays, one worker thread and one full single-GPU pipeline per device, the 96-byte partial results written
+// into the primary device's memory over NVLink (peer copy), one G-term sum there.  Results are the same group element
+// whatever the number of devices.
+// ------------------------------------------------------------------------------------------------
+extern std::vector<int> g_multi;
+static inline void shard_range(size_t n, size_t g, size_t G, size_t *lo, size_t *hi) {
+    const size_t base = n / G, rem = n % G;
+    *lo = g * base + (g < rem ? g : rem);
+    *hi = *lo + base + (g < rem ? 1 : 0);
+}
+// runs fn(g) on one thread per device with that device's context current; collects the first error
+static int multi_run(const std::function<int(size_t)> &fn) {
+    const size_t G = g_multi.size();
+    std::vector<std::string> errs(G);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++)
+        th.emplace_back([&, g]() {
+            g_cur = &g_ctxs[g_multi[g]];
+            if (cudaSetDevice(g_multi[g]) != cudaSuccess) { rcs[g] = 1; errs[g] = "cudaSetDevice failed"; return; }
+            rcs[g] = fn(g);
+            if (rcs[g]) errs[g] = last_error_string();
+        });
+    for (auto &t : th) t.join();
+    cudaSetDevice(g_primary->device);
+    for (size_t g = 0; g < G; g++) if (rcs[g]) return fail("device " + std::to_string(g_multi[g]) + ": " + errs[g]);
+    return 0;
+}
+static int multi_finish(int curve, int repr, void *out_xyz) {     // the G-term sum on the primary device
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    const size_t G = g_multi.size();
+    const int canon = repr == H2_REPR_CANONICAL;
+    if (X.result.ensure(sizeof(jacobian))) return 1;
+    if (curve == H2_CURVE_PALLAS) LAUNCH(point_sum_kernel<FpParams>, 1, 32, 0, s, X.multi_parts.as<jacobian>(), (uint32_t)G, canon, X.result.as<jacobian>());
+    else LAUNCH(point_sum_kernel<FqParams>, 1, 32, 0, s, X.multi_parts.as<jacobian>(), (uint32_t)G, canon, X.result.as<jacobian>());
+    CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+extern "C" int h2_msm_multi_gpu(int curve, const void *scalars, const void *bases_xy, size_t n, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+    if (g_multi.empty()) return fail("h2_msm_multi_gpu: call h2_multi_init first");
+    const size_t G = g_multi.size();
+    Context &P0 = *g_primary;
+    if (P0.multi_parts.ensure(G * sizeof(jacobian))) return 1;
+    jacobian *parts = P0.multi_parts.as<jacobian>();
+    const int prim = P0.device;
+    int rc = multi_run([&](size_t g) -> int {
+        Context &X = g_ctx;
+        size_t lo, hi;
+        shard_range(n, g, G, &lo, &hi);
+        if (scratch_acquire(X.stream)) return 1;
+        if (X.bases_in.ensure((hi - lo + 1) * sizeof(affine))) return 1;
+        return msm_host_common(curve, (const fe *)scalars + lo, hi - lo, nullptr, X.bases_in.as<affine>(), hi - lo, repr, nullptr, 0, 0, 0,
+                               (const affine *)bases_xy + lo, parts + g, prim);
+    });
+    if (rc) return rc;
+    return multi_finish(curve, repr, out_xyz);
+}
+// resident shards: bases[lo_g, hi_g) live on device g (handle valid for h2_msm_multi_registered only)
+struct MultiBases { int curve; size_t n; std::vector<uint64_t> handles; };
+static std::map<uint64_t, MultiBases> g_multi_bases;
+static uint64_t g_multi_next = 1;
+extern "C" int h2_multi_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (require_ready()) return 1;
+        if (curve != H2_CURVE_PALLAS && curve != H2_CURVE_VESTA) return fail("unknown curve id");
+        if (g_multi.empty()) return fail("h2_multi_bases_register: call h2_multi_init first");
+    }
+    const size_t G = g_multi.size();
+    MultiBases mb;
+    mb.curve = curve; mb.n = n; mb.handles.assign(G, 0);
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = multi_run([&](size_t g) -> int {
+        Context &X = g_ctx;
+        size_t lo, hi;
+        shard_range(n, g, G, &lo, &hi);
+        BaseSet *b = new BaseSet();
+        b->curve = curve; b->n = hi - lo;
+        if (b->buf.ensure((hi - lo + 1) * sizeof(affine))) { delete b; return 1; }
+        cudaStream_t s = X.stream;
+        if (upload_async(b->buf.p, (const affine *)bases_xy + lo, (hi - lo) * sizeof(affine), s) ||
+            (repr == H2_REPR_CANONICAL && convert_points(curve, b->buf.as<affine>(), hi - lo, 1, s)) ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            cudaStreamSynchronize(s); b->buf.release(); delete b;
+            return fail("h2_multi_bases_register: upload failed");
+        }
+        mb.handles[g] = X.next_handle++;
+        X.bases[mb.handles[g]] = b;
+        return 0;
+    });
+    if (rc) return rc;
+    *handle = g_multi_next++;
+    g_multi_bases[*handle] = mb;
+    return 0;
+}
+extern "C" int h2_multi_bases_release(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_multi_bases.find(handle);
+    if (it == g_multi_bases.end()) return fail("h2_multi_bases_release: unknown handle");
+    MultiBases mb = it->second;
+    g_multi_bases.erase(it);
+    return multi_run([&](size_t g) -> int {
+        Context &X = g_ctx;
+        auto ib = X.bases.find(mb.handles[g]);
+        if (ib == X.bases.end()) return 0;
+        cudaDeviceSynchronize();
+        ib->second->buf.release(); ib->second->table.release(); ib->second->dtable.release();
+        delete ib->second;
+        X.bases.erase(ib);
+        return 0;
+    });
+}
+extern "C" int h2_msm_multi_registered(uint64_t handle, const void *scalars, size_t n, int repr, void *out_xyz) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    auto it = g_multi_bases.find(handle);
+    if (it == g_multi_bases.end()) return fail("h2_msm_multi_registered: unknown handle");
+    const MultiBases &mb = it->second;
+    if (n != mb.n) return fail("h2_msm_multi_registered: scalar count differs from the registered bases");
+    if (mb.handles.size() != g_multi.size()) return fail("h2_msm_multi_registered: the device set changed since registration");
+    const size_t G = g_multi.size();
+    Context &P0 = *g_primary;
+    if (P0.multi_parts.ensure(G * sizeof(jacobian))) return 1;
+    jacobian *parts = P0.multi_parts.as<jacobian>();
+    const int prim = P0.device;
+    int rc = multi_run([&](size_t g) -> int {
+        Context &X = g_ctx;
+        size_t lo, hi;
+        shard_range(n, g, G, &lo, &hi);
+        auto ib = X.bases.find(mb.handles[g]);
+        if (ib == X.bases.end()) return fail("h2_msm_multi_registered: a shard was released");
+        return msm_host_common(mb.curve, (const fe *)scalars + lo, hi - lo, nullptr, ib->second->buf.as<affine>(), hi - lo, repr, nullptr, 0, 0, 0,
+                               nullptr, parts + g, prim);
+    });
+    if (rc) return rc;
+    return multi_finish(mb.curve, repr, out_xyz);
+}
+
 // ------------------------------------------------------------------------------------------------
 static void ipa_free(IpaSession *q) {   // back to the pool (the caller has synchronised the stream)
     if (g_ctx.ipa_pool.size() < 2) { g_ctx.ipa_pool.push_back(q); return; }
@@ -542,7 +730,7 @@ template <class PS> static int ipa_begin_impl(IpaSession *q, const void *p_prime
     if (q->p.ensure(n * sizeof(fe)) || q->b.ensure(n * sizeof(fe)) || q->s.ensure(n * sizeof(fe)) || q->scal.ensure(2 * (n + 2) * sizeof(fe)) ||
         q->out.ensure(2 * sizeof(jacobian)) || X.pow2.ensure(64 * sizeof(fe)))
         return 1;
-    CU(cudaMemcpyAsync(q->p.p, p_prime, n * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (upload_async(q->p.p, p_prime, n * sizeof(fe), s)) return 1;
     IpaState S = ipa_state(q);
     LAUNCH(ipa_init_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, repr == H2_REPR_MONTGOMERY);
     // b_t = x3^t (prover.rs:86-93) with the NTT twiddle generator

@@ -112,12 +112,10 @@ static int ntt_host(int field, int mode, const void *a_in, uint32_t in_log_n, ui
     if (zeta) z = host_to_mont<P>(zeta, repr);
     if (divisor) d = host_to_mont<P>(divisor, repr);
     NttScales sc = make_scales<P>(repr, mode == 2 ? &z : nullptr, (mode == 1 || mode == 3) ? &d : nullptr, mode == 3 ? &z : nullptr);
-    CU(cudaMemcpyAsync(X.ntt_io.p, a_in, n_in * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (upload_async(X.ntt_io.p, a_in, n_in * sizeof(fe), s)) return 1;
     if (ntt_run<P>(field, X.ntt_io.as<fe>(), in_log_n, X.ntt_out.as<fe>(), log_n, w, sc, out_len, s)) return 1;
-    CU(cudaMemcpyAsync(out, X.ntt_out.p, out_len * sizeof(fe), cudaMemcpyDeviceToHost, s));
-    if (scratch_release(s)) return 1;
-    CU(cudaStreamSynchronize(s));
-    return 0;
+    if (download_sync(out, X.ntt_out.p, out_len * sizeof(fe), s)) return 1;
+    return scratch_release(s);
 }
 static int ntt_host_dispatch(int field, int mode, const void *a_in, uint32_t in_log_n, uint32_t log_n, const void *omega, const void *zeta,
                              const void *divisor, size_t out_len, void *out, int repr) {
@@ -182,6 +180,8 @@ extern "C" int h2_poly_alloc(int field, size_t len, uint64_t *poly) {
     PolyBuf *b = new PolyBuf();
     b->field = field; b->len = len;
     if (b->buf.ensure((len + 1) * sizeof(fe))) { delete b; return 1; }
+    // zero-filled: a commit after a partial upload, or of a quotient shorter than the buffer, must not read stale memory
+    if (cudaMemsetAsync(b->buf.p, 0, (len + 1) * sizeof(fe), g_ctx.stream) != cudaSuccess) { b->buf.release(); delete b; return fail("h2_poly_alloc: memset failed"); }
     uint64_t h = g_ctx.next_handle++;
     g_ctx.polys[h] = b;
     *poly = h;
@@ -211,7 +211,7 @@ extern "C" int h2_poly_upload(uint64_t poly, const void *src, size_t len, int re
     if (!b) return fail("h2_poly_upload: unknown handle");
     if (len > b->len) return fail("h2_poly_upload: more elements than the polynomial holds");
     cudaStream_t s = g_ctx.stream;
-    CU(cudaMemcpyAsync(b->buf.p, src, len * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (upload_async(b->buf.p, src, len * sizeof(fe), s)) return 1;
     if (repr == H2_REPR_CANONICAL && convert_field(b->field, b->buf.as<fe>(), len, 1, s)) return 1;
     CU(cudaStreamSynchronize(s));      // src may be pageable
     return 0;
@@ -232,9 +232,8 @@ extern "C" int h2_poly_download(uint64_t poly, void *dst, size_t len, int repr) 
         if (convert_field(b->field, X.ntt_out.as<fe>(), len, 0, s)) return 1;
         from = X.ntt_out.as<fe>();
     }
-    CU(cudaMemcpyAsync(dst, from, len * sizeof(fe), cudaMemcpyDeviceToHost, s));
+    if (download_sync(dst, from, len * sizeof(fe), s)) return 1;
     if (repr == H2_REPR_CANONICAL && scratch_release(s)) return 1;
-    CU(cudaStreamSynchronize(s));
     return 0;
 }
 // mode as in ntt_host: 1 = inverse transform with divisor, 2 = coeff_to_extended, 3 = extended_to_coeff

@@ -69,6 +69,9 @@ static int polyops_run(int mode, const std::vector<PolyBuf *> &a, const std::vec
         LAUNCH(poly_kate_down_kernel<P>, grid, 128, 0, s, l == 0 ? d_a : (const fe *const *)nullptr, l == 0 ? (const fe *)nullptr : (const fe *)level(l), m[l],
                (const fe *)(pts + l * batch), carry, m[l + 1], l == 0 ? (fe *)nullptr : qlevel(l), l == 0 ? d_q : (fe *const *)nullptr);
     }
+    // the quotient has n - 1 coefficients; slot n - 1 becomes the zero the reference pushes before committing n of them
+    // (poly/multiopen/prover.rs: `kate_division(..); poly.push(ZERO)`)
+    for (uint32_t b = 0; b < batch; b++) CU(cudaMemsetAsync(c[b]->buf.as<fe>() + (n - 1), 0, sizeof(fe), s));
     return scratch_release(s);
 }
 static int polyops_dispatch(int mode, const uint64_t *ah, const uint64_t *ch, size_t batch, size_t n, const void *points, int repr, void *out,
@@ -90,9 +93,14 @@ static int polyops_dispatch(int mode, const uint64_t *ah, const uint64_t *ch, si
             if (!c[b]) return fail(std::string(who) + ": unknown polynomial handle");
             if (c[b]->field != a[0]->field) return fail(std::string(who) + ": the polynomials live in different fields");
             if (c[b]->len + (mode == 2 ? 1 : 0) < n) return fail(std::string(who) + ": the second polynomial is too short");
-            if (mode == 2 && c[b] == a[b]) return fail(std::string(who) + ": the quotient cannot overwrite its dividend");
         }
     }
+    if (mode == 2)   // batch slices run concurrently: no quotient may be another slice's dividend, or be written twice
+        for (size_t b = 0; b < batch; b++)
+            for (size_t b2 = 0; b2 < batch; b2++) {
+                if (c[b] == a[b2]) return fail(std::string(who) + ": the quotient cannot overwrite a dividend");
+                if (b2 < b && c[b] == c[b2]) return fail(std::string(who) + ": a quotient handle appears twice");
+            }
     if (a[0]->field == H2_FIELD_FP) return polyops_run<FpParams>(mode, a, c, n, points, repr, out);
     return polyops_run<FqParams>(mode, a, c, n, points, repr, out);
 }

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/halo2_b200.h"
@@ -26,6 +27,7 @@ using namespace h2;
 // errors, context
 // ------------------------------------------------------------------------------------------------
 int fail(const std::string &m);          // sets the calling thread's last error, returns 1
+const std::string &last_error_string();  // the calling thread's last error (worker threads hand theirs to the caller)
 #define CU(expr)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (expr);                                                                         \
@@ -36,7 +38,7 @@ int fail(const std::string &m);          // sets the calling thread's last error
 // (re)allocation or release of a TRACKED buffer bumps the generation and invalidates them.  Buffers a graph can only see
 // through its key (caller polynomials, IPA session vectors: the scalars / out pointers are part of the key) are untracked --
 // allocating a ResidentPoly between two commits must not throw the commit graphs away.
-extern uint64_t g_alloc_gen;
+extern std::atomic<uint64_t> g_alloc_gen;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -79,6 +81,21 @@ struct MsmGraph {
     cudaGraphExec_t exec = nullptr;
 };
 
+// Pinned staging ring for transfers from / to PAGEABLE caller memory (a Rust Vec, a numpy array): a plain cudaMemcpyAsync
+// from pageable memory is staged by the driver through one thread and runs at a fraction of the link rate, and it blocks
+// the caller so nothing overlaps.  Here a small pool of host threads copies slot-sized pieces into pinned slots while the
+// DMA engine drains the previous ones (capi_core.cu: upload_async / download_sync).
+struct StageRing {
+    enum { SLOTS = 4 };
+    uint8_t *slot[SLOTS] = {};
+    size_t slot_bytes = 0;
+    cudaEvent_t done[SLOTS] = {};
+    bool busy[SLOTS] = {};
+    uint32_t next = 0;
+    int ensure();
+    void destroy();
+};
+
 struct Context {
     bool ready = false;
     int device = -1;
@@ -104,6 +121,8 @@ struct Context {
     // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms
     DevBuf ec_work, ec_io, ec_out;
     DevBuf fb_a, fb_b;                       // partial sums of the direct-sum fixed-base MSM (ping-pong)
+    DevBuf multi_parts;                      // primary device: the per-GPU partial results of a multi-GPU MSM (peer-written)
+    StageRing stage;
     DevBuf ast_code, ast_consts;             // asteval.cuh: the postfix program and its constants
     DevBuf po_lvl, po_q, po_pts, po_ptrs;    // polyops.cuh: level arrays, kate carries, per-level points, pointer arrays
     std::vector<TwiddleEntry *> twiddles;
@@ -117,11 +136,15 @@ struct Context {
     std::vector<IpaSession *> ipa_pool;      // finished sessions keep their buffers for the next proof (no cudaMalloc per opening)
     uint64_t next_handle = 1;
 };
-// One Context per CUDA device.  g_cur is the context the calling API function works on (the primary device bound by
-// h2_init; the multi-GPU entry points switch it, under g_mu, while they issue work to the other devices).
+// One Context per CUDA device.  API functions work on the PRIMARY context (the device h2_init bound); the multi-GPU
+// entry points (h2_multi_*) run one worker thread per device, each of which points its thread-local g_cur at its device's
+// context while the calling thread holds g_mu -- so all the single-GPU code below runs unchanged, concurrently, on every
+// device.
 extern Context g_ctxs[H2_MAX_DEVICES];
-extern Context *g_cur;
-#define g_ctx (*g_cur)
+extern Context *g_primary;
+extern thread_local Context *g_cur;
+static inline Context &cur_ctx() { return *(g_cur ? g_cur : g_primary); }
+#define g_ctx (cur_ctx())
 extern std::mutex g_mu;
 // optional per-kernel timing (bench.py's roofline leg): event pairs recorded on the launch stream
 struct ProfSpan { int kind; cudaEvent_t e0, e1; };
@@ -140,6 +163,13 @@ extern std::atomic<uint64_t> g_launches;
         if (e_ != cudaSuccess) return fail(std::string(#kernel) + " launch: " + cudaGetErrorString(e_)); \
     } while (0)
 
+// Host -> device copy on stream `s` that keeps the link busy whatever the caller's memory is: pinned / registered memory
+// goes straight to cudaMemcpyAsync (the source must then stay valid until the stream has run it -- every caller synchronises
+// before returning); pageable memory goes through the context's pinned ring and has been fully READ when this returns.
+int upload_async(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s);
+// Device -> host copy ordered behind the work already on `s`; returns when the data is in h_dst.
+int download_sync(void *h_dst, const void *d_src, size_t bytes, cudaStream_t s);
+void h2_set_staging(int on);             // test / bench hook: 0 = always plain cudaMemcpyAsync
 int require_ready();
 int scratch_acquire(cudaStream_t s);     // make `s` wait for whatever last used the shared scratch
 int scratch_release(cudaStream_t s);
@@ -163,7 +193,24 @@ static inline const affine *fixed_table(const BaseSet *b, uint32_t *c, uint32_t 
 }
 
 // ---- functions one TU defines and others call -------------------------------------------------------------------
-struct BasesChunks { uint32_t k = 0; cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS], ev_scal[H2_MAX_UPLOAD_CHUNKS]; };   // bases / scalars of chunk j have landed
+// Arrival of a one-shot MSM's inputs in k chunks: events on the copy stream -- bases / scalars of chunk j have landed.
+// When the inputs are staged from pageable memory an uploader thread records the events while the calling thread issues
+// the kernels: `recorded` (2 j + 1 after the scalars of chunk j, 2 j + 2 after its bases) tells the issuer that an event
+// HAS been recorded and may be waited on; `failed` aborts the issue.
+struct BasesChunks {
+    uint32_t k = 0;
+    cudaEvent_t ev[H2_MAX_UPLOAD_CHUNKS], ev_scal[H2_MAX_UPLOAD_CHUNKS];
+    std::atomic<uint32_t> *recorded = nullptr;
+    std::atomic<int> *failed = nullptr;
+    int wait_recorded(uint32_t want) const {
+        if (!recorded) return 0;
+        while (recorded->load(std::memory_order_acquire) < want) {
+            if (failed && failed->load()) return 1;
+            std::this_thread::yield();
+        }
+        return 0;
+    }
+};
 // capi_msm.cu
 int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine *d_bases, size_t n, uint32_t c,
                  jacobian *d_out, int out_canonical, cudaStream_t s, uint32_t fixed = 0, uint64_t stride = 0,

@@ -59,3 +59,44 @@ def best_multiexp_sharded(coeffs, bases, curve: str = "vesta", group=None,
     dist.all_gather(gathered, mine, group=group)
     parts = np.stack([g.cpu().numpy() for g in gathered])
     return (point_sum or _point_sum)(curve, parts)
+
+
+# ---- single-process multi-GPU (include/halo2_b200.h: h2_multi_*) ----------------------------------------------------
+def multi_init(ngpu: int) -> int:
+    """Binds the engine to `ngpu` devices of this process (the primary one from lib.init() first); returns the count."""
+    lib = _l.init()
+    _l.check(lib.h2_multi_init(int(ngpu)))
+    return int(lib.h2_multi_count())
+
+
+def best_multiexp_multi_gpu(coeffs, bases, curve: str = "vesta") -> np.ndarray:
+    """best_multiexp (arithmetic.rs:143-180) sharded over the devices of multi_init inside ONE process: contiguous shards,
+    parallel uploads, per-device Pippenger, partial results peer-written to the primary device and added there."""
+    c = _l.as_u8(coeffs, 32)
+    b = _l.as_u8(bases, 64)
+    assert c.shape[0] == b.shape[0], "best_multiexp: coeffs.len() != bases.len()"
+    out = np.zeros(96, dtype=np.uint8)
+    _l.check(_l.init().h2_msm_multi_gpu(_l.CURVE_ID[curve], _l.ptr(c), _l.ptr(b), ctypes.c_size_t(c.shape[0]), _l.REPR_CANONICAL, _l.ptr(out)))
+    return out
+
+
+class MultiGpuBases:
+    """A base vector resident in shards on the devices of multi_init (BASELINE configs[4]: bases pre-resident)."""
+
+    def __init__(self, bases, curve: str = "vesta"):
+        b = _l.as_u8(bases, 64)
+        self.curve, self.n = curve, b.shape[0]
+        self._h = ctypes.c_uint64(0)
+        _l.check(_l.init().h2_multi_bases_register(_l.CURVE_ID[curve], _l.ptr(b), ctypes.c_size_t(self.n), _l.REPR_CANONICAL, ctypes.byref(self._h)))
+
+    def msm(self, coeffs) -> np.ndarray:
+        c = _l.as_u8(coeffs, 32)
+        assert c.shape[0] == self.n, "best_multiexp: coeffs.len() != bases.len()"
+        out = np.zeros(96, dtype=np.uint8)
+        _l.check(_l.init().h2_msm_multi_registered(self._h, _l.ptr(c), ctypes.c_size_t(self.n), _l.REPR_CANONICAL, _l.ptr(out)))
+        return out
+
+    def close(self) -> None:
+        if self._h.value:
+            _l.check(_l.load().h2_multi_bases_release(self._h))
+            self._h = ctypes.c_uint64(0)

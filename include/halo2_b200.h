@@ -178,6 +178,24 @@ int h2_msm_dev(int curve, const void *d_scalars, int scalars_repr, const void *d
 /* Sum of g Jacobian points (host, 96 B each): the combine step after the multi-GPU
  * all-gather of per-shard partial results. */
 int h2_point_sum(int curve, const void *points_xyz, size_t g, int repr, void *out_xyz);
+/* The same sum on device pointers (Montgomery in and out), enqueued on `stream`: the combine step directly behind an NCCL
+ * all-gather, no host round trip. */
+int h2_point_sum_dev(int curve, const void *d_points_xyz, size_t g, void *d_out_xyz, void *stream);
+
+/* ---- single-process multi-GPU: SURVEY.md section 8(b) `h2_msm_multi_gpu`, section 8(e) --------------------------- */
+/* best_multiexp (arithmetic.rs:143-180) is called from ONE process: after h2_init(primary), h2_multi_init(ngpu) binds
+ * contexts to ngpu devices (the primary first, then the others in index order) and enables peer access.  h2_msm_multi_gpu
+ * is h2_msm sharded over them: device g receives pairs [g n / G, (g + 1) n / G) (one worker thread per device, uploads in
+ * parallel), runs the whole single-GPU pipeline, writes its 96-byte partial result into the primary device's memory over
+ * NVLink, and the primary adds the G partial results.  Same group element as h2_msm for every ngpu. */
+int h2_multi_init(int ngpu);
+int h2_multi_count(void);
+int h2_msm_multi_gpu(int curve, const void *scalars, const void *bases_xy, size_t n, int repr, void *out_xyz);
+/* Bases resident per shard (the Params generators of a prover session; BASELINE configs[4]: "bases pre-resident"):
+ * h2_msm_multi_registered then ships only the scalars. */
+int h2_multi_bases_register(int curve, const void *bases_xy, size_t n, int repr, uint64_t *handle);
+int h2_multi_bases_release(uint64_t handle);
+int h2_msm_multi_registered(uint64_t handle, const void *scalars, size_t n, int repr, void *out_xyz);
 
 /* ---- NTT: replaces best_fft for G = Scalar, arithmetic.rs:192-295 --------------------------- */
 /* In-place radix-2 network on 2^log_n elements with the given omega (any field element,
@@ -248,6 +266,10 @@ int h2_test_last_msm_flags(uint32_t *out);
 /* Test hook: h2_msm uploads the bases of inputs with >= 2^log2_n points in chunks that are sorted and accumulated
  * separately while the next chunk is on the PCIe link (default 19). */
 int h2_test_set_chunk_threshold(uint32_t log2_n);
+/* Transfers from / to PAGEABLE caller memory (a Rust Vec) go through a pinned staging ring filled by a few host threads,
+ * so that the link runs near its pinned rate and uploads still overlap compute; pinned / registered memory is used in
+ * place.  0 switches the ring off (plain cudaMemcpyAsync): bench.py times both. */
+int h2_test_set_staging(int on);
 /* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
  * parameters on (default); 0 issues every launch individually. */
 int h2_test_set_graphs(int on);

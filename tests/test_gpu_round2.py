@@ -1,0 +1,167 @@
+"""GPU tests added in round 2: the single-process multi-GPU entry points (run on however many devices the box has --
+one device exercises the whole code path with G = 1), staged transfers from pageable memory, the concurrent-caller pattern
+of BatchVerifier, and the round-1 advisor findings."""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cref, pasta  # noqa: E402
+
+SEED = 0x48414C4F32
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import halo2_b200
+    from halo2_b200 import lib as L
+    L.init()
+    return halo2_b200
+
+
+def _affine(curve, xyz):
+    return cref.bytes_to_affine(cref.jac_to_affine(curve, xyz))
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_msm_multi_gpu_single_process(eng, curve):
+    """h2_msm_multi_gpu / h2_msm_multi_registered vs the oracle, for every device count the box offers, incl. n < G,
+    n = 0 and ragged shards.  SURVEY.md section 8(e): the result is the same group element whatever G is."""
+    from halo2_b200 import lib as L, parallel
+    ndev = L.load().h2_device_count()
+    c = pasta.CURVES[curve]
+    n = 3001
+    kb = cref.gen_scalars(c.scalar, SEED + 31, n)
+    pb = cref.gen_points(curve, SEED + 32, n)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    for g in sorted({1, min(2, ndev), ndev}):
+        assert parallel.multi_init(g) == g
+        assert _affine(curve, parallel.best_multiexp_multi_gpu(kb, pb, curve)) == want
+        for m in (0, 1, g - 1 if g > 1 else 2, 2 * g + 1):
+            w = cref.bytes_to_affine(cref.best_multiexp(curve, kb[:m], pb[:m])) if m else None
+            assert _affine(curve, parallel.best_multiexp_multi_gpu(kb[:m], pb[:m], curve)) == w
+        mb = parallel.MultiGpuBases(pb, curve)
+        assert _affine(curve, mb.msm(kb)) == want
+        k2 = cref.gen_scalars(c.scalar, SEED + 33, n)
+        assert _affine(curve, mb.msm(k2)) == cref.bytes_to_affine(cref.best_multiexp(curve, k2, pb))
+        mb.close()
+    # a larger problem takes the chunked, threaded upload path on every device
+    n = 1 << 17
+    kb = cref.gen_scalars(c.scalar, SEED + 34, n)
+    pb = cref.gen_points(curve, SEED + 35, n)
+    assert _affine(curve, parallel.best_multiexp_multi_gpu(kb, pb, curve)) == _affine(curve, eng.best_multiexp(kb, pb, curve))
+    assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+
+
+def test_staged_and_plain_transfers_agree(eng):
+    """Pageable numpy buffers go through the pinned staging ring (MSM inputs on an uploader thread, NTT in and out);
+    results must equal the plain cudaMemcpyAsync path and the oracle."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    c = pasta.PALLAS
+    n = (1 << 18) + 77                       # > 4 MiB of bases: uploader thread; 3 chunks
+    kb = cref.gen_scalars(c.scalar, SEED + 41, n)
+    pb = cref.gen_points("pallas", SEED + 42, n)
+    outs = []
+    for on in (1, 0, 1):
+        L.check(lib.h2_test_set_staging(on))
+        outs.append(_affine("pallas", eng.best_multiexp(kb, pb, "pallas")))
+    L.check(lib.h2_test_set_staging(1))
+    assert outs[0] == outs[1] == outs[2] == cref.bytes_to_affine(cref.best_multiexp("pallas", kb, pb))
+    log_n = 19                               # 16 MiB each way: two ring slots in flight
+    a = cref.gen_scalars("fq", SEED + 43, 1 << log_n)
+    w = pasta.omega_for_k("fq", log_n)
+    want = cref.best_fft("fq", a, w, log_n)
+    for on in (1, 0):
+        L.check(lib.h2_test_set_staging(on))
+        got = a.copy()
+        eng.best_fft(got, w, log_n, "fq")
+        assert (got == want).all()
+    L.check(lib.h2_test_set_staging(1))
+
+
+def test_concurrent_callers(eng):
+    """BatchVerifier::finalize calls the MSM from many rayon workers at once (plonk/verifier/batch.rs:97-110 ->
+    verifier.rs:100): exported functions must be thread-safe.  8 host threads x mixed calls, each result vs the oracle."""
+    c = pasta.VESTA
+    k = 8
+    n = 1 << k
+    bases = cref.gen_points("vesta", SEED + 51, n + 2)
+    prm = eng.Params("vesta", k, bases[:n], bases[:n], bases[n:n + 1], u=bases[n + 1:])
+    polys = [cref.gen_scalars(c.scalar, SEED + 60 + i, n) for i in range(8)]
+    want_commit = [cref.bytes_to_affine(cref.best_multiexp("vesta", np.concatenate([p, cref.ints_to_bytes([i + 1])]), bases[:n + 1]))
+                   for i, p in enumerate(polys)]
+    pts = cref.gen_points("vesta", SEED + 52, 777)
+    ks = [cref.gen_scalars(c.scalar, SEED + 70 + i, 777) for i in range(8)]
+    want_msm = [cref.bytes_to_affine(cref.best_multiexp("vesta", kk, pts)) for kk in ks]
+    w = pasta.omega_for_k("fp", 10)
+    ntt_in = [cref.gen_scalars("fp", SEED + 80 + i, 1 << 10) for i in range(8)]
+    want_ntt = [cref.best_fft("fp", a, w, 10) for a in ntt_in]
+    errs = []
+
+    def worker(i):
+        try:
+            for rep in range(6):
+                assert _affine("vesta", prm.commit_lagrange(polys[i], eng.Blind(i + 1))) == want_commit[i]
+                assert _affine("vesta", eng.best_multiexp(ks[i], pts, "vesta")) == want_msm[i]
+                a = ntt_in[i].copy()
+                eng.best_fft(a, w, 10, "fp")
+                assert (a == want_ntt[i]).all()
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    prm.close()
+
+
+def test_advisor_findings_round1(eng):
+    """(a) n == 0 batched commits return `batch` identities; (b) a fresh ResidentPoly is zero-filled
+    and kate_division writes the zero the reference pushes behind the quotient; (c) kate_division rejects a quotient that
+    aliases ANY dividend of the batch or appears twice; (d) an IPA-capable base set (g ++ [w, u]) commits."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    c = pasta.VESTA
+    k = 5
+    n = 1 << k
+    bases = cref.gen_points("vesta", SEED + 91, n + 2)
+    prm = eng.Params("vesta", k, bases[:n], bases[:n], bases[n:n + 1], u=bases[n + 1:])
+    # (a) three empty scalar vectors, no blinds, against the resident table
+    out = np.full((3, 96), 0xAB, dtype=np.uint8)
+    L.check(lib.h2_msm_registered_batch(prm._h_g, None, ctypes.c_size_t(0), None, ctypes.c_size_t(3), L.REPR_CANONICAL, L.ptr(out)))
+    assert all(_affine("vesta", o) is None for o in out)
+    # (b)
+    p = eng.ResidentPoly("fp", n)
+    assert (p.download() == 0).all()
+    a = pasta.gen_scalars("fp", SEED + 92, n)
+    src = eng.ResidentPoly("fp", n)
+    src.upload(cref.ints_to_bytes(a))
+    dst = eng.ResidentPoly("fp", n)
+    dst.upload(cref.ints_to_bytes([7] * n))                        # stale contents
+    eng.kate_division_resident([src], [12345], dst=[dst])
+    got = cref.bytes_to_ints(dst.download())
+    assert got[:n - 1] == pasta.kate_division("fp", a, 12345) and got[n - 1] == 0
+    # committing n coefficients of the quotient therefore equals the reference's kate_division + push(ZERO) + commit
+    want = pasta.to_affine(c, pasta.best_multiexp(c, got[:n - 1] + [0, 9], [cref.bytes_to_affine(x) for x in bases[:n + 1]]))
+    assert _affine("vesta", prm.commit_resident([dst], [eng.Blind(9)])[0]) == want
+    # (c)
+    other = eng.ResidentPoly("fp", n)
+    other.upload(cref.ints_to_bytes(a))
+    with pytest.raises(eng.H2Error):
+        eng.kate_division_resident([src, dst], [3, 4], dst=[dst, other])      # dst[0] is src[1]
+    with pytest.raises(eng.H2Error):
+        eng.kate_division_resident([src, other], [3, 4], dst=[dst, dst])      # duplicate quotient handle
+    # (d) commit over a set that also holds u (n + 2 bases): the blind rides on bases[n]
+    poly = cref.gen_scalars(c.scalar, SEED + 93, n)
+    assert _affine("vesta", prm.commit(poly, eng.Blind(3))) == cref.bytes_to_affine(
+        cref.best_multiexp("vesta", np.concatenate([poly, cref.ints_to_bytes([3])]), bases[:n + 1]))
+    for q in (p, src, dst, other):
+        q.close()
+    prm.close()
