@@ -232,6 +232,8 @@ static void ctx_destroy(Context &C) {
     C.ipa.clear();
     for (auto &kv : C.polys) { kv.second->buf.release(); delete kv.second; }
     C.polys.clear();
+    for (PolyBuf *q : C.poly_pool) { q->buf.release(); delete q; }
+    C.poly_pool.clear();
     for (auto &ge : C.graphs) if (ge.exec) cudaGraphExecDestroy(ge.exec);
     C.graphs.clear();
     for (IpaSession *q : C.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }

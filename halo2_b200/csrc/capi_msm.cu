@@ -724,22 +724,39 @@ static IpaState ipa_state(IpaSession *q) {
     S.p = q->p.as<fe>(); S.b = q->b.as<fe>(); S.s = q->s.as<fe>(); S.scal = q->scal.as<fe>(); S.n = 1ull << q->k;
     return S;
 }
-template <class PS> static int ipa_begin_impl(IpaSession *q, const void *p_prime, const void *x3, int repr, cudaStream_t s) {
+template <class PS> static int ipa_begin_impl(IpaSession *q, const void *p_prime, PolyBuf *p_poly, const void *x3, int repr, cudaStream_t s) {
     Context &X = g_ctx;
     const uint64_t n = 1ull << q->k;
     if (q->p.ensure(n * sizeof(fe)) || q->b.ensure(n * sizeof(fe)) || q->s.ensure(n * sizeof(fe)) || q->scal.ensure(2 * (n + 2) * sizeof(fe)) ||
         q->out.ensure(2 * sizeof(jacobian)) || X.pow2.ensure(64 * sizeof(fe)))
         return 1;
-    if (upload_async(q->p.p, p_prime, n * sizeof(fe), s)) return 1;
+    if (p_poly) CU(cudaMemcpyAsync(q->p.p, p_poly->buf.p, n * sizeof(fe), cudaMemcpyDeviceToDevice, s));
+    else if (upload_async(q->p.p, p_prime, n * sizeof(fe), s)) return 1;
     IpaState S = ipa_state(q);
-    LAUNCH(ipa_init_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, repr == H2_REPR_MONTGOMERY);
+    LAUNCH(ipa_init_kernel<PS>, blocks_for(n, 256), 256, 0, s, S, p_poly ? 1 : repr == H2_REPR_MONTGOMERY);
     // b_t = x3^t (prover.rs:86-93) with the NTT twiddle generator
     fe x = host_to_mont<PS>(x3, repr);
     LAUNCH(twiddle_pow2_kernel<PS>, 1, 32, 0, s, X.pow2.as<fe>(), x, q->k + 1);
     LAUNCH(twiddle_fill_kernel<PS>, blocks_for((n + 31) / 32, 128), 128, 0, s, S.b, X.pow2.as<fe>(), n);
     return 0;
 }
+static int ipa_begin_common(uint64_t bases_handle, uint32_t k, const void *p_prime, PolyBuf *p_poly, const void *x3, int repr, uint64_t *session);
 extern "C" int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_prime, const void *x3, int repr, uint64_t *session) {
+    return ipa_begin_common(bases_handle, k, p_prime, nullptr, x3, repr, session);
+}
+// p' taken from a device-resident polynomial (Montgomery form): nothing but x3 goes up
+extern "C" int h2_ipa_begin_poly(uint64_t bases_handle, uint32_t k, uint64_t p_prime_poly, const void *x3, int repr, uint64_t *session) {
+    PolyBuf *pp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (require_ready()) return 1;
+        pp = find_poly(p_prime_poly);
+        if (!pp) return fail("h2_ipa_begin_poly: unknown polynomial handle");
+        if (k > 28 || pp->len < ((size_t)1 << k)) return fail("h2_ipa_begin_poly: the polynomial holds fewer than 2^k coefficients");
+    }
+    return ipa_begin_common(bases_handle, k, nullptr, pp, x3, repr, session);
+}
+static int ipa_begin_common(uint64_t bases_handle, uint32_t k, const void *p_prime, PolyBuf *p_poly, const void *x3, int repr, uint64_t *session) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;
     auto it = g_ctx.bases.find(bases_handle);
@@ -754,7 +771,8 @@ extern "C" int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_pri
     q->bases = bases_handle; q->k = k; q->round = 0; q->folded = 1;
     cudaStream_t s = g_ctx.stream;
     if (scratch_acquire(s)) { ipa_free(q); return 1; }   // pow2 is shared scratch
-    int rc = b->curve == H2_CURVE_PALLAS ? ipa_begin_impl<FqParams>(q, p_prime, x3, repr, s) : ipa_begin_impl<FpParams>(q, p_prime, x3, repr, s);
+    if (p_poly && p_poly->field != (b->curve == H2_CURVE_PALLAS ? H2_FIELD_FQ : H2_FIELD_FP)) { ipa_free(q); return fail("h2_ipa_begin_poly: the polynomial is not over the curve's scalar field"); }
+    int rc = b->curve == H2_CURVE_PALLAS ? ipa_begin_impl<FqParams>(q, p_prime, p_poly, x3, repr, s) : ipa_begin_impl<FpParams>(q, p_prime, p_poly, x3, repr, s);
     if (rc) { ipa_free(q); return 1; }
     if (scratch_release(s)) { ipa_free(q); return 1; }
     cudaError_t e = cudaStreamSynchronize(s);   // p_prime may be pageable host memory
@@ -764,7 +782,7 @@ extern "C" int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_pri
     *session = h;
     return 0;
 }
-template <class PS> static int ipa_round_impl(IpaSession *q, BaseSet *b, const void *z, const void *l_rand, const void *r_rand, int repr, cudaStream_t s) {
+template <class PS> static int ipa_round_impl(IpaSession *q, BaseSet *b, const void *z, const void *l_rand, const void *r_rand, int repr, int out_canonical, cudaStream_t s) {
     const uint64_t n = 1ull << q->k;
     const uint32_t bit = q->k - 1 - q->round;
     IpaState S = ipa_state(q);
@@ -772,9 +790,17 @@ template <class PS> static int ipa_round_impl(IpaSession *q, BaseSet *b, const v
     LAUNCH(ipa_inner_kernel<PS>, 1, 512, 0, s, S, bit, host_to_mont<PS>(z, repr), host_to_mont<PS>(l_rand, repr), host_to_mont<PS>(r_rand, repr));
     uint32_t tc, tmode;
     const affine *tbl = fixed_table(b, &tc, &tmode);
-    return msm_dispatch(b->curve, S.scal, 1, tbl, n + 2, tc, q->out.as<jacobian>(), repr == H2_REPR_CANONICAL, s, tmode, b->n, nullptr, 2);
+    return msm_dispatch(b->curve, S.scal, 1, tbl, n + 2, tc, q->out.as<jacobian>(), out_canonical, s, tmode, b->n, nullptr, 2);
 }
+static int ipa_round_common(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out, int affine_out);
 extern "C" int h2_ipa_round(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz) {
+    return ipa_round_common(session, z, l_rand, r_rand, repr, out_lr_xyz, 0);
+}
+// L_j, R_j as the two AFFINE points the prover writes to the transcript (prover.rs:120-125 `to_affine`), 2 x 64 B
+extern "C" int h2_ipa_round_affine(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xy) {
+    return ipa_round_common(session, z, l_rand, r_rand, repr, out_lr_xy, 1);
+}
+static int ipa_round_common(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz, int affine_out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;
     auto it = g_ctx.ipa.find(session);
@@ -787,8 +813,16 @@ extern "C" int h2_ipa_round(uint64_t session, const void *z, const void *l_rand,
     BaseSet *b = ib->second;
     cudaStream_t s = g_ctx.stream;
     if (scratch_acquire(s)) return 1;
-    int rc = b->curve == H2_CURVE_PALLAS ? ipa_round_impl<FqParams>(q, b, z, l_rand, r_rand, repr, s) : ipa_round_impl<FpParams>(q, b, z, l_rand, r_rand, repr, s);
+    const int oc = affine_out ? 0 : repr == H2_REPR_CANONICAL;
+    int rc = b->curve == H2_CURVE_PALLAS ? ipa_round_impl<FqParams>(q, b, z, l_rand, r_rand, repr, oc, s) : ipa_round_impl<FpParams>(q, b, z, l_rand, r_rand, repr, oc, s);
     if (rc) return rc;
+    if (affine_out) {
+        if (g_ctx.ec_out.ensure(2 * sizeof(affine))) return 1;
+        const int canon = repr == H2_REPR_CANONICAL;
+        if (b->curve == H2_CURVE_PALLAS) LAUNCH(normalize_kernel<FpParams>, 1, 64, 0, s, (const xyzz *)nullptr, q->out.as<jacobian>(), 0, g_ctx.ec_out.as<affine>(), canon, (uint64_t)2);
+        else LAUNCH(normalize_kernel<FqParams>, 1, 64, 0, s, (const xyzz *)nullptr, q->out.as<jacobian>(), 0, g_ctx.ec_out.as<affine>(), canon, (uint64_t)2);
+        CU(cudaMemcpyAsync(out_lr_xyz, g_ctx.ec_out.p, 2 * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    } else
     CU(cudaMemcpyAsync(out_lr_xyz, q->out.p, 2 * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
     if (scratch_release(s)) return 1;
     CU(cudaStreamSynchronize(s));
@@ -844,8 +878,19 @@ extern "C" int h2_ipa_finish(uint64_t session, int repr, void *out_c_b) {
 
 
 // commit(poly, blind) = <poly[0..n), bases[0..n)> + blind * bases[n] for `batch` resident polynomials in one pass
+static int msm_registered_polys_impl(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
+                                     void *out_xyz, int affine_out);
 extern "C" int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
                                        void *out_xyz) {
+    return msm_registered_polys_impl(bases_handle, polys, batch, n, extra_scalars, repr, out_xyz, 0);
+}
+// ... followed by batch_normalize on the device: `batch` affine points (64 B), what the prover writes to the transcript
+extern "C" int h2_msm_registered_polys_affine(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars,
+                                              int repr, void *out_xy) {
+    return msm_registered_polys_impl(bases_handle, polys, batch, n, extra_scalars, repr, out_xy, 1);
+}
+static int msm_registered_polys_impl(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
+                                     void *out_xyz, int affine_out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;
     auto it = g_ctx.bases.find(bases_handle);
@@ -877,11 +922,22 @@ extern "C" int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *po
     int rc;
     uint32_t tc = 0, tmode = 0;
     const affine *tbl = b->table.p ? fixed_table(b, &tc, &tmode) : nullptr;
-    if (tbl) rc = msm_dispatch(b->curve, d, 1, tbl, total, tc, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s, tmode, b->n,
+    const int canon = repr == H2_REPR_CANONICAL;
+    if (tbl) rc = msm_dispatch(b->curve, d, 1, tbl, total, tc, X.result.as<jacobian>(), affine_out ? 0 : canon, s, tmode, b->n,
                                nullptr, (uint32_t)batch);
-    else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), repr == H2_REPR_CANONICAL, s);
+    else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), affine_out ? 0 : canon, s);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (affine_out) {
+        if (X.ec_out.ensure(batch * sizeof(affine))) return 1;
+        const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
+        if (b->curve == H2_CURVE_PALLAS)
+            LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+        else
+            LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+        CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
+    } else {
+        CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    }
     if (scratch_release(s)) return 1;
     CU(cudaStreamSynchronize(s));
     return 0;

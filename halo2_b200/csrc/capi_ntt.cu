@@ -177,25 +177,46 @@ extern "C" int h2_poly_alloc(int field, size_t len, uint64_t *poly) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (require_ready()) return 1;
     if (field != H2_FIELD_FP && field != H2_FIELD_FQ) return fail("unknown field id");
-    PolyBuf *b = new PolyBuf();
+    // A prover allocates and frees the same few sizes proof after proof: freed polynomials keep their device buffer in a small
+    // pool, so that this is a memset on the stream instead of a cudaMalloc (and h2_poly_free no cudaFree + device sync).
+    Context &X = g_ctx;
+    PolyBuf *b = nullptr;
+    for (size_t i = 0; i < X.poly_pool.size(); i++) {
+        PolyBuf *c = X.poly_pool[i];
+        if (c->buf.cap >= (len + 1) * sizeof(fe) && c->buf.cap <= (len + 1) * sizeof(fe) * 9 / 8 + 512) {
+            b = c;
+            X.poly_pool_bytes -= c->buf.cap;
+            X.poly_pool.erase(X.poly_pool.begin() + i);
+            break;
+        }
+    }
+    if (!b) b = new PolyBuf();
     b->field = field; b->len = len;
     if (b->buf.ensure((len + 1) * sizeof(fe))) { delete b; return 1; }
     // zero-filled: a commit after a partial upload, or of a quotient shorter than the buffer, must not read stale memory
-    if (cudaMemsetAsync(b->buf.p, 0, (len + 1) * sizeof(fe), g_ctx.stream) != cudaSuccess) { b->buf.release(); delete b; return fail("h2_poly_alloc: memset failed"); }
-    uint64_t h = g_ctx.next_handle++;
-    g_ctx.polys[h] = b;
+    if (cudaMemsetAsync(b->buf.p, 0, (len + 1) * sizeof(fe), X.stream) != cudaSuccess) { b->buf.release(); delete b; return fail("h2_poly_alloc: memset failed"); }
+    uint64_t h = X.next_handle++;
+    X.polys[h] = b;
     *poly = h;
     return 0;
 }
 extern "C" int h2_poly_free(uint64_t poly) {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ctx.polys.find(poly);
-    if (it == g_ctx.polys.end()) return fail("h2_poly_free: unknown handle");
-    cudaSetDevice(g_ctx.device);
-    cudaStreamSynchronize(g_ctx.stream);
-    it->second->buf.release();
-    delete it->second;
-    g_ctx.polys.erase(it);
+    Context &X = g_ctx;
+    auto it = X.polys.find(poly);
+    if (it == X.polys.end()) return fail("h2_poly_free: unknown handle");
+    PolyBuf *b = it->second;
+    X.polys.erase(it);
+    // every use of a resident polynomial is ordered on the context's stream, and so is its next owner's first write
+    if (X.poly_pool.size() < 96 && X.poly_pool_bytes + b->buf.cap <= ((size_t)4 << 30)) {
+        X.poly_pool.push_back(b);
+        X.poly_pool_bytes += b->buf.cap;
+        return 0;
+    }
+    cudaSetDevice(X.device);
+    cudaStreamSynchronize(X.stream);
+    b->buf.release();
+    delete b;
     return 0;
 }
 int convert_field(int field, fe *d, size_t n, int to_mont, cudaStream_t s) {
@@ -214,6 +235,33 @@ extern "C" int h2_poly_upload(uint64_t poly, const void *src, size_t len, int re
     if (upload_async(b->buf.p, src, len * sizeof(fe), s)) return 1;
     if (repr == H2_REPR_CANONICAL && convert_field(b->field, b->buf.as<fe>(), len, 1, s)) return 1;
     CU(cudaStreamSynchronize(s));      // src may be pageable
+    return 0;
+}
+// a[index] += delta: the one-coefficient corrections of the opening argument (poly/commitment/prover.rs:51 `s_poly[0] -= s_at_x3`,
+// :78 `p_prime_poly[0] -= v`) on a resident polynomial
+template <class P> __global__ void poly_add_at_kernel(fe *a, fe delta_mont) { fe_store(a, fe_add<P>(fe_load(a), delta_mont)); }
+extern "C" int h2_poly_add_at(uint64_t poly, size_t index, const void *delta, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *b = find_poly(poly);
+    if (!b) return fail("h2_poly_add_at: unknown handle");
+    if (index >= b->len) return fail("h2_poly_add_at: index out of range");
+    cudaStream_t s = g_ctx.stream;
+    if (b->field == H2_FIELD_FP) LAUNCH(poly_add_at_kernel<FpParams>, 1, 1, 0, s, b->buf.as<fe>() + index, host_to_mont<FpParams>(delta, repr));
+    else LAUNCH(poly_add_at_kernel<FqParams>, 1, 1, 0, s, b->buf.as<fe>() + index, host_to_mont<FqParams>(delta, repr));
+    return 0;
+}
+// dst[dst_off .. dst_off + len) = src[src_off .. src_off + len) on the device: the h(X) pieces (plonk/vanishing/prover.rs:95-100
+// `h_poly.chunks_exact(n)`), or a copy of a column that an in-place step is about to overwrite
+extern "C" int h2_poly_copy(uint64_t dst, size_t dst_off, uint64_t src, size_t src_off, size_t len) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *d = find_poly(dst), *a = find_poly(src);
+    if (!d || !a) return fail("h2_poly_copy: unknown handle");
+    if (d->field != a->field) return fail("h2_poly_copy: the polynomials live in different fields");
+    if (dst_off + len > d->len || src_off + len > a->len) return fail("h2_poly_copy: range out of bounds");
+    if (d == a && !(dst_off + len <= src_off || src_off + len <= dst_off)) return fail("h2_poly_copy: overlapping ranges");
+    if (len) CU(cudaMemcpyAsync(d->buf.as<fe>() + dst_off, a->buf.as<fe>() + src_off, len * sizeof(fe), cudaMemcpyDeviceToDevice, g_ctx.stream));
     return 0;
 }
 extern "C" int h2_poly_download(uint64_t poly, void *dst, size_t len, int repr) {

@@ -133,6 +133,8 @@ struct Context {
     std::vector<MsmGraph> graphs;
     uint64_t graph_stamp = 0;
     uint32_t graphs_on = 1;
+    std::vector<PolyBuf *> poly_pool;        // freed resident polynomials keep their buffers for the next h2_poly_alloc of that size
+    size_t poly_pool_bytes = 0;
     std::vector<IpaSession *> ipa_pool;      // finished sessions keep their buffers for the next proof (no cudaMalloc per opening)
     uint64_t next_handle = 1;
 };

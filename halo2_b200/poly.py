@@ -229,6 +229,54 @@ class Params:
                                                     _l.ptr(bl), _l.REPR_CANONICAL, _l.ptr(out)))
         return out
 
+    def commit_resident_affine(self, polys: Sequence["ResidentPoly"], blinds: Sequence[Blind], lagrange: bool = False) -> np.ndarray:
+        """commit_resident + C::Curve::batch_normalize on the device: (batch, 64) affine points, ready for write_point."""
+        batch = len(polys)
+        assert batch == len(blinds) and batch >= 1
+        hs = (ctypes.c_uint64 * batch)(*[p._h.value for p in polys])
+        bl = np.ascontiguousarray(np.stack([_l.fe_bytes(b.value) for b in blinds]))
+        out = np.zeros((batch, 64), dtype=np.uint8)
+        _l.check(_l.init().h2_msm_registered_polys_affine(self._h_gl if lagrange else self._h_g, hs, ctypes.c_size_t(batch), ctypes.c_size_t(self.n),
+                                                           _l.ptr(bl), _l.REPR_CANONICAL, _l.ptr(out)))
+        return out
+
+    def ipa_rounds_transcript(self, p_prime, x3: int, z: int, challenge, l_rand: Sequence[int], r_rand: Sequence[int]):
+        """ipa_rounds for a transcript-driven caller: `p_prime` may be a ResidentPoly (nothing is uploaded), L_j / R_j come back
+        as the AFFINE points the reference writes to the transcript (prover.rs:120-125), and `challenge(j, l_xy, r_xy) -> u_j`.
+        Returns (L (k, 64), R (k, 64), c)."""
+        if self.u is None or not self._has_table:
+            raise _l.H2Error("ipa_rounds needs Params(u=..., precompute=True)")
+        m = FIELDS[{"pallas": "fq", "vesta": "fp"}[self.curve]]
+        lib = _l.init()
+        assert len(l_rand) == self.k and len(r_rand) == self.k
+        sess = ctypes.c_uint64(0)
+        if isinstance(p_prime, ResidentPoly):
+            _l.check(lib.h2_ipa_begin_poly(self._h_g, ctypes.c_uint32(self.k), p_prime._h, _l.ptr(_l.fe_bytes(x3 % m)), _l.REPR_CANONICAL,
+                                           ctypes.byref(sess)))
+        else:
+            pp = _l.as_u8(p_prime, 32)
+            assert pp.shape[0] == self.n
+            _l.check(lib.h2_ipa_begin(self._h_g, ctypes.c_uint32(self.k), _l.ptr(pp), _l.ptr(_l.fe_bytes(x3 % m)), _l.REPR_CANONICAL,
+                                      ctypes.byref(sess)))
+        ls = np.zeros((self.k, 64), dtype=np.uint8)
+        rs = np.zeros((self.k, 64), dtype=np.uint8)
+        lr = np.zeros((2, 64), dtype=np.uint8)
+        zb = _l.fe_bytes(z % m)
+        try:
+            for j in range(self.k):
+                _l.check(lib.h2_ipa_round_affine(sess, _l.ptr(zb), _l.ptr(_l.fe_bytes(l_rand[j] % m)), _l.ptr(_l.fe_bytes(r_rand[j] % m)),
+                                                 _l.REPR_CANONICAL, _l.ptr(lr)))
+                ls[j], rs[j] = lr[0], lr[1]
+                u_j = int(challenge(j, ls[j], rs[j])) % m
+                _l.check(lib.h2_ipa_fold(sess, _l.ptr(_l.fe_bytes(u_j)), _l.ptr(_l.fe_bytes(pow(u_j, m - 2, m))), _l.REPR_CANONICAL))
+            cb = np.zeros((2, 32), dtype=np.uint8)
+            _l.check(lib.h2_ipa_finish(sess, _l.REPR_CANONICAL, _l.ptr(cb)))
+            sess.value = 0
+        finally:
+            if sess.value:
+                lib.h2_ipa_finish(sess, _l.REPR_CANONICAL, None)
+        return ls, rs, int.from_bytes(cb[0].tobytes(), "little")
+
     def ipa_rounds(self, p_prime, x3: int, z: int, challenge, l_rand: Sequence[int], r_rand: Sequence[int]):
         """The round loop of commitment::create_proof (poly/commitment/prover.rs:100-142) on the device.
         `p_prime` (:80) is the blinded polynomial with P(x3) removed; `challenge(j, L_j, R_j) -> u_j` is the
@@ -298,6 +346,15 @@ class ResidentPoly:
         out = np.zeros((n, 32), dtype=np.uint8)
         _l.check(_l.init().h2_poly_download(self._h, _l.ptr(out), ctypes.c_size_t(n), _l.REPR_CANONICAL))
         return out
+
+    def copy_from(self, src: "ResidentPoly", length: int, src_off: int = 0, dst_off: int = 0) -> "ResidentPoly":
+        """self[dst_off : dst_off + length] = src[src_off : src_off + length] on the device (`h_poly.chunks_exact(n)`)."""
+        _l.check(_l.init().h2_poly_copy(self._h, ctypes.c_size_t(int(dst_off)), src._h, ctypes.c_size_t(int(src_off)), ctypes.c_size_t(int(length))))
+        return self
+
+    def add_at(self, index: int, delta: int) -> None:
+        """a[index] += delta in place (poly/commitment/prover.rs:51, :78: `poly[0] -= value`)."""
+        _l.check(_l.init().h2_poly_add_at(self._h, ctypes.c_size_t(int(index)), _l.ptr(_l.fe_bytes(int(delta) % FIELDS[self.field])), _l.REPR_CANONICAL))
 
     def close(self) -> None:
         if self._h.value:

@@ -105,7 +105,11 @@ int h2_msm_registered_batch_affine(uint64_t handle, const void *scalars, size_t 
  * `bases_handle` must be a set of 2^k + 2 points g[0..2^k) || w || u registered with H2_BASES_PRECOMPUTE
  * (the same set serves commit(): w sits at index n).  h2_ipa_finish with out_c_b == NULL aborts a session. */
 int h2_ipa_begin(uint64_t bases_handle, uint32_t k, const void *p_prime, const void *x3, int repr, uint64_t *session);
+/* p' taken from a device-resident polynomial (h2_poly_* handle, 2^k coefficients): nothing but x3 goes up. */
+int h2_ipa_begin_poly(uint64_t bases_handle, uint32_t k, uint64_t p_prime_poly, const void *x3, int repr, uint64_t *session);
 int h2_ipa_round(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xyz);
+/* L_j, R_j as the two AFFINE points the prover writes to the transcript (`to_affine`, prover.rs:120-125): 2 x 64 B. */
+int h2_ipa_round_affine(uint64_t session, const void *z, const void *l_rand, const void *r_rand, int repr, void *out_lr_xy);
 int h2_ipa_fold(uint64_t session, const void *u, const void *u_inv, int repr);
 int h2_ipa_finish(uint64_t session, int repr, void *out_c_b);
 
@@ -127,12 +131,22 @@ int h2_poly_alloc(int field, size_t len, uint64_t *poly);
 int h2_poly_free(uint64_t poly);
 int h2_poly_upload(uint64_t poly, const void *src, size_t len, int repr);
 int h2_poly_download(uint64_t poly, void *dst, size_t len, int repr);
+/* a[index] += delta on a resident polynomial: the one-coefficient corrections of the opening argument
+ * (poly/commitment/prover.rs:51 `s_poly[0] -= s_at_x3`, :78 `p_prime_poly[0] -= v`). */
+int h2_poly_add_at(uint64_t poly, size_t index, const void *delta, int repr);
+/* dst[dst_off .. +len) = src[src_off .. +len) on the device: the h(X) pieces (plonk/vanishing/prover.rs:95-100,
+ * `h_poly.chunks_exact(n)`), or a copy of a column that an in-place step is about to overwrite. */
+int h2_poly_copy(uint64_t dst, size_t dst_off, uint64_t src, size_t src_off, size_t len);
 int h2_poly_lagrange_to_coeff(uint64_t dst, uint64_t src, uint32_t k, const void *omega_inv, const void *divisor, int repr);
 int h2_poly_coeff_to_extended(uint64_t dst, uint64_t src, uint32_t k, uint32_t ext_k, const void *zeta, const void *ext_omega, int repr);
 int h2_poly_extended_to_coeff(uint64_t dst, uint64_t src, uint32_t ext_k, const void *ext_omega_inv, const void *ext_divisor,
                               const void *zeta, size_t out_len, int repr);
 int h2_msm_registered_polys(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars, int repr,
                             void *out_xyz);
+/* The same pass followed by batch_normalize on the device: `batch` affine points (64 B each) -- what the prover writes to
+ * the transcript (plonk/prover.rs:305-316 commit + batch_normalize + write_point). */
+int h2_msm_registered_polys_affine(uint64_t bases_handle, const uint64_t *polys, size_t batch, size_t n, const void *extra_scalars,
+                                   int repr, void *out_xy);
 
 /* The prover's coefficient-form reductions on resident polynomials, each a tree of
  * 32-coefficient serial pieces instead of the reference's serial loop; `batch` polynomials of n coefficients per call.

@@ -258,3 +258,24 @@ def ipa_rounds(curve: str, bases: np.ndarray, k: int, p_prime: np.ndarray, x3, z
                          _p(_fe(x3)), _p(_fe(z)), _p(np.ascontiguousarray(challenges)), _p(np.ascontiguousarray(l_rand)),
                          _p(np.ascontiguousarray(r_rand)), threads or default_threads(), _p(out_l), _p(out_r), _p(out_c))
     return out_l, out_r, int.from_bytes(out_c.tobytes(), "little")
+
+
+def ipa_rounds_transcript(curve: str, bases: np.ndarray, k: int, p_prime: np.ndarray, x3, z, challenge, l_rand: np.ndarray,
+                          r_rand: np.ndarray, threads: Optional[int] = None):
+    """The same loop driven by a transcript: `challenge(j, l_xy (64,) uint8, r_xy (64,) uint8) -> int u_j` is called once per
+    round, where the reference writes L_j, R_j and squeezes u_j (prover.rs:124-128).  Returns (L, R, c)."""
+    out_l = np.zeros((k, 64), dtype=np.uint8)
+    out_r = np.zeros((k, 64), dtype=np.uint8)
+    out_c = np.zeros(32, dtype=np.uint8)
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint8),
+                          ctypes.c_void_p)
+
+    def _cb(j, l_ptr, r_ptr, u_ptr, _ctx):
+        u = int(challenge(int(j), np.ctypeslib.as_array(l_ptr, (64,)).copy(), np.ctypeslib.as_array(r_ptr, (64,)).copy()))
+        ctypes.memmove(u_ptr, u.to_bytes(32, "little"), 32)
+
+    cb = CB(_cb)
+    lib().orc_ipa_rounds_cb(CURVE_ID[curve], _p(np.ascontiguousarray(bases)), ctypes.c_uint32(k), _p(np.ascontiguousarray(p_prime)),
+                            _p(_fe(x3)), _p(_fe(z)), cb, None, _p(np.ascontiguousarray(l_rand)), _p(np.ascontiguousarray(r_rand)),
+                            threads or default_threads(), _p(out_l), _p(out_r), _p(out_c))
+    return out_l, out_r, int.from_bytes(out_c.tobytes(), "little")

@@ -879,9 +879,25 @@ static void generator_collapse(const field_t *F, aff *g, size_t len, const uint8
     for (size_t c = 0; c + 1 < nchunks; c++) pthread_join(th[c], NULL);
     free(th); free(ts);
 }
+/* challenge source of the transcript-driven form: called once per round with the affine L_j, R_j just computed
+ * (prover.rs:124-128 writes them to the transcript and squeezes u_j); writes the canonical u_j */
+typedef void (*orc_challenge_fn)(uint32_t j, const uint8_t *l_xy, const uint8_t *r_xy, uint8_t *u_out, void *ctx);
+static int ipa_rounds_impl(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z,
+                           const uint8_t *challenges, orc_challenge_fn cb, void *cb_ctx, const uint8_t *l_rand, const uint8_t *r_rand, int threads,
+                           uint8_t *out_l_xy, uint8_t *out_r_xy, uint8_t *out_c);
 int orc_ipa_rounds(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z,
                    const uint8_t *challenges, const uint8_t *l_rand, const uint8_t *r_rand, int threads,
                    uint8_t *out_l_xy, uint8_t *out_r_xy, uint8_t *out_c) {
+    return ipa_rounds_impl(curve, bases, k, p_prime, x3, z, challenges, NULL, NULL, l_rand, r_rand, threads, out_l_xy, out_r_xy, out_c);
+}
+int orc_ipa_rounds_cb(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z,
+                      orc_challenge_fn cb, void *cb_ctx, const uint8_t *l_rand, const uint8_t *r_rand, int threads,
+                      uint8_t *out_l_xy, uint8_t *out_r_xy, uint8_t *out_c) {
+    return ipa_rounds_impl(curve, bases, k, p_prime, x3, z, NULL, cb, cb_ctx, l_rand, r_rand, threads, out_l_xy, out_r_xy, out_c);
+}
+static int ipa_rounds_impl(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p_prime, const uint8_t *x3, const uint8_t *z,
+                           const uint8_t *challenges, orc_challenge_fn cb, void *cb_ctx, const uint8_t *l_rand, const uint8_t *r_rand, int threads,
+                           uint8_t *out_l_xy, uint8_t *out_r_xy, uint8_t *out_c) {
     ensure_init();
     if (threads < 1) threads = 1;
     const field_t *F = base_field(curve), *S = scalar_field(curve);
@@ -912,12 +928,14 @@ int orc_ipa_rounds(int curve, const uint8_t *bases, uint32_t k, const uint8_t *p
         msm_core(F, two, wu, 2, threads, &t); jac_add(F, &rj, &rj, &t);                      /* :119 */
         aff a; jac_to_aff(F, &a, &lj); aff_to_bytes(F, out_l_xy + 64 * j, &a);
         jac_to_aff(F, &a, &rj); aff_to_bytes(F, out_r_xy + 64 * j, &a);
-        fe u, ui; fe_from_bytes(S, &u, challenges + 32 * j); fe_inv(S, &ui, &u);
+        uint8_t ub[32];
+        if (cb) cb(j, out_l_xy + 64 * j, out_r_xy + 64 * j, ub, cb_ctx); else memcpy(ub, challenges + 32 * j, 32);
+        fe u, ui; fe_from_bytes(S, &u, ub); fe_inv(S, &ui, &u);
         for (size_t i = 0; i < half; i++) {                                                  /* :134-137 */
             fe_mul(S, &m, &p[i + half], &ui); fe_add(S, &p[i], &p[i], &m);
             fe_mul(S, &m, &b[i + half], &u); fe_add(S, &b[i], &b[i], &m);
         }
-        generator_collapse(F, g, 2 * half, challenges + 32 * j, threads);                    /* :140 */
+        generator_collapse(F, g, 2 * half, ub, threads);                                     /* :140 */
     }
     fe_to_bytes(S, out_c, &p[0]);
     free(g); free(p); free(b); free(sc);

@@ -1,0 +1,366 @@
+"""A proof-shaped replay of plonk::create_proof's hot path with a REAL transcript (test / bench infrastructure).
+
+The Rust prover cannot run here (no toolchain), so this drives the same sequence of hot-path calls the prover makes for the
+`benches/plonk.rs` circuit (3 advice columns, one permutation product, degree 5 => extended_k = k + 2)
+-- in order, with the real data dependencies -- through two interchangeable arms:
+  * GpuArm: the engine's reference-facing API on device-resident polynomials (halo2_b200);
+  * CpuArm: the C restatement of the reference algorithm (oracle/halo2_oracle.c), i.e. the timed CPU baseline.
+Both arms feed ONE implementation of the reference's transcript, Blake2bWrite with Challenge255
+(/root/reference/halo2_proofs/src/transcript.rs:160-219, :289-318): every commitment is written as the reference writes
+it (prefix 1 || x || y into the hash, the 32-byte compressed point into the proof), every evaluation as a scalar (prefix 2),
+and every challenge is squeezed from the running BLAKE2b state (prefix 0, 64-byte digest reduced as from_uniform_bytes).
+The challenges flow back into the computation (theta/beta/gamma into the permutation product, y into h(X), x into the
+evaluations, x_1..x_4 into the multiopen combination, xi / z / u_j into the inner product argument,
+poly/commitment/prover.rs:36-145), so two arms produce the same proof bytes iff every commitment, evaluation and opening
+round they compute is bit-identical.  What is replayed is the CALL SCHEDULE on synthetic columns: the circuit's own
+gate expressions and witness are stand-ins of the same shape and size (stated wherever a number from this file is quoted).
+
+Order of operations (file:line in halo2_proofs/src):
+  1. advice columns: commit_lagrange x3 (batched) -> write_point x3; lagrange_to_coeff x3; coeff_to_extended x3   plonk/prover.rs:305-328
+  2. theta, beta, gamma; permutation product z: commit_lagrange, lagrange_to_coeff, coeff_to_extended                plonk/permutation/prover.rs:172-178
+  3. vanishing random polynomial: commit                                                                             plonk/vanishing/prover.rs:36-60
+  4. y; h(X) = Ast over the cosets, divide_by_vanishing_poly, extended_to_coeff, 4 pieces committed (batched)        plonk/vanishing/prover.rs:81-108
+  5. x; evaluations of every polynomial at x (and the rotations) -> write_scalar                                     plonk/prover.rs:601-675
+  6. multiopen: x_1, x_2, q polynomials, kate_division per point set, commit f; x_3; q evals; x_4; final p           poly/multiopen/prover.rs:29-124
+  7. the opening: s_poly, commit, xi, z, p' = s xi + p, p'[0] -= p'(x_3), k rounds (L_j, R_j, u_j), c, f             poly/commitment/prover.rs:36-145
+"""
+from __future__ import annotations
+
+import hashlib
+import time
+from typing import List, Sequence
+
+import numpy as np
+
+P_MOD = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001   # Fp: the scalar field of Vesta (EqAffine)
+CURVE, FIELD = "vesta", "fp"
+DEGREE_J = 5   # benches/plonk.rs:183 set_minimum_degree(5) => quotient degree 4, extended_k = k + 2
+
+
+class Blake2bTranscript:
+    """transcript.rs:160-219 (Blake2bWrite) with Challenge255 (:289-318)."""
+
+    def __init__(self):
+        self.state = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
+        self.proof = bytearray()
+
+    def write_point(self, xy: np.ndarray) -> None:            # :183-187 write_point, :205-216 common_point
+        b = bytes(np.ascontiguousarray(xy, dtype=np.uint8).reshape(64))
+        if b == bytes(64):
+            raise ValueError("cannot write points at infinity to the transcript")
+        self.state.update(b"\x01" + b[:32] + b[32:])
+        enc = bytearray(b[:32])
+        enc[31] |= (b[32] & 1) << 7                            # C::to_bytes: x with the LSB of y in the top bit
+        self.proof += enc
+
+    def write_scalar(self, s: int) -> None:                   # :188-192, :218-223
+        b = int(s).to_bytes(32, "little")
+        self.state.update(b"\x02" + b)
+        self.proof += b
+
+    def squeeze_challenge(self) -> int:                       # :198-203; Challenge255::new = from_uniform_bytes of the 64-byte digest
+        self.state.update(b"\x00")
+        return int.from_bytes(self.state.copy().digest(), "little") % P_MOD
+
+
+def _schedule_ast(kind, leaves, ch):
+    """The elementwise programs of the replay (built from halo2_b200.evaluator.Ast, the mirror of poly/evaluator.rs)."""
+    from halo2_b200.evaluator import Ast
+    if kind == "perm_z":            # stand-in for the grand product's dependence on beta, gamma: z = base * beta + gamma
+        return leaves[0] * ch["beta"] + Ast.constant_term(ch["gamma"])
+    if kind == "h":                 # h(X)-shaped: two gates and a permutation-style product, folded by powers of y
+        a, b, c, z = leaves
+        gate0 = a * b - c
+        gate1 = (a.with_rotation(1) - a) * (b.with_rotation(-1) + Ast.constant_term(7))
+        perm = (z.with_rotation(1) + Ast.linear_term(ch["beta"]) + Ast.constant_term(ch["gamma"])) * (c + b * ch["theta"]) - z * a
+        return Ast.distribute_powers([gate0, gate1, perm], ch["y"])
+    if kind == "lincomb":           # sum_i coeff_i * poly_i
+        acc = None
+        for leaf, cf in zip(leaves, ch["coeffs"]):
+            t = leaf * cf
+            acc = t if acc is None else acc + t
+        return acc
+    raise ValueError(kind)
+
+
+class GpuArm:
+    name = "gpu"
+
+    def __init__(self, h2, k, g, g_lagrange, w, u):
+        self.h2, self.k, self.n = h2, k, 1 << k
+        zeta = pow(5, (P_MOD - 1) // 3, P_MOD)
+        self.params = h2.Params(CURVE, k, g, g_lagrange, w, u=u)
+        self.dom = h2.EvaluationDomain(FIELD, DEGREE_J, k, zeta)
+        self.ev_n = h2.Evaluator(self.dom, "lagrange")
+        self.ev_ext = h2.Evaluator(self.dom, "extended")
+        self._live: List = []
+
+    def poly(self, values, length=None):
+        arr = np.ascontiguousarray(values, dtype=np.uint8).reshape(-1, 32)
+        p = self.h2.ResidentPoly(FIELD, length or arr.shape[0], arr)
+        self._live.append(p)
+        return p
+
+    def empty(self, length):
+        p = self.h2.ResidentPoly(FIELD, length)
+        self._live.append(p)
+        return p
+
+    def commit(self, polys, blinds, lagrange):
+        return self.params.commit_resident_affine(polys, [self.h2.Blind(b) for b in blinds], lagrange=lagrange)
+
+    def l2c(self, p):
+        return self.dom.lagrange_to_coeff_resident(p, out=self.empty(self.n))
+
+    def c2e(self, p):
+        return self.dom.coeff_to_extended_resident(p, out=self.empty(self.dom.extended_len()))
+
+    def e2c(self, p):
+        return self.dom.extended_to_coeff_resident(p, out=self.empty(self.n * self.dom.quotient_poly_degree))
+
+    def vanish(self, p):
+        return self.dom.divide_by_vanishing_poly_resident(p)
+
+    def ast(self, kind, polys, ch, extended):
+        ev = self.ev_ext if extended else self.ev_n
+        ev.polys = []
+        leaves = [ev.register_poly(p) for p in polys]
+        return ev.evaluate(_schedule_ast(kind, leaves, ch), out=self.empty(self.dom.extended_len() if extended else self.n))
+
+    def evals(self, polys, points):
+        return self.h2.eval_polynomial_resident(polys, points, n=self.n)
+
+    def kate(self, p, point):
+        return self.h2.kate_division_resident([p], [point], dst=[self.empty(self.n)], n=self.n)[0]
+
+    def pieces(self, p, count):
+        return [self.empty(self.n).copy_from(p, self.n, src_off=i * self.n) for i in range(count)]
+
+    def add_at(self, p, idx, delta):
+        p.add_at(idx, delta)
+
+    def ipa(self, p_prime, x3, z, challenge, l_rand, r_rand):
+        return self.params.ipa_rounds_transcript(p_prime, x3, z, challenge, l_rand, r_rand)
+
+    def sync(self):
+        if self._live:
+            self._live[-1].download(1)
+
+    def free(self):
+        for p in self._live:
+            p.close()
+        self._live = []
+
+    def close(self):
+        self.free()
+        self.params.close()
+
+
+class CpuArm:
+    """The reference algorithm, C restatement, `threads` host threads: best_multiexp per commitment (poly/commitment.rs:119-150),
+    best_fft-based transforms, serial eval_polynomial / kate_division (arithmetic.rs:297-341), the IPA loop with
+    parallel_generator_collapse.  Only these hot-path calls are timed (`hot_s`); the elementwise glue is not."""
+    name = "cpu"
+
+    def __init__(self, cref, pasta, k, g, g_lagrange, w, u, threads):
+        self.cref, self.k, self.n, self.threads = cref, k, 1 << k, threads
+        zeta = pasta.zeta_candidates(FIELD)[0]
+        assert zeta == pow(5, (P_MOD - 1) // 3, P_MOD)
+        self.d = pasta.EvaluationDomain(FIELD, DEGREE_J, k, zeta)
+        self.zeta = zeta
+        self.bases = np.concatenate([g, w])
+        self.bases_l = np.concatenate([g_lagrange, w])
+        self.gwu = np.concatenate([g, w, u])
+        self.hot_s = 0.0
+        self.by_kind = {}
+        self.ipa_threads = threads
+
+    def _t(self, kind, t0):
+        dt = time.time() - t0
+        self.hot_s += dt
+        self.by_kind[kind] = self.by_kind.get(kind, 0.0) + dt
+
+    def poly(self, values, length=None):
+        arr = np.ascontiguousarray(values, dtype=np.uint8).reshape(-1, 32)
+        if length and length > arr.shape[0]:
+            arr = np.concatenate([arr, np.zeros((length - arr.shape[0], 32), dtype=np.uint8)])
+        return arr
+
+    def commit(self, polys, blinds, lagrange):
+        t0 = time.time()
+        out = np.stack([self.cref.best_multiexp(CURVE, np.concatenate([p[:self.n], self.cref.ints_to_bytes([b])]),
+                                                self.bases_l if lagrange else self.bases, self.threads) for p, b in zip(polys, blinds)])
+        self._t("commit_lagrange" if lagrange else "commit", t0)
+        return out
+
+    def l2c(self, p):
+        t0 = time.time()
+        out = self.cref.ifft(FIELD, p, self.d.omega_inv, self.k, self.d.ifft_divisor, self.threads)
+        self._t("lagrange_to_coeff", t0)
+        return out
+
+    def c2e(self, p):
+        t0 = time.time()
+        out = self.cref.coeff_to_extended(FIELD, p, self.k, self.d.extended_k, self.zeta, self.d.extended_omega, self.threads)
+        self._t("coeff_to_extended", t0)
+        return out
+
+    def e2c(self, p):
+        t0 = time.time()
+        out = self.cref.extended_to_coeff(FIELD, p, self.d.extended_k, self.d.extended_omega_inv, self.d.extended_ifft_divisor, self.zeta,
+                                          self.n * (DEGREE_J - 1), self.threads)
+        self._t("extended_to_coeff", t0)
+        return out
+
+    def vanish(self, p):
+        tev = self.cref.ints_to_bytes(self.d.t_evaluations)
+        tfull = tev[np.arange(1 << self.d.extended_k) % len(self.d.t_evaluations)]
+        return self.cref.ast_eval(FIELD, np.stack([p, tfull]), self.d.extended_k,
+                                  np.array([[0, 0, 0, 0], [0, 1, 0, 0], [4, 0, 0, 0]], dtype=np.uint32), [], self.d.extended_omega, self.zeta, self.threads)
+
+    def ast(self, kind, polys, ch, extended):
+        from halo2_b200.evaluator import AstLeaf, compile_ast      # the pure-host flattener of the Ast (no GPU involved)
+        log_n = self.d.extended_k if extended else self.k
+        stride = 1 << (self.d.extended_k - self.k) if extended else 1
+        code, consts = compile_ast(_schedule_ast(kind, [AstLeaf(i) for i in range(len(polys))], ch), P_MOD, stride)
+        omega = self.d.extended_omega if extended else self.d.omega
+        return self.cref.ast_eval(FIELD, np.stack([p[:1 << log_n] for p in polys]), log_n, code, consts, omega, self.zeta if extended else 1, self.threads)
+
+    def evals(self, polys, points):
+        t0 = time.time()
+        out = [self.cref.eval_polynomial(FIELD, p[:self.n], x) for p, x in zip(polys, points)]
+        self._t("eval_polynomial", t0)
+        return out
+
+    def kate(self, p, point):
+        t0 = time.time()
+        q = self.cref.kate_division(FIELD, p[:self.n], point)
+        self._t("kate_division", t0)
+        return np.concatenate([q, np.zeros((1, 32), dtype=np.uint8)])       # multiopen/prover.rs: poly.push(ZERO)
+
+    def pieces(self, p, count):
+        return [p[i * self.n:(i + 1) * self.n] for i in range(count)]
+
+    def add_at(self, p, idx, delta):
+        v = (int.from_bytes(p[idx].tobytes(), "little") + delta) % P_MOD
+        p[idx] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+
+    def ipa(self, p_prime, x3, z, challenge, l_rand, r_rand):
+        t0 = time.time()
+        out = self.cref.ipa_rounds_transcript(CURVE, self.gwu, self.k, p_prime[:self.n], x3, z, challenge, self.cref.ints_to_bytes(l_rand),
+                                              self.cref.ints_to_bytes(r_rand), self.ipa_threads)
+        self._t("ipa", t0)
+        return out
+
+    def sync(self):
+        pass
+
+    def free(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def replay_inputs(cref, k, seed):
+    """Synthetic witness of the replay: three advice columns and the base of the permutation product (Lagrange values), the
+    vanishing argument's random polynomial and the opening's s_poly (coefficients), every blind and the per-round randomness
+    -- all from the seeded generator of SURVEY.md section 8(d)."""
+    n = 1 << k
+    cols = [cref.gen_scalars(FIELD, seed + 10 + i, n) for i in range(3)]
+    zbase = cref.gen_scalars(FIELD, seed + 20, n)
+    rand_poly = cref.gen_scalars(FIELD, seed + 21, n)
+    s_poly = cref.gen_scalars(FIELD, seed + 22, n)
+    blinds = cref.bytes_to_ints(cref.gen_scalars(FIELD, seed + 23, 16))
+    l_rand = cref.bytes_to_ints(cref.gen_scalars(FIELD, seed + 24, k))
+    r_rand = cref.bytes_to_ints(cref.gen_scalars(FIELD, seed + 25, k))
+    return {"cols": cols, "zbase": zbase, "rand_poly": rand_poly, "s_poly": s_poly, "blinds": blinds, "l_rand": l_rand, "r_rand": r_rand}
+
+
+def run(arm, inp, k, omega):
+    """One proof-shaped pass; returns the proof bytes.  `omega`: the 2^k-th root of unity of the domain."""
+    T = Blake2bTranscript()
+    n = 1 << k
+    bl = list(inp["blinds"])
+    m = P_MOD
+    # 1. advice columns
+    adv_l = [arm.poly(c) for c in inp["cols"]]
+    for pt in arm.commit(adv_l, bl[0:3], lagrange=True):
+        T.write_point(pt)
+    adv = [arm.l2c(p) for p in adv_l]
+    adv_e = [arm.c2e(p) for p in adv]
+    # 2. permutation product
+    ch = {"theta": T.squeeze_challenge(), "beta": T.squeeze_challenge(), "gamma": T.squeeze_challenge()}
+    z_l = arm.ast("perm_z", [arm.poly(inp["zbase"])], ch, extended=False)
+    T.write_point(arm.commit([z_l], bl[3:4], lagrange=True)[0])
+    z = arm.l2c(z_l)
+    z_e = arm.c2e(z)
+    # 3. vanishing argument: random polynomial
+    rnd = arm.poly(inp["rand_poly"])
+    T.write_point(arm.commit([rnd], bl[4:5], lagrange=False)[0])
+    # 4. h(X)
+    ch["y"] = T.squeeze_challenge()
+    h_e = arm.vanish(arm.ast("h", adv_e + [z_e], ch, extended=True))
+    h = arm.e2c(h_e)
+    hp = arm.pieces(h, DEGREE_J - 1)
+    for pt in arm.commit(hp, bl[5:9], lagrange=False):
+        T.write_point(pt)
+    # 5. evaluations at x (advice at x and x*omega, z at x, x*omega, x*omega^-1... : 3 + 3 + 3 + 4 + 1 = 14 serial Horner loops)
+    x = T.squeeze_challenge()
+    xw, xwi = x * omega % m, x * pow(omega, m - 2, m) % m
+    ev_polys = adv + adv + [z, z, z] + hp + [rnd]
+    ev_points = [x] * 3 + [xw] * 3 + [x, xw, xwi] + [x] * 4 + [x]
+    evals = arm.evals(ev_polys, ev_points)
+    for e in evals:
+        T.write_scalar(e)
+    # 6. multiopen: two point sets {x}: advice, h pieces, random poly;  {x omega}: advice, z
+    x1 = T.squeeze_challenge()
+    x2 = T.squeeze_challenge()
+    set0 = adv + hp + [rnd]
+    set1 = adv + [z]
+    c0 = {"coeffs": [pow(x1, i, m) for i in range(len(set0))]}
+    c1 = {"coeffs": [pow(x1, i, m) for i in range(len(set1))]}
+    q0 = arm.ast("lincomb", set0, c0, extended=False)
+    q1 = arm.ast("lincomb", set1, c1, extended=False)
+    e0, e1 = arm.evals([q0, q1], [x, xw])
+    arm.add_at(q0, 0, -e0)                                   # (q(X) - q(point)) / (X - point)
+    arm.add_at(q1, 0, -e1)
+    k0, k1 = arm.kate(q0, x), arm.kate(q1, xw)
+    f = arm.ast("lincomb", [k0, k1], {"coeffs": [1, x2]}, extended=False)
+    T.write_point(arm.commit([f], bl[9:10], lagrange=False)[0])
+    x3 = T.squeeze_challenge()
+    arm.add_at(q0, 0, e0)
+    arm.add_at(q1, 0, e1)
+    for e in arm.evals([q0, q1], [x3, x3]):
+        T.write_scalar(e)
+    x4 = T.squeeze_challenge()
+    p = arm.ast("lincomb", [f, q0, q1], {"coeffs": [1, x4, x4 * x4 % m]}, extended=False)
+    p_blind = (bl[9] + x4 * bl[10] + x4 * x4 % m * bl[11]) % m
+    # 7. the opening, poly/commitment/prover.rs:36-145
+    s = arm.poly(inp["s_poly"])
+    s_at = arm.evals([s], [x3])[0]
+    arm.add_at(s, 0, -s_at)                                  # :51
+    s_blind = bl[12]
+    T.write_point(arm.commit([s], [s_blind], lagrange=False)[0])
+    xi = T.squeeze_challenge()
+    zc = T.squeeze_challenge()
+    pp = arm.ast("lincomb", [s, p], {"coeffs": [xi, 1]}, extended=False)      # :76
+    v = arm.evals([pp], [x3])[0]
+    arm.add_at(pp, 0, -v)                                    # :78
+    fsyn = (s_blind * xi + p_blind) % m                      # :79
+
+    us = []
+
+    def challenge(j, l_xy, r_xy):                            # :124-128
+        T.write_point(l_xy)
+        T.write_point(r_xy)
+        us.append(T.squeeze_challenge())
+        return us[-1]
+
+    ls, rs, c = arm.ipa(pp, x3, zc, challenge, inp["l_rand"], inp["r_rand"])
+    for j, u in enumerate(us):                               # :143-144
+        fsyn = (fsyn + inp["l_rand"][j] * pow(u, m - 2, m) + inp["r_rand"][j] * u) % m
+    T.write_scalar(c)                                        # :150
+    T.write_scalar(fsyn)                                     # :151
+    arm.sync()
+    return bytes(T.proof)
