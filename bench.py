@@ -214,6 +214,16 @@ def prover_replay(h2, cref, threads, reps=3):
                 "glue and host-side transcript included.  CPU arm: C restatement, hot-path calls only."}
 
 
+def prover_replay_inputs(cref):
+    n = 1 << PROVER_K
+    gl = cref.gen_points("vesta", SEED + 50, n + 1)
+    g = cref.gen_points("vesta", SEED + 51, n + 2)       # g || w || u
+    g[n] = gl[n]                                         # same w
+    polys = [cref.gen_scalars("fp", SEED + 60 + i, n) for i in range(4)]
+    ext = cref.gen_scalars("fp", SEED + 70, n << 2)
+    return g, gl, polys, ext
+
+
 def params_lagrange_ms(h2, cref, threads, reps=3):
     """Params::new's g -> g_lagrange derivation at k=14 (poly/commitment.rs:74-101: EC-iFFT = best_fft at G = curve point,
     * 2^-k, batch_normalize) through h2_params_lagrange, host generators in / host g_lagrange out, next to the C
