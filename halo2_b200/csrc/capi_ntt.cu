@@ -65,7 +65,9 @@ static int ntt_run(int field, const fe *d_in, uint32_t in_log_n, fe *d_out, uint
         A.in_log_n = in_log_n; A.out_len = out_len;
         for (int k = 0; k < 3; k++) { A.in_scale[k] = sc.in_s[k]; A.out_scale[k] = sc.out_s[k]; }
         uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
-        uint32_t smem = ntt_smem_bytes(sp[i], logc[i]);
+        uint32_t smem = ntt_smem_bytes(sp[i], logc[i]) + ntt_twc_bytes(sp[i], logc[i], i == passes - 1);
+        static bool smem_optin = false;      // per instantiation <P>: a single-CTA transform of 2^10 elements wants 64 KiB
+        if (!smem_optin) { CU(cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); smem_optin = true; }
         prof_begin(PROF_NTT_PASS, s);
         LAUNCH(ntt_pass_kernel<P>, tiles, 128, smem, s, A);
         prof_end(s);

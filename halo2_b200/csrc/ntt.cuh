@@ -56,6 +56,8 @@ H2_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
 
 H2_HD uint32_t ntt_smem_stride(uint32_t logc) { return (1u << logc) + (logc ? 1u : 0u); }
 H2_HD uint32_t ntt_smem_bytes(uint32_t sp, uint32_t logc) { return 2u * 16u * (ntt_smem_stride(logc) << sp); }
+// + the pass's twiddles (two planes as well): (2^sp - 1) per tile, times the C columns in the last pass
+H2_HD uint32_t ntt_twc_bytes(uint32_t sp, uint32_t logc, bool last) { return 32u * ((last ? (1u << logc) : 1u) * ((1u << sp) - 1u)); }
 
 H2_HD fe sm_load(const uint4 *sm, uint32_t plane, uint32_t idx) {
     uint4 lo = sm[idx], hi = sm[plane + idx];
@@ -128,6 +130,95 @@ template <class P> struct NttPass {
         }
     }
 
+    // ---- twiddles of the pass staged in shared memory, stages taken two at a time in registers ---------------------------
+    // The twiddle of stage sl (1-based inside the pass) for local index k < 2^(sl-1) is tw[((k << s0) | p_low) << (log_n - s0 - sl)].
+    // Geometry A: p_low is a property of the TILE, so a tile needs 2^sp - 1 twiddles, shared by its columns; geometry B: p_low
+    // differs per column: C (2^sp - 1).  They are fetched once per tile into `twc` (slot = col_slot (2^sp - 1) + 2^(sl-1) - 1 + k,
+    // two 16-byte planes like the data), so the stage loop touches no global memory.
+    static H2_HD uint32_t twc_count(const NttPassArgs &A) { return ((A.flags & NTT_LAST) ? (1u << A.logc) : 1u) * ((1u << A.sp) - 1u); }
+    static H2_HD uint64_t twc_exponent(const NttPassArgs &A, uint32_t tile, uint32_t slot) {
+        const uint32_t per = (1u << A.sp) - 1u;
+        const uint32_t cs = slot / per, w = slot % per + 1u;       // w = 2^(sl-1) + k
+        uint32_t sl = 1;
+        while ((w >> sl) != 0) sl++;
+        const uint32_t k = w - (1u << (sl - 1));
+        return (((uint64_t)k << A.s0) | p_low_of(A, tile, cs)) << (A.log_n - A.s0 - sl);
+    }
+    static H2_HD void twiddle_phase(const NttPassArgs &A, uint32_t tile, uint32_t tid, uint32_t nthr, uint4 *twc) {
+        const uint32_t total = twc_count(A);
+        for (uint32_t slot = tid; slot < total; slot += nthr) sm_store(twc, total, slot, fe_load(A.tw + twc_exponent(A, tile, slot)));
+    }
+    static H2_HD fe twc_load(const NttPassArgs &A, const uint4 *twc, uint32_t col, uint32_t sl, uint32_t k) {
+        const uint32_t per = (1u << A.sp) - 1u;
+        return sm_load(twc, twc_count(A), ((A.flags & NTT_LAST) ? col * per : 0u) + (1u << (sl - 1)) - 1u + k);
+    }
+    static H2_HD uint32_t num_steps(uint32_t sp) { return (sp + 1) / 2; }
+    // step `st` = stages 2 st + 1 and 2 st + 2 of the pass (the last step of an odd pass is a single stage).  A radix-4
+    // unit holds rows base | {0, 2^(d-1), 2^d, 2^d + 2^(d-1)} of one column in registers: two butterflies of stage sl (pairing
+    // bit d = sp - sl, one twiddle), two of stage sl + 1 (pairing bit d - 1, two twiddles) -- half the shared-memory traffic
+    // and half the barriers of one stage at a time.  Twiddle 1 (exponent 0, arithmetic.rs:229-236) skips its multiply.
+    // L: the shared-memory layout of the tile (element (r, col) -> load / store).
+    template <class L>
+    static H2_HD void step_phase_l(const NttPassArgs &A, uint32_t tile, uint32_t st, uint32_t tid, uint32_t nthr, const L &lay, const uint4 *twc) {
+        const uint32_t R = 1u << A.sp, C = 1u << A.logc;
+        const uint32_t sl = 2 * st + 1;
+        const bool geomB = (A.flags & NTT_LAST) != 0;
+        const bool tile_p0 = !geomB && p_low_of(A, tile, 0) == 0;
+        const bool last_step = st + 1 == num_steps(A.sp);
+        if (sl == A.sp) {                                   // single last stage: d = 0
+            for (uint32_t w = tid; w < (R >> 1) * C; w += nthr) {
+                const uint32_t col = w & (C - 1), pr = w >> A.logc;
+                const uint32_t r0 = pr << 1, r1 = r0 | 1u;
+                const uint32_t k = bitrev32(pr, sl - 1);
+                const bool unit = k == 0 && (geomB ? p_low_of(A, tile, col) == 0 : tile_p0);
+                fe a = lay.load(A, tile, st, r0, col), b = lay.load(A, tile, st, r1, col);
+                fe t = unit ? b : fe_mul<P>(b, twc_load(A, twc, col, sl, k));
+                lay.store(A, tile, last_step, r0, col, fe_add<P>(a, t));
+                lay.store(A, tile, last_step, r1, col, fe_sub<P>(a, t));
+            }
+            return;
+        }
+        const uint32_t d = A.sp - sl;                       // stage sl pairs bit d, stage sl + 1 bit d - 1  (d >= 1)
+        for (uint32_t w = tid; w < (R >> 2) * C; w += nthr) {
+            const uint32_t col = w & (C - 1), q = w >> A.logc;
+            const uint32_t base = ((q >> (d - 1)) << (d + 1)) | (q & ((1u << (d - 1)) - 1u));
+            const uint32_t r00 = base, r01 = base | (1u << (d - 1)), r10 = base | (1u << d), r11 = base | (1u << d) | (1u << (d - 1));
+            const uint32_t k1 = bitrev32(base >> (d + 1), sl - 1);          // stage sl: both butterflies
+            const uint32_t k2a = bitrev32(base >> d, sl);                    // stage sl + 1, rows (00, 01)
+            const uint32_t k2b = bitrev32((base >> d) | 1u, sl);             //              rows (10, 11): top bit set, never exponent 0
+            const bool p0 = geomB ? p_low_of(A, tile, col) == 0 : tile_p0;
+            fe x00 = lay.load(A, tile, st, r00, col), x01 = lay.load(A, tile, st, r01, col);
+            fe x10 = lay.load(A, tile, st, r10, col), x11 = lay.load(A, tile, st, r11, col);
+            {
+                const bool unit = p0 && k1 == 0;
+                fe t1 = unit ? fe_zero() : twc_load(A, twc, col, sl, k1);
+                fe t = unit ? x10 : fe_mul<P>(x10, t1);
+                x10 = fe_sub<P>(x00, t); x00 = fe_add<P>(x00, t);
+                t = unit ? x11 : fe_mul<P>(x11, t1);
+                x11 = fe_sub<P>(x01, t); x01 = fe_add<P>(x01, t);
+            }
+            {
+                fe t = (p0 && k2a == 0) ? x01 : fe_mul<P>(x01, twc_load(A, twc, col, sl + 1, k2a));
+                x01 = fe_sub<P>(x00, t); x00 = fe_add<P>(x00, t);
+                t = fe_mul<P>(x11, twc_load(A, twc, col, sl + 1, k2b));
+                x11 = fe_sub<P>(x10, t); x10 = fe_add<P>(x10, t);
+            }
+            lay.store(A, tile, last_step, r00, col, x00); lay.store(A, tile, last_step, r01, col, x01);
+            lay.store(A, tile, last_step, r10, col, x10); lay.store(A, tile, last_step, r11, col, x11);
+        }
+    }
+    // the two-plane layout of the classic kernel (row stride C + 1 units)
+    struct PlaneLayout {
+        uint4 *sm; uint32_t stride, plane;
+        H2_HD fe load(const NttPassArgs &, uint32_t, uint32_t, uint32_t r, uint32_t col) const { return sm_load(sm, plane, r * stride + col); }
+        H2_HD void store(const NttPassArgs &, uint32_t, bool, uint32_t r, uint32_t col, const fe &x) const { sm_store(sm, plane, r * stride + col, x); }
+    };
+    static H2_HD void step_phase(const NttPassArgs &A, uint32_t tile, uint32_t st, uint32_t tid, uint32_t nthr, uint4 *sm, const uint4 *twc) {
+        PlaneLayout lay;
+        lay.sm = sm; lay.stride = ntt_smem_stride(A.logc); lay.plane = lay.stride << A.sp;
+        step_phase_l(A, tile, st, tid, nthr, lay, twc);
+    }
+
     static H2_HD void store_phase(const NttPassArgs &A, uint32_t tile, uint32_t tid, uint32_t nthr, const uint4 *sm) {
         const uint32_t R = 1u << A.sp, C = 1u << A.logc, stride = ntt_smem_stride(A.logc), plane = stride << A.sp;
         const bool last = (A.flags & NTT_LAST) != 0;
@@ -167,13 +258,15 @@ template <class P> struct TwiddleGen {
 };
 
 #if defined(__CUDACC__)
-template <class P> __global__ void __launch_bounds__(128, 7) ntt_pass_kernel(const NttPassArgs A) {
+template <class P> __global__ void __launch_bounds__(128, 4) ntt_pass_kernel(const NttPassArgs A) {
     extern __shared__ uint4 h2_ntt_smem[];
     const uint32_t tile = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    uint4 *twc = h2_ntt_smem + (ntt_smem_bytes(A.sp, A.logc) >> 4);
+    NttPass<P>::twiddle_phase(A, tile, tid, nthr, twc);
     NttPass<P>::load_phase(A, tile, tid, nthr, h2_ntt_smem);
     __syncthreads();
-    for (uint32_t sl = 1; sl <= A.sp; sl++) {
-        NttPass<P>::stage_phase(A, tile, sl, tid, nthr, h2_ntt_smem);
+    for (uint32_t st = 0; st < NttPass<P>::num_steps(A.sp); st++) {
+        NttPass<P>::step_phase(A, tile, st, tid, nthr, h2_ntt_smem, twc);
         __syncthreads();
     }
     NttPass<P>::store_phase(A, tile, tid, nthr, h2_ntt_smem);

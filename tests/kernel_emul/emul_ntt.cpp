@@ -39,11 +39,17 @@ static int run_ntt(int mode, const uint8_t *in, uint32_t in_log_n, uint32_t log_
         if (mode == 3) { oc[0] = fe_from_mont<P>(dv); oc[1] = fe_from_mont<P>(fe_mul<P>(dv, zp[2])); oc[2] = fe_from_mont<P>(fe_mul<P>(dv, zp[1])); }
         for (int k = 0; k < 3; k++) A.out_scale[k] = oc[k];
         uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
-        std::vector<uint4> sm(ntt_smem_bytes(sp[i], logc[i]) / 16);
-        for (uint32_t tile = 0; tile < tiles; tile++) {
+        std::vector<uint4> sm(ntt_smem_bytes(sp[i], logc[i]) / 16), twc(ntt_twc_bytes(sp[i], logc[i], i == passes - 1) / 16 + 1);
+        for (uint32_t tile = 0; tile < tiles; tile++) {      // the same phase order as ntt_pass_kernel, one barrier between phases
+            for (uint32_t t = 0; t < nthr; t++) NttPass<P>::twiddle_phase(A, tile, t, nthr, twc.data());
             for (uint32_t t = 0; t < nthr; t++) NttPass<P>::load_phase(A, tile, t, nthr, sm.data());
-            for (uint32_t sl = 1; sl <= sp[i]; sl++)
-                for (uint32_t t = 0; t < nthr; t++) NttPass<P>::stage_phase(A, tile, sl, t, nthr, sm.data());
+            if (tile & 1) {                                   // the one-stage-at-a-time form stays as a cross-check of the radix-4 steps
+                for (uint32_t sl = 1; sl <= sp[i]; sl++)
+                    for (uint32_t t = 0; t < nthr; t++) NttPass<P>::stage_phase(A, tile, sl, t, nthr, sm.data());
+            } else {
+                for (uint32_t st = 0; st < NttPass<P>::num_steps(sp[i]); st++)
+                    for (uint32_t t = 0; t < nthr; t++) NttPass<P>::step_phase(A, tile, st, t, nthr, sm.data(), twc.data());
+            }
             for (uint32_t t = 0; t < nthr; t++) NttPass<P>::store_phase(A, tile, t, nthr, sm.data());
         }
         s0 += sp[i];
