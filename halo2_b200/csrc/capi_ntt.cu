@@ -67,8 +67,21 @@ static int ntt_run(int field, const fe *d_in, uint32_t in_log_n, fe *d_out, uint
         uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
         uint32_t smem = ntt_smem_bytes(sp[i], logc[i]) + ntt_twc_bytes(sp[i], logc[i], i == passes - 1);
         static bool smem_optin = false;      // per instantiation <P>: a single-CTA transform of 2^10 elements wants 64 KiB
-        if (!smem_optin) { CU(cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); smem_optin = true; }
+        if (!smem_optin) {
+            CU(cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CU(cudaFuncSetAttribute(ntt_pass_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            smem_optin = true;
+        }
         prof_begin(PROF_NTT_PASS, s);
+        if (X.ntt_tma && NttDense<P>::supported(A)) {
+            // persistent CTAs (4 per SM by registers), double-buffered tiles on the bulk-copy engine
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, X.device);
+            // every CTA walks the same number of tiles (+-1): grid = tiles / ceil(tiles / resident CTAs)
+            const uint32_t slots = (uint32_t)sms * 4u, per = (tiles + slots - 1) / slots;
+            const uint32_t grid = (tiles + per - 1) / per;
+            LAUNCH(ntt_pass_tma_kernel<P>, grid, 128, ntt_tma_smem_bytes(sp[i], logc[i], i == passes - 1), s, A, tiles);
+        } else
         LAUNCH(ntt_pass_kernel<P>, tiles, 128, smem, s, A);
         prof_end(s);
         s0 += sp[i];
@@ -154,6 +167,12 @@ extern "C" int h2_ntt_dev(int field, const void *d_in, void *d_out, const void *
     else return fail("unknown field id");
     if (rc) return rc;
     return scratch_release(s);
+}
+// test / bench hook: 1 = the bulk-copy (TMA) persistent pass kernel where it applies, 0 = the classic kernel (default: measured faster)
+extern "C" int h2_test_set_ntt_tma(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ctx.ntt_tma = on ? 1u : 0u;
+    return 0;
 }
 extern "C" int h2_ntt_clear_cache(void) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -112,6 +112,10 @@ struct Context {
     uint32_t accum_ways = 1;                 // quads per work item in the small-problem accumulation (1, 2, 4; test hook).  Measured at
                                              // k = 14, c = 15: commit 0.360 / 0.329 / 0.361 ms, IPA opening 5.7 / 6.1 / 7.6 ms -- the accumulation is
                                              // bound by lane-multiplies (a quad addition occupies 16 slots for 10 products), not by its chains
+    uint32_t ntt_tma = 0;                    // NTT passes: 1 = bulk-copy (TMA) persistent kernel where it applies, 0 = classic kernel.  Measured on
+                                             // B200 (profiles/r2e_*): 2^20 0.27-0.30 ms vs 0.215 ms, 2^24 4.77 vs 3.67 ms -- the pass is bound by the
+                                             // integer pipes (fmaheavy 55-61 %, ALU 54 %, issue 51 %, top stall `wait`), not by its memory phases, and
+                                             // the double-buffered tiles cost occupancy (4 CTAs/SM, 2 in the last pass): opt-in, default off
     uint32_t ecfft_quad = 1;                 // EC-FFT butterfly form: 1 = by size (default), 0 = one thread each, 2 = quads (test hook)
     // MSM scratch
     DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,

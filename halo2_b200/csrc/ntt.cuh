@@ -271,6 +271,195 @@ template <class P> __global__ void __launch_bounds__(128, 4) ntt_pass_kernel(con
     }
     NttPass<P>::store_phase(A, tile, tid, nthr, h2_ntt_smem);
 }
+#endif
+// ------------------------------------------------------------------------------------------------------------------
+// The same pass with the tile traffic on the bulk-copy (TMA) engine: a persistent CTA walks tiles, the rows of tile
+// i + 1 land in the second shared-memory buffer (cp.async.bulk global -> shared, completion counted on an mbarrier)
+// and the rows of tile i - 1 drain (cp.async.bulk shared -> global) while the warps run the butterflies of tile i, and the
+// next tile's twiddles arrive by cp.async.  The compute warps execute no global load or store and no address arithmetic
+// per element: one bulk-copy instruction per thread and tile each way.
+//   geometry A: a tile row (C adjacent elements, C x 32 B) is contiguous in global memory both ways -> R row copies.
+//   geometry B: a tile COLUMN (the 2^sp low indices, 2^sp x 32 B) is contiguous on the way in -> C column copies; the
+//       outputs p = bitrev(r) << s0 | p_low are contiguous across the C columns of a row -> the last step writes into a
+//       row-major staging area and R row copies carry it out.
+// Shared memory is dense (32-byte elements, rows padded by 16 B so that consecutive rows start 4 banks apart).
+// ------------------------------------------------------------------------------------------------------------------
+H2_HD uint32_t ntt_tma_rowb(uint32_t logc) { return (32u << logc) + 16u; }
+H2_HD uint32_t ntt_tma_colb(uint32_t sp) { return (32u << sp) + 16u; }
+H2_HD uint32_t ntt_tma_buf_bytes(uint32_t sp, uint32_t logc, bool last) {
+    return last ? (ntt_tma_colb(sp) << logc) : (ntt_tma_rowb(logc) << sp);
+}
+H2_HD uint32_t ntt_tma_smem_bytes(uint32_t sp, uint32_t logc, bool last) {
+    return 128u + 2u * ntt_tma_buf_bytes(sp, logc, last) + 2u * ntt_twc_bytes(sp, logc, last) + (last ? (ntt_tma_rowb(logc) << sp) : 0u);
+}
+H2_HD fe dense_load(const uint8_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fe r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+H2_HD void dense_store(uint8_t *p, const fe &a) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+template <class P> struct NttDense {
+    // element (r, col) of the tile in the dense buffers; the first step applies in_scale, the last step out_scale
+    struct Layout {
+        uint8_t *buf, *out;          // out: geometry B's row-major staging (last step), else == buf
+        uint32_t rowb, colb;
+        bool geomB;
+        H2_HD fe load(const NttPassArgs &A, uint32_t tile, uint32_t st, uint32_t r, uint32_t col) const {
+            fe x = dense_load(geomB ? buf + col * colb + r * 32u : buf + r * rowb + col * 32u);
+            if (st == 0 && (A.flags & NTT_FIRST) && (A.flags & NTT_IN_SCALE)) x = fe_mul<P>(x, A.in_scale[NttPass<P>::elem_j(A, tile, r, col) % 3]);
+            return x;
+        }
+        H2_HD void store(const NttPassArgs &A, uint32_t tile, bool last_step, uint32_t r, uint32_t col, const fe &x) const {
+            if (last_step && geomB) {
+                fe y = x;
+                if (A.flags & NTT_OUT_SCALE) {
+                    const uint64_t p = ((uint64_t)bitrev32(r, A.sp) << A.s0) | NttPass<P>::p_low_of(A, tile, col);
+                    y = fe_mul<P>(y, A.out_scale[p % 3]);
+                }
+                dense_store(out + r * rowb + col * 32u, y);
+            } else dense_store(geomB ? buf + col * colb + r * 32u : buf + r * rowb + col * 32u, x);
+        }
+    };
+    // what the copy engine moves for one tile.  Copy unit u: geometry A -> row u (u < R); geometry B in -> column u (u < C),
+    // geometry B out -> row u (u < R).  `valid` = false: nothing to copy (zero padding in, truncated out).
+    struct Span { uint64_t elem; uint32_t smem_off, bytes; bool valid; };
+    static H2_HD uint32_t in_units(const NttPassArgs &A) { return (A.flags & NTT_LAST) ? (1u << A.logc) : (1u << A.sp); }
+    static H2_HD Span in_span(const NttPassArgs &A, uint32_t tile, uint32_t u) {
+        Span s;
+        const bool geomB = (A.flags & NTT_LAST) != 0;
+        s.elem = geomB ? NttPass<P>::elem_j(A, tile, 0, u) : NttPass<P>::elem_j(A, tile, u, 0);
+        s.smem_off = geomB ? u * ntt_tma_colb(A.sp) : u * ntt_tma_rowb(A.logc);
+        s.bytes = geomB ? (32u << A.sp) : (32u << A.logc);
+        s.valid = !((A.flags & NTT_FIRST) && (s.elem >> A.in_log_n) != 0);     // runs never straddle 2^in_log_n (powers of two)
+        return s;
+    }
+    static H2_HD Span out_span(const NttPassArgs &A, uint32_t tile, uint32_t r) {
+        Span s;
+        s.smem_off = r * ntt_tma_rowb(A.logc);
+        s.bytes = 32u << A.logc;
+        if (A.flags & NTT_LAST) {
+            s.elem = ((uint64_t)bitrev32(r, A.sp) << A.s0) | NttPass<P>::p_low_of(A, tile, 0);
+            s.valid = s.elem < A.out_len;
+        } else { s.elem = NttPass<P>::elem_j(A, tile, r, 0); s.valid = true; }
+        return s;
+    }
+    static H2_HD bool supported(const NttPassArgs &A) {
+        if ((A.flags & NTT_LAST) && (A.out_len & ((1ull << A.logc) - 1))) return false;      // whole rows only on the way out
+        if ((A.flags & NTT_FIRST) && (A.flags & NTT_LAST)) return false;                      // single-pass transforms: classic kernel
+        return true;
+    }
+};
+
+#if defined(__CUDACC__)
+namespace tma {
+__device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(saddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(dst)), "l"(src), "r"(bytes),
+                 "r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp16(void *dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+}  // namespace tma
+
+template <class P> __global__ void __launch_bounds__(128, 4) ntt_pass_tma_kernel(const NttPassArgs A, uint32_t tiles) {
+    extern __shared__ __align__(128) uint8_t h2_ntt_tma_smem[];
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const bool geomB = (A.flags & NTT_LAST) != 0;
+    const uint32_t R = 1u << A.sp, bufb = ntt_tma_buf_bytes(A.sp, A.logc, geomB), twb = ntt_twc_bytes(A.sp, A.logc, geomB);
+    uint64_t *full = reinterpret_cast<uint64_t *>(h2_ntt_tma_smem);                 // full[0], full[1]
+    uint8_t *buf0 = h2_ntt_tma_smem + 128;
+    uint8_t *twc0 = buf0 + 2 * bufb;
+    uint8_t *outst = twc0 + 2 * twb;                                                 // geometry B only
+    const uint32_t ntw = NttPass<P>::twc_count(A);
+    const uint32_t units_in = NttDense<P>::in_units(A);
+    if (tid == 0) {   // one arrival per copy unit: every issuing thread announces its own bytes
+        tma::mbar_init(&full[0], units_in);
+        tma::mbar_init(&full[1], units_in);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // everything one tile needs, issued asynchronously: rows / columns by the bulk-copy engine, twiddles by cp.async
+    auto fetch = [&](uint32_t tile, uint32_t b) {
+        uint8_t *buf = buf0 + b * bufb;
+        for (uint32_t u = tid; u < units_in; u += nthr) {
+            const auto sp_ = NttDense<P>::in_span(A, tile, u);
+            if (sp_.valid) {
+                tma::mbar_expect_tx(&full[b], sp_.bytes);
+                tma::bulk_g2s(buf + sp_.smem_off, A.in + sp_.elem, sp_.bytes, &full[b]);
+            } else {
+                for (uint32_t o = 0; o < sp_.bytes; o += 16) *reinterpret_cast<uint4 *>(buf + sp_.smem_off + o) = make_uint4(0, 0, 0, 0);
+                tma::mbar_expect_tx(&full[b], 0);          // zero padding: arrive without bytes (the release orders the stores above)
+            }
+        }
+        uint4 *twc = reinterpret_cast<uint4 *>(twc0 + b * twb);
+        for (uint32_t slot = tid; slot < ntw; slot += nthr) {
+            const fe *src = A.tw + NttPass<P>::twc_exponent(A, tile, slot);
+            tma::cp16(twc + slot, src);
+            tma::cp16(twc + ntw + slot, reinterpret_cast<const uint8_t *>(src) + 16);
+        }
+        tma::cp_commit();
+    };
+    uint32_t cur = blockIdx.x;
+    if (cur < tiles) fetch(cur, 0);
+    for (uint32_t it = 0; cur < tiles; it++, cur += gridDim.x) {
+        const uint32_t b = it & 1u, nxt = cur + gridDim.x;
+        // this thread's stores of the previous tile have finished READING shared memory: its rows of the other buffer (geometry
+        // A) / of the staging area (geometry B) may be overwritten
+        tma::bulk_wait_read0();
+        if (nxt < tiles) { fetch(nxt, b ^ 1u); tma::cp_wait<1>(); } else tma::cp_wait<0>();
+        tma::mbar_wait(&full[b], (it >> 1) & 1u);
+        __syncthreads();
+        typename NttDense<P>::Layout lay;
+        lay.buf = buf0 + b * bufb; lay.out = geomB ? outst : lay.buf;
+        lay.rowb = ntt_tma_rowb(A.logc); lay.colb = ntt_tma_colb(A.sp); lay.geomB = geomB;
+        const uint4 *twc = reinterpret_cast<const uint4 *>(twc0 + b * twb);
+        for (uint32_t st = 0; st < NttPass<P>::num_steps(A.sp); st++) {
+            NttPass<P>::step_phase_l(A, cur, st, tid, nthr, lay, twc);
+            if (st + 1 < NttPass<P>::num_steps(A.sp)) __syncthreads();
+        }
+        tma::fence_async_smem();          // the generic-proxy writes above become visible to the bulk-copy engine
+        __syncthreads();
+        for (uint32_t r = tid; r < R; r += nthr) {
+            const auto sp_ = NttDense<P>::out_span(A, cur, r);
+            if (sp_.valid) tma::bulk_s2g(A.out + sp_.elem, lay.out + sp_.smem_off, sp_.bytes);
+        }
+        tma::bulk_commit();
+    }
+    tma::bulk_wait0();
+}
+#endif
+
+#if defined(__CUDACC__)
 template <class P> __global__ void twiddle_pow2_kernel(fe *pow2, fe omega, uint32_t count) {
     if (threadIdx.x == 0 && blockIdx.x == 0) TwiddleGen<P>::pow2_body(pow2, omega, count);
 }

@@ -284,6 +284,10 @@ int h2_test_set_chunk_threshold(uint32_t log2_n);
  * so that the link runs near its pinned rate and uploads still overlap compute; pinned / registered memory is used in
  * place.  0 switches the ring off (plain cudaMemcpyAsync): bench.py times both. */
 int h2_test_set_staging(int on);
+/* 1: NTT passes run as a persistent kernel whose tile traffic is on the bulk-copy (TMA) engine (cp.async.bulk + mbarrier,
+ * double buffered) wherever the pass geometry allows; 0 (default -- measured faster on B200): the classic
+ * load / compute / store kernel.  bench.py times both. */
+int h2_test_set_ntt_tma(int on);
 /* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
  * parameters on (default); 0 issues every launch individually. */
 int h2_test_set_graphs(int on);

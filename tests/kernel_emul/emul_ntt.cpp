@@ -40,6 +40,31 @@ static int run_ntt(int mode, const uint8_t *in, uint32_t in_log_n, uint32_t log_
         for (int k = 0; k < 3; k++) A.out_scale[k] = oc[k];
         uint32_t tiles = (uint32_t)(n >> (sp[i] + logc[i]));
         std::vector<uint4> sm(ntt_smem_bytes(sp[i], logc[i]) / 16), twc(ntt_twc_bytes(sp[i], logc[i], i == passes - 1) / 16 + 1);
+        const bool last = i == passes - 1;
+        if ((nthr & 1) && NttDense<P>::supported(A)) {
+            // odd thread counts select the dense-layout path of ntt_pass_tma_kernel: the bulk copies become memcpy
+            std::vector<uint8_t> buf(ntt_tma_buf_bytes(sp[i], logc[i], last) + 64), outst((ntt_tma_rowb(logc[i]) << sp[i]) + 64);
+            const fe *src = A.in;
+            std::vector<fe> dst_tmp;
+            fe *dst = A.out;
+            if (A.in == A.out) { dst_tmp.assign(A.in, A.in + n); src = dst_tmp.data(); }   // the kernel's in-place passes read a tile before writing it
+            for (uint32_t tile = 0; tile < tiles; tile++) {
+                for (uint32_t u = 0; u < NttDense<P>::in_units(A); u++) {
+                    auto spn = NttDense<P>::in_span(A, tile, u);
+                    if (spn.valid) memcpy(buf.data() + spn.smem_off, src + spn.elem, spn.bytes); else memset(buf.data() + spn.smem_off, 0, spn.bytes);
+                }
+                for (uint32_t t = 0; t < nthr; t++) NttPass<P>::twiddle_phase(A, tile, t, nthr, twc.data());
+                typename NttDense<P>::Layout lay;
+                lay.buf = buf.data(); lay.out = last ? outst.data() : buf.data();
+                lay.rowb = ntt_tma_rowb(logc[i]); lay.colb = ntt_tma_colb(sp[i]); lay.geomB = last;
+                for (uint32_t st = 0; st < NttPass<P>::num_steps(sp[i]); st++)
+                    for (uint32_t t = 0; t < nthr; t++) NttPass<P>::step_phase_l(A, tile, st, t, nthr, lay, twc.data());
+                for (uint32_t r = 0; r < (1u << sp[i]); r++) {
+                    auto spn = NttDense<P>::out_span(A, tile, r);
+                    if (spn.valid) memcpy(dst + spn.elem, lay.out + spn.smem_off, spn.bytes);
+                }
+            }
+        } else
         for (uint32_t tile = 0; tile < tiles; tile++) {      // the same phase order as ntt_pass_kernel, one barrier between phases
             for (uint32_t t = 0; t < nthr; t++) NttPass<P>::twiddle_phase(A, tile, t, nthr, twc.data());
             for (uint32_t t = 0; t < nthr; t++) NttPass<P>::load_phase(A, tile, t, nthr, sm.data());

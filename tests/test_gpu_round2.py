@@ -165,3 +165,32 @@ def test_advisor_findings_round1(eng):
     for q in (p, src, dst, other):
         q.close()
     prm.close()
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_ntt_tma_pass_kernel(eng, field):
+    """The bulk-copy (TMA) form of the NTT passes (cp.async.bulk + mbarrier, persistent CTAs, dense shared-memory tiles; opt-in
+    via h2_test_set_ntt_tma) against the oracle: plain transforms with a true root and a random omega, ifft, coeff_to_extended
+    (zero padding + zeta scaling inside the first step), extended_to_coeff (un-scaling + truncation in the last step)."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    L.check(lib.h2_test_set_ntt_tma(1))
+    try:
+        for log_n in (11, 13, 16, 18):
+            a = cref.gen_scalars(field, 300 + log_n, 1 << log_n)
+            for w in (pasta.omega_for_k(field, log_n), pasta.gen_scalars(field, 79, 1)[0]):
+                got = a.copy()
+                eng.best_fft(got, w, log_n, field)
+                assert (got == cref.best_fft(field, a, w, log_n)).all(), (field, log_n)
+        for (j, k) in ((4, 10), (5, 12), (5, 14)):
+            d = pasta.EvaluationDomain(field, j, k)
+            dom = eng.EvaluationDomain(field, j, k, d.g_coset)
+            a = cref.gen_scalars(field, 7, 1 << k)
+            co = cref.ifft(field, a, d.omega_inv, k, d.ifft_divisor)
+            assert (dom.lagrange_to_coeff(a) == co).all()
+            ext = cref.coeff_to_extended(field, co, k, d.extended_k, d.g_coset, d.extended_omega)
+            assert (dom.coeff_to_extended(co) == ext).all()
+            back = cref.extended_to_coeff(field, ext, d.extended_k, d.extended_omega_inv, d.extended_ifft_divisor, d.g_coset, (1 << k) * (j - 1))
+            assert (dom.extended_to_coeff(ext) == back).all()
+    finally:
+        L.check(lib.h2_test_set_ntt_tma(0))

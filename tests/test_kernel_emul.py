@@ -84,6 +84,24 @@ def test_emul_ntt(emu, field):
         for w in (pasta.omega_for_k(field, log_n), pasta.gen_scalars(field, 77, 1)[0]):
             got = _ntt(emu, field, 0, a, log_n, log_n, w, nthr=(7 if log_n < 8 else 64))
             assert (got == cref.best_fft(field, a, w, log_n)).all(), (field, log_n)
+    # odd thread counts select the dense shared-memory layout of the bulk-copy (TMA) pass kernel (emul_ntt.cpp): row /
+    # column spans, zero padding, the row-major output staging of the last pass, in_scale / out_scale inside the steps
+    for log_n in (11, 12, 14, 15):
+        a = cref.gen_scalars(field, 200 + log_n, 1 << log_n)
+        for w in (pasta.omega_for_k(field, log_n), pasta.gen_scalars(field, 78, 1)[0]):
+            assert (_ntt(emu, field, 0, a, log_n, log_n, w, nthr=63) == cref.best_fft(field, a, w, log_n)).all(), (field, log_n)
+    for (j, k) in ((4, 9), (5, 11), (5, 12)):
+        d = pasta.EvaluationDomain(field, j, k)
+        a = cref.gen_scalars(field, 6, 1 << k)
+        co = cref.ifft(field, a, d.omega_inv, k, d.ifft_divisor)
+        assert (_ntt(emu, field, 1, a, k, k, d.omega_inv, div=d.ifft_divisor, nthr=63) == co).all()
+        ext = cref.coeff_to_extended(field, co, k, d.extended_k, d.g_coset, d.extended_omega)
+        assert (_ntt(emu, field, 2, co, k, d.extended_k, d.extended_omega, zeta=d.g_coset, nthr=63) == ext).all()
+        ol = (1 << k) * (j - 1)
+        back = cref.extended_to_coeff(field, ext, d.extended_k, d.extended_omega_inv, d.extended_ifft_divisor, d.g_coset, ol)
+        got = _ntt(emu, field, 3, ext, d.extended_k, d.extended_k, d.extended_omega_inv, zeta=d.g_coset,
+                   div=d.extended_ifft_divisor, out_len=ol, nthr=63)
+        assert (got == back).all()
     for (j, k) in ((5, 5), (3, 6), (4, 9), (5, 11)):
         d = pasta.EvaluationDomain(field, j, k)
         a = cref.gen_scalars(field, 5, 1 << k)

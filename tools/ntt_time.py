@@ -8,7 +8,9 @@ dev = torch.device("cuda", 0)
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 P = {"fp": 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001, "fq": 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001}
 for log_n in [int(a) for a in sys.argv[1:]] or [20]:
-    n = 1 << log_n
+  n = 1 << log_n
+  for tma in (1, 0):
+    L.check(lib.h2_test_set_ntt_tma(tma))
     for f in ("fp", "fq"):
         m = P[f]
         w = pow(5, (m - 1) >> 32, m)
@@ -32,4 +34,4 @@ for log_n in [int(a) for a in sys.argv[1:]] or [20]:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        print(f"ntt 2^{log_n} {f}: {ms:.4f} ms  {n / ms / 1e6:.2f} G elems/s")
+        print(f"ntt 2^{log_n} {f} tma={tma}: {ms:.4f} ms  {n / ms / 1e6:.2f} G elems/s")
