@@ -30,15 +30,41 @@ std::atomic<uint64_t> g_launches{0};
 // ------------------------------------------------------------------------------------------------
 #include <condition_variable>
 #include <thread>
+#include <immintrin.h>
 namespace {
-struct CopyPool {            // a handful of host threads that memcpy slices in parallel
+// Slice copy of the staging pool.  The destination (a pinned ring slot on upload) is written once and next read by the DMA
+// engine, never by this core: non-temporal stores skip the read-for-ownership of every destination line (2 instead of 3
+// bytes of DRAM traffic per byte copied) and leave the caches to the source.  Falls back to memcpy without AVX2.
+__attribute__((target("avx2"))) static void copy_stream_avx2(uint8_t *d, const uint8_t *s, size_t n) {
+    while (n && ((uintptr_t)d & 31u)) { *d++ = *s++; n--; }
+    size_t v = n / 128;
+    for (; v; v--, d += 128, s += 128) {
+        __m256i a = _mm256_loadu_si256((const __m256i *)s), b = _mm256_loadu_si256((const __m256i *)(s + 32));
+        __m256i c = _mm256_loadu_si256((const __m256i *)(s + 64)), e = _mm256_loadu_si256((const __m256i *)(s + 96));
+        _mm256_stream_si256((__m256i *)d, a); _mm256_stream_si256((__m256i *)(d + 32), b);
+        _mm256_stream_si256((__m256i *)(d + 64), c); _mm256_stream_si256((__m256i *)(d + 96), e);
+    }
+    n &= 127;
+    if (n) memcpy(d, s, n);
+    _mm_sfence();
+}
+std::atomic<int> g_copy_nt{1};
+static void slice_copy(uint8_t *d, const uint8_t *s, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && g_copy_nt.load(std::memory_order_relaxed) && n >= 4096) copy_stream_avx2(d, s, n);
+    else memcpy(d, s, n);
+}
+struct CopyPool {            // a handful of host threads that copy slices in parallel
     std::mutex mu;
     std::condition_variable cv, cv_done;
     std::vector<std::thread> threads;
     uint8_t *dst = nullptr; const uint8_t *src = nullptr; size_t bytes = 0;
     uint32_t parts = 0, next_part = 0, done_parts = 0; uint64_t job = 0;
     bool stop = false;
+    uint32_t active = 0;     // workers a job is cut for (<= threads.size()): h2_test_set_copy_threads
+    size_t part_lo(uint32_t p) const { return p >= parts ? bytes : (bytes / parts * p) & ~(size_t)127; }   // 128-byte aligned cuts
     void start(unsigned n) {
+        active = n;
         for (unsigned i = 0; i < n; i++) threads.emplace_back([this] { run(); });
     }
     void run() {
@@ -50,10 +76,10 @@ struct CopyPool {            // a handful of host threads that memcpy slices in 
             const uint64_t my_job = job;
             while (next_part < parts && job == my_job) {
                 const uint32_t p = next_part++;
-                const size_t lo = bytes * p / parts, hi = bytes * (p + 1) / parts;
+                const size_t lo = part_lo(p), hi = part_lo(p + 1);
                 uint8_t *d = dst; const uint8_t *s = src;
                 lk.unlock();
-                memcpy(d + lo, s + lo, hi - lo);
+                slice_copy(d + lo, s + lo, hi - lo);
                 lk.lock();
                 if (++done_parts == parts) cv_done.notify_all();
             }
@@ -63,17 +89,17 @@ struct CopyPool {            // a handful of host threads that memcpy slices in 
     // one job at a time (callers serialise on job_mu); the calling thread takes slices too
     std::mutex job_mu;
     void copy(void *d, const void *s, size_t n) {
-        if (n < (1u << 20) || threads.empty()) { memcpy(d, s, n); return; }
+        if (n < (1u << 20) || threads.empty() || active == 0) { slice_copy((uint8_t *)d, (const uint8_t *)s, n); return; }
         std::lock_guard<std::mutex> jl(job_mu);
         std::unique_lock<std::mutex> lk(mu);
         dst = (uint8_t *)d; src = (const uint8_t *)s; bytes = n;
-        parts = (uint32_t)threads.size() + 1; next_part = 0; done_parts = 0; job++;
+        parts = (active < threads.size() ? active : (uint32_t)threads.size()) + 1; next_part = 0; done_parts = 0; job++;
         cv.notify_all();
         while (next_part < parts) {
             const uint32_t p = next_part++;
-            const size_t lo = bytes * p / parts, hi = bytes * (p + 1) / parts;
+            const size_t lo = part_lo(p), hi = part_lo(p + 1);
             lk.unlock();
-            memcpy(dst + lo, src + lo, hi - lo);
+            slice_copy(dst + lo, src + lo, hi - lo);
             lk.lock();
             ++done_parts;
         }
@@ -89,7 +115,9 @@ CopyPool *copy_pool() {
     static CopyPool *P = [] {
         CopyPool *p = new CopyPool();    // leaked on purpose: worker threads must not be joined from a static destructor
         unsigned hw = std::thread::hardware_concurrency();
-        p->start(hw >= 16 ? 7 : hw >= 4 ? 3 : 0);
+        p->start(hw >= 64 ? 31 : hw >= 16 ? 7 : hw >= 4 ? 3 : 0);
+        if (const char *e = getenv("H2_COPY_THREADS")) { long v = atol(e); if (v >= 0 && v <= 31) p->active = (uint32_t)v; }
+        else p->active = hw >= 64 ? 15 : p->active;
         return p;
     }();
     return P;
@@ -98,6 +126,14 @@ std::atomic<int> g_staging{1};
 }  // namespace
 void h2_set_staging(int on) { g_staging.store(on ? 1 : 0); }
 extern "C" int h2_test_set_staging(int on) { h2_set_staging(on); return 0; }
+// staging-copy tuning (bench sweep): worker threads a copy is cut for (the caller's thread takes a slice too), NT stores on/off
+extern "C" int h2_test_set_copy_threads(int n, int nt_stores) {
+    CopyPool *P = copy_pool();
+    std::lock_guard<std::mutex> jl(P->job_mu);
+    if (n >= 0) P->active = (uint32_t)n < P->threads.size() ? (uint32_t)n : (uint32_t)P->threads.size();
+    if (nt_stores >= 0) g_copy_nt.store(nt_stores ? 1 : 0);
+    return 0;
+}
 
 int StageRing::ensure() {
     if (slot_bytes) return 0;
@@ -222,7 +258,7 @@ static void ctx_destroy(Context &C) {
                      &C.items, &C.bucket_sum, &C.pkey, &C.pstart, &C.pend, &C.ppt, &C.ra_t, &C.ra_e,
                      &C.r0, &C.r1, &C.wsum, &C.scan_blocks, &C.result, &C.misc, &C.ntt_io, &C.ntt_out,
                      &C.ntt_work, &C.pow2, &C.ec_work, &C.ec_io, &C.ec_out, &C.fb_a, &C.fb_b, &C.po_lvl, &C.po_q, &C.po_pts, &C.po_ptrs, &C.ast_code, &C.ast_consts,
-                     &C.multi_parts};
+                     &C.multi_parts, &C.ba_lv[0], &C.ba_lv[1], &C.ba_lv[2]};
     for (DevBuf *b : all) b->release();
     for (auto *t : C.twiddles) { t->buf.release(); delete t; }
     C.twiddles.clear();
@@ -329,6 +365,19 @@ extern "C" int h2_test_set_accum_ways(uint32_t ways) {
     if (ways != 1 && ways != 2 && ways != 4) return fail("h2_test_set_accum_ways: 1, 2 or 4");
     g_ctx.accum_ways = ways;
     for (auto &ge : g_ctx.graphs) if (ge.exec) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; ge.seen = 0; }
+    return 0;
+}
+// test / tuning hook: batched-affine halving rounds ahead of the XYZZ accumulation of large one-shot MSMs (0 = classic
+// accumulation only, at most 3) and the pairs per thread that share one inversion (0 keeps the current value)
+extern "C" int h2_test_set_batched_affine(uint32_t rounds, uint32_t pairs_per_thread) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint32_t variant = rounds >> 8;     // bits 8..: kernel variant + 1 (tuning; 0 = the default variant)
+    rounds &= 0xffu;
+    if (rounds > H2_BA_MAX_ROUNDS) return fail("h2_test_set_batched_affine: at most 3 rounds");
+    for (int d = 0; d < H2_MAX_DEVICES; d++) {
+        g_ctxs[d].ba_rounds = rounds; g_ctxs[d].ba_variant = variant ? variant - 1 : 3;
+        if (pairs_per_thread) g_ctxs[d].ba_target = pairs_per_thread;
+    }
     return 0;
 }
 // test hook: EC-FFT butterfly form -- 1: quads of lanes, 0: one thread each, -1: by size (the default)

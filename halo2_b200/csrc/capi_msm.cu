@@ -155,6 +155,17 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         part_total = pk[j].part_total > part_total ? pk[j].part_total : part_total;
         t_max = pk[j].T > t_max ? pk[j].T : t_max;
     }
+    // batched-affine rounds ahead of the XYZZ chain (msm.cuh K4a) for the throughput-bound sizes: every chunk plans its own
+    uint64_t ba_space = 0;
+    if (!fixed && X.ba_rounds)
+        for (uint32_t j = 0; j < K; j++) {
+            if (pk[j].max_refs > H2_MSM_QUAD_ACCUM_REFS && pk[j].ref_space * 56 <= (48ull << 30)) msm_plan_ba(pk[j], X.ba_rounds, X.ba_target);
+            if (pk[j].ba) ba_space = pk[j].ref_space > ba_space ? pk[j].ref_space : ba_space;
+        }
+    if (K == 1) p.ba = pk[0].ba;
+    if (ba_space)
+        for (uint32_t r = 0; r < H2_BA_MAX_ROUNDS; r++)
+            if (X.ba_lv[r].ensure(K * ((ba_space >> (r + 1)) + 1) * sizeof(affine))) return 1;
     if (glv && (X.bases_phi.ensure(n * sizeof(affine)) || X.glv_parts.ensure(n * 32))) return 1;
     if (fixed && (uint64_t)p.W * stride >= (1ull << 31)) return fail("msm: window table too large for 31-bit references");
     if (p.G >= (1ull << 32) || n >= (1ull << 31)) return fail("msm: n * windows exceeds 2^32 references");
@@ -181,6 +192,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         M.size_hist = X.size_hist.as<uint32_t>() + j * small_words; M.size_cursor = M.size_hist + (pk[j].T + 2); M.flags = M.size_cursor + (pk[j].T + 2);
         M.items = X.items.as<uint2>() + j * max_items;
         M.bucket_sum = X.bucket_sum.as<xyzz>() + j * p.G;
+        for (uint32_t r = 0; r < H2_BA_MAX_ROUNDS; r++) M.ba[r] = ba_space ? X.ba_lv[r].as<affine>() + j * ((ba_space >> (r + 1)) + 1) : nullptr;
         M.pkey = X.pkey.as<uint32_t>() + j * part_total; M.pstart = X.pstart.as<uint32_t>() + j * part_total;
         M.pend = X.pend.as<uint32_t>() + j * part_total; M.ppt = X.ppt.as<xyzz>() + j * part_total;
         M.ra_t = X.ra_t.as<xyzz>(); M.ra_e = X.ra_e.as<xyzz>(); M.r0 = X.r0.as<xyzz>(); M.r1 = X.r1.as<xyzz>();
@@ -209,6 +221,9 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
         auto k_accum0m2 = msm_accum0_multi_kernel<P, PS, 2>;
         auto k_accum0m4 = msm_accum0_multi_kernel<P, PS, 4>;
+        auto k_ba = X.ba_variant == 1 ? msm_ba_round_kernel<P, PS, 4, 5> : X.ba_variant == 2 ? msm_ba_round_kernel<P, PS, 2, 4>
+                  : X.ba_variant == 3 ? msm_ba_round_kernel<P, PS, 2, 5> : msm_ba_round_kernel<P, PS, 4, 4>;
+        auto k_accum0p = msm_accum0_pts_kernel<P, PS>;
         auto k_accumN = msm_accumN_kernel<P, PS>;
         auto k_rest = msm_accum_rest_kernel<P, PS>;
         auto k_reduceA = msm_reduceA_kernel<P, PS>;
@@ -253,7 +268,14 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
                 else if (X.accum_ways == 2) LAUNCH(k_accum0m2, blocks_for(q.max_items * 8, 128), 128, 0, s, q, M);
                 else LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);
             }
-            else LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+            else {
+                // batched-affine halving rounds, then the chain over the last level; all of them return at once if the
+                // exact sort ran (flags[1]) -- then the classic kernel below does the work, otherwise IT returns at once
+                for (uint32_t r = 1; r <= q.ba; r++)
+                    LAUNCH(k_ba, blocks_for((q.max_items + q.ba_m[r - 1] - 1) / q.ba_m[r - 1], 128), 128, 0, s, q, M, r);
+                if (q.ba) LAUNCH(k_accum0p, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+                LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
+            }
             prof_end(s);
             if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
             if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);

@@ -116,10 +116,17 @@ struct Context {
                                              // B200 (profiles/r2e_*): 2^20 0.27-0.30 ms vs 0.215 ms, 2^24 4.77 vs 3.67 ms -- the pass is bound by the
                                              // integer pipes (fmaheavy 55-61 %, ALU 54 %, issue 51 %, top stall `wait`), not by its memory phases, and
                                              // the double-buffered tiles cost occupancy (4 CTAs/SM, 2 in the last pass): opt-in, default off
+    uint32_t ba_variant = 3;                 // kernel variant of the rounds (tuning): 0 / 1 = gather chunks of 4 pairs at 4 / 5 CTAs per SM, 2 / 3 = chunks of 2
+    uint32_t ba_rounds = 0, ba_target = 32;  // batched-affine halving rounds ahead of the XYZZ accumulation of large one-shot MSMs and the pairs per thread
+                                             // one inversion is shared by (h2_test_set_batched_affine).  OFF by default -- measured on B200 at 2^20
+                                             // (profiles/r2k_ba_sweep.txt): best setting (1 round, 32 pairs) 3.62 ms vs 3.61 ms without; 2 / 3 rounds
+                                             // 3.84 / 4.04 ms.  An affine addition is 6 multiplies instead of 10 but 2 520 instructions against 2 640
+                                             // (field add/sub, the inversion's share, call marshalling, local-memory products), and its dependent
+                                             // reference -> point gathers leave the kernel latency-bound at 14-20 warps per SM
     uint32_t ecfft_quad = 1;                 // EC-FFT butterfly form: 1 = by size (default), 0 = one thread each, 2 = quads (test hook)
     // MSM scratch
     DevBuf scal_in, bases_in, bases_phi, glv_parts, scal_canon, counts, cursor, refs, size_hist, items, bucket_sum, pkey, pstart, pend, ppt, ra_t, ra_e, r0, r1,
-        wsum, scan_blocks, result, misc;
+        wsum, scan_blocks, result, misc, ba_lv[3];
     // NTT scratch
     DevBuf ntt_io, ntt_out, ntt_work, pow2;
     // EC-FFT / batch-normalise scratch: XYZZ work array (128 B per point), staging for the host forms

@@ -149,7 +149,7 @@ template <class P> H2_HD jacobian xyzz_to_jacobian(const xyzz &p) {
 template <class P> H2_HD affine jacobian_to_affine(const jacobian &j) {
     affine r;
     if (fe_is_zero(j.z)) { r.x = fe_zero(); r.y = fe_zero(); return r; }
-    fe zi = fe_inv<P>(j.z);
+    fe zi = fe_inv_gcd<P>(j.z);
     fe zi2 = cs<P>(zi);
     r.x = cm<P>(j.x, zi2);
     r.y = cm<P>(j.y, cm<P>(zi2, zi));

@@ -290,7 +290,7 @@ template <class P> struct Normalize {
             pre[i] = acc;
             if (!fe_is_zero(p.z)) acc = fe_mul_call<P>(acc, p.z);
         }
-        acc = fe_inv<P>(acc);
+        acc = fe_inv_gcd<P>(acc);
         for (uint32_t i = m; i-- > 0;) {
             jacobian p = get(in_xyzz, in_jac, in_canonical, lo + i);
             affine r;

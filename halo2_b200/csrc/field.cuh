@@ -87,6 +87,10 @@ struct FpParams {   // Pallas base field / Vesta scalar field
         constexpr uint32_t v[8] = {0x0000000fu, 0x8c78ecb3u, 0x8b0de0e7u, 0xd7d30dbdu, 0xc3c95d18u, 0x7797a99bu, 0x7b9cb714u, 0x096d41afu};
         return v[i];
     }
+    static H2_HD uint32_t r3(int i) {    // R^3 mod m (fe_inv_gcd: the inverse of a Montgomery residue, back in Montgomery form)
+        constexpr uint32_t v[8] = {0x3a9e10f9u, 0xf185a599u, 0x6ac5b1d1u, 0xf6a68f3bu, 0x353fd42cu, 0xdf8d1014u, 0x2d2d9910u, 0x2ae30922u};
+        return v[i];
+    }
 };
 struct FqParams {   // Vesta base field / Pallas scalar field
     static constexpr int ID = 1;
@@ -97,6 +101,10 @@ struct FqParams {   // Vesta base field / Pallas scalar field
     }
     static H2_HD uint32_t r2(int i) {
         constexpr uint32_t v[8] = {0x0000000fu, 0xfc9678ffu, 0x891a16e3u, 0x67bb433du, 0x04ccf590u, 0x7fae2310u, 0x7ccfdaa9u, 0x096d41afu};
+        return v[i];
+    }
+    static H2_HD uint32_t r3(int i) {
+        constexpr uint32_t v[8] = {0x249dae4cu, 0x008b421cu, 0xdba41326u, 0xe13bda50u, 0x8e15cb63u, 0x88fececbu, 0x6e6792c8u, 0x07dd97a0u};
         return v[i];
     }
 };
@@ -415,6 +423,116 @@ template <class P> H2_HD fe fe_inv(const fe &a) {
         }
     }
     return acc;
+}
+
+// ------------------------------------------------------------------ inversion by divsteps (Bernstein-Yang "safegcd")
+// The Fermat ladder above is ~380 DEPENDENT multiplies: 0.1 ms for a lone thread (every batch_normalize of a handful of
+// commitments, every IPA round that returns affine points) and ~300 multiply-equivalents of issue slots when every lane
+// inverts (the shared inversion of a batch of affine additions).  This one runs 20 rounds of 30 division steps on the low
+// words of (f, g) -- 32-bit scalar work off the multiply pipe -- each followed by one 2x2 matrix update of the full-width
+// pairs (f, g) and (d, e), in 9 signed 30-bit limbs: ~11 k instructions, ~1.7 k of them wide multiplies (a Montgomery
+// multiply is 244 / 63), no data-dependent branch (uniform across a warp), ~10x shorter as a dependent chain.
+// 600 division steps cover any 256-bit odd modulus (the published bound for this variant is 590); g = 0 yields 0 like
+// fe_inv.  Moduli here are = 1 mod 2^30, so the "modulus^-1 mod 2^30" of the (d, e) update is 1.
+struct s30 { int32_t v[9]; };                    // sum v[i] 2^(30 i), limbs signed
+H2_HD s30 s30_from_fe(const fe &a) {
+    s30 r;
+    for (int i = 0; i < 9; i++) {
+        const int bit = 30 * i, j = bit >> 5, sh = bit & 31;
+        uint32_t w = a.v[j] >> sh;
+        if (sh > 2 && j + 1 < 8) w |= a.v[j + 1] << (32 - sh);
+        r.v[i] = (int32_t)(w & 0x3fffffffu);
+    }
+    return r;
+}
+H2_HD fe s30_to_fe(const s30 &a) {               // limbs in [0, 2^30), value < 2^256
+    fe r;
+    for (int j = 0; j < 8; j++) {
+        const int bit = 32 * j, i = bit / 30, sh = bit % 30;      // sh <= 14: two limbs cover a word
+        r.v[j] = ((uint32_t)a.v[i] >> sh) | ((uint32_t)a.v[i + 1] << (30 - sh));
+    }
+    return r;
+}
+template <class P> H2_HD s30 s30_modulus() {
+    fe m;
+    for (int i = 0; i < 8; i++) m.v[i] = mod_limb<P>(i);
+    return s30_from_fe(m);
+}
+// 30 division steps on the low words; returns the new zeta = -(delta + 1/2) and the transition matrix (u v; q r), entries
+// in [-2^30, 2^30], with  2^30 (f', g') = (u v; q r) (f, g)
+H2_HD int32_t divsteps30(int32_t zeta, uint32_t f, uint32_t g, int32_t (&t)[4]) {
+    uint32_t u = 1, v = 0, q = 0, r = 1;
+    for (int i = 0; i < 30; i++) {
+        uint32_t m1 = (uint32_t)(zeta >> 31), m2 = 0u - (g & 1u);
+        const uint32_t x = (f ^ m1) - m1, y = (u ^ m1) - m1, z = (v ^ m1) - m1;     // -(f, u, v) when zeta < 0
+        g += x & m2; q += y & m2; r += z & m2;
+        m1 &= m2;                                                                    // zeta < 0 and g odd: swap roles
+        zeta = (zeta ^ (int32_t)m1) - 1;
+        f += g & m1; u += q & m1; v += r & m1;
+        g >>= 1; u <<= 1; v <<= 1;
+    }
+    t[0] = (int32_t)u; t[1] = (int32_t)v; t[2] = (int32_t)q; t[3] = (int32_t)r;
+    return zeta;
+}
+// (f, g) <- (u v; q r) (f, g) / 2^30   (exact)
+H2_HD void s30_update_fg(s30 &f, s30 &g, const int32_t (&t)[4]) {
+    const int64_t u = t[0], v = t[1], q = t[2], r = t[3];
+    int64_t cf = u * f.v[0] + v * g.v[0], cg = q * f.v[0] + r * g.v[0];
+    cf >>= 30; cg >>= 30;
+    for (int i = 1; i < 9; i++) {
+        cf += u * f.v[i] + v * g.v[i];
+        cg += q * f.v[i] + r * g.v[i];
+        f.v[i - 1] = (int32_t)cf & 0x3fffffff; cf >>= 30;
+        g.v[i - 1] = (int32_t)cg & 0x3fffffff; cg >>= 30;
+    }
+    f.v[8] = (int32_t)cf; g.v[8] = (int32_t)cg;
+}
+// (d, e) <- (u v; q r) (d, e) / 2^30 mod m: a multiple of m is added first so that the division is exact
+template <class P> H2_HD void s30_update_de(s30 &d, s30 &e, const int32_t (&t)[4], const s30 &m) {
+    const int32_t u = t[0], v = t[1], q = t[2], r = t[3];
+    const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;
+    int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+    int64_t cd = (int64_t)u * d.v[0] + (int64_t)v * e.v[0], ce = (int64_t)q * d.v[0] + (int64_t)r * e.v[0];
+    md -= (int32_t)(((uint32_t)cd + (uint32_t)md) & 0x3fffffffu);      // m^-1 mod 2^30 = 1
+    me -= (int32_t)(((uint32_t)ce + (uint32_t)me) & 0x3fffffffu);
+    cd += (int64_t)m.v[0] * md; ce += (int64_t)m.v[0] * me;
+    cd >>= 30; ce >>= 30;
+    for (int i = 1; i < 9; i++) {
+        cd += (int64_t)u * d.v[i] + (int64_t)v * e.v[i];
+        ce += (int64_t)q * d.v[i] + (int64_t)r * e.v[i];
+        if (i < 5 || i == 8) { cd += (int64_t)m.v[i] * md; ce += (int64_t)m.v[i] * me; }   // limbs 5..7 of both moduli are 0
+        d.v[i - 1] = (int32_t)cd & 0x3fffffff; cd >>= 30;
+        e.v[i - 1] = (int32_t)ce & 0x3fffffff; ce >>= 30;
+    }
+    d.v[8] = (int32_t)cd; e.v[8] = (int32_t)ce;
+}
+// a^-1 for a Montgomery residue a (0 -> 0), result in Montgomery form
+template <class P> H2_HD fe fe_inv_gcd(const fe &a) {
+    const s30 m = s30_modulus<P>();
+    s30 d, e, f = m, g = s30_from_fe(a);
+    for (int i = 0; i < 9; i++) { d.v[i] = 0; e.v[i] = 0; }
+    e.v[0] = 1;
+    int32_t zeta = -1;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int it = 0; it < 20; it++) {
+        int32_t t[4];
+        zeta = divsteps30(zeta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+        s30_update_de<P>(d, e, t, m);
+        s30_update_fg(f, g, t);
+    }
+    // f = +-1 and d = +- a^-1 in (-2m, m): add m if negative, negate if f < 0, add m again if still negative
+    const int32_t M30 = 0x3fffffff;
+    int32_t add = d.v[8] >> 31, neg = f.v[8] >> 31;
+    for (int i = 0; i < 9; i++) d.v[i] = ((d.v[i] + (m.v[i] & add)) ^ neg) - neg;
+    for (int i = 0; i < 8; i++) { d.v[i + 1] += d.v[i] >> 30; d.v[i] &= M30; }
+    add = d.v[8] >> 31;
+    for (int i = 0; i < 9; i++) d.v[i] += m.v[i] & add;
+    for (int i = 0; i < 8; i++) { d.v[i + 1] += d.v[i] >> 30; d.v[i] &= M30; }
+    fe r3;
+    for (int i = 0; i < 8; i++) r3.v[i] = P::r3(i);
+    return fe_mul<P>(s30_to_fe(d), r3);          // (a R)^-1 R^3 / R = a^-1 R
 }
 
 // 128-bit global/shared memory access helpers

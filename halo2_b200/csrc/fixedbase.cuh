@@ -65,7 +65,7 @@ template <class P, class PS> struct FixedBase {
                 zz[j] = R.zz; zzz[j] = R.zzz; pre[j] = run;
                 run = fe_mul_call<P>(run, fe_mul_call<P>(R.zz, R.zzz));
             }
-            fe inv = fe_inv<P>(run);
+            fe inv = fe_inv_gcd<P>(run);
             for (uint32_t j = H2_FB_NORM; j-- > 0;) {
                 fe id = fe_mul_call<P>(inv, pre[j]);                    // 1 / (zz zzz)
                 inv = fe_mul_call<P>(inv, fe_mul_call<P>(zz[j], zzz[j]));

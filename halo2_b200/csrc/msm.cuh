@@ -63,6 +63,8 @@ struct MsmPlan {
     uint64_t G;          // total buckets = Wb * B
     uint64_t max_refs;   // n * W (x 2 with the GLV split)
     uint32_t T;          // references per work item (larger buckets are split)
+    uint32_t ba;         // batched-affine rounds before the XYZZ chain (0: none), see Msm::ba_round_body
+    uint32_t ba_m[4];    // work items per thread in round r = 1 .. ba (index r - 1)
     uint64_t max_items;  // upper bound of work items = G + max_refs / T
     // partial-merge levels: level 1 consumes the slots written by split buckets
     uint32_t acc_levels;                       // level 0 = the bucket items
@@ -99,6 +101,7 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
                           uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1, uint32_t force_cap = 0) {
     p.n = n; p.c = c; p.chunks = 1;
+    p.ba = 0; p.ba_m[0] = p.ba_m[1] = p.ba_m[2] = p.ba_m[3] = 1;
     p.glv = fixed ? 0u : glv;
     // GLV sub-scalars are < 2^127 (glv.cuh): with W c >= 128 the top window's raw digit is < 2^(c-1), so it
     // absorbs the signed-digit carry without opening another window
@@ -181,6 +184,28 @@ inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t =
     p.r1_rows = 2 + p.bits0 + p.bits1;
 }
 
+// Batched-affine rounds (Msm::ba_round_body) for a planned one-shot MSM: `rounds` halvings of every work item's list of
+// points, `target` pairs per thread (the batch one inversion is shared by).  Needs the binned layout with 8-aligned bins
+// and work items (level r lives at index >> r), so forced odd capacities / item sizes (tests) switch it off.
+#define H2_BA_MAX_ROUNDS 3
+inline void msm_plan_ba(MsmPlan &p, uint32_t rounds, uint32_t target) {
+    p.ba = 0;
+    if (p.fixed || p.cap == 0 || (p.cap & 7u) || (p.cap_top & 7u) || (p.T & 7u) || rounds == 0) return;
+    if (rounds > H2_BA_MAX_ROUNDS) rounds = H2_BA_MAX_ROUNDS;
+    uint64_t mean = p.max_refs / (p.G ? p.G : 1);       // references per bucket
+    if (mean > p.T) mean = p.T;
+    if (mean < 4) return;                                // nothing to pair up
+    p.ba = rounds;
+    for (uint32_t r = 1; r <= rounds; r++) {
+        // `target` pairs per thread in round 1; later rounds keep the thread count (half the pairs per inversion each time)
+        // unless bit 16 of target asks for `target` pairs in every round (fewer threads in the later rounds)
+        uint64_t pairs = mean >> ((target >> 16) & 1u ? r : 1u);
+        if (pairs == 0) pairs = 1;
+        uint64_t m = ((target & 0xffffu) + pairs / 2) / pairs;
+        p.ba_m[r - 1] = (uint32_t)(m < 1 ? 1 : m > 64 ? 64 : m);
+    }
+}
+
 struct MsmBuffers {
     // inputs
     const fe *scalars;        // n, canonical or Montgomery (see scalars_mont)
@@ -199,6 +224,7 @@ struct MsmBuffers {
     uint32_t *flags;          // [0] = some bucket exceeded T references (partials exist)
     uint2 *items;             // max_items  (bucket id, first reference), sorted by size descending
     xyzz *bucket_sum;         // G
+    affine *ba[H2_BA_MAX_ROUNDS];   // batched-affine levels: ba[r - 1] holds (ref_space >> r) + 1 points, item lists at (start >> r)
     uint32_t *pkey, *pstart, *pend;   // part_total
     xyzz *ppt;                // part_total
     xyzz *ra_t, *ra_e;        // W * m1            level A: chunk totals / weighted sums
@@ -352,8 +378,171 @@ template <class P, class PS> struct Msm {
         }
     };
 
+    // ---- K4a: batched-affine rounds.  An affine addition costs 3 multiplies (lambda = dy / dx, x3 = lambda^2 - x1 - x2,
+    // y3 = lambda (x1 - x3) - y1) plus ONE inversion -- which Montgomery's trick shares among a whole batch of independent
+    // additions at 3 more multiplies each: 6 per addition instead of the 10 of a mixed XYZZ addition.  The additions of a
+    // bucket's chain are not independent, but the pairs of a halving round are: round r turns every work item's list of
+    // len points into ceil(len / 2) sums (P0 + P1, P2 + P3, ..., an odd last point moves up unchanged).  Level 0 is the
+    // item's references (gathered bases, negated / phi-mapped as the reference says), level r is stored at index >> r of
+    // M.ba[r - 1] (bins and items are 8-aligned).  A thread takes ba_m[r - 1] consecutive items of the size-sorted item
+    // list -- ~equal work per lane -- and runs its pairs in sub-batches of SUB: forward pass (denominators, running
+    // product), one inversion by division steps (fe_inv_gcd, ~45 multiply-equivalents), backward pass (the sums).
+    // Degenerate pairs keep the batch alive with a substitute denominator: an identity operand or P + (-P) uses 1, P + P
+    // uses 2 y (the tangent slope 3 x^2 / 2 y).  After p.ba rounds accum0_pts_body runs the short XYZZ chain that is left.
+    struct BaItem { uint32_t in_base, out_base, len, np; };      // len points at level r - 1, np = len / 2 pairs
+    static H2_HD BaItem ba_item(const MsmPlan &p, const MsmBuffers &M, uint32_t r, uint64_t t) {
+        const uint2 it = M.items[t];
+        const uint32_t hi = bucket_hi(p, M, it.x), end = it.y + p.T < hi ? it.y + p.T : hi;
+        BaItem b;
+        b.len = (end - it.y + (1u << (r - 1)) - 1u) >> (r - 1);
+        b.np = b.len >> 1; b.in_base = it.y >> (r - 1); b.out_base = it.y >> r;
+        return b;
+    }
+    // Operand `key` of round r: a reference (r == 1: point index | phi << 30 | negate << 31) or a slot of level r - 1.
+    static H2_HD const affine *ba_addr(const MsmPlan &p, const MsmBuffers &M, uint32_t r, uint32_t key) {
+        if (r > 1) return M.ba[r - 2] + key;
+        if (p.glv) return ((key >> 30) & 1u ? M.bases_phi : M.bases) + (key & 0x3fffffffu);
+        return M.bases + (key & 0x7fffffffu);
+    }
+    static H2_HD affine ba_load(const MsmPlan &p, const MsmBuffers &M, uint32_t r, uint32_t key) {
+        affine b = ld_affine(ba_addr(p, M, r, key));
+        if (r == 1 && (key >> 31)) b.y = fe_neg<P>(b.y);
+        return b;
+    }
+    static H2_HD uint32_t ba_key(const MsmBuffers &M, uint32_t r, uint32_t idx) { return r == 1 ? M.refs[idx] : idx; }
+    static H2_HD void ba_prefetch(const void *q) {
+#ifdef __CUDA_ARCH__
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+#else
+        (void)q;
+#endif
+    }
+    // kind of the addition A + B and its denominator: 0 generic (x2 - x1), 1 an operand is the identity (1),
+    // 2 doubling (2 y1; y != 0 on a prime-order curve), 3 opposite points (1)
+    static H2_HD uint32_t ba_kind(const affine &A, const affine &B, fe &d) {
+        d = fe_sub<P>(B.x, A.x);
+        if (!fe_is_zero(d) && !fe_is_zero(A.x) && !fe_is_zero(B.x)) return 0;
+        if (affine_is_identity(A) || affine_is_identity(B)) { d = fe_one<P>(); return 1; }
+        if (!fe_is_zero(d)) return 0;
+        if (fe_eq(A.y, B.y)) { d = fe_dbl<P>(A.y); return 2; }
+        d = fe_one<P>();
+        return 3;
+    }
+    // One batch = the pairs [k_lo, k_hi) of item ta (single == true) or all pairs of items [ta, tb): forward pass
+    // (denominators, running products pre[]), one inversion, backward pass (the sums).  Both passes walk the items in
+    // chunks of U pairs: the chunk's 2 U operand keys are loaded first and their points prefetched, so 2 U gathers are in
+    // flight per lane instead of one dependent reference -> point chain per pair (the kernel was bound by exactly that
+    // latency: ncu r2i, long-scoreboard stalls at every use of a gathered value, 14 warps per SM).
+    template <int U> static H2_HD void ba_batch(const MsmPlan &p, const MsmBuffers &M, uint32_t r, uint64_t ta, uint64_t tb, bool single,
+                                                 uint32_t k_lo, uint32_t k_hi, fe *pre) {
+        affine *out = M.ba[r - 1];
+        fe acc = fe_one<P>();
+        uint32_t c = 0;
+        for (uint64_t tt = ta; tt < tb; tt++) {
+            const BaItem it = ba_item(p, M, r, tt);
+            const uint32_t ka = single ? k_lo : 0u, kb = single ? k_hi : it.np;
+            for (uint32_t k = ka; k < kb; k += U) {
+                uint32_t key[2 * U];
+#pragma unroll
+                for (int u = 0; u < 2 * U; u++) key[u] = 2 * k + u < 2 * kb ? ba_key(M, r, it.in_base + 2 * k + u) : 0u;
+#pragma unroll
+                for (int u = 0; u < 2 * U; u++) if (2 * k + u < 2 * kb) ba_prefetch(ba_addr(p, M, r, key[u]));
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (k + u >= kb) break;
+                    const fe x1 = fe_load(&ba_addr(p, M, r, key[2 * u])->x), x2 = fe_load(&ba_addr(p, M, r, key[2 * u + 1])->x);
+                    fe d = fe_sub<P>(x2, x1);
+                    // the x coordinates alone decide the generic case; anything else looks at the whole points
+                    if (fe_is_zero(d) || fe_is_zero(x1) || fe_is_zero(x2)) { affine A = ba_load(p, M, r, key[2 * u]), B = ba_load(p, M, r, key[2 * u + 1]); ba_kind(A, B, d); }
+                    pre[c++] = acc;
+                    acc = fe_mul_call<P>(acc, d);
+                }
+            }
+        }
+        if (c == 0) return;
+        fe inv = fe_inv_gcd<P>(acc);
+        // backward: inv = 1 / (d_0 ... d_c) on entry of step c
+        for (uint64_t tt = tb; tt-- > ta;) {
+            const BaItem it = ba_item(p, M, r, tt);
+            const uint32_t ka = single ? k_lo : 0u, kb = single ? k_hi : it.np;
+            if (kb <= ka) continue;
+            for (uint32_t k = ka + ((kb - ka - 1) / U) * U;; k -= U) {
+                uint32_t key[2 * U];
+#pragma unroll
+                for (int u = 0; u < 2 * U; u++) key[u] = 2 * k + u < 2 * kb ? ba_key(M, r, it.in_base + 2 * k + u) : 0u;
+#pragma unroll
+                for (int u = 0; u < 2 * U; u++) if (2 * k + u < 2 * kb) ba_prefetch(ba_addr(p, M, r, key[u]));
+#pragma unroll
+                for (int u = U - 1; u >= 0; u--) {
+                    if (k + u >= kb) continue;
+                    const affine A = ba_load(p, M, r, key[2 * u]), B = ba_load(p, M, r, key[2 * u + 1]);
+                    fe d;
+                    const uint32_t kind = ba_kind(A, B, d);
+                    const fe dinv = fe_mul_call<P>(inv, pre[--c]);
+                    inv = fe_mul_call<P>(inv, d);
+                    affine S;
+                    if (kind == 0 || kind == 2) {
+                        fe num;
+                        if (kind == 0) num = fe_sub<P>(B.y, A.y);
+                        else { fe xx = fe_sqr_call<P>(A.x); num = fe_add<P>(fe_dbl<P>(xx), xx); }
+                        const fe lam = fe_mul_call<P>(num, dinv);
+                        S.x = fe_sub<P>(fe_sub<P>(fe_sqr_call<P>(lam), A.x), B.x);
+                        S.y = fe_sub<P>(fe_mul_call<P>(lam, fe_sub<P>(A.x, S.x)), A.y);
+                    } else if (kind == 1) {
+                        S = affine_is_identity(A) ? B : A;
+                    } else {
+                        S.x = fe_zero(); S.y = fe_zero();
+                    }
+                    st_affine(out + it.out_base + k + u, S);
+                }
+                if (k == ka) break;
+            }
+        }
+    }
+    // PRE: pairs per inversion at most (the local array of running products); U: pairs per gather chunk (PRE % U == 0)
+    template <int PRE = 128, int U = 4> static H2_HD void ba_round_body(const MsmPlan &p, const MsmBuffers &M, uint32_t r, uint64_t j) {
+        if (M.flags[1]) return;                      // exact-sort layout: the classic kernel accumulates
+        const uint64_t nitems = M.size_hist[p.T + 1];
+        const uint32_t m = p.ba_m[r - 1];
+        uint64_t t = j * m;
+        const uint64_t t1 = t + m < nitems ? t + m : nitems;
+        if (t >= nitems) return;
+        affine *out = M.ba[r - 1];
+        fe pre[PRE];
+        while (t < t1) {
+            // the next batch: consecutive items while their pairs fit PRE; an item with more pairs than that goes alone, in slices
+            uint64_t tg = t;
+            uint32_t total = 0;
+            bool big = false;
+            while (tg < t1) {
+                const BaItem b = ba_item(p, M, r, tg);
+                if (b.len & 1u) st_affine(out + b.out_base + b.np, ba_load(p, M, r, ba_key(M, r, b.in_base + 2 * b.np)));   // odd last point moves up
+                if (b.np > (uint32_t)PRE) { big = tg == t; if (big) { total = b.np; tg++; } break; }
+                if (total + b.np > (uint32_t)PRE) break;
+                total += b.np; tg++;
+            }
+            if (big) for (uint32_t k0 = 0; k0 < total; k0 += PRE) ba_batch<U>(p, M, r, t, t + 1, true, k0, k0 + PRE < total ? k0 + PRE : total, pre);
+            else ba_batch<U>(p, M, r, t, tg, false, 0, 0, pre);
+            t = tg;
+        }
+    }
+    // ... and the XYZZ chain over what the rounds left of item t (level p.ba), flushed like accum0_body does
+    static H2_HD void accum0_pts_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
+        if (M.flags[1] || t >= M.size_hist[p.T + 1]) return;
+        const uint2 it = M.items[t];
+        const uint32_t g = it.x, start = it.y, lo = bucket_lo(p, M, g), hi = bucket_hi(p, M, g);
+        const uint32_t end = start + p.T < hi ? start + p.T : hi;
+        const uint32_t len = (end - start + (1u << p.ba) - 1u) >> p.ba;
+        const affine *src = M.ba[p.ba - 1] + (start >> p.ba);
+        xyzz acc = xyzz_identity();
+        for (uint32_t i = 0; i < len; i++) xyzz_add_mixed<P>(acc, ld_affine(src + i));
+        Flusher F; F.M = &M; F.p = &p;
+        F.flush(g, start, end, acc, p.part_offset[1] + item_slot(p, start, start == lo));
+    }
+
     // level 0: one work item
     template <class MADD = SerialAdd> static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
+        if (p.ba && !M.flags[1]) return;             // the batched-affine rounds + accum0_pts_body did the work
         if (t >= M.size_hist[p.T + 1]) return;
         uint2 it = M.items[t];
         const uint32_t g = it.x, start = it.y, lo = bucket_lo(p, M, g), hi = bucket_hi(p, M, g);
@@ -477,7 +666,7 @@ template <class P, class PS> struct Msm {
             zs[w] = Z; pre[w] = run;
             run = fe_mul<P>(run, Z);
         }
-        fe inv = fe_inv<P>(run);          // Z != 0: a prime-order curve has no 2-torsion
+        fe inv = fe_inv_gcd<P>(run);      // Z != 0: a prime-order curve has no 2-torsion
         for (uint32_t w = W - 1; w >= 1; w--) {
             fe zi = fe_mul<P>(inv, pre[w]);
             inv = fe_mul<P>(inv, zs[w]);
@@ -646,6 +835,13 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_table_ke
 template <class P, class PS> __global__ void __launch_bounds__(128, 5) msm_accum0_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Msm<P, PS>::accum0_body(p, M, t);
+}
+// batched-affine round r (Msm::ba_round_body) and the XYZZ chain over its last level
+template <class P, class PS, int U, int MINB> __global__ void __launch_bounds__(128, MINB) msm_ba_round_kernel(const MsmPlan p, const MsmBuffers M, uint32_t r) {
+    Msm<P, PS>::template ba_round_body<128, U>(p, M, r, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+template <class P, class PS> __global__ void __launch_bounds__(128, 5) msm_accum0_pts_kernel(const MsmPlan p, const MsmBuffers M) {
+    Msm<P, PS>::accum0_pts_body(p, M, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 // small problems: one QUAD per work item -- the kernel lasts as long as the longest bucket's chain of additions, and a
 // quad runs that chain 2.5x faster (4 multiply latencies per mixed addition instead of 10)

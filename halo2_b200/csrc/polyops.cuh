@@ -83,7 +83,7 @@ template <class P> struct GrandProduct {
             pre[i] = acc;
             if (!fe_is_zero(v[i])) acc = fe_mul<P>(acc, v[i]);
         }
-        acc = fe_inv<P>(acc);
+        acc = fe_inv_gcd<P>(acc);
         for (uint32_t i = m; i-- > 0;) {
             if (fe_is_zero(v[i])) continue;
             fe_store(a + lo + i, fe_mul<P>(acc, pre[i]));

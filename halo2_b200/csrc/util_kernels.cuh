@@ -31,7 +31,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 template <class P> __device__ affine xyzz_to_affine_dev(const xyzz &p) {
     affine r;
     if (xyzz_is_identity(p)) { r.x = fe_zero(); r.y = fe_zero(); return r; }
-    fe t = fe_inv<P>(fe_mul<P>(p.zz, p.zzz));
+    fe t = fe_inv_gcd<P>(fe_mul<P>(p.zz, p.zzz));
     r.x = fe_mul<P>(p.x, fe_mul<P>(t, p.zzz));   // X / ZZ
     r.y = fe_mul<P>(p.y, fe_mul<P>(t, p.zz));    // Y / ZZZ
     return r;
@@ -59,6 +59,7 @@ template <class P> __global__ void test_field_kernel(const fe *a, const fe *b, f
     case 1: r = fe_sub<P>(x, y); break;
     case 2: r = fe_mul<P>(x, y); break;
     case 3: r = fe_inv<P>(x); break;
+    case 5: r = fe_inv_gcd<P>(x); break;
     default: r = fe_sqr<P>(x); break;
     }
     fe_store(out + i, fe_from_mont<P>(r));

@@ -284,6 +284,10 @@ int h2_test_set_chunk_threshold(uint32_t log2_n);
  * so that the link runs near its pinned rate and uploads still overlap compute; pinned / registered memory is used in
  * place.  0 switches the ring off (plain cudaMemcpyAsync): bench.py times both. */
 int h2_test_set_staging(int on);
+/* Staging-copy tuning: `threads` worker threads share every ring-slot copy with the calling thread (-1 keeps the current
+ * value; default 15 on hosts with >= 64 hardware threads, else 7 / 3; env H2_COPY_THREADS overrides); nt_stores: 1 = AVX2
+ * non-temporal stores into the pinned slot (default), 0 = memcpy, -1 keeps. */
+int h2_test_set_copy_threads(int threads, int nt_stores);
 /* 1: NTT passes run as a persistent kernel whose tile traffic is on the bulk-copy (TMA) engine (cp.async.bulk + mbarrier,
  * double buffered) wherever the pass geometry allows; 0 (default -- measured faster on B200): the classic
  * load / compute / store kernel.  bench.py times both. */
@@ -293,10 +297,15 @@ int h2_test_set_ntt_tma(int on);
 int h2_test_set_graphs(int on);
 /* EC-FFT butterfly form: 1 = quads of lanes, 0 = one thread each, -1 = chosen by size (the default). */
 int h2_test_set_ecfft_quad(int on);
+/* Opt-in: large one-shot MSMs add their buckets' points pairwise in AFFINE coordinates first -- `rounds` halving rounds (0 = off,
+ * the default; at most 3), one shared inversion per `pairs_per_thread` additions (0 keeps the value) -- and finish with the
+ * XYZZ chain.  6 multiplies per addition instead of 10, but measured no faster on B200. */
+int h2_test_set_batched_affine(uint32_t rounds, uint32_t pairs_per_thread);
 /* Quads of lanes per work item in the accumulation of small MSMs (1, 2 or 4; default 1). */
 int h2_test_set_accum_ways(uint32_t ways);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
- * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 square(a). */
+ * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a) by the Fermat ladder,
+ * 4 square(a), 5 inverse(a) by division steps (fe_inv_gcd, what the kernels use). */
 int h2_test_field_op(int field, int op, const void *a, const void *b, size_t n, void *out);
 /* out[i] = affine(a[i] + b[i]) (op 0), affine(2 a[i]) (op 1), affine(k[i] * a[i]) with b = 32-byte
  * scalars padded to 64 B (op 2); canonical affine, host buffers. */

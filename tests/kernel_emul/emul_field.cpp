@@ -17,6 +17,7 @@ template <class P> static void field_op(int op, const uint8_t *a, const uint8_t 
     case 4: r = fe_sqr<P>(x); break;
     case 5: r = fe_neg<P>(x); break;
     case 6: r = fe_dbl<P>(x); break;
+    case 7: r = fe_inv_gcd<P>(x); break;
     default: r = fe_zero();
     }
     r = fe_from_mont<P>(r);

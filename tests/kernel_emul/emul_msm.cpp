@@ -7,6 +7,10 @@ using namespace h2;
 
 static uint32_t g_force_cap = 0;      // 0 auto, H2_MSM_NO_BINS exact sort only, else the bin capacity (tests force overflows)
 extern "C" void emu_msm_set_cap(uint32_t cap) { g_force_cap = cap; }
+static uint32_t g_ba_rounds = 0, g_ba_target = 64;   // batched-affine rounds before the XYZZ chain (0: classic accumulation)
+extern "C" void emu_msm_set_ba(uint32_t rounds, uint32_t target) { g_ba_rounds = rounds; g_ba_target = target ? target : 64; }
+static uint32_t g_last_ba = 0;
+extern "C" uint32_t emu_msm_last_ba(void) { return g_last_ba; }
 template <class P, class PS>
 static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint32_t c, int scalars_mont,
                    uint32_t force_t, uint32_t force_kn, int fixed, int glv, uint8_t *out_xyz, uint32_t sets = 1) {
@@ -17,6 +21,8 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     if (fixed && c < 4) c = 4;      // table windows: W = ceil(256 / c) <= 64
     msm_make_plan(p, n, c, force_t, force_kn, fixed ? 1u : 0u, n + 3, glv ? 1u : 0u, sets, g_force_cap);
     if (p.acc_levels > H2_MSM_MAX_LEVELS) return -2;
+    msm_plan_ba(p, g_ba_rounds, g_ba_target);
+    g_last_ba = p.ba;
     std::vector<fe> sc(ns ? ns : 1), sc_canon(ns ? ns : 1);
     std::vector<affine> bs(n ? n : 1);
     for (size_t i = 0; i < ns; i++) {
@@ -53,6 +59,12 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
     M.bucket_sum = bucket_sum.data(); M.pkey = pkey.data(); M.pstart = pstart.data(); M.pend = pend.data();
     M.ppt = ppt.data(); M.ra_t = ra_t.data(); M.ra_e = ra_e.data(); M.r0 = r0.data(); M.r1 = r1.data();
     M.wsum = wsum.data(); M.result = result.data();
+    std::vector<affine> ba_lv[H2_BA_MAX_ROUNDS];
+    for (uint32_t r = 0; r < H2_BA_MAX_ROUNDS; r++) {
+        affine poison; for (int i = 0; i < 8; i++) { poison.x.v[i] = 0xdeadbeefu; poison.y.v[i] = 0xdeadbeefu; }
+        ba_lv[r].assign(p.ba ? (p.ref_space >> (r + 1)) + 1 : 1, poison);
+        M.ba[r] = ba_lv[r].data();
+    }
     typedef Msm<P, PS> K;
     // single-pass binned sort (reverse order to mimic the arbitrary order atomics give); a full bin -> flags[1]
     if (p.cap == 0) flags[1] = 1;
@@ -87,6 +99,10 @@ static int run_msm(const uint8_t *scalars, const uint8_t *bases, size_t n, uint3
         if (rem) items[size_cursor[rem]++] = make_uint2((uint32_t)g, K::bucket_lo(p, M, g) + nfull * p.T);
     }
     if (size_hist[p.T + 1] > p.max_items) return -4;
+    // K4a: batched-affine rounds + the chain over the last level (no-ops when the exact sort ran)
+    for (uint32_t r = 1; r <= p.ba; r++)
+        for (uint64_t j = 0; j < (p.max_items + p.ba_m[r - 1] - 1) / p.ba_m[r - 1]; j++) K::template ba_round_body<8, 4>(p, M, r, j);
+    if (p.ba) for (uint64_t t = 0; t < p.max_items; t++) K::accum0_pts_body(p, M, t);
     // K4
     for (uint64_t t = 0; t < p.max_items; t++) K::accum0_body(p, M, t);
     for (uint32_t lv = 1; lv < p.acc_levels; lv++)

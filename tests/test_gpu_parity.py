@@ -81,12 +81,15 @@ def test_device_field_ops(eng, field):
     assert _field_op(field, 4, xs) == [a * a % m for a in xs]
     nz = [x for x in xs if x][:300]
     assert _field_op(field, 3, nz) == [pow(a, m - 2, m) for a in nz]
+    # the divsteps inversion the kernels use (fe_inv_gcd): all samples, 0 -> 0, and the structured Montgomery residues below
+    assert _field_op(field, 5, xs) == [pow(a, m - 2, m) if a else 0 for a in xs]
     # structured MONTGOMERY operands (all-ones / zero / single-bit limbs): the carry edges of the dedicated squaring
     raws = _structured_limbs(m)
     rinv = pow(1 << 256, -1, m)
     zs = [x * rinv % m for x in raws]              # to_mont(z) == x
     assert _field_op(field, 4, zs) == [a * a % m for a in zs]
     assert _field_op(field, 2, zs, zs[5:] + zs[:5]) == [a * b % m for a, b in zip(zs, zs[5:] + zs[:5])]
+    assert _field_op(field, 5, zs) == [pow(a, m - 2, m) if a else 0 for a in zs]
 
 
 @pytest.mark.parametrize("field", ["fp", "fq"])

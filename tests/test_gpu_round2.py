@@ -194,3 +194,40 @@ def test_ntt_tma_pass_kernel(eng, field):
             assert (dom.extended_to_coeff(ext) == back).all()
     finally:
         L.check(lib.h2_test_set_ntt_tma(0))
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_batched_affine_accumulation(eng, curve):
+    """Large one-shot MSMs pair up their buckets' points in affine coordinates first (msm.cuh K4a: halving rounds with a
+    shared inversion, then the XYZZ chain).  Every round count and batch size gives the oracle's point -- on random inputs
+    and on inputs whose buckets are full of P + P, P + (-P) and identity operands (repeated / negated / missing bases under
+    repeated scalars), where the batch runs on substitute denominators."""
+    from halo2_b200 import lib as L
+    lib = L.init()
+    c = pasta.CURVES[curve]
+    n = (1 << 17) + 5                          # 2 x 8 x n > 2^20 references: the throughput path
+    kb = cref.gen_scalars(c.scalar, SEED + 91, n)
+    pb = cref.gen_points(curve, SEED + 92, n)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    # degenerate variant: every (scalar, base) pair appears twice -- the copies meet in the same buckets (a few thousand of
+    # them side by side: P + P) -- a third of the copies negated (P + (-P)), every 50th base the identity.  Two copies keep
+    # the bins of the single-pass sort from overflowing, so the batched rounds really run (checked through the sort flag).
+    kd, pd = kb.copy(), pb.copy()
+    half = n // 2
+    kd[half:2 * half], pd[half:2 * half] = kb[:half], pb[:half]
+    negm = np.zeros(n, dtype=bool)
+    negm[half:2 * half] = (np.arange(half) % 3) == 2
+    ys = cref.bytes_to_ints(np.ascontiguousarray(pd[negm, 32:]))
+    pd[negm, 32:] = cref.ints_to_bytes([(c.p - y) % c.p for y in ys])
+    pd[(np.arange(n) % 50) == 7] = 0
+    want_d = cref.bytes_to_affine(cref.best_multiexp(curve, kd, pd))
+    try:
+        for rounds, target in ((3, 64), (0, 0), (1, 64), (2, 8), (3, 200), (3, 1)):
+            L.check(lib.h2_test_set_batched_affine(rounds, target))
+            assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want, (rounds, target)
+            assert _affine(curve, eng.best_multiexp(kd, pd, curve)) == want_d, ("degenerate", rounds, target)
+            fl = ctypes.c_uint32(0)
+            L.check(lib.h2_test_last_msm_flags(ctypes.byref(fl)))
+            assert fl.value & 2 == 0, "the exact sort ran: the batched-affine rounds were skipped"
+    finally:
+        L.check(lib.h2_test_set_batched_affine(0, 32))

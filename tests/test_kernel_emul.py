@@ -40,6 +40,9 @@ def test_emul_field(emu, field):
     for a in xs[:10] + xs[-6:]:
         if a:
             assert _fop(emu, field, 3, a) == pow(a, m - 2, m)
+    # the divsteps inversion (fe_inv_gcd): every sample, the structured values, small and near-modulus inputs; 0 -> 0
+    for a in xs + [3, 5, 1 << 30, (1 << 30) - 1, 1 << 60, m - 3, (m + 1) // 2, pow(2, 256, m), pow(2, 512, m), (1 << 253) + 12345]:
+        assert _fop(emu, field, 7, a) == (pow(a, m - 2, m) if a else 0), hex(a)
 
 
 def _cop(emu, curve, op, a, b):
@@ -293,6 +296,59 @@ def test_emul_field_structured_limbs(emu, field):
         b = raws[(i * 7 + 3) % len(raws)] * rinv % m
         assert _fop(emu, field, 4, a) == a * a % m, hex(x)
         assert _fop(emu, field, 2, a, b) == a * b % m, hex(x)
+
+
+@pytest.mark.parametrize("curve", ["pallas", "vesta"])
+def test_emul_msm_batched_affine(emu, curve):
+    """Batched-affine rounds before the XYZZ chain (msm.cuh ba_round_body / accum0_pts_body): 1-3 halving rounds, batches of
+    every size (items per thread from the target, sub-batches of 8 in this build), odd list lengths, split buckets (T = 8, 16),
+    and every degenerate pair -- P + P, P + (-P), identity operands, all-equal scalars -- give the oracle's point."""
+    c = pasta.CURVES[curve]
+    g = pasta.generator(c)
+
+    def run(kb, pb, cb, k0, glv, rounds, target, expect_ba=True):
+        emu.emu_msm_set_ba(rounds, target)
+        try:
+            got = _msm(emu, curve, kb, pb, cb, 0, k0, 4 if k0 else 0, glv=glv)
+            if expect_ba:
+                assert emu.emu_msm_last_ba() == rounds
+            return got
+        finally:
+            emu.emu_msm_set_ba(0, 0)
+
+    for n in (40, 97, 300):
+        kb = cref.gen_scalars(c.scalar, 70 + n, n)
+        pb = cref.gen_points(curve, 71 + n, n)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+        for cb, k0 in ((3, 0), (2, 8), (4, 16), (5, 0)):
+            for glv in (False, True):
+                for rounds, target in ((1, 64), (2, 5), (3, 1), (3, 20)):
+                    dense = ((2 * n if glv else n) >> (cb - 1)) >= 4      # under 4 references per bucket there is nothing to pair up
+                    assert run(kb, pb, cb, k0, glv, rounds, target, expect_ba=dense) == want, (n, cb, k0, glv, rounds, target)
+    # degenerate inputs: repeated / opposite / identity bases under equal scalars put P + P, P - P and O + P into the pairs
+    pts = [cref.bytes_to_affine(x) for x in cref.gen_points(curve, 5, 6)]
+    neg = lambda q: (q[0], c.p - q[1])  # noqa: E731
+    pts2 = [g, g, neg(g), None, pts[3], pts[3], pts[4], neg(pts[4]), None, g, None, None, pts[5], neg(pts[5]), pts[5], pts[5]] * 6
+    n2 = len(pts2)
+    pb2 = cref.affines_to_bytes(pts2)
+    for name, ks in (("equal", [5] * n2), ("ones", [1] * n2), ("rminus1", [c.r - 1] * n2), ("mix", [(i % 3) + 1 for i in range(n2)]),
+                     ("random", pasta.gen_scalars(c.scalar, 4, n2))):
+        kb = cref.ints_to_bytes(ks)
+        want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb2))
+        for cb, k0 in ((3, 0), (4, 8), (13, 0)):
+            for glv in (False, True):
+                for rounds, target in ((1, 4), (3, 64), (2, 9)):
+                    # (sparse plans -- under 4 references per bucket -- keep the classic accumulation: nothing to pair up)
+                    assert run(kb, pb2, cb, k0, glv, rounds, target, expect_ba=False) == want, (name, cb, k0, glv, rounds, target)
+    # a forced odd bin capacity or item size cannot be halved in place: the plan falls back to the classic accumulation
+    kb = cref.gen_scalars(c.scalar, 3, 64)
+    pb = cref.gen_points(curve, 4, 64)
+    want = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
+    emu.emu_msm_set_ba(3, 64)
+    try:
+        assert _msm(emu, curve, kb, pb, 3, 0, 5, 4) == want and emu.emu_msm_last_ba() == 0
+    finally:
+        emu.emu_msm_set_ba(0, 0)
 
 
 @pytest.mark.parametrize("curve", ["pallas", "vesta"])

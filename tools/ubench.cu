@@ -31,6 +31,9 @@ template <int MODE> __global__ void k(uint32_t *out, uint32_t seed, long long *c
             if (MODE == 10) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x), "r"(y)); asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(x)); asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(y)); }
             if (MODE == 11) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(a[i]) : "r"(x));
             if (MODE == 12) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(x), "r"(y));
+            if (MODE == 13) { asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(dx), "d"(dy)); asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x), "r"(y)); }
+            if (MODE == 14) { asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(dx), "d"(dy)); asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(x), "r"(y)); }
+            if (MODE == 15) { asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(dx), "d"(dy)); asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d[i]) : "d"(dy), "d"(dx)); asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x), "r"(y)); asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(x), "r"(y)); }
         }
     }
     long long t1 = clock64();
@@ -74,5 +77,8 @@ int main() {
     run<10>("IMAD.WIDE + 2 IADD (count 3)", 3);
     run<11>("SHF", 1);
     run<12>("LOP3", 1);
+    run<13>("DFMA + IMAD.WIDE (count 2)", 2);
+    run<14>("DFMA + add.cc/addc (count 3)", 3);
+    run<15>("2 DFMA + IMAD.WIDE + 2 IADD (5)", 5);
     return 0;
 }
