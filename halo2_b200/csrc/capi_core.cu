@@ -258,7 +258,7 @@ static void ctx_destroy(Context &C) {
                      &C.items, &C.bucket_sum, &C.pkey, &C.pstart, &C.pend, &C.ppt, &C.ra_t, &C.ra_e,
                      &C.r0, &C.r1, &C.wsum, &C.scan_blocks, &C.result, &C.misc, &C.ntt_io, &C.ntt_out,
                      &C.ntt_work, &C.pow2, &C.ec_work, &C.ec_io, &C.ec_out, &C.fb_a, &C.fb_b, &C.po_lvl, &C.po_q, &C.po_pts, &C.po_ptrs, &C.ast_code, &C.ast_consts,
-                     &C.multi_parts, &C.ba_lv[0], &C.ba_lv[1], &C.ba_lv[2]};
+                     &C.multi_parts, &C.ba_lv[0], &C.ba_lv[1], &C.ba_lv[2], &C.lk_keys, &C.lk_left, &C.lk_u32};
     for (DevBuf *b : all) b->release();
     for (auto *t : C.twiddles) { t->buf.release(); delete t; }
     C.twiddles.clear();

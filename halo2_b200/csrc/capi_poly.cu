@@ -2,6 +2,7 @@
 #include "util_kernels.cuh"
 #include "polyops.cuh"
 #include "asteval.cuh"
+#include "lookup.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // eval_polynomial / compute_inner_product / kate_division on resident polynomials (polyops.cuh)
@@ -253,3 +254,74 @@ extern "C" int h2_poly_kate_division(const uint64_t *dst, const uint64_t *src, s
     return polyops_dispatch(2, src, dst, batch, n, points, repr, nullptr, "h2_poly_kate_division");
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// the lookup argument's permuted columns (lookup.cuh)
+// ------------------------------------------------------------------------------------------------
+static int lk_scan(uint32_t *d, uint64_t n, cudaStream_t s) {     // exclusive scan in place (kernels of msm.cuh)
+    const uint64_t per_block = (uint64_t)H2_SCAN_BLOCK * H2_SCAN_ITEMS;
+    const uint32_t nb = (uint32_t)((n + per_block - 1) / per_block);
+    if (g_ctx.scan_blocks.ensure((size_t)nb * 4 + 16)) return 1;
+    uint32_t *bs = g_ctx.scan_blocks.as<uint32_t>();
+    LAUNCH(scan_block_sums_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs, (const uint32_t *)nullptr);
+    LAUNCH(scan_single_block_kernel, 1, H2_SCAN_BLOCK, 0, s, bs, nb, (const uint32_t *)nullptr);
+    LAUNCH(scan_apply_kernel, nb, H2_SCAN_BLOCK, 0, s, d, n, bs, (const uint32_t *)nullptr);
+    return 0;
+}
+template <class P> static int lk_sort(fe *keys, uint64_t N, cudaStream_t s) {    // ascending bitonic sort of N = 2^m canonical keys
+    const uint64_t BL = N < (1ull << H2_LK_BLOCK_LOG) ? N : (1ull << H2_LK_BLOCK_LOG);
+    const uint32_t smem = (uint32_t)(BL * sizeof(fe)), thr = (uint32_t)(BL / 2 < 512 ? (BL / 2 ? BL / 2 : 1) : 512);
+    LAUNCH(lk_bitonic_block_kernel, (uint32_t)(N / BL), thr, smem, s, keys, N, (uint64_t)2, 1u);
+    for (uint64_t size = 2 * BL; size <= N; size <<= 1) {
+        for (uint64_t stride = size / 2; stride >= BL; stride >>= 1)
+            LAUNCH(lk_bitonic_global_kernel<P>, blocks_for(N / 2, 256), 256, 0, s, keys, N, size, stride);
+        LAUNCH(lk_bitonic_block_kernel, (uint32_t)(N / BL), thr, smem, s, keys, N, size, 0u);
+    }
+    return 0;
+}
+template <class P> static int lookup_permute_run(PolyBuf *in, PolyBuf *tab, size_t u, PolyBuf *out_in, PolyBuf *out_tab) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    uint64_t N = 2;
+    while (N < u) N <<= 1;
+    // u32 scratch: first flags | their scan (u + 1) | unconsumed flags | their scan (u + 1) | error word
+    const size_t w = u + 1;
+    if (X.lk_keys.ensure(2 * N * sizeof(fe)) || X.lk_left.ensure((u + 1) * sizeof(fe)) || X.lk_u32.ensure((4 * w + 4) * sizeof(uint32_t))) return 1;
+    fe *ka = X.lk_keys.as<fe>(), *kt = ka + N, *left = X.lk_left.as<fe>();
+    uint32_t *first = X.lk_u32.as<uint32_t>(), *first_scan = first + w, *unc = first_scan + w, *unc_scan = unc + w, *err = unc_scan + w;
+    LAUNCH(lk_load_kernel<P>, blocks_for(N, 256), 256, 0, s, (const fe *)in->buf.as<fe>(), (uint64_t)u, ka, N);
+    LAUNCH(lk_load_kernel<P>, blocks_for(N, 256), 256, 0, s, (const fe *)tab->buf.as<fe>(), (uint64_t)u, kt, N);
+    if (lk_sort<P>(ka, N, s) || lk_sort<P>(kt, N, s)) return 1;
+    CU(cudaMemsetAsync(first, 0, (4 * w + 4) * sizeof(uint32_t), s));
+    LAUNCH(lk_fill_u32_kernel, blocks_for(u, 256), 256, 0, s, unc, (uint64_t)u, 1u);
+    LAUNCH(lk_first_kernel<P>, blocks_for(u, 128), 128, 0, s, (const fe *)ka, (const fe *)kt, (uint64_t)u, first, unc, err, out_in->buf.as<fe>(),
+           out_tab->buf.as<fe>());
+    CU(cudaMemcpyAsync(first_scan, first, w * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(unc_scan, unc, w * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    if (lk_scan(first_scan, w, s) || lk_scan(unc_scan, w, s)) return 1;
+    LAUNCH(lk_leftover_kernel<P>, blocks_for(u, 256), 256, 0, s, (const fe *)kt, (uint64_t)u, (const uint32_t *)unc, (const uint32_t *)unc_scan, left);
+    LAUNCH(lk_fill_kernel<P>, blocks_for(u, 256), 256, 0, s, (uint64_t)u, (const uint32_t *)first, (const uint32_t *)first_scan, (const fe *)left,
+           out_tab->buf.as<fe>());
+    uint32_t h_err = 0;
+    CU(cudaMemcpyAsync(&h_err, err, sizeof h_err, cudaMemcpyDeviceToHost, s));
+    if (scratch_release(s)) return 1;
+    CU(cudaStreamSynchronize(s));
+    if (h_err) return fail("h2_poly_lookup_permute: an input value does not occur in the table (Error::ConstraintSystemFailure, plonk/lookup/prover.rs:605-608)");
+    return 0;
+}
+extern "C" int h2_poly_lookup_permute(uint64_t input, uint64_t table, size_t usable_rows, uint64_t out_input, uint64_t out_table) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *a = find_poly(input), *t = find_poly(table), *oa = find_poly(out_input), *ot = find_poly(out_table);
+    if (!a || !t || !oa || !ot) return fail("h2_poly_lookup_permute: unknown polynomial handle");
+    if (oa == ot || oa == a || oa == t || ot == a || ot == t) return fail("h2_poly_lookup_permute: the outputs must be two polynomials other than the inputs");
+    if (a->field != t->field || a->field != oa->field || a->field != ot->field) return fail("h2_poly_lookup_permute: the polynomials live in different fields");
+    if (a->len < usable_rows || t->len < usable_rows || oa->len < usable_rows || ot->len < usable_rows)
+        return fail("h2_poly_lookup_permute: a polynomial holds fewer than usable_rows elements");
+    if (usable_rows >= (1ull << 31)) return fail("h2_poly_lookup_permute: usable_rows >= 2^31");
+    if (usable_rows == 0) return 0;
+    if (a->field == H2_FIELD_FP) return lookup_permute_run<FpParams>(a, t, usable_rows, oa, ot);
+    return lookup_permute_run<FqParams>(a, t, usable_rows, oa, ot);
+}

@@ -136,6 +136,7 @@ struct Context {
     StageRing stage;
     DevBuf ast_code, ast_consts;             // asteval.cuh: the postfix program and its constants
     DevBuf po_lvl, po_q, po_pts, po_ptrs;    // polyops.cuh: level arrays, kate carries, per-level points, pointer arrays
+    DevBuf lk_keys, lk_left, lk_u32;         // lookup.cuh: sorted canonical keys (input | table), leftover table values, flag / scan arrays
     std::vector<TwiddleEntry *> twiddles;
     uint64_t tw_stamp = 0;
     std::map<uint64_t, BaseSet *> bases;

@@ -424,6 +424,19 @@ def running_product_resident(src: "ResidentPoly", init: int = 1, dst: Optional["
     return dst
 
 
+def permute_expression_pair_resident(input_expression: "ResidentPoly", table_expression: "ResidentPoly", usable_rows: int,
+                                     out_input: Optional["ResidentPoly"] = None, out_table: Optional["ResidentPoly"] = None):
+    """permute_expression_pair (plonk/lookup/prover.rs:563-647) on resident Lagrange-basis columns: returns (A', S') with
+    A'[:usable_rows] the sorted input values and S'[:usable_rows] the table values arranged so that S'[r] == A'[r] on the first
+    row of every run of equal inputs.  The blinding rows from `usable_rows` on (:625-627) are the caller's: write them with
+    `upload_at`-style calls or `add_at`.  An input value missing from the table raises H2Error (the reference returns
+    Error::ConstraintSystemFailure, :605-608)."""
+    out_input = ResidentPoly(input_expression.field, input_expression.len) if out_input is None else out_input
+    out_table = ResidentPoly(input_expression.field, input_expression.len) if out_table is None else out_table
+    _l.check(_l.init().h2_poly_lookup_permute(input_expression._h, table_expression._h, ctypes.c_size_t(int(usable_rows)), out_input._h, out_table._h))
+    return out_input, out_table
+
+
 class EvaluationDomain:
     """poly/domain.rs:20-146.  `zeta` is F::ZETA (domain.rs:85): pasta_curves' choice of cube root
     is not pinned by any in-tree golden, so the caller supplies it."""

@@ -167,6 +167,13 @@ int h2_poly_batch_invert(uint64_t poly, size_t n);
 /* ... and the running product dst[0] = init (last_z), dst[i] = dst[i - 1] * src[i - 1], i < n (:150-156).  The elementwise
  * numerators / denominators before it are Ast programs in the Lagrange basis (h2_poly_eval_ast).  Both asynchronous. */
 int h2_poly_running_product(uint64_t dst, uint64_t src, size_t n, const void *init, int repr);
+/* The lookup argument's permuted columns, permute_expression_pair (plonk/lookup/prover.rs:563-647), on resident Lagrange-basis
+ * polynomials: out_input[0, usable_rows) = the input values sorted (ff's Ord = the canonical integers, :577-581);
+ * out_table[r] = out_input[r] on the first row of every run of equal values (:595-603), the remaining rows take the table
+ * values that are left over, ascending, from the last such row down (:617-622).  Rows from usable_rows on -- the blinding rows,
+ * :625-627 -- are not touched: the caller writes its random values there.  Fails (non-zero, nothing useful in the outputs) when
+ * an input value does not occur in the table, the reference's Error::ConstraintSystemFailure (:605-608).  Synchronous. */
+int h2_poly_lookup_permute(uint64_t input, uint64_t table, size_t usable_rows, uint64_t out_input, uint64_t out_table);
 /* EvaluationDomain::divide_by_vanishing_poly (poly/domain.rs:329-348) in place on a resident extended-domain polynomial:
  * h[i] *= t_evals[i mod t_len]; t_evals = the domain's t_evaluations (domain.rs:86-128), t_len = 2^(ext_k - k).  Asynchronous. */
 int h2_poly_divide_by_vanishing(uint64_t poly, uint32_t ext_k, const void *t_evals, uint32_t t_len, int repr);

@@ -44,7 +44,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 # --------------------------------------------------------------------------------------
 # Fields.  tests/plonk_api.rs:591-592
@@ -1053,3 +1053,32 @@ def params_generators(c: Curve, k: int) -> Tuple[List[Affine], Affine, Affine]:
     hasher = hash_to_curve(c, "Halo2-Parameters")
     g = [hasher(b"\0" + i.to_bytes(4, "little")) for i in range(1 << k)]
     return g, hasher(b"\x01"), hasher(b"\x02")
+
+
+def permute_expression_pair(field: str, input_expression: Sequence[int], table_expression: Sequence[int], usable_rows: int):
+    """plonk/lookup/prover.rs:563-647 without the blinding rows (:625-627, random): (A', S') over the usable rows, or None
+    where the reference returns Error::ConstraintSystemFailure (:605-608).  Line for line: sort the input (:577-581), count the
+    table values (:584-591), walk the sorted input -- first row of a run takes its own value and removes one instance from the
+    map, repeated rows are remembered (:595-614) -- then hand the leftover table values, ascending, to the remembered rows
+    popped from the back (:617-622)."""
+    u = int(usable_rows)
+    permuted_input = sorted(int(x) % FIELDS[field] for x in input_expression[:u])
+    leftover: Dict[int, int] = {}
+    for t in table_expression[:u]:
+        leftover[int(t)] = leftover.get(int(t), 0) + 1
+    permuted_table = [0] * u
+    repeated_rows: List[int] = []
+    for row, v in enumerate(permuted_input):
+        if row == 0 or v != permuted_input[row - 1]:
+            permuted_table[row] = v
+            if leftover.get(v, 0) > 0:
+                leftover[v] -= 1
+            else:
+                return None
+        else:
+            repeated_rows.append(row)
+    for coeff in sorted(leftover):                     # BTreeMap iteration order: ascending keys
+        for _ in range(leftover[coeff]):
+            permuted_table[repeated_rows.pop()] = coeff
+    assert not repeated_rows
+    return permuted_input, permuted_table

@@ -231,3 +231,42 @@ def test_batched_affine_accumulation(eng, curve):
             assert fl.value & 2 == 0, "the exact sort ran: the batched-affine rounds were skipped"
     finally:
         L.check(lib.h2_test_set_batched_affine(0, 32))
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_lookup_permuted_columns(eng, field):
+    """permute_expression_pair (plonk/lookup/prover.rs:563-647) on resident columns against the oracle's line-for-line
+    restatement: every size class of the sort (one shared-memory block, several blocks + global stages, non powers of two),
+    tables with few / many distinct values, small integers (the high limbs tie) and full-width values, rows past usable_rows
+    untouched, and the failure when an input value is missing from the table."""
+    import random
+    import halo2_b200 as h2
+    m = pasta.FIELDS[field]
+    rnd = random.Random(5)
+    for n, u, distinct, small in ((8, 5, 3, True), (64, 64, 1, False), (1024, 1019, 40, True), (1 << 12, (1 << 12) - 6, 4000, False),
+                                  (1 << 14, (1 << 14) - 6, 1 << 10, True), (3000, 2500, 2500, False)):
+        pool = [rnd.randrange(1 << 12) if small else rnd.randrange(m) for _ in range(distinct)]
+        tab = (pool + [rnd.choice(pool) for _ in range(u)])[:u] if distinct <= u else pool[:u]
+        rnd.shuffle(tab)
+        inp = [rnd.choice(tab) for _ in range(u)]
+        tail = [rnd.randrange(m) for _ in range(n - u)]
+        a = h2.ResidentPoly(field, n, cref.ints_to_bytes(inp + tail))
+        t = h2.ResidentPoly(field, n, cref.ints_to_bytes(tab + tail))
+        marker = [123456789 + i for i in range(n)]
+        oa = h2.ResidentPoly(field, n, cref.ints_to_bytes(marker))
+        ot = h2.ResidentPoly(field, n, cref.ints_to_bytes(marker))
+        h2.permute_expression_pair_resident(a, t, u, oa, ot)
+        want_a, want_s = pasta.permute_expression_pair(field, inp, tab, u)
+        got_a, got_s = cref.bytes_to_ints(oa.download()), cref.bytes_to_ints(ot.download())
+        assert got_a[:u] == want_a and got_s[:u] == want_s, (n, u, distinct)
+        assert got_a[u:] == marker[u:] and got_s[u:] == marker[u:]             # the blinding rows are the caller's
+        # an input value that the table does not hold: Error::ConstraintSystemFailure
+        bad = list(inp)
+        bad[u // 2] = (max(tab) + 1) % m if small else (tab[0] + 1) % m
+        if bad[u // 2] not in set(tab):
+            b = h2.ResidentPoly(field, n, cref.ints_to_bytes(bad + tail))
+            with pytest.raises(h2.H2Error):
+                h2.permute_expression_pair_resident(b, t, u, oa, ot)
+            b.close()
+        for p in (a, t, oa, ot):
+            p.close()

@@ -182,3 +182,25 @@ def test_ast_evaluate_restatements_agree():
             got = cref.ast_eval(field, pb, log_n, code, consts, d.omega if basis == "lagrange" else d.extended_omega,
                                 1 if basis == "lagrange" else d.g_coset, threads)
             assert cref.bytes_to_ints(got) == want, (basis, threads)
+
+
+def test_permute_expression_pair_properties():
+    """The restated permute_expression_pair against what the reference's own sanity check demands (plonk/lookup/prover.rs:630-641:
+    where A' and S' differ, A' repeats the previous row) plus the multiset equalities, and the failure case (:605-608)."""
+    import random
+    rnd = random.Random(11)
+    m = pasta.FIELDS["fp"]
+    for u, vals in ((1, 1), (7, 3), (200, 16), (257, 300), (64, 1)):
+        table = [rnd.randrange(m) for _ in range(vals)]
+        tab_col = [table[i % vals] if i < vals else rnd.choice(table) for i in range(u)]
+        rnd.shuffle(tab_col)
+        inp = [rnd.choice(tab_col) for _ in range(u)]
+        a, s = pasta.permute_expression_pair("fp", inp + [5, 6], tab_col + [7, 8], u)
+        assert a == sorted(inp) and sorted(s) == sorted(tab_col)
+        last = None
+        for x, y in zip(a, s):
+            if x != y:
+                assert x == last
+            last = x
+    assert pasta.permute_expression_pair("fp", [1, 2, 3], [1, 2, 4], 3) is None
+    assert pasta.permute_expression_pair("fp", [1, 2, 9], [1, 2, 4], 2) == ([1, 2], [1, 2])     # rows past usable_rows are ignored
