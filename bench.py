@@ -278,6 +278,32 @@ def poly_reductions_ms(h2, cref, reps=5):
     return out
 
 
+def lookup_permute_ms(h2, cref, reps=5):
+    """The lookup argument's permuted columns (permute_expression_pair, plonk/lookup/prover.rs:563-647) at k=14 on resident
+    columns -- a 2^10-value table, inputs drawn from it -- next to the C restatement (serial like the reference: sort + ordered map)."""
+    import numpy as np
+    n = 1 << PROVER_K
+    u = n - 6
+    rng = np.random.default_rng(SEED & 0xffffffff)
+    pool = cref.gen_scalars("fp", SEED + 120, 1 << 10)
+    tab = pool[np.concatenate([np.arange(1 << 10), rng.integers(0, 1 << 10, n - (1 << 10))])]
+    inp = tab[rng.integers(0, u, n)]
+    a, t = h2.ResidentPoly("fp", n, inp), h2.ResidentPoly("fp", n, tab)
+    oa, ot = h2.ResidentPoly("fp", n), h2.ResidentPoly("fp", n)
+    h2.permute_expression_pair_resident(a, t, u, oa, ot)
+    t0 = time.time()
+    for _ in range(reps):
+        h2.permute_expression_pair_resident(a, t, u, oa, ot)
+    gpu_ms = (time.time() - t0) / reps * 1e3
+    t0 = time.time()
+    want = cref.permute_expression_pair(inp, tab, u)
+    cpu_ms = (time.time() - t0) * 1e3
+    same = bool((oa.download(u) == want[0]).all() and (ot.download(u) == want[1]).all())
+    for r in (a, t, oa, ot):
+        r.close()
+    return {"k": PROVER_K, "usable_rows": u, "gpu_ms": gpu_ms, "cpu_baseline": {"ms": cpu_ms, "cores": 1, "kind": "port"}, "same_result": same}
+
+
 def quotient_pipeline_ms(h2, cref, threads, reps=5):
     """The quotient pipeline of plonk/vanishing/prover.rs:81-88 at k=14, extended_k=16, resident on the device: coeff_to_extended of
     four columns, an h(X)-shaped Ast over them (two gates, a permutation-style product with the linear term, folded by powers of
@@ -867,6 +893,7 @@ def main():
             extra["params_lagrange_k14"] = guarded(params_lagrange_ms, h2, cref, threads)
             extra["poly_reductions_k14"] = guarded(poly_reductions_ms, h2, cref)
             extra["quotient_pipeline_k14"] = guarded(quotient_pipeline_ms, h2, cref, threads)
+            extra["lookup_permute_k14"] = guarded(lookup_permute_ms, h2, cref)
             extra["create_proof_k14_replay"] = guarded(prover_replay, h2, cref, threads)
 
         extra["msm_2p24_strong"] = c5

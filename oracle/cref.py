@@ -30,8 +30,7 @@ def build(force: bool = False) -> str:
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()                  # no-op unless the source is newer than the library
         _lib = ctypes.CDLL(_SO)
         for name in ("orc_best_multiexp", "orc_naive_msm", "orc_best_fft", "orc_ifft", "orc_coeff_to_extended",
                      "orc_extended_to_coeff", "orc_field_op", "orc_scalar_mul", "orc_point_add",
@@ -167,6 +166,16 @@ def kate_division(field: str, a: np.ndarray, b) -> np.ndarray:
     out = np.zeros((max(p.shape[0] - 1, 0), 32), dtype=np.uint8)
     lib().orc_kate_division(FIELD_ID[field], _p(p), ctypes.c_size_t(p.shape[0]), _p(_fe(b)), _p(out))
     return out
+
+
+def permute_expression_pair(input_expression: np.ndarray, table_expression: np.ndarray, usable_rows: int):
+    """plonk/lookup/prover.rs:563-647 over the usable rows (canonical bytes); None where the reference fails (:605-608)."""
+    a = np.ascontiguousarray(input_expression, dtype=np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(table_expression, dtype=np.uint8).reshape(-1, 32)
+    u = int(usable_rows)
+    oa, ot = np.zeros((u, 32), dtype=np.uint8), np.zeros((u, 32), dtype=np.uint8)
+    rc = lib().orc_permute_expression_pair(_p(a), _p(t), ctypes.c_size_t(u), _p(oa), _p(ot))
+    return None if rc else (oa, ot)
 
 
 def ast_eval(field: str, polys: np.ndarray, log_n: int, code: np.ndarray, consts, omega, lin_base, threads: Optional[int] = None) -> np.ndarray:

@@ -688,6 +688,40 @@ int orc_kate_division(int field, const uint8_t *a, size_t n, const uint8_t *b, u
     return 0;
 }
 
+/* ---------------------------------------------------------------- permute_expression_pair (plonk/lookup/prover.rs:563-647)
+ * The usable rows only (the blinding rows, :625-627, are random).  Serial like the reference: sort the input (:577-581); the
+ * reference's BTreeMap of table values with counts (:584-591) is restated as the sorted table with one "taken" mark per value
+ * consumed -- iterating what is left in ascending order is the map's iteration order (:617); repeated rows are handed out
+ * from the back (:619, `pop`).  Canonical 32-byte little-endian values in and out.  Returns 1 where the reference returns
+ * Error::ConstraintSystemFailure (:605-608). */
+static int cmp_bytes32(const void *a, const void *b) {
+    const uint8_t *x = (const uint8_t *)a, *y = (const uint8_t *)b;
+    for (int i = 31; i >= 0; i--) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+    return 0;
+}
+int orc_permute_expression_pair(const uint8_t *input, const uint8_t *table, size_t usable_rows, uint8_t *out_input, uint8_t *out_table) {
+    const size_t u = usable_rows;
+    if (u == 0) return 0;
+    uint8_t *ts = (uint8_t *)malloc(32 * u), *taken = (uint8_t *)calloc(u, 1);
+    size_t *rep = (size_t *)malloc(sizeof(size_t) * u), nrep = 0;
+    memcpy(out_input, input, 32 * u); qsort(out_input, u, 32, cmp_bytes32);
+    memcpy(ts, table, 32 * u); qsort(ts, u, 32, cmp_bytes32);
+    int rc = 0;
+    for (size_t row = 0; row < u && !rc; row++) {
+        const uint8_t *v = out_input + 32 * row;
+        if (row == 0 || cmp_bytes32(v, v - 32) != 0) {
+            memcpy(out_table + 32 * row, v, 32);
+            size_t lo = 0, hi = u;                       /* first instance of v in the sorted table */
+            while (lo < hi) { size_t mid = (lo + hi) / 2; if (cmp_bytes32(ts + 32 * mid, v) < 0) lo = mid + 1; else hi = mid; }
+            if (lo >= u || cmp_bytes32(ts + 32 * lo, v) != 0) rc = 1; else taken[lo] = 1;
+        } else rep[nrep++] = row;
+    }
+    for (size_t i = 0; i < u && !rc; i++)
+        if (!taken[i]) memcpy(out_table + 32 * rep[--nrep], ts + 32 * i, 32);
+    free(ts); free(taken); free(rep);
+    return rc;
+}
+
 /* ---------------------------------------------------------------- Evaluator::evaluate (poly/evaluator.rs:129-228)
  * The Ast arrives flattened in postfix form (four uint32 per instruction: op, arg, shift, 0 -- 0 POLY, 1 CONST, 2 LINEAR, 3 ADD,
  * 4 MUL, 5 SCALE, 6 NEG; DistributePowers = CONST 0 then SCALE base / term / ADD per term); like the reference the work is split

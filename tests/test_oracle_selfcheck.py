@@ -197,10 +197,13 @@ def test_permute_expression_pair_properties():
         inp = [rnd.choice(tab_col) for _ in range(u)]
         a, s = pasta.permute_expression_pair("fp", inp + [5, 6], tab_col + [7, 8], u)
         assert a == sorted(inp) and sorted(s) == sorted(tab_col)
+        ca, cs = cref.permute_expression_pair(cref.ints_to_bytes(inp + [5, 6]), cref.ints_to_bytes(tab_col + [7, 8]), u)   # the C restatement agrees
+        assert cref.bytes_to_ints(ca) == a and cref.bytes_to_ints(cs) == s
         last = None
         for x, y in zip(a, s):
             if x != y:
                 assert x == last
             last = x
     assert pasta.permute_expression_pair("fp", [1, 2, 3], [1, 2, 4], 3) is None
+    assert cref.permute_expression_pair(cref.ints_to_bytes([1, 2, 3]), cref.ints_to_bytes([1, 2, 4]), 3) is None
     assert pasta.permute_expression_pair("fp", [1, 2, 9], [1, 2, 4], 2) == ([1, 2], [1, 2])     # rows past usable_rows are ignored
