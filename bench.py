@@ -651,11 +651,13 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     k_ms = tot.value / max(cnt.value, 1)
     achieved = MSM_BYTES_PER_PAIR * n / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram read+write bytes per launch from the committed ncu --set full capture
+    traffic, traffic_src, ntt_traffic, ntt_traffic_src = None, None, None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram read+write bytes per launch from the committed ncu --set full captures
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("msm_accum0_kernel", {}).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("msm_accum0_kernel", {}).get("dram_bytes_per_launch"), tj.get("msm_accum0_kernel", {}).get("source")
+        ntt_traffic, ntt_traffic_src = tj.get("ntt_pass_kernel", {}).get("dram_bytes_per_launch"), tj.get("ntt_pass_kernel", {}).get("source")
     # the pipe that actually bounds it: 255-bit modular multiplies on the INT32 multiply-add pipe.  Peak = the multiply
     # microbenchmark measured live at full occupancy (h2_bench_field_mul: 4 dependent-chain multiplies per thread and
     # iteration, 64 warps per SM); achieved = multiplies the kernel must execute / its duration.
@@ -669,7 +671,7 @@ def main():
                "frac": achieved_gmul / peak_gmul, "modmul_per_launch": n * refs_per_pair * 10,
                "peak_source": "h2_bench_field_mul measured in this run (Montgomery multiply microbenchmark, 64 warps/SM)"}
     roofline = {"kernel": "msm_accum0_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "compute": compute,
-                "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": MSM_BYTES_PER_PAIR * n, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": MSM_BYTES_PER_PAIR * n, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                 "peak_source": peak_src,
                 "note": "255-bit modular integer work: the limiter is the INT32 multiply-add pipe, not HBM (DESIGN.md section 5)"}
 
@@ -810,7 +812,10 @@ def main():
             "config": {"workload": f"best_fft 2^{LOG_N} over Fp (configs[1]), twiddles cached per (omega, log_n), "
                                    "5 rotating 32 MiB buffers (> L2)"},
             "roofline": {"kernel": "ntt_pass_kernel", "bound": "hbm", "achieved": ntt_ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ntt_ach / hbm_peak, "traffic": None, "kernel_ms": pass_ms, "passes_per_step": 3},
+                         "frac": ntt_ach / hbm_peak, "traffic": ntt_traffic, "traffic_source": ntt_traffic_src, "kernel_ms": pass_ms, "passes_per_step": 3,
+                         "compute": {"pipe": "INT32 multiply-add (fmaheavy)", "unit": "G modmul/s", "achieved": (LOG_N * n / 2) / (ntt_ms * 1e-3) / 1e9,
+                                     "peak": peak_gmul, "frac": (LOG_N * n / 2) / (ntt_ms * 1e-3) / 1e9 / peak_gmul,
+                                     "note": "log_n * n / 2 butterflies, one multiply each, over the whole transform"}},
             "e2e": {"value": n / ntt_e2e, "unit": "elems/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
                     "ms_per_step": ntt_e2e * 1e3, "api": "h2_ntt (host buffers, canonical repr)"},
         }

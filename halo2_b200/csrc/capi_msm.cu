@@ -219,6 +219,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         auto k_iplace = msm_item_place_kernel<P, PS>;
         auto k_accum0 = msm_accum0_kernel<P, PS>;
         auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
+        auto k_accum0p2 = msm_accum0_pair_kernel<P, PS>;
         auto k_accum0m2 = msm_accum0_multi_kernel<P, PS, 2>;
         auto k_accum0m4 = msm_accum0_multi_kernel<P, PS, 4>;
         auto k_ba = X.ba_variant == 1 ? msm_ba_round_kernel<P, PS, 4, 5> : X.ba_variant == 2 ? msm_ba_round_kernel<P, PS, 2, 4>
@@ -266,6 +267,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
             if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) {   // latency-bound: quads, several per work item
                 if (X.accum_ways == 4) LAUNCH(k_accum0m4, blocks_for(q.max_items * 16, 128), 128, 0, s, q, M);
                 else if (X.accum_ways == 2) LAUNCH(k_accum0m2, blocks_for(q.max_items * 8, 128), 128, 0, s, q, M);
+                else if (X.accum_ways == 0) LAUNCH(k_accum0p2, blocks_for(q.max_items * 2, 128), 128, 0, s, q, M);
                 else LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);
             }
             else {

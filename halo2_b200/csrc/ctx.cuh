@@ -109,9 +109,10 @@ struct Context {
     const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
     uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
-    uint32_t accum_ways = 1;                 // quads per work item in the small-problem accumulation (1, 2, 4; test hook).  Measured at
-                                             // k = 14, c = 15: commit 0.360 / 0.329 / 0.361 ms, IPA opening 5.7 / 6.1 / 7.6 ms -- the accumulation is
-                                             // bound by lane-multiplies (a quad addition occupies 16 slots for 10 products), not by its chains
+    uint32_t accum_ways = 0;                 // lanes per work item in the small-problem accumulation: 0 = a PAIR (default: 10 lane-multiplies per addition at
+                                             // 5 multiply latencies), 1 / 2 / 4 = quads (16 slots for 10 products, 4 latencies).  Measured at k = 14, c = 15:
+                                             // commit 0.389 (pair) / 0.407 / 0.329-0.36 (2 quads) / 0.361 ms, IPA opening 5.56 (pair) / 5.68 / 6.1 / 7.6 ms --
+                                             // the accumulation is bound by lane-multiplies, not by its chains (test hook h2_test_set_accum_ways)
     uint32_t ntt_tma = 0;                    // NTT passes: 1 = bulk-copy (TMA) persistent kernel where it applies, 0 = classic kernel.  Measured on
                                              // B200 (profiles/r2e_*): 2^20 0.27-0.30 ms vs 0.215 ms, 2^24 4.77 vs 3.67 ms -- the pass is bound by the
                                              // integer pipes (fmaheavy 55-61 %, ALU 54 %, issue 51 %, top stall `wait`), not by its memory phases, and

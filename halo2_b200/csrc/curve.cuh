@@ -265,6 +265,37 @@ template <class P> H2_D void xyzz_add_mixed_quad(xyzz &a, const affine &p) {
     a.x = x3; a.y = fe_sub<P>(t1, t2);
     a.zz = zz3; a.zzz = zzz3;
 }
+// acc += affine p for a PAIR of lanes (lanes 2 i and 2 i + 1 hold the same a and p).  The 10 products of madd-2008-s split
+// into five levels of two -- (u2, s2) -> (pp^2, r^2) -> (pp^3, q) -> (zz3, y1 pp^3) -> (r (q - x3), zzz3) -- so a pair spends
+// exactly 10 lane-multiplies per addition (a quad: 16 slots for 10 products) at 5 multiply latencies (a quad: 4, one lane:
+// 10).  For the small accumulations whose kernel is bound by lane-multiplies AND by its longest chain (k <= 16 commits, IPA rounds).
+template <class P> H2_D void xyzz_add_mixed_pair(xyzz &a, const affine &p) {
+    if (affine_is_identity(p)) return;                   // all tests are uniform within the pair
+    if (xyzz_is_identity(a)) { a = xyzz_from_affine<P>(p); return; }
+    const uint32_t lane = threadIdx.x & 31u, mask = 0x3u << (lane & ~1u);
+    const bool s0 = (lane & 1u) == 0;
+    auto swap = [&](const fe &mine, fe &first, fe &second) {   // first = lane 0's product, second = lane 1's
+        fe other;
+#pragma unroll
+        for (int i = 0; i < 8; i++) other.v[i] = __shfl_xor_sync(mask, mine.v[i], 1);
+        first = fe_select(s0, mine, other); second = fe_select(s0, other, mine);
+    };
+    fe u2, s2, pp2, rr, ppp, q, zz3, t2, t1, zzz3;
+    swap(fe_mul<P>(fe_select(s0, p.x, p.y), fe_select(s0, a.zz, a.zzz)), u2, s2);
+    const fe pp = fe_sub<P>(u2, a.x), r = fe_sub<P>(s2, a.y);
+    if (fe_is_zero(pp)) {
+        if (fe_is_zero(r)) a = xyzz_double_affine<P>(p);   // same point
+        else a = xyzz_identity();                          // opposite points
+        return;
+    }
+    swap(fe_sqr<P>(fe_select(s0, pp, r)), pp2, rr);
+    swap(fe_mul<P>(fe_select(s0, pp, a.x), pp2), ppp, q);
+    const fe x3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(rr, ppp), q), q);
+    swap(fe_mul<P>(fe_select(s0, a.zz, a.y), fe_select(s0, pp2, ppp)), zz3, t2);
+    swap(fe_mul<P>(fe_select(s0, r, a.zzz), fe_select(s0, fe_sub<P>(q, x3), ppp)), t1, zzz3);
+    a.x = x3; a.y = fe_sub<P>(t1, t2);
+    a.zz = zz3; a.zzz = zzz3;
+}
 template <class P> H2_D void xyzz_shift_quad(xyzz &a, uint32_t k) {
     if (k == 0 || xyzz_is_identity(a)) return;          // uniform within the quad
     const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, mask = 0xFu << (lane & ~3u);

@@ -246,6 +246,9 @@ struct QuadAdd {
     template <class P> static H2_D void add(xyzz &a, const xyzz &b) { xyzz_add_quad<P>(a, b); }
     template <class P> static H2_D void add_mixed(xyzz &a, const affine &b) { xyzz_add_mixed_quad<P>(a, b); }
 };
+struct PairAdd {
+    template <class P> static H2_D void add_mixed(xyzz &a, const affine &b) { xyzz_add_mixed_pair<P>(a, b); }
+};
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -848,6 +851,11 @@ template <class P, class PS> __global__ void __launch_bounds__(128, 5) msm_accum
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_quad_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     Msm<P, PS>::template accum0_body<QuadAdd>(p, M, t);
+}
+// ... or one PAIR of lanes per work item (xyzz_add_mixed_pair: no idle multiply slots, 5 multiply latencies per addition)
+template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_pair_kernel(const MsmPlan p, const MsmBuffers M) {
+    uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    Msm<P, PS>::template accum0_body<PairAdd>(p, M, t);
 }
 // ... and WAYS quads per work item (test hook h2_test_set_accum_ways; NOT the default: measured at k = 14, c = 15 -- ~17
 // references per bucket, the fullest ~35 -- 2 / 4 ways change a commit by -9 % / 0 % and the IPA opening by +6 % / +32 %: the

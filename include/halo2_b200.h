@@ -308,7 +308,7 @@ int h2_test_set_ecfft_quad(int on);
  * the default; at most 3), one shared inversion per `pairs_per_thread` additions (0 keeps the value) -- and finish with the
  * XYZZ chain.  6 multiplies per addition instead of 10, but measured no faster on B200. */
 int h2_test_set_batched_affine(uint32_t rounds, uint32_t pairs_per_thread);
-/* Quads of lanes per work item in the accumulation of small MSMs (1, 2 or 4; default 1). */
+/* Lanes per work item in the accumulation of small MSMs: 1, 2 or 4 quads, or 0 = one pair of lanes (see the default in ctx.cuh). */
 int h2_test_set_accum_ways(uint32_t ways);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a) by the Fermat ladder,

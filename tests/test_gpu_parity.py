@@ -727,7 +727,9 @@ def test_small_multiexp_and_batch_normalize(eng):
 
 
 def test_accum_ways(eng):
-    """Small MSMs accumulate with 1, 2 or 4 quads of lanes per work item (msm_accum0_multi_kernel): same points."""
+    """Small MSMs accumulate with 1, 2 or 4 quads of lanes per work item (msm_accum0_multi_kernel) or one pair of lanes
+    (ways = 0, msm_accum0_pair_kernel): same points -- incl. a 0/1/2 column and a constant column, whose buckets are full of
+    repeated points (P + P in the pair / quad formulas)."""
     from halo2_b200 import lib as L
     lib = L.init()
     curve, c, k = "vesta", pasta.VESTA, 10
@@ -740,7 +742,7 @@ def test_accum_ways(eng):
     want_one = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
     wants = [cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([p, cref.ints_to_bytes([9])]), g)) for p in polys]
     try:
-        for ways in (1, 2, 4):
+        for ways in (1, 2, 4, 0):
             L.check(lib.h2_test_set_accum_ways(ways))
             params = eng.Params(curve, k, g[:n], g[:n], g[n:])
             for rep in range(3):     # eager, captured, replayed
@@ -750,7 +752,7 @@ def test_accum_ways(eng):
             assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want_one, ways
         assert lib.h2_test_set_accum_ways(3) != 0
     finally:
-        L.check(lib.h2_test_set_accum_ways(1))
+        L.check(lib.h2_test_set_accum_ways(0))
 
 
 # ------------------------------------------------------------------------------------------ K13

@@ -12,7 +12,7 @@ parts = [f"# {title}\n",
          "`ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/prof_run.py {msm,small}`, `... tools/ipa_time.py 14 1`, "
          "`... tools/ecfft_time.py 14` (cold-cache, serialised launches: compare shares, not absolutes; gen_points / at:: kernels are input "
          "generation).  Command list: `tools/capture.sh`.\n"]
-for name, ttl in (("msm", "MSM 2^20 Pallas one-shot (device-resident inputs), 3 calls"), ("small", "MSM 2^14+1 Vesta one-shot, 3 calls"),
+for name, ttl in (("msm", "MSM 2^20 Pallas one-shot (device-resident inputs), 3 calls"), ("ntt", "NTT 2^20 Fp (best_fft), 4 calls"), ("small", "MSM 2^14+1 Vesta one-shot, 3 calls"),
                   ("ipa", "k=14 Vesta: Params setup (window tables), 1 commit, 14 IPA rounds"),
                   ("ecfft", "k=14 Vesta g -> g_lagrange (EC-iFFT + scale + batch_normalize), thread form then quad form, 4 calls each")):
     f = f"{src}/{tag}_launches_{name}.csv"
@@ -35,9 +35,20 @@ if os.path.exists(b) and os.path.getsize(b):
     n = x["ntt"]
     parts.append(f"* NTT 2^20: {n['value'] / 1e9:.2f} G elems/s ({n['ms_per_step']:.3f} ms), host API {n['e2e']['value'] / 1e9:.2f} G elems/s.")
     c = x["create_proof_k14_replay"]
-    parts.append(f"* create_proof k=14 hot-path replay: {c['value']:.2f} ms (window tables, default) / "
-                 f"{c.get('with_digit_tables', {}).get('value', float('nan')):.2f} ms (opt-in digit-multiples tables) vs {c['cpu_baseline']['value']:.0f} ms CPU; by kind "
-                 f"{json.dumps({k: round(v, 3) for k, v in c['gpu_ms_by_kind'].items()})}; Params setup {c['params_setup_ms']:.0f} ms.")
+    if "value" in c:
+        parts.append(f"* create_proof k=14 proof-shaped replay (Blake2b transcript in both arms, transcript_identical = {c.get('transcript_identical')}): "
+                     f"{c['value']:.2f} ms vs {c['cpu_baseline']['value']:.0f} ms on the C restatement ({c['cpu_baseline']['cores']} threads) = "
+                     f"{c['cpu_baseline']['value'] / c['value']:.1f}x; by kind (synchronised after every call) "
+                     f"{json.dumps({k: round(v, 3) for k, v in c.get('gpu_ms_by_kind_synced', {}).items()})}; Params setup {c['params_setup_ms']:.0f} ms.")
+    e2 = d["e2e"]
+    parts.append(f"* e2e by caller memory: pageable (staged, headline) {e2['ms_per_step']:.3f} ms, pinned {e2['pinned']['ms_per_step']:.3f} ms, "
+                 f"pageable with the staging ring off {e2['pageable_plain']['ms_per_step']:.3f} ms.")
+    if "msm_2p24_strong" in x and x["msm_2p24_strong"] and "value" in x["msm_2p24_strong"]:
+        m24 = x["msm_2p24_strong"]
+        parts.append(f"* MSM 2^24 (BASELINE configs[4], N = {m24['n_gpus']}): {m24['value'] / 1e6:.1f} M pairs/s ({m24['ms_per_step']:.2f} ms), parity vs oracle {m24.get('parity_vs_oracle')}.")
+    if "lookup_permute_k14" in x and "gpu_ms" in x["lookup_permute_k14"]:
+        lp = x["lookup_permute_k14"]
+        parts.append(f"* lookup permuted columns at k=14: {lp['gpu_ms']:.3f} ms vs {lp['cpu_baseline']['ms']:.1f} ms (C restatement, 1 core), same result: {lp['same_result']}.")
     if "params_lagrange_k14" in x:
         p = x["params_lagrange_k14"]
         parts.append(f"* g -> g_lagrange at k=14: {p['gpu_ms']:.2f} ms vs CPU restatement {p['cpu_baseline']['ms']:.0f} ms at k={p['cpu_baseline']['k']} "

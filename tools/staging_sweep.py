@@ -50,7 +50,14 @@ def msm(pinned=False, reps=8):
 
 
 print(f"h2_msm 2^20 pinned: {msm(True):.3f} ms", flush=True)
-for nt in (1, 0):
+for nt in ((1, 0) if len(sys.argv) < 2 else ()):
     for th in (0, 3, 7, 11, 15, 23, 31):
         L.check(lib.h2_test_set_copy_threads(th, nt))
         print(f"nt={nt} threads={th:2d}: upload {up():5.1f} GB/s   h2_msm 2^20 pageable {msm():.3f} ms", flush=True)
+
+if len(sys.argv) > 1 and sys.argv[1] == "chunks":
+    L.check(lib.h2_test_set_copy_threads(15, 1))
+    for thr, name in ((40, "1 upload"), (20, "2 chunks"), (19, "3 chunks (default)"), (17, "4 chunks")):
+        L.check(lib.h2_test_set_chunk_threshold(thr))
+        print(f"{name:20s}: pageable {msm():.3f} ms   pinned {msm(True):.3f} ms", flush=True)
+    L.check(lib.h2_test_set_chunk_threshold(19))

@@ -15,8 +15,8 @@ ch = cref.bytes_to_ints(cref.gen_scalars("fp", 3, k))
 lr = cref.bytes_to_ints(cref.gen_scalars("fp", 4, k))
 import os  # noqa: E402
 from halo2_b200 import lib as L  # noqa: E402
-ways = int(os.environ.get("ACCUM_WAYS", "0"))
-if ways:
+ways = int(os.environ.get("ACCUM_WAYS", "-1"))
+if ways >= 0:
     L.check(L.init().h2_test_set_accum_ways(ways))
     print(f"accum ways = {ways}", flush=True)
 for c in [int(a) for a in sys.argv[2:]] or [-1, 0, 13, 15, 17]:      # -1: digit-multiples table (direct sum); 0: automatic window
