@@ -387,6 +387,16 @@ extern "C" int h2_test_set_ecfft_quad(int on) {
     return 0;
 }
 // test hook: one-shot MSMs (h2_msm) of >= 2^log2_n points upload their bases in chunks (default 19)
+// tuning hook: where a k-chunk upload cuts its points, in sixteenths (k = 2 .. 4; c1 < c2 < c3 < 16, unused ones ignored)
+extern uint32_t g_chunk_cut[H2_MAX_UPLOAD_CHUNKS + 1][H2_MAX_UPLOAD_CHUNKS + 1];
+extern "C" int h2_test_set_chunk_cuts(uint32_t k, uint32_t c1, uint32_t c2, uint32_t c3) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (k < 2 || k > H2_MAX_UPLOAD_CHUNKS) return fail("h2_test_set_chunk_cuts: k must be 2, 3 or 4");
+    const uint32_t c[5] = {0, c1, k > 2 ? c2 : 16, k > 3 ? c3 : 16, 16};
+    for (uint32_t j = 1; j <= 4; j++) if (c[j] < c[j - 1] || c[j] > 16 || (j < k && c[j] == c[j - 1])) return fail("h2_test_set_chunk_cuts: cuts must increase, below 16");
+    for (uint32_t j = 0; j <= 4; j++) g_chunk_cut[k][j] = c[j];
+    return 0;
+}
 extern "C" int h2_test_set_chunk_threshold(uint32_t log2_n) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (log2_n > 40) return fail("h2_test_set_chunk_threshold: log2_n > 40");

@@ -28,9 +28,10 @@ static int exclusive_scan_u32(uint32_t *d, uint64_t n, cudaStream_t s, const uin
 // landed, so it is small (1/16 - 1/4 of the points), and the accumulation of chunk j hides the upload of the larger
 // chunk j + 1 -- the link stays busy from t = 0 and the GPU from the first chunk's arrival.  (Equal chunks left the
 // GPU idle for 1/k of the upload time: 2^20 pairs, 96 MiB at ~50 GB/s, 2 chunks: 0.95 of 4.57 ms.)
+uint32_t g_chunk_cut[H2_MAX_UPLOAD_CHUNKS + 1][H2_MAX_UPLOAD_CHUNKS + 1] = {
+    {0, 16, 16, 16, 16}, {0, 16, 16, 16, 16}, {0, 4, 16, 16, 16}, {0, 2, 8, 16, 16}, {0, 1, 4, 10, 16}};   // sixteenths (h2_test_set_chunk_cuts)
 static inline size_t chunk_first(size_t n, uint32_t k, uint32_t j) {
-    static const uint32_t cut[H2_MAX_UPLOAD_CHUNKS + 1][H2_MAX_UPLOAD_CHUNKS + 1] = {
-        {0, 16, 16, 16, 16}, {0, 16, 16, 16, 16}, {0, 4, 16, 16, 16}, {0, 2, 8, 16, 16}, {0, 1, 4, 10, 16}};   // sixteenths
+    const auto &cut = g_chunk_cut;
     if (k > H2_MAX_UPLOAD_CHUNKS) k = H2_MAX_UPLOAD_CHUNKS;
     if (j >= k) return n;
     return (size_t)((unsigned __int128)n * cut[k][j] / 16);

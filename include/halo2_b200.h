@@ -287,6 +287,9 @@ int h2_test_last_msm_flags(uint32_t *out);
 /* Test hook: h2_msm uploads the bases of inputs with >= 2^log2_n points in chunks that are sorted and accumulated
  * separately while the next chunk is on the PCIe link (default 19). */
 int h2_test_set_chunk_threshold(uint32_t log2_n);
+/* Tuning hook: the points at which a k-chunk upload (k = 2, 3, 4) is cut, in sixteenths of n: chunks GROW so that the upload
+ * of chunk j + 1 hides behind the accumulation of chunk j (defaults 4 | 2, 8 | 1, 4, 10). */
+int h2_test_set_chunk_cuts(uint32_t k, uint32_t c1, uint32_t c2, uint32_t c3);
 /* Transfers from / to PAGEABLE caller memory (a Rust Vec) go through a pinned staging ring filled by a few host threads,
  * so that the link runs near its pinned rate and uploads still overlap compute; pinned / registered memory is used in
  * place.  0 switches the ring off (plain cudaMemcpyAsync): bench.py times both. */

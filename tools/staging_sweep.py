@@ -61,3 +61,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "chunks":
         L.check(lib.h2_test_set_chunk_threshold(thr))
         print(f"{name:20s}: pageable {msm():.3f} ms   pinned {msm(True):.3f} ms", flush=True)
     L.check(lib.h2_test_set_chunk_threshold(19))
+
+if len(sys.argv) > 1 and sys.argv[1] == "cuts":
+    L.check(lib.h2_test_set_copy_threads(15, 1))
+    for k, thr, cuts in ((3, 19, (2, 8, 16)), (3, 19, (3, 8, 16)), (3, 19, (3, 9, 16)), (3, 19, (4, 9, 16)), (3, 19, (4, 10, 16)), (3, 19, (5, 10, 16)),
+                         (4, 17, (1, 4, 10)), (4, 17, (2, 6, 11)), (4, 17, (3, 7, 11)), (4, 17, (3, 6, 10)), (2, 20, (4, 16, 16)), (2, 20, (6, 16, 16))):
+        L.check(lib.h2_test_set_chunk_threshold(thr))
+        L.check(lib.h2_test_set_chunk_cuts(k, *cuts))
+        print(f"k={k} cuts={cuts}: pageable {msm(reps=12):.3f} ms   pinned {msm(True, reps=12):.3f} ms", flush=True)
