@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
 PROVER_K, PROVER_J = 14, 5
 
 
-def prover_replay(h2, cref, threads, reps=3):
+def prover_replay(h2, cref, threads, reps=3, k=None):
     """create_proof k=14 (BASELINE configs[3]) as a proof-shaped replay with the reference's Blake2b transcript in both arms
     (tests/prover_replay.py): the GPU arm through the reference-facing API on device-resident polynomials, wall-clock per
     proof including the Python glue and the host-side transcript; the CPU arm through the C restatement, counting ONLY its
@@ -152,7 +152,8 @@ def prover_replay(h2, cref, threads, reps=3):
     compared: every commitment, evaluation and opening round enters the transcript and every challenge feeds back."""
     from oracle import pasta
     from tests import prover_replay as R
-    k, n = PROVER_K, 1 << PROVER_K
+    k = PROVER_K if k is None else k
+    n = 1 << k
     pts = cref.gen_points("vesta", SEED + 50, n + 2)           # g || w || u: seeded stand-ins (a real Params::new(14) hashes 2^14 messages)
     g, w, u = pts[:n], pts[n:n + 1], pts[n + 1:n + 2]
     gl = h2.lagrange_generators("vesta", k, g)                 # g_lagrange as Params::new derives it (EC-iFFT on the device)
@@ -900,6 +901,8 @@ def main():
             extra["quotient_pipeline_k14"] = guarded(quotient_pipeline_ms, h2, cref, threads)
             extra["lookup_permute_k14"] = guarded(lookup_permute_ms, h2, cref)
             extra["create_proof_k14_replay"] = guarded(prover_replay, h2, cref, threads)
+            # the top of the reference's own bench range (benches/plonk.rs: k = 8..16): the passes stop being latency-bound
+            extra["create_proof_k16_replay"] = guarded(prover_replay, h2, cref, threads, 2, 16)
 
         extra["msm_2p24_strong"] = c5
         line = {

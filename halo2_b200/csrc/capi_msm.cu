@@ -1,5 +1,7 @@
 // C ABI of the engine, part 2 of 5: the MSM pipeline (msm.cuh, fixedbase.cuh), resident base sets, the IPA round loop (ipa.cuh).
-#define H2_MSM_QUAD_ACCUM_REFS (1ull << 20)   // up to this many references the accumulation runs one quad per work item
+// up to this many references the accumulation runs a pair / quad of lanes per work item; fixed-base passes (few, short buckets: the kernel lasts
+// as long as its longest chain) up to twice that -- measured: 4 batched k = 14 commits (1.1 M references) 0.83 -> 0.74 ms, one-shot 2^17 1.08 -> 1.37 ms
+#define H2_MSM_QUAD_ACCUM_REFS (g_ctx.small_accum_refs)
 #include "util_kernels.cuh"
 #include "msm.cuh"
 #include "ipa.cuh"
@@ -265,7 +267,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
                 LAUNCH(k_phi, blocks_for(q.n, 256), 256, 0, s, M.bases, M.bases_phi, (uint64_t)q.n);
             }
             prof_begin(PROF_MSM_ACCUM0, s);
-            if (q.max_refs <= H2_MSM_QUAD_ACCUM_REFS) {   // latency-bound: quads, several per work item
+            if (q.max_refs <= (q.fixed ? 2 : 1) * H2_MSM_QUAD_ACCUM_REFS) {   // latency-bound: cooperating lanes per work item
                 if (X.accum_ways == 4) LAUNCH(k_accum0m4, blocks_for(q.max_items * 16, 128), 128, 0, s, q, M);
                 else if (X.accum_ways == 2) LAUNCH(k_accum0m2, blocks_for(q.max_items * 8, 128), 128, 0, s, q, M);
                 else if (X.accum_ways == 0) LAUNCH(k_accum0p2, blocks_for(q.max_items * 2, 128), 128, 0, s, q, M);

@@ -17,7 +17,7 @@ import os  # noqa: E402
 from halo2_b200 import lib as L  # noqa: E402
 ways = int(os.environ.get("ACCUM_WAYS", "-1"))
 if ways >= 0:
-    L.check(L.init().h2_test_set_accum_ways(ways))
+    L.check(L.init().h2_test_set_accum_ways(ways | (int(os.environ.get("ACCUM_LOG", "0")) << 8)))
     print(f"accum ways = {ways}", flush=True)
 for c in [int(a) for a in sys.argv[2:]] or [-1, 0, 13, 15, 17]:      # -1: digit-multiples table (direct sum); 0: automatic window
     try:
