@@ -268,7 +268,7 @@ class Params:
                                                  _l.REPR_CANONICAL, _l.ptr(lr)))
                 ls[j], rs[j] = lr[0], lr[1]
                 u_j = int(challenge(j, ls[j], rs[j])) % m
-                _l.check(lib.h2_ipa_fold(sess, _l.ptr(_l.fe_bytes(u_j)), _l.ptr(_l.fe_bytes(pow(u_j, m - 2, m))), _l.REPR_CANONICAL))
+                _l.check(lib.h2_ipa_fold(sess, _l.ptr(_l.fe_bytes(u_j)), _l.ptr(_l.fe_bytes(pow(u_j, -1, m))), _l.REPR_CANONICAL))
             cb = np.zeros((2, 32), dtype=np.uint8)
             _l.check(lib.h2_ipa_finish(sess, _l.REPR_CANONICAL, _l.ptr(cb)))
             sess.value = 0
@@ -301,7 +301,7 @@ class Params:
                                           _l.REPR_CANONICAL, _l.ptr(lr)))
                 ls[j], rs[j] = lr[0], lr[1]
                 u_j = int(challenge(j, ls[j], rs[j])) % m
-                _l.check(lib.h2_ipa_fold(sess, _l.ptr(_l.fe_bytes(u_j)), _l.ptr(_l.fe_bytes(pow(u_j, m - 2, m))), _l.REPR_CANONICAL))
+                _l.check(lib.h2_ipa_fold(sess, _l.ptr(_l.fe_bytes(u_j)), _l.ptr(_l.fe_bytes(pow(u_j, -1, m))), _l.REPR_CANONICAL))
             cb = np.zeros((2, 32), dtype=np.uint8)
             _l.check(lib.h2_ipa_finish(sess, _l.REPR_CANONICAL, _l.ptr(cb)))
             sess.value = 0
@@ -458,13 +458,13 @@ class EvaluationDomain:
         for _ in range(k, ext_k):
             w = w * w % m
         self.omega = w
-        self.omega_inv = pow(w, m - 2, m)
-        self.extended_omega_inv = pow(ew, m - 2, m)
+        self.omega_inv = pow(w, -1, m)
+        self.extended_omega_inv = pow(ew, -1, m)
         assert pow(zeta, 3, m) == 1 and zeta != 1, "zeta must be a primitive cube root of unity"
         self.g_coset = zeta
         self.g_coset_inv = zeta * zeta % m
-        self.ifft_divisor = pow((1 << k) % m, m - 2, m)
-        self.extended_ifft_divisor = pow((1 << ext_k) % m, m - 2, m)
+        self.ifft_divisor = pow((1 << k) % m, -1, m)
+        self.extended_ifft_divisor = pow((1 << ext_k) % m, -1, m)
         # t(X) = X^n - 1 over the coset, inverted (domain.rs:86-128): 2^(ext_k - k) values, then it repeats
         orig, step = pow(zeta, self.n, m), pow(ew, self.n, m)
         t, cur = [], orig

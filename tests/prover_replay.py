@@ -307,7 +307,7 @@ def run(arm, inp, k, omega):
         T.write_point(pt)
     # 5. evaluations at x (advice at x and x*omega, z at x, x*omega, x*omega^-1... : 3 + 3 + 3 + 4 + 1 = 14 serial Horner loops)
     x = T.squeeze_challenge()
-    xw, xwi = x * omega % m, x * pow(omega, m - 2, m) % m
+    xw, xwi = x * omega % m, x * pow(omega, -1, m) % m
     ev_polys = adv + adv + [z, z, z] + hp + [rnd]
     ev_points = [x] * 3 + [xw] * 3 + [x, xw, xwi] + [x] * 4 + [x]
     evals = arm.evals(ev_polys, ev_points)
@@ -359,7 +359,7 @@ def run(arm, inp, k, omega):
 
     ls, rs, c = arm.ipa(pp, x3, zc, challenge, inp["l_rand"], inp["r_rand"])
     for j, u in enumerate(us):                               # :143-144
-        fsyn = (fsyn + inp["l_rand"][j] * pow(u, m - 2, m) + inp["r_rand"][j] * u) % m
+        fsyn = (fsyn + inp["l_rand"][j] * pow(u, -1, m) + inp["r_rand"][j] * u) % m
     T.write_scalar(c)                                        # :150
     T.write_scalar(fsyn)                                     # :151
     arm.sync()
