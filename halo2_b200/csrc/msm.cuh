@@ -544,20 +544,38 @@ template <class P, class PS> struct Msm {
     }
 
     // level 0: one work item
-    template <class MADD = SerialAdd> static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
+    static H2_HD affine ref_point(const MsmPlan &p, const MsmBuffers &M, uint32_t ref) {
+        if (p.glv) return ld_affine(((ref >> 30) & 1u ? M.bases_phi : M.bases) + (ref & 0x3fffffffu));
+        return ld_affine(M.bases + (ref & 0x7fffffffu));
+    }
+    // AHEAD: the small-problem kernels (lanes cooperating on one item; the kernel lasts as long as its longest chain) fetch
+    // the next reference and its point BEFORE the current addition, so the dependent reference -> point gather (~1.2 us) runs
+    // under the addition's multiplies instead of between two of them.  The throughput kernel (one thread per item, 20 warps per
+    // SM to hide latency, 96 registers) keeps the plain loop: 16 more live registers would cost it a CTA per SM.
+    template <class MADD = SerialAdd, bool AHEAD = false> static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
         if (p.ba && !M.flags[1]) return;             // the batched-affine rounds + accum0_pts_body did the work
         if (t >= M.size_hist[p.T + 1]) return;
         uint2 it = M.items[t];
         const uint32_t g = it.x, start = it.y, lo = bucket_lo(p, M, g), hi = bucket_hi(p, M, g);
         const uint32_t end = start + p.T < hi ? start + p.T : hi;
         xyzz acc = xyzz_identity();
-        for (uint32_t pos = start; pos < end; pos++) {
-            uint32_t ref = M.refs[pos];
-            affine b;
-            if (p.glv) b = ld_affine(((ref >> 30) & 1u ? M.bases_phi : M.bases) + (ref & 0x3fffffffu));
-            else b = ld_affine(M.bases + (ref & 0x7fffffffu));
-            if (ref >> 31) b.y = fe_neg<P>(b.y);
-            MADD::template add_mixed<P>(acc, b);
+        if (AHEAD) {
+            uint32_t ref = M.refs[start];
+            affine nxt = ref_point(p, M, ref);
+            for (uint32_t pos = start; pos < end; pos++) {
+                affine b = nxt;
+                const uint32_t neg = ref >> 31;
+                if (pos + 1 < end) { ref = M.refs[pos + 1]; nxt = ref_point(p, M, ref); }
+                if (neg) b.y = fe_neg<P>(b.y);
+                MADD::template add_mixed<P>(acc, b);
+            }
+        } else {
+            for (uint32_t pos = start; pos < end; pos++) {
+                const uint32_t ref = M.refs[pos];
+                affine b = ref_point(p, M, ref);
+                if (ref >> 31) b.y = fe_neg<P>(b.y);
+                MADD::template add_mixed<P>(acc, b);
+            }
         }
         Flusher F; F.M = &M; F.p = &p;
         F.flush(g, start, end, acc, p.part_offset[1] + item_slot(p, start, start == lo));
@@ -600,6 +618,22 @@ template <class P, class PS> struct Msm {
         const uint32_t L = 1u << p.l0;
         const xyzz *A = M.bucket_sum + (uint64_t)w * p.B + (uint64_t)u * L;
         xyzz run = xyzz_identity(), acc = xyzz_identity();
+        if (p.chunks == 1) {
+            // one bucket array (everything but a chunked upload): bucket i - 1 is fetched before the two additions of
+            // bucket i, off the dependent chain (small problems run this on a handful of otherwise idle warps)
+            xyzz nxt = ld_xyzz(A + (L - 1));
+            for (uint32_t i = L - 1; i > 0; i--) {
+                const xyzz cur = nxt;
+                nxt = ld_xyzz(A + (i - 1));
+                ADD::template add<P>(run, cur);
+                ADD::template add<P>(acc, run);
+            }
+            ADD::template add<P>(run, nxt);
+            uint64_t o1 = (uint64_t)w * p.m1 + u;
+            st_xyzz(M.ra_t + o1, run);
+            st_xyzz(M.ra_e + o1, acc);
+            return;
+        }
         for (uint32_t i = L - 1; i > 0; i--) {
             for (uint32_t k = 0; k < p.chunks; k++) ADD::template add<P>(run, ld_xyzz(A + k * p.G + i));
             ADD::template add<P>(acc, run);
@@ -850,12 +884,12 @@ template <class P, class PS> __global__ void __launch_bounds__(128, 5) msm_accum
 // quad runs that chain 2.5x faster (4 multiply latencies per mixed addition instead of 10)
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_quad_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    Msm<P, PS>::template accum0_body<QuadAdd>(p, M, t);
+    Msm<P, PS>::template accum0_body<QuadAdd, true>(p, M, t);
 }
 // ... or one PAIR of lanes per work item (xyzz_add_mixed_pair: no idle multiply slots, 5 multiply latencies per addition)
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_pair_kernel(const MsmPlan p, const MsmBuffers M) {
     uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    Msm<P, PS>::template accum0_body<PairAdd>(p, M, t);
+    Msm<P, PS>::template accum0_body<PairAdd, true>(p, M, t);
 }
 // ... and WAYS quads per work item (test hook h2_test_set_accum_ways; NOT the default: measured at k = 14, c = 15 -- ~17
 // references per bucket, the fullest ~35 -- 2 / 4 ways change a commit by -9 % / 0 % and the IPA opening by +6 % / +32 %: the
@@ -952,9 +986,15 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_r0_kerne
     uint64_t wb = tid / rows;
     uint32_t w = (uint32_t)(wb / p.nb0), blk = (uint32_t)(wb % p.nb0);
     xyzz v = xyzz_identity();
-    for (uint32_t lane = 0; lane < (1u << H2_R0_LOG); lane++) {
-        if (row >= 2 && !((lane >> (row - 2)) & 1u)) continue;
-        xyzz c = Msm<P, PS>::r0_contrib(p, M, w, blk, row, lane);
+    // the contributing lanes of this row, each operand fetched one addition ahead of its use
+    const uint32_t want = row >= 2 ? 1u << (row - 2) : 0u;
+    auto next_lane = [&](uint32_t l) { while (l < (1u << H2_R0_LOG) && (l & want) != want) l++; return l; };
+    uint32_t lane = next_lane(0);
+    xyzz nxt = lane < (1u << H2_R0_LOG) ? Msm<P, PS>::r0_contrib(p, M, w, blk, row, lane) : xyzz_identity();
+    while (lane < (1u << H2_R0_LOG)) {
+        const xyzz c = nxt;
+        lane = next_lane(lane + 1);
+        if (lane < (1u << H2_R0_LOG)) nxt = Msm<P, PS>::r0_contrib(p, M, w, blk, row, lane);
         xyzz_add_quad<P>(v, c);
     }
     st_xyzz(M.r0 + ((uint64_t)w * p.nb0 + blk) * H2_R0_ROWS + row, v);
@@ -965,8 +1005,10 @@ template <class P, class PS> __global__ void __launch_bounds__(4 * H2_R1_QUADS) 
     __shared__ xyzz sh[H2_R1_QUADS];
     const uint32_t w = blockIdx.x / p.r1_rows, row = blockIdx.x % p.r1_rows, qd = threadIdx.x >> 2;
     xyzz v = xyzz_identity();
+    xyzz nxt = qd < p.nb0 ? Msm<P, PS>::r1_contrib(p, M, w, row, qd) : xyzz_identity();
     for (uint32_t blk = qd; blk < p.nb0; blk += H2_R1_QUADS) {
-        xyzz c = Msm<P, PS>::r1_contrib(p, M, w, row, blk);
+        const xyzz c = nxt;
+        if (blk + H2_R1_QUADS < p.nb0) nxt = Msm<P, PS>::r1_contrib(p, M, w, row, blk + H2_R1_QUADS);
         xyzz_add_quad<P>(v, c);
     }
     quad_tree_sum<P>(sh, v, qd, H2_R1_QUADS);
