@@ -618,9 +618,9 @@ template <class P, class PS> struct Msm {
         const uint32_t L = 1u << p.l0;
         const xyzz *A = M.bucket_sum + (uint64_t)w * p.B + (uint64_t)u * L;
         xyzz run = xyzz_identity(), acc = xyzz_identity();
-        if (p.chunks == 1) {
-            // one bucket array (everything but a chunked upload): bucket i - 1 is fetched before the two additions of
-            // bucket i, off the dependent chain (small problems run this on a handful of otherwise idle warps)
+        if (p.chunks == 1 && p.G <= (1ull << 17)) {
+            // small problems (latency-bound: a handful of warps on idle SMs): bucket i - 1 is fetched before the two additions of
+            // bucket i, off the dependent chain (the throughput-bound large reduce keeps the plain loop: measured +1 % slower with it)
             xyzz nxt = ld_xyzz(A + (L - 1));
             for (uint32_t i = L - 1; i > 0; i--) {
                 const xyzz cur = nxt;
