@@ -275,6 +275,7 @@ static void ctx_destroy(Context &C) {
     for (IpaSession *q : C.ipa_pool) { q->p.release(); q->b.release(); q->s.release(); q->scal.release(); q->out.release(); delete q; }
     C.ipa_pool.clear();
     C.stage.destroy();
+    if (C.h_flags) { cudaFreeHost(C.h_flags); C.h_flags = nullptr; }
     cudaEventDestroy(C.ev_scalars_up);
     for (int j = 0; j < H2_MAX_UPLOAD_CHUNKS; j++) { cudaEventDestroy(C.ev_bases_up[j]); cudaEventDestroy(C.ev_scal_up[j]); }
     cudaStreamDestroy(C.copy_stream);
@@ -350,6 +351,12 @@ extern "C" int h2_test_last_msm_flags(uint32_t *out) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(f, g_ctx.last_flags, sizeof f, cudaMemcpyDeviceToHost));
     *out = (f[0] ? 1u : 0u) | (f[1] ? 2u : 0u);
+    return 0;
+}
+// test / A-B hook: fixed-base passes first run without their fallback kernels (1, default) or always run the full pass (0)
+extern "C" int h2_test_set_fast_fixed(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int d = 0; d < H2_MAX_DEVICES; d++) g_ctxs[d].fast_on = on ? 1u : 0u;
     return 0;
 }
 // test hook: CUDA-graph replay of fixed-base MSMs on / off

@@ -48,7 +48,7 @@ static int msm_issue_or_replay(const std::function<int()> &issue, bool graphable
     MsmGraph *ge = nullptr;
     for (auto &e : X.graphs)
         if (e.scalars == d_scalars && e.bases == d_bases && e.out == d_out && e.n == n && e.stride == stride && e.c == c && e.sets == sets &&
-            e.scalars_mont == scalars_mont && e.out_canonical == out_canonical) { ge = &e; break; }
+            e.scalars_mont == scalars_mont && e.out_canonical == out_canonical && e.fast == (X.fast_now ? 1u : 0u)) { ge = &e; break; }
     if (ge && ge->gen != g_alloc_gen) {   // some buffer moved since the capture
         if (ge->exec) cudaGraphExecDestroy(ge->exec);
         ge->exec = nullptr; ge->seen = 0; ge->gen = g_alloc_gen;
@@ -62,7 +62,7 @@ static int msm_issue_or_replay(const std::function<int()> &issue, bool graphable
         }
         MsmGraph e;
         e.scalars = d_scalars; e.bases = d_bases; e.out = d_out; e.n = n; e.stride = stride; e.gen = g_alloc_gen; e.c = c; e.sets = sets;
-        e.scalars_mont = scalars_mont; e.out_canonical = out_canonical;
+        e.scalars_mont = scalars_mont; e.out_canonical = out_canonical; e.fast = X.fast_now ? 1u : 0u;
         X.graphs.push_back(e);
         ge = &X.graphs.back();
     }
@@ -144,6 +144,12 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     MsmPlan p;                       // the whole problem: bucket reduce and window combine
     msm_make_plan(p, n, c, 0, 0, fixed, stride, glv, sets, force_cap);
     p.chunks = K;
+    // fast fixed-base pass: no fallback kernels; the caller checks the flags (fixed_pass_ok) and re-runs with fast_now = false
+    p.fast = (fixed == 1 && !bc && X.fast_now && p.cap != 0) ? 1u : 0u;
+    X.last_fast = p.fast != 0;
+    // ... whose work items are whole buckets: with T >= the bin capacity a bucket can only exceed T by overflowing its bin, so
+    // "a bucket was split" (flags[0], ~5 buckets of a k = 14 commit at T = 32) never fails a pass that the sort flag would not
+    if (p.fast && p.T < p.cap) { p.T = p.cap; p.acc_chunk[0] = p.T; }
     MsmPlan pk[H2_MAX_UPLOAD_CHUNKS];   // one chunk of points: sort, work items, accumulation
     size_t first[H2_MAX_UPLOAD_CHUNKS + 1];
     for (uint32_t j = 0; j <= K; j++) first[j] = chunk_first(n, K, j);
@@ -208,11 +214,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         if (X.scan_blocks.ensure((size_t)((p.G + 1 + per_block - 1) / per_block) * 4 + 16)) return 1;
     }
     issue = [&]() -> int {
-        CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
+        if (!p.fast) CU(cudaMemsetAsync(X.counts.p, 0, K * (p.G + 1) * 4, s));
         CU(cudaMemsetAsync(X.cursor.p, 0, K * 2 * p.G * 4, s));
         CU(cudaMemsetAsync(X.size_hist.p, 0, K * small_words * 4, s));
         CU(cudaMemsetAsync(X.bucket_sum.p, 0, K * p.G * sizeof(xyzz), s));
-        CU(cudaMemsetAsync(X.pkey.p, 0xff, K * part_total * 4, s));
+        if (!p.fast) CU(cudaMemsetAsync(X.pkey.p, 0xff, K * part_total * 4, s));
 
         auto k_bin = msm_bin_kernel<P, PS>;
         auto k_hist = msm_hist_kernel<P, PS>;
@@ -249,9 +255,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
             // are no bins (set here)
             if (q.cap == 0) CU(cudaMemsetAsync(M.flags + 1, 0x01, 4, s));
             else LAUNCH(k_bin, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
-            LAUNCH(k_hist, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
-            if (exclusive_scan_u32(M.counts, q.G + 1, s, M.flags + 1)) return 1;
-            LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            if (!q.fast) {
+                LAUNCH(k_hist, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+                if (exclusive_scan_u32(M.counts, q.G + 1, s, M.flags + 1)) return 1;
+                LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
+            }
             // K4: work items (one per bucket, oversized buckets split), largest first
             LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
             LAUNCH(k_ibases, 1, 32, 0, s, q, M);
@@ -282,9 +290,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
                 LAUNCH(k_accum0, blocks_for(q.max_items, 128), 128, 0, s, q, M);
             }
             prof_end(s);
-            if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
-            if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);
-            if (q.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, q, M);
+            if (!q.fast) {
+                if (q.acc_levels > 1) LAUNCH(k_accumN, blocks_for(q.acc_threads[1], 128), 128, 0, s, q, M, 1u);
+                if (q.acc_levels > 2) LAUNCH(k_accumN, blocks_for(q.acc_threads[2], 128), 128, 0, s, q, M, 2u);
+                if (q.acc_levels > 3) LAUNCH(k_rest, 1, 256, 0, s, q, M);
+            }
         }
         // K5: bucket reduce (adds the per-chunk bucket sums) and window combine
         const MsmBuffers &M = Mk[0];
@@ -304,6 +314,20 @@ int msm_dispatch(int curve, const fe *d_scalars, int scalars_mont, const affine 
     if (curve == H2_CURVE_PALLAS) return msm_run<FpParams, FqParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bc, sets);
     if (curve == H2_CURVE_VESTA) return msm_run<FqParams, FpParams>(d_scalars, scalars_mont, d_bases, n, c, fixed, stride, d_out, out_canonical, s, bc, sets);
     return fail("unknown curve id");
+}
+// The fast fixed-base pass (MsmPlan::fast): callers queue `fixed_pass_flags` right behind the pass (with the copy of the result),
+// synchronise, and ask `fixed_pass_ok`; false = a bin overflowed or a bucket was split, the result is not valid: issue the pass again
+// with X.fast_now = false.
+int fixed_pass_flags(cudaStream_t s) {
+    Context &X = g_ctx;
+    if (!X.last_fast) return 0;
+    if (!X.h_flags) CU(cudaHostAlloc((void **)&X.h_flags, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    CU(cudaMemcpyAsync(X.h_flags, X.last_flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+bool fixed_pass_ok() {
+    Context &X = g_ctx;
+    return !X.last_fast || (X.h_flags[0] == 0 && X.h_flags[1] == 0);
 }
 // window size for a precomputed table over n bases: few references per bucket (short serial chains)
 // for small n, fewer windows for large n
@@ -428,15 +452,22 @@ static int msm_host_common(int curve, const void *scalars, size_t n_scalars, con
         if (n_scalars && upload_async(X.scal_in.p, scalars, n_scalars * sizeof(fe), s)) return 1;
         if (extra_scalar) CU(cudaMemcpyAsync(X.scal_in.as<fe>() + n_scalars, extra_scalar, sizeof(fe), cudaMemcpyHostToDevice, s));
     }
-    int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
-                          repr == H2_REPR_CANONICAL, s, fixed, stride, bc.k ? &bc : nullptr);
-    if (uploader.joinable()) uploader.join();
-    if (up_failed.load()) { cudaStreamSynchronize(s); cudaStreamSynchronize(X.copy_stream); return fail(up_err); }
-    if (rc) return rc;
-    if (d_result_peer) CU(cudaMemcpyPeerAsync(d_result_peer, peer_dev, X.result.p, X.device, sizeof(jacobian), s));
-    else CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
-    if (scratch_release(s)) return 1;
-    CU(cudaStreamSynchronize(s));
+    for (int attempt = 0; attempt < 2; attempt++) {   // fixed-base: the fast pass first, the full one if its flags came back set
+        X.fast_now = attempt == 0 && fixed == 1 && X.fast_on && !bc.k;
+        int rc = msm_dispatch(curve, X.scal_in.as<fe>(), repr == H2_REPR_MONTGOMERY, d_bases, n_total, c, X.result.as<jacobian>(),
+                              repr == H2_REPR_CANONICAL, s, fixed, stride, bc.k ? &bc : nullptr);
+        X.fast_now = false;
+        if (uploader.joinable()) uploader.join();
+        if (up_failed.load()) { cudaStreamSynchronize(s); cudaStreamSynchronize(X.copy_stream); return fail(up_err); }
+        if (rc) return rc;
+        if (d_result_peer) CU(cudaMemcpyPeerAsync(d_result_peer, peer_dev, X.result.p, X.device, sizeof(jacobian), s));
+        else CU(cudaMemcpyAsync(out_xyz, X.result.p, sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+        if (fixed_pass_flags(s)) return 1;
+        if (scratch_release(s)) return 1;
+        CU(cudaStreamSynchronize(s));
+        if (fixed_pass_ok()) break;
+        if (scratch_acquire(s)) return 1;
+    }
     return 0;
 }
 
@@ -547,22 +578,29 @@ static int msm_registered_batch_impl(uint64_t handle, const void *scalars, size_
     const int canon = repr == H2_REPR_CANONICAL;
     uint32_t tc, tmode;
     const affine *tbl = fixed_table(b, &tc, &tmode);
-    int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, tbl, total, tc, X.result.as<jacobian>(),
-                          affine_out ? 0 : canon, s, tmode, b->n, nullptr, (uint32_t)batch);
-    if (rc) return rc;
-    if (affine_out) {
-        if (X.ec_out.ensure(batch * sizeof(affine))) return 1;
-        const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
-        if (b->curve == H2_CURVE_PALLAS)
-            LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
-        else
-            LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
-        CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
-    } else {
-        CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (affine_out && X.ec_out.ensure(batch * sizeof(affine))) return 1;
+    for (int attempt = 0; attempt < 2; attempt++) {   // the fast pass first, the full one if its flags came back set
+        X.fast_now = attempt == 0 && tmode == 1 && X.fast_on;
+        int rc = msm_dispatch(b->curve, d, repr == H2_REPR_MONTGOMERY, tbl, total, tc, X.result.as<jacobian>(),
+                              affine_out ? 0 : canon, s, tmode, b->n, nullptr, (uint32_t)batch);
+        X.fast_now = false;
+        if (rc) return rc;
+        if (affine_out) {
+            const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
+            if (b->curve == H2_CURVE_PALLAS)
+                LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+            else
+                LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+            CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
+        } else {
+            CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+        }
+        if (fixed_pass_flags(s)) return 1;
+        if (scratch_release(s)) return 1;
+        CU(cudaStreamSynchronize(s));
+        if (fixed_pass_ok()) break;
+        if (scratch_acquire(s)) return 1;
     }
-    if (scratch_release(s)) return 1;
-    CU(cudaStreamSynchronize(s));
     return 0;
 }
 
@@ -841,18 +879,27 @@ static int ipa_round_common(uint64_t session, const void *z, const void *l_rand,
     cudaStream_t s = g_ctx.stream;
     if (scratch_acquire(s)) return 1;
     const int oc = affine_out ? 0 : repr == H2_REPR_CANONICAL;
-    int rc = b->curve == H2_CURVE_PALLAS ? ipa_round_impl<FqParams>(q, b, z, l_rand, r_rand, repr, oc, s) : ipa_round_impl<FpParams>(q, b, z, l_rand, r_rand, repr, oc, s);
-    if (rc) return rc;
-    if (affine_out) {
-        if (g_ctx.ec_out.ensure(2 * sizeof(affine))) return 1;
-        const int canon = repr == H2_REPR_CANONICAL;
-        if (b->curve == H2_CURVE_PALLAS) LAUNCH(normalize_kernel<FpParams>, 1, 64, 0, s, (const xyzz *)nullptr, q->out.as<jacobian>(), 0, g_ctx.ec_out.as<affine>(), canon, (uint64_t)2);
-        else LAUNCH(normalize_kernel<FqParams>, 1, 64, 0, s, (const xyzz *)nullptr, q->out.as<jacobian>(), 0, g_ctx.ec_out.as<affine>(), canon, (uint64_t)2);
-        CU(cudaMemcpyAsync(out_lr_xyz, g_ctx.ec_out.p, 2 * sizeof(affine), cudaMemcpyDeviceToHost, s));
-    } else
-    CU(cudaMemcpyAsync(out_lr_xyz, q->out.p, 2 * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
-    if (scratch_release(s)) return 1;
-    CU(cudaStreamSynchronize(s));
+    if (affine_out && g_ctx.ec_out.ensure(2 * sizeof(affine))) return 1;
+    uint32_t tc0, tmode0;
+    fixed_table(b, &tc0, &tmode0);
+    for (int attempt = 0; attempt < 2; attempt++) {   // the fast pass first, the full one if its flags came back set (the prep / inner kernels are idempotent)
+        g_ctx.fast_now = attempt == 0 && tmode0 == 1 && g_ctx.fast_on;
+        int rc = b->curve == H2_CURVE_PALLAS ? ipa_round_impl<FqParams>(q, b, z, l_rand, r_rand, repr, oc, s) : ipa_round_impl<FpParams>(q, b, z, l_rand, r_rand, repr, oc, s);
+        g_ctx.fast_now = false;
+        if (rc) return rc;
+        if (affine_out) {
+            const int canon = repr == H2_REPR_CANONICAL;
+            if (b->curve == H2_CURVE_PALLAS) LAUNCH(normalize_kernel<FpParams>, 1, 64, 0, s, (const xyzz *)nullptr, q->out.as<jacobian>(), 0, g_ctx.ec_out.as<affine>(), canon, (uint64_t)2);
+            else LAUNCH(normalize_kernel<FqParams>, 1, 64, 0, s, (const xyzz *)nullptr, q->out.as<jacobian>(), 0, g_ctx.ec_out.as<affine>(), canon, (uint64_t)2);
+            CU(cudaMemcpyAsync(out_lr_xyz, g_ctx.ec_out.p, 2 * sizeof(affine), cudaMemcpyDeviceToHost, s));
+        } else
+            CU(cudaMemcpyAsync(out_lr_xyz, q->out.p, 2 * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+        if (fixed_pass_flags(s)) return 1;
+        if (scratch_release(s)) return 1;
+        CU(cudaStreamSynchronize(s));
+        if (fixed_pass_ok()) break;
+        if (scratch_acquire(s)) return 1;
+    }
     q->folded = 0;
     return 0;
 }
@@ -946,27 +993,34 @@ static int msm_registered_polys_impl(uint64_t bases_handle, const uint64_t *poly
         CU(cudaMemcpyAsync(d + j * total, q->buf.p, n * sizeof(fe), cudaMemcpyDeviceToDevice, s));
         if (extra_scalars) CU(cudaMemcpyAsync(d + j * total + n, X.misc.as<fe>() + j, sizeof(fe), cudaMemcpyDeviceToDevice, s));
     }
-    int rc;
     uint32_t tc = 0, tmode = 0;
     const affine *tbl = b->table.p ? fixed_table(b, &tc, &tmode) : nullptr;
     const int canon = repr == H2_REPR_CANONICAL;
-    if (tbl) rc = msm_dispatch(b->curve, d, 1, tbl, total, tc, X.result.as<jacobian>(), affine_out ? 0 : canon, s, tmode, b->n,
-                               nullptr, (uint32_t)batch);
-    else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), affine_out ? 0 : canon, s);
-    if (rc) return rc;
-    if (affine_out) {
-        if (X.ec_out.ensure(batch * sizeof(affine))) return 1;
-        const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
-        if (b->curve == H2_CURVE_PALLAS)
-            LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
-        else
-            LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
-        CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
-    } else {
-        CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+    if (affine_out && X.ec_out.ensure(batch * sizeof(affine))) return 1;
+    for (int attempt = 0; attempt < 2; attempt++) {   // the fast pass first, the full one if its flags came back set
+        int rc;
+        X.fast_now = attempt == 0 && tbl && tmode == 1 && X.fast_on;
+        if (tbl) rc = msm_dispatch(b->curve, d, 1, tbl, total, tc, X.result.as<jacobian>(), affine_out ? 0 : canon, s, tmode, b->n,
+                                   nullptr, (uint32_t)batch);
+        else rc = msm_dispatch(b->curve, d, 1, b->buf.as<affine>(), total, 0, X.result.as<jacobian>(), affine_out ? 0 : canon, s);
+        X.fast_now = false;
+        if (rc) return rc;
+        if (affine_out) {
+            const uint32_t nb = blocks_for((batch + H2_NORM_CHUNK - 1) / H2_NORM_CHUNK, 64);
+            if (b->curve == H2_CURVE_PALLAS)
+                LAUNCH(normalize_kernel<FpParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+            else
+                LAUNCH(normalize_kernel<FqParams>, nb, 64, 0, s, (const xyzz *)nullptr, X.result.as<jacobian>(), 0, X.ec_out.as<affine>(), canon, (uint64_t)batch);
+            CU(cudaMemcpyAsync(out_xyz, X.ec_out.p, batch * sizeof(affine), cudaMemcpyDeviceToHost, s));
+        } else {
+            CU(cudaMemcpyAsync(out_xyz, X.result.p, batch * sizeof(jacobian), cudaMemcpyDeviceToHost, s));
+        }
+        if (fixed_pass_flags(s)) return 1;
+        if (scratch_release(s)) return 1;
+        CU(cudaStreamSynchronize(s));
+        if (fixed_pass_ok()) break;
+        if (scratch_acquire(s)) return 1;
     }
-    if (scratch_release(s)) return 1;
-    CU(cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -77,6 +77,7 @@ struct MsmGraph {
     const void *scalars, *bases, *out;
     size_t n; uint64_t stride, gen;
     uint32_t c, sets; int scalars_mont, out_canonical;
+    uint32_t fast = 0;
     uint32_t seen = 0; uint64_t launches = 0, stamp = 0;
     cudaGraphExec_t exec = nullptr;
 };
@@ -106,7 +107,13 @@ struct Context {
     cudaEvent_t last_use = nullptr;
     bool have_last = false;
     uint32_t window_override = 0;
-    const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook)
+    const uint32_t *last_flags = nullptr;    // device flags of the most recent MSM (test hook; the fast fixed-base pass's validity check)
+    uint32_t fast_on = 1;                    // fixed-base passes over resident tables first run WITHOUT the fallback kernels (exact sort: histogram, 3 scan
+                                             // kernels, scatter; partial merges: 3 kernels) and their two memsets -- 10 of ~27 graph nodes that do nothing on
+                                             // ordinary inputs; the two device flags come back with the result and a set flag re-runs the full pass
+    bool fast_now = false;                   // ... the pass being issued is such a fast one
+    bool last_fast = false;                  // ... the most recent pass was
+    uint32_t *h_flags = nullptr;             // pinned host copy of the two flags
     uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
     uint32_t accum_ways = 0;                 // lanes per work item in the small-problem accumulation: 0 = a PAIR (default: 10 lane-multiplies per addition at

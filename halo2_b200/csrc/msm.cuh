@@ -63,6 +63,8 @@ struct MsmPlan {
     uint64_t G;          // total buckets = Wb * B
     uint64_t max_refs;   // n * W (x 2 with the GLV split)
     uint32_t T;          // references per work item (larger buckets are split)
+    uint32_t fast;       // fixed-base pass WITHOUT the fallback kernels (exact sort, partial merges): valid only if the device flags stay
+                         // clear -- the host checks them with the result and re-runs the full pass otherwise (capi_msm.cu)
     uint32_t ba;         // batched-affine rounds before the XYZZ chain (0: none), see Msm::ba_round_body
     uint32_t ba_m[4];    // work items per thread in round r = 1 .. ba (index r - 1)
     uint64_t max_items;  // upper bound of work items = G + max_refs / T
@@ -101,6 +103,7 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
                           uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1, uint32_t force_cap = 0) {
     p.n = n; p.c = c; p.chunks = 1;
+    p.fast = 0;
     p.ba = 0; p.ba_m[0] = p.ba_m[1] = p.ba_m[2] = p.ba_m[3] = 1;
     p.glv = fixed ? 0u : glv;
     // GLV sub-scalars are < 2^127 (glv.cuh): with W c >= 128 the top window's raw digit is < 2^(c-1), so it
@@ -554,6 +557,7 @@ template <class P, class PS> struct Msm {
     // SM to hide latency, 96 registers) keeps the plain loop: 16 more live registers would cost it a CTA per SM.
     template <class MADD = SerialAdd, bool AHEAD = false> static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
         if (p.ba && !M.flags[1]) return;             // the batched-affine rounds + accum0_pts_body did the work
+        if (p.fast && M.flags[1]) return;            // a bin overflowed and no exact sort follows: the references are not usable (the host re-runs)
         if (t >= M.size_hist[p.T + 1]) return;
         uint2 it = M.items[t];
         const uint32_t g = it.x, start = it.y, lo = bucket_lo(p, M, g), hi = bucket_hi(p, M, g);
@@ -845,6 +849,7 @@ template <class P, class PS> __global__ void __launch_bounds__(256) msm_phi_kern
 }
 // work-item construction: size histogram, bases, then placement (descending size)
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_hist_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (p.fast && M.flags[1]) return;            // fast pass after a bin overflow: no exact sort follows, the counts are not there (the host re-runs)
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nfull = 0, rem = 0;
     if (g < p.G) Msm<P, PS>::count_items(p, M, g, nfull, rem);
@@ -855,6 +860,7 @@ template <class P, class PS> __global__ void msm_item_bases_kernel(const MsmPlan
     if (threadIdx.x == 0 && blockIdx.x == 0) Msm<P, PS>::size_bases_body(p, M);
 }
 template <class P, class PS> __global__ void __launch_bounds__(256) msm_item_place_kernel(const MsmPlan p, const MsmBuffers M) {
+    if (p.fast && M.flags[1]) return;
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nfull = 0, rem = 0, lo = 0;
     if (g < p.G) { Msm<P, PS>::count_items(p, M, g, nfull, rem); lo = Msm<P, PS>::bucket_lo(p, M, g); }
@@ -899,6 +905,7 @@ template <class P, class PS> __global__ void __launch_bounds__(128) msm_accum0_p
 // at the group-wide shuffles.
 template <class P, class PS, int WAYS> __global__ void __launch_bounds__(128) msm_accum0_multi_kernel(const MsmPlan p, const MsmBuffers M) {
     const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / (4 * WAYS);
+    if (p.fast && M.flags[1]) return;
     if (t >= M.size_hist[p.T + 1]) return;
     const uint32_t lane = threadIdx.x & 31u, h = (lane >> 2) & (WAYS - 1);
     const uint32_t gmask = (WAYS == 8 ? 0xffffffffu : ((1u << (4 * WAYS)) - 1u) << (lane & ~(4u * WAYS - 1u)));

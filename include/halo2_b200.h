@@ -302,6 +302,10 @@ int h2_test_set_copy_threads(int threads, int nt_stores);
  * double buffered) wherever the pass geometry allows; 0 (default -- measured faster on B200): the classic
  * load / compute / store kernel.  bench.py times both. */
 int h2_test_set_ntt_tma(int on);
+/* Fixed-base MSMs over resident window tables first run WITHOUT their fallback kernels (the exact two-pass sort and the merge of
+ * split buckets: 10 of ~27 graph nodes that do nothing on ordinary scalars); the two device flags come back with the result
+ * and a set flag -- a constant or 0/1 column, for instance -- re-runs the full pass.  1 (default) / 0 = always the full pass. */
+int h2_test_set_fast_fixed(int on);
 /* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
  * parameters on (default); 0 issues every launch individually. */
 int h2_test_set_graphs(int on);

@@ -270,3 +270,48 @@ def test_lookup_permuted_columns(eng, field):
             b.close()
         for p in (a, t, oa, ot):
             p.close()
+
+
+def test_fast_fixed_base_pass_and_its_fallback(eng):
+    """Fixed-base passes run without their fallback kernels first and re-run in full when a device flag comes back set
+    (h2_test_set_fast_fixed): ordinary polynomials take the fast pass, constant / 0-1 / all-equal columns overflow the sort bins
+    and take the re-run -- same points either way, through every entry point that issues such a pass (single and batched commits,
+    commits of resident polynomials with batch_normalize, the IPA round loop), eager, captured and replayed."""
+    import halo2_b200 as h2
+    from halo2_b200 import lib as L
+    lib = L.init()
+    curve, c, k = "vesta", pasta.VESTA, 9
+    n = 1 << k
+    g = cref.gen_points(curve, SEED + 700, n + 2)
+    polys = [cref.gen_scalars(c.scalar, SEED + 701, n), cref.ints_to_bytes([0] * n), cref.ints_to_bytes([1] * n),
+             cref.ints_to_bytes([i & 1 for i in range(n)]), cref.ints_to_bytes([c.r - 1] * n), cref.gen_scalars(c.scalar, SEED + 702, n)]
+    blind = h2.Blind(11)
+    wants = [cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([p, cref.ints_to_bytes([11])]), g[:n + 1])) for p in polys]
+    ch = pasta.gen_scalars(c.scalar, SEED + 703, k)
+    lr = pasta.gen_scalars(c.scalar, SEED + 704, k)
+    ipa_want = {}
+    for name, pp in (("random", polys[0]), ("constant", polys[4])):
+        ipa_want[name] = cref.ipa_rounds(curve, g, k, pp, 3, 5, cref.ints_to_bytes(ch), cref.ints_to_bytes(lr), cref.ints_to_bytes(lr))
+    try:
+        for on in (1, 0, 1):
+            L.check(lib.h2_test_set_fast_fixed(on))
+            params = h2.Params(curve, k, g[:n], g[:n], g[n:n + 1], u=g[n + 1:n + 2])
+            for rep in range(3):
+                assert [_affine(curve, params.commit(p, blind)) for p in polys] == wants, (on, rep)
+            assert [_affine(curve, m) for m in params.commit_many(polys, [blind] * len(polys))] == wants, on
+            res = [h2.ResidentPoly(c.scalar, n, p) for p in polys]
+            for rep in range(3):
+                aff = params.commit_resident_affine(res, [blind] * len(res))
+                assert [cref.bytes_to_affine(a) for a in aff] == wants, (on, rep)
+            for name, pp in (("random", polys[0]), ("constant", polys[4])):
+                wl, wr, wc = ipa_want[name]
+                for rep in range(2):
+                    gl_, gr_, gc_ = params.ipa_rounds(pp, 3, 5, lambda j, a, b: ch[j], lr, lr)
+                    assert gc_ == wc, (on, name)
+                    for j in range(k):
+                        assert (cref.jac_to_affine(curve, gl_[j]) == wl[j]).all() and (cref.jac_to_affine(curve, gr_[j]) == wr[j]).all(), (on, name, j)
+            for r_ in res:
+                r_.close()
+            params.close()
+    finally:
+        L.check(lib.h2_test_set_fast_fixed(1))
