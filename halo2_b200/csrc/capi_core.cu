@@ -356,7 +356,8 @@ extern "C" int h2_test_last_msm_flags(uint32_t *out) {
 // test / A-B hook: fixed-base passes first run without their fallback kernels (1, default) or always run the full pass (0)
 extern "C" int h2_test_set_fast_fixed(int on) {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (int d = 0; d < H2_MAX_DEVICES; d++) g_ctxs[d].fast_on = on ? 1u : 0u;
+    // on > 1 (tuning): log2 of the bucket count up to which a fast pass takes its buckets in index order (on = 2: never)
+    for (int d = 0; d < H2_MAX_DEVICES; d++) { g_ctxs[d].fast_on = on ? 1u : 0u; if (on > 1) g_ctxs[d].natural_max_buckets = on == 2 ? 0 : 1ull << on; }
     return 0;
 }
 // test hook: CUDA-graph replay of fixed-base MSMs on / off

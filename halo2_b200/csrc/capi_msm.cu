@@ -150,6 +150,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     // ... whose work items are whole buckets: with T >= the bin capacity a bucket can only exceed T by overflowing its bin, so
     // "a bucket was split" (flags[0], ~5 buckets of a k = 14 commit at T = 32) never fails a pass that the sort flag would not
     if (p.fast && p.T < p.cap) { p.T = p.cap; p.acc_chunk[0] = p.T; }
+    p.natural = (p.fast && p.G <= X.natural_max_buckets && p.max_refs <= 2 * H2_MSM_QUAD_ACCUM_REFS && X.accum_ways <= 1) ? 1u : 0u;
     MsmPlan pk[H2_MAX_UPLOAD_CHUNKS];   // one chunk of points: sort, work items, accumulation
     size_t first[H2_MAX_UPLOAD_CHUNKS + 1];
     for (uint32_t j = 0; j <= K; j++) first[j] = chunk_first(n, K, j);
@@ -261,9 +262,11 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
                 LAUNCH(k_scatter, blocks_for(q.n * q.sets, 256), 256, 0, s, q, M);
             }
             // K4: work items (one per bucket, oversized buckets split), largest first
-            LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
-            LAUNCH(k_ibases, 1, 32, 0, s, q, M);
-            LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
+            if (!q.natural) {
+                LAUNCH(k_ihist, blocks_for(q.G, 256), 256, 0, s, q, M);
+                LAUNCH(k_ibases, 1, 32, 0, s, q, M);
+                LAUNCH(k_iplace, blocks_for(q.G, 256), 256, 0, s, q, M);
+            }
             if (bc && bc->k) {   // the sort above only needed the scalars
                 for (uint32_t e = (K > 1 ? j : 0); e < (K > 1 ? j + 1 : bc->k); e++) {
                     if (bc->wait_recorded(2 * e + 2)) return fail("msm: the upload of the inputs failed");

@@ -111,6 +111,9 @@ struct Context {
     uint32_t fast_on = 1;                    // fixed-base passes over resident tables first run WITHOUT the fallback kernels (exact sort: histogram, 3 scan
                                              // kernels, scatter; partial merges: 3 kernels) and their two memsets -- 10 of ~27 graph nodes that do nothing on
                                              // ordinary inputs; the two device flags come back with the result and a set flag re-runs the full pass
+    uint64_t natural_max_buckets = 1ull << 14;   // fast passes with up to this many buckets take them in index order (MsmPlan::natural).  Measured at k = 14
+                                             // (one lane pair per bucket): 2^14 buckets (a single commit) 0.379 -> 0.356 ms; 2^15 (an IPA round's two sets, 1.15 waves)
+                                             // 4.60 -> 4.74 ms per opening; 2^16 (4 batched commits) 0.71 -> 0.80 ms: only a pass that is resident at once gains
     bool fast_now = false;                   // ... the pass being issued is such a fast one
     bool last_fast = false;                  // ... the most recent pass was
     uint32_t *h_flags = nullptr;             // pinned host copy of the two flags

@@ -63,6 +63,8 @@ struct MsmPlan {
     uint64_t G;          // total buckets = Wb * B
     uint64_t max_refs;   // n * W (x 2 with the GLV split)
     uint32_t T;          // references per work item (larger buckets are split)
+    uint32_t natural;    // fast pass whose work items are simply the buckets in index order (no size sort: when every lane-group is resident at
+                         // once the kernel lasts as long as the longest bucket whatever the order, and three item kernels go away)
     uint32_t fast;       // fixed-base pass WITHOUT the fallback kernels (exact sort, partial merges): valid only if the device flags stay
                          // clear -- the host checks them with the result and re-runs the full pass otherwise (capi_msm.cu)
     uint32_t ba;         // batched-affine rounds before the XYZZ chain (0: none), see Msm::ba_round_body
@@ -103,7 +105,7 @@ inline uint32_t msm_default_window(uint64_t n, uint32_t glv = 0) {
 inline void msm_make_plan(MsmPlan &p, uint64_t n, uint32_t c, uint32_t force_t = 0, uint32_t force_kn = 0, uint32_t fixed = 0,
                           uint64_t stride = 0, uint32_t glv = 0, uint32_t sets = 1, uint32_t force_cap = 0) {
     p.n = n; p.c = c; p.chunks = 1;
-    p.fast = 0;
+    p.fast = 0; p.natural = 0;
     p.ba = 0; p.ba_m[0] = p.ba_m[1] = p.ba_m[2] = p.ba_m[3] = 1;
     p.glv = fixed ? 0u : glv;
     // GLV sub-scalars are < 2^127 (glv.cuh): with W c >= 128 the top window's raw digit is < 2^(c-1), so it
@@ -558,8 +560,15 @@ template <class P, class PS> struct Msm {
     template <class MADD = SerialAdd, bool AHEAD = false> static H2_HD void accum0_body(const MsmPlan &p, const MsmBuffers &M, uint64_t t) {
         if (p.ba && !M.flags[1]) return;             // the batched-affine rounds + accum0_pts_body did the work
         if (p.fast && M.flags[1]) return;            // a bin overflowed and no exact sort follows: the references are not usable (the host re-runs)
-        if (t >= M.size_hist[p.T + 1]) return;
-        uint2 it = M.items[t];
+        uint2 it;
+        if (p.natural) {                             // item t = bucket t, whole (T >= the bin capacity in a fast pass)
+            if (t >= p.G) return;
+            it = make_uint2((uint32_t)t, bucket_lo(p, M, t));
+            if (bucket_hi(p, M, t) == it.y) return;  // empty bucket: its sum stays the identity the memset wrote
+        } else {
+            if (t >= M.size_hist[p.T + 1]) return;
+            it = M.items[t];
+        }
         const uint32_t g = it.x, start = it.y, lo = bucket_lo(p, M, g), hi = bucket_hi(p, M, g);
         const uint32_t end = start + p.T < hi ? start + p.T : hi;
         xyzz acc = xyzz_identity();

@@ -19,6 +19,9 @@ ways = int(os.environ.get("ACCUM_WAYS", "-1"))
 if ways >= 0:
     L.check(L.init().h2_test_set_accum_ways(ways | (int(os.environ.get("ACCUM_LOG", "0")) << 8)))
     print(f"accum ways = {ways}", flush=True)
+if os.environ.get("FAST"):
+    L.check(L.init().h2_test_set_fast_fixed(int(os.environ["FAST"])))
+    print("fast-fixed setting", os.environ["FAST"], flush=True)
 for c in [int(a) for a in sys.argv[2:]] or [-1, 0, 13, 15, 17]:      # -1: digit-multiples table (direct sum); 0: automatic window
     try:
         t0 = time.perf_counter()
