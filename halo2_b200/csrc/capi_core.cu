@@ -360,6 +360,12 @@ extern "C" int h2_test_set_fast_fixed(int on) {
     for (int d = 0; d < H2_MAX_DEVICES; d++) { g_ctxs[d].fast_on = on ? 1u : 0u; if (on > 1) g_ctxs[d].natural_max_buckets = on == 2 ? 0 : 1ull << on; }
     return 0;
 }
+// test hook: small polynomials reduce in one CTA each (1, default) or through the level tree like large ones (0)
+extern "C" int h2_test_set_poly_cta(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int d = 0; d < H2_MAX_DEVICES; d++) g_ctxs[d].poly_cta = on ? 1u : 0u;
+    return 0;
+}
 // test hook: CUDA-graph replay of fixed-base MSMs on / off
 extern "C" int h2_test_set_graphs(int on) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -38,6 +38,21 @@ static int polyops_run(int mode, const std::vector<PolyBuf *> &a, const std::vec
         CU(cudaMemcpyAsync(pts, points, batch * sizeof(fe), cudaMemcpyHostToDevice, s));
         if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(batch, 64), 64, 0, s, pts, (uint64_t)batch, 1);
     }
+    if (mode != 1 && n <= (1ull << 16) && n >= 2 && X.poly_cta) {
+        // small polynomials: one CTA per polynomial does the whole reduction (polyops.cuh poly_eval_cta_kernel / poly_kate_cta_kernel)
+        if (mode == 0) {
+            fe *res = X.misc.as<fe>();
+            LAUNCH(poly_eval_cta_kernel<P>, batch, H2_POLY_CTA, 0, s, d_a, (uint64_t)n, (const fe *)pts, res);
+            if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(batch, 64), 64, 0, s, res, (uint64_t)batch, 0);
+            CU(cudaMemcpyAsync(out, res, batch * sizeof(fe), cudaMemcpyDeviceToHost, s));
+            if (scratch_release(s)) return 1;
+            CU(cudaStreamSynchronize(s));
+            return 0;
+        }
+        LAUNCH(poly_kate_cta_kernel<P>, batch, H2_KATE_CTA, 0, s, d_a, (uint64_t)n, (const fe *)pts, (fe *const *)d_c);
+        for (uint32_t b = 0; b < batch; b++) CU(cudaMemsetAsync(c[b]->buf.as<fe>() + (n - 1), 0, sizeof(fe), s));
+        return scratch_release(s);
+    }
     // upward pass: level l + 1 from level l at the point x^(CHUNK^l)
     for (size_t l = 0; l < L; l++) {
         const dim3 grid(blocks_for(m[l + 1], 128), batch);

@@ -810,15 +810,21 @@ def test_poly_reductions(eng, field):
     the restated loops, at the chunk-tree's edge sizes and at k = 14; kate_division's defining identity; misuse fails."""
     from halo2_b200 import lib as L
     m = pasta.FIELDS[field]
-    for n in (1, 2, 32, 33, 1025, 1 << 14):
-        a = cref.gen_scalars(field, SEED + 800 + n, n)
-        c = cref.gen_scalars(field, SEED + 801 + n, n)
-        ai, ci = cref.bytes_to_ints(a), cref.bytes_to_ints(c)
-        x = pasta.gen_scalars(field, SEED + 802 + n, 1)[0]
-        assert eng.eval_polynomial(a, x, field) == pasta.eval_polynomial(field, ai, x)
-        assert eng.compute_inner_product(a, c, field) == pasta.compute_inner_product(m, ai, ci)
-        q = eng.kate_division(a, x, field)
-        assert cref.bytes_to_ints(q) == pasta.kate_division(field, ai, x)
+    lib = L.init()
+    try:
+        for cta in (1, 0):      # one CTA per polynomial (n <= 2^16) / the level tree: same values
+            L.check(lib.h2_test_set_poly_cta(cta))
+            for n in (1, 2, 3, 32, 33, 511, 1025, 1 << 14) + ((1000, 1 << 16, (1 << 16) + 1) if cta else ()):
+                a = cref.gen_scalars(field, SEED + 800 + n, n)
+                c = cref.gen_scalars(field, SEED + 801 + n, n)
+                ai, ci = cref.bytes_to_ints(a), cref.bytes_to_ints(c)
+                for x in (pasta.gen_scalars(field, SEED + 802 + n, 1)[0], 0, 1):
+                    assert eng.eval_polynomial(a, x, field) == pasta.eval_polynomial(field, ai, x), (cta, n, x)
+                    q = eng.kate_division(a, x, field)
+                    assert cref.bytes_to_ints(q) == pasta.kate_division(field, ai, x), (cta, n, x)
+                assert eng.compute_inner_product(a, c, field) == pasta.compute_inner_product(m, ai, ci)
+    finally:
+        L.check(lib.h2_test_set_poly_cta(1))
     # a batch of resident polynomials, each at its own point (the prover's evaluation loop, plonk/prover.rs: eval_polynomial per
     # column and rotation), x = 0 and x = 1 included; the quotients stay on the device and evaluate to (a(z) - a(x)) / (z - x)
     n, batch = 1 << 12, 5
