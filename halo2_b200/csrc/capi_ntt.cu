@@ -228,16 +228,28 @@ extern "C" int h2_poly_free(uint64_t poly) {
     if (it == X.polys.end()) return fail("h2_poly_free: unknown handle");
     PolyBuf *b = it->second;
     X.polys.erase(it);
-    // every use of a resident polynomial is ordered on the context's stream, and so is its next owner's first write
-    if (X.poly_pool.size() < 96 && X.poly_pool_bytes + b->buf.cap <= ((size_t)4 << 30)) {
-        X.poly_pool.push_back(b);
-        X.poly_pool_bytes += b->buf.cap;
+    // every use of a resident polynomial is ordered on the context's stream, and so is its next owner's first write.
+    // The pool is first-in first-out: when it is full the OLDEST buffers go (sizes an earlier workload left behind must not
+    // pin the pool and push every later free onto the cudaFree + device-sync path: bench.py's replay ran 1.8 ms slower than
+    // the same replay in a fresh process for exactly that reason)
+    if (b->buf.cap > ((size_t)4 << 30)) {
+        cudaSetDevice(X.device);
+        cudaStreamSynchronize(X.stream);
+        b->buf.release();
+        delete b;
         return 0;
     }
-    cudaSetDevice(X.device);
-    cudaStreamSynchronize(X.stream);
-    b->buf.release();
-    delete b;
+    bool synced = false;
+    while (!X.poly_pool.empty() && (X.poly_pool.size() >= 192 || X.poly_pool_bytes + b->buf.cap > ((size_t)4 << 30))) {
+        PolyBuf *old = X.poly_pool.front();
+        X.poly_pool.erase(X.poly_pool.begin());
+        X.poly_pool_bytes -= old->buf.cap;
+        if (!synced) { cudaSetDevice(X.device); cudaStreamSynchronize(X.stream); synced = true; }
+        old->buf.release();
+        delete old;
+    }
+    X.poly_pool.push_back(b);
+    X.poly_pool_bytes += b->buf.cap;
     return 0;
 }
 int convert_field(int field, fe *d, size_t n, int to_mont, cudaStream_t s) {
