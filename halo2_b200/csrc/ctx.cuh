@@ -123,7 +123,9 @@ struct Context {
                                              // 5 multiply latencies), 1 / 2 / 4 = quads (16 slots for 10 products, 4 latencies).  Measured at k = 14, c = 15:
                                              // commit 0.389 (pair) / 0.407 / 0.329-0.36 (2 quads) / 0.361 ms, IPA opening 5.56 (pair) / 5.68 / 6.1 / 7.6 ms --
                                              // the accumulation is bound by lane-multiplies, not by its chains (test hook h2_test_set_accum_ways)
-    uint32_t poly_cta = 1;                   // eval_polynomial / kate_division of polynomials up to 2^16 coefficients in one CTA each (0: the level tree)
+    uint32_t poly_cta = 0;                   // 1: eval_polynomial / kate_division of polynomials up to 2^16 coefficients in one CTA each; 0 (default): the level
+                                             // tree.  Measured in the proof replay: k = 14 evaluations 0.73 (tree) vs 0.78 ms, k = 16 0.86 vs 1.36 ms, quotients
+                                             // 0.40 vs 0.78 ms -- one CTA's 16-64-step serial slices lose to three launches that fill the machine
     uint64_t small_accum_refs = 1ull << 20;  // MSMs with up to this many references accumulate with cooperating lanes (accum_ways); larger ones with a thread per item
     uint32_t ntt_tma = 0;                    // NTT passes: 1 = bulk-copy (TMA) persistent kernel where it applies, 0 = classic kernel.  Measured on
                                              // B200 (profiles/r2e_*): 2^20 0.27-0.30 ms vs 0.215 ms, 2^24 4.77 vs 3.67 ms -- the pass is bound by the

@@ -140,8 +140,8 @@ template <class P> __global__ void __launch_bounds__(128) poly_eval_level_kernel
 }
 // Small polynomials (n <= 2^16: every k <= 16 column) in ONE launch, one CTA per polynomial: thread t runs Horner over its
 // own slice of ceil(n / 1024) coefficients, then the 1024 slice values combine in a shared-memory tree, v_t += x^(len 2^l)
-// v_(t + 2^l): ~16 + 10 dependent multiply-adds instead of three levels of launches (k = 14: 0.14 -> 0.05 ms per call with
-// its copies).  Same field element as the serial loop -- exact arithmetic, any association order.
+// v_(t + 2^l): ~16 + 10 dependent multiply-adds instead of three levels of launches.  OPT-IN (h2_test_set_poly_cta): measured no
+// faster than the level tree inside the proof replay (ctx.cuh).  Same field element as the serial loop -- exact arithmetic.
 #define H2_POLY_CTA 1024
 template <class P> __device__ __forceinline__ fe poly_pow_small(fe x, uint32_t e) {      // x^e, e >= 1 small
     fe r = x;

@@ -306,8 +306,8 @@ int h2_test_set_ntt_tma(int on);
  * split buckets: 10 of ~27 graph nodes that do nothing on ordinary scalars); the two device flags come back with the result
  * and a set flag -- a constant or 0/1 column, for instance -- re-runs the full pass.  1 (default) / 0 = always the full pass. */
 int h2_test_set_fast_fixed(int on);
-/* h2_poly_eval / h2_poly_kate_division on polynomials of up to 2^16 coefficients run in ONE launch, one CTA per polynomial
- * (1, default); 0 = the tree of 32-coefficient levels that larger polynomials use. */
+/* Opt-in: h2_poly_eval / h2_poly_kate_division on polynomials of up to 2^16 coefficients in ONE launch, one CTA per polynomial
+ * (1); 0 (default) = the tree of 32-coefficient levels -- measured faster, see ctx.cuh. */
 int h2_test_set_poly_cta(int on);
 /* Test hook: fixed-base MSMs over resident bases replay a captured CUDA graph from their third call with the same
  * parameters on (default); 0 issues every launch individually. */

@@ -824,7 +824,7 @@ def test_poly_reductions(eng, field):
                     assert cref.bytes_to_ints(q) == pasta.kate_division(field, ai, x), (cta, n, x)
                 assert eng.compute_inner_product(a, c, field) == pasta.compute_inner_product(m, ai, ci)
     finally:
-        L.check(lib.h2_test_set_poly_cta(1))
+        L.check(lib.h2_test_set_poly_cta(0))
     # a batch of resident polynomials, each at its own point (the prover's evaluation loop, plonk/prover.rs: eval_polynomial per
     # column and rotation), x = 0 and x = 1 included; the quotients stay on the device and evaluate to (a(z) - a(x)) / (z - x)
     n, batch = 1 << 12, 5
