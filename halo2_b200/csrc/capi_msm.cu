@@ -344,7 +344,8 @@ static uint32_t table_window(size_t n) {
     if (want <= 9) return 8;
     if (want <= 15) return 15;
     if (want == 16) return 15;        // k = 14: 15 measured better than 16 (IPA opening 5.5 vs 6.2 ms, commit equal; tools/table_sweep.py)
-    if (want <= 18) return 17;
+    if (want <= 18) return 16;        // k = 15, 16: 16 (top window 14 bits) measured against 15 / 17 at k = 16: IPA opening 10.5 vs 11.5 / 10.8 ms, 4 commits 2.01 vs 2.35 / 2.08 ms
+    if (want <= 20) return 17;        // k = 17, 18: at k = 18 17 against 16 / 20: IPA opening 22.4 vs 27.6 / 46.0 ms, commit 1.81 vs 2.06 / 2.17 ms
     return 20;
 }
 static int build_table(BaseSet *b, uint32_t c, cudaStream_t s) {
