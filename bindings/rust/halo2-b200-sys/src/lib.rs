@@ -72,6 +72,27 @@ extern "C" {
     pub fn h2_points_decompress(curve: c_int, bytes: *const c_void, n: usize, repr: c_int, out_xy: *mut c_void) -> c_int;
     pub fn h2_params_lagrange(curve: c_int, g_xy: *const c_void, k: u32, omega_inv: *const c_void, minv: *const c_void, repr: c_int,
                               out_g_lagrange_xy: *mut c_void) -> c_int;
+    // round 2
+    pub fn h2_hash_to_curve(curve: c_int, domain_prefix: *const c_char, messages: *const c_void, msg_len: usize, n: usize, repr: c_int,
+                            out_xy: *mut c_void) -> c_int;
+    pub fn h2_params_new(curve: c_int, k: u32, repr: c_int, out_g_xy: *mut c_void, out_g_lagrange_xy: *mut c_void, out_w_xy: *mut c_void,
+                         out_u_xy: *mut c_void) -> c_int;
+    pub fn h2_msm_registered_batch_affine(handle: u64, scalars: *const c_void, n: usize, extra_scalars: *const c_void, batch: usize,
+                                          repr: c_int, out_xy: *mut c_void) -> c_int;
+    pub fn h2_msm_registered_polys_affine(bases_handle: u64, polys: *const u64, batch: usize, n: usize, extra_scalars: *const c_void,
+                                          repr: c_int, out_xy: *mut c_void) -> c_int;
+    pub fn h2_ipa_begin_poly(bases_handle: u64, k: u32, p_prime_poly: u64, x3: *const c_void, repr: c_int, session: *mut u64) -> c_int;
+    pub fn h2_ipa_round_affine(session: u64, z: *const c_void, l_rand: *const c_void, r_rand: *const c_void, repr: c_int,
+                               out_lr_xy: *mut c_void) -> c_int;
+    pub fn h2_poly_add_at(poly: u64, index: usize, delta: *const c_void, repr: c_int) -> c_int;
+    pub fn h2_poly_copy(dst: u64, dst_off: usize, src: u64, src_off: usize, len: usize) -> c_int;
+    pub fn h2_poly_lookup_permute(input: u64, table: u64, usable_rows: usize, out_input: u64, out_table: u64) -> c_int;
+    pub fn h2_multi_init(ngpu: c_int) -> c_int;
+    pub fn h2_multi_count() -> c_int;
+    pub fn h2_msm_multi_gpu(curve: c_int, scalars: *const c_void, bases_xy: *const c_void, n: usize, repr: c_int, out_xyz: *mut c_void) -> c_int;
+    pub fn h2_multi_bases_register(curve: c_int, bases_xy: *const c_void, n: usize, repr: c_int, handle: *mut u64) -> c_int;
+    pub fn h2_multi_bases_release(handle: u64) -> c_int;
+    pub fn h2_msm_multi_registered(handle: u64, scalars: *const c_void, n: usize, repr: c_int, out_xyz: *mut c_void) -> c_int;
 }
 
 fn check(rc: c_int) {
@@ -389,4 +410,28 @@ impl<C: B200Curve> Drop for ResidentBases<C> {
 /// Call once per process (one process per GPU).
 pub fn init(device: i32) {
     check(unsafe { h2_init(device) });
+}
+
+/// One process, several GPUs: after `init(primary)`, bind `ngpu` devices; `best_multiexp_multi_gpu` then shards every call
+/// (contiguous ranges, a 96-byte partial per device written to the primary over NVLink, one sum there).
+pub fn multi_init(ngpu: i32) {
+    check(unsafe { h2_multi_init(ngpu) });
+}
+/// `best_multiexp` (arithmetic.rs:143-180) over every device bound by `multi_init`.
+pub fn best_multiexp_multi_gpu<C: B200Curve>(coeffs: &[C::Scalar], bases: &[C]) -> C::Curve {
+    assert_eq!(coeffs.len(), bases.len());
+    let (s, b) = (scalars_to_bytes(coeffs), bases_to_bytes(bases));
+    let mut out = [0u8; 96];
+    check(unsafe {
+        h2_msm_multi_gpu(C::CURVE_ID, s.as_ptr() as *const c_void, b.as_ptr() as *const c_void, coeffs.len(), REPR_CANONICAL,
+                         out.as_mut_ptr() as *mut c_void)
+    });
+    point_from_xyz::<C>(&out)
+}
+
+/// `permute_expression_pair` (plonk/lookup/prover.rs:563-647) on two resident Lagrange columns (handles from `h2_poly_alloc`):
+/// the usable rows of `out_input` / `out_table` are written; the caller appends its random blinding rows (:625-627).
+/// Returns false where the reference returns `Error::ConstraintSystemFailure` (:605-608).
+pub fn lookup_permute_resident(input: u64, table: u64, usable_rows: usize, out_input: u64, out_table: u64) -> bool {
+    unsafe { h2_poly_lookup_permute(input, table, usable_rows, out_input, out_table) == 0 }
 }

@@ -17,8 +17,9 @@
  *   ifft / distribute_powers_zeta / coeff_to_extended / extended_to_coeff
  *                      poly/domain.rs:375-383, :357-373, :241-255, :303-325.
  *   best_fft (G = curve point), batch_normalize, g -> g_lagrange
- *                      arithmetic.rs:192-295 at G = C::Curve; poly/commitment.rs:74-101 (Params::new without
- *                      hash_to_curve, which lives in the un-vendored pasta_curves).
+ *                      arithmetic.rs:192-295 at G = C::Curve; poly/commitment.rs:74-101 (Params::new from the generators on).
+ *   permute_expression_pair  plonk/lookup/prover.rs:563-647 (sort + ordered map restated as sorted table + taken marks; serial).
+ *   eval_polynomial, kate_division, Evaluator::evaluate (postfix form): see each section (hash_to_curve is restated in pasta.py only).
  *   IPA round loop     poly/commitment/prover.rs:100-142 with parallel_generator_collapse :154-166 and
  *                      compute_inner_product arithmetic.rs:308-319; the transcript is factored out (challenges and
  *                      randomness are inputs).

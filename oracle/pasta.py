@@ -17,6 +17,7 @@ What it restates (all file:line relative to /root/reference/halo2_proofs/src):
   * point compression and Params::{write, read}   book/src/background/curves.md:203-240, poly/commitment.rs:168-205
   * the IPA round loop       poly/commitment/prover.rs:100-142, :154-166 (transcript factored out: challenges
     and randomness are inputs, the points / scalar written to the transcript are outputs)
+  * permute_expression_pair  plonk/lookup/prover.rs:563-647 (the lookup argument's permuted columns, usable rows only)
 
 Third-party arithmetic that is NOT in the reference tree: crate `pasta_curves 0.5.1`
 (Cargo.lock:1303-1306), `ff 0.13.0`, `group 0.13.0`.  Its published algorithm is restated
