@@ -656,3 +656,35 @@ def test_emul_hash_to_curve(emu, curve):
         assert emu.emu_hash_to_curve(cref.CURVE_ID[curve], b"z.cash:test", cref._p(buf), ml, 0, ctypes.c_uint64(0), ctypes.c_uint64(2), cref._p(out)) == 0
         assert [cref.bytes_to_affine(o) for o in out] == [h(m) for m in ms]
     assert emu.emu_hash_to_curve(cref.CURVE_ID[curve], b"p" * 250, None, 0, 1, ctypes.c_uint64(0), ctypes.c_uint64(1), cref._p(out)) == 1
+
+
+@pytest.mark.parametrize("field", ["fp", "fq"])
+def test_emul_lookup_permute(emu, field):
+    """The lookup permutation's kernel bodies (lookup.cuh) run serially == the oracle's permute_expression_pair
+    (plonk/lookup/prover.rs:563-647): sizes around the powers of two of the bitonic network, one / few / all-distinct table
+    values, small integers (the high limbs of the keys tie), rows past usable_rows untouched, a missing value fails."""
+    import random
+    m = pasta.FIELDS[field]
+    rnd = random.Random(9)
+    for n, u, distinct, small in ((4, 1, 1, True), (4, 2, 2, False), (8, 5, 3, True), (20, 16, 16, False), (40, 33, 7, True), (70, 64, 1, False),
+                                  (300, 257, 100, True), (300, 290, 290, False)):
+        pool = [rnd.randrange(1 << 10) if small else rnd.randrange(m) for _ in range(distinct)]
+        tab = (pool + [rnd.choice(pool) for _ in range(u)])[:u]
+        rnd.shuffle(tab)
+        inp = [rnd.choice(tab) for _ in range(u)]
+        tail = [rnd.randrange(m) for _ in range(n - u)]
+        marker = [7000 + i for i in range(n)]
+        oa, ot = cref.ints_to_bytes(marker), cref.ints_to_bytes(marker)
+        rc = emu.emu_lookup_permute(cref.FIELD_ID[field], cref._p(cref.ints_to_bytes(inp + tail)), cref._p(cref.ints_to_bytes(tab + tail)),
+                                    ctypes.c_size_t(n), ctypes.c_size_t(u), cref._p(oa), cref._p(ot))
+        assert rc == 0
+        want_a, want_s = pasta.permute_expression_pair(field, inp, tab, u)
+        ga, gs = cref.bytes_to_ints(oa), cref.bytes_to_ints(ot)
+        assert ga[:u] == want_a and gs[:u] == want_s, (n, u, distinct)
+        assert ga[u:] == marker[u:] and gs[u:] == marker[u:]
+        bad = list(inp)
+        bad[u // 2] = (max(tab) + 1) % m
+        if bad[u // 2] not in set(tab):
+            rc = emu.emu_lookup_permute(cref.FIELD_ID[field], cref._p(cref.ints_to_bytes(bad + tail)), cref._p(cref.ints_to_bytes(tab + tail)),
+                                        ctypes.c_size_t(n), ctypes.c_size_t(u), cref._p(oa), cref._p(ot))
+            assert rc == 1
