@@ -304,7 +304,8 @@ int h2_test_set_copy_threads(int threads, int nt_stores);
 int h2_test_set_ntt_tma(int on);
 /* Fixed-base MSMs over resident window tables first run WITHOUT their fallback kernels (the exact two-pass sort and the merge of
  * split buckets: 10 of ~27 graph nodes that do nothing on ordinary scalars); the two device flags come back with the result
- * and a set flag -- a constant or 0/1 column, for instance -- re-runs the full pass.  1 (default) / 0 = always the full pass. */
+ * and a set flag -- a constant or 0/1 column, for instance -- re-runs the full pass.  1 (default) / 0 = always the full pass.
+ * Tuning values: 2 = fast passes never take their buckets in index order; v >= 3 = they do up to 2^v buckets (default 14). */
 int h2_test_set_fast_fixed(int on);
 /* Opt-in: h2_poly_eval / h2_poly_kate_division on polynomials of up to 2^16 coefficients in ONE launch, one CTA per polynomial
  * (1); 0 (default) = the tree of 32-coefficient levels -- measured faster, see ctx.cuh. */
@@ -316,9 +317,13 @@ int h2_test_set_graphs(int on);
 int h2_test_set_ecfft_quad(int on);
 /* Opt-in: large one-shot MSMs add their buckets' points pairwise in AFFINE coordinates first -- `rounds` halving rounds (0 = off,
  * the default; at most 3), one shared inversion per `pairs_per_thread` additions (0 keeps the value) -- and finish with the
- * XYZZ chain.  6 multiplies per addition instead of 10, but measured no faster on B200. */
+ * XYZZ chain.  6 multiplies per addition instead of 10, but measured no faster on B200.  Tuning: bits 8.. of
+ * `rounds` select the kernel variant + 1 (gather chunk of 4 / 2 pairs at 4 / 5 CTAs per SM); bit 16 of `pairs_per_thread` keeps that
+ * many pairs per thread in every round instead of keeping the thread count. */
 int h2_test_set_batched_affine(uint32_t rounds, uint32_t pairs_per_thread);
-/* Lanes per work item in the accumulation of small MSMs: 1, 2 or 4 quads, or 0 = one pair of lanes (see the default in ctx.cuh). */
+/* Lanes per work item in the accumulation of small MSMs: 1, 2 or 4 quads, or 0 = one pair of lanes (see the default in ctx.cuh).
+ * Tuning: bits 8.. of `ways`, when non-zero, set log2 of the reference count up to which lanes cooperate (default 20; fixed-base
+ * passes use twice that). */
 int h2_test_set_accum_ways(uint32_t ways);
 /* Self-test kernels used by tests/: out[i] = a[i] (op) b[i] on the device, canonical bytes,
  * host buffers.  op: 0 add, 1 sub, 2 mul, 3 inverse(a) by the Fermat ladder,
