@@ -377,7 +377,8 @@ extern "C" int h2_test_set_graphs(int on) {
 extern "C" int h2_test_set_accum_ways(uint32_t ways) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (ways >> 8) { g_ctx.small_accum_refs = 1ull << (ways >> 8); ways &= 0xffu; }   // tuning: bits 8.. = log2 of the reference count up to which lanes cooperate
-    if (ways != 0 && ways != 1 && ways != 2 && ways != 4) return fail("h2_test_set_accum_ways: 0 (a pair of lanes), 1, 2 or 4 (quads)");
+    if (ways != 0 && ways != 1 && ways != 2 && ways != 4 && ways != 12 && ways != 14)
+        return fail("h2_test_set_accum_ways: 0 (a pair of lanes), 1, 2 or 4 (quads), 12 / 14 (2 / 4 independent lanes per item)");
     g_ctx.accum_ways = ways;
     for (auto &ge : g_ctx.graphs) if (ge.exec) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; ge.seen = 0; }
     return 0;

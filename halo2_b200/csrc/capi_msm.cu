@@ -150,7 +150,7 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
     // ... whose work items are whole buckets: with T >= the bin capacity a bucket can only exceed T by overflowing its bin, so
     // "a bucket was split" (flags[0], ~5 buckets of a k = 14 commit at T = 32) never fails a pass that the sort flag would not
     if (p.fast && p.T < p.cap) { p.T = p.cap; p.acc_chunk[0] = p.T; }
-    p.natural = (p.fast && p.G <= X.natural_max_buckets && p.max_refs <= 2 * H2_MSM_QUAD_ACCUM_REFS && X.accum_ways <= 1) ? 1u : 0u;
+    p.natural = (p.fast && p.G <= X.natural_max_buckets && p.max_refs <= 2 * H2_MSM_QUAD_ACCUM_REFS && (X.accum_ways <= 1 || X.accum_ways >= 12)) ? 1u : 0u;
     MsmPlan pk[H2_MAX_UPLOAD_CHUNKS];   // one chunk of points: sort, work items, accumulation
     size_t first[H2_MAX_UPLOAD_CHUNKS + 1];
     for (uint32_t j = 0; j <= K; j++) first[j] = chunk_first(n, K, j);
@@ -230,6 +230,8 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
         auto k_accum0 = msm_accum0_kernel<P, PS>;
         auto k_accum0q = msm_accum0_quad_kernel<P, PS>;
         auto k_accum0p2 = msm_accum0_pair_kernel<P, PS>;
+        auto k_accum0s2 = msm_accum0_split_kernel<P, PS, 2>;
+        auto k_accum0s4 = msm_accum0_split_kernel<P, PS, 4>;
         auto k_accum0m2 = msm_accum0_multi_kernel<P, PS, 2>;
         auto k_accum0m4 = msm_accum0_multi_kernel<P, PS, 4>;
         auto k_ba = X.ba_variant == 1 ? msm_ba_round_kernel<P, PS, 4, 5> : X.ba_variant == 2 ? msm_ba_round_kernel<P, PS, 2, 4>
@@ -282,6 +284,8 @@ static int msm_run(const fe *d_scalars, int scalars_mont, const affine *d_bases,
                 if (X.accum_ways == 4) LAUNCH(k_accum0m4, blocks_for(q.max_items * 16, 128), 128, 0, s, q, M);
                 else if (X.accum_ways == 2) LAUNCH(k_accum0m2, blocks_for(q.max_items * 8, 128), 128, 0, s, q, M);
                 else if (X.accum_ways == 0) LAUNCH(k_accum0p2, blocks_for(q.max_items * 2, 128), 128, 0, s, q, M);
+                else if (X.accum_ways == 12) LAUNCH(k_accum0s2, blocks_for(q.max_items * 2, 128), 128, 0, s, q, M);
+                else if (X.accum_ways == 14) LAUNCH(k_accum0s4, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);
                 else LAUNCH(k_accum0q, blocks_for(q.max_items * 4, 128), 128, 0, s, q, M);
             }
             else {

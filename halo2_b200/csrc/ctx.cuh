@@ -119,10 +119,12 @@ struct Context {
     uint32_t *h_flags = nullptr;             // pinned host copy of the two flags
     uint32_t sort_bins = 1;                  // single-pass binned sort (0: always the exact two-pass sort)
     uint32_t glv_on = 1;                     // GLV endomorphism split for one-shot / table-less MSMs
-    uint32_t accum_ways = 0;                 // lanes per work item in the small-problem accumulation: 0 = a PAIR (default: 10 lane-multiplies per addition at
-                                             // 5 multiply latencies), 1 / 2 / 4 = quads (16 slots for 10 products, 4 latencies).  Measured at k = 14, c = 15:
-                                             // commit 0.389 (pair) / 0.407 / 0.329-0.36 (2 quads) / 0.361 ms, IPA opening 5.56 (pair) / 5.68 / 6.1 / 7.6 ms --
-                                             // the accumulation is bound by lane-multiplies, not by its chains (test hook h2_test_set_accum_ways)
+    uint32_t accum_ways = 12;                // lanes per work item in the small-problem accumulation: 12 (default) / 14 = 2 / 4 INDEPENDENT lanes, each adding every
+                                             // 2nd / 4th reference serially, partial sums folded by shuffles (msm_accum0_split_kernel); 0 = a cooperating PAIR
+                                             // (10 lane-multiplies per addition, 5 levels); 1 / 2 / 4 = quads.  A cooperative addition is no shorter than a serial
+                                             // one in practice (3.3-4.4 us against 3.6 us), so cutting the longest bucket's chain in two is what helps.  Measured
+                                             // at k = 14, c = 15, same box: commit 0.367 (2 lanes) / 0.411 (pair) / 0.417 ms (4 lanes), 4 batched commits
+                                             // 0.754 / 0.792 / 0.816 ms, IPA opening 4.58 / 4.58 / 4.97 ms; quads earlier: 0.407 ms, 5.68 ms
     uint32_t poly_cta = 0;                   // 1: eval_polynomial / kate_division of polynomials up to 2^16 coefficients in one CTA each; 0 (default): the level
                                              // tree.  Measured in the proof replay: k = 14 evaluations 0.73 (tree) vs 0.78 ms, k = 16 0.86 vs 1.36 ms, quotients
                                              // 0.40 vs 0.78 ms -- one CTA's 16-64-step serial slices lose to three launches that fill the machine

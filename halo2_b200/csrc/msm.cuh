@@ -947,6 +947,56 @@ template <class P, class PS, int WAYS> __global__ void __launch_bounds__(128) ms
         F.flush(g, start, end, acc, p.part_offset[1] + Msm<P, PS>::item_slot(p, start, start == lo));
     }
 }
+// ... or WAYS independent LANES per work item: lane h adds references start + h, start + h + WAYS, ... with the plain serial
+// mixed addition (10 multiplies, no exchange between lanes, next operand fetched ahead), then log2(WAYS) shuffle + full-addition
+// steps fold the partial sums.  A cooperative addition is no shorter than a serial one in practice (a level of the pair / quad
+// forms costs its multiply plus ~0.3-0.7 us of shuffles and selects: 3.3-4.4 us per addition against 3.6 us serial), so what
+// shortens the longest bucket's chain is cutting it into WAYS independent pieces.
+template <class P, class PS, int WAYS> __global__ void __launch_bounds__(128) msm_accum0_split_kernel(const MsmPlan p, const MsmBuffers M) {
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / WAYS;
+    if (p.fast && M.flags[1]) return;
+    const uint32_t lane = threadIdx.x & 31u, h = lane & (WAYS - 1);
+    uint2 it;
+    bool live = true;
+    if (p.natural) {
+        live = t < p.G;
+        it = make_uint2((uint32_t)(live ? t : 0), live ? Msm<P, PS>::bucket_lo(p, M, live ? t : 0) : 0u);
+    } else {
+        live = t < M.size_hist[p.T + 1];
+        it = live ? M.items[t] : make_uint2(0u, 0u);
+    }
+    // lanes of a warp leave together (the shuffles below are warp-wide): a dead group just carries identities
+    const uint32_t g = it.x, start = it.y, lo = Msm<P, PS>::bucket_lo(p, M, g), hi = live ? Msm<P, PS>::bucket_hi(p, M, g) : start;
+    const uint32_t end = start + p.T < hi ? start + p.T : hi;
+    xyzz acc = xyzz_identity();
+    if (start + h < end) {
+        uint32_t ref = M.refs[start + h];
+        affine nxt = Msm<P, PS>::ref_point(p, M, ref);
+        for (uint32_t pos = start + h; pos < end; pos += WAYS) {
+            affine b = nxt;
+            const uint32_t neg = ref >> 31;
+            if (pos + WAYS < end) { ref = M.refs[pos + WAYS]; nxt = Msm<P, PS>::ref_point(p, M, ref); }
+            if (neg) b.y = fe_neg<P>(b.y);
+            xyzz_add_mixed<P>(acc, b);
+        }
+    }
+#pragma unroll
+    for (int step = WAYS / 2; step >= 1; step >>= 1) {
+        xyzz other;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            other.x.v[i] = __shfl_down_sync(0xffffffffu, acc.x.v[i], step, WAYS);
+            other.y.v[i] = __shfl_down_sync(0xffffffffu, acc.y.v[i], step, WAYS);
+            other.zz.v[i] = __shfl_down_sync(0xffffffffu, acc.zz.v[i], step, WAYS);
+            other.zzz.v[i] = __shfl_down_sync(0xffffffffu, acc.zzz.v[i], step, WAYS);
+        }
+        if ((int)h < step) xyzz_add<P>(acc, other);
+    }
+    if (h == 0 && live && end > start) {
+        typename Msm<P, PS>::Flusher F; F.M = &M; F.p = &p;
+        F.flush(g, start, end, acc, p.part_offset[1] + Msm<P, PS>::item_slot(p, start, start == lo));
+    }
+}
 template <class P, class PS> __global__ void __launch_bounds__(128) msm_accumN_kernel(const MsmPlan p, const MsmBuffers M, uint32_t lv) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < p.acc_threads[lv]) Msm<P, PS>::accumN_body(p, M, lv, t);

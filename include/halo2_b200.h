@@ -321,7 +321,8 @@ int h2_test_set_ecfft_quad(int on);
  * `rounds` select the kernel variant + 1 (gather chunk of 4 / 2 pairs at 4 / 5 CTAs per SM); bit 16 of `pairs_per_thread` keeps that
  * many pairs per thread in every round instead of keeping the thread count. */
 int h2_test_set_batched_affine(uint32_t rounds, uint32_t pairs_per_thread);
-/* Lanes per work item in the accumulation of small MSMs: 1, 2 or 4 quads, or 0 = one pair of lanes (see the default in ctx.cuh).
+/* Lanes per work item in the accumulation of small MSMs: 12 / 14 = 2 / 4 independent lanes (12 is the default), 0 = one cooperating
+ * pair of lanes, 1, 2 or 4 = quads (measurements in ctx.cuh).
  * Tuning: bits 8.. of `ways`, when non-zero, set log2 of the reference count up to which lanes cooperate (default 20; fixed-base
  * passes use twice that). */
 int h2_test_set_accum_ways(uint32_t ways);

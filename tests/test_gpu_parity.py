@@ -742,7 +742,7 @@ def test_accum_ways(eng):
     want_one = cref.bytes_to_affine(cref.best_multiexp(curve, kb, pb))
     wants = [cref.bytes_to_affine(cref.best_multiexp(curve, np.concatenate([p, cref.ints_to_bytes([9])]), g)) for p in polys]
     try:
-        for ways in (1, 2, 4, 0):
+        for ways in (1, 2, 4, 0, 12, 14):     # 12 / 14: 2 / 4 independent lanes per item (msm_accum0_split_kernel)
             L.check(lib.h2_test_set_accum_ways(ways))
             params = eng.Params(curve, k, g[:n], g[:n], g[n:])
             for rep in range(3):     # eager, captured, replayed
@@ -752,7 +752,7 @@ def test_accum_ways(eng):
             assert _affine(curve, eng.best_multiexp(kb, pb, curve)) == want_one, ways
         assert lib.h2_test_set_accum_ways(3) != 0
     finally:
-        L.check(lib.h2_test_set_accum_ways(0))
+        L.check(lib.h2_test_set_accum_ways(12))
 
 
 # ------------------------------------------------------------------------------------------ K13
