@@ -3,6 +3,7 @@
 #include "polyops.cuh"
 #include "asteval.cuh"
 #include "lookup.cuh"
+#include "verifier.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // eval_polynomial / compute_inner_product / kate_division on resident polynomials (polyops.cuh)
@@ -339,4 +340,55 @@ extern "C" int h2_poly_lookup_permute(uint64_t input, uint64_t table, size_t usa
     if (usable_rows == 0) return 0;
     if (a->field == H2_FIELD_FP) return lookup_permute_run<FpParams>(a, t, usable_rows, oa, ot);
     return lookup_permute_run<FqParams>(a, t, usable_rows, oa, ot);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// the verifier's MSM: g_scalars resident (verifier.cuh)
+// ------------------------------------------------------------------------------------------------
+// dst[i] (+)= init * prod_{j : bit j of i} u[k - 1 - j], i < 2^k: compute_s (poly/commitment/verifier.rs:156-171); with
+// `accumulate` the add_to_g_scalars of Guard::use_challenges (:36-41, msm.rs:104-113) in the same pass
+template <class P> static int compute_s_run(PolyBuf *d, const void *u, uint32_t k, const void *init, int accumulate, int repr) {
+    Context &X = g_ctx;
+    cudaStream_t s = X.stream;
+    if (scratch_acquire(s)) return 1;
+    if (X.po_pts.ensure((size_t)k * sizeof(fe))) return 1;
+    fe *du = X.po_pts.as<fe>();
+    CU(cudaMemcpyAsync(du, u, (size_t)k * sizeof(fe), cudaMemcpyHostToDevice, s));
+    if (repr == H2_REPR_CANONICAL) LAUNCH(convert_kernel<P>, blocks_for(k, 64), 64, 0, s, du, (uint64_t)k, 1);
+    const uint64_t groups = 1ull << (k - (k < 2 ? k : 2));
+    LAUNCH(verifier_compute_s_kernel<P>, blocks_for(groups, 128), 128, 0, s, d->buf.as<fe>(), (const fe *)du, k, host_to_mont<P>(init, repr), accumulate);
+    return scratch_release(s);
+}
+extern "C" int h2_poly_compute_s(uint64_t dst, const void *u, uint32_t k, const void *init, int accumulate, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *d = find_poly(dst);
+    if (!d) return fail("h2_poly_compute_s: unknown polynomial handle");
+    if (k == 0) return fail("h2_poly_compute_s: no challenges (assert!(!u.is_empty()), poly/commitment/verifier.rs:157)");
+    if (k > 30 || d->len < ((size_t)1 << k)) return fail("h2_poly_compute_s: the polynomial holds fewer than 2^k elements");
+    if (d->field == H2_FIELD_FP) return compute_s_run<FpParams>(d, u, k, init, accumulate, repr);
+    return compute_s_run<FqParams>(d, u, k, init, accumulate, repr);
+}
+// dst[i] = a * dst[i] + b * src[i], i < n (src == 0: dst[i] *= a): MSM::scale and the g_scalars part of MSM::add_msm
+// (poly/commitment/msm.rs:126-139, :37-62); BatchVerifier's accumulate_msm (plonk/verifier/batch.rs:83-93) is one call
+extern "C" int h2_poly_scale_add(uint64_t dst, const void *a, uint64_t src, const void *b, size_t n, int repr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (require_ready()) return 1;
+    PolyBuf *d = find_poly(dst), *x = src ? find_poly(src) : nullptr;
+    if (!d || (src && !x)) return fail("h2_poly_scale_add: unknown polynomial handle");
+    if (x == d) return fail("h2_poly_scale_add: src must be another polynomial than dst");
+    if (x && x->field != d->field) return fail("h2_poly_scale_add: the polynomials live in different fields");
+    if (d->len < n || (x && x->len < n)) return fail("h2_poly_scale_add: a polynomial holds fewer than n elements");
+    if (!a || (x && !b)) return fail("h2_poly_scale_add: null factor");
+    if (n == 0) return 0;
+    cudaStream_t s = g_ctx.stream;
+    const fe *sp = x ? x->buf.as<fe>() : nullptr;
+    if (d->field == H2_FIELD_FP)
+        LAUNCH(verifier_scale_add_kernel<FpParams>, blocks_for(n, 256), 256, 0, s, d->buf.as<fe>(), sp, host_to_mont<FpParams>(a, repr),
+               x ? host_to_mont<FpParams>(b, repr) : fe_zero(), (uint64_t)n);
+    else
+        LAUNCH(verifier_scale_add_kernel<FqParams>, blocks_for(n, 256), 256, 0, s, d->buf.as<fe>(), sp, host_to_mont<FqParams>(a, repr),
+               x ? host_to_mont<FqParams>(b, repr) : fe_zero(), (uint64_t)n);
+    return 0;
 }

@@ -183,6 +183,22 @@ int h2_poly_inner_product(const uint64_t *a, const uint64_t *b, size_t batch, si
  * dst[i] must be a different polynomial with room for n - 1 coefficients.  Asynchronous. */
 int h2_poly_kate_division(const uint64_t *dst, const uint64_t *src, size_t batch, size_t n, const void *points, int repr);
 
+/* ---- The verifier's side: MSM<C> (poly/commitment/msm.rs:9-178) with its g_scalars vector resident -------------------------
+ * The verifier's hot path is MSM::eval (msm.rs:142-177): ONE best_multiexp over params.g (2^k resident bases) plus w, u and
+ * the few dozen commitments of the proof.  Its g_scalars is a polynomial handle of the curve's scalar field; `other`, w_scalar
+ * and u_scalar stay with the caller (a few dozen scalars).  eval = h2_msm_registered_polys over the resident g (w_scalar rides
+ * on base index n) + h2_msm over the other terms + h2_point_sum, identity <=> z = 0.
+ *
+ * compute_s (poly/commitment/verifier.rs:156-171): dst[i] = init * prod_{j : bit j of i} u[k - 1 - j] for i < 2^k, u = the
+ * k round challenges u_0 .. u_{k-1} (host, 32 B each).  accumulate != 0 adds into dst instead: the
+ * `msm.add_to_g_scalars(&compute_s(&u, neg_c))` of Guard::use_challenges (:36-41, msm.rs:104-113) without materialising s.
+ * Fails for k == 0 like the reference's assert (:157).  Asynchronous. */
+int h2_poly_compute_s(uint64_t dst, const void *u, uint32_t k, const void *init, int accumulate, int repr);
+/* dst[i] = a * dst[i] + b * src[i] for i < n; src == 0: dst[i] = a * dst[i] (b ignored).  MSM::scale's g_scalars loop
+ * (msm.rs:126-131), the g_scalars part of MSM::add_msm (msm.rs:52-54: a = 1, b = 1), and BatchVerifier's
+ * `acc.scale(random); acc.add_msm(&msm)` (plonk/verifier/batch.rs:83-93) in one pass.  Asynchronous. */
+int h2_poly_scale_add(uint64_t dst, const void *a, uint64_t src, const void *b, size_t n, int repr);
+
 /* Reference sort of the MSM: by default every (point, window) reference is binned in ONE pass into fixed-capacity
  * per-bucket bins, with an automatic fallback to the exact histogram / scan / scatter sort when a bin overflows
  * (heavily repeated scalars).  exact_only != 0 forces the exact sort.  Same result; for A/B runs and tests. */

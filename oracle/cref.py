@@ -35,7 +35,7 @@ def lib() -> ctypes.CDLL:
         for name in ("orc_best_multiexp", "orc_naive_msm", "orc_best_fft", "orc_ifft", "orc_coeff_to_extended",
                      "orc_extended_to_coeff", "orc_field_op", "orc_scalar_mul", "orc_point_add",
                      "orc_jac_to_affine", "orc_on_curve", "orc_gen_scalars", "orc_gen_points", "orc_ec_fft",
-                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds", "orc_eval_polynomial", "orc_kate_division", "orc_ast_eval"):
+                     "orc_batch_normalize", "orc_params_lagrange", "orc_ipa_rounds", "orc_eval_polynomial", "orc_kate_division", "orc_ast_eval", "orc_compute_s"):
             getattr(_lib, name).restype = ctypes.c_int
     return _lib
 
@@ -158,6 +158,15 @@ def eval_polynomial(field: str, poly: np.ndarray, point) -> int:
     out = np.zeros(32, dtype=np.uint8)
     lib().orc_eval_polynomial(FIELD_ID[field], _p(p), ctypes.c_size_t(p.shape[0]), _p(_fe(point)), _p(out))
     return int.from_bytes(out.tobytes(), "little")
+
+
+def compute_s(field: str, u, init) -> np.ndarray:
+    """poly/commitment/verifier.rs:156-171 (the serial doubling loop); u: the k round challenges as ints."""
+    ub = ints_to_bytes(list(u))
+    out = np.zeros((1 << len(u), 32), dtype=np.uint8)
+    if lib().orc_compute_s(FIELD_ID[field], _p(ub), len(u), _p(_fe(int(init))), _p(out)) != 0:
+        raise AssertionError("compute_s: !u.is_empty()")
+    return out
 
 
 def kate_division(field: str, a: np.ndarray, b) -> np.ndarray:

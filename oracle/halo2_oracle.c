@@ -689,6 +689,26 @@ int orc_kate_division(int field, const uint8_t *a, size_t n, const uint8_t *b, u
     return 0;
 }
 
+/* ---------------------------------------------------------------- compute_s (poly/commitment/verifier.rs:156-171)
+ * v[0] = init; for each challenge from the LAST to the first, the filled prefix of length len is copied behind itself and
+ * the copy multiplied by u_j -- the reference's doubling loop, serial.  u: k canonical elements, out: 2^k. */
+int orc_compute_s(int field, const uint8_t *u, uint32_t k, const uint8_t *init, uint8_t *out) {
+    ensure_init(); const field_t *F = &FLD[field];
+    if (k == 0 || k > 30) return 1;                    /* assert!(!u.is_empty()), :157 */
+    size_t n = (size_t)1 << k;
+    fe *v = (fe *)calloc(n, sizeof(fe)), uj;
+    if (!v) return 1;
+    fe_from_bytes(F, &v[0], init);
+    for (uint32_t i = 0; i < k; i++) {                 /* u.iter().rev().enumerate(): len = 1 << i, u_j = u[k - 1 - i] */
+        size_t len = (size_t)1 << i;
+        fe_from_bytes(F, &uj, u + 32 * (size_t)(k - 1 - i));
+        for (size_t t = 0; t < len; t++) fe_mul(F, &v[len + t], &v[t], &uj);
+    }
+    store_vec(F, out, v, n);
+    free(v);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- permute_expression_pair (plonk/lookup/prover.rs:563-647)
  * The usable rows only (the blinding rows, :625-627, are random).  Serial like the reference: sort the input (:577-581); the
  * reference's BTreeMap of table values with counts (:584-591) is restated as the sorted table with one "taken" mark per value

@@ -1083,3 +1083,246 @@ def permute_expression_pair(field: str, input_expression: Sequence[int], table_e
             permuted_table[repeated_rows.pop()] = coeff
     assert not repeated_rows
     return permuted_input, permuted_table
+
+
+# --------------------------------------------------------------------------------------
+# The verifier's side of the polynomial commitment scheme: MSM<C> (poly/commitment/msm.rs:9-178), the opening
+# verifier commitment::verify_proof + Guard + compute_b + compute_s (poly/commitment/verifier.rs:13-171), and the
+# opening prover commitment::create_proof whole (poly/commitment/prover.rs:36-151; ipa_rounds above is its round loop).
+# The transcript is an argument (any object with write_point / write_scalar / read_point / read_scalar /
+# squeeze_challenge on ints and affine tuples); points are Affine tuples, None = the identity.
+# --------------------------------------------------------------------------------------
+class VerifyError(Exception):
+    """Error::OpeningError / Error::SamplingError of poly/commitment/verifier.rs:77-134."""
+
+
+def compute_b(m: int, x: int, u: Sequence[int]) -> int:
+    """verifier.rs:144-153: prod_{i<k} (1 + u_{k-1-i} x^(2^i))."""
+    tmp, cur = 1, x % m
+    for u_j in reversed(list(u)):
+        tmp = tmp * (1 + u_j * cur) % m
+        cur = cur * cur % m
+    return tmp
+
+
+def compute_s(m: int, u: Sequence[int], init: int) -> List[int]:
+    """verifier.rs:156-171: the coefficients of prod_{i<k} (1 + u_{k-1-i} X^(2^i)) times init, by the reference's
+    doubling copies."""
+    u = list(u)
+    assert len(u) > 0
+    v = [0] * (1 << len(u))
+    v[0] = init % m
+    for i, u_j in enumerate(reversed(u)):
+        ln = 1 << i
+        for t in range(ln):
+            v[ln + t] = v[t] * u_j % m
+    return v
+
+
+class MSM:
+    """poly/commitment/msm.rs:9-178.  `other` maps x -> (scalar, y) like the reference's BTreeMap<C::Base, _>; its
+    iteration order (ascending x) only fixes the order of the terms of one multiexp, not the result."""
+
+    def __init__(self, c: Curve, g: Sequence[Affine], w: Affine, u: Affine):
+        self.c, self.g, self.w, self.u = c, g, w, u
+        self.n = len(g)
+        self.g_scalars: Optional[List[int]] = None
+        self.w_scalar: Optional[int] = None
+        self.u_scalar: Optional[int] = None
+        self.other: Dict[int, Tuple[int, int]] = {}
+
+    def clone(self) -> "MSM":
+        o = MSM(self.c, self.g, self.w, self.u)
+        o.g_scalars = None if self.g_scalars is None else list(self.g_scalars)
+        o.w_scalar, o.u_scalar, o.other = self.w_scalar, self.u_scalar, dict(self.other)
+        return o
+
+    def _merge(self, x: int, y: int, scalar: int) -> None:     # :40-50, :73-83
+        r = self.c.r
+        if x in self.other:
+            ours, our_y = self.other[x]
+            if our_y == y:
+                self.other[x] = ((ours + scalar) % r, our_y)
+            else:
+                assert our_y == (-y) % self.c.p
+                self.other[x] = ((ours - scalar) % r, our_y)
+        else:
+            self.other[x] = (scalar % r, y)
+
+    def add_msm(self, other: "MSM") -> None:                   # :37-62
+        for x, (scalar, y) in other.other.items():
+            self._merge(x, y, scalar)
+        if other.g_scalars is not None:
+            self.add_to_g_scalars(other.g_scalars)
+        if other.w_scalar is not None:
+            self.add_to_w_scalar(other.w_scalar)
+        if other.u_scalar is not None:
+            self.add_to_u_scalar(other.u_scalar)
+
+    def append_term(self, scalar: int, point: Affine) -> None:  # :65-84 (the identity is skipped)
+        if point is not None:
+            self._merge(point[0], point[1], scalar)
+
+    def add_constant_term(self, constant: int) -> None:        # :87-95
+        if self.g_scalars is None:
+            self.g_scalars = [0] * self.n
+        self.g_scalars[0] = (self.g_scalars[0] + constant) % self.c.r
+
+    def add_to_g_scalars(self, scalars: Sequence[int]) -> None:  # :99-109
+        assert len(scalars) == self.n
+        if self.g_scalars is None:
+            self.g_scalars = [s % self.c.r for s in scalars]
+        else:
+            self.g_scalars = [(a + b) % self.c.r for a, b in zip(self.g_scalars, scalars)]
+
+    def add_to_w_scalar(self, scalar: int) -> None:            # :112-114
+        self.w_scalar = scalar % self.c.r if self.w_scalar is None else (self.w_scalar + scalar) % self.c.r
+
+    def add_to_u_scalar(self, scalar: int) -> None:            # :117-119
+        self.u_scalar = scalar % self.c.r if self.u_scalar is None else (self.u_scalar + scalar) % self.c.r
+
+    def scale(self, factor: int) -> None:                      # :122-135
+        r = self.c.r
+        if self.g_scalars is not None:
+            self.g_scalars = [a * factor % r for a in self.g_scalars]
+        self.other = {x: (s * factor % r, y) for x, (s, y) in self.other.items()}
+        if self.w_scalar is not None:
+            self.w_scalar = self.w_scalar * factor % r
+        if self.u_scalar is not None:
+            self.u_scalar = self.u_scalar * factor % r
+
+    def terms(self) -> Tuple[List[int], List[Affine]]:
+        """The (scalars, bases) of eval's one multiexp in the reference's order (:142-172): other, w, u, g."""
+        scalars: List[int] = []
+        bases: List[Affine] = []
+        for x in sorted(self.other):
+            s, y = self.other[x]
+            scalars.append(s)
+            bases.append((x, y))
+        if self.w_scalar is not None:
+            scalars.append(self.w_scalar)
+            bases.append(self.w)
+        if self.u_scalar is not None:
+            scalars.append(self.u_scalar)
+            bases.append(self.u)
+        if self.g_scalars is not None:
+            scalars.extend(self.g_scalars)
+            bases.extend(self.g)
+        return scalars, bases
+
+    def eval(self, multiexp=None) -> bool:                     # :138-177: best_multiexp(...).is_identity()
+        scalars, bases = self.terms()
+        res = (multiexp or (lambda s, b: best_multiexp(self.c, s, b)))(scalars, bases)
+        return res[2] == 0
+
+
+class Guard:
+    """verifier.rs:13-63."""
+
+    def __init__(self, msm: MSM, neg_c: int, u: List[int]):
+        self.msm, self.neg_c, self.u = msm, neg_c, u
+
+    def use_challenges(self) -> MSM:                           # :36-41
+        self.msm.add_to_g_scalars(compute_s(self.msm.c.r, self.u, self.neg_c))
+        return self.msm
+
+    def use_g(self, g: Affine) -> Tuple[MSM, Tuple[Affine, List[int]]]:   # :45-55
+        self.msm.append_term(self.neg_c, g)
+        return self.msm, (g, list(self.u))
+
+    def compute_g(self, multiexp=None) -> Affine:              # :58-62
+        c = self.msm.c
+        s = compute_s(c.r, self.u, 1)
+        return to_affine(c, (multiexp or (lambda a, b: best_multiexp(c, a, b)))(s, list(self.msm.g)))
+
+
+def ipa_verify_proof(k: int, msm: MSM, transcript, x: int, v: int) -> Guard:
+    """commitment::verify_proof (verifier.rs:67-141): `msm` evaluates to the commitment P being opened at x to v."""
+    r = msm.c.r
+    msm.add_constant_term((-v) % r)                            # :76  P' = P - [v] G_0 + [xi] S
+    try:
+        s_poly_commitment = transcript.read_point()            # :77
+    except Exception as e:                                     # Error::OpeningError
+        raise VerifyError("OpeningError") from e
+    xi = transcript.squeeze_challenge()                        # :78
+    msm.append_term(xi, s_poly_commitment)                     # :79
+    z = transcript.squeeze_challenge()                         # :81
+    rounds = []
+    for _ in range(k):                                         # :84-93
+        try:
+            l = transcript.read_point()
+            rr = transcript.read_point()
+        except Exception as e:
+            raise VerifyError("OpeningError") from e
+        rounds.append((l, rr, transcript.squeeze_challenge()))
+    u: List[int] = []
+    for l, rr, u_j in rounds:                                  # :95-111 (batch_invert: the same inverses)
+        msm.append_term(inv(u_j, r), l)
+        msm.append_term(u_j, rr)
+        u.append(u_j)
+    try:
+        c_val = transcript.read_scalar()                       # :126  Error::SamplingError
+        f = transcript.read_scalar()                           # :128
+    except Exception as e:
+        raise VerifyError("SamplingError") from e
+    neg_c = (-c_val) % r
+    b = compute_b(r, x, u)                                     # :129
+    msm.add_to_u_scalar(neg_c * b % r * z % r)                 # :131
+    msm.add_to_w_scalar((-f) % r)                              # :132
+    return Guard(msm, neg_c, u)
+
+
+def ipa_create_proof(c: Curve, g: Sequence[Affine], w: Affine, u: Affine, transcript, p_poly: Sequence[int], p_blind: int, x3: int,
+                     s_poly: Sequence[int], s_poly_blind: int, l_rand: Sequence[int], r_rand: Sequence[int]) -> None:
+    """commitment::create_proof whole (prover.rs:36-151).  The reference draws s_poly, its blind and the per-round
+    randomness from its RNG; here they are arguments (s_poly any polynomial of the same length: its evaluation at x3 is
+    removed as at :50-51)."""
+    r = c.r
+    n = len(g)
+    k = n.bit_length() - 1
+    assert len(p_poly) == n                                    # :41
+    s = [a % r for a in s_poly]
+    s[0] = (s[0] - eval_polynomial_mod(r, s, x3)) % r          # :51-52
+    transcript.write_point(to_affine(c, best_multiexp(c, s + [s_poly_blind], list(g) + [w])))   # :57-58
+    xi = transcript.squeeze_challenge()                        # :63
+    z = transcript.squeeze_challenge()                         # :67
+    p_prime = [(a * xi + b) % r for a, b in zip(s, p_poly)]    # :71  p' = s * xi + p
+    v = eval_polynomial_mod(r, p_prime, x3)                    # :72
+    p_prime[0] = (p_prime[0] - v) % r                          # :73
+    f = (s_poly_blind * xi + p_blind) % r                      # :74-76
+    state = {"f": f}
+    challenges: List[int] = []
+    # the round loop (:100-142) needs each challenge right after its L_j, R_j: run it round by round
+    b = [1] * n
+    for i in range(1, n):
+        b[i] = b[i - 1] * x3 % r                               # :86-93
+    g_prime = list(g)
+    for j in range(k):
+        half = 1 << (k - j - 1)
+        l_j = best_multiexp(c, p_prime[half:], g_prime[:half])
+        r_j = best_multiexp(c, p_prime[:half], g_prime[half:])
+        value_l = compute_inner_product(r, p_prime[half:], b[:half])
+        value_r = compute_inner_product(r, p_prime[:half], b[half:])
+        l_j = jac_add(c, l_j, best_multiexp(c, [value_l * z % r, l_rand[j]], [u, w]))
+        r_j = jac_add(c, r_j, best_multiexp(c, [value_r * z % r, r_rand[j]], [u, w]))
+        transcript.write_point(to_affine(c, l_j))              # :119-120
+        transcript.write_point(to_affine(c, r_j))
+        u_j = transcript.squeeze_challenge()                   # :122
+        u_inv = inv(u_j, r)
+        challenges.append(u_j)
+        for i in range(half):                                  # :128-133
+            p_prime[i] = (p_prime[i] + p_prime[i + half] * u_inv) % r
+            b[i] = (b[i] + b[i + half] * u_j) % r
+        p_prime, b = p_prime[:half], b[:half]
+        g_prime = parallel_generator_collapse(c, g_prime, u_j)  # :136-137
+        state["f"] = (state["f"] + l_rand[j] * u_inv + r_rand[j] * u_j) % r   # :140-141
+    transcript.write_scalar(p_prime[0])                        # :145-149
+    transcript.write_scalar(state["f"])
+
+
+def eval_polynomial_mod(m: int, poly: Sequence[int], point: int) -> int:
+    """arithmetic.rs:297-303 with the modulus given directly."""
+    acc = 0
+    for coeff in reversed(list(poly)):
+        acc = (acc * point + coeff) % m
+    return acc

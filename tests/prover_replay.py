@@ -40,9 +40,10 @@ DEGREE_J = 5   # benches/plonk.rs:183 set_minimum_degree(5) => quotient degree 4
 class Blake2bTranscript:
     """transcript.rs:160-219 (Blake2bWrite) with Challenge255 (:289-318)."""
 
-    def __init__(self):
+    def __init__(self, modulus: int = P_MOD):
         self.state = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
         self.proof = bytearray()
+        self.modulus = modulus                                # of the curve's scalar field (the challenge space)
 
     def write_point(self, xy: np.ndarray) -> None:            # :183-187 write_point, :205-216 common_point
         b = bytes(np.ascontiguousarray(xy, dtype=np.uint8).reshape(64))
@@ -60,7 +61,42 @@ class Blake2bTranscript:
 
     def squeeze_challenge(self) -> int:                       # :198-203; Challenge255::new = from_uniform_bytes of the 64-byte digest
         self.state.update(b"\x00")
-        return int.from_bytes(self.state.copy().digest(), "little") % P_MOD
+        return int.from_bytes(self.state.copy().digest(), "little") % self.modulus
+
+
+class Blake2bRead:
+    """transcript.rs:66-158 (Blake2bRead) with Challenge255: the verifier's view of the same transcript.  `decompress`:
+    32 proof bytes -> (64,) uint8 affine x||y, raising on an invalid encoding (C::from_bytes, :91-100) -- the engine's
+    h2_points_decompress in the GPU arm, the oracle's in the CPU arm."""
+
+    def __init__(self, proof: bytes, decompress, modulus: int = P_MOD):
+        self.state = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")
+        self.proof, self.pos, self.decompress, self.modulus = bytes(proof), 0, decompress, modulus
+
+    def _take(self) -> bytes:
+        if self.pos + 32 > len(self.proof):
+            raise EOFError("proof too short")                 # read_exact fails, :93 / :104
+        self.pos += 32
+        return self.proof[self.pos - 32:self.pos]
+
+    def read_point(self) -> np.ndarray:                       # :91-100, then common_point :130-141
+        xy = np.ascontiguousarray(self.decompress(self._take()), dtype=np.uint8).reshape(64)
+        if not xy.any():
+            raise ValueError("cannot write points at infinity to the transcript")
+        self.state.update(b"\x01" + bytes(xy[:32]) + bytes(xy[32:]))
+        return xy
+
+    def read_scalar(self) -> int:                             # :102-114, then common_scalar :143-148
+        b = self._take()
+        v = int.from_bytes(b, "little")
+        if v >= self.modulus:
+            raise ValueError("invalid field element encoding in proof")
+        self.state.update(b"\x02" + b)
+        return v
+
+    def squeeze_challenge(self) -> int:                       # :121-128
+        self.state.update(b"\x00")
+        return int.from_bytes(self.state.copy().digest(), "little") % self.modulus
 
 
 def _schedule_ast(kind, leaves, ch):
@@ -313,29 +349,27 @@ def run(arm, inp, k, omega):
     evals = arm.evals(ev_polys, ev_points)
     for e in evals:
         T.write_scalar(e)
-    # 6. multiopen: two point sets {x}: advice, h pieces, random poly;  {x omega}: advice, z
+    # 6. multiopen (poly/multiopen/prover.rs:38-123): two point sets {x}: advice, h pieces, random poly;  {x omega}: advice, z
     x1 = T.squeeze_challenge()
     x2 = T.squeeze_challenge()
-    set0 = adv + hp + [rnd]
-    set1 = adv + [z]
-    c0 = {"coeffs": [pow(x1, i, m) for i in range(len(set0))]}
-    c1 = {"coeffs": [pow(x1, i, m) for i in range(len(set1))]}
+    set0, b0 = adv + hp + [rnd], bl[0:3] + bl[5:9] + [bl[4]]
+    set1, b1 = adv + [z], bl[0:3] + [bl[3]]
+    # q_i = Horner in x_1 over the set's polynomials, first polynomial first (:53-63); the blinds fold the same way (:60-61)
+    c0 = {"coeffs": [pow(x1, len(set0) - 1 - i, m) for i in range(len(set0))]}
+    c1 = {"coeffs": [pow(x1, len(set1) - 1 - i, m) for i in range(len(set1))]}
     q0 = arm.ast("lincomb", set0, c0, extended=False)
     q1 = arm.ast("lincomb", set1, c1, extended=False)
-    e0, e1 = arm.evals([q0, q1], [x, xw])
-    arm.add_at(q0, 0, -e0)                                   # (q(X) - q(point)) / (X - point)
-    arm.add_at(q1, 0, -e1)
-    k0, k1 = arm.kate(q0, x), arm.kate(q1, xw)
-    f = arm.ast("lincomb", [k0, k1], {"coeffs": [1, x2]}, extended=False)
-    T.write_point(arm.commit([f], bl[9:10], lagrange=False)[0])
+    qb0 = sum(cf * b for cf, b in zip(c0["coeffs"], b0)) % m
+    qb1 = sum(cf * b for cf, b in zip(c1["coeffs"], b1)) % m
+    k0, k1 = arm.kate(q0, x), arm.kate(q1, xw)               # :78-84: kate_division drops the remainder q_i(point)
+    f = arm.ast("lincomb", [k0, k1], {"coeffs": [x2, 1]}, extended=False)      # :91-95  q' = q'_0 * x_2 + q'_1
+    T.write_point(arm.commit([f], bl[9:10], lagrange=False)[0])                # :99-102
     x3 = T.squeeze_challenge()
-    arm.add_at(q0, 0, e0)
-    arm.add_at(q1, 0, e1)
-    for e in arm.evals([q0, q1], [x3, x3]):
+    for e in arm.evals([q0, q1], [x3, x3]):                  # :108-110
         T.write_scalar(e)
     x4 = T.squeeze_challenge()
-    p = arm.ast("lincomb", [f, q0, q1], {"coeffs": [1, x4, x4 * x4 % m]}, extended=False)
-    p_blind = (bl[9] + x4 * bl[10] + x4 * x4 % m * bl[11]) % m
+    p = arm.ast("lincomb", [f, q0, q1], {"coeffs": [x4 * x4 % m, x4, 1]}, extended=False)   # :114-122  ((q' x_4) + q_0) x_4 + q_1
+    p_blind = (bl[9] * x4 % m * x4 + qb0 * x4 + qb1) % m
     # 7. the opening, poly/commitment/prover.rs:36-145
     s = arm.poly(inp["s_poly"])
     s_at = arm.evals([s], [x3])[0]
@@ -364,3 +398,163 @@ def run(arm, inp, k, omega):
     T.write_scalar(fsyn)                                     # :151
     arm.sync()
     return bytes(T.proof)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The verifier's side: the proof bytes of run() checked the way plonk::verify_proof's tail does it -- multiopen::verify_proof
+# (poly/multiopen/verifier.rs:29-140) building the MSM of the commitment being opened from the proof's own commitments and
+# evaluations, commitment::verify_proof (poly/commitment/verifier.rs:67-141) reading the opening, and the final
+# `guard.use_challenges().eval()` of SingleVerifier (plonk/verifier.rs:53-62): ONE multiexp over all 2^k generators.  Two
+# interchangeable arms again; what is NOT checked is the vanishing argument's identity (plonk/verifier.rs:294-357): the
+# replay's gate expressions are stand-ins that do not vanish on the domain.
+# ------------------------------------------------------------------------------------------------------------------------
+class GpuVerifierArm:
+    """halo2_b200.verifier: g_scalars resident, compute_s / scale / add on the device, eval over the resident generator table."""
+    name = "gpu"
+
+    def __init__(self, h2, k, g, g_lagrange, w, u, params=None):
+        self.h2, self.k = h2, k
+        self._own = params is None
+        self.params = params if params is not None else h2.Params(CURVE, k, g, g_lagrange, w, u=u)
+
+    def decompress(self, b32: bytes) -> np.ndarray:
+        return self.h2.decompress_points(np.frombuffer(b32, dtype=np.uint8).reshape(1, 32), CURVE)[0]
+
+    def msm(self):
+        return self.h2.MSM(self.params)
+
+    def append(self, msm, scalar, xy):
+        msm.append_term(scalar, xy)
+
+    def ipa_verify(self, msm, T, x, v):
+        return self.h2.verify_proof(self.params, msm, T, x, v)
+
+    def finish(self, guard) -> bool:                          # plonk/verifier.rs:57-58
+        msm = guard.use_challenges()
+        try:
+            return msm.eval()
+        finally:
+            msm.close()
+
+    def close(self):
+        if self._own:
+            self.params.close()
+
+
+class _TupleTranscript:
+    """The oracle speaks affine tuples; the transcripts of this file speak (64,) uint8 arrays."""
+
+    def __init__(self, T, cref):
+        self.T, self.cref = T, cref
+
+    def read_point(self):
+        return self.cref.bytes_to_affine(self.T.read_point())
+
+    def read_scalar(self):
+        return self.T.read_scalar()
+
+    def squeeze_challenge(self):
+        return self.T.squeeze_challenge()
+
+
+class CpuVerifierArm:
+    """oracle/pasta.py's restatement of MSM / verify_proof / Guard; the two hot calls -- compute_s (verifier.rs:156-171) and
+    the final best_multiexp (msm.rs:175) -- run through the C restatement and are the only ones timed (`hot_s`)."""
+    name = "cpu"
+
+    def __init__(self, cref, pasta, k, g, g_lagrange, w, u, threads):
+        self.cref, self.pasta, self.k, self.threads = cref, pasta, k, threads
+        self.c = pasta.CURVES[CURVE]
+        self.g_bytes = np.ascontiguousarray(g, dtype=np.uint8).reshape(-1, 64)
+        self.w_xy, self.u_xy = cref.bytes_to_affine(np.asarray(w).reshape(64)), cref.bytes_to_affine(np.asarray(u).reshape(64))
+        self.hot_s = 0.0
+
+    def decompress(self, b32: bytes) -> np.ndarray:
+        return self.cref.affines_to_bytes([self.pasta.decompress(self.c, b32)])[0]
+
+    def msm(self):
+        return self.pasta.MSM(self.c, [None] * (1 << self.k), self.w_xy, self.u_xy)    # the generators stay in self.g_bytes
+
+    def append(self, msm, scalar, xy):
+        msm.append_term(scalar, self.cref.bytes_to_affine(np.asarray(xy).reshape(64)))
+
+    def ipa_verify(self, msm, T, x, v):
+        return self.pasta.ipa_verify_proof(self.k, msm, _TupleTranscript(T, self.cref), x, v)
+
+    def finish(self, guard) -> bool:
+        cref, msm = self.cref, guard.msm
+        t0 = time.time()
+        s = cref.compute_s(FIELD, guard.u, guard.neg_c)                       # Guard::use_challenges, verifier.rs:36
+        self.hot_s += time.time() - t0
+        if msm.g_scalars is not None:                                         # add_to_g_scalars, msm.rs:99-109 (glue: a handful of non-zeros)
+            for i, gv in enumerate(msm.g_scalars):
+                if gv:
+                    cur = int.from_bytes(s[i].tobytes(), "little")
+                    s[i] = np.frombuffer(((cur + gv) % P_MOD).to_bytes(32, "little"), dtype=np.uint8)
+        msm.g_scalars = None
+        sc, bs = msm.terms()                                                  # other, w, u in the reference's order (msm.rs:150-166)
+        scalars = np.concatenate([cref.ints_to_bytes(sc), s])
+        bases = np.concatenate([cref.affines_to_bytes(bs), self.g_bytes])
+        t0 = time.time()
+        res = cref.best_multiexp(CURVE, scalars, bases, self.threads)          # msm.rs:175
+        self.hot_s += time.time() - t0
+        return not res.any()
+
+    def close(self):
+        pass
+
+
+def verify(arm, proof: bytes, k: int, omega: int) -> bool:
+    """Reads the proof run() wrote and checks its openings; returns msm.eval() of the final MSM (False also on a proof that
+    cannot be parsed: Error::OpeningError / SamplingError / an invalid encoding)."""
+    m = P_MOD
+    T = Blake2bRead(proof, arm.decompress)
+    try:
+        adv_c = [T.read_point() for _ in range(3)]
+        for _ in range(3):
+            T.squeeze_challenge()                                             # theta, beta, gamma
+        z_c = T.read_point()
+        rnd_c = T.read_point()
+        T.squeeze_challenge()                                                 # y
+        h_c = [T.read_point() for _ in range(DEGREE_J - 1)]
+        x = T.squeeze_challenge()
+        ev = [T.read_scalar() for _ in range(14)]
+        xw = x * omega % m
+        # multiopen::verify_proof, poly/multiopen/verifier.rs:29-140, for the replay's two single-point sets
+        x1 = T.squeeze_challenge()
+        x2 = T.squeeze_challenge()
+        sets = [(x, adv_c + h_c + [rnd_c], ev[0:3] + ev[9:13] + [ev[13]]),     # commitments and their evaluations at the set's point
+                (xw, adv_c + [z_c], ev[3:6] + [ev[7]])]
+        q_commitments, q_evals = [], []
+        for _, comms, evals in sets:                                          # :39-87: increasing powers of x_1 from the LAST commitment
+            q, qe, power = arm.msm(), 0, 1
+            for cm, e in zip(reversed(comms), reversed(evals)):
+                arm.append(q, power, cm)
+                qe = (qe + e * power) % m
+                power = power * x1 % m
+            q_commitments.append(q)
+            q_evals.append(qe)
+        f_c = T.read_point()                                                  # :90
+        x3 = T.squeeze_challenge()
+        u_ev = [T.read_scalar() for _ in sets]                                # :98-101
+        msm_eval = 0
+        for (point, _, _), r_eval, proof_eval in zip(sets, q_evals, u_ev):    # :105-119; one point: r(X) is the constant q_i(point)
+            msm_eval = (msm_eval * x2 + (proof_eval - r_eval) * pow(x3 - point, -1, m)) % m
+        x4 = T.squeeze_challenge()
+        msm = arm.msm()
+        arm.append(msm, 1, f_c)                                               # :126
+        v = msm_eval
+        for q, qe in zip(q_commitments, u_ev):                                # :127-134
+            msm.scale(x4)
+            msm.add_msm(q)
+            v = (v * x4 + qe) % m
+        guard = arm.ipa_verify(msm, T, x3, v)                                 # :137
+    except Exception as e:                                                    # any parse / opening error: the proof is rejected
+        if isinstance(e, AssertionError):
+            raise
+        return False
+    finally:
+        for q in locals().get("q_commitments", []):
+            if hasattr(q, "close"):
+                q.close()
+    return arm.finish(guard)
