@@ -172,6 +172,17 @@ def prover_replay(h2, cref, threads, reps=3, k=None):
             proof_t = R.run(gpu, inp, k, omega)
             gpu.free()
         gdt = (time.time() - t0) / reps
+        # the verifier's side of the same proof (tests/prover_replay.verify): multiopen MSM from the proof's commitments, the opening,
+        # ONE multiexp over all 2^k generators with compute_s built on the device -- against the resident table the prover used
+        gver = R.GpuVerifierArm(h2, k, g, gl, w, u, params=gpu.params)
+        v_ok = R.verify(gver, proof, k, omega)                 # warm-up
+        t0 = time.time()
+        for _ in range(reps):
+            v_ok = R.verify(gver, proof_t, k, omega) and v_ok
+        vdt = (time.time() - t0) / reps
+        bad = bytearray(proof)
+        bad[len(bad) - 40] ^= 1                                # one bit of c
+        v_rej = not R.verify(gver, bytes(bad), k, omega)
         # per-kind attribution: one more pass with a device sync after every arm call (perturbs the total; not the headline)
         by_kind = {}
         class Timed:
@@ -199,13 +210,27 @@ def prover_replay(h2, cref, threads, reps=3, k=None):
     t0 = time.time()
     proof_c = R.run(cpu, inp, k, omega)
     cpu_wall = time.time() - t0
+    cver = R.CpuVerifierArm(cref, pasta, k, g, gl, w, u, threads)
+    t0 = time.time()
+    cv_ok = R.verify(cver, proof_c, k, omega)
+    cver_wall = time.time() - t0
+    verify = {"metric": "ms_per_verification", "value": vdt * 1e3, "unit": "ms", "higher_is_better": False, "accepted": bool(v_ok),
+              "tampered_rejected": bool(v_rej),
+              "cpu_baseline": {"value": cver.hot_s * 1e3, "unit": "ms", "cores": threads, "kind": "port", "accepted": bool(cv_ok),
+                               "wall_ms_incl_glue": cver_wall * 1e3,
+                               "sample": "1 verification: compute_s (serial doubling loop, verifier.rs:156-171) and the final best_multiexp over "
+                                         "2^k + 2 + ~40 terms (msm.rs:175); parsing, the transcript and the scalar glue are not counted"},
+              "note": "the multiopen + opening checks of plonk::verify_proof's tail on the replay's proof (poly/multiopen/verifier.rs:29-140, "
+                      "poly/commitment/verifier.rs:67-141, SingleVerifier plonk/verifier.rs:53-62); GPU arm: wall-clock through halo2_b200.verifier "
+                      "incl. point decompression on the device, the host-side transcript and glue"}
     return {
+        "verify": verify,
         "metric": "hot_path_ms_per_proof", "value": gdt * 1e3, "unit": "ms", "higher_is_better": False, "k": k,
         "transcript_identical": bool(proof == proof_c and proof_t == proof_c), "proof_bytes": len(proof_c),
         "proof_blake2b": __import__("hashlib").blake2b(proof_c, digest_size=16).hexdigest(),
         "cpu_baseline": {"value": cpu.hot_s * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ipa_threads": cpu.ipa_threads,
                          "ms_by_kind": {k_: v * 1e3 for k_, v in cpu.by_kind.items()}, "wall_ms_incl_glue": cpu_wall * 1e3,
-                         "sample": "1 proof: the hot-path calls only (11 commitments, 4 + 4 + 1 transforms, 19 eval_polynomial, 2 kate_division, "
+                         "sample": "1 proof: the hot-path calls only (11 commitments, 4 + 4 + 1 transforms, 18 eval_polynomial, 2 kate_division, "
                                    "the 14-round opening); elementwise glue and the transcript are not counted"},
         "params_setup_ms": setup_s * 1e3, "gpu_ms_by_kind_synced": by_kind,
         "note": "proof-shaped replay of plonk::create_proof's hot path for the benches/plonk.rs circuit shape (Vesta, k=14, extended_k=16; "

@@ -1,0 +1,203 @@
+"""TEST-ONLY stand-in for the CUDA library's ctypes handle, so that the HOST LOGIC of halo2_b200.verifier (the mirror of
+poly/commitment/msm.rs and verifier.rs: term merging, the order of calls, what goes to which entry point) runs in the
+`-m "not gpu"` suite.  It implements just the C-ABI entry points that mirror touches, with the ABI's own calling convention
+(ctypes values, pointers and out-parameters exactly as halo2_b200/lib.py passes them): the two verifier kernels run as the
+device bodies on the host emulation (tests/kernel_emul), the group operations through the oracle.  It is never importable from
+the package: a test installs it with `installed()` and removes it again; the product has no CPU fallback."""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+
+import numpy as np
+
+from oracle import cref, pasta
+from tests.kernel_emul import build as emul_build
+
+_CURVES = {0: "pallas", 1: "vesta"}
+_FIELDS = {0: "fp", 1: "fq"}
+
+
+def _rd(p, nbytes: int) -> np.ndarray:
+    addr = p.value if hasattr(p, "value") else p
+    return np.frombuffer(ctypes.string_at(addr, nbytes), dtype=np.uint8).copy()
+
+
+def _wr(p, arr: np.ndarray) -> None:
+    data = np.ascontiguousarray(arr, dtype=np.uint8).tobytes()
+    ctypes.memmove(p.value if hasattr(p, "value") else p, data, len(data))
+
+
+def _v(x) -> int:
+    return int(x.value) if hasattr(x, "value") else int(x)
+
+
+def _jac_bytes(xy: np.ndarray) -> np.ndarray:
+    out = np.zeros(96, dtype=np.uint8)
+    if xy.any():
+        out[:64] = xy
+        out[64] = 1
+    return out
+
+
+class FakeLib:
+    def __init__(self):
+        self.emu = ctypes.CDLL(emul_build.build())
+        self.polys, self.bases, self.next = {}, {}, 1
+        self.err = b""
+        self.calls = []
+
+    def _fail(self, msg: str) -> int:
+        self.err = msg.encode()
+        return 1
+
+    def _log(self, name):
+        self.calls.append(name)
+
+    # ---- plumbing ----
+    def h2_init(self, device):
+        return 0
+
+    def h2_last_error(self):
+        return self.err
+
+    def h2_launch_count(self):
+        return len(self.calls)
+
+    # ---- base sets ----
+    def h2_bases_register_ex(self, curve, bases, n, repr_, window_bits, flags, out_handle):
+        h = self.next
+        self.next += 1
+        self.bases[h] = (_CURVES[_v(curve)], _rd(bases, 64 * _v(n)).reshape(-1, 64))
+        out_handle._obj.value = h
+        return 0
+
+    def h2_bases_release(self, h):
+        self.bases.pop(_v(h), None)
+        return 0
+
+    # ---- resident polynomials ----
+    def h2_poly_alloc(self, field, length, out_handle):
+        h = self.next
+        self.next += 1
+        self.polys[h] = [_FIELDS[_v(field)], np.zeros((_v(length), 32), dtype=np.uint8)]
+        out_handle._obj.value = h
+        return 0
+
+    def h2_poly_free(self, h):
+        self.polys.pop(_v(h), None)
+        return 0
+
+    def h2_poly_upload(self, h, src, length, repr_):
+        self.polys[_v(h)][1][:_v(length)] = _rd(src, 32 * _v(length)).reshape(-1, 32)
+        return 0
+
+    def h2_poly_download(self, h, dst, length, repr_):
+        _wr(dst, self.polys[_v(h)][1][:_v(length)])
+        return 0
+
+    def h2_poly_copy(self, dst, dst_off, src, src_off, length):
+        d, s, n = self.polys[_v(dst)][1], self.polys[_v(src)][1], _v(length)
+        d[_v(dst_off):_v(dst_off) + n] = s[_v(src_off):_v(src_off) + n]
+        return 0
+
+    def h2_poly_add_at(self, h, index, delta, repr_):
+        f, a = self.polys[_v(h)]
+        m = pasta.FIELDS[f]
+        i = _v(index)
+        cur = int.from_bytes(a[i].tobytes(), "little") + int.from_bytes(_rd(delta, 32).tobytes(), "little")
+        a[i] = np.frombuffer((cur % m).to_bytes(32, "little"), dtype=np.uint8)
+        return 0
+
+    def h2_poly_compute_s(self, dst, u, k, init, accumulate, repr_):
+        self._log("h2_poly_compute_s")
+        if _v(dst) not in self.polys:
+            return self._fail("h2_poly_compute_s: unknown polynomial handle")
+        f, a = self.polys[_v(dst)]
+        k = _v(k)
+        if k == 0 or a.shape[0] < (1 << k):
+            return self._fail("h2_poly_compute_s: bad size")
+        ub, ib = _rd(u, 32 * k), _rd(init, 32)
+        buf = np.ascontiguousarray(a[:1 << k])
+        self.emu.emu_compute_s(cref.FIELD_ID[f], cref._p(ub), k, cref._p(ib), int(accumulate), cref._p(buf))
+        a[:1 << k] = buf
+        return 0
+
+    def h2_poly_scale_add(self, dst, a, src, b, n, repr_):
+        self._log("h2_poly_scale_add")
+        n = _v(n)
+        if _v(src) and _v(src) == _v(dst):
+            return self._fail("h2_poly_scale_add: src must be another polynomial than dst")
+        f, d = self.polys[_v(dst)]
+        buf = np.ascontiguousarray(d[:n])
+        sb = np.ascontiguousarray(self.polys[_v(src)][1][:n]) if _v(src) else None
+        self.emu.emu_scale_add(cref.FIELD_ID[f], cref._p(buf), cref._p(_rd(a, 32)), cref._p(sb) if sb is not None else None,
+                               cref._p(_rd(b, 32)) if sb is not None else None, ctypes.c_uint64(n))
+        d[:n] = buf
+        return 0
+
+    # ---- group operations (through the oracle) ----
+    def _registered(self, handle, polys, batch, n, extra, affine):
+        curve, bases = self.bases[_v(handle)]
+        n, batch = _v(n), _v(batch)
+        blinds = _rd(extra, 32 * batch).reshape(-1, 32) if extra is not None else None
+        out = []
+        for i in range(batch):
+            sc = self.polys[int(polys[i])][1][:n]
+            bs = bases[:n]
+            if blinds is not None:
+                sc, bs = np.concatenate([sc, blinds[i:i + 1]]), bases[:n + 1]
+            xy = cref.best_multiexp(curve, np.ascontiguousarray(sc), np.ascontiguousarray(bs), 2)
+            out.append(xy if affine else _jac_bytes(xy))
+        return np.stack(out)
+
+    def h2_msm_registered_polys(self, handle, polys, batch, n, extra, repr_, out):
+        self._log("h2_msm_registered_polys")
+        _wr(out, self._registered(handle, polys, batch, n, extra, False))
+        return 0
+
+    def h2_msm_registered_polys_affine(self, handle, polys, batch, n, extra, repr_, out):
+        self._log("h2_msm_registered_polys_affine")
+        _wr(out, self._registered(handle, polys, batch, n, extra, True))
+        return 0
+
+    def h2_msm(self, curve, scalars, bases, n, repr_, out):
+        self._log("h2_msm")
+        n = _v(n)
+        xy = cref.best_multiexp(_CURVES[_v(curve)], _rd(scalars, 32 * n).reshape(-1, 32), _rd(bases, 64 * n).reshape(-1, 64), 2)
+        _wr(out, _jac_bytes(xy))
+        return 0
+
+    def h2_point_sum(self, curve, points, g, repr_, out):
+        self._log("h2_point_sum")
+        c = pasta.CURVES[_CURVES[_v(curve)]]
+        acc = (0, 1, 0)
+        for row in _rd(points, 96 * _v(g)).reshape(-1, 96):
+            x, y, z = (int.from_bytes(row[i:i + 32].tobytes(), "little") for i in (0, 32, 64))
+            acc = pasta.jac_add(c, acc, (x, y, z))
+        _wr(out, _jac_bytes(cref.affines_to_bytes([pasta.to_affine(c, acc)])[0]))
+        return 0
+
+    def h2_points_decompress(self, curve, data, n, repr_, out):
+        self._log("h2_points_decompress")
+        c = pasta.CURVES[_CURVES[_v(curve)]]
+        rows = _rd(data, 32 * _v(n)).reshape(-1, 32)
+        try:
+            pts = [pasta.decompress(c, r.tobytes()) for r in rows]
+        except Exception as e:
+            return self._fail(f"h2_points_decompress: {e}")
+        _wr(out, cref.affines_to_bytes(pts))
+        return 0
+
+
+@contextlib.contextmanager
+def installed():
+    """halo2_b200.lib bound to a FakeLib for the duration of the block (and back to whatever it was afterwards)."""
+    from halo2_b200 import lib as L
+    saved = (L._lib, L._inited_device)
+    fake = FakeLib()
+    L._lib, L._inited_device = fake, 0
+    try:
+        yield fake
+    finally:
+        L._lib, L._inited_device = saved

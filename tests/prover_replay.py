@@ -417,7 +417,23 @@ class GpuVerifierArm:
         self._own = params is None
         self.params = params if params is not None else h2.Params(CURVE, k, g, g_lagrange, w, u=u)
 
+    def prepare(self, proof: bytes, point_offsets) -> None:
+        """All of the proof's points through ONE h2_points_decompress call (the layout of a proof is known before it is read);
+        if any encoding is invalid the batch fails and read_point meets the bad one on its own."""
+        self._pts = {}
+        enc = [proof[o:o + 32] for o in point_offsets if o + 32 <= len(proof)]
+        if not enc:
+            return
+        try:
+            xy = self.h2.decompress_points(np.frombuffer(b"".join(enc), dtype=np.uint8).reshape(-1, 32), CURVE)
+        except self.h2.H2Error:
+            return
+        self._pts = {e: xy[i] for i, e in enumerate(enc)}
+
     def decompress(self, b32: bytes) -> np.ndarray:
+        hit = getattr(self, "_pts", {}).get(b32)
+        if hit is not None:
+            return hit
         return self.h2.decompress_points(np.frombuffer(b32, dtype=np.uint8).reshape(1, 32), CURVE)[0]
 
     def msm(self):
@@ -508,6 +524,9 @@ def verify(arm, proof: bytes, k: int, omega: int) -> bool:
     """Reads the proof run() wrote and checks its openings; returns msm.eval() of the final MSM (False also on a proof that
     cannot be parsed: Error::OpeningError / SamplingError / an invalid encoding)."""
     m = P_MOD
+    if hasattr(arm, "prepare"):
+        npt = 5 + DEGREE_J - 1                                                # 3 advice, z, the random polynomial, the h pieces
+        arm.prepare(proof, [32 * i for i in range(npt)] + [32 * (npt + 14)] + [32 * (npt + 17 + i) for i in range(1 + 2 * k)])
     T = Blake2bRead(proof, arm.decompress)
     try:
         adv_c = [T.read_point() for _ in range(3)]
