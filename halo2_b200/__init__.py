@@ -14,8 +14,9 @@ from .poly import (Params, EvaluationDomain, Blind, ResidentPoly, lagrange_gener
 
 from .evaluator import Ast, AstLeaf, Evaluator  # noqa: F401
 from .verifier import MSM, Guard, VerifyError, verify_proof, compute_b  # noqa: F401
+from . import multiopen, opening  # noqa: F401
 
-__all__ = ["Ast", "AstLeaf", "Evaluator", "MSM", "Guard", "VerifyError", "verify_proof", "compute_b", "H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "small_multiexp", "best_fft",
+__all__ = ["Ast", "AstLeaf", "Evaluator", "MSM", "Guard", "VerifyError", "verify_proof", "compute_b", "multiopen", "opening", "H2Error", "lib_path", "load", "init", "launch_count", "best_multiexp", "small_multiexp", "best_fft",
            "best_fft_curve", "batch_normalize", "multiexp_window_bits", "Params", "EvaluationDomain", "Blind", "ResidentPoly",
            "lagrange_generators", "compress_points", "decompress_points", "hash_to_curve",
            "eval_polynomial", "compute_inner_product", "kate_division", "eval_polynomial_resident", "inner_product_resident",

@@ -1326,3 +1326,199 @@ def eval_polynomial_mod(m: int, poly: Sequence[int], point: int) -> int:
     for coeff in reversed(list(poly)):
         acc = (acc * point + coeff) % m
     return acc
+
+
+# --------------------------------------------------------------------------------------
+# The multi-point opening argument: poly/multiopen.rs:144-275 (construct_intermediate_sets), poly/multiopen/prover.rs:18-124
+# (create_proof), poly/multiopen/verifier.rs:14-140 (verify_proof), arithmetic.rs:376-432 (lagrange_interpolate).
+# Queries are (point, object, ...) records; "the same polynomial / commitment" is object identity, as the reference's
+# PolynomialPointer / CommitmentReference compare by pointer (prover.rs:133-137, multiopen.rs:103-114).  The reference draws
+# f's blind and the opening's randomness from its RNG; here `rng` is any object with scalar() -> int and poly(n) -> [int].
+# --------------------------------------------------------------------------------------
+class ProverQuery:                                             # multiopen.rs:42-50
+    def __init__(self, point: int, poly: Sequence[int], blind: int):
+        self.point, self.poly, self.blind = point, poly, blind
+
+    def key(self):
+        return id(self.poly)
+
+    def value(self):                                           # Query::get_eval: the polynomial itself, with its blind (prover.rs:148-152)
+        return (self.poly, self.blind)
+
+
+class VerifierQuery:                                           # multiopen.rs:53-88
+    def __init__(self, commitment, point: int, eval_: int):
+        self.commitment, self.point, self.eval = commitment, point, eval_
+
+    @classmethod
+    def new_commitment(cls, commitment, point: int, eval_: int) -> "VerifierQuery":
+        return cls(commitment, point, eval_)
+
+    new_msm = new_commitment                                   # the commitment is an MSM object instead of a point
+
+    def key(self):
+        return id(self.commitment)
+
+    def value(self):
+        return self.eval
+
+
+def construct_intermediate_sets(queries, prover: bool):
+    """multiopen.rs:144-275.  Returns (commitment_data, point_sets) with commitment_data a list of dicts {commitment, set_index,
+    point_indices, evals} in first-seen order, or None when one commitment is queried twice at one point with different
+    evaluations (:243-249; a prover's "evaluation" is the polynomial itself, so its repeats are merely redundant -- and rejected
+    alike, since the slot is already filled)."""
+    queries = list(queries)
+    commitment_map: Dict[int, dict] = {}                       # IndexMap: insertion order
+    point_index_map: Dict[int, int] = {}
+    for q in queries:                                          # :162-173
+        idx = point_index_map.setdefault(q.point, len(point_index_map))
+        commitment_map.setdefault(q.key(), {"commitment": q.poly if prover else q.commitment, "blind": getattr(q, "blind", None),
+                                            "set_index": 0, "point_indices": [], "evals": []})["point_indices"].append(idx)
+    inverse = {i: p for p, i in point_index_map.items()}       # :176-179
+    point_idx_sets: Dict[Tuple[int, ...], int] = {}
+    commitment_set: Dict[int, Tuple[int, ...]] = {}
+    for key, data in commitment_map.items():                   # :186-203
+        pset = tuple(sorted(set(data["point_indices"])))
+        commitment_set[key] = pset
+        point_idx_sets.setdefault(pset, len(point_idx_sets))
+        data["evals"] = [None] * len(pset)
+    for q in queries:                                          # :206-250
+        data = commitment_map[q.key()]
+        pset = commitment_set[q.key()]
+        data["set_index"] = point_idx_sets[pset]
+        slot = pset.index(point_index_map[q.point])
+        if data["evals"][slot] is None:
+            data["evals"][slot] = q.value()
+        else:
+            return None
+    point_sets: List[List[int]] = [[] for _ in point_idx_sets]  # :266-272
+    for pset, sidx in point_idx_sets.items():
+        point_sets[sidx] = [inverse[i] for i in pset]
+    return list(commitment_map.values()), point_sets
+
+
+def lagrange_interpolate(m: int, points: Sequence[int], evals: Sequence[int]) -> List[int]:
+    """arithmetic.rs:376-432: the coefficients of the polynomial of degree < len(points) through (points[i], evals[i])."""
+    assert len(points) == len(evals)
+    if len(points) == 1:
+        return [evals[0] % m]
+    final = [0] * len(points)
+    for j, (x_j, ev) in enumerate(zip(points, evals)):
+        tmp = [1]
+        for kk, x_k in enumerate(points):
+            if kk == j:
+                continue
+            denom = inv((x_j - x_k) % m, m)
+            a = tmp + [0]
+            b = [0] + tmp
+            tmp = [(ai * ((-denom * x_k) % m) + bi * denom) % m for ai, bi in zip(a, b)]
+        for i, coeff in enumerate(tmp):
+            final[i] = (final[i] + coeff * ev) % m
+    return final
+
+
+def multiopen_create_proof(c: Curve, g: Sequence[Affine], w: Affine, u: Affine, rng, transcript, queries) -> None:
+    """poly/multiopen/prover.rs:18-124."""
+    r = c.r
+    n = len(g)
+    x1 = transcript.squeeze_challenge()                        # :38
+    x2 = transcript.squeeze_challenge()                        # :39
+    sets = construct_intermediate_sets(queries, prover=True)   # :41-46
+    if sets is None:
+        raise ValueError("queries iterator contains mismatching evaluations")
+    poly_map, point_sets = sets
+    q_polys: List[Optional[List[int]]] = [None] * len(point_sets)
+    q_blinds = [0] * len(point_sets)
+    for data in poly_map:                                      # :53-73: q_i = q_i * x_1 + poly, the blinds alike
+        s = data["set_index"]
+        poly = [a % r for a in data["commitment"]]
+        q_polys[s] = poly if q_polys[s] is None else [(a * x1 + b) % r for a, b in zip(q_polys[s], poly)]
+        q_blinds[s] = (q_blinds[s] * x1 + data["blind"]) % r
+    q_prime: Optional[List[int]] = None
+    for points, poly in zip(point_sets, q_polys):              # :75-96
+        cur = list(poly)
+        for pt in points:
+            cur = kate_division_mod(r, cur, pt)
+        cur = cur + [0] * (n - len(cur))                       # :84 resize
+        q_prime = cur if q_prime is None else [(a * x2 + b) % r for a, b in zip(q_prime, cur)]
+    q_prime_blind = rng.scalar()                               # :98
+    transcript.write_point(to_affine(c, best_multiexp(c, q_prime + [q_prime_blind], list(g) + [w])))   # :99-101
+    x3 = transcript.squeeze_challenge()                        # :103
+    for q in q_polys:                                          # :107-109
+        transcript.write_scalar(eval_polynomial_mod(r, q, x3))
+    x4 = transcript.squeeze_challenge()                        # :111
+    p_poly, p_blind = q_prime, q_prime_blind
+    for poly, blind in zip(q_polys, q_blinds):                 # :113-121
+        p_poly = [(a * x4 + b) % r for a, b in zip(p_poly, poly)]
+        p_blind = (p_blind * x4 + blind) % r
+    s_poly = rng.poly(n)                                       # commitment::create_proof draws these (prover.rs:46-54, :112-113)
+    s_blind = rng.scalar()
+    k = n.bit_length() - 1
+    rand = [(rng.scalar(), rng.scalar()) for _ in range(k)]
+    ipa_create_proof(c, g, w, u, transcript, p_poly, p_blind, x3, s_poly, s_blind, [a for a, _ in rand], [b for _, b in rand])   # :123
+
+
+def kate_division_mod(m: int, a: Sequence[int], b: int) -> List[int]:
+    """arithmetic.rs:322-341 with the modulus given directly."""
+    nb = (-b) % m
+    q = [0] * (len(a) - 1)
+    tmp = 0
+    for qi, coeff in zip(range(len(q) - 1, -1, -1), reversed(list(a))):
+        lead = (coeff - tmp) % m
+        q[qi] = lead
+        tmp = lead * nb % m
+    return q
+
+
+def multiopen_verify_proof(k: int, transcript, queries, msm: MSM) -> Guard:
+    """poly/multiopen/verifier.rs:14-140.  `msm`: the (usually empty) MSM the opened commitment is accumulated into."""
+    c = msm.c
+    r = c.r
+    x1 = transcript.squeeze_challenge()                        # :31
+    x2 = transcript.squeeze_challenge()                        # :35
+    sets = construct_intermediate_sets(queries, prover=False)  # :37-38
+    if sets is None:
+        raise VerifyError("OpeningError")
+    commitment_map, point_sets = sets
+    q_commitments = [[MSM(c, msm.g, msm.w, msm.u), 1] for _ in point_sets]   # :42-44 (accumulator, next x_1 power)
+    q_eval_sets = [[0] * len(ps) for ps in point_sets]         # :48-51
+    for data in reversed(commitment_map):                      # :54-86: increasing powers of x_1 from the last commitment
+        acc = q_commitments[data["set_index"]]
+        cm = data["commitment"]
+        if isinstance(cm, MSM):                                # :62-66
+            scaled = cm.clone()
+            scaled.scale(acc[1])
+            acc[0].add_msm(scaled)
+        else:
+            acc[0].append_term(acc[1], cm)                     # :59-61
+        es = q_eval_sets[data["set_index"]]
+        for i, ev in enumerate(data["evals"]):                 # :68-70
+            es[i] = (es[i] + ev * acc[1]) % r
+        acc[1] = acc[1] * x1 % r
+    try:
+        q_prime_commitment = transcript.read_point()           # :90
+    except Exception as e:
+        raise VerifyError("SamplingError") from e
+    x3 = transcript.squeeze_challenge()                        # :94
+    u_evals = []
+    for _ in q_eval_sets:                                      # :98-101
+        try:
+            u_evals.append(transcript.read_scalar())
+        except Exception as e:
+            raise VerifyError("SamplingError") from e
+    msm_eval = 0
+    for points, evals, proof_eval in zip(point_sets, q_eval_sets, u_evals):   # :105-119
+        r_eval = eval_polynomial_mod(r, lagrange_interpolate(r, points, evals), x3)
+        ev = (proof_eval - r_eval) % r
+        for pt in points:
+            ev = ev * inv((x3 - pt) % r, r) % r
+        msm_eval = (msm_eval * x2 + ev) % r
+    x4 = transcript.squeeze_challenge()                        # :123
+    msm.append_term(1, q_prime_commitment)                     # :126
+    v = msm_eval
+    for (q_commitment, _), q_eval in zip(q_commitments, u_evals):   # :127-134
+        msm.scale(x4)
+        msm.add_msm(q_commitment)
+        v = (v * x4 + q_eval) % r
+    return ipa_verify_proof(k, msm, transcript, x3, v)         # :137

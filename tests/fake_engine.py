@@ -178,6 +178,104 @@ class FakeLib:
         _wr(out, _jac_bytes(cref.affines_to_bytes([pasta.to_affine(c, acc)])[0]))
         return 0
 
+    def h2_msm_registered(self, handle, scalars, n, extra, repr_, out):
+        self._log("h2_msm_registered")
+        curve, bases = self.bases[_v(handle)]
+        n = _v(n)
+        sc, bs = _rd(scalars, 32 * n).reshape(-1, 32), bases[:n]
+        if extra is not None:
+            sc, bs = np.concatenate([sc, _rd(extra, 32).reshape(1, 32)]), bases[:n + 1]
+        _wr(out, _jac_bytes(cref.best_multiexp(curve, np.ascontiguousarray(sc), np.ascontiguousarray(bs), 2)))
+        return 0
+
+    def h2_batch_normalize(self, curve, points, n, repr_, out):
+        c = pasta.CURVES[_CURVES[_v(curve)]]
+        rows = _rd(points, 96 * _v(n)).reshape(-1, 96)
+        pts = [pasta.to_affine(c, tuple(int.from_bytes(row[i:i + 32].tobytes(), "little") for i in (0, 32, 64))) for row in rows]
+        _wr(out, cref.affines_to_bytes(pts))
+        return 0
+
+    # ---- reductions on resident polynomials ----
+    def h2_poly_eval(self, polys, batch, n, points, repr_, out):
+        self._log("h2_poly_eval")
+        n, batch = _v(n), _v(batch)
+        pts = _rd(points, 32 * batch).reshape(-1, 32)
+        res = []
+        for i in range(batch):
+            f, a = self.polys[int(polys[i])]
+            res.append(cref.eval_polynomial(f, a[:n], int.from_bytes(pts[i].tobytes(), "little")))
+        _wr(out, cref.ints_to_bytes(res))
+        return 0
+
+    def h2_poly_kate_division(self, dst, src, batch, n, points, repr_):
+        self._log("h2_poly_kate_division")
+        n, batch = _v(n), _v(batch)
+        pts = _rd(points, 32 * batch).reshape(-1, 32)
+        for i in range(batch):
+            if int(dst[i]) == int(src[i]):
+                return self._fail("h2_poly_kate_division: dst aliases src")
+            f, a = self.polys[int(src[i])]
+            q = cref.kate_division(f, a[:n], int.from_bytes(pts[i].tobytes(), "little"))
+            d = self.polys[int(dst[i])][1]
+            d[:n - 1] = q
+            if d.shape[0] >= n:
+                d[n - 1] = 0
+        return 0
+
+    # ---- the opening's round loop: the reference's own folding loop, one round per call (poly/commitment/prover.rs:100-142) ----
+    def h2_ipa_begin_poly(self, bases_handle, k, poly, x3, repr_, out_session):
+        f, a = self.polys[_v(poly)]
+        return self._ipa_begin(bases_handle, k, cref.bytes_to_ints(a[:1 << _v(k)]), x3, out_session)
+
+    def h2_ipa_begin(self, bases_handle, k, p_prime, x3, repr_, out_session):
+        return self._ipa_begin(bases_handle, k, cref.bytes_to_ints(_rd(p_prime, 32 << _v(k)).reshape(-1, 32)), x3, out_session)
+
+    def _ipa_begin(self, bases_handle, k, p_prime, x3, out_session):
+        self._log("h2_ipa_begin")
+        curve, bases = self.bases[_v(bases_handle)]
+        c = pasta.CURVES[curve]
+        k = _v(k)
+        n = 1 << k
+        x = int.from_bytes(_rd(x3, 32).tobytes(), "little")
+        b = [1] * n
+        for i in range(1, n):
+            b[i] = b[i - 1] * x % c.r
+        pts = [cref.bytes_to_affine(row) for row in bases[:n + 2]]
+        h = self.next
+        self.next += 1
+        self.sessions = getattr(self, "sessions", {})
+        self.sessions[h] = {"c": c, "g": pts[:n], "w": pts[n], "u": pts[n + 1], "p": list(p_prime), "b": b}
+        out_session._obj.value = h
+        return 0
+
+    def h2_ipa_round_affine(self, session, z, l_rand, r_rand, repr_, out):
+        self._log("h2_ipa_round")
+        S = self.sessions[_v(session)]
+        c, r = S["c"], S["c"].r
+        zi, lr, rr = (int.from_bytes(_rd(x, 32).tobytes(), "little") for x in (z, l_rand, r_rand))
+        half = len(S["p"]) // 2
+        p, b, g = S["p"], S["b"], S["g"]
+        l_j = pasta.best_multiexp(c, p[half:] + [pasta.compute_inner_product(r, p[half:], b[:half]) * zi % r, lr], g[:half] + [S["u"], S["w"]])
+        r_j = pasta.best_multiexp(c, p[:half] + [pasta.compute_inner_product(r, p[:half], b[half:]) * zi % r, rr], g[half:] + [S["u"], S["w"]])
+        _wr(out, cref.affines_to_bytes([pasta.to_affine(c, l_j), pasta.to_affine(c, r_j)]))
+        return 0
+
+    def h2_ipa_fold(self, session, u, u_inv, repr_):
+        S = self.sessions[_v(session)]
+        c, r = S["c"], S["c"].r
+        uj, ui = (int.from_bytes(_rd(x, 32).tobytes(), "little") for x in (u, u_inv))
+        half = len(S["p"]) // 2
+        S["p"] = [(S["p"][i] + S["p"][i + half] * ui) % r for i in range(half)]
+        S["b"] = [(S["b"][i] + S["b"][i + half] * uj) % r for i in range(half)]
+        S["g"] = pasta.parallel_generator_collapse(c, S["g"], uj)
+        return 0
+
+    def h2_ipa_finish(self, session, repr_, out):
+        S = self.sessions.pop(_v(session))
+        if out is not None:
+            _wr(out, cref.ints_to_bytes([S["p"][0], S["b"][0]]))
+        return 0
+
     def h2_points_decompress(self, curve, data, n, repr_, out):
         self._log("h2_points_decompress")
         c = pasta.CURVES[_CURVES[_v(curve)]]

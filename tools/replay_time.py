@@ -28,4 +28,13 @@ def timed_ipa(*a):
 gpu.ipa = timed_ipa
 R.run(gpu, inp, k, omega); gpu.free()
 print(f"ipa (unsynced entry) {stamps['ipa']:.2f} ms")
+proof = R.run(gpu, inp, k, omega); gpu.free()
+gv = R.GpuVerifierArm(h2, k, g, gl, w, u, params=gpu.params)
+ok = R.verify(gv, proof, k, omega)
+ts = []
+for _ in range(reps):
+    t0 = time.time(); ok = R.verify(gv, proof, k, omega) and ok; ts.append((time.time() - t0) * 1e3)
+print(f"verify accepted={ok} ms " + " ".join(f"{t:.2f}" for t in ts) + f"   min {min(ts):.2f}", flush=True)
+t0 = time.time(); cv = R.CpuVerifierArm(cref, pasta, k, g, gl, w, u, 128); okc = R.verify(cv, proof, k, omega)
+print(f"cpu verify accepted={okc} hot {cv.hot_s * 1e3:.1f} ms wall {(time.time() - t0) * 1e3:.1f} ms", flush=True)
 gpu.close()
