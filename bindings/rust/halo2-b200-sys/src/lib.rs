@@ -64,6 +64,9 @@ extern "C" {
                             n_consts: usize, omega: *const c_void, lin_base: *const c_void, repr: c_int) -> c_int;
     pub fn h2_poly_batch_invert(poly: u64, n: usize) -> c_int;
     pub fn h2_poly_running_product(dst: u64, src: u64, n: usize, init: *const c_void, repr: c_int) -> c_int;
+    // the verifier's MSM with resident g_scalars: compute_s (poly/commitment/verifier.rs:156-171) and MSM::scale / add_msm (msm.rs:37-139)
+    pub fn h2_poly_compute_s(dst: u64, u: *const c_void, k: u32, init: *const c_void, accumulate: c_int, repr: c_int) -> c_int;
+    pub fn h2_poly_scale_add(dst: u64, a: *const c_void, src: u64, b: *const c_void, n: usize, repr: c_int) -> c_int;
     pub fn h2_poly_divide_by_vanishing(poly: u64, ext_k: u32, t_evals: *const c_void, t_len: u32, repr: c_int) -> c_int;
     pub fn h2_poly_eval(polys: *const u64, batch: usize, n: usize, points: *const c_void, repr: c_int, out: *mut c_void) -> c_int;
     pub fn h2_poly_inner_product(a: *const u64, b: *const u64, batch: usize, n: usize, repr: c_int, out: *mut c_void) -> c_int;
