@@ -1,0 +1,459 @@
+"""plonk::verify_proof driven by a PINNED verifying key (test infrastructure: the caller of the path's verifier side).
+
+The reference's tests hold a golden proof, `tests/plonk_api_proof.bin`, checked with `verify_proof` against a verifying key whose
+pinned Debug form is a literal of the same test (/root/reference/halo2_proofs/tests/plonk_api.rs:462-476, :586-985).  The pinned
+form contains everything the verifier reads from a key -- domain, gate polynomials, query lists, permutation columns, lookup
+expressions, fixed and permutation commitments -- and its compact `{:?}` rendering is the string the key hashes into every
+transcript (src/plonk.rs:75-86).  This file restates the verifier's control flow around the path, in the reference's order:
+
+  plonk/verifier.rs:67-347         verify_proof: instance commitments (commit_lagrange), the reads and challenges, the
+                                   expected h(x), the query list, multiopen::verify_proof under a SingleVerifier
+  plonk/permutation/verifier.rs    read_product_commitments :34-53, evaluate :56-101, expressions :104-196, queries :198-241
+  plonk/lookup/verifier.rs         the commitments :35-70, evaluate :73-92, expressions :95-164, queries :166-208
+  plonk/vanishing/verifier.rs      the commitments :41-88, verify :91-118, queries :121-138
+  plonk/circuit.rs                 Expression::evaluate :514-611 and degree :614-626, ConstraintSystem::degree :1403-1431,
+                                   blinding_factors :1435-1460
+  poly/domain.rs                   rotate_omega :408-418, l_i_range :447-472, quotient_poly_degree :40-42
+
+It is generic over the pinned key, not written for one circuit.  The group work -- commit_lagrange of the instance columns, the
+multiopen MSMs, the opening, the final multiexp over every generator -- goes through an arm: the oracle (oracle/pasta.py) or the
+engine (halo2_b200.multiopen / halo2_b200.verifier on the GPU).
+"""
+from __future__ import annotations
+
+import hashlib
+import re
+from typing import List
+
+import numpy as np
+
+from oracle import cref, pasta
+from tests import prover_replay as R
+
+DELTA_EXP_T = None
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Rust's Debug renderings: `{:#?}` (the literal in the test) -> `{:?}` (what src/plonk.rs:80 hashes), and a parser of the latter
+# ------------------------------------------------------------------------------------------------------------------------
+def pretty_to_compact(pretty: str) -> str:
+    """core::fmt's builders: pretty output puts every field / entry on its own line, indented, each followed by a comma; compact
+    output joins them with ", ", writes structs as `Name { a: 1, b: 2 }` and tuples / lists as `Name(1, 2)` / `[1, 2]`.  Lines
+    that carry a whole value (field elements, the points' own `(x, y)` Debug, `[]`, `None`) are copied as they are."""
+    out: List[str] = []
+    for raw in pretty.strip().splitlines():
+        line = raw.strip()
+        if not line:
+            continue
+        if line[-1] in "{([":
+            out.append(line + (" " if line[-1] == "{" else ""))
+            continue
+        comma = line.endswith(",")
+        body = line[:-1] if comma else line
+        if body in ("}", ")", "]"):
+            if out and out[-1].endswith(", "):
+                out[-1] = out[-1][:-2]
+            out.append((" }" if body == "}" else body))
+        else:
+            out.append(body)
+        if comma:
+            out.append(", ")
+    s = "".join(out)
+    return s[:-2] if s.endswith(", ") else s
+
+
+_TOKEN = re.compile(r'\s*("(?:[^"\\]|\\.)*"|0x[0-9a-fA-F]+|-?\d+|[A-Za-z_][A-Za-z0-9_]*|[{}()\[\],:])')
+
+
+def parse_debug(s: str):
+    """Compact Debug text -> ("struct", name, {field: value}) | ("tuple", name or None, [values]) | ("list", [values]) | atom."""
+    toks = _TOKEN.findall(s)
+    assert "".join(toks) == re.sub(r"\s+", "", s), "unparsed characters in the Debug text"
+    pos = 0
+
+    def peek():
+        return toks[pos] if pos < len(toks) else None
+
+    def take(expect=None):
+        nonlocal pos
+        t = toks[pos]
+        assert expect is None or t == expect, (t, expect, pos)
+        pos += 1
+        return t
+
+    def items(close):
+        vals = []
+        while peek() != close:
+            vals.append(value())
+            if peek() == ",":
+                take(",")
+        take(close)
+        return vals
+
+    def value():
+        t = take()
+        if t == "(":
+            return ("tuple", None, items(")"))
+        if t == "[":
+            return ("list", items("]"))
+        if t[0] == '"':
+            return t[1:-1]
+        if t.startswith("0x"):
+            return int(t, 16)
+        if re.fullmatch(r"-?\d+", t):
+            return int(t)
+        if peek() == "{":
+            take("{")
+            fields = {}
+            while peek() != "}":
+                name = take()
+                take(":")
+                fields[name] = value()
+                if peek() == ",":
+                    take(",")
+            take("}")
+            return ("struct", t, fields)
+        if peek() == "(":
+            take("(")
+            return ("tuple", t, items(")"))
+        return t                                                  # a unit variant: Advice, Fixed, Instance, None
+
+    v = value()
+    assert pos == len(toks)
+    return v
+
+
+class PinnedKey:
+    """The verifier's view of a key, from its pinned Debug text."""
+
+    def __init__(self, pretty: str):
+        self.compact = pretty_to_compact(pretty)
+        t = parse_debug(self.compact)
+        assert t[0] == "struct" and t[1] == "PinnedVerificationKey"
+        f = t[2]
+        self.scalar_modulus = int(f["scalar_modulus"], 16)
+        self.base_modulus = int(f["base_modulus"], 16)
+        dom = f["domain"][2]
+        self.k, self.extended_k, self.omega = dom["k"], dom["extended_k"], dom["omega"]
+        cs = f["cs"][2]
+        self.num_fixed_columns, self.num_advice_columns = cs["num_fixed_columns"], cs["num_advice_columns"]
+        self.num_instance_columns = cs["num_instance_columns"]
+        self.gates = cs["gates"][1]                               # the flat list of gate polynomials (PinnedGates, circuit.rs:986-994)
+        q = lambda key: [(c[2][0][2]["index"], c[2][1][2][0]) for c in cs[key][1]]      # (column index, rotation)
+        self.advice_queries, self.instance_queries, self.fixed_queries = q("advice_queries"), q("instance_queries"), q("fixed_queries")
+        self.permutation_columns = [(c[2]["column_type"], c[2]["index"]) for c in cs["permutation"][2]["columns"][1]]
+        self.lookups = [(l[2]["input_expressions"][1], l[2]["table_expressions"][1]) for l in cs["lookups"][1]]
+        md = cs["minimum_degree"]
+        self.minimum_degree = None if md == "None" else md[2][0]
+        pt = lambda v: (v[2][0], v[2][1])
+        self.fixed_commitments = [pt(v) for v in f["fixed_commitments"][1]]
+        self.permutation_commitments = [pt(v) for v in f["permutation"][2]["commitments"][1]]
+
+    # ---- src/plonk.rs:75-86 ----
+    def transcript_repr(self) -> int:
+        h = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
+        s = self.compact.encode()
+        h.update(len(s).to_bytes(8, "little"))
+        h.update(s)
+        return int.from_bytes(h.digest(), "little") % self.scalar_modulus     # from_uniform_bytes
+
+    # ---- plonk/circuit.rs ----
+    def expr_degree(self, e) -> int:                              # :614-626
+        if isinstance(e, tuple) and e[0] == "struct":
+            return 1
+        name, args = e[1], e[2]
+        if name == "Constant":
+            return 0
+        if name == "Selector":
+            return 1
+        if name in ("Negated", "Scaled"):
+            return self.expr_degree(args[0])
+        if name == "Sum":
+            return max(self.expr_degree(args[0]), self.expr_degree(args[1]))
+        if name == "Product":
+            return self.expr_degree(args[0]) + self.expr_degree(args[1])
+        raise ValueError(name)
+
+    def degree(self) -> int:                                      # :1403-1431
+        d = 3                                                     # permutation::Argument::required_degree, plonk/permutation.rs:26-58
+        for inp, tab in self.lookups:                             # lookup::Argument::required_degree, plonk/lookup.rs:25-71
+            di = max([1] + [self.expr_degree(e) for e in inp])
+            dt = max([1] + [self.expr_degree(e) for e in tab])
+            d = max(d, max(4, 2 + di + dt))
+        d = max([d] + [self.expr_degree(g) for g in self.gates])
+        return max(d, self.minimum_degree or 1)
+
+    def blinding_factors(self) -> int:                            # :1435-1460; num_advice_queries = distinct queries per column (:1101-1115)
+        per_col = [0] * self.num_advice_columns
+        for col, _ in self.advice_queries:
+            per_col[col] += 1
+        return max(3, max(per_col + [1]) if per_col else 1) + 2
+
+    def evaluate(self, e, m, fixed, advice, instance) -> int:     # Expression::evaluate, :514-611, with the verifier's closures
+        if e[0] == "struct":
+            src = {"Fixed": fixed, "Advice": advice, "Instance": instance}[e[1]]
+            return src[e[2]["query_index"]]
+        name, args = e[1], e[2]
+        if name == "Constant":
+            return args[0] % m
+        if name == "Negated":
+            return (-self.evaluate(args[0], m, fixed, advice, instance)) % m
+        if name == "Sum":
+            return (self.evaluate(args[0], m, fixed, advice, instance) + self.evaluate(args[1], m, fixed, advice, instance)) % m
+        if name == "Product":
+            return self.evaluate(args[0], m, fixed, advice, instance) * self.evaluate(args[1], m, fixed, advice, instance) % m
+        if name == "Scaled":
+            return self.evaluate(args[0], m, fixed, advice, instance) * args[1] % m
+        raise ValueError("virtual selectors are removed during optimization" if name == "Selector" else name)
+
+    def any_query_index(self, column) -> int:                     # get_any_query_index, :1172-1185: the column at Rotation::cur()
+        kind, idx = column
+        qs = {"Advice": self.advice_queries, "Fixed": self.fixed_queries, "Instance": self.instance_queries}[kind]
+        return qs.index((idx, 0))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# the two arms
+# ------------------------------------------------------------------------------------------------------------------------
+class OracleArm:
+    name = "oracle"
+
+    def __init__(self, curve: str, k: int, g, g_lagrange, w, u):
+        self.c, self.k, self.curve = pasta.CURVES[curve], k, curve
+        T = cref.bytes_to_affine
+        self.g, self.gl = [T(x) for x in g], [T(x) for x in g_lagrange]
+        self.w, self.u = T(np.asarray(w).reshape(64)), T(np.asarray(u).reshape(64))
+
+    def point(self, xy):                                          # how this arm holds a commitment
+        return cref.bytes_to_affine(np.asarray(xy).reshape(64))
+
+    def commit_lagrange(self, values: List[int], blind: int) -> np.ndarray:
+        return cref.affines_to_bytes([pasta.to_affine(self.c, pasta.best_multiexp(self.c, list(values) + [blind], self.gl + [self.w]))])[0]
+
+    def decompress(self, b32: bytes) -> np.ndarray:
+        return cref.affines_to_bytes([pasta.decompress(self.c, b32)])[0]
+
+    def msm(self):
+        return pasta.MSM(self.c, self.g, self.w, self.u)
+
+    def query(self, commitment, point, ev):
+        return pasta.VerifierQuery(commitment, point, ev)
+
+    def multiopen_verify(self, T, queries, msm):
+        return pasta.multiopen_verify_proof(self.k, R._TupleTranscript(T, cref), queries, msm)
+
+    def finish(self, guard) -> bool:                              # SingleVerifier::process, plonk/verifier.rs:53-62
+        return guard.use_challenges().eval()
+
+    def close(self):
+        pass
+
+
+class EngineArm:
+    name = "engine"
+
+    def __init__(self, eng, curve: str, k: int, g, g_lagrange, w, u):
+        self.eng, self.curve, self.k = eng, curve, k
+        self.params = eng.Params(curve, k, g, g_lagrange, w, u=u)
+
+    def point(self, xy):
+        return np.ascontiguousarray(xy, dtype=np.uint8).reshape(64)
+
+    def commit_lagrange(self, values: List[int], blind: int) -> np.ndarray:
+        out = self.params.commit_lagrange(cref.ints_to_bytes(values), self.eng.Blind(blind))
+        return self.eng.batch_normalize(out.reshape(1, 96), self.curve)[0]
+
+    def decompress(self, b32: bytes) -> np.ndarray:
+        return self.eng.decompress_points(np.frombuffer(b32, dtype=np.uint8).reshape(1, 32), self.curve)[0]
+
+    def msm(self):
+        return self.eng.MSM(self.params)
+
+    def query(self, commitment, point, ev):
+        return self.eng.multiopen.VerifierQuery(commitment, point, ev)
+
+    def multiopen_verify(self, T, queries, msm):
+        return self.eng.multiopen.verify_proof(self.params, T, queries, msm)
+
+    def finish(self, guard) -> bool:
+        msm = guard.use_challenges()
+        try:
+            return msm.eval()
+        finally:
+            msm.close()
+
+    def close(self):
+        self.params.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# plonk::verify_proof
+# ------------------------------------------------------------------------------------------------------------------------
+def verify_proof(arm, vk: PinnedKey, proof: bytes, instances: List[List[List[int]]], delta: int) -> bool:
+    """plonk/verifier.rs:67-347 with a SingleVerifier.  `instances[proof][column]` = that instance column's values; `delta` = the
+    scalar field's DELTA (plonk/permutation/verifier.rs:172).  Returns False where the reference returns an Err or a failed eval."""
+    m = vk.scalar_modulus
+    n = 1 << vk.k
+    omega, omega_inv = vk.omega, pow(vk.omega, -1, m)
+    rot = lambda x, r: x * pow(omega if r >= 0 else omega_inv, abs(r), m) % m             # rotate_omega, domain.rs:408-418
+    bf = vk.blinding_factors()
+    cs_degree = vk.degree()
+    chunk_len = cs_degree - 2
+    P = arm.point
+    num_proofs = len(instances)
+    for inst in instances:                                        # :77-81
+        if len(inst) != vk.num_instance_columns:
+            return False
+    inst_comm = []
+    for inst in instances:                                        # :83-104
+        row = []
+        for col in inst:
+            if len(col) > n - (bf + 1):
+                return False
+            row.append(arm.commit_lagrange([v % m for v in col] + [0] * (n - len(col)), 1))
+        inst_comm.append(row)
+    T = R.Blake2bRead(proof, arm.decompress, m)
+    try:
+        T.common_scalar(vk.transcript_repr())                     # :109  vk.hash_into
+        for row in inst_comm:                                     # :111-116
+            for cm in row:
+                T.common_point(cm)
+        advice_comm = [[T.read_point() for _ in range(vk.num_advice_columns)] for _ in range(num_proofs)]   # :118-124
+        theta = T.squeeze_challenge()                             # :127
+        lookups_permuted = [[(T.read_point(), T.read_point()) for _ in vk.lookups] for _ in range(num_proofs)]   # :129-138
+        beta = T.squeeze_challenge()                              # :141
+        gamma = T.squeeze_challenge()                             # :144
+        nsets = -(-len(vk.permutation_columns) // chunk_len) if vk.permutation_columns else 0
+        perm_comm = [[T.read_point() for _ in range(nsets)] for _ in range(num_proofs)]                     # :146-151
+        lookups_product = [[T.read_point() for _ in vk.lookups] for _ in range(num_proofs)]                  # :153-162
+        random_poly_commitment = T.read_point()                   # :164
+        y = T.squeeze_challenge()                                 # :167
+        h_commitments = [T.read_point() for _ in range(cs_degree - 1)]   # :169  quotient_poly_degree = degree - 1
+        x = T.squeeze_challenge()                                 # :173
+        instance_evals = [[T.read_scalar() for _ in vk.instance_queries] for _ in range(num_proofs)]        # :174-176
+        advice_evals = [[T.read_scalar() for _ in vk.advice_queries] for _ in range(num_proofs)]            # :178-180
+        fixed_evals = [T.read_scalar() for _ in vk.fixed_queries]                                            # :182
+        random_eval = T.read_scalar()                             # :184
+        perm_common = [T.read_scalar() for _ in vk.permutation_commitments]                                  # :186
+        perm_eval = []
+        for pr in range(num_proofs):                              # :188-191, permutation/verifier.rs:73-101
+            sets = []
+            for i in range(nsets):
+                pe, pne = T.read_scalar(), T.read_scalar()
+                ple = T.read_scalar() if i + 1 < nsets else None
+                sets.append((perm_comm[pr][i], pe, pne, ple))
+            perm_eval.append(sets)
+        lookup_eval = [[tuple(T.read_scalar() for _ in range(5)) for _ in vk.lookups] for _ in range(num_proofs)]   # :193-202
+    except (EOFError, ValueError) + arm_errors(arm):
+        return False
+    # ---- the expected value of h(x), :206-276 ----
+    xn = pow(x, n, m)
+    rots = list(range(-(bf + 1), 1))                              # l_i_range(x, xn, -(bf + 1) ..= 0), domain.rs:447-472
+    common = (xn - 1) * pow(n, -1, m) % m
+    l_evals = [rot(pow((x - rot(1, r)) % m, -1, m) * common % m, r) for r in rots]
+    assert len(l_evals) == 2 + bf
+    l_last, l_blind, l_0 = l_evals[0], sum(l_evals[1:1 + bf]) % m, l_evals[1 + bf]
+    active = (1 - (l_last + l_blind)) % m
+    exprs: List[int] = []
+    for pr in range(num_proofs):
+        fe, ae, ie = fixed_evals, advice_evals[pr], instance_evals[pr]
+        col_eval = lambda col: {"Advice": ae, "Fixed": fe, "Instance": ie}[col[0]][vk.any_query_index(col)]
+        for gate in vk.gates:                                     # :224-238
+            exprs.append(vk.evaluate(gate, m, fe, ae, ie))
+        sets = perm_eval[pr]                                      # permutation/verifier.rs:104-196
+        if sets:
+            exprs.append(l_0 * (1 - sets[0][1]) % m)
+            exprs.append((sets[-1][1] * sets[-1][1] - sets[-1][1]) * l_last % m)
+            for cur, prev in zip(sets[1:], sets):
+                exprs.append((cur[1] - prev[3]) * l_0 % m)
+            for ci, st in enumerate(sets):
+                cols = vk.permutation_columns[ci * chunk_len:(ci + 1) * chunk_len]
+                pevals = perm_common[ci * chunk_len:(ci + 1) * chunk_len]
+                left = st[2]
+                for col, pe in zip(cols, pevals):
+                    left = left * ((col_eval(col) + beta * pe + gamma) % m) % m
+                right = st[1]
+                cur_delta = beta * x % m * pow(delta, ci * chunk_len, m) % m
+                for col in cols:
+                    right = right * ((col_eval(col) + cur_delta + gamma) % m) % m
+                    cur_delta = cur_delta * delta % m
+                exprs.append((left - right) * active % m)
+        for (inp, tab), (pe, pne, pie, piie, pte) in zip(vk.lookups, lookup_eval[pr]):      # lookup/verifier.rs:95-164
+            compress = lambda es: __import__("functools").reduce(lambda acc, e: (acc * theta + vk.evaluate(e, m, fe, ae, ie)) % m, es, 0)
+            left = pne * ((pie + beta) % m) % m * ((pte + gamma) % m) % m
+            right = pe * ((compress(inp) + beta) % m) % m * ((compress(tab) + gamma) % m) % m
+            exprs.append(l_0 * (1 - pe) % m)
+            exprs.append(l_last * (pe * pe - pe) % m)
+            exprs.append((left - right) * active % m)
+            exprs.append(l_0 * (pie - pte) % m)
+            exprs.append((pie - pte) * (pie - piie) % m * active % m)
+    expected_h = 0
+    for v in exprs:                                               # vanishing/verifier.rs:99-100
+        expected_h = (expected_h * y + v) % m
+    expected_h = expected_h * pow(xn - 1, -1, m) % m
+    h_commitment = arm.msm()                                      # :102-110
+    for cm in reversed(h_commitments):
+        h_commitment.scale(xn)
+        h_commitment.append_term(1, P(cm))
+    # ---- the queries, :278-337, in the reference's order ----
+    Q = arm.query
+    queries = []
+    x_next, x_prev, x_last = rot(x, 1), rot(x, -1), rot(x, -(bf + 1))
+    for pr in range(num_proofs):
+        ic = [P(c_) for c_ in inst_comm[pr]]
+        ac = [P(c_) for c_ in advice_comm[pr]]
+        for qi, (col, at) in enumerate(vk.instance_queries):
+            queries.append(Q(ic[col], rot(x, at), instance_evals[pr][qi]))
+        for qi, (col, at) in enumerate(vk.advice_queries):
+            queries.append(Q(ac[col], rot(x, at), advice_evals[pr][qi]))
+        sets = [(P(s[0]), s[1], s[2], s[3]) for s in perm_eval[pr]]           # permutation/verifier.rs:198-227
+        for cm, pe, pne, _ in sets:
+            queries.append(Q(cm, x, pe))
+            queries.append(Q(cm, x_next, pne))
+        for cm, _, _, ple in list(reversed(sets))[1:]:
+            queries.append(Q(cm, x_last, ple))
+        for (pin, ptab), prod, (pe, pne, pie, piie, pte) in zip(lookups_permuted[pr], lookups_product[pr], lookup_eval[pr]):   # lookup/verifier.rs:166-208
+            pin, ptab, prod = P(pin), P(ptab), P(prod)
+            queries += [Q(prod, x, pe), Q(pin, x, pie), Q(ptab, x, pte), Q(pin, x_prev, piie), Q(prod, x_next, pne)]
+    fc = [P(cref.affines_to_bytes([pt])[0]) for pt in vk.fixed_commitments]
+    for qi, (col, at) in enumerate(vk.fixed_queries):             # :318-330
+        queries.append(Q(fc[col], rot(x, at), fixed_evals[qi]))
+    for pt, ev in zip(vk.permutation_commitments, perm_common):   # permutation/verifier.rs:231-240
+        queries.append(Q(P(cref.affines_to_bytes([pt])[0]), x, ev))
+    queries.append(Q(h_commitment, x, expected_h))                # vanishing/verifier.rs:121-138
+    queries.append(Q(P(random_poly_commitment), x, random_eval))
+    try:
+        guard = arm.multiopen_verify(T, queries, arm.msm())       # :341-346
+    except (EOFError, ValueError) + arm_errors(arm):
+        return False
+    finally:
+        if hasattr(h_commitment, "close"):
+            h_commitment.close()
+    if T.pos != len(proof):
+        return False                                              # (the reference leaves trailing bytes unread; the golden proof has none)
+    return arm.finish(guard)
+
+
+def arm_errors(arm):
+    if isinstance(arm, EngineArm):
+        return (arm.eng.VerifyError, arm.eng.H2Error)
+    return (pasta.VerifyError,)
+
+
+def load_golden_proofs():
+    """tests/golden/golden_proofs.json.gz (made by tests/golden/make_golden_proof.py from the reference's stored proofs and pinned
+    keys): [{name, source, curve, key text, instances, proof bytes}]."""
+    import gzip
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_proofs.json.gz")
+    with gzip.open(path, "rb") as f:
+        d = json.load(f)
+    return [{"name": c["name"], "source": c["source"], "curve": c["curve"], "key_text": d["keys"][c["key"]],
+             "instances": [[[int(v, 16) for v in col] for col in pr] for pr in c["instances"]], "proof": bytes.fromhex(c["proof_hex"])}
+            for c in d["cases"]]
+
+
+def scalar_delta(modulus: int) -> int:
+    """F::DELTA = MULTIPLICATIVE_GENERATOR^(2^S) (pasta_curves; used at plonk/permutation/keygen.rs:131, verifier.rs:172)."""
+    return pow(pasta.MULT_GEN, 1 << pasta.S_2ADICITY, modulus)

@@ -86,6 +86,15 @@ class Blake2bRead:
         self.state.update(b"\x01" + bytes(xy[:32]) + bytes(xy[32:]))
         return xy
 
+    def common_point(self, xy) -> None:                       # :128-141
+        xy = np.ascontiguousarray(xy, dtype=np.uint8).reshape(64)
+        if not xy.any():
+            raise ValueError("cannot write points at infinity to the transcript")
+        self.state.update(b"\x01" + bytes(xy[:32]) + bytes(xy[32:]))
+
+    def common_scalar(self, s: int) -> None:                  # :143-148
+        self.state.update(b"\x02" + int(s).to_bytes(32, "little"))
+
     def read_scalar(self) -> int:                             # :102-114, then common_scalar :143-148
         b = self._take()
         v = int.from_bytes(b, "little")
