@@ -18,6 +18,10 @@ What it restates (all file:line relative to /root/reference/halo2_proofs/src):
   * the IPA round loop       poly/commitment/prover.rs:100-142, :154-166 (transcript factored out: challenges
     and randomness are inputs, the points / scalar written to the transcript are outputs)
   * permute_expression_pair  plonk/lookup/prover.rs:563-647 (the lookup argument's permuted columns, usable rows only)
+  * the verifier's side: MSM (poly/commitment/msm.rs:9-178), commitment::verify_proof / Guard / compute_s / compute_b
+    (poly/commitment/verifier.rs:13-171), commitment::create_proof whole (poly/commitment/prover.rs:36-151)
+  * the multi-point opening argument: poly/multiopen.rs:144-275, multiopen/prover.rs:18-124, multiopen/verifier.rs:14-140,
+    lagrange_interpolate arithmetic.rs:376-432
 
 Third-party arithmetic that is NOT in the reference tree: crate `pasta_curves 0.5.1`
 (Cargo.lock:1303-1306), `ff 0.13.0`, `group 0.13.0`.  Its published algorithm is restated
@@ -39,6 +43,10 @@ PARITY PINNING STATUS: PINNED on reference-held vectors.
     butterfly network as the pinned G = curve-point instantiation (one generic function,
     arithmetic.rs:192-295), checked against the DFT definition for true roots of unity and, through
     the domain constants it is used with, against the pinned omegas.
+  * the verifier's side -- MSM, verify_proof / Guard, compute_s / compute_b, the multiopen verifier, lagrange_interpolate -- on
+    the reference's sixteen GOLDEN PROOFS (halo2_proofs/tests/plonk_api_proof.bin and the fifteen proof_*.bin of
+    halo2_gadgets/src/test_circuits/circuit_data/): every one is accepted under its pinned key, every tampered one rejected
+    (tests/test_golden_proofs.py, tests/plonk_verifier.py; on the device: tests/test_gpu_golden_proofs.py).
   The reference itself cannot be built here (no Rust toolchain; pasta_curves un-vendored).
 """
 from __future__ import annotations
