@@ -330,6 +330,103 @@ def lookup_permute_ms(h2, cref, reps=5):
     return {"k": PROVER_K, "usable_rows": u, "gpu_ms": gpu_ms, "cpu_baseline": {"ms": cpu_ms, "cores": 1, "kind": "port"}, "same_result": same}
 
 
+def golden_proofs_verify_ms(h2, cref, threads):
+    """The reference's fifteen stored k = 11 proofs (halo2_gadgets/src/test_circuits/circuit_data/proof_*.bin: ECC chip, Sinsemilla,
+    Merkle, range checks) verified through the engine under their pinned keys (tests/plonk_verifier.py restates plonk::verify_proof
+    around the path).  Reported: acceptance; per proof, the wall time of the whole verification through the Python host mirror and
+    the share of the path's own tail -- Guard::use_challenges (compute_s on the device) + MSM::eval (one multiexp over the 2^11
+    resident generators) -- next to the same two hot calls on the C restatement; and the BatchVerifier shape
+    (plonk/verifier/batch.rs:83-131): all fifteen MSMs scaled and accumulated on the device, ONE eval."""
+    from oracle import pasta
+    from tests import plonk_verifier as PV
+    cases = [c for c in PV.load_golden_proofs() if c["name"] != "plonk_api"]
+    k = 11
+    delta = PV.scalar_delta(pasta.P_MOD)
+    prm = h2.Params.new("vesta", k)
+    g_bytes, w_xy, u_xy = prm.g.copy(), prm.w.copy(), prm.u.copy()
+
+    class TimedArm(PV.EngineArm):
+        tail_s = 0.0
+        keep = None
+
+        def finish(self, guard):
+            t0 = time.time()
+            if self.keep is not None:                              # batch mode: hand the MSM over instead of evaluating it
+                self.keep.append(guard.use_challenges())
+                ok = True
+            else:
+                ok = PV.EngineArm.finish(self, guard)
+            self.tail_s += time.time() - t0
+            return ok
+
+    arm = TimedArm(h2, "vesta", k, prm.g, prm.g_lagrange, prm.w, prm.u)
+    prm.close()
+    keys = [PV.PinnedKey(c["key_text"]) for c in cases]
+    try:
+        ok = all(PV.verify_proof(arm, vk, c["proof"], c["instances"], delta) for vk, c in zip(keys, cases))     # warm-up
+        arm.tail_s = 0.0
+        t0 = time.time()
+        ok = all(PV.verify_proof(arm, vk, c["proof"], c["instances"], delta) for vk, c in zip(keys, cases)) and ok
+        wall = time.time() - t0
+        tail = arm.tail_s
+        bad = bytearray(cases[0]["proof"])
+        bad[-40] ^= 1
+        rejected = not PV.verify_proof(arm, keys[0], bytes(bad), cases[0]["instances"], delta)
+        # batch: every proof's MSM into one accumulator, one eval
+        factors = cref.bytes_to_ints(cref.gen_scalars("fp", SEED + 130, len(cases)))
+        arm.keep = []
+        t0 = time.time()
+        for vk, c in zip(keys, cases):
+            PV.verify_proof(arm, vk, c["proof"], c["instances"], delta)
+        t_guard = time.time() - t0
+        t0 = time.time()
+        acc = h2.MSM(arm.params)
+        for f, m_i in zip(factors, arm.keep):
+            acc.scale_add_msm(f, m_i)
+        batch_ok = acc.eval()
+        batch_tail = time.time() - t0
+        for m_i in arm.keep:
+            m_i.close()
+        acc.close()
+    finally:
+        arm.close()
+    # the C restatement's two hot calls per proof (compute_s, the multiexp), on the MSMs the oracle's verifier builds
+    class CpuArm(PV.OracleArm):
+        hot_s = 0.0
+
+        def finish(self, guard):
+            t0 = time.time()
+            s = cref.compute_s("fp", guard.u, guard.neg_c)
+            self.hot_s += time.time() - t0
+            msm = guard.msm
+            if msm.g_scalars is not None:
+                for i, gv in enumerate(msm.g_scalars):
+                    if gv:
+                        s[i] = cref.ints_to_bytes([(int.from_bytes(s[i].tobytes(), "little") + gv) % pasta.P_MOD])[0]
+            msm.g_scalars = None
+            sc, bs = msm.terms()
+            import numpy as np
+            scalars = np.concatenate([cref.ints_to_bytes(sc), s])
+            bases = np.concatenate([cref.affines_to_bytes(bs), g_bytes])
+            t0 = time.time()
+            res = cref.best_multiexp("vesta", scalars, bases, threads)
+            self.hot_s += time.time() - t0
+            return not res.any()
+
+    carm = CpuArm("vesta", k, g_bytes[:1], g_bytes[:1], w_xy, u_xy)          # the generators stay in g_bytes (bytes): no 2^11 tuple conversions
+    carm.g = [None] * (1 << k)
+    cpu_ok = all(PV.verify_proof(carm, vk, c["proof"], c["instances"], delta) for vk, c in zip(keys, cases))
+    n = len(cases)
+    return {"k": k, "proofs": n, "accepted": bool(ok), "tampered_rejected": bool(rejected),
+            "gpu_ms_per_proof_wall": wall / n * 1e3, "gpu_ms_per_proof_path_tail": tail / n * 1e3,
+            "batch": {"accepted": bool(batch_ok), "gpu_ms_accumulate_and_eval": batch_tail * 1e3, "gpu_ms_guards_wall": t_guard * 1e3},
+            "cpu_baseline": {"ms_per_proof_hot": carm.hot_s / n * 1e3, "accepted": bool(cpu_ok), "cores": threads, "kind": "port",
+                             "sample": "compute_s (verifier.rs:156-171) + the final best_multiexp (msm.rs:175) of each of the 15 proofs; the "
+                                       "plonk::verify_proof glue around them is the same Python code in both arms and is not counted here"},
+            "note": "reference-held proofs and keys (tests/golden/golden_proofs.json.gz); wall = everything incl. the Python restatement of "
+                    "plonk::verify_proof, the Blake2b transcript and per-point decompression calls; path tail = use_challenges + eval"}
+
+
 def quotient_pipeline_ms(h2, cref, threads, reps=5):
     """The quotient pipeline of plonk/vanishing/prover.rs:81-88 at k=14, extended_k=16, resident on the device: coeff_to_extended of
     four columns, an h(X)-shaped Ast over them (two gates, a permutation-style product with the linear term, folded by powers of
@@ -925,6 +1022,7 @@ def main():
             extra["poly_reductions_k14"] = guarded(poly_reductions_ms, h2, cref)
             extra["quotient_pipeline_k14"] = guarded(quotient_pipeline_ms, h2, cref, threads)
             extra["lookup_permute_k14"] = guarded(lookup_permute_ms, h2, cref)
+            extra["golden_proofs_verify_k11"] = guarded(golden_proofs_verify_ms, h2, cref, threads)
             extra["create_proof_k14_replay"] = guarded(prover_replay, h2, cref, threads)
             # the top of the reference's own bench range (benches/plonk.rs: k = 8..16): the passes stop being latency-bound
             extra["create_proof_k16_replay"] = guarded(prover_replay, h2, cref, threads, 2, 16)

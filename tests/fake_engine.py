@@ -276,6 +276,29 @@ class FakeLib:
             _wr(out, cref.ints_to_bytes([S["p"][0], S["b"][0]]))
         return 0
 
+    def h2_params_lagrange(self, curve, g_xy, k, omega_inv, minv, repr_, out):
+        k = _v(k)
+        gl = cref.params_lagrange(_CURVES[_v(curve)], _rd(g_xy, 64 << k).reshape(-1, 64), k, int.from_bytes(_rd(omega_inv, 32).tobytes(), "little"),
+                                  int.from_bytes(_rd(minv, 32).tobytes(), "little"))
+        _wr(out, gl)
+        return 0
+
+    def h2_params_new(self, curve, k, repr_, out_g, out_gl, out_w, out_u):
+        name = _CURVES[_v(curve)]
+        c = pasta.CURVES[name]
+        k = _v(k)
+        g, w, u = pasta.params_generators(c, k)
+        gb = cref.affines_to_bytes(g)
+        r = c.r
+        gl = cref.params_lagrange(name, gb, k, pasta.inv(pasta.omega_for_k(c.scalar, k), r), pow(pasta.inv(2, r), k, r))
+        _wr(out_g, gb), _wr(out_gl, gl), _wr(out_w, cref.affines_to_bytes([w])), _wr(out_u, cref.affines_to_bytes([u]))
+        return 0
+
+    def h2_points_compress(self, curve, points, n, repr_, out):
+        rows = _rd(points, 64 * _v(n)).reshape(-1, 64)
+        _wr(out, np.frombuffer(b"".join(pasta.compress(cref.bytes_to_affine(r)) for r in rows), dtype=np.uint8))
+        return 0
+
     def h2_points_decompress(self, curve, data, n, repr_, out):
         self._log("h2_points_decompress")
         c = pasta.CURVES[_CURVES[_v(curve)]]
