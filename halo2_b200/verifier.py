@@ -41,6 +41,23 @@ def compute_b(x: int, u: Sequence[int], modulus: int) -> int:
     return tmp
 
 
+def batch_invert(values: Sequence[int], modulus: int) -> List[int]:
+    """ff::BatchInvert (verifier.rs:95-98): all inverses from ONE modular inversion (Montgomery's trick); zeros stay zero."""
+    prefix, acc = [], 1
+    for v in values:
+        prefix.append(acc)
+        if v % modulus:
+            acc = acc * v % modulus
+    inv = pow(acc, -1, modulus)
+    out = [0] * len(values)
+    for i in range(len(values) - 1, -1, -1):
+        v = values[i] % modulus
+        if v:
+            out[i] = inv * prefix[i] % modulus
+            inv = inv * v % modulus
+    return out
+
+
 def _is_identity_xy(xy: np.ndarray) -> bool:
     return not xy.any()
 
@@ -263,8 +280,9 @@ def verify_proof(params: Params, msm: MSM, transcript, x: int, v: int) -> Guard:
             raise VerifyError("OpeningError") from e
         rounds.append((l, rr, transcript.squeeze_challenge()))
     u: List[int] = []
-    for l, rr, u_j in rounds:                                    # :95-111 (batch_invert: the same k inverses)
-        msm.append_term(pow(u_j, -1, r) if u_j else 0, l)    # ff::BatchInvert leaves a zero as it is
+    u_inv = batch_invert([u_j for _, _, u_j in rounds], r)       # :95-98
+    for (l, rr, u_j), u_j_inv in zip(rounds, u_inv):             # :104-111
+        msm.append_term(u_j_inv, l)
         msm.append_term(u_j, rr)
         u.append(u_j)
     try:
