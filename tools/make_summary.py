@@ -19,7 +19,7 @@ for name, ttl in (("msm", "MSM 2^20 Pallas one-shot (device-resident inputs), 3 
     if os.path.exists(f):
         shutil.copy(f, dst)
         parts.append(subprocess.run([sys.executable, "tools/summarize_launches.py", f, ttl], capture_output=True, text=True).stdout)
-for extra in (f"{tag}_bench_n1.json", f"{tag}_ecfft_stage_ncu_full_raw.csv", f"{tag}_pytest_gpu.txt", f"{tag}_smoke.txt"):
+for extra in (f"{tag}_bench_n1.json", f"{tag}_ecfft_stage_ncu_full_raw.csv", f"{tag}_pytest_gpu.txt", f"{tag}_smoke.txt", f"{tag}_replay_time.txt"):
     if os.path.exists(f"{src}/{extra}") and os.path.getsize(f"{src}/{extra}"):
         shutil.copy(f"{src}/{extra}", dst)
 b = f"{src}/{tag}_bench_n1.json"
@@ -61,6 +61,22 @@ if os.path.exists(b) and os.path.getsize(b):
         r_ = x["poly_reductions_k14"]
         parts.append(f"* k=14 reductions on resident polynomials: 16 eval_polynomial {r_['eval_x16']['gpu_ms']:.3f} ms vs {r_['eval_x16']['cpu_baseline']['ms']:.1f} ms, "
                      f"4 kate_division {r_['kate_division_x4']['gpu_ms']:.3f} ms vs {r_['kate_division_x4']['cpu_baseline']['ms']:.1f} ms (1 core).")
+    if "verify" in c:
+        v = c["verify"]
+        parts.append(f"* verification of that proof (multiopen MSM, the opening, compute_s on the device, ONE multiexp over the resident generators): "
+                     f"{v['value']:.2f} ms wall through the Python mirror vs {v['cpu_baseline']['value']:.1f} ms of hot calls on the C restatement; accepted = "
+                     f"{v['accepted']}, tampered rejected = {v['tampered_rejected']}.")
+    c16 = x.get("create_proof_k16_replay", {})
+    if "value" in c16:
+        parts.append(f"* k=16 replay: {c16['value']:.2f} ms vs {c16['cpu_baseline']['value']:.0f} ms = {c16['cpu_baseline']['value'] / c16['value']:.1f}x (transcript_identical = "
+                     f"{c16.get('transcript_identical')}); its verification {c16.get('verify', {}).get('value', float('nan')):.2f} ms vs "
+                     f"{c16.get('verify', {}).get('cpu_baseline', {}).get('value', float('nan')):.1f} ms.")
+    gp = x.get("golden_proofs_verify_k11", {})
+    if "accepted" in gp:
+        parts.append(f"* the reference's {gp['proofs']} stored k=11 proofs through the engine: accepted = {gp['accepted']}, tampered rejected = {gp['tampered_rejected']}; "
+                     f"{gp['gpu_ms_per_proof_wall']:.1f} ms wall per proof (the Python restatement of plonk::verify_proof dominates), the path's tail "
+                     f"(use_challenges + eval) {gp['gpu_ms_per_proof_path_tail']:.2f} ms vs {gp['cpu_baseline']['ms_per_proof_hot']:.2f} ms of hot calls on the C restatement; "
+                     f"BatchVerifier shape: {gp['batch']['gpu_ms_accumulate_and_eval']:.1f} ms to accumulate all {gp['proofs']} MSMs and evaluate once (accepted = {gp['batch']['accepted']}).")
     parts.append(f"* clocks {d['clocks']}\n")
 open(f"{dst}/{tag}_summary.md", "w").write("\n".join(parts))
 print(open(f"{dst}/{tag}_summary.md").read()[:3000])
