@@ -30,7 +30,14 @@ import numpy as np
 from oracle import cref, pasta
 from tests import prover_replay as R
 
-DELTA_EXP_T = None
+
+
+def _ints_to_bytes(xs) -> np.ndarray:                             # 32-byte little-endian rows (no oracle code on the engine's path)
+    return np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in xs), dtype=np.uint8).reshape(-1, 32).copy()
+
+
+def _point_bytes(pt) -> np.ndarray:                               # (x, y) -> 64 bytes x || y little-endian
+    return np.frombuffer(int(pt[0]).to_bytes(32, "little") + int(pt[1]).to_bytes(32, "little"), dtype=np.uint8).copy()
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -260,7 +267,7 @@ class EngineArm:
         return np.ascontiguousarray(xy, dtype=np.uint8).reshape(64)
 
     def commit_lagrange(self, values: List[int], blind: int) -> np.ndarray:
-        out = self.params.commit_lagrange(cref.ints_to_bytes(values), self.eng.Blind(blind))
+        out = self.params.commit_lagrange(_ints_to_bytes(values), self.eng.Blind(blind))
         return self.eng.batch_normalize(out.reshape(1, 96), self.curve)[0]
 
     def decompress(self, b32: bytes) -> np.ndarray:
@@ -415,11 +422,11 @@ def verify_proof(arm, vk: PinnedKey, proof: bytes, instances: List[List[List[int
         for (pin, ptab), prod, (pe, pne, pie, piie, pte) in zip(lookups_permuted[pr], lookups_product[pr], lookup_eval[pr]):   # lookup/verifier.rs:166-208
             pin, ptab, prod = P(pin), P(ptab), P(prod)
             queries += [Q(prod, x, pe), Q(pin, x, pie), Q(ptab, x, pte), Q(pin, x_prev, piie), Q(prod, x_next, pne)]
-    fc = [P(cref.affines_to_bytes([pt])[0]) for pt in vk.fixed_commitments]
+    fc = [P(_point_bytes(pt)) for pt in vk.fixed_commitments]
     for qi, (col, at) in enumerate(vk.fixed_queries):             # :318-330
         queries.append(Q(fc[col], rot(x, at), fixed_evals[qi]))
     for pt, ev in zip(vk.permutation_commitments, perm_common):   # permutation/verifier.rs:231-240
-        queries.append(Q(P(cref.affines_to_bytes([pt])[0]), x, ev))
+        queries.append(Q(P(_point_bytes(pt)), x, ev))
     queries.append(Q(h_commitment, x, expected_h))                # vanishing/verifier.rs:121-138
     queries.append(Q(P(random_poly_commitment), x, random_eval))
     try:
@@ -456,4 +463,4 @@ def load_golden_proofs():
 
 def scalar_delta(modulus: int) -> int:
     """F::DELTA = MULTIPLICATIVE_GENERATOR^(2^S) (pasta_curves; used at plonk/permutation/keygen.rs:131, verifier.rs:172)."""
-    return pow(pasta.MULT_GEN, 1 << pasta.S_2ADICITY, modulus)
+    return pow(5, 1 << 32, modulus)                               # MULTIPLICATIVE_GENERATOR = 5, S = 32 for both Pasta fields
