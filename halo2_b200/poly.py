@@ -479,6 +479,23 @@ class EvaluationDomain:
     def extended_len(self) -> int:
         return 1 << self.extended_k
 
+    def rotate_omega(self, value: int, rotation: int) -> int:
+        """domain.rs:408-418: value * omega^rotation (a handful of scalars per proof: host arithmetic)."""
+        return value * pow(self.omega if rotation >= 0 else self.omega_inv, abs(rotation), self.m) % self.m
+
+    def l_i_range(self, x: int, xn: int, rotations) -> list:
+        """domain.rs:447-472: l_i(x) for every rotation i in `rotations` (xn = x^n), l_i(omega^i) = 1:
+        l_i(x) = omega^i (x^n - 1) / (n (x - omega^i)); the reference batch-inverts the denominators, and panics (division by
+        zero in the inversion's unwrap-free path gives 0) only for x on the domain, which a challenge never is."""
+        m = self.m
+        rotations = list(rotations)
+        common = (xn - 1) * self.ifft_divisor % m                 # (x^n - 1) * barycentric_weight, :465
+        out = []
+        for r in rotations:
+            d = (x - self.rotate_omega(1, r)) % m
+            out.append(self.rotate_omega((pow(d, -1, m) if d else 0) * common % m, r))
+        return out
+
     def lagrange_to_coeff(self, a) -> np.ndarray:
         """domain.rs:227-237 (+ ifft :375-383)."""
         arr = _l.as_u8(a, 32).copy()

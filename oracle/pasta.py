@@ -500,6 +500,18 @@ class EvaluationDomain:
     def extended_len(self) -> int:
         return 1 << self.extended_k
 
+    def rotate_omega(self, value: int, rotation: int) -> int:
+        """domain.rs:408-418."""
+        return value * pow(self.omega if rotation >= 0 else self.omega_inv, abs(rotation), self.m) % self.m
+
+    def l_i_range(self, x: int, xn: int, rotations: Sequence[int]) -> List[int]:
+        """domain.rs:447-472: results[i] = rotate_omega((x - omega^rot)^-1 * (xn - 1) * barycentric_weight, rot)."""
+        m = self.m
+        results = [(x - self.rotate_omega(1, r)) % m for r in rotations]
+        results = [inv(v, m) if v else 0 for v in results]        # batch_invert (:462): zeros stay zero
+        common = (xn - 1) * self.ifft_divisor % m                 # barycentric_weight = 1 / n (:118-128)
+        return [self.rotate_omega(v * common % m, r) for v, r in zip(results, rotations)]
+
     def distribute_powers_zeta(self, a: List[int], into_coset: bool) -> None:
         """domain.rs:357-373."""
         cp = [self.g_coset, self.g_coset_inv] if into_coset else [self.g_coset_inv, self.g_coset]

@@ -165,3 +165,24 @@ def test_lagrange_interpolate(field):
         co = pasta.lagrange_interpolate(m, pts, ev)
         assert len(co) == npts and [pasta.eval_polynomial_mod(m, co, p) for p in pts] == ev
         assert lagrange_interpolate(pts, ev, m) == co
+
+
+@pytest.mark.parametrize("field", ["fq", "fp"])
+def test_l_i(field):
+    """poly/domain.rs:541-569 (`test_l_i`, pallas::Scalar, k = 3): l_i_range(x, x^n, -7..=7) against the Lagrange basis polynomials
+    built by lagrange_interpolate over the domain -- on the oracle's EvaluationDomain and on the host mirror's (host arithmetic:
+    the mirror's constructor and these two methods touch no device); rotate_omega alongside (domain.rs:408-418)."""
+    import halo2_b200
+    m = pasta.FIELDS[field]
+    for D in (pasta.EvaluationDomain(field, 1 + 1, 3), halo2_b200.EvaluationDomain(field, 1 + 1, 3, pasta.zeta_candidates(field)[0])):
+        points = [pow(D.omega, i, m) for i in range(8)]
+        basis = [pasta.lagrange_interpolate(m, points, [1 if j == i else 0 for j in range(8)]) for i in range(8)]
+        x = cref.bytes_to_ints(cref.gen_scalars(field, SEED + 77, 1))[0]
+        xn = pow(x, 8, m)
+        ev = D.l_i_range(x, xn, range(-7, 8))
+        assert len(ev) == 15
+        for i in range(8):
+            assert pasta.eval_polynomial_mod(m, basis[i], x) == ev[7 + i]
+            assert pasta.eval_polynomial_mod(m, basis[(8 - i) % 8], x) == ev[7 - i]
+        assert D.rotate_omega(x, 3) == x * pow(D.omega, 3, m) % m and D.rotate_omega(x, -2) * pow(D.omega, 2, m) % m == x
+        assert D.rotate_omega(D.rotate_omega(x, 5), -5) == x
