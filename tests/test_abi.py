@@ -65,5 +65,5 @@ def test_product_does_not_import_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 for pat in (r"(from|import)\s+oracle", r"halo2_oracle", r"oracle[/.](pasta|cref|_build|_ref)",
-                            r"(from|import)\s+tests", r"libh2_kernel_emul"):
+                            r"(from|import)\s+tests", r"libh2_kernel_emul", r"fake_engine", r"FakeLib"):
                     assert not re.search(pat, src), (fn, pat)
