@@ -16,7 +16,9 @@ A "step" is one pass of the hot path over one batch of synthetic input:
   * more single-GPU side measurements under `extra` (N = 1 only, each next to the C restatement): `create_proof_k14_replay`
     (the prover's hot-path call schedule), `resident_column_k14`, `params_lagrange_k14` (Params::new's
     EC-FFT), `poly_reductions_k14` (eval_polynomial / kate_division), `quotient_pipeline_k14` (coeff_to_extended -> Ast ->
-    divide_by_vanishing_poly -> extended_to_coeff on resident polynomials).
+    divide_by_vanishing_poly -> extended_to_coeff on resident polynomials), `create_proof_k14_replay.verify` (the verifier's side of the
+    same proof: multiopen MSM, the opening, compute_s on the device, one multiexp over the resident generators),
+    `golden_proofs_verify_k11` (the reference's fifteen stored k = 11 proofs verified through the engine under their pinned keys).
 
 `--impl reference` times that CPU restatement alone (the reference arm).
 """
