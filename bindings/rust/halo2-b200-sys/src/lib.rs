@@ -438,3 +438,68 @@ pub fn best_multiexp_multi_gpu<C: B200Curve>(coeffs: &[C::Scalar], bases: &[C]) 
 pub fn lookup_permute_resident(input: u64, table: u64, usable_rows: usize, out_input: u64, out_table: u64) -> bool {
     unsafe { h2_poly_lookup_permute(input, table, usable_rows, out_input, out_table) == 0 }
 }
+
+/// The verifier's `g_scalars` (poly/commitment/msm.rs:12) kept in HBM: what `MSM<C>` holds under the `b200` feature instead of
+/// `Option<Vec<C::Scalar>>`.  `compute_s` (poly/commitment/verifier.rs:156-171) is built on the device straight into it,
+/// `scale` / `add_msm` (msm.rs:37-62, :122-135) are one elementwise pass, and `eval` (msm.rs:138-177) commits the resident vector
+/// against the resident generators (`w_scalar` rides on base index n) and adds the multiexp of the few dozen other terms.
+pub struct ResidentGScalars<C: B200Curve> {
+    handle: u64,
+    n: usize,
+    _c: std::marker::PhantomData<C>,
+}
+impl<C: B200Curve> ResidentGScalars<C>
+where
+    C::Base: PrimeField<Repr = [u8; 32]>,
+{
+    /// `vec![C::Scalar::ZERO; params.n]` (msm.rs:91): zero-filled on the device.
+    pub fn zeros(n: usize) -> Self {
+        let mut handle = 0u64;
+        check(unsafe { h2_poly_alloc(C::SCALAR_FIELD_ID, n, &mut handle) });
+        ResidentGScalars { handle, n, _c: std::marker::PhantomData }
+    }
+    /// `g_scalars[0] += constant` (msm.rs:87-95).
+    pub fn add_constant_term(&mut self, constant: C::Scalar) {
+        check(unsafe { h2_poly_add_at(self.handle, 0, constant.to_repr().as_ref().as_ptr() as *const c_void, REPR_CANONICAL) });
+    }
+    /// `self.add_to_g_scalars(&compute_s(u, init))` (verifier.rs:36-38) in one pass; panics for an empty `u` like the reference (:157).
+    pub fn add_compute_s(&mut self, u: &[C::Scalar], init: C::Scalar) {
+        assert_eq!(1usize << u.len(), self.n);
+        let ub = scalars_to_bytes(u);
+        check(unsafe {
+            h2_poly_compute_s(self.handle, ub.as_ptr() as *const c_void, u.len() as u32, init.to_repr().as_ref().as_ptr() as *const c_void,
+                              1, REPR_CANONICAL)
+        });
+    }
+    /// `g_scalar *= factor` for every entry (msm.rs:126-131).
+    pub fn scale(&mut self, factor: C::Scalar) {
+        check(unsafe {
+            h2_poly_scale_add(self.handle, factor.to_repr().as_ref().as_ptr() as *const c_void, 0, std::ptr::null(), self.n, REPR_CANONICAL)
+        });
+    }
+    /// `self = factor * self + other`: `acc.scale(r); acc.add_msm(&msm)` of BatchVerifier::finalize (plonk/verifier/batch.rs:83-93)
+    /// for the vector part, one pass; `factor = 1` is the plain `add_to_g_scalars` of msm.rs:52-54.
+    pub fn scale_add(&mut self, factor: C::Scalar, other: &Self) {
+        assert_eq!(self.n, other.n);
+        let one = C::Scalar::ONE.to_repr();
+        check(unsafe {
+            h2_poly_scale_add(self.handle, factor.to_repr().as_ref().as_ptr() as *const c_void, other.handle,
+                              one.as_ref().as_ptr() as *const c_void, self.n, REPR_CANONICAL)
+        });
+    }
+    /// The multiexp of `MSM::eval` (msm.rs:142-175): <g_scalars, g> + w_scalar * w over the resident set `g ++ [w, u]`, plus the
+    /// other terms (`u`, the proof's commitments) through the plain MSM; the caller tests `is_identity()`.
+    pub fn eval_with(&self, g: &ResidentBases<C>, w_scalar: C::Scalar, other_scalars: &[C::Scalar], other_bases: &[C]) -> C::Curve {
+        let mut out = [0u8; 96];
+        check(unsafe {
+            h2_msm_registered_polys(g.handle, &self.handle as *const u64, 1, self.n, w_scalar.to_repr().as_ref().as_ptr() as *const c_void,
+                                    REPR_CANONICAL, out.as_mut_ptr() as *mut c_void)
+        });
+        point_from_xyz::<C>(&out) + best_multiexp::<C>(other_scalars, other_bases)
+    }
+}
+impl<C: B200Curve> Drop for ResidentGScalars<C> {
+    fn drop(&mut self) {
+        unsafe { h2_poly_free(self.handle) };
+    }
+}
