@@ -365,6 +365,7 @@ extern "C" int h2_poly_compute_s(uint64_t dst, const void *u, uint32_t k, const 
     if (require_ready()) return 1;
     PolyBuf *d = find_poly(dst);
     if (!d) return fail("h2_poly_compute_s: unknown polynomial handle");
+    if (!u || !init) return fail("h2_poly_compute_s: null challenge vector or init");
     if (k == 0) return fail("h2_poly_compute_s: no challenges (assert!(!u.is_empty()), poly/commitment/verifier.rs:157)");
     if (k > 30 || d->len < ((size_t)1 << k)) return fail("h2_poly_compute_s: the polynomial holds fewer than 2^k elements");
     if (d->field == H2_FIELD_FP) return compute_s_run<FpParams>(d, u, k, init, accumulate, repr);
