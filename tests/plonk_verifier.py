@@ -252,6 +252,21 @@ class OracleArm:
     def finish(self, guard) -> bool:                              # SingleVerifier::process, plonk/verifier.rs:53-62
         return guard.use_challenges().eval()
 
+    def accumulate(self, guard) -> bool:                          # AccumulationVerifier::process, tests/plonk_api.rs:530-544
+        g = guard.compute_g()
+        msm, _ = guard.use_g(g)
+        return msm.eval()
+
+    def use_challenges(self, guard):                              # BatchStrategy::process, plonk/verifier/batch.rs:43-51
+        return guard.use_challenges()
+
+    def batch_eval(self, msms, factors) -> bool:                  # BatchVerifier::finalize, batch.rs:83-131
+        acc = self.msm()
+        for f, m_i in zip(factors, msms):
+            acc.scale(f)
+            acc.add_msm(m_i)
+        return acc.eval()
+
     def close(self):
         pass
 
@@ -289,6 +304,28 @@ class EngineArm:
         finally:
             msm.close()
 
+    def accumulate(self, guard) -> bool:
+        g = guard.compute_g()
+        msm, _ = guard.use_g(g)
+        try:
+            return msm.eval()
+        finally:
+            msm.close()
+
+    def use_challenges(self, guard):
+        return guard.use_challenges()
+
+    def batch_eval(self, msms, factors) -> bool:
+        acc = self.msm()
+        try:
+            for f, m_i in zip(factors, msms):
+                acc.scale_add_msm(f, m_i)                         # acc.scale(f); acc.add_msm(&m_i), the vector part in one pass
+            return acc.eval()
+        finally:
+            acc.close()
+            for m_i in msms:
+                m_i.close()
+
     def close(self):
         self.params.close()
 
@@ -296,8 +333,11 @@ class EngineArm:
 # ------------------------------------------------------------------------------------------------------------------------
 # plonk::verify_proof
 # ------------------------------------------------------------------------------------------------------------------------
-def verify_proof(arm, vk: PinnedKey, proof: bytes, instances: List[List[List[int]]], delta: int) -> bool:
-    """plonk/verifier.rs:67-347 with a SingleVerifier.  `instances[proof][column]` = that instance column's values; `delta` = the
+def verify_proof(arm, vk: PinnedKey, proof: bytes, instances: List[List[List[int]]], delta: int, process=None) -> bool:
+    """plonk/verifier.rs:67-347.  `process(guard) -> bool` is the VerificationStrategy (:21-62): by default the arm's
+    SingleVerifier (`finish`); `arm.accumulate` is the AccumulationVerifier of the reference's test (tests/plonk_api.rs:515-545),
+    and a closure that keeps `arm.use_challenges(guard)` for `arm.batch_eval` is BatchVerifier's BatchStrategy
+    (plonk/verifier/batch.rs:24-52, :83-131).  `instances[proof][column]` = that instance column's values; `delta` = the
     scalar field's DELTA (plonk/permutation/verifier.rs:172).  Returns False where the reference returns an Err or a failed eval."""
     m = vk.scalar_modulus
     n = 1 << vk.k
@@ -438,7 +478,7 @@ def verify_proof(arm, vk: PinnedKey, proof: bytes, instances: List[List[List[int
             h_commitment.close()
     if T.pos != len(proof):
         return False                                              # (the reference leaves trailing bytes unread; the golden proof has none)
-    return arm.finish(guard)
+    return (process or arm.finish)(guard)
 
 
 def arm_errors(arm):

@@ -102,3 +102,31 @@ def test_golden_proof_through_the_host_mirror(gens, name):
         bad[len(bad) - 40] ^= 1
         assert not PV.verify_proof(arm, vk, bytes(bad), case["instances"], DELTA)
         arm.close()
+
+
+@pytest.mark.parametrize("engine", [False, True], ids=["oracle", "host-mirror"])
+def test_golden_proof_under_every_strategy(gens, engine):
+    """The three strategies the reference's test runs its proofs through (tests/plonk_api.rs:497-583) on the stored proof:
+    SingleVerifier, the AccumulationVerifier (Guard::compute_g + use_g, verifier.rs:45-62) and BatchVerifier (the same proof
+    twice, as the reference does at :567-577, every MSM scaled by a random factor and accumulated: plonk/verifier/batch.rs:83-131);
+    a batch with one tampered proof fails."""
+    import contextlib
+    import halo2_b200
+    case = CASES[0]
+    vk = PV.PinnedKey(case["key_text"])
+    with (fake_engine.installed() if engine else contextlib.nullcontext()):
+        arm = PV.EngineArm(halo2_b200, "vesta", 5, *gens[5]) if engine else FastOracleArm("vesta", 5, *gens[5])
+        if not engine:
+            arm.accumulate = lambda guard: PV.OracleArm.accumulate(arm, guard)
+        assert PV.verify_proof(arm, vk, case["proof"], case["instances"], DELTA)
+        assert PV.verify_proof(arm, vk, case["proof"], case["instances"], DELTA, process=arm.accumulate)
+        bad = bytearray(case["proof"])
+        bad[-40] ^= 1
+        assert not PV.verify_proof(arm, vk, bytes(bad), case["instances"], DELTA, process=arm.accumulate)
+        factors = cref.bytes_to_ints(cref.gen_scalars("fp", 12345, 2))
+        for proofs, want in (([case["proof"], case["proof"]], True), ([case["proof"], bytes(bad)], False)):
+            kept = []
+            keep = lambda guard: kept.append(arm.use_challenges(guard)) or True
+            assert all(PV.verify_proof(arm, vk, p, case["instances"], DELTA, process=keep) for p in proofs)
+            assert arm.batch_eval(kept, factors) == want
+        arm.close()
