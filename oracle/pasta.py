@@ -42,7 +42,13 @@ PARITY PINNING STATUS: PINNED on reference-held vectors.
   * best_fft at G = scalar has no reference-held input->output vector of its own; it is the same
     butterfly network as the pinned G = curve-point instantiation (one generic function,
     arithmetic.rs:192-295), checked against the DFT definition for true roots of unity and, through
-    the domain constants it is used with, against the pinned omegas.
+    the domain constants it is used with, against the pinned omegas -- and it is tied to the
+    reference's verification equation end to end: a REAL proof of the reference's own test circuit
+    (tests/plonk_api.rs:21-420), produced by this file's lagrange_to_coeff / coeff_to_extended /
+    extended_to_coeff / divide_by_vanishing_poly / permute_expression_pair / kate_division /
+    eval_polynomial / commit / multiopen / opening restatements under the reference's golden verifying
+    key (tests/plonk_prover.py), is accepted by the golden-proof-pinned verifier
+    (tests/test_real_proof.py); a wrong butterfly or zeta power anywhere makes it fail.
   * the verifier's side -- MSM, verify_proof / Guard, compute_s / compute_b, the multiopen verifier, lagrange_interpolate -- on
     the reference's sixteen GOLDEN PROOFS (halo2_proofs/tests/plonk_api_proof.bin and the fifteen proof_*.bin of
     halo2_gadgets/src/test_circuits/circuit_data/): every one is accepted under its pinned key, every tampered one rejected

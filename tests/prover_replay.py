@@ -54,6 +54,15 @@ class Blake2bTranscript:
         enc[31] |= (b[32] & 1) << 7                            # C::to_bytes: x with the LSB of y in the top bit
         self.proof += enc
 
+    def common_point(self, xy) -> None:                       # :205-216: into the hash only
+        b = bytes(np.ascontiguousarray(xy, dtype=np.uint8).reshape(64))
+        if b == bytes(64):
+            raise ValueError("cannot write points at infinity to the transcript")
+        self.state.update(b"\x01" + b)
+
+    def common_scalar(self, s: int) -> None:                  # :218-223
+        self.state.update(b"\x02" + int(s).to_bytes(32, "little"))
+
     def write_scalar(self, s: int) -> None:                   # :188-192, :218-223
         b = int(s).to_bytes(32, "little")
         self.state.update(b"\x02" + b)

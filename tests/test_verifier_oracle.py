@@ -145,6 +145,12 @@ class _WriteT:
     def write_scalar(self, s):
         self.T.write_scalar(s)
 
+    def common_point(self, pt):
+        self.T.common_point(cref.affines_to_bytes([pt])[0])
+
+    def common_scalar(self, s):
+        self.T.common_scalar(s)
+
     def squeeze_challenge(self):
         return self.T.squeeze_challenge()
 
