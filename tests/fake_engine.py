@@ -222,6 +222,101 @@ class FakeLib:
                 d[n - 1] = 0
         return 0
 
+    # ---- transforms (C restatement) and the elementwise programs / scans (the device bodies on the host emulation) ----
+    def _fe_int(self, p):
+        return int.from_bytes(_rd(p, 32).tobytes(), "little")
+
+    def h2_poly_lagrange_to_coeff(self, dst, src, k, omega_inv, divisor, repr_):
+        self._log("h2_poly_lagrange_to_coeff")
+        f, a = self.polys[_v(src)]
+        n = 1 << _v(k)
+        self.polys[_v(dst)][1][:n] = cref.ifft(f, np.ascontiguousarray(a[:n]), self._fe_int(omega_inv), _v(k), self._fe_int(divisor), 2)
+        return 0
+
+    def h2_poly_coeff_to_extended(self, dst, src, k, ext_k, zeta, ext_omega, repr_):
+        self._log("h2_poly_coeff_to_extended")
+        f, a = self.polys[_v(src)]
+        self.polys[_v(dst)][1][:1 << _v(ext_k)] = cref.coeff_to_extended(f, np.ascontiguousarray(a[:1 << _v(k)]), _v(k), _v(ext_k), self._fe_int(zeta),
+                                                                        self._fe_int(ext_omega), 2)
+        return 0
+
+    def h2_poly_extended_to_coeff(self, dst, src, ext_k, ext_omega_inv, ext_divisor, zeta, out_len, repr_):
+        self._log("h2_poly_extended_to_coeff")
+        f, a = self.polys[_v(src)]
+        self.polys[_v(dst)][1][:_v(out_len)] = cref.extended_to_coeff(f, np.ascontiguousarray(a[:1 << _v(ext_k)]), _v(ext_k), self._fe_int(ext_omega_inv),
+                                                                     self._fe_int(ext_divisor), self._fe_int(zeta), _v(out_len), 2)
+        return 0
+
+    def h2_poly_divide_by_vanishing(self, poly, ext_k, t_evals, t_len, repr_):
+        self._log("h2_poly_divide_by_vanishing")
+        f, a = self.polys[_v(poly)]
+        m = pasta.FIELDS[f]
+        t = cref.bytes_to_ints(_rd(t_evals, 32 * _v(t_len)).reshape(-1, 32))
+        vals = cref.bytes_to_ints(a[:1 << _v(ext_k)])
+        a[:1 << _v(ext_k)] = cref.ints_to_bytes([x * t[i % len(t)] % m for i, x in enumerate(vals)])
+        return 0
+
+    def h2_poly_eval_ast(self, out, polys, n_polys, log_n, code, n_code, consts, n_consts, omega, lin_base, repr_):
+        self._log("h2_poly_eval_ast")
+        n_polys, log_n, n_code, n_consts = _v(n_polys), _v(log_n), _v(n_code), _v(n_consts)
+        n = 1 << log_n
+        prog = np.frombuffer(ctypes.string_at(_v(code), 16 * n_code), dtype=np.uint32).reshape(-1, 4).copy()
+        depth = 0                                                 # the library's own validation (capi_poly.cu): operand stack of 24
+        for op, arg, _, _ in prog:
+            if op in (0, 1, 2):
+                depth += 1
+            elif op in (3, 4):
+                depth -= 1
+            if depth > 24 or depth < 1:
+                return self._fail("h2_poly_eval_ast: operand stack out of range")
+        if depth != 1:
+            return self._fail("h2_poly_eval_ast: the program leaves more than one value")
+        if _v(out) in [int(polys[i]) for i in range(n_polys)]:
+            return self._fail("h2_poly_eval_ast: the output cannot be one of the operands")
+        f = self.polys[_v(out)][0]
+        if self.polys[_v(out)][1].shape[0] < n or any(self.polys[int(polys[i])][1].shape[0] < n for i in range(n_polys)):
+            return self._fail("h2_poly_eval_ast: a polynomial holds fewer than 2^log_n elements")
+        stack = np.ascontiguousarray(np.stack([self.polys[int(polys[i])][1][:n] for i in range(n_polys)])) if n_polys else np.zeros((1, n, 32), dtype=np.uint8)
+        cs = _rd(consts, 32 * n_consts) if n_consts else np.zeros(32, dtype=np.uint8)
+        res = np.zeros((n, 32), dtype=np.uint8)
+        self.emu.emu_ast_eval(cref.FIELD_ID[f], cref._p(stack), n_polys, log_n, prog.ctypes.data_as(ctypes.c_void_p), n_code, cref._p(cs), n_consts,
+                              cref._p(_rd(omega, 32)), cref._p(_rd(lin_base, 32)), cref._p(res))
+        self.polys[_v(out)][1][:n] = res
+        return 0
+
+    def h2_poly_batch_invert(self, poly, n):
+        self._log("h2_poly_batch_invert")
+        f, a = self.polys[_v(poly)]
+        n = _v(n)
+        res = np.zeros((n, 32), dtype=np.uint8)
+        self.emu.emu_grand_product(cref.FIELD_ID[f], 0, cref._p(np.ascontiguousarray(a[:n])), ctypes.c_uint64(n), None, cref._p(res))
+        a[:n] = res
+        return 0
+
+    def h2_poly_running_product(self, dst, src, n, init, repr_):
+        self._log("h2_poly_running_product")
+        if _v(dst) == _v(src):
+            return self._fail("h2_poly_running_product: the product cannot overwrite its factors")
+        f, a = self.polys[_v(src)]
+        n = _v(n)
+        res = np.zeros((n, 32), dtype=np.uint8)
+        self.emu.emu_grand_product(cref.FIELD_ID[f], 1, cref._p(np.ascontiguousarray(a[:n])), ctypes.c_uint64(n), cref._p(_rd(init, 32)), cref._p(res))
+        self.polys[_v(dst)][1][:n] = res
+        return 0
+
+    def h2_poly_lookup_permute(self, inp, tab, usable, out_in, out_tab):
+        self._log("h2_poly_lookup_permute")
+        f, a = self.polys[_v(inp)]
+        t = self.polys[_v(tab)][1]
+        n, u = a.shape[0], _v(usable)
+        oa, ot = np.ascontiguousarray(self.polys[_v(out_in)][1][:n]), np.ascontiguousarray(self.polys[_v(out_tab)][1][:n])
+        rc = self.emu.emu_lookup_permute(cref.FIELD_ID[f], cref._p(np.ascontiguousarray(a)), cref._p(np.ascontiguousarray(t[:n])), ctypes.c_size_t(n),
+                                         ctypes.c_size_t(u), cref._p(oa), cref._p(ot))
+        if rc != 0:
+            return self._fail("h2_poly_lookup_permute: an input value does not occur in the table")
+        self.polys[_v(out_in)][1][:n], self.polys[_v(out_tab)][1][:n] = oa, ot
+        return 0
+
     # ---- the opening's round loop: the reference's own folding loop, one round per call (poly/commitment/prover.rs:100-142) ----
     def h2_ipa_begin_poly(self, bases_handle, k, poly, x3, repr_, out_session):
         f, a = self.polys[_v(poly)]

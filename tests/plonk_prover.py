@@ -268,3 +268,266 @@ def create_proof(c: pasta.Curve, g, g_lagrange, w, u, vk: PV.PinnedKey, fixed: L
     queries.append(Q(x, h_poly, h_blind))                          # vanishing/prover.rs:153-175
     queries.append(Q(x, random_poly, random_blind))
     pasta.multiopen_create_proof(c, g, w, u, rng, transcript, queries)                      # :726
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The same prover through the ENGINE's reference-facing API (halo2_b200: resident polynomials, device transforms, Ast programs,
+# batch_invert / running product, the lookup permutation, fixed-base commits, the multi-point opening) -- the composition a
+# patched plonk::create_proof would make.  With the same seeded randomness it writes THE SAME PROOF BYTES as the oracle version
+# above.  (tests/test_real_proof.py runs it over the ABI stand-in: transforms and group operations through the oracle, the
+# Ast evaluator / scans / lookup permutation through the host-emulated device bodies.)
+# ------------------------------------------------------------------------------------------------------------------------
+def _to_ast(eng, e, fixed_l, advice_l, instance_l):
+    """Expression::evaluate (circuit.rs:514-611) with the prover's closures (prover.rs:481-516): queries become leaves with rotations."""
+    Ast = eng.Ast
+    if e[0] == "struct":
+        leaves = {"Fixed": fixed_l, "Advice": advice_l, "Instance": instance_l}[e[1]]
+        return leaves[e[2]["column_index"]].with_rotation(e[2]["rotation"][2][0])
+    name, args = e[1], e[2]
+    if name == "Constant":
+        return Ast.constant_term(args[0])
+    if name == "Negated":
+        return -_to_ast(eng, args[0], fixed_l, advice_l, instance_l)
+    if name == "Sum":
+        return _to_ast(eng, args[0], fixed_l, advice_l, instance_l) + _to_ast(eng, args[1], fixed_l, advice_l, instance_l)
+    if name == "Product":
+        return _to_ast(eng, args[0], fixed_l, advice_l, instance_l) * _to_ast(eng, args[1], fixed_l, advice_l, instance_l)
+    if name == "Scaled":
+        return _to_ast(eng, args[0], fixed_l, advice_l, instance_l) * args[1]
+    raise ValueError(name)
+
+
+def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, instances, rng, transcript, zeta: int, delta: int) -> None:
+    """plonk::create_proof (prover.rs:43-727) on the engine.  `params`: halo2_b200.Params with u; `rng`: scalar() -> int,
+    poly(n) -> (n, 32) bytes; `transcript`: tests/prover_replay.Blake2bTranscript (points as (64,) uint8)."""
+    Ast, Blind = eng.Ast, eng.Blind
+    field = {pasta.P_MOD: "fp", pasta.Q_MOD: "fq"}[vk.scalar_modulus]
+    m = vk.scalar_modulus
+    k, n = vk.k, 1 << vk.k
+    bf = vk.blinding_factors()
+    usable = n - (bf + 1)
+    cs_degree = vk.degree()
+    chunk_len = cs_degree - 2
+    D = eng.EvaluationDomain(field, cs_degree, k, zeta)
+    assert D.extended_k == vk.extended_k and D.omega == vk.omega
+    L = D.extended_len()
+    num_proofs = len(advice)
+    live = []
+
+    def RP(vals, length=n):
+        p = eng.ResidentPoly(field, length, PV._ints_to_bytes(vals) if vals is not None else None)
+        live.append(p)
+        return p
+
+    coeff = lambda lag: D.lagrange_to_coeff_resident(lag, out=RP(None))
+    ext = lambda co: D.coeff_to_extended_resident(co, out=RP(None, L))
+    commit = lambda polys, blinds, lagrange: params.commit_resident_affine(polys, [Blind(b) for b in blinds], lagrange=lagrange)
+
+    def overwrite_rows(p, start, vals):                            # rows [start, start + len) <- vals, on the device (h2_poly_copy)
+        tmp = RP(vals, len(vals))
+        p.copy_from(tmp, len(vals), src_off=0, dst_off=start)
+
+    def element(p, idx):                                           # one element back to the host
+        one = RP(None, 1)
+        one.copy_from(p, 1, src_off=idx)
+        return int.from_bytes(one.download(1)[0].tobytes(), "little")
+
+    try:
+        transcript.common_scalar(vk.transcript_repr())
+        # ---- instance and advice columns ----
+        inst_l, inst_p, inst_c = [], [], []
+        for inst in instances:
+            vals = [RP([v % m for v in col] + [0] * (n - len(col))) for col in inst]
+            if vals:
+                for cm in commit(vals, [1] * len(vals), True):
+                    transcript.common_point(cm)
+            polys = [coeff(v) for v in vals]
+            inst_l.append(vals), inst_p.append(polys), inst_c.append([ext(p) for p in polys])
+        adv_l, adv_p, adv_c, adv_b = [], [], [], []
+        for cols in advice:
+            vals = [RP([v % m for v in col[:usable]] + [rng.scalar() for _ in range(n - usable)]) for col in cols]
+            blinds = [rng.scalar() for _ in vals]
+            for cm in commit(vals, blinds, True):                   # all columns of a proof in one pass (prover.rs:290-299)
+                transcript.write_point(cm)
+            polys = [coeff(v) for v in vals]
+            adv_l.append(vals), adv_p.append(polys), adv_c.append([ext(p) for p in polys]), adv_b.append(blinds)
+        fixed_l = [RP(f) for f in fixed]
+        fixed_p = [coeff(f) for f in fixed_l]
+        fixed_c = [ext(p) for p in fixed_p]
+        sigma_l = [RP(s) for s in sigma]
+        sigma_p = [coeff(s) for s in sigma_l]
+        sigma_c = [ext(p) for p in sigma_p]
+        ind = lambda rows: ext(coeff(RP([1 if r in rows else 0 for r in range(n)])))
+        l0_c, l_blind_c, l_last_c = ind({0}), ind(set(range(n - bf, n))), ind({n - bf - 1})
+        # the Lagrange-basis evaluator (value_evaluator, prover.rs:331-365)
+        ev_l = eng.Evaluator(D, "lagrange")
+        FL = [ev_l.register_poly(p) for p in fixed_l]
+        SL = [ev_l.register_poly(p) for p in sigma_l]
+        AL = [[ev_l.register_poly(p) for p in cols] for cols in adv_l]
+        IL = [[ev_l.register_poly(p) for p in cols] for cols in inst_l]
+        theta = transcript.squeeze_challenge()
+        # ---- lookups: compressed and permuted columns ----
+        lookups = []
+        for pr in range(num_proofs):
+            per = []
+            for inp, tab in vk.lookups:
+                def compress(exprs):
+                    acc = Ast.constant_term(0)
+                    for e in exprs:
+                        acc = acc * theta + _to_ast(eng, e, FL, AL[pr], IL[pr])
+                    out = ev_l.evaluate(acc, out=RP(None))
+                    return out
+                ci, ct = compress(inp), compress(tab)
+                pi, pt = eng.permute_expression_pair_resident(ci, ct, usable, RP(None), RP(None))
+                overwrite_rows(pi, usable, [rng.scalar() for _ in range(bf + 1)])
+                overwrite_rows(pt, usable, [rng.scalar() for _ in range(bf + 1)])
+                bi = rng.scalar()
+                bt = rng.scalar()
+                cmi, cmt = commit([pi, pt], [bi, bt], True)
+                transcript.write_point(cmi)
+                transcript.write_point(cmt)
+                per.append({"ci": ci, "ct": ct, "pi": pi, "pt": pt, "pi_poly": coeff(pi), "pt_poly": coeff(pt), "bi": bi, "bt": bt})
+            lookups.append(per)
+        beta = transcript.squeeze_challenge()
+        gamma = transcript.squeeze_challenge()
+        # ---- permutation products: denominators and numerators as Ast programs, batch_invert, the running product ----
+        col_leaf = lambda pr, col: {"Advice": AL[pr], "Fixed": FL, "Instance": IL[pr]}[col[0]][col[1]]
+        perms = []
+        for pr in range(num_proofs):
+            sets, last_z = [], 1
+            for ci_ in range(0, len(vk.permutation_columns), chunk_len):
+                cols = vk.permutation_columns[ci_:ci_ + chunk_len]
+                den = None
+                for col, sl in zip(cols, SL[ci_:ci_ + chunk_len]):
+                    term = sl * beta + Ast.constant_term(gamma) + col_leaf(pr, col)
+                    den = term if den is None else den * term
+                inv_den = eng.batch_invert_resident(ev_l.evaluate(den, out=RP(None)))
+                num = ev_l.register_poly(inv_den)
+                for j, col in enumerate(cols):                      # deltaomega = delta^(global column index) * omega^row
+                    num = num * (Ast.linear_term(pow(delta, ci_ + j, m) * beta % m) + Ast.constant_term(gamma) + col_leaf(pr, col))
+                mv = ev_l.evaluate(num, out=RP(None))
+                z = eng.running_product_resident(mv, init=last_z, dst=RP(None))
+                overwrite_rows(z, n - bf, [rng.scalar() for _ in range(bf)])
+                last_z = element(z, n - (bf + 1))
+                blind = rng.scalar()
+                transcript.write_point(commit([z], [blind], True)[0])
+                zp = coeff(z)
+                sets.append({"poly": zp, "coset": ext(zp), "blind": blind})
+            perms.append(sets)
+        # ---- lookup products ----
+        for pr in range(num_proofs):
+            for lk in lookups[pr]:
+                PI, PT, CI, CT = (ev_l.register_poly(lk[kk]) for kk in ("pi", "pt", "ci", "ct"))
+                den = (PI + Ast.constant_term(beta)) * (PT + Ast.constant_term(gamma))
+                inv_den = eng.batch_invert_resident(ev_l.evaluate(den, out=RP(None)))
+                num = ev_l.register_poly(inv_den) * (CI + Ast.constant_term(beta)) * (CT + Ast.constant_term(gamma))
+                z = eng.running_product_resident(ev_l.evaluate(num, out=RP(None)), init=1, dst=RP(None))
+                overwrite_rows(z, n - bf, [rng.scalar() for _ in range(bf)])
+                lk["zb"] = rng.scalar()
+                transcript.write_point(commit([z], [lk["zb"]], True)[0])
+                lk["z_poly"] = coeff(z)
+        # ---- the vanishing argument's random polynomial ----
+        random_poly = rng.poly(n)
+        random_poly = random_poly if isinstance(random_poly, eng.ResidentPoly) else eng.ResidentPoly(field, n, random_poly)
+        live.append(random_poly)
+        random_blind = rng.scalar()
+        transcript.write_point(commit([random_poly], [random_blind], False)[0])
+        y = transcript.squeeze_challenge()
+        # ---- h(X): one Ast over the cosets, folded by y; / (X^n - 1); back to coefficients; pieces ----
+        ev_e = eng.Evaluator(D, "extended")
+        FC = [ev_e.register_poly(p) for p in fixed_c]
+        SC = [ev_e.register_poly(p) for p in sigma_c]
+        L0, LB, LL = (ev_e.register_poly(p) for p in (l0_c, l_blind_c, l_last_c))
+        one = Ast.constant_term(1)
+        active = one - (LL + LB)
+        last_rot = -(bf + 1)
+        exprs = []
+        for pr in range(num_proofs):
+            AC = [ev_e.register_poly(p) for p in adv_c[pr]]
+            IC = [ev_e.register_poly(p) for p in inst_c[pr]]
+            exprs += [_to_ast(eng, gate, FC, AC, IC) for gate in vk.gates]
+            ZC = [ev_e.register_poly(s["coset"]) for s in perms[pr]]
+            if ZC:
+                exprs.append((one - ZC[0]) * L0)
+                exprs.append((ZC[-1] * ZC[-1] - ZC[-1]) * LL)
+                for a in range(1, len(ZC)):
+                    exprs.append((ZC[a] - ZC[a - 1].with_rotation(last_rot)) * L0)
+                colc = lambda col: {"Advice": AC, "Fixed": FC, "Instance": IC}[col[0]][col[1]]
+                for a in range(len(ZC)):
+                    cols = vk.permutation_columns[a * chunk_len:(a + 1) * chunk_len]
+                    left = ZC[a].with_rotation(1)
+                    for col, sc in zip(cols, SC[a * chunk_len:(a + 1) * chunk_len]):
+                        left = left * (colc(col) + sc * beta + Ast.constant_term(gamma))
+                    right = ZC[a]
+                    for j, col in enumerate(cols):
+                        right = right * (colc(col) + Ast.linear_term(beta * pow(delta, a * chunk_len + j, m) % m) + Ast.constant_term(gamma))
+                    exprs.append((left - right) * active)
+            for lk in lookups[pr]:
+                Z_, A_, S_ = (ev_e.register_poly(ext(lk[kk])) for kk in ("z_poly", "pi_poly", "pt_poly"))
+                CI_, CT_ = (ev_e.register_poly(ext(coeff(lk[kk]))) for kk in ("ci", "ct"))
+                exprs.append((one - Z_) * L0)
+                exprs.append((Z_ * Z_ - Z_) * LL)
+                left = Z_.with_rotation(1) * (A_ + Ast.constant_term(beta)) * (S_ + Ast.constant_term(gamma))
+                right = Z_ * (CI_ + Ast.constant_term(beta)) * (CT_ + Ast.constant_term(gamma))
+                exprs.append((left - right) * active)
+                exprs.append((A_ - S_) * L0)
+                exprs.append((A_ - S_) * (A_ - A_.with_rotation(-1)) * active)
+        h_ext = ev_e.evaluate(Ast.distribute_powers(exprs, y), out=RP(None, L))
+        D.divide_by_vanishing_poly_resident(h_ext)
+        h = D.extended_to_coeff_resident(h_ext, out=RP(None, n * (cs_degree - 1)))
+        h_pieces = [RP(None).copy_from(h, n, src_off=a * n) for a in range(cs_degree - 1)]
+        h_blinds = [rng.scalar() for _ in h_pieces]
+        for cm in commit(h_pieces, h_blinds, False):
+            transcript.write_point(cm)
+        x = transcript.squeeze_challenge()
+        xn = pow(x, n, m)
+        rotx = lambda r: D.rotate_omega(x, r)
+        # ---- every evaluation in ONE batched reduction, written in the reference's order ----
+        ev_list = []
+        for pr in range(num_proofs):
+            ev_list += [(inst_p[pr][col], rotx(r)) for col, r in vk.instance_queries]
+        for pr in range(num_proofs):
+            ev_list += [(adv_p[pr][col], rotx(r)) for col, r in vk.advice_queries]
+        ev_list += [(fixed_p[col], rotx(r)) for col, r in vk.fixed_queries]
+        ev_list.append((random_poly, x))
+        ev_list += [(sp, x) for sp in sigma_p]
+        for pr in range(num_proofs):
+            sets = perms[pr]
+            for a, st in enumerate(sets):
+                ev_list += [(st["poly"], x), (st["poly"], rotx(1))]
+                if a + 1 < len(sets):
+                    ev_list.append((st["poly"], rotx(last_rot)))
+        for pr in range(num_proofs):
+            for lk in lookups[pr]:
+                ev_list += [(lk["z_poly"], x), (lk["z_poly"], rotx(1)), (lk["pi_poly"], x), (lk["pi_poly"], rotx(-1)), (lk["pt_poly"], x)]
+        for e in eng.eval_polynomial_resident([p for p, _ in ev_list], [pt for _, pt in ev_list], n=n):
+            transcript.write_scalar(e)
+        # h_poly = sum_i piece_i * xn^i, one scale_add pass per piece (vanishing/prover.rs:128-138)
+        h_poly = RP(None).copy_from(h_pieces[-1], n)
+        h_blind = h_blinds[-1]
+        for piece, b in zip(reversed(h_pieces[:-1]), reversed(h_blinds[:-1])):
+            eng.opening._scale_add(h_poly, xn, piece, 1, n)
+            h_blind = (h_blind * xn + b) % m
+        # ---- the query list and the multi-point opening ----
+        Q = eng.multiopen.ProverQuery
+        one_b = Blind(1)
+        queries = []
+        for pr in range(num_proofs):
+            queries += [Q(rotx(r), inst_p[pr][col], one_b) for col, r in vk.instance_queries]
+            queries += [Q(rotx(r), adv_p[pr][col], Blind(adv_b[pr][col])) for col, r in vk.advice_queries]
+            sets = perms[pr]
+            for st in sets:
+                queries += [Q(x, st["poly"], Blind(st["blind"])), Q(rotx(1), st["poly"], Blind(st["blind"]))]
+            for st in list(reversed(sets))[1:]:
+                queries.append(Q(rotx(last_rot), st["poly"], Blind(st["blind"])))
+            for lk in lookups[pr]:
+                queries += [Q(x, lk["z_poly"], Blind(lk["zb"])), Q(x, lk["pi_poly"], Blind(lk["bi"])), Q(x, lk["pt_poly"], Blind(lk["bt"])),
+                            Q(rotx(-1), lk["pi_poly"], Blind(lk["bi"])), Q(rotx(1), lk["z_poly"], Blind(lk["zb"]))]
+        queries += [Q(rotx(r), fixed_p[col], one_b) for col, r in vk.fixed_queries]
+        queries += [Q(x, sp, one_b) for sp in sigma_p]
+        queries.append(Q(x, h_poly, Blind(h_blind)))
+        queries.append(Q(x, random_poly, Blind(random_blind)))
+        eng.multiopen.create_proof(params, rng, transcript, queries)
+    finally:
+        for p in live:
+            p.close()

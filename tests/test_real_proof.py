@@ -99,3 +99,29 @@ def test_single_instance_and_unsatisfied_witness(setup):
     # a public input the witness does not match (the "Public input" gate, sp * (a - p))
     wrong = prove(setup, [witness()], [[[3]]], 902)
     assert not PV.verify_proof(arm, vk, wrong, [[[3]]], DELTA)
+
+
+def test_real_proof_through_the_engine_api(setup):
+    """The same prover composed from the engine's reference-facing API (tests/plonk_prover.create_proof_engine: resident
+    polynomials, device transforms, Ast programs in both bases, batch_invert + running product, the lookup permutation,
+    fixed-base commits, the batched evaluations, halo2_b200.multiopen / opening) over the ABI stand-in -- transforms and group
+    operations through the oracle, the Ast evaluator / scans / lookup permutation / scale_add through the host-emulated DEVICE
+    BODIES: with the same seeded randomness it writes THE SAME 4 160 BYTES as the oracle's prover, and the golden-proof-pinned
+    verifier accepts them."""
+    import halo2_b200
+    from tests import prover_replay as R
+    c, P, vk, fixed, sigma, gens = setup
+    inst = [[[2]], [[2]]]
+    want = prove(setup, [witness(), witness()], inst, 777)
+    with fake_engine.installed() as fake:
+        prm = halo2_b200.Params("vesta", 5, gens[0], gens[1], gens[2], u=gens[3])
+        T = R.Blake2bTranscript(M)
+        PP.create_proof_engine(halo2_b200, prm, vk, fixed, sigma, [witness(), witness()], inst, MC.SeededRng("fp", 777, True), T, ZETA, DELTA)
+        got = bytes(T.proof)
+        assert got == want
+        assert fake.calls.count("h2_poly_eval_ast") > 20 and fake.calls.count("h2_poly_lookup_permute") == 2
+        assert not fake.polys                                      # every resident polynomial the prover allocated is released
+        earm = PV.EngineArm(halo2_b200, "vesta", 5, *gens)
+        assert PV.verify_proof(earm, vk, got, inst, DELTA)
+        earm.close()
+        prm.close()
