@@ -18,7 +18,8 @@ A "step" is one pass of the hot path over one batch of synthetic input:
     EC-FFT), `poly_reductions_k14` (eval_polynomial / kate_division), `quotient_pipeline_k14` (coeff_to_extended -> Ast ->
     divide_by_vanishing_poly -> extended_to_coeff on resident polynomials), `create_proof_k14_replay.verify` (the verifier's side of the
     same proof: multiopen MSM, the opening, compute_s on the device, one multiexp over the resident generators),
-    `golden_proofs_verify_k11` (the reference's fifteen stored k = 11 proofs verified through the engine under their pinned keys).
+    `golden_proofs_verify_k11` (the reference's fifteen stored k = 11 proofs verified through the engine under their pinned keys),
+    `create_proof_k14_real` (a real proof of the reference's benchmark circuit through the engine's API, verified through the engine).
 
 `--impl reference` times that CPU restatement alone (the reference arm).
 """
@@ -427,6 +428,70 @@ def golden_proofs_verify_ms(h2, cref, threads):
                                        "plonk::verify_proof glue around them is the same Python code in both arms and is not counted here"},
             "note": "reference-held proofs and keys (tests/golden/golden_proofs.json.gz); wall = everything incl. the Python restatement of "
                     "plonk::verify_proof, the Blake2b transcript and per-point decompression calls; path tail = use_challenges + eval"}
+
+
+def real_proof_ms(h2, cref, k=None, reps=3):
+    """A REAL proof of the reference's benchmark circuit (benches/plonk.rs: StandardPlonk, 3 advice columns under one permutation,
+    4 fixed columns, one gate, minimum degree 5, every usable row filled; rebuilt in tests/bench_circuit.py) at k = 14 on the GPU:
+    plonk::create_proof composed from the engine's reference-facing API (tests/plonk_prover.create_proof_engine -- resident
+    polynomials, device transforms, Ast programs, batch_invert + running product, fixed-base commits, one batched evaluation call,
+    the multi-point opening and the opening argument), with a key generated here (commit_lagrange of the fixed / permutation
+    columns) and the proving key's polynomials resident between proofs; the proof is then VERIFIED through the engine
+    (tests/plonk_verifier.verify_proof: the verifier the reference's sixteen golden proofs pin).  Wall-clock per proof through the
+    Python composition, witness columns given as byte arrays.  No CPU arm: the pure-Python oracle prover that validates this
+    composition bit for bit at small k (tests/test_real_proof.py) would take minutes here; `create_proof_k14_replay.cpu_baseline`
+    times the same kinds and numbers of hot calls on the C restatement."""
+    from tests import bench_circuit as BC
+    from tests import multiopen_cases as MC
+    from tests import plonk_prover as PP
+    from tests import plonk_verifier as PV
+    from tests import prover_replay as R
+    k = PROVER_K if k is None else k
+    n = 1 << k
+    m = P_MOD
+    zeta = pow(5, (m - 1) // 3, m)
+    delta = PV.scalar_delta(m)
+    pts = cref.gen_points("vesta", SEED + 50, n + 2)
+    g, w, u = pts[:n], pts[n:n + 1], pts[n + 1:n + 2]
+    t0 = time.time()
+    prm = h2.Params("vesta", k, g, h2.lagrange_generators("vesta", k, g), w, u=u)
+    D = h2.EvaluationDomain("fp", BC.DEGREE, k, zeta)
+    fixed, sigma, adv = BC.columns(k, m, D.omega, delta, 2834758237 * zeta % m)
+    to_b = PV._ints_to_bytes
+    fixed_b, sigma_b, adv_b = [to_b(c_) for c_ in fixed], [to_b(c_) for c_ in sigma], [to_b(c_) for c_ in adv]
+    xy = lambda col: h2.batch_normalize(prm.commit_lagrange(col, h2.Blind(1)).reshape(1, 96), "vesta")[0]           # keygen.rs:233-236
+    as_pt = lambda b: (int.from_bytes(bytes(b[:32]), "little"), int.from_bytes(bytes(b[32:]), "little"))
+    vk = PV.PinnedKey(BC.pinned_key_text(k, D.extended_k, 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001, m, D.omega,
+                                         [as_pt(xy(c_)) for c_ in fixed_b], [as_pt(xy(c_)) for c_ in sigma_b]))
+    pk = {}
+    setup_s = time.time() - t0
+    try:
+        def prove(seed):
+            T = R.Blake2bTranscript(m)
+            PP.create_proof_engine(h2, prm, vk, fixed_b, sigma_b, [adv_b], [[]], MC.SeededRng("fp", SEED + seed, True), T, zeta, delta, pk=pk)
+            return bytes(T.proof)
+        proof = prove(200)                                         # warm-up: the proving key's polynomials, pools, graphs
+        prove(201)
+        t0 = time.time()
+        for r_ in range(reps):
+            proof = prove(202 + r_)
+        dt = (time.time() - t0) / reps
+        arm = PV.EngineArm(h2, "vesta", k, params=prm)
+        t0 = time.time()
+        accepted = PV.verify_proof(arm, vk, proof, [[]], delta)
+        verify_ms = (time.time() - t0) * 1e3
+        bad = bytearray(proof)
+        bad[len(bad) // 2] ^= 1
+        rejected = not PV.verify_proof(arm, vk, bytes(bad), [[]], delta)
+    finally:
+        PP.close_proving_key(pk)
+        prm.close()
+    return {"metric": "ms_per_real_proof", "value": dt * 1e3, "unit": "ms", "higher_is_better": False, "k": k, "proof_bytes": len(proof),
+            "accepted_by_the_verifier": bool(accepted), "tampered_rejected": bool(rejected), "verify_ms": verify_ms, "setup_ms": setup_s * 1e3,
+            "circuit": "benches/plonk.rs StandardPlonk: 3 advice columns, 1 permutation set, 4 fixed columns, 1 gate, degree 5, 2^k - 6 rows",
+            "note": "a real proof (not the replay): plonk::create_proof composed from the engine's API (tests/plonk_prover.create_proof_engine), "
+                    "verified through the engine by the pinned-key-driven verifier (tests/plonk_verifier.py).  Wall-clock per proof incl. the "
+                    "Python composition; no CPU arm (see the docstring)."}
 
 
 def quotient_pipeline_ms(h2, cref, threads, reps=5):
@@ -1025,6 +1090,7 @@ def main():
             extra["quotient_pipeline_k14"] = guarded(quotient_pipeline_ms, h2, cref, threads)
             extra["lookup_permute_k14"] = guarded(lookup_permute_ms, h2, cref)
             extra["golden_proofs_verify_k11"] = guarded(golden_proofs_verify_ms, h2, cref, threads)
+            extra["create_proof_k14_real"] = guarded(real_proof_ms, h2, cref)
             extra["create_proof_k14_replay"] = guarded(prover_replay, h2, cref, threads)
             # the top of the reference's own bench range (benches/plonk.rs: k = 8..16): the passes stop being latency-bound
             extra["create_proof_k16_replay"] = guarded(prover_replay, h2, cref, threads, 2, 16)

@@ -297,9 +297,11 @@ def _to_ast(eng, e, fixed_l, advice_l, instance_l):
     raise ValueError(name)
 
 
-def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, instances, rng, transcript, zeta: int, delta: int) -> None:
+def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, instances, rng, transcript, zeta: int, delta: int, pk=None) -> None:
     """plonk::create_proof (prover.rs:43-727) on the engine.  `params`: halo2_b200.Params with u; `rng`: scalar() -> int,
-    poly(n) -> (n, 32) bytes; `transcript`: tests/prover_replay.Blake2bTranscript (points as (64,) uint8)."""
+    poly(n) -> (n, 32) bytes; `transcript`: tests/prover_replay.Blake2bTranscript (points as (64,) uint8).  Columns are lists of
+    ints or (n, 32) uint8 arrays.  `pk`: a dict that keeps the key-dependent resident polynomials (the ProvingKey's fixed /
+    permutation polynomials and cosets, l_0 / l_blind / l_last: keygen.rs:240-331) between proofs; the caller closes its values."""
     Ast, Blind = eng.Ast, eng.Blind
     field = {pasta.P_MOD: "fp", pasta.Q_MOD: "fq"}[vk.scalar_modulus]
     m = vk.scalar_modulus
@@ -314,9 +316,11 @@ def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, ins
     num_proofs = len(advice)
     live = []
 
-    def RP(vals, length=n):
-        p = eng.ResidentPoly(field, length, PV._ints_to_bytes(vals) if vals is not None else None)
-        live.append(p)
+    def RP(vals, length=n, keep=False):
+        data = None if vals is None else (vals if hasattr(vals, "dtype") else PV._ints_to_bytes(vals))
+        p = eng.ResidentPoly(field, length, data)
+        if not keep:
+            live.append(p)
         return p
 
     coeff = lambda lag: D.lagrange_to_coeff_resident(lag, out=RP(None))
@@ -332,6 +336,7 @@ def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, ins
         one.copy_from(p, 1, src_off=idx)
         return int.from_bytes(one.download(1)[0].tobytes(), "little")
 
+    own_pk = pk is None
     try:
         transcript.common_scalar(vk.transcript_repr())
         # ---- instance and advice columns ----
@@ -345,20 +350,36 @@ def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, ins
             inst_l.append(vals), inst_p.append(polys), inst_c.append([ext(p) for p in polys])
         adv_l, adv_p, adv_c, adv_b = [], [], [], []
         for cols in advice:
-            vals = [RP([v % m for v in col[:usable]] + [rng.scalar() for _ in range(n - usable)]) for col in cols]
+            vals = []
+            for col in cols:                                        # the blinding rows are the prover's (prover.rs:276-282)
+                v = RP(col if hasattr(col, "dtype") else [x % m for x in col])
+                overwrite_rows(v, usable, [rng.scalar() for _ in range(n - usable)])
+                vals.append(v)
             blinds = [rng.scalar() for _ in vals]
             for cm in commit(vals, blinds, True):                   # all columns of a proof in one pass (prover.rs:290-299)
                 transcript.write_point(cm)
             polys = [coeff(v) for v in vals]
             adv_l.append(vals), adv_p.append(polys), adv_c.append([ext(p) for p in polys]), adv_b.append(blinds)
-        fixed_l = [RP(f) for f in fixed]
-        fixed_p = [coeff(f) for f in fixed_l]
-        fixed_c = [ext(p) for p in fixed_p]
-        sigma_l = [RP(s) for s in sigma]
-        sigma_p = [coeff(s) for s in sigma_l]
-        sigma_c = [ext(p) for p in sigma_p]
-        ind = lambda rows: ext(coeff(RP([1 if r in rows else 0 for r in range(n)])))
-        l0_c, l_blind_c, l_last_c = ind({0}), ind(set(range(n - bf, n))), ind({n - bf - 1})
+        own_pk = pk is None
+        pk = {} if pk is None else pk
+        if "fixed_l" not in pk:                                     # keygen_pk's part (keygen.rs:240-331), once per key
+            kcoeff = lambda lag: D.lagrange_to_coeff_resident(lag, out=RP(None, keep=True))
+            kext = lambda co: D.coeff_to_extended_resident(co, out=RP(None, L, keep=True))
+            pk["fixed_l"] = [RP(f, keep=True) for f in fixed]
+            pk["fixed_p"] = [kcoeff(f) for f in pk["fixed_l"]]
+            pk["fixed_c"] = [kext(p_) for p_ in pk["fixed_p"]]
+            pk["sigma_l"] = [RP(s_, keep=True) for s_ in sigma]
+            pk["sigma_p"] = [kcoeff(s_) for s_ in pk["sigma_l"]]
+            pk["sigma_c"] = [kext(p_) for p_ in pk["sigma_p"]]
+            pk["l"] = []
+            for rows in ({0}, set(range(n - bf, n)), {n - bf - 1}):
+                lag = RP([1 if r in rows else 0 for r in range(n)], keep=True)
+                co = kcoeff(lag)
+                pk["l"].append(kext(co))
+                pk.setdefault("tmp", []).extend([lag, co])
+        fixed_l, fixed_p, fixed_c = pk["fixed_l"], pk["fixed_p"], pk["fixed_c"]
+        sigma_l, sigma_p, sigma_c = pk["sigma_l"], pk["sigma_p"], pk["sigma_c"]
+        l0_c, l_blind_c, l_last_c = pk["l"]
         # the Lagrange-basis evaluator (value_evaluator, prover.rs:331-365)
         ev_l = eng.Evaluator(D, "lagrange")
         FL = [ev_l.register_poly(p) for p in fixed_l]
@@ -530,4 +551,12 @@ def create_proof_engine(eng, params, vk: PV.PinnedKey, fixed, sigma, advice, ins
         eng.multiopen.create_proof(params, rng, transcript, queries)
     finally:
         for p in live:
+            p.close()
+        if own_pk and pk:
+            close_proving_key(pk)
+
+
+def close_proving_key(pk) -> None:
+    for key in ("fixed_l", "fixed_p", "fixed_c", "sigma_l", "sigma_p", "sigma_c", "l", "tmp"):
+        for p in pk.pop(key, []):
             p.close()

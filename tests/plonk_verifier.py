@@ -274,9 +274,10 @@ class OracleArm:
 class EngineArm:
     name = "engine"
 
-    def __init__(self, eng, curve: str, k: int, g, g_lagrange, w, u):
+    def __init__(self, eng, curve: str, k: int, g=None, g_lagrange=None, w=None, u=None, params=None):
         self.eng, self.curve, self.k = eng, curve, k
-        self.params = eng.Params(curve, k, g, g_lagrange, w, u=u)
+        self._own = params is None
+        self.params = eng.Params(curve, k, g, g_lagrange, w, u=u) if params is None else params
 
     def point(self, xy):
         return np.ascontiguousarray(xy, dtype=np.uint8).reshape(64)
@@ -327,7 +328,8 @@ class EngineArm:
                 m_i.close()
 
     def close(self):
-        self.params.close()
+        if self._own:
+            self.params.close()
 
 
 # ------------------------------------------------------------------------------------------------------------------------

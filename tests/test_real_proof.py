@@ -125,3 +125,47 @@ def test_real_proof_through_the_engine_api(setup):
         assert PV.verify_proof(earm, vk, got, inst, DELTA)
         earm.close()
         prm.close()
+
+
+@pytest.mark.parametrize("k", [4, 6])
+def test_benchmark_circuit_real_proof(k):
+    """The circuit of the reference's prover benchmark (benches/plonk.rs: StandardPlonk, every usable row filled; rebuilt in
+    tests/bench_circuit.py) with a key generated here (commit_lagrange of its fixed and permutation columns, Blind::default(),
+    plonk/keygen.rs:233-236): the oracle's prover and the engine-API prover (over the ABI stand-in, the proving key's resident
+    polynomials kept between two proofs) write the same proof, and both verifiers accept it.  This is the workload
+    `bench.py`'s `extra.create_proof_k14_real` times on the GPU at k = 14."""
+    import halo2_b200
+    from tests import bench_circuit as BC
+    from tests import prover_replay as R
+    c = pasta.VESTA
+    n = 1 << k
+    pts = cref.gen_points("vesta", 99, n + 2)
+    A = cref.bytes_to_affine
+    P = pasta.Params.from_generators(c, k, [A(x) for x in pts[:n]], A(pts[n]), A(pts[n + 1]))
+    D = pasta.EvaluationDomain("fp", BC.DEGREE, k, ZETA)
+    fixed, sigma, adv = BC.columns(k, M, D.omega, DELTA, circ.A_SMALL * ZETA % M)
+    cl = lambda v: pasta.to_affine(c, pasta.best_multiexp(c, list(v) + [1], P.g_lagrange + [P.w]))
+    vk = PV.PinnedKey(BC.pinned_key_text(k, D.extended_k, c.p, M, D.omega, [cl(f) for f in fixed], [cl(s_) for s_ in sigma]))
+    assert (vk.degree(), vk.blinding_factors(), vk.extended_k) == (5, BC.BLINDING_FACTORS, k + 2)
+    W = _WriteT(M)
+    PP.create_proof(c, P.g, P.g_lagrange, P.w, P.u, vk, fixed, sigma, [adv], [[]], MC.SeededRng("fp", 5, False), W, ZETA, DELTA)
+    want = bytes(W.T.proof)
+    # 3 advice + 1 permutation product + random + 4 h pieces + f + s + 2k rounds; 3 + 4 + 1 + 3 + 2 evaluations + the q's + c, f
+    gens = (cref.affines_to_bytes(P.g), cref.affines_to_bytes(P.g_lagrange), cref.affines_to_bytes([P.w]), cref.affines_to_bytes([P.u]))
+    assert PV.verify_proof(PV.OracleArm("vesta", k, *gens), vk, want, [[]], DELTA)
+    with fake_engine.installed() as fake:
+        prm = halo2_b200.Params("vesta", k, gens[0], gens[1], gens[2], u=gens[3])
+        pk = {}
+        adv_bytes = [cref.ints_to_bytes(col) for col in adv]
+        for seed, expect in ((5, want), (6, None)):
+            T = R.Blake2bTranscript(M)
+            PP.create_proof_engine(halo2_b200, prm, vk, fixed, sigma, [adv_bytes], [[]], MC.SeededRng("fp", seed, True), T, ZETA, DELTA, pk=pk)
+            got = bytes(T.proof)
+            assert expect is None or got == expect
+            earm = PV.EngineArm(halo2_b200, "vesta", k, params=prm)
+            assert PV.verify_proof(earm, vk, got, [[]], DELTA)
+            earm.close()
+        assert pk and all(p._h.value for p in pk["fixed_c"])           # the key's polynomials stayed resident between the proofs
+        PP.close_proving_key(pk)
+        assert not fake.polys
+        prm.close()
