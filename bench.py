@@ -430,7 +430,7 @@ def golden_proofs_verify_ms(h2, cref, threads):
                     "plonk::verify_proof, the Blake2b transcript and per-point decompression calls; path tail = use_challenges + eval"}
 
 
-def real_proof_ms(h2, cref, k=None, reps=3):
+def real_proof_ms(h2, cref, k=None, reps=3, threads=None):
     """A REAL proof of the reference's benchmark circuit (benches/plonk.rs: StandardPlonk, 3 advice columns under one permutation,
     4 fixed columns, one gate, minimum degree 5, every usable row filled; rebuilt in tests/bench_circuit.py) at k = 14 on the GPU:
     plonk::create_proof composed from the engine's reference-facing API (tests/plonk_prover.create_proof_engine -- resident
@@ -438,9 +438,10 @@ def real_proof_ms(h2, cref, k=None, reps=3):
     the multi-point opening and the opening argument), with a key generated here (commit_lagrange of the fixed / permutation
     columns) and the proving key's polynomials resident between proofs; the proof is then VERIFIED through the engine
     (tests/plonk_verifier.verify_proof: the verifier the reference's sixteen golden proofs pin).  Wall-clock per proof through the
-    Python composition, witness columns given as byte arrays.  No CPU arm: the pure-Python oracle prover that validates this
-    composition bit for bit at small k (tests/test_real_proof.py) would take minutes here; `create_proof_k14_replay.cpu_baseline`
-    times the same kinds and numbers of hot calls on the C restatement."""
+    Python composition, witness columns given as byte arrays.  CPU arm: the same prover on the C restatement
+    (tests/plonk_prover.CrefProver, validated bit for bit against the big-integer oracle prover at small k), same randomness, counting
+    ONLY its hot-path calls (commitments, transforms, eval_polynomial, kate_division, the opening's round loop) like the replay's CPU
+    arm; the two proofs are compared byte for byte (`transcript_identical`)."""
     from tests import bench_circuit as BC
     from tests import multiopen_cases as MC
     from tests import plonk_prover as PP
@@ -454,7 +455,8 @@ def real_proof_ms(h2, cref, k=None, reps=3):
     pts = cref.gen_points("vesta", SEED + 50, n + 2)
     g, w, u = pts[:n], pts[n:n + 1], pts[n + 1:n + 2]
     t0 = time.time()
-    prm = h2.Params("vesta", k, g, h2.lagrange_generators("vesta", k, g), w, u=u)
+    gl = h2.lagrange_generators("vesta", k, g)
+    prm = h2.Params("vesta", k, g, gl, w, u=u)
     D = h2.EvaluationDomain("fp", BC.DEGREE, k, zeta)
     fixed, sigma, adv = BC.columns(k, m, D.omega, delta, 2834758237 * zeta % m)
     to_b = PV._ints_to_bytes
@@ -486,12 +488,23 @@ def real_proof_ms(h2, cref, k=None, reps=3):
     finally:
         PP.close_proving_key(pk)
         prm.close()
+    threads = threads or (os.cpu_count() or 1)
+    cp = PP.CrefProver(cref, "vesta", "fp", g, gl, w, u, threads)
+    Tc = R.Blake2bTranscript(m)
+    t0 = time.time()
+    cp.create_proof(vk, fixed_b, sigma_b, [adv_b], [[]], MC.SeededRng("fp", SEED + 202 + reps - 1, True), Tc, zeta, delta)
+    cpu_wall = time.time() - t0
     return {"metric": "ms_per_real_proof", "value": dt * 1e3, "unit": "ms", "higher_is_better": False, "k": k, "proof_bytes": len(proof),
+            "transcript_identical": bool(bytes(Tc.proof) == proof),
+            "cpu_baseline": {"value": cp.hot_s * 1e3, "unit": "ms", "cores": threads, "kind": "port", "ms_by_kind": {k_: v * 1e3 for k_, v in cp.by_kind.items()},
+                             "wall_ms_incl_glue": cpu_wall * 1e3,
+                             "sample": "1 real proof on the C restatement: the hot-path calls only (11 commitments, 4 + 4 + 1 transforms, 13 + 4 eval_polynomial, "
+                                       "3 kate_division, the 14-round opening); expressions, products and folds are not counted"},
             "accepted_by_the_verifier": bool(accepted), "tampered_rejected": bool(rejected), "verify_ms": verify_ms, "setup_ms": setup_s * 1e3,
             "circuit": "benches/plonk.rs StandardPlonk: 3 advice columns, 1 permutation set, 4 fixed columns, 1 gate, degree 5, 2^k - 6 rows",
             "note": "a real proof (not the replay): plonk::create_proof composed from the engine's API (tests/plonk_prover.create_proof_engine), "
                     "verified through the engine by the pinned-key-driven verifier (tests/plonk_verifier.py).  Wall-clock per proof incl. the "
-                    "Python composition; no CPU arm (see the docstring)."}
+                    "Python composition; CPU arm: the same prover on the C restatement, hot-path calls only."}
 
 
 def quotient_pipeline_ms(h2, cref, threads, reps=5):
@@ -1095,7 +1108,7 @@ def main():
             extra["create_proof_k16_replay"] = guarded(prover_replay, h2, cref, threads, 2, 16)
             # a REAL proof of the reference's benchmark circuit through the engine's API, verified through the engine (after the replays,
             # whose timings it must not perturb)
-            extra["create_proof_k14_real"] = guarded(real_proof_ms, h2, cref)
+            extra["create_proof_k14_real"] = guarded(real_proof_ms, h2, cref, None, 3, threads)
 
         extra["msm_2p24_strong"] = c5
         line = {

@@ -560,3 +560,369 @@ def close_proving_key(pk) -> None:
     for key in ("fixed_l", "fixed_p", "fixed_c", "sigma_l", "sigma_p", "sigma_c", "l", "tmp"):
         for p in pk.pop(key, []):
             p.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The same prover on the C RESTATEMENT of the reference algorithms (oracle/halo2_oracle.c through oracle/cref.py): the timed
+# CPU arm for real proofs at benchmark sizes, where the big-integer version above would take minutes.  Same order, same
+# randomness, THE SAME PROOF BYTES (tests/test_real_proof.py).  `hot_s` accumulates only the reference's hot-path calls --
+# best_multiexp per commitment, the best_fft-based transforms, eval_polynomial, kate_division, the opening's round loop -- as
+# tests/prover_replay.CpuArm does; the elementwise work (expressions, products, folds: Python integers or the C evaluator)
+# is not counted.
+# ------------------------------------------------------------------------------------------------------------------------
+class CrefProver:
+    def __init__(self, cref, curve: str, field: str, g, g_lagrange, w, u, threads: int):
+        import numpy as np
+        self.np, self.cref, self.curve, self.field, self.threads = np, cref, curve, field, threads
+        self.bases = np.concatenate([g, w])
+        self.bases_l = np.concatenate([g_lagrange, w])
+        self.gwu = np.concatenate([g, w, u])
+        self.hot_s, self.by_kind = 0.0, {}
+
+    def _t(self, kind, t0):
+        import time
+        dt = time.time() - t0
+        self.hot_s += dt
+        self.by_kind[kind] = self.by_kind.get(kind, 0.0) + dt
+
+    def commit(self, poly, blind: int, lagrange: bool):
+        import time
+        t0 = time.time()
+        out = self.cref.best_multiexp(self.curve, self.np.concatenate([poly, self.cref.ints_to_bytes([blind])]),
+                                      self.bases_l if lagrange else self.bases, self.threads)
+        self._t("commit_lagrange" if lagrange else "commit", t0)
+        return out
+
+    def create_proof(self, vk: PV.PinnedKey, fixed, sigma, advice, instances, rng, transcript, zeta: int, delta: int) -> None:
+        """plonk::create_proof; columns as (n, 32) uint8 arrays or int lists; `transcript`: tests/prover_replay.Blake2bTranscript."""
+        import time
+        from halo2_b200.evaluator import Ast, AstLeaf, compile_ast           # the pure-host flattener of the Ast (no GPU involved)
+        np, cref, field = self.np, self.cref, self.field
+        m = vk.scalar_modulus
+        k, n = vk.k, 1 << vk.k
+        bf = vk.blinding_factors()
+        usable = n - (bf + 1)
+        cs_degree = vk.degree()
+        chunk_len = cs_degree - 2
+        D = pasta.EvaluationDomain(field, cs_degree, k, zeta)
+        L = D.extended_len()
+        stride = 1 << (D.extended_k - k)
+        B = lambda col: col if hasattr(col, "dtype") else cref.ints_to_bytes([v % m for v in col])
+        I = cref.bytes_to_ints
+
+        def timed(kind, fn, *a):
+            t0 = time.time()
+            out = fn(*a)
+            self._t(kind, t0)
+            return out
+
+        l2c = lambda v: timed("lagrange_to_coeff", cref.ifft, field, v, D.omega_inv, k, D.ifft_divisor, self.threads)
+        c2e = lambda p: timed("coeff_to_extended", cref.coeff_to_extended, field, p, k, D.extended_k, zeta, D.extended_omega, self.threads)
+        evalp = lambda p, x: timed("eval_polynomial", cref.eval_polynomial, field, p, x)
+
+        def run_ast(ast, polys, extended):                         # Evaluator::evaluate: the C evaluator, not counted as hot
+            log_n = D.extended_k if extended else k
+            code, consts = compile_ast(ast, m, stride if extended else 1)
+            return cref.ast_eval(field, np.stack(polys), log_n, code, consts, D.extended_omega if extended else D.omega, zeta if extended else 1, self.threads)
+
+        class Eng:                                                 # what _to_ast needs from an engine namespace
+            pass
+        Eng.Ast = Ast
+        num_proofs = len(advice)
+        transcript.common_scalar(vk.transcript_repr())
+        inst_l, inst_p, inst_c = [], [], []
+        for inst in instances:
+            vals = [B(list(col) + [0] * (n - len(col))) for col in inst]
+            for v in vals:
+                transcript.common_point(self.commit(v, 1, True))
+            polys = [l2c(v) for v in vals]
+            inst_l.append(vals), inst_p.append(polys), inst_c.append([c2e(p) for p in polys])
+        adv_l, adv_p, adv_c, adv_b = [], [], [], []
+        for cols in advice:
+            vals = []
+            for col in cols:
+                v = B(col).copy()
+                v[usable:] = cref.ints_to_bytes([rng.scalar() for _ in range(n - usable)])
+                vals.append(v)
+            blinds = [rng.scalar() for _ in vals]
+            for v, b in zip(vals, blinds):
+                transcript.write_point(self.commit(v, b, True))
+            polys = [l2c(v) for v in vals]
+            adv_l.append(vals), adv_p.append(polys), adv_c.append([c2e(p) for p in polys]), adv_b.append(blinds)
+        fixed_l = [B(f) for f in fixed]
+        fixed_p = [cref.ifft(field, f, D.omega_inv, k, D.ifft_divisor, self.threads) for f in fixed_l]       # the proving key's: not per proof
+        fixed_c = [cref.coeff_to_extended(field, p, k, D.extended_k, zeta, D.extended_omega, self.threads) for p in fixed_p]
+        sigma_l = [B(s) for s in sigma]
+        sigma_p = [cref.ifft(field, s, D.omega_inv, k, D.ifft_divisor, self.threads) for s in sigma_l]
+        sigma_c = [cref.coeff_to_extended(field, p, k, D.extended_k, zeta, D.extended_omega, self.threads) for p in sigma_p]
+        ind = lambda rows: cref.coeff_to_extended(field, cref.ifft(field, cref.ints_to_bytes([1 if r in rows else 0 for r in range(n)]), D.omega_inv, k,
+                                                                 D.ifft_divisor, self.threads), k, D.extended_k, zeta, D.extended_omega, self.threads)
+        l0_c, l_blind_c, l_last_c = ind({0}), ind(set(range(n - bf, n))), ind({n - bf - 1})
+        # leaf numbering of the Lagrange-basis programs: fixed, then per proof advice and instance
+        lag_polys = list(fixed_l)
+        FL = [AstLeaf(i) for i in range(len(fixed_l))]
+        AL, IL = [], []
+        for pr in range(num_proofs):
+            AL.append([AstLeaf(len(lag_polys) + i) for i in range(len(adv_l[pr]))])
+            lag_polys += adv_l[pr]
+            IL.append([AstLeaf(len(lag_polys) + i) for i in range(len(inst_l[pr]))])
+            lag_polys += inst_l[pr]
+        theta = transcript.squeeze_challenge()
+        lookups = []
+        for pr in range(num_proofs):
+            per = []
+            for inp, tab in vk.lookups:
+                def compress(exprs):
+                    acc = Ast.constant_term(0)
+                    for e in exprs:
+                        acc = acc * theta + _to_ast(Eng, e, FL, AL[pr], IL[pr])
+                    return run_ast(acc, lag_polys, False)
+                ci, ct = compress(inp), compress(tab)
+                res = cref.permute_expression_pair(ci, ct, usable)
+                assert res is not None, "an input value does not occur in the table"
+                pi = np.concatenate([res[0], cref.ints_to_bytes([rng.scalar() for _ in range(bf + 1)])])
+                pt = np.concatenate([res[1], cref.ints_to_bytes([rng.scalar() for _ in range(bf + 1)])])
+                bi = rng.scalar()
+                bt = rng.scalar()
+                transcript.write_point(self.commit(pi, bi, True))
+                transcript.write_point(self.commit(pt, bt, True))
+                per.append({"ci": ci, "ct": ct, "pi": pi, "pt": pt, "pi_poly": l2c(pi), "pt_poly": l2c(pt), "bi": bi, "bt": bt})
+            lookups.append(per)
+        beta = transcript.squeeze_challenge()
+        gamma = transcript.squeeze_challenge()
+        omega_pows = [1] * n
+        for i in range(1, n):
+            omega_pows[i] = omega_pows[i - 1] * D.omega % m
+        col_vals = lambda pr, col: {"Advice": adv_l[pr], "Fixed": fixed_l, "Instance": inst_l[pr]}[col[0]][col[1]]
+        perms = []
+        for pr in range(num_proofs):                               # permutation/prover.rs:42-173 on Python integers (elementwise: not counted)
+            sets, last_z = [], 1
+            for ci_ in range(0, len(vk.permutation_columns), chunk_len):
+                cols = vk.permutation_columns[ci_:ci_ + chunk_len]
+                mod = [1] * n
+                vals_i = [I(col_vals(pr, col)) for col in cols]
+                for v, sg in zip(vals_i, sigma_l[ci_:ci_ + chunk_len]):
+                    mod = [a * ((beta * s_ + gamma + x_) % m) % m for a, s_, x_ in zip(mod, I(sg), v)]
+                from halo2_b200.verifier import batch_invert         # pure host arithmetic (Montgomery's trick)
+                mod = batch_invert(mod, m)
+                for j, v in enumerate(vals_i):
+                    d_j = pow(delta, ci_ + j, m) * beta % m
+                    mod = [a * ((d_j * w_ + gamma + x_) % m) % m for a, w_, x_ in zip(mod, omega_pows, v)]
+                z = [last_z]
+                for row in range(1, n):
+                    z.append(z[row - 1] * mod[row - 1] % m)
+                for row in range(n - bf, n):
+                    z[row] = rng.scalar()
+                last_z = z[n - (bf + 1)]
+                blind = rng.scalar()
+                zb = cref.ints_to_bytes(z)
+                transcript.write_point(self.commit(zb, blind, True))
+                zp = l2c(zb)
+                sets.append({"poly": zp, "coset": c2e(zp), "blind": blind})
+            perms.append(sets)
+        for pr in range(num_proofs):
+            for lk in lookups[pr]:
+                from halo2_b200.verifier import batch_invert
+                pi_i, pt_i, ci_i, ct_i = I(lk["pi"]), I(lk["pt"]), I(lk["ci"]), I(lk["ct"])
+                prod = batch_invert([(beta + a) * (gamma + s_) % m for a, s_ in zip(pi_i, pt_i)], m)
+                prod = [p * ((a + beta) % m) % m * ((s_ + gamma) % m) % m for p, a, s_ in zip(prod, ci_i, ct_i)]
+                z, state = [], 1
+                for cur in [1] + prod:
+                    state = state * cur % m
+                    z.append(state)
+                z = z[:n - bf] + [rng.scalar() for _ in range(bf)]
+                lk["zb"] = rng.scalar()
+                zbytes = cref.ints_to_bytes(z)
+                transcript.write_point(self.commit(zbytes, lk["zb"], True))
+                lk["z_poly"] = l2c(zbytes)
+        random_poly = B(rng.poly(n))
+        random_blind = rng.scalar()
+        transcript.write_point(self.commit(random_poly, random_blind, False))
+        y = transcript.squeeze_challenge()
+        # ---- h(X): the same Ast as the engine version, evaluated by the C evaluator over the extended cosets ----
+        ext_polys = list(fixed_c) + list(sigma_c) + [l0_c, l_blind_c, l_last_c]
+        FC = [AstLeaf(i) for i in range(len(fixed_c))]
+        SC = [AstLeaf(len(fixed_c) + i) for i in range(len(sigma_c))]
+        L0, LB, LL = (AstLeaf(len(fixed_c) + len(sigma_c) + i) for i in range(3))
+
+        def reg(p):
+            ext_polys.append(p)
+            return AstLeaf(len(ext_polys) - 1)
+
+        one = Ast.constant_term(1)
+        active = one - (LL + LB)
+        last_rot = -(bf + 1)
+        exprs = []
+        for pr in range(num_proofs):
+            AC = [reg(p) for p in adv_c[pr]]
+            IC = [reg(p) for p in inst_c[pr]]
+            exprs += [_to_ast(Eng, gate, FC, AC, IC) for gate in vk.gates]
+            ZC = [reg(s_["coset"]) for s_ in perms[pr]]
+            if ZC:
+                exprs.append((one - ZC[0]) * L0)
+                exprs.append((ZC[-1] * ZC[-1] - ZC[-1]) * LL)
+                for a in range(1, len(ZC)):
+                    exprs.append((ZC[a] - ZC[a - 1].with_rotation(last_rot)) * L0)
+                colc = lambda col: {"Advice": AC, "Fixed": FC, "Instance": IC}[col[0]][col[1]]
+                for a in range(len(ZC)):
+                    cols = vk.permutation_columns[a * chunk_len:(a + 1) * chunk_len]
+                    left = ZC[a].with_rotation(1)
+                    for col, sc in zip(cols, SC[a * chunk_len:(a + 1) * chunk_len]):
+                        left = left * (colc(col) + sc * beta + Ast.constant_term(gamma))
+                    right = ZC[a]
+                    for j, col in enumerate(cols):
+                        right = right * (colc(col) + Ast.linear_term(beta * pow(delta, a * chunk_len + j, m) % m) + Ast.constant_term(gamma))
+                    exprs.append((left - right) * active)
+            for lk in lookups[pr]:
+                Z_, A_, S_ = (reg(c2e(lk[kk])) for kk in ("z_poly", "pi_poly", "pt_poly"))
+                CI_, CT_ = (reg(c2e(l2c(lk[kk]))) for kk in ("ci", "ct"))
+                exprs.append((one - Z_) * L0)
+                exprs.append((Z_ * Z_ - Z_) * LL)
+                left = Z_.with_rotation(1) * (A_ + Ast.constant_term(beta)) * (S_ + Ast.constant_term(gamma))
+                right = Z_ * (CI_ + Ast.constant_term(beta)) * (CT_ + Ast.constant_term(gamma))
+                exprs.append((left - right) * active)
+                exprs.append((A_ - S_) * L0)
+                exprs.append((A_ - S_) * (A_ - A_.with_rotation(-1)) * active)
+        h_ext = run_ast(Ast.distribute_powers(exprs, y), ext_polys, True)
+        tev = cref.ints_to_bytes(D.t_evaluations)                  # divide_by_vanishing_poly (domain.rs:329-348) as an elementwise program
+        tfull = tev[np.arange(L) % len(D.t_evaluations)]
+        h_ext = cref.ast_eval(field, np.stack([h_ext, tfull]), D.extended_k, np.array([[0, 0, 0, 0], [0, 1, 0, 0], [4, 0, 0, 0]], dtype=np.uint32), [],
+                              D.extended_omega, zeta, self.threads)
+        h = timed("extended_to_coeff", cref.extended_to_coeff, field, h_ext, D.extended_k, D.extended_omega_inv, D.extended_ifft_divisor, zeta,
+                  n * (cs_degree - 1), self.threads)
+        h_pieces = [h[a * n:(a + 1) * n] for a in range(cs_degree - 1)]
+        h_blinds = [rng.scalar() for _ in h_pieces]
+        for piece, b in zip(h_pieces, h_blinds):
+            transcript.write_point(self.commit(piece, b, False))
+        x = transcript.squeeze_challenge()
+        xn = pow(x, n, m)
+        rotx = lambda r: D.rotate_omega(x, r)
+        for pr in range(num_proofs):
+            for col, r in vk.instance_queries:
+                transcript.write_scalar(evalp(inst_p[pr][col], rotx(r)))
+        for pr in range(num_proofs):
+            for col, r in vk.advice_queries:
+                transcript.write_scalar(evalp(adv_p[pr][col], rotx(r)))
+        for col, r in vk.fixed_queries:
+            transcript.write_scalar(evalp(fixed_p[col], rotx(r)))
+        transcript.write_scalar(evalp(random_poly, x))
+        for sp in sigma_p:
+            transcript.write_scalar(evalp(sp, x))
+        for pr in range(num_proofs):
+            sets = perms[pr]
+            for a, st in enumerate(sets):
+                transcript.write_scalar(evalp(st["poly"], x))
+                transcript.write_scalar(evalp(st["poly"], rotx(1)))
+                if a + 1 < len(sets):
+                    transcript.write_scalar(evalp(st["poly"], rotx(last_rot)))
+        for pr in range(num_proofs):
+            for lk in lookups[pr]:
+                for poly, r in ((lk["z_poly"], 0), (lk["z_poly"], 1), (lk["pi_poly"], 0), (lk["pi_poly"], -1), (lk["pt_poly"], 0)):
+                    transcript.write_scalar(evalp(poly, rotx(r)))
+        h_poly, h_blind = [0] * n, 0                               # fold of the pieces by x^n: elementwise, Python integers
+        for piece, b in zip(reversed(h_pieces), reversed(h_blinds)):
+            h_poly = [(a * xn + p) % m for a, p in zip(h_poly, I(piece))]
+            h_blind = (h_blind * xn + b) % m
+        queries = []                                               # (point, key, polynomial bytes, blind)
+        for pr in range(num_proofs):
+            queries += [(rotx(r), ("i", pr, col), inst_p[pr][col], 1) for col, r in vk.instance_queries]
+            queries += [(rotx(r), ("a", pr, col), adv_p[pr][col], adv_b[pr][col]) for col, r in vk.advice_queries]
+            sets = perms[pr]
+            for a, st in enumerate(sets):
+                queries += [(x, ("z", pr, a), st["poly"], st["blind"]), (rotx(1), ("z", pr, a), st["poly"], st["blind"])]
+            for a in reversed(range(len(sets) - 1)):
+                queries.append((rotx(last_rot), ("z", pr, a), sets[a]["poly"], sets[a]["blind"]))
+            for li, lk in enumerate(lookups[pr]):
+                queries += [(x, ("lz", pr, li), lk["z_poly"], lk["zb"]), (x, ("li", pr, li), lk["pi_poly"], lk["bi"]), (x, ("lt", pr, li), lk["pt_poly"], lk["bt"]),
+                            (rotx(-1), ("li", pr, li), lk["pi_poly"], lk["bi"]), (rotx(1), ("lz", pr, li), lk["z_poly"], lk["zb"])]
+        queries += [(rotx(r), ("f", col), fixed_p[col], 1) for col, r in vk.fixed_queries]
+        queries += [(x, ("s", i), sp, 1) for i, sp in enumerate(sigma_p)]
+        queries.append((x, ("h",), cref.ints_to_bytes(h_poly), h_blind))
+        queries.append((x, ("r",), random_poly, random_blind))
+        self._multiopen(vk, rng, transcript, queries, m, k)
+
+    def _multiopen(self, vk, rng, transcript, queries, m, k):
+        """poly/multiopen/prover.rs:18-124 + poly/commitment/prover.rs:36-151: the folds on Python integers (elementwise, not counted), the
+        divisions / evaluations / commitments / round loop on the C restatement."""
+        import time
+        np, cref, field = self.np, self.cref, self.field
+        n = 1 << k
+        I = cref.bytes_to_ints
+
+        class Q:                                                   # pasta.construct_intermediate_sets wants objects with these members
+            def __init__(self, point, key, poly, blind):
+                self.point, self._k, self.poly, self.blind = point, key, poly, blind
+
+            def key(self):
+                return self._k
+
+            def value(self):
+                return (self.poly, self.blind)
+
+        x1 = transcript.squeeze_challenge()
+        x2 = transcript.squeeze_challenge()
+        poly_map, point_sets = pasta.construct_intermediate_sets([Q(*q) for q in queries], prover=True)
+        q_polys, q_blinds = [None] * len(point_sets), [0] * len(point_sets)
+        for data in poly_map:
+            s_ = data["set_index"]
+            poly = I(data["commitment"])
+            q_polys[s_] = poly if q_polys[s_] is None else [(a * x1 + b) % m for a, b in zip(q_polys[s_], poly)]
+            q_blinds[s_] = (q_blinds[s_] * x1 + data["blind"]) % m
+        q_prime = None
+        for points, poly in zip(point_sets, q_polys):
+            cur = cref.ints_to_bytes(poly)
+            for pt in points:
+                t0 = time.time()
+                quo = cref.kate_division(field, cur, pt)
+                self._t("kate_division", t0)
+                cur = np.concatenate([quo, np.zeros((n - quo.shape[0], 32), dtype=np.uint8)])
+            cur = I(cur)
+            q_prime = cur if q_prime is None else [(a * x2 + b) % m for a, b in zip(q_prime, cur)]
+        q_prime_blind = rng.scalar()
+        transcript.write_point(self.commit(cref.ints_to_bytes(q_prime), q_prime_blind, False))
+        x3 = transcript.squeeze_challenge()
+        for q in q_polys:
+            t0 = time.time()
+            e = cref.eval_polynomial(field, cref.ints_to_bytes(q), x3)
+            self._t("eval_polynomial", t0)
+            transcript.write_scalar(e)
+        x4 = transcript.squeeze_challenge()
+        p_poly, p_blind = q_prime, q_prime_blind
+        for poly, blind in zip(q_polys, q_blinds):
+            p_poly = [(a * x4 + b) % m for a, b in zip(p_poly, poly)]
+            p_blind = (p_blind * x4 + blind) % m
+        # commitment::create_proof (poly/commitment/prover.rs:36-151)
+        drawn = rng.poly(n)
+        s = I(drawn) if hasattr(drawn, "dtype") else [v % m for v in drawn]
+        sb = cref.ints_to_bytes(s)
+        t0 = time.time()
+        s_at = cref.eval_polynomial(field, sb, x3)
+        self._t("eval_polynomial", t0)
+        s[0] = (s[0] - s_at) % m
+        s_blind = rng.scalar()
+        transcript.write_point(self.commit(cref.ints_to_bytes(s), s_blind, False))
+        xi = transcript.squeeze_challenge()
+        z = transcript.squeeze_challenge()
+        pp = [(a * xi + b) % m for a, b in zip(s, p_poly)]
+        t0 = time.time()
+        v = cref.eval_polynomial(field, cref.ints_to_bytes(pp), x3)
+        self._t("eval_polynomial", t0)
+        pp[0] = (pp[0] - v) % m
+        f = (s_blind * xi + p_blind) % m
+        rand = [(rng.scalar(), rng.scalar()) for _ in range(k)]
+        us = []
+
+        def challenge(j, l_xy, r_xy):
+            transcript.write_point(l_xy)
+            transcript.write_point(r_xy)
+            us.append(transcript.squeeze_challenge())
+            return us[-1]
+
+        t0 = time.time()
+        _, _, c_val = cref.ipa_rounds_transcript(self.curve, self.gwu, k, cref.ints_to_bytes(pp), x3, z, challenge,
+                                                 cref.ints_to_bytes([a for a, _ in rand]), cref.ints_to_bytes([b for _, b in rand]), min(self.threads, 16))
+        self._t("ipa", t0)
+        for (lr, rr), uj in zip(rand, us):
+            f = (f + lr * pow(uj, -1, m) + rr * uj) % m
+        transcript.write_scalar(c_val)
+        transcript.write_scalar(f)

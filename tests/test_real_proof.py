@@ -166,6 +166,24 @@ def test_benchmark_circuit_real_proof(k):
             assert PV.verify_proof(earm, vk, got, [[]], DELTA)
             earm.close()
         assert pk and all(p._h.value for p in pk["fixed_c"])           # the key's polynomials stayed resident between the proofs
+        # the timed CPU arm of bench.py's extra.create_proof_k14_real: the same prover on the C restatement, the same bytes
+        cp = PP.CrefProver(cref, "vesta", "fp", *gens, threads=4)
+        T = R.Blake2bTranscript(M)
+        cp.create_proof(vk, fixed, sigma, [adv_bytes], [[]], MC.SeededRng("fp", 5, True), T, ZETA, DELTA)
+        assert bytes(T.proof) == want and cp.hot_s > 0 and set(cp.by_kind) >= {"commit", "commit_lagrange", "ipa", "kate_division"}
         PP.close_proving_key(pk)
         assert not fake.polys
         prm.close()
+
+
+def test_cref_prover_matches_the_oracle_on_the_reference_circuit(setup):
+    """PP.CrefProver (the C restatement's hot calls under the same control flow: the timed CPU arm for real proofs) on the
+    plonk_api circuit -- lookup, instance column, six permutation sets, two instances: the oracle prover's 4 160 bytes."""
+    from tests import prover_replay as R
+    c, P, vk, fixed, sigma, gens = setup
+    inst = [[[2]], [[2]]]
+    want = prove(setup, [witness(), witness()], inst, 777)
+    cp = PP.CrefProver(cref, "vesta", "fp", *gens, threads=4)
+    T = R.Blake2bTranscript(M)
+    cp.create_proof(vk, fixed, sigma, [witness(), witness()], inst, MC.SeededRng("fp", 777, True), T, ZETA, DELTA)
+    assert bytes(T.proof) == want
