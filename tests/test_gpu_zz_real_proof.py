@@ -54,3 +54,45 @@ def test_real_proof_on_the_device():
         assert not PV.verify_proof(PV.OracleArm("vesta", 5, *gens), vk, bytes(T2.proof), [[[2]]], TR.DELTA)
     finally:
         prm.close()
+
+
+def test_benchmark_circuit_real_proof_on_the_device():
+    """The reference's benchmark circuit (benches/plonk.rs, tests/bench_circuit.py) at k = 8: key generated on the device, a real proof
+    through the engine-API prover with the proving key's polynomials resident between two proofs, THE SAME BYTES as the same prover
+    on the C restatement (tests/plonk_prover.CrefProver), accepted by the engine's verifier -- the workload of bench.py's
+    extra.create_proof_k14_real."""
+    import halo2_b200 as h2
+    from halo2_b200 import lib as L
+    from tests import bench_circuit as BC
+    L.init()
+    k = 8
+    n = 1 << k
+    m = TR.M
+    pts = cref.gen_points("vesta", 99, n + 2)
+    g, w, u = pts[:n], pts[n:n + 1], pts[n + 1:n + 2]
+    gl = h2.lagrange_generators("vesta", k, g)
+    prm = h2.Params("vesta", k, g, gl, w, u=u)
+    pk = {}
+    try:
+        D = h2.EvaluationDomain("fp", BC.DEGREE, k, TR.ZETA)
+        fixed, sigma, adv = BC.columns(k, m, D.omega, TR.DELTA, circ.A_SMALL * TR.ZETA % m)
+        fb, sb, ab = ([cref.ints_to_bytes(c_) for c_ in cols] for cols in (fixed, sigma, adv))
+        xy = lambda col: cref.bytes_to_affine(h2.batch_normalize(prm.commit_lagrange(col, h2.Blind(1)).reshape(1, 96), "vesta")[0])
+        vk = PV.PinnedKey(BC.pinned_key_text(k, D.extended_k, pasta.Q_MOD, m, D.omega, [xy(c_) for c_ in fb], [xy(c_) for c_ in sb]))
+        proofs = []
+        for seed in (5, 6):
+            T = R.Blake2bTranscript(m)
+            PP.create_proof_engine(h2, prm, vk, fb, sb, [ab], [[]], MC.SeededRng("fp", seed, True), T, TR.ZETA, TR.DELTA, pk=pk)
+            proofs.append(bytes(T.proof))
+        cp = PP.CrefProver(cref, "vesta", "fp", g, gl, w, u, 8)
+        Tc = R.Blake2bTranscript(m)
+        cp.create_proof(vk, fb, sb, [ab], [[]], MC.SeededRng("fp", 6, True), Tc, TR.ZETA, TR.DELTA)
+        assert proofs[1] == bytes(Tc.proof) and proofs[0] != proofs[1]
+        arm = PV.EngineArm(h2, "vesta", k, params=prm)
+        assert PV.verify_proof(arm, vk, proofs[0], [[]], TR.DELTA) and PV.verify_proof(arm, vk, proofs[1], [[]], TR.DELTA)
+        bad = bytearray(proofs[1])
+        bad[len(bad) // 3] ^= 8
+        assert not PV.verify_proof(arm, vk, bytes(bad), [[]], TR.DELTA)
+    finally:
+        PP.close_proving_key(pk)
+        prm.close()
